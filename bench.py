@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- train windows/sec of the sliding-window error classifier (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): window 16 / stride 4 over a synthetic
+per-frame table (2048-d image stream + 26-d kinematics), FeatureExtractor 2048-512-256-32 + 3-layer
+LSTM(128) head, BCE loss, Adam; B = 8192 windows per GPU per step (weak scaling).  A "step" is one full
+train step: K1 gather/standardise -> K2 FE forward -> head -> K3 loss/metrics -> backward -> gradient
+all-reduce -> fused Adam.  `value` times K steps on the device (CUDA events, barrier + synchronize on
+both sides, max over ranks) with the step's window indices already resident in HBM; `e2e` runs the
+public ``train_single_epoch`` over the same number of steps with pinned-host index batches copied in
+and the loss read back every step.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+W, S = 16, 4
+IMAGE_DIM, KIN_DIM = 2048, 26
+METRIC, UNIT = "train_windows_per_sec", "windows/s"
+
+
+def exp_kwargs(batch, precision):
+    return dict(dataset_type="window", error_type="global", pos_weight=True, n_epochs=15, batch_size=batch, lr=1e-3,
+                lr_scheduler=True, weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32, data_type="multimodal",
+                delete_ND=True, return_train_preds=False, siamese=False, model_name="SimpleLSTM", precision=precision)
+
+
+def workload_name(batch, videos):
+    return (f"train_window T: W={W} S={S} streams[{IMAGE_DIM},{KIN_DIM}] FE(2048-512-256-32)+LSTM(58,{W},3,128,1) "
+            f"BCE+Adam, B={batch}/GPU, table {videos} videos/GPU U[300,900] frames")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p.get("hbm_gbs", 6650.0), p.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ======================================================================================== CPU arms
+def oracle_dataset(n_windows, seed):
+    """A bounded sample of the workload for the CPU arm, in the reference's representation:
+    MATERIALISED windows [n, W, 2048] on the host (dataset_utils.py:243-244)."""
+    from multimodal_error_detection_b200 import synthetic
+    from oracle import loops, window_index as O
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_videos = n_windows // 60 + 4
+    g, e5, offsets = synthetic.label_tracks(seed, n_videos, 300, 900)
+    N = len(g)
+    image = np.maximum(rng.standard_normal((N, IMAGE_DIM), dtype=np.float32), 0)
+    kin = rng.standard_normal((N, KIN_DIM), dtype=np.float32)
+    names = np.repeat(np.arange(n_videos), np.diff(offsets))
+    t0 = time.perf_counter()
+    rows, subj = O.window_starts(g, names, W, S)
+    rows = rows[:n_windows]
+    build_s = time.perf_counter() - t0
+    e7, _ = O.powerset_error_labels(e5[rows[:, 0]], True)
+    stats = {"image": {"mean": torch.from_numpy(image.mean(0)), "std": torch.from_numpy(image.std(0) + 1e-3)},
+             "kinematics": {"mean": torch.from_numpy(kin.mean(0)), "std": torch.from_numpy(kin.std(0) + 1e-3)}}
+    ds = loops.OracleWindowDataset(torch.from_numpy(image[rows]), torch.from_numpy(kin[rows]),
+                                   torch.from_numpy(g[rows[:, 0]].reshape(-1, 1)), torch.from_numpy(e7), subj[:len(rows)], stats)
+    return ds, build_s
+
+
+def cpu_train_windows_per_sec(n_windows, batch, steps=None, warmup=0):
+    """The reference's train_single_epoch cost structure (oracle port) on the host cores:
+    windows/s = windows processed / wall time, data loading and sklearn metrics included."""
+    from oracle import loops, nets
+    kw = exp_kwargs(batch, "fp32")
+    ds, build_s = oracle_dataset(n_windows, seed=7)
+    fe, model, crit, opt, sched = nets.build_objects(kw, {"multimodal": 58, "video": 32, "kinematics": 26},
+                                                     ds.binary_error_distribution, W)
+    loader, _ = loops.make_loaders(ds, ds, batch)
+    if warmup:
+        it = iter(loader)
+        model.train(); fe.train()
+        for _ in range(min(warmup, len(loader))):
+            images, kin, g, e7, subj = next(it)
+            out = model(loops.fuse_inputs(images, kin, fe, kw))
+            loss, _ = loops.loss_fn(out, loops.select_labels(e7, kw).float(), crit, "window")
+            opt.zero_grad(); loss.backward(); opt.step()
+    t0 = time.perf_counter()
+    loops.train_epoch(model, fe, loader, crit, opt, None, kw)
+    dt = time.perf_counter() - t0
+    return len(ds) / dt, dt, len(ds), build_s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    batch = 512
+    n = batch * max(1, args.steps)
+    wps, dt, n_done, build_s = cpu_train_windows_per_sec(n, batch, warmup=args.warmup)
+    line = {"metric": METRIC, "value": wps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(args.batch, args.videos),
+                       "note": "reference CPU path (oracle port of train_single_epoch, torch CPU fp32 + sklearn); each step "
+                               "is a bounded sample of 512 windows of the same workload"},
+            "cpu_baseline": {"value": wps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n_done} windows, B={batch}, {args.steps} steps, window build {build_s:.2f}s excluded"},
+            "e2e": {"value": wps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ======================================================================================== GPU arm
+def build_gpu_job(args, rank, device):
+    from multimodal_error_detection_b200 import synthetic
+    from multimodal_error_detection_b200.dataset.CustomWindowDataset import CustomWindowDataset
+    from multimodal_error_detection_b200.dataset.dataset_utils import dataset_from_index
+    from multimodal_error_detection_b200.table import FrameTable
+    g, e5, offsets = synthetic.label_tracks(1000 + rank, args.videos, 300, 900)
+    N = len(g)
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    image = torch.empty(N, IMAGE_DIM, device=device)
+    for lo in range(0, N, 1 << 16):                       # chunked: no 2x transient of the 10 GB table
+        image[lo:lo + (1 << 16)] = torch.randn(min(1 << 16, N - lo), IMAGE_DIM, device=device, generator=gen).clamp_min_(0)
+    kin = torch.randn(N, KIN_DIM, device=device, generator=gen)
+    names = np.repeat(np.arange(args.videos), np.diff(offsets))
+    table = FrameTable(image, kin, torch.from_numpy(g), torch.from_numpy(e5), names, device=device)
+    index = table.window_index(W, S)
+    stats = {"image": {"mean": image[: 1 << 16].mean(0).cpu(), "std": (image[: 1 << 16].std(0) + 1e-3).cpu()},
+             "kinematics": {"mean": kin.mean(0).cpu(), "std": (kin.std(0) + 1e-3).cpu()}}
+    ds = dataset_from_index(index, True, stats)
+    return ds, N
+
+
+def run_gpu(args):
+    from multimodal_error_detection_b200 import _lib, ops, parallel
+    from multimodal_error_detection_b200.dataset.CustomWindowDataset import DeviceWindowLoader
+    from multimodal_error_detection_b200.engine import WindowTrainStep
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200med path has no CPU fallback (use --impl reference for the CPU arm)")
+    rank, local_rank, world = parallel.init_from_env()
+    device = torch.device("cuda", local_rank)
+    B, K, Wm = args.batch, args.steps, max(3, args.warmup)
+    kw = exp_kwargs(B, args.precision)
+    ds, n_frames = build_gpu_job(args, rank, device)
+    n_windows = len(ds)
+    fe, model, crit, opt, sched = mu.define_model_objects(kw, {"multimodal": 58, "video": 32, "kinematics": 26}, device,
+                                                          ds.binary_error_distribution, W)
+    n_params = opt.n_params
+
+    # ---- device-timed steps: the K + warmup batches of window indices are staged in HBM beforehand
+    gen = torch.Generator().manual_seed(42)
+    perm = torch.randperm(n_windows, generator=gen)
+    need = (K + Wm) * B
+    perm = perm.repeat((need + n_windows - 1) // n_windows)[:need].reshape(K + Wm, B)
+    starts_all = ds._starts[perm.to(device)].contiguous()                 # [K+Wm, B] int32, resident
+    labels_all = ds.e_labels_data[:, -1].float()[perm.to(device)].contiguous()
+    stepper = WindowTrainStep(ds, fe, model, crit, opt, kw, B, gather_variant=args.gather_variant)
+    graph_note = "eager"
+    if args.graph:
+        try:
+            stepper.load(starts_all[0], labels_all[0])
+            stepper.capture()
+            graph_note = "cuda_graph"
+        except Exception as e:  # capture is an optimisation, never a correctness dependency
+            stepper.graph = None
+            graph_note = f"eager (graph capture failed: {type(e).__name__})"
+    for i in range(Wm):
+        stepper.load(starts_all[i], labels_all[i])
+        stepper.run()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    gather_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(K):
+        stepper.load(starts_all[Wm + i], labels_all[Wm + i])
+        if stepper.graph is None:
+            stepper.gather_events = gather_ev[i]
+        stepper.run()
+    ev[1].record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    step_ms = parallel.max_over_ranks(ev[0].elapsed_time(ev[1]) / K, device)
+    stepper.gather_events = None
+    launches = (_lib.launch_count() - launches0) if stepper.graph is None else None
+    clocks = sampler.stop() if sampler else None
+    final_loss = float(stepper.loss.item())
+    value = world * B / (step_ms * 1e-3)
+
+    # ---- roofline of the dominant HBM kernel (K1), timed with CUDA events on the launch stream
+    out_es = 2 if args.precision == "bf16" else 4
+    k1_bytes = B * W * (IMAGE_DIM * (4 + out_es) + KIN_DIM * 8)
+    if stepper.graph is None:
+        k1_ms = statistics.mean(a.elapsed_time(b) for a, b in gather_ev)
+        k1_how = "CUDA events around the K1 launch inside each of the K timed steps"
+    else:
+        k1_ms = None
+    iso = []
+    for i in range(min(K, 10) + 3):      # isolated launches; every launch touches a fresh 1.1 GB slice (> L2)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stepper.starts.copy_(starts_all[i % (K + Wm)])
+        a.record()
+        ds.gather_batch(None, image_out=stepper.images, kin_out=stepper.kin, starts=stepper.starts,
+                        exact=args.precision != "bf16", variant=args.gather_variant)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            iso.append(a.elapsed_time(b))
+    k1_iso_ms = statistics.mean(iso)
+    if k1_ms is None:
+        k1_ms, k1_how = k1_iso_ms, "CUDA events around isolated K1 launches (the step itself is a replayed CUDA graph)"
+    hbm_peak, tf_peak, peak_src = measured_peaks()
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+    roofline = {"kernel": "gather_norm_kernel (K1: window gather + standardise + concat)", "bound": "hbm",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms, "ms_per_launch_isolated": k1_iso_ms,
+                "share_of_step": k1_ms / step_ms, "how": k1_how, "peak_source": peak_src}
+
+    # ---- tensor-pipe evidence for K2: FE layer-1 forward GEMM alone
+    gemm = None
+    if args.precision == "bf16" and ops.has_tcgen05():
+        M = B * W
+        x = stepper.images.reshape(M, IMAGE_DIM)
+        w1 = ops.to_bf16(fe.linear.linear_0.weight.detach().contiguous())
+        ts = []
+        for i in range(8):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.gemm_bf16(x, w1, M, 512, IMAGE_DIM, True, True, bias=fe.linear.linear_0.bias, relu=True)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        tf = 2.0 * M * 512 * IMAGE_DIM / (statistics.mean(ts) * 1e-3) / 1e12
+        gemm = {"kernel": "gemm_bf16_tcgen05_kernel<256> (K2: FE layer-1 forward, M=B*W, N=512, K=2048)", "bound": "tensor",
+                "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "ms_per_launch": statistics.mean(ts)}
+
+    # ---- e2e: the public train_single_epoch over K steps; pinned-host index batches in, loss out EVERY step
+    e2e = None
+    if not args.no_e2e:
+        kw_e2e = dict(kw, host_sync="step")
+        loader = DeviceWindowLoader(ds, B, shuffle=True, generator=torch.Generator().manual_seed(42), rank=0, world_size=1)
+        steps_e2e = min(K, len(loader))
+        loader.max_batches = steps_e2e
+        torch.cuda.synchronize(); parallel.barrier()
+        t0 = time.perf_counter()
+        res = mu.train_single_epoch(model, fe, loader, crit, opt, None, device, kw_e2e)
+        torch.cuda.synchronize()
+        dt = parallel.max_over_ranks(time.perf_counter() - t0, device)
+        e2e = {"value": world * steps_e2e * B / dt, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": 4,
+               "steps": steps_e2e, "api": "modeling_utils.train_single_epoch(DeviceWindowLoader)", "loss": res[0],
+               "table_upload_bytes_once": int(n_frames * (IMAGE_DIM + KIN_DIM + 6) * 4)}
+
+    if rank == 0:
+        cpu = None
+        if True:
+            try:
+                wps, dt, n_done, build_s = cpu_train_windows_per_sec(args.cpu_windows, 512)
+                cpu = {"value": wps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                       "sample": f"{n_done} windows (W={W}) of the same workload, B=512, one oracle train_epoch = {dt:.1f}s "
+                                 f"(host window build {build_s:.2f}s for the sample not included)"}
+            except Exception as e:
+                cpu = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {e}"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": step_ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": workload_name(B, args.videos), "global_batch": world * B, "window": W, "stride": S,
+                           "frames_per_gpu": n_frames, "windows_per_gpu": n_windows, "params": n_params,
+                           "parallelism": f"dp{world}", "launch": graph_note,
+                           "l2": "every step gathers a fresh ~1.1 GB slice of a >2 GB table (inputs larger than the 126 MB L2)",
+                           "gather_variant": args.gather_variant},
+                "roofline": roofline, "roofline_gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks, "final_loss": final_loss}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--videos", type=int, default=1024)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--gather-variant", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-windows", type=int, default=4096)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

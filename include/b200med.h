@@ -1,0 +1,235 @@
+/* b200med.h -- C ABI of libb200med.so: B200 (sm_100a) kernels for the train / inference hot path
+ * of GonzaloPlaaza/Multimodal-Error-Detection (frame-level and sliding-window error classifiers).
+ *
+ * The reference is pure Python and has NO plugin / operator / FFI interface:
+ * its boundary is the set of Python call signatures its notebooks use.  This header is therefore
+ * the boundary a maintainer binds with ctypes; each entry point names the
+ * reference routine (file:line under MED/) whose work it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - Every pointer is a DEVICE pointer unless its name ends in _host.  The caller allocates all
+ *     inputs, outputs and workspaces; the library owns no memory.
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and re-entrant.
+ *   - Return value: 0 on success, negative on error (B200MED_E_*); b200med_last_error() returns a
+ *     thread-local message.  There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with B200MED_E_CUDA.
+ *   - Row-major everywhere.  "window b, step t" is row m = b*W + t of a [B*W, D] matrix.
+ */
+#ifndef B200MED_H
+#define B200MED_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MED_VERSION 100
+
+#define B200MED_OK 0
+#define B200MED_E_ARG (-1)       /* invalid argument (shape, alignment, null pointer) */
+#define B200MED_E_CUDA (-2)      /* CUDA runtime / driver error; see b200med_last_error() */
+#define B200MED_E_UNSUPPORTED (-3)
+
+#define B200MED_F32 0
+#define B200MED_BF16 1
+
+int b200med_version(void);
+const char *b200med_last_error(void);
+/* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+int64_t b200med_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K0  Window index + label transforms (integer work, bit-exact bar)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Count the windows of every subject and exclusive-scan the counts.
+ * Replaces the per-subject `while` walk of window_data (MED/dataset/dataset_utils.py:206-240):
+ * start at the first frame with gesture != 0, loop while start < n - W, compare the two end-point
+ * gestures, advance by 1 on mismatch and by S on a match.
+ *   g            [N]  f32 gesture id per frame (subjects contiguous)
+ *   subj_offsets [n_subjects+1] i64 first row of each subject, last = N
+ *   win_offsets  [n_subjects+1] i64 OUT exclusive scan of window counts, last = total windows
+ *   status       [1] i32 OUT -1 if fine, else the first subject index with no non-zero gesture
+ *                (the reference raises IndexError there, dataset_utils.py:211-212)            */
+int b200med_window_count(const float *g, const int64_t *subj_offsets, int64_t n_subjects, int32_t W,
+                         int32_t S, int64_t *win_offsets, int32_t *status, void *stream);
+
+/* Emit the global start row of every window (subject order, then time order) and, optionally,
+ * the labels of its FIRST frame (dataset_utils.py:232-233).
+ *   starts [total] i32 OUT; g_win [total] f32 OUT or NULL; e5 [N,5] f32 or NULL; e5_win [total,5] OUT or NULL;
+ *   subj_win [total] i32 OUT or NULL (subject index of each window).                            */
+int b200med_window_fill(const float *g, const int64_t *subj_offsets, const int64_t *win_offsets,
+                        int64_t n_subjects, int32_t W, int32_t S, const float *e5, int32_t *starts,
+                        float *g_win, float *e5_win, int32_t *subj_win, void *stream);
+
+/* 5-column error labels (OOV, ND, MA, NP, Error) -> 7-column powerset labels + Needle-Drop mask.
+ * Replaces powerset_error_labels (MED/dataset/dataset_utils.py:760-845 and its duplicate
+ * MED/dataset/CustomFrameDataset.py:162-247).  e7 [n,7] i32 OUT, nd_mask [n] u8 OUT.            */
+int b200med_powerset(const float *e5, int64_t n, int32_t delete_nd, int32_t *e7, uint8_t *nd_mask,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  Fused window gather + per-stream standardise + concat (HBM-bound)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One modality stream of the device-resident per-frame table. */
+typedef struct b200med_stream_desc {
+    const void *table;   /* [N, dim] row-major per-frame features                                   */
+    const float *mean;   /* [stat_rows, dim] or NULL (stream is copied un-standardised)             */
+    const float *stdv;   /* [stat_rows, dim] or NULL                                                */
+    void *out;           /* [B*W, out_ld] destination matrix (may be shared by streams = concat)    */
+    int32_t dim;         /* feature width                                                           */
+    int32_t table_dtype; /* B200MED_F32 | B200MED_BF16                                              */
+    int32_t out_dtype;   /* B200MED_F32 | B200MED_BF16                                              */
+    int32_t out_ld;      /* elements between consecutive output rows                                */
+    int32_t out_col;     /* first output column of this stream (concat offset)                      */
+    int32_t stat_rows;   /* 1: statistics broadcast over time; W: one statistics row per step       */
+    int32_t exact_div;   /* 1: (x-mean)/std with IEEE division (bit-exact vs the reference);
+                            0: (x-mean)*(1/std)                                                     */
+    int32_t reserved;
+} b200med_stream_desc;
+
+#define B200MED_MAX_STREAMS 8
+
+/* out_s[b*W+t, out_col_s + d] = (table_s[starts[b]+t, d] - mean_s[d]) / std_s[d] for every stream s.
+ * Replaces: per-window fancy-index copy + torch.stack (dataset_utils.py:230-231,243-244), the
+ * per-sample standardisation in CustomWindowDataset.__getitem__ (CustomWindowDataset.py:53-60),
+ * default_collate, and the H2D copy in define_inputs (modeling_utils.py:40,42).
+ *   streams_host: HOST array of n_streams descriptors (pointers inside are device pointers).
+ *   variant: 0 = auto, 1 = LDG path, 2 = TMA bulk-copy staging path.                             */
+int b200med_gather_norm(const b200med_stream_desc *streams_host, int32_t n_streams,
+                        const int32_t *starts, int64_t B, int32_t W, int32_t variant, void *stream);
+
+/* Frame path: standardise whole rows in place order (no gather): out[r,:] = (x[r,:]-mean)/std.
+ * Replaces the kinematics standardisation of CustomFrameDataset.__getitem__ (CustomFrameDataset.py:93-95). */
+int b200med_standardise_rows(const float *x, const float *mean, const float *stdv, float *out,
+                             int64_t rows, int32_t dim, int32_t out_ld, int32_t out_col, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  Modality-projection MLP (FeatureExtractor, MED/modeling/models.py:6-47) as GEMMs
+ *     y = act(x W^T + b);  W is [N_out, K_in] row-major exactly like nn.Linear.weight.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* fp32 SIMT path (parity mode, 1e-5): y[M,N] = x[M,K] W[N,K]^T + b, optional ReLU.               */
+int b200med_linear_fwd_f32(const float *x, const float *w, const float *bias, float *y, int64_t M,
+                           int32_t N, int32_t K, int32_t relu, void *stream);
+/* dx[M,K] = dy[M,N] W[N,K]; if relu_out != NULL the result is masked by (relu_out > 0), i.e. the
+ * ReLU backward of the PREVIOUS layer whose forward output is relu_out [M,K].                     */
+int b200med_linear_bwd_data_f32(const float *dy, const float *w, const float *relu_out, float *dx,
+                                int64_t M, int32_t N, int32_t K, void *stream);
+/* dW[N,K] (+)= dy[M,N]^T x[M,K];  db[N] (+)= sum_m dy[m,n].  accumulate: 0 overwrite, 1 add.
+ * Deterministic (fixed reduction order).  workspace: >= b200med_linear_bwd_weight_ws_bytes().     */
+int64_t b200med_linear_bwd_weight_ws_bytes(int64_t M, int32_t N, int32_t K);
+int b200med_linear_bwd_weight_f32(const float *dy, const float *x, float *dw, float *db, int64_t M,
+                                  int32_t N, int32_t K, int32_t accumulate, void *workspace,
+                                  void *stream);
+
+/* bf16 tcgen05 / TMEM / TMA path (throughput mode, 2e-2).  All operands bf16 row-major, fp32
+ * accumulation in tensor memory.  D[M,N] = A[M,K] B[N,K]^T  (+bias, ReLU, ReLU-mask epilogues).
+ *   a_kmajor / b_kmajor: 1 if the operand is stored [rows, K] (K contiguous); 0 if it is stored
+ *   [K, rows] (rows contiguous, "MN-major") -- used by the weight-gradient GEMM whose reduction
+ *   dimension is the row index of both activations.
+ *   out_dtype: B200MED_BF16 or B200MED_F32.  bias [N] f32 or NULL.  relu: apply max(.,0).
+ *   mask [M,N] bf16 or NULL: multiply the result by (mask > 0) (ReLU backward).
+ *   split_k > 1: K is split over split_k CTAs whose fp32 partial tiles are summed in a fixed
+ *   order (deterministic); needs workspace >= b200med_gemm_bf16_ws_bytes().                       */
+int64_t b200med_gemm_bf16_ws_bytes(int64_t M, int64_t N, int64_t K, int32_t split_k);
+int b200med_gemm_bf16(const void *A, const void *B, void *D, const float *bias, const void *mask,
+                      int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd,
+                      int32_t a_kmajor, int32_t b_kmajor, int32_t out_dtype, int32_t relu,
+                      int32_t split_k, void *workspace, void *stream);
+/* 1 if the tcgen05 path can run on the current device (compute capability 10.x). */
+int b200med_has_tcgen05(void);
+
+/* db[N] = sum_m dy[m,n] (bf16 or f32 input, f32 output), deterministic. */
+int b200med_colsum(const void *dy, int32_t dtype, float *db, int64_t M, int32_t N, int64_t ld,
+                   void *workspace, void *stream);
+int64_t b200med_colsum_ws_bytes(int64_t M, int32_t N);
+
+/* fp32 <-> bf16 conversion and [R,C] -> [C,R] transpose helpers used between layers. */
+int b200med_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stream);
+int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  Fused loss + gradient + metric counts (latency-bound; deterministic reductions)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Binary window loss.  Replaces BCEWithLogitsLoss(pos_weight?) (modeling_utils.py:234-246, 276),
+ * sigmoid > 0.5 (:374-375) and the sklearn confusion-matrix / F1 inputs (:377-381) in one pass.
+ *   logits, labels [B] f32; pos_weight: 1.0f when unused.
+ *   loss [1] f32 OUT mean loss; dlogits [B] OUT or NULL = d(mean loss)/dlogit * grad_scale;
+ *   probs [B] OUT or NULL sigmoid; preds [B] OUT or NULL in {0,1};
+ *   counts [4] i64 (tn, fp, fn, tp): overwritten if accumulate == 0, else added to.
+ *   workspace >= b200med_loss_ws_bytes(B).                                                       */
+int64_t b200med_loss_ws_bytes(int64_t B);
+int b200med_bce_logits(const float *logits, const float *labels, int64_t B, float pos_weight,
+                       float grad_scale, float *loss, float *dlogits, float *probs, float *preds,
+                       int64_t *counts, int32_t accumulate, void *workspace, void *stream);
+
+/* Multi-class window loss.  Replaces CrossEntropyLoss(weight?) (modeling_utils.py:240-248), the
+ * masked reduction of the cascade (:612-625, :988-996), softmax/argmax (:493-495) and the confusion
+ * matrix inputs (:519-528).
+ *   logits [B,C] f32; target [B] i32 class index; class_weight [C] f32 or NULL; mask [B] f32 or NULL.
+ *   target_shift: class index fed to the loss is max(target + target_shift, 0)  (cascade: -1).
+ *   reduction: 0 = weighted mean (sum w_y l / sum w_y), 1 = sum(l*mask)/sum(mask) if sum(mask)>0
+ *              else sum(l*mask) [train cascade], 2 = plain sum, 3 = cascade validation quirk
+ *              (sum(l) if sum(mask) > 0 else mean(l); the reference broadcasts [B]*[B,1], :989-996).
+ *   pred_shift / pred_mask_mode: preds = argmax + pred_shift, forced to 0 where
+ *              (mode 1: target == 0) or (mode 2: mask == 0); mode 0: never.
+ *   cm [C_cm, C_cm] i64 confusion counts of (target, pred), C_cm = cm_classes; accumulate as above.
+ *   probs [B,C] OUT or NULL softmax.                                                             */
+int b200med_ce_logits(const float *logits, const int32_t *target, const float *class_weight,
+                      const float *mask, int64_t B, int32_t C, int32_t target_shift,
+                      int32_t reduction, float grad_scale, float *loss, float *dlogits,
+                      float *probs, int32_t *preds, int32_t pred_shift, int32_t pred_mask_mode,
+                      int64_t *cm, int32_t cm_classes, int32_t accumulate, void *workspace,
+                      void *stream);
+
+/* Frame-path loss.  Replaces compute_loss('frame') (modeling_utils.py:278-295): cross entropy of
+ * every stage's [2, T] logits against the soft targets [1-e, e], mean over frames, mean over stages;
+ * predictions = argmax of the LAST stage (:370); counts as in b200med_bce_logits.
+ *   logits [stages, C=2, T] f32 (the [S,1,2,T] model output); e [T] f32.                          */
+int b200med_ce_frame(const float *logits, const float *e, int32_t stages, int64_t T,
+                     float grad_scale, float *loss, float *dlogits, float *preds, int64_t *counts,
+                     int32_t accumulate, void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser: Adam with coupled L2 decay, torch.optim.Adam semantics (modeling_utils.py:221-222)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* state [4] f32 device scalars, owned by the caller: {step, lr, bias_corr1, sqrt(bias_corr2)}.
+ * b200med_adam_advance: step += 1 and recompute the corrections (1 thread, double precision).    */
+int b200med_adam_advance(float *state, float beta1, float beta2, void *stream);
+/* p, g, m, v [n] f32 flat buffers.  g is multiplied by grad_scale first (1/world_size after the
+ * gradient all-reduce).  lr and the bias corrections are read from `state` on the device so the
+ * launch is CUDA-graph replayable.                                                               */
+int b200med_adam_step(float *p, const float *g, float *m, float *v, int64_t n, const float *state,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                      void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame -> window post-processing and ensemble fusion (config 5)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Window value of frame-level predictions: mean over [start, start+W) in fp64, then `>= 0.5`
+ * (binary) or round-half-to-even (multi-class).  Replaces window_predictions
+ * (MED/modeling/modeling_utils.py:2752-2758).  frame_preds [N] f32, out [n] f32.                  */
+int b200med_window_vote(const float *frame_preds, const int32_t *starts, int64_t n, int32_t W,
+                        int32_t binary, float *out, void *stream);
+/* Soft vote of two window models, (pa+pb)/2 >= 0.5 in fp64 (ensemble.ipynb cell 6, lines 10-19),
+ * with confusion counts against labels (or labels == NULL).                                      */
+int b200med_soft_vote(const float *pa, const float *pb, const float *labels, int64_t n, float *preds,
+                      int64_t *counts, int32_t accumulate, void *workspace, void *stream);
+/* Cascade: out = binary == 1 ? multiclass : 0 (ensemble.ipynb cell 15, lines 53-63).             */
+int b200med_cascade(const int32_t *binary, const int32_t *multiclass, int64_t n, int32_t *out,
+                    void *stream);
+/* Confusion counts cm[C,C] of (target, pred) i32 vectors; deterministic.                         */
+int b200med_confusion(const int32_t *target, const int32_t *pred, int64_t n, int32_t C, int64_t *cm,
+                      int32_t accumulate, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MED_H */

@@ -1,0 +1,19 @@
+// Error reporting, version and launch accounting for the C ABI (include/b200med.h).
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace b200med {
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace b200med
+
+extern "C" __attribute__((visibility("default"))) int b200med_version(void) { return B200MED_VERSION; }
+extern "C" __attribute__((visibility("default"))) const char *b200med_last_error(void) { return b200med::g_err; }
+extern "C" __attribute__((visibility("default"))) int64_t b200med_launch_count(void) { return (int64_t)b200med::g_launches.load(); }

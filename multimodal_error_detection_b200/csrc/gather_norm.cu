@@ -1,0 +1,428 @@
+// K1: fused window gather + per-stream standardise + concat, from the device-resident frame table.
+//
+//   out_s[b*W + t, col_s + d] = (table_s[starts[b] + t, d] - mean_s[d]) / std_s[d]
+//
+// Roofline: HBM bandwidth.  Algorithmic bytes per window = W * sum_s D_s * (s_in + s_out)
+// (SURVEY.md section 8d): 165 920 B at W=10, D=2048+26, f32->f32; 199 104 B at W=16, f32->bf16.
+// A window's W frames are CONTIGUOUS rows of the table (window_data never crosses a subject and
+// subjects are contiguous), so the "gather" is B independent contiguous runs of W*D elements --
+// fully coalesced 128-bit traffic; only the run starts are data dependent.
+//
+// Three device paths, chosen per stream on the host:
+//   wide     D*4 bytes a multiple of the CTA's vector footprint (the 2048-d image stream): every
+//            thread owns fixed columns, keeps mean/std in registers and streams U rows at a time
+//            with 128-bit L1-bypassing loads -> U*16 B in flight per thread.
+//   tma      same mapping, but the rows of a chunk are staged global->shared by one elected thread
+//            with cp.async.bulk (1-D TMA) into an mbarrier-guarded ring, so the LSU only carries the
+//            shared-memory reads and the global stores.
+//   generic  any D / alignment (26-d kinematics, concat offsets): one element per thread, the
+//            window's run is still read contiguously.
+// All streams of a call are served by ONE launch: a CTA first decodes which stream its work unit
+// belongs to (block-uniform branch).
+#include "common.cuh"
+
+namespace b200med {
+
+constexpr int kThreads = 256;
+constexpr int kRowsPerUnit = 4;  // U: rows in flight per thread in the wide path
+
+struct StreamParams {
+    const void *table;
+    const float *mean;
+    const float *stdv;
+    void *out;
+    int dim, table_dtype, out_dtype, out_ld, out_col, stat_rows, exact_div, path;  // path: 0 generic, 1 wide
+    long long unit_begin;  // first global work-unit index of this stream
+    int slabs;             // wide: column slabs per row; generic: unused
+    int chunks;            // wide: row chunks per window
+};
+
+struct GatherParams {
+    StreamParams s[B200MED_MAX_STREAMS];
+    int n_streams;
+    int W;
+    long long B;
+    long long total_units;
+    const int32_t *starts;
+};
+
+template <bool EXACT>
+__device__ __forceinline__ float standardise(float x, float mean, float sd_or_inv) {
+    // EXACT: IEEE-754 subtract then divide, the op order of CustomWindowDataset.py:58,60.
+    return EXACT ? __fdiv_rn(__fsub_rn(x, mean), sd_or_inv) : (x - mean) * sd_or_inv;
+}
+
+// ---- wide path: f32 table, VPT consecutive floats per thread, U rows in flight ------------------
+template <typename OutT, bool EXACT>
+__device__ __forceinline__ void wide_unit(const StreamParams &sp, const int32_t *__restrict__ starts, int W,
+                                          long long unit) {
+    constexpr int VPT = sizeof(OutT) == 2 ? 8 : 4;  // keep the STORE 128-bit wide
+    constexpr int NV = VPT / 4;
+    const int slab = (int)(unit % sp.slabs);
+    const long long rest = unit / sp.slabs;
+    const int chunk = (int)(rest % sp.chunks);
+    const long long b = rest / sp.chunks;
+    const int col = (slab * kThreads + threadIdx.x) * VPT;
+    const int t0 = chunk * kRowsPerUnit;
+    const int rows = min(kRowsPerUnit, W - t0);
+    const long long src_row = (long long)starts[b] + t0;
+    const float *src = reinterpret_cast<const float *>(sp.table) + src_row * sp.dim + col;
+
+    float4 x[kRowsPerUnit][NV];
+#pragma unroll
+    for (int r = 0; r < kRowsPerUnit; ++r)
+        if (r < rows) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                x[r][v] = ldg_stream(reinterpret_cast<const float4 *>(src + (long long)r * sp.dim) + v);
+        }
+
+    float4 mu[NV], sd[NV];
+    const bool per_step = sp.stat_rows > 1;
+    auto load_stats = [&](int t) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            if (sp.mean) {
+                mu[v] = __ldg(reinterpret_cast<const float4 *>(sp.mean + (long long)t * sp.dim + col) + v);
+                sd[v] = __ldg(reinterpret_cast<const float4 *>(sp.stdv + (long long)t * sp.dim + col) + v);
+                if (!EXACT) sd[v] = make_float4(1.0f / sd[v].x, 1.0f / sd[v].y, 1.0f / sd[v].z, 1.0f / sd[v].w);
+            } else {
+                mu[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sd[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+        }
+    };
+    if (!per_step) load_stats(0);
+
+    OutT *dst = reinterpret_cast<OutT *>(sp.out) + ((long long)b * W + t0) * sp.out_ld + sp.out_col + col;
+#pragma unroll
+    for (int r = 0; r < kRowsPerUnit; ++r)
+        if (r < rows) {
+            if (per_step) load_stats(t0 + r);
+            float y[VPT];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                y[4 * v + 0] = standardise<EXACT>(x[r][v].x, mu[v].x, sd[v].x);
+                y[4 * v + 1] = standardise<EXACT>(x[r][v].y, mu[v].y, sd[v].y);
+                y[4 * v + 2] = standardise<EXACT>(x[r][v].z, mu[v].z, sd[v].z);
+                y[4 * v + 3] = standardise<EXACT>(x[r][v].w, mu[v].w, sd[v].w);
+            }
+            OutT *d = dst + (long long)r * sp.out_ld;
+            if constexpr (sizeof(OutT) == 4) {
+                stg_stream(reinterpret_cast<float4 *>(d), make_float4(y[0], y[1], y[2], y[3]));
+            } else {
+                stg_stream(reinterpret_cast<uint4 *>(d),
+                           make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                                      pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7])));
+            }
+        }
+}
+
+// ---- generic path: one element per thread over the window's contiguous run -----------------------
+__device__ __forceinline__ float load_elem(const void *table, int dtype, long long idx) {
+    return dtype == B200MED_F32 ? __ldg(reinterpret_cast<const float *>(table) + idx)
+                                : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(table)[idx]);
+}
+
+__device__ __forceinline__ void generic_unit(const StreamParams &sp, const int32_t *__restrict__ starts, int W,
+                                             long long unit) {
+    // unit -> (window b, slice of the W*dim run); kThreads*4 elements per unit
+    const int run = W * sp.dim;
+    const int per_unit = kThreads * 4;
+    const int units_per_window = (run + per_unit - 1) / per_unit;
+    const long long b = unit / units_per_window;
+    const int u = (int)(unit % units_per_window);
+    const long long src0 = (long long)starts[b] * sp.dim;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = u * per_unit + k * kThreads + threadIdx.x;
+        if (e >= run) break;
+        const int t = e / sp.dim, d = e - t * sp.dim;
+        float x = load_elem(sp.table, sp.table_dtype, src0 + e);
+        if (sp.mean) {
+            const int srow = sp.stat_rows > 1 ? t : 0;
+            const float mu = __ldg(sp.mean + (long long)srow * sp.dim + d);
+            const float sd = __ldg(sp.stdv + (long long)srow * sp.dim + d);
+            x = sp.exact_div ? __fdiv_rn(__fsub_rn(x, mu), sd) : (x - mu) * (1.0f / sd);
+        }
+        const long long o = ((long long)b * W + t) * sp.out_ld + sp.out_col + d;
+        if (sp.out_dtype == B200MED_F32) reinterpret_cast<float *>(sp.out)[o] = x;
+        else reinterpret_cast<__nv_bfloat16 *>(sp.out)[o] = __float2bfloat16_rn(x);
+    }
+}
+
+// Stream 0 may be a wide stream (template-specialised on its output type / division mode); all other
+// streams go through the generic path.  One launch serves every stream of the call.
+template <typename OutT, bool EXACT, bool HAS_WIDE>
+__global__ void __launch_bounds__(kThreads, (sizeof(OutT) == 2 ? 3 : 4))
+gather_norm_kernel(const __grid_constant__ GatherParams p) {
+    const long long wide_units = HAS_WIDE ? p.s[1].unit_begin : 0;  // s[1].unit_begin == units of stream 0
+    for (long long unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+        if (HAS_WIDE && unit < wide_units) {
+            wide_unit<OutT, EXACT>(p.s[0], p.starts, p.W, unit);
+        } else {
+            int si = HAS_WIDE ? 1 : 0;
+#pragma unroll
+            for (int k = 1; k < B200MED_MAX_STREAMS; ++k)
+                if (k < p.n_streams && unit >= p.s[k].unit_begin) si = k;
+            // copy the (small) descriptor out of the parameter bank once per unit
+            StreamParams sp;
+#pragma unroll
+            for (int k = 0; k < B200MED_MAX_STREAMS; ++k)
+                if (k == si) sp = p.s[k];
+            generic_unit(sp, p.starts, p.W, unit - sp.unit_begin);
+        }
+    }
+}
+
+// ---- TMA staging variant (wide f32 streams only) --------------------------------------------------
+// Ring of kStages shared-memory buffers, each holding one chunk (U rows x D floats, contiguous in
+// the table).  Thread 0 is the producer: it arms the stage's mbarrier with the byte count and issues
+// ONE cp.async.bulk per chunk; all threads consume.  A stage is re-armed only after the CTA-wide
+// barrier that follows its consumption, so no separate "empty" barrier is needed.
+constexpr int kTmaStages = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename OutT, bool EXACT>
+__global__ void __launch_bounds__(kThreads, 2)
+gather_norm_tma_kernel(const __grid_constant__ GatherParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kTmaStages];
+    const StreamParams &sp = p.s[0];
+    const int D = sp.dim;
+    const int W = p.W;
+    const int chunks = sp.chunks;
+    const long long n_units = (long long)p.B * chunks;  // unit = (window, row chunk), all columns
+    const size_t stage_bytes = (size_t)kRowsPerUnit * D * sizeof(float);
+    float *stage_ptr[kTmaStages];
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) stage_ptr[s] = reinterpret_cast<float *>(smem_raw + s * stage_bytes);
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](long long unit, int stage) {
+        const int chunk = (int)(unit % chunks);
+        const long long b = unit / chunks;
+        const int t0 = chunk * kRowsPerUnit;
+        const int rows = min(kRowsPerUnit, W - t0);
+        const uint32_t bytes = (uint32_t)((size_t)rows * D * sizeof(float));
+        const float *src = reinterpret_cast<const float *>(sp.table) + ((long long)p.starts[b] + t0) * D;
+        mbar_expect_tx(&full_bar[stage], bytes);
+        tma_bulk_g2s(stage_ptr[stage], src, bytes, &full_bar[stage]);
+    };
+
+    // prologue: fill the ring
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTmaStages; ++s) {
+            const long long u = blockIdx.x + (long long)s * gridDim.x;
+            if (u < n_units) issue(u, s);
+        }
+    }
+
+    const int nvec = D / 4;  // float4 per row
+    int it = 0;
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+        const int stage = it % kTmaStages;
+        const uint32_t parity = (uint32_t)((it / kTmaStages) & 1);
+        const int chunk = (int)(unit % chunks);
+        const long long b = unit / chunks;
+        const int t0 = chunk * kRowsPerUnit;
+        const int rows = min(kRowsPerUnit, W - t0);
+        mbar_wait(&full_bar[stage], parity);
+        const float4 *buf = reinterpret_cast<const float4 *>(stage_ptr[stage]);
+        OutT *dst_base = reinterpret_cast<OutT *>(sp.out) + ((long long)b * W + t0) * sp.out_ld + sp.out_col;
+        for (int r = 0; r < rows; ++r) {
+            const int srow = sp.stat_rows > 1 ? (t0 + r) : 0;
+            for (int v = threadIdx.x; v < nvec; v += kThreads) {
+                const float4 x = buf[r * nvec + v];
+                float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), sd = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (sp.mean) {
+                    mu = __ldg(reinterpret_cast<const float4 *>(sp.mean + (long long)srow * D) + v);
+                    sd = __ldg(reinterpret_cast<const float4 *>(sp.stdv + (long long)srow * D) + v);
+                    if (!EXACT) sd = make_float4(1.0f / sd.x, 1.0f / sd.y, 1.0f / sd.z, 1.0f / sd.w);
+                }
+                const float y0 = standardise<EXACT>(x.x, mu.x, sd.x), y1 = standardise<EXACT>(x.y, mu.y, sd.y),
+                            y2 = standardise<EXACT>(x.z, mu.z, sd.z), y3 = standardise<EXACT>(x.w, mu.w, sd.w);
+                OutT *d = dst_base + (long long)r * sp.out_ld + v * 4;
+                if constexpr (sizeof(OutT) == 4) {
+                    stg_stream(reinterpret_cast<float4 *>(d), make_float4(y0, y1, y2, y3));
+                } else {
+                    *reinterpret_cast<uint2 *>(d) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                }
+            }
+        }
+        __syncthreads();  // everyone is done reading this stage
+        if (threadIdx.x == 0) {
+            const long long next = unit + (long long)kTmaStages * gridDim.x;
+            if (next < n_units) issue(next, stage);
+        }
+    }
+}
+
+__global__ void standardise_rows_kernel(const float *__restrict__ x, const float *__restrict__ mean,
+                                        const float *__restrict__ stdv, float *__restrict__ out, long long rows,
+                                        int dim, int out_ld, int out_col) {
+    const long long n = rows * dim;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / dim;
+        const int d = (int)(i - r * dim);
+        out[r * out_ld + out_col + d] = __fdiv_rn(__fsub_rn(x[i], mean[d]), stdv[d]);
+    }
+}
+
+}  // namespace b200med
+
+using namespace b200med;
+
+extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const b200med_stream_desc *streams, int32_t n_streams, const int32_t *starts,
+                                   int64_t B, int32_t W, int32_t variant, void *stream) {
+    B200MED_REQUIRE(streams && n_streams >= 1 && n_streams <= B200MED_MAX_STREAMS, "1..8 streams");
+    B200MED_REQUIRE(B >= 0 && W >= 1, "need B >= 0 and W >= 1");
+    if (B == 0) return B200MED_OK;
+    B200MED_REQUIRE(starts, "null starts");
+    GatherParams p{};
+    p.n_streams = n_streams;
+    p.W = W;
+    p.B = B;
+    p.starts = starts;
+    long long units = 0;
+    for (int i = 0; i < n_streams; ++i) {
+        const b200med_stream_desc &d = streams[i];
+        B200MED_REQUIRE(d.table && d.out && d.dim >= 1, "stream needs table, out, dim >= 1");
+        B200MED_REQUIRE((d.mean == nullptr) == (d.stdv == nullptr), "mean and std must both be given or both NULL");
+        B200MED_REQUIRE(d.stat_rows == 1 || d.stat_rows == W, "stat_rows must be 1 or W");
+        B200MED_REQUIRE(d.out_ld >= d.out_col + d.dim, "out_ld too small for out_col + dim");
+        B200MED_REQUIRE(d.table_dtype == B200MED_F32 || d.table_dtype == B200MED_BF16, "bad table dtype");
+        B200MED_REQUIRE(d.out_dtype == B200MED_F32 || d.out_dtype == B200MED_BF16, "bad out dtype");
+        StreamParams &sp = p.s[i];
+        sp.table = d.table; sp.mean = d.mean; sp.stdv = d.stdv; sp.out = d.out;
+        sp.dim = d.dim; sp.table_dtype = d.table_dtype; sp.out_dtype = d.out_dtype;
+        sp.out_ld = d.out_ld; sp.out_col = d.out_col; sp.stat_rows = d.stat_rows; sp.exact_div = d.exact_div;
+        const int vpt = d.out_dtype == B200MED_BF16 ? 8 : 4;
+        const size_t out_es = d.out_dtype == B200MED_BF16 ? 2 : 4;
+        const bool aligned = ((uintptr_t)d.table % 16 == 0) && ((uintptr_t)d.out % 16 == 0) &&
+                             ((d.out_ld * out_es) % 16 == 0) && ((d.out_col * out_es) % 16 == 0) &&
+                             (!d.mean || (((uintptr_t)d.mean % 16 == 0) && ((uintptr_t)d.stdv % 16 == 0)));
+        const bool wide = d.table_dtype == B200MED_F32 && aligned && (d.dim % (kThreads * vpt) == 0);
+        sp.path = wide ? 1 : 0;
+        sp.unit_begin = units;
+        if (wide) {
+            sp.slabs = d.dim / (kThreads * vpt);
+            sp.chunks = (W + kRowsPerUnit - 1) / kRowsPerUnit;
+            units += (long long)B * sp.chunks * sp.slabs;
+        } else {
+            const long long run = (long long)W * d.dim;
+            units += (long long)B * ((run + kThreads * 4 - 1) / (kThreads * 4));
+        }
+    }
+    p.total_units = units;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // TMA staging: only for a single wide f32 stream (the image stream); other streams of the call
+    // go through the LDG kernel in a second launch.
+    if (variant == 2 && p.s[0].path == 1) {
+        GatherParams pt = p;
+        pt.n_streams = 1;
+        pt.s[0].chunks = (W + kRowsPerUnit - 1) / kRowsPerUnit;
+        const size_t smem = (size_t)kTmaStages * kRowsPerUnit * pt.s[0].dim * sizeof(float);
+        B200MED_REQUIRE(smem <= 200 * 1024, "row too wide for the TMA staging ring");
+        const long long n_units = (long long)B * pt.s[0].chunks;
+        const long long cap_t = 2LL * num_sms();
+        const int grid = (int)(n_units < cap_t ? n_units : cap_t);
+        auto launch = [&](auto kern) -> int {
+            if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                   "cudaFuncSetAttribute(gather_norm_tma)")) return e;
+            kern<<<grid, kThreads, smem, st>>>(pt);
+            return after_launch("gather_norm_tma_kernel");
+        };
+        int e;
+        if (pt.s[0].out_dtype == B200MED_F32)
+            e = pt.s[0].exact_div ? launch(gather_norm_tma_kernel<float, true>) : launch(gather_norm_tma_kernel<float, false>);
+        else
+            e = pt.s[0].exact_div ? launch(gather_norm_tma_kernel<__nv_bfloat16, true>)
+                                  : launch(gather_norm_tma_kernel<__nv_bfloat16, false>);
+        if (e) return e;
+        if (n_streams == 1) return B200MED_OK;
+        // remaining streams
+        GatherParams pr{};
+        pr.n_streams = n_streams - 1; pr.W = W; pr.B = B; pr.starts = starts;
+        const long long shift = p.s[1].unit_begin;
+        for (int i = 1; i < n_streams; ++i) { pr.s[i - 1] = p.s[i]; pr.s[i - 1].unit_begin -= shift; }
+        pr.total_units = units - shift;
+        p = pr;
+    }
+    // stream order for the single launch: at most one wide stream, placed first
+    int wide_idx = -1;
+    for (int i = 0; i < p.n_streams; ++i)
+        if (p.s[i].path == 1) { wide_idx = i; break; }
+    GatherParams q{};
+    q.n_streams = p.n_streams; q.W = W; q.B = B; q.starts = starts;
+    {
+        int k = 0;
+        long long u = 0;
+        auto push = [&](const StreamParams &src, bool as_wide) {
+            StreamParams sp = src;
+            sp.unit_begin = u;
+            if (as_wide) {
+                u += (long long)B * sp.chunks * sp.slabs;
+            } else {
+                sp.path = 0;
+                const long long run = (long long)W * sp.dim;
+                u += (long long)B * ((run + kThreads * 4 - 1) / (kThreads * 4));
+            }
+            q.s[k++] = sp;
+        };
+        if (wide_idx >= 0) push(p.s[wide_idx], true);
+        for (int i = 0; i < p.n_streams; ++i)
+            if (i != wide_idx) push(p.s[i], false);
+        if (k < B200MED_MAX_STREAMS) q.s[k].unit_begin = u;  // sentinel: s[1].unit_begin must exist
+        q.total_units = u;
+    }
+    const long long max_grid = (long long)num_sms() * 8;  // up to 8 CTAs of 256 threads per SM
+    const int grid = (int)(q.total_units < max_grid ? q.total_units : max_grid);
+    if (wide_idx < 0) {
+        gather_norm_kernel<float, true, false><<<grid, kThreads, 0, st>>>(q);
+    } else if (q.s[0].out_dtype == B200MED_F32) {
+        if (q.s[0].exact_div) gather_norm_kernel<float, true, true><<<grid, kThreads, 0, st>>>(q);
+        else gather_norm_kernel<float, false, true><<<grid, kThreads, 0, st>>>(q);
+    } else {
+        if (q.s[0].exact_div) gather_norm_kernel<__nv_bfloat16, true, true><<<grid, kThreads, 0, st>>>(q);
+        else gather_norm_kernel<__nv_bfloat16, false, true><<<grid, kThreads, 0, st>>>(q);
+    }
+    return after_launch("gather_norm_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_standardise_rows(const float *x, const float *mean, const float *stdv, float *out,
+                                        int64_t rows, int32_t dim, int32_t out_ld, int32_t out_col, void *stream) {
+    B200MED_REQUIRE(rows >= 0 && dim >= 1 && out_ld >= out_col + dim, "bad shape");
+    if (rows == 0) return B200MED_OK;
+    B200MED_REQUIRE(x && mean && stdv && out, "null pointer");
+    const long long n = rows * dim;
+    const long long want = (n + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    standardise_rows_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        x, mean, stdv, out, rows, dim, out_ld, out_col);
+    return after_launch("standardise_rows_kernel");
+}

@@ -1,0 +1,243 @@
+// K2 (parity mode): fp32 SIMT GEMMs for the FeatureExtractor MLP (MED/modeling/models.py:6-47).
+//
+// TF32 / bf16 tensor-core products cannot meet the 1e-5 relative bar of the fp32 parity mode
+// ("hard parts"), so this path uses true fp32 FMAs on the CUDA cores with a fixed
+// reduction order (deterministic).  The throughput mode is the tcgen05 kernel in gemm_tcgen05.cu.
+//
+// One tiled kernel covers the three products of a Linear layer:
+//   NT  y [M,N] = x [M,K]  W[N,K]^T            (forward,           A row = m, B row = n, both K-contiguous)
+//   NN  dx[M,K] = dy[M,N]  W[N,K]              (data gradient,     reduction over n)
+//   TN  dW[N,K] = dy[M,N]^T x[M,K]             (weight gradient,   reduction over m, split in slabs)
+// Tile 64x64x16, 256 threads, 4x4 outputs per thread, operands staged in shared memory as [k][row].
+#include "common.cuh"
+
+namespace b200med {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+// C[i,j] = sum_r A(i,r) * B(j,r)   with A(i,r) = A[i*a_rs + r*a_cs], B(j,r) = B[j*b_rs + r*b_cs].
+// Epilogue: + bias[j], ReLU, * (mask[i,j] > 0).  blockIdx.z = reduction slab (split-R), partial
+// results go to C + z*slab_stride when gridDim.z > 1.
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C,
+                long long I, long long J, long long R, long long a_rs, long long a_cs, long long b_rs,
+                long long b_cs, long long ldc, const float *__restrict__ bias, int relu,
+                const float *__restrict__ mask, long long ld_mask, long long r_per_slab,
+                long long slab_stride) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each a 4x4 micro-tile
+    const long long i0 = (long long)blockIdx.y * BM, j0 = (long long)blockIdx.x * BN;
+    const long long r_begin = (long long)blockIdx.z * r_per_slab;
+    const long long r_end = min(R, r_begin + r_per_slab);
+
+    float acc[4][4] = {};
+    // loader mapping: when the reduction index is the contiguous one (cs == 1) let consecutive
+    // threads walk r; otherwise let them walk the row index.
+    const bool a_r_fast = (a_cs == 1), b_r_fast = (b_cs == 1);
+    for (long long r0 = r_begin; r0 < r_end; r0 += BK) {
+#pragma unroll
+        for (int l = 0; l < (BM * BK) / 256; ++l) {
+            const int e = l * 256 + tid;
+            const int rr = a_r_fast ? (e % BK) : (e / BM);
+            const int ii = a_r_fast ? (e / BK) : (e % BM);
+            const long long gi = i0 + ii, gr = r0 + rr;
+            As[rr][ii] = (gi < I && gr < r_end) ? __ldg(A + gi * a_rs + gr * a_cs) : 0.0f;
+        }
+#pragma unroll
+        for (int l = 0; l < (BN * BK) / 256; ++l) {
+            const int e = l * 256 + tid;
+            const int rr = b_r_fast ? (e % BK) : (e / BN);
+            const int jj = b_r_fast ? (e / BK) : (e % BN);
+            const long long gj = j0 + jj, gr = r0 + rr;
+            Bs[rr][jj] = (gj < J && gr < r_end) ? __ldg(B + gj * b_rs + gr * b_cs) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+    float *Cz = C + (long long)blockIdx.z * slab_stride;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const long long gi = i0 + ty * 4 + u;
+        if (gi >= I) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const long long gj = j0 + tx * 4 + v;
+            if (gj >= J) continue;
+            float y = acc[u][v];
+            if (bias) y += bias[gj];
+            if (relu) y = fmaxf(y, 0.0f);
+            if (mask && !(mask[gi * ld_mask + gj] > 0.0f)) y = 0.0f;
+            Cz[gi * ldc + gj] = y;
+        }
+    }
+}
+
+// out[e] (+)= sum_z part[z*stride + e], z ascending (fixed order).
+__global__ void slab_reduce_kernel(const float *__restrict__ part, float *__restrict__ out, long long n, int slabs,
+                                   long long stride, int accumulate) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        for (int z = 0; z < slabs; ++z) s += part[z * stride + e];
+        out[e] = accumulate ? out[e] + s : s;
+    }
+}
+
+// Column sums of a [M, N] matrix (bias gradient).  Stage 1: each block sums a slab of rows for a tile
+// of 32 columns; stage 2: slabs are added in ascending order.  T = float or bf16.
+template <typename T>
+__global__ void colsum_partial_kernel(const T *__restrict__ x, float *__restrict__ part, long long M, int N,
+                                      long long ld, long long rows_per_slab) {
+    __shared__ float sh[8][33];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int lane_row = threadIdx.x >> 5;  // 8 row lanes
+    const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+    float s = 0.0f;
+    if (col < N)
+        for (long long m = m0 + lane_row; m < m1; m += 8) s += (float)x[m * ld + col];
+    sh[lane_row][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (lane_row == 0 && col < N) {
+        float t = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += sh[r][threadIdx.x & 31];
+        part[(long long)blockIdx.y * N + col] = t;
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __bfloat162float(x[i]);
+}
+
+static long long weight_slabs(long long M) {
+    // enough slabs to fill the GPU for the small [N,K] weight outputs, at least 1024 rows each
+    long long s = (M + 2047) / 2048;
+    if (s < 1) s = 1;
+    if (s > 64) s = 64;
+    return s;
+}
+static long long colsum_slabs(long long M) {
+    long long s = (M + 1023) / 1024;
+    if (s < 1) s = 1;
+    if (s > 128) s = 128;
+    return s;
+}
+
+}  // namespace b200med
+
+using namespace b200med;
+
+static int launch_gemm(const float *A, const float *B, float *C, long long I, long long J, long long R,
+                       long long a_rs, long long a_cs, long long b_rs, long long b_cs, long long ldc,
+                       const float *bias, int relu, const float *mask, long long ld_mask, int slabs,
+                       long long slab_stride, cudaStream_t st) {
+    dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + BM - 1) / BM), (unsigned)slabs);
+    const long long per = ((R + slabs - 1) / slabs + BK - 1) / BK * BK;
+    gemm_f32_kernel<<<grid, 256, 0, st>>>(A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, relu, mask, ld_mask,
+                                           per, slab_stride);
+    return after_launch("gemm_f32_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_linear_fwd_f32(const float *x, const float *w, const float *bias, float *y, int64_t M,
+                                      int32_t N, int32_t K, int32_t relu, void *stream) {
+    B200MED_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad shape");
+    if (M == 0) return B200MED_OK;
+    B200MED_REQUIRE(x && w && y, "null pointer");
+    return launch_gemm(x, w, y, M, N, K, K, 1, K, 1, N, bias, relu, nullptr, 0, 1, 0, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_linear_bwd_data_f32(const float *dy, const float *w, const float *relu_out, float *dx,
+                                           int64_t M, int32_t N, int32_t K, void *stream) {
+    B200MED_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad shape");
+    if (M == 0) return B200MED_OK;
+    B200MED_REQUIRE(dy && w && dx, "null pointer");
+    // dx[m,k] = sum_n dy[m,n] * w[n,k]:  A = dy (row m, r = n contiguous), B(j=k, r=n) = w[n*K + k]
+    return launch_gemm(dy, w, dx, M, K, N, N, 1, 1, K, K, nullptr, 0, relu_out, K, 1, 0, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t b200med_linear_bwd_weight_ws_bytes(int64_t M, int32_t N, int32_t K) {
+    const long long a = weight_slabs(M) * (long long)N * K * 4;
+    const long long b = colsum_slabs(M) * (long long)N * 4;
+    return a + b + 256;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_linear_bwd_weight_f32(const float *dy, const float *x, float *dw, float *db, int64_t M,
+                                             int32_t N, int32_t K, int32_t accumulate, void *workspace,
+                                             void *stream) {
+    B200MED_REQUIRE(M >= 1 && N >= 1 && K >= 1, "bad shape");
+    B200MED_REQUIRE(dy && x && dw && workspace, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slabs = (int)weight_slabs(M);
+    float *part = reinterpret_cast<float *>(workspace);
+    // dW[n,k] = sum_m dy[m,n] * x[m,k]:  A(i=n, r=m) = dy[m*N + n], B(j=k, r=m) = x[m*K + k]
+    if (int e = launch_gemm(dy, x, part, N, K, M, 1, N, 1, K, K, nullptr, 0, nullptr, 0, slabs, (long long)N * K, st))
+        return e;
+    const long long n = (long long)N * K;
+    const long long blocks = (n + 255) / 256;
+    slab_reduce_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(part, dw, n, slabs, n, accumulate);
+    if (int e = after_launch("slab_reduce_kernel")) return e;
+    if (db) {
+        float *cpart = part + (long long)slabs * n;
+        const int cs = (int)colsum_slabs(M);
+        const long long rows = (M + cs - 1) / cs;
+        dim3 grid((unsigned)((N + 31) / 32), (unsigned)cs);
+        colsum_partial_kernel<float><<<grid, 256, 0, st>>>(dy, cpart, M, N, N, rows);
+        if (int e = after_launch("colsum_partial_kernel")) return e;
+        slab_reduce_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(cpart, db, N, cs, N, accumulate);
+        if (int e = after_launch("slab_reduce_kernel")) return e;
+    }
+    return B200MED_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t b200med_colsum_ws_bytes(int64_t M, int32_t N) { return colsum_slabs(M) * (long long)N * 4 + 256; }
+
+extern "C" __attribute__((visibility("default"))) int b200med_colsum(const void *dy, int32_t dtype, float *db, int64_t M, int32_t N, int64_t ld,
+                              void *workspace, void *stream) {
+    B200MED_REQUIRE(M >= 1 && N >= 1 && ld >= N, "bad shape");
+    B200MED_REQUIRE(dy && db && workspace, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *cpart = reinterpret_cast<float *>(workspace);
+    const int cs = (int)colsum_slabs(M);
+    const long long rows = (M + cs - 1) / cs;
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)cs);
+    if (dtype == B200MED_F32)
+        colsum_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(dy), cpart, M, N, ld, rows);
+    else
+        colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rows);
+    if (int e = after_launch("colsum_partial_kernel")) return e;
+    slab_reduce_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(cpart, db, N, cs, N, 0);
+    return after_launch("slab_reduce_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stream) {
+    if (n <= 0) return B200MED_OK;
+    B200MED_REQUIRE(x && y, "null pointer");
+    const long long blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
+    cast_f32_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<__nv_bfloat16 *>(y), n);
+    return after_launch("cast_f32_bf16_kernel");
+}
+extern "C" __attribute__((visibility("default"))) int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream) {
+    if (n <= 0) return B200MED_OK;
+    B200MED_REQUIRE(x && y, "null pointer");
+    const long long blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
+    cast_bf16_f32_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(x), y, n);
+    return after_launch("cast_bf16_f32_kernel");
+}

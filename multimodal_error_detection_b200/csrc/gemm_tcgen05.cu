@@ -1,0 +1,490 @@
+// K2 (throughput mode): bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// tensor memory, operands staged by TMA), for the FeatureExtractor MLP forward, data-gradient and
+// weight-gradient products (MED/modeling/models.py:19-35 and its autograd backward).
+//
+//   D[M,N] = A[M,K] * B[N,K]^T      A, B bf16; fp32 accumulation in TMEM; D bf16 or fp32
+//
+// Either operand may be K-major (stored [rows, K]) or MN-major (stored [K, rows]); the weight
+// gradient dW = dY^T X reduces over the ROW index of both activations, i.e. both are MN-major.
+//
+// Kernel anatomy (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) into a kStages ring,
+//               completion by mbarrier complete_tx.
+//   warp 1      allocates TMEM (2 accumulators x BLOCK_N columns), then one elected lane issues
+//               tcgen05.mma.cta_group::1.kind::f16 (128 x BLOCK_N x 16) and tcgen05.commit to the
+//               ring's "empty" barriers / the accumulator's "full" barrier.
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / ReLU / ReLU-mask -> 128-bit
+//               global stores; releases the accumulator so the MMA warp can start the next tile while
+//               this one is drained (double-buffered TMEM).
+// Roofline: tensor pipe.  128x256x16 per instruction = 128 cycles at cta_group::1, operand traffic
+// 12 KB per instruction = 96 B/cycle of shared-memory bandwidth (below the 128 B/cycle port), which
+// is why BLOCK_N = 256 is the default tile for the wide layers.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace b200med {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr uint32_t kATileBytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
+
+__device__ __forceinline__ uint32_t s_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s_addr(bar)) : "memory");
+}
+// Bounded spin: a mis-programmed pipeline traps (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
+        if (!done && spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
+//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
+//   [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmParams {
+    long long M, N, K;
+    long long ldd;          // elements between output rows (of D, or of a split-K partial slab = N)
+    int a_kmajor, b_kmajor;
+    int out_f32;            // 1: fp32 output, 0: bf16
+    int relu;
+    int split_k;            // >= 1
+    int kb_per_split;       // k-blocks per split
+    int tiles_m, tiles_n;
+    const float *bias;      // [N] or null (ignored when split_k > 1)
+    const __nv_bfloat16 *mask;  // [M, ldd] or null (ignored when split_k > 1)
+    void *D;                // output, or the fp32 partial workspace when split_k > 1
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr uint32_t kBTileBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int kAccStages = 2;
+    static constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two: BLOCK_N in {32,64,128,256}
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+    uint64_t *empty_bar = full_bar + Cfg::kStages;
+    uint64_t *acc_full = empty_bar + Cfg::kStages;
+    uint64_t *acc_empty = acc_full + Cfg::kAccStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + Cfg::kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb_total = (int)((p.K + BLOCK_K - 1) / BLOCK_K);
+    const long long tiles_mn = (long long)p.tiles_m * p.tiles_n;
+    const long long total_tiles = tiles_mn * p.split_k;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
+        for (int s = 0; s < Cfg::kStages; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < Cfg::kAccStages; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(s_addr(tmem_slot)), "r"(Cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int z = (int)(tile / tiles_mn);
+                const long long mn = tile % tiles_mn;
+                const int m0 = (int)(mn / p.tiles_n) * BLOCK_M, n0 = (int)(mn % p.tiles_n) * BLOCK_N;
+                const int kb0 = z * p.kb_per_split;
+                const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    bar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *sa = smem + (size_t)stage * Cfg::kStageBytes;
+                    unsigned char *sb = sa + kATileBytes;
+                    bar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    const int k0 = kb * BLOCK_K;
+                    if (p.a_kmajor) {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);           // box {64 k, 128 m}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 64; ++j)                          // boxes {64 m, 64 k}
+                            tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+                    }
+                    if (p.b_kmajor) {
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);           // box {64 k, BLOCK_N n}
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++j)
+                            tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+                    }
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, !p.a_kmajor, !p.b_kmajor);
+            // K-major, SW128: 8-row groups are 1024 B apart (SBO); LBO unused (1).  One UMMA_K step = 32 B.
+            // MN-major, SW128: 64-element MN atoms are 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
+            // one UMMA_K step = 16 k-rows = 2048 B.
+            const uint32_t a_lbo = p.a_kmajor ? 16 : 8192, b_lbo = p.b_kmajor ? 16 : 8192;
+            const uint32_t a_kstep = p.a_kmajor ? 32 : 2048, b_kstep = p.b_kmajor ? 32 : 2048;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int z = (int)(tile / tiles_mn);
+                const int kb0 = z * p.kb_per_split;
+                const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+                bar_wait(&acc_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    bar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = s_addr(smem + (size_t)stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+                        const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+                        umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[acc]);         // accumulator complete -> epilogue
+                if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int z = (int)(tile / tiles_mn);
+            const long long mn = tile % tiles_mn;
+            const long long m0 = (mn / p.tiles_n) * BLOCK_M, n0 = (mn % p.tiles_n) * BLOCK_N;
+            bar_wait(&acc_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const long long m = m0 + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            const bool partial = p.split_k > 1;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
+                const long long n_base = n0 + c0;
+                if (row_ok && n_base < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    const bool full = n_base + 32 <= p.N;
+                    if (!partial) {
+                        if (p.bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (full || n_base + j < p.N) f[j] += __ldg(p.bias + n_base + j);
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+                        }
+                        if (p.mask) {
+                            const __nv_bfloat16 *mk = p.mask + m * p.ldd + n_base;
+                            if (full && (((uintptr_t)mk) % 16 == 0)) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint4 u = __ldg(reinterpret_cast<const uint4 *>(mk) + q);
+                                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                    for (int h = 0; h < 4; ++h) {
+                                        // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                                        const uint32_t lo = w[h] & 0xFFFFu, hi = w[h] >> 16;
+                                        if (!((lo & 0x8000u) == 0 && (lo & 0x7FFFu) != 0)) f[q * 8 + h * 2] = 0.0f;
+                                        if (!((hi & 0x8000u) == 0 && (hi & 0x7FFFu) != 0)) f[q * 8 + h * 2 + 1] = 0.0f;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (n_base + j < p.N && !(__bfloat162float(mk[j]) > 0.0f)) f[j] = 0.0f;
+                            }
+                        }
+                    }
+                    if (p.out_f32 || partial) {
+                        float *dst = reinterpret_cast<float *>(p.D) +
+                                     (partial ? (long long)z * p.M * p.N + m * p.N : m * p.ldd) + n_base;
+                        if (full && (((uintptr_t)dst) % 16 == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                reinterpret_cast<float4 *>(dst)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n_base + j < p.N) dst[j] = f[j];
+                        }
+                    } else {
+                        __nv_bfloat16 *dst = reinterpret_cast<__nv_bfloat16 *>(p.D) + m * p.ldd + n_base;
+                        if (full && (((uintptr_t)dst) % 16 == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                reinterpret_cast<uint4 *>(dst)[q] =
+                                    make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
+                                               pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (n_base + j < p.N) dst[j] = __float2bfloat16_rn(f[j]);
+                        }
+                    }
+                }
+            }
+            // all of this warp's TMEM reads are complete (tcgen05.wait::ld above) -> release the accumulator
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&acc_empty[acc]);
+            if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+    }
+}
+
+// D = sum_z partial[z] (ascending z, fixed order) + bias, ReLU, ReLU-mask, dtype conversion.
+__global__ void splitk_reduce_kernel(const float *__restrict__ part, int split, long long M, long long N, long long ldd,
+                                     const float *__restrict__ bias, int relu, const __nv_bfloat16 *__restrict__ mask,
+                                     void *__restrict__ D, int out_f32) {
+    const long long total = M * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e / N, n = e - m * N;
+        float s = 0.0f;
+        for (int z = 0; z < split; ++z) s += part[(long long)z * total + e];
+        if (bias) s += bias[n];
+        if (relu) s = fmaxf(s, 0.0f);
+        if (mask && !(__bfloat162float(mask[m * ldd + n]) > 0.0f)) s = 0.0f;
+        if (out_f32) reinterpret_cast<float *>(D)[m * ldd + n] = s;
+        else reinterpret_cast<__nv_bfloat16 *>(D)[m * ldd + n] = __float2bfloat16_rn(s);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, `ld` elements between rows.
+static int make_tmap(CUtensorMap *map, const void *ptr, long long inner, long long outer, long long ld,
+                     int box_inner, int box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200MED_E_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) inner=%lld outer=%lld ld=%lld box=%dx%d", (int)r, inner,
+                  outer, ld, box_inner, box_outer);
+        return B200MED_E_CUDA;
+    }
+    return B200MED_OK;
+}
+
+static int pick_block_n(long long N, int b_kmajor) {
+    if (N >= 256) return 256;
+    if (N > 64) return 128;
+    if (N > 32 || !b_kmajor) return 64;  // MN-major B tiles are built from 64-element atoms
+    return 32;
+}
+
+template <int BLOCK_N>
+static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &p, cudaStream_t st) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes),
+                               "cudaFuncSetAttribute(gemm_bf16_tcgen05)")) return e;
+        attr_set = true;
+    }
+    const long long tiles = (long long)p.tiles_m * p.tiles_n * p.split_k;
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+    return after_launch("gemm_bf16_tcgen05_kernel");
+}
+
+}  // namespace b200med
+
+using namespace b200med;
+
+extern "C" __attribute__((visibility("default"))) int b200med_has_tcgen05(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10 ? 1 : 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t b200med_gemm_bf16_ws_bytes(int64_t M, int64_t N, int64_t K, int32_t split_k) {
+    (void)K;
+    return split_k > 1 ? (int64_t)split_k * M * N * 4 : 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const void *A, const void *B, void *D, const float *bias, const void *mask,
+                                 int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd,
+                                 int32_t a_kmajor, int32_t b_kmajor, int32_t out_dtype, int32_t relu,
+                                 int32_t split_k, void *workspace, void *stream) {
+    B200MED_REQUIRE(M >= 1 && N >= 1 && K >= 1, "bad shape");
+    B200MED_REQUIRE(A && B && D, "null pointer");
+    B200MED_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "operand leading dimensions must be multiples of 8 elements (16 bytes)");
+    B200MED_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "operands must be 16-byte aligned");
+    B200MED_REQUIRE(out_dtype == B200MED_BF16 || out_dtype == B200MED_F32, "bad out dtype");
+    B200MED_REQUIRE(ldd >= N, "ldd < N");
+    if (!b200med_has_tcgen05()) { set_error("tcgen05 path needs a compute-capability 10.x device"); return B200MED_E_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const int block_n = pick_block_n(N, b_kmajor);
+    const int nkb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+    if (split_k < 1) split_k = 1;
+    if (split_k > nkb) split_k = nkb;
+    int kb_per = (nkb + split_k - 1) / split_k;
+    split_k = (nkb + kb_per - 1) / kb_per;
+    B200MED_REQUIRE(split_k == 1 || workspace, "split_k > 1 needs a workspace");
+
+    CUtensorMap ta, tb;
+    // K-major operand: rows x K, K contiguous -> box {64 k, rows}.  MN-major: K x rows -> box {64 rows, 64 k}.
+    if (int e = a_kmajor ? make_tmap(&ta, A, K, M, lda, BLOCK_K, BLOCK_M) : make_tmap(&ta, A, M, K, lda, 64, BLOCK_K)) return e;
+    if (int e = b_kmajor ? make_tmap(&tb, B, K, N, ldb, BLOCK_K, block_n) : make_tmap(&tb, B, N, K, ldb, 64, BLOCK_K)) return e;
+
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.ldd = ldd;
+    p.a_kmajor = a_kmajor; p.b_kmajor = b_kmajor;
+    p.out_f32 = out_dtype == B200MED_F32; p.relu = relu;
+    p.split_k = split_k; p.kb_per_split = kb_per;
+    p.tiles_m = (int)((M + BLOCK_M - 1) / BLOCK_M);
+    p.tiles_n = (int)((N + block_n - 1) / block_n);
+    p.bias = split_k > 1 ? nullptr : bias;
+    p.mask = split_k > 1 ? nullptr : reinterpret_cast<const __nv_bfloat16 *>(mask);
+    p.D = split_k > 1 ? workspace : D;
+
+    int e;
+    switch (block_n) {
+        case 256: e = launch_gemm_tc<256>(ta, tb, p, st); break;
+        case 128: e = launch_gemm_tc<128>(ta, tb, p, st); break;
+        case 64: e = launch_gemm_tc<64>(ta, tb, p, st); break;
+        default: e = launch_gemm_tc<32>(ta, tb, p, st); break;
+    }
+    if (e) return e;
+    if (split_k > 1) {
+        const long long total = M * N;
+        const long long want = (total + 255) / 256, cap = (long long)num_sms() * 8;
+        splitk_reduce_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
+            reinterpret_cast<const float *>(workspace), split_k, M, N, ldd, bias, relu,
+            reinterpret_cast<const __nv_bfloat16 *>(mask), D, out_dtype == B200MED_F32);
+        return after_launch("splitk_reduce_kernel");
+    }
+    return B200MED_OK;
+}

@@ -1,0 +1,717 @@
+"""Drop-in for the hot-path functions of the reference ``MED/modeling/modeling_utils.py``.
+
+Same function names, argument order and return tuples as the reference (file:line cited per
+function).  What changes is where the work happens:
+
+* batches are built on the device by the fused gather/standardise kernel (K1) from the resident frame
+  table -- no per-sample ``__getitem__``, no collate, no 42 MB host->device copy per batch;
+* the FeatureExtractor runs on the b200med GEMM kernels (K2);
+* loss, its gradient, predictions and confusion counts come from ONE fused kernel (K3); per-batch
+  losses / counts stay on the device and are read back ONCE per epoch (the reference syncs 1 + 10
+  (+3B) times per batch, modeling_utils.py:366, 377-392);
+* Adam is one fused kernel over a flat parameter buffer, after one gradient all-reduce when
+  data-parallel.
+
+Out of scope: Siamese loops, TransSVNet / COG loops, mlflow retrieval.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Optional
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.nn as nn
+
+from .. import metrics as M
+from .. import ops
+from ..dataset.CustomWindowDataset import DeviceWindowLoader
+from ..optim import FusedAdam
+from ..table import cuda_device
+from .models import CNN, LSTM, FeatureExtractor
+from .models_TCN import MultiStageModel
+
+ERROR_COLUMNS = {"No Error": 0, "Out_Of_View": 1, "Multiple_Attempts": 2, "Needle_Position": 3,
+                 "Out_Of_View_Multiple_Attempts": 4, "Multiple_Attempts_Needle_Position": 5,
+                 "global": -1, "all_errors": [0, 1, 2, 3, 4, 5]}
+
+
+# =====================================================================================================
+# criteria: callable like the torch modules the reference builds, backed by the fused K3 kernel
+# =====================================================================================================
+class _BCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, pos_weight):
+        r = ops.bce_logits(logits.detach().contiguous().float(), labels.contiguous().float(), pos_weight, want_probs=True)
+        ctx.save_for_backward(r["dlogits"])
+        ctx.shape = logits.shape
+        ctx.mark_non_differentiable(r["probs"], r["preds"], r["counts"])
+        return r["loss"].reshape(()), r["probs"], r["preds"], r["counts"]
+
+    @staticmethod
+    def backward(ctx, gl, *_):
+        (dl,) = ctx.saved_tensors
+        return (dl * gl).reshape(ctx.shape), None, None
+
+
+class _CEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, weight, mask, target_shift, reduction, pred_shift, pred_mask_mode, cm_classes):
+        r = ops.ce_logits(logits.detach().contiguous().float(), target.to(torch.int32).contiguous(), weight, mask,
+                          target_shift=target_shift, reduction=reduction, want_probs=True, pred_shift=pred_shift,
+                          pred_mask_mode=pred_mask_mode, cm_classes=cm_classes)
+        ctx.save_for_backward(r["dlogits"])
+        ctx.mark_non_differentiable(r["probs"], r["preds"], r["cm"])
+        return r["loss"].reshape(()), r["probs"], r["preds"], r["cm"]
+
+    @staticmethod
+    def backward(ctx, gl, *_):
+        (dl,) = ctx.saved_tensors
+        return dl * gl, None, None, None, None, None, None, None, None
+
+
+class _FrameCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, e):
+        r = ops.ce_frame(logits.detach().contiguous().float(), e.contiguous().float())
+        ctx.save_for_backward(r["dlogits"])
+        ctx.mark_non_differentiable(r["preds"], r["counts"])
+        return r["loss"].reshape(()), r["preds"], r["counts"]
+
+    @staticmethod
+    def backward(ctx, gl, *_):
+        (dl,) = ctx.saved_tensors
+        return dl * gl, None
+
+
+class FusedBCEWithLogitsLoss(nn.Module):
+    """``nn.BCEWithLogitsLoss(pos_weight=...)`` (mean reduction) on the K3 kernel.  After a call,
+    ``.last`` holds (probs, preds, counts[tn, fp, fn, tp]) of that batch."""
+
+    def __init__(self, pos_weight=None):
+        super().__init__()
+        self.pos_weight = None if pos_weight is None else float(pos_weight)
+        self.last = None
+
+    def forward(self, outputs, labels):
+        loss, probs, preds, counts = _BCEFn.apply(outputs, labels, 1.0 if self.pos_weight is None else self.pos_weight)
+        self.last = (probs, preds, counts)
+        return loss
+
+
+class FusedCrossEntropyLoss(nn.Module):
+    """``nn.CrossEntropyLoss(weight=..., reduction=...)`` on the K3 kernel for class-index targets
+    (window path) and for the frame path's two-column soft targets (see :func:`compute_loss`)."""
+
+    def __init__(self, weight=None, reduction="mean"):
+        super().__init__()
+        self.weight = None if weight is None else torch.as_tensor(weight, dtype=torch.float32)
+        self.reduction = reduction
+        self.last = None
+
+    def forward(self, outputs, labels, mask=None, target_shift=0, reduction=None, pred_shift=0, pred_mask_mode=0,
+                cm_classes=None):
+        w = None if self.weight is None else self.weight.to(outputs.device)
+        red = {"mean": 0, "sum": 2}.get(self.reduction, 0) if reduction is None else reduction
+        loss, probs, preds, cm = _CEFn.apply(outputs, labels, w, mask, target_shift, red, pred_shift, pred_mask_mode,
+                                             cm_classes or outputs.shape[1])
+        self.last = (probs, preds, cm)
+        return loss
+
+
+def _bce_pos_weight(criterion) -> float:
+    pw = getattr(criterion, "pos_weight", None)
+    return 1.0 if pw is None else float(pw)
+
+
+# =====================================================================================================
+# glue with the reference's signatures
+# =====================================================================================================
+def define_inputs(images, kinematics, feature_extractor, exp_kwargs: dict, device) -> torch.Tensor:
+    """Reference modeling_utils.py:19-84: FE on the image stream, concat with the kinematics on the
+    feature axis, permute to [B, F, W] (COG is out of scope, so the permute always happens)."""
+    dt = exp_kwargs["data_type"]
+    if dt == "multimodal":
+        feats = feature_extractor(images.to(device))
+        inputs = torch.cat((feats.float(), kinematics.to(device)), dim=2).permute(0, 2, 1)
+    elif dt == "kinematics":
+        inputs = kinematics.permute(0, 2, 1).to(device)
+    elif dt == "video":
+        images = images.to(device)
+        inputs = (images if exp_kwargs["video_dims"] == 2048 else feature_extractor(images).float()).permute(0, 2, 1)
+    else:
+        raise ValueError(f"Data type {dt} is not supported.")
+    if inputs.size(0) == 0:
+        raise ValueError("Inputs tensor is empty. Check the data loader and the inputs.")
+    return inputs
+
+
+def define_error_labels(e_labels: torch.Tensor, exp_kwargs: dict) -> torch.Tensor:
+    """Reference modeling_utils.py:137-191."""
+    if "error_type" not in exp_kwargs:
+        raise ValueError("error_type must be defined in exp_kwargs.")
+    if exp_kwargs["error_type"] not in ERROR_COLUMNS:
+        raise ValueError(f"Error type {exp_kwargs['error_type']} is not supported. Supported error types are: "
+                         f"{list(ERROR_COLUMNS.keys())}.")
+    col = ERROR_COLUMNS[exp_kwargs["error_type"]]
+    if exp_kwargs["dataset_type"] == "window":
+        return e_labels[:, col]
+    if exp_kwargs["dataset_type"] == "frame":
+        return e_labels[:, :, col]
+    raise ValueError(f"Dataset type {exp_kwargs['dataset_type']} is not supported.")
+
+
+def instantiate_model(exp_kwargs: dict, in_features: int, window_size: int, device=None) -> nn.Module:
+    """Reference modeling_utils.py:3043-3117 (heads on the hot path only)."""
+    name = exp_kwargs["model_name"]
+    n_out = exp_kwargs["out_features"] if "out_features" in exp_kwargs else 1
+    if name == "SimpleCNN":
+        return CNN(in_features=in_features, window_size=window_size, n_classes=n_out)
+    if name == "SimpleLSTM":
+        return LSTM(in_features=in_features, window_size=window_size, hidden_size=exp_kwargs["hidden_size"],
+                    num_layers=exp_kwargs["num_layers"], n_classes=n_out)
+    if name == "TeCNo":
+        return MultiStageModel(exp_kwargs["mstcn_stages"], exp_kwargs["mstcn_layers"], exp_kwargs["mstcn_f_maps"],
+                               exp_kwargs["mstcn_f_dim"], exp_kwargs["out_features"], exp_kwargs["mstcn_causal_conv"])
+    raise ValueError(f"Model {name} is not supported.")
+
+
+def define_model_objects(exp_kwargs: dict, in_features_dict: dict, device, class_counts: tuple, window_size: int = 0):
+    """Reference modeling_utils.py:194-262 -> (feature_extractor, model, criterion, optimizer, scheduler).
+
+    Seed 42, head built BEFORE the feature extractor, both on the host RNG (that order fixes the
+    weights bit for bit), then moved to the GPU.  ``exp_kwargs['precision']``
+    (optional, absent in the reference) selects "fp32" (default, 1e-5 parity) or "bf16" (tcgen05)."""
+    device = torch.device(device) if device is not None else cuda_device()
+    if device.type != "cuda":
+        raise RuntimeError("b200med runs on CUDA devices only (no CPU fallback)")
+    precision = exp_kwargs.get("precision", "fp32")
+    if precision == "fp32":      # TF32 convolutions / matmuls cannot hold 1e-5
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(42)
+    model = instantiate_model(exp_kwargs, in_features_dict[exp_kwargs["data_type"]], window_size, device).to(device)
+    if exp_kwargs["data_type"] != "kinematics":
+        feature_extractor = FeatureExtractor(input_dim=2048, output_dim=exp_kwargs["video_dims"], hidden_dims=[512, 256],
+                                             precision=precision).to(device)
+        params = list(feature_extractor.parameters()) + list(model.parameters())
+    else:
+        feature_extractor, params = None, list(model.parameters())
+    optimizer = FusedAdam(params, lr=exp_kwargs["lr"], weight_decay=exp_kwargs["weight_decay"]).prepare()
+    print("Number of parameters to optimize:", sum(p.numel() for p in params if p.requires_grad))
+
+    criterion = None
+    if exp_kwargs["pos_weight"]:
+        if exp_kwargs["error_type"] == "global":
+            pw = torch.tensor(float(class_counts[0]) / float(class_counts[1]), dtype=torch.float32) \
+                if not torch.is_tensor(class_counts[0]) else (class_counts[0] / class_counts[1]).float()
+            criterion = FusedBCEWithLogitsLoss(pos_weight=float(pw))
+        elif exp_kwargs["error_type"] == "all_errors":
+            criterion = FusedCrossEntropyLoss(weight=torch.tensor([float(c) for c in class_counts], dtype=torch.float32))
+    elif exp_kwargs["dataset_type"] == "window":
+        if exp_kwargs["error_type"] == "global":
+            criterion = FusedBCEWithLogitsLoss()
+        elif exp_kwargs["error_type"] == "all_errors":
+            criterion = FusedCrossEntropyLoss()
+    elif exp_kwargs["dataset_type"] == "frame":
+        criterion = FusedCrossEntropyLoss(reduction="none" if exp_kwargs["error_type"] == "sequential" else "mean")
+
+    scheduler = (torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=exp_kwargs["n_epochs"], eta_min=1e-6)
+                 if exp_kwargs["lr_scheduler"] else None)
+    return feature_extractor, model, criterion, optimizer, scheduler
+
+
+def compute_loss(outputs: torch.Tensor, e_labels: torch.Tensor, criterion, dataset_type: str):
+    """Reference modeling_utils.py:265-297 -> (loss, outputs).  Window: squeeze dim 1 and apply the
+    criterion.  Frame: CE of every stage against the soft targets [1-e, e], mean over stages -- one
+    K3 launch for all stages."""
+    if dataset_type == "window":
+        if outputs.dim() > 1 and outputs.size(1) == 1:
+            outputs = outputs.squeeze(1)
+        if isinstance(criterion, (FusedBCEWithLogitsLoss, nn.BCEWithLogitsLoss)):
+            if not isinstance(criterion, FusedBCEWithLogitsLoss):
+                criterion = FusedBCEWithLogitsLoss(_bce_pos_weight(criterion))
+            return criterion(outputs, e_labels), outputs
+        if isinstance(criterion, nn.CrossEntropyLoss):
+            criterion = FusedCrossEntropyLoss(criterion.weight, criterion.reduction)
+        return criterion(outputs, e_labels.long()), outputs
+    if dataset_type == "frame":
+        loss, preds, counts = _FrameCEFn.apply(outputs, e_labels.reshape(-1).to(outputs.device))
+        if hasattr(criterion, "last"):
+            criterion.last = (None, preds, counts)
+        compute_loss.last_frame = (preds, counts)
+        return loss, outputs
+    raise ValueError(f"Dataset type {dataset_type} is not supported.")
+
+
+# =====================================================================================================
+# epoch bookkeeping: everything stays on the device until the epoch ends
+# =====================================================================================================
+class _EpochLog:
+    def __init__(self):
+        self.losses, self.counts, self.extra = [], [], {}
+
+    def add(self, loss, counts=None, **kw):
+        self.losses.append(loss.detach().reshape(1))
+        if counts is not None:
+            self.counts.append(counts.reshape(1, -1))
+        for k, v in kw.items():
+            self.extra.setdefault(k, []).append(v)
+
+    def losses_host(self) -> np.ndarray:
+        return torch.cat(self.losses).cpu().numpy().astype(np.float64) if self.losses else np.zeros(0)
+
+    def counts_host(self) -> np.ndarray:
+        return torch.cat(self.counts).cpu().numpy() if self.counts else np.zeros((0, 4), dtype=np.int64)
+
+    def cat_host(self, key) -> np.ndarray:
+        xs = self.extra.get(key, [])
+        return torch.cat([x.reshape(-1) for x in xs]).cpu().numpy() if xs else np.zeros(0)
+
+
+def _batch_scores(counts4: np.ndarray):
+    """Per-batch (f1, f1_weighted, acc, jaccard, sklearn-style cm contribution) from (tn, fp, fn, tp)."""
+    cm = np.asarray(counts4, dtype=np.int64).reshape(2, 2)
+    small = M.sklearn_cm(cm)
+    # reference quirk: `train_cm += confusion_matrix(...)` broadcasts a 1x1 matrix over the 2x2 accumulator
+    contrib = cm if small.shape == (2, 2) else np.full((2, 2), int(small.sum()), dtype=np.int64)
+    return M.f1_binary(cm), M.f1_avg(cm, "weighted"), M.accuracy(cm), M.jaccard_binary(cm), contrib
+
+
+def _set_train(model, feature_extractor, exp_kwargs, train: bool):
+    mods = [model] if exp_kwargs["data_type"] == "kinematics" else [feature_extractor, model]
+    for m in mods:
+        m.train(train)
+
+
+def _allreduce_grads(optimizer):
+    """Data-parallel exchange: ONE sum all-reduce of the flat gradient buffer."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(optimizer.flat_grad, op=dist.ReduceOp.SUM)
+        optimizer.grad_scale = 1.0 / dist.get_world_size()
+
+
+def _window_batches(loader, exp_kwargs, device, image_dtype):
+    """Yield (images, kinematics, g, e7, host_idx) per batch.  DeviceWindowLoader: one K1 launch per
+    batch straight from the resident table; anything else: the reference's tuple protocol."""
+    if isinstance(loader, DeviceWindowLoader):
+        ds = loader.dataset
+        need_img = exp_kwargs["data_type"] != "kinematics"
+        for idx in loader.index_batches():
+            if idx.numel() == 0:
+                continue
+            didx = idx.pin_memory().to(device, non_blocking=True)      # pinned host -> device, 8 B per window
+            images, kin = ds.gather_batch(didx, image_dtype=image_dtype if need_img else torch.float32,
+                                          exact=image_dtype == torch.float32)
+            yield images, kin, ds.g_labels_data.index_select(0, didx), ds.e_labels_data.index_select(0, didx), idx
+    else:
+        for batch in loader:
+            images, kin, g, e7, subject = batch[:5]
+            yield images.to(device), kin.to(device), g.to(device), e7.to(device), subject
+
+
+def _subjects(loader, idx):
+    if isinstance(loader, DeviceWindowLoader):
+        return loader.dataset.subjects_of(idx.tolist())
+    return list(idx)
+
+
+def _image_dtype(feature_extractor):
+    return torch.bfloat16 if getattr(feature_extractor, "precision", "fp32") == "bf16" else torch.float32
+
+
+# =====================================================================================================
+# train / validate: binary ("global") window and frame paths
+# =====================================================================================================
+def train_single_epoch(model, feature_extractor, train_dataloader, criterion, optimizer, scheduler, device, exp_kwargs):
+    """Reference modeling_utils.py:300-407.  Returns (loss, f1, f1_weighted, acc, jaccard, cm) -- the MEAN
+    over batches of per-batch scores and the summed confusion matrix (:398-402) -- plus
+    (probs, preds, labels, subjects) lists when ``return_train_preds``."""
+    device = torch.device(device)
+    _set_train(model, feature_extractor, exp_kwargs, True)
+    log = _EpochLog()
+    subjects_all = []
+    frame = exp_kwargs["dataset_type"] == "frame"
+    batches = _frame_batches(train_dataloader, device) if frame else \
+        _window_batches(train_dataloader, exp_kwargs, device, _image_dtype(feature_extractor))
+    for images, kin, g, e7, who in batches:
+        y = define_error_labels(e7, exp_kwargs).float()
+        inputs = define_inputs(images, kin, feature_extractor, exp_kwargs, device)
+        outputs = model(inputs)
+        loss, outputs = compute_loss(outputs, y, criterion, exp_kwargs["dataset_type"])
+        optimizer.zero_grad()
+        loss.backward()
+        _allreduce_grads(optimizer)
+        optimizer.step()
+        if exp_kwargs.get("host_sync") == "step":
+            loss.item()      # the reference's per-batch `train_loss += loss.item()` (:366); default: one read per epoch
+        if frame:
+            preds, counts = compute_loss.last_frame
+            probs = None
+        else:
+            probs, preds, counts = criterion.last if hasattr(criterion, "last") and criterion.last else _rescore(outputs, y)
+        if exp_kwargs["return_train_preds"]:
+            log.add(loss, counts, preds=preds, labels=y.reshape(-1), **({} if probs is None else {"probs": probs}))
+            subjects_all += _subjects(train_dataloader, who) if not frame else [who] * int(preds.numel())
+        else:
+            log.add(loss, counts)
+    if scheduler is not None:
+        scheduler.step()
+    n_batches = max(len(log.losses), 1)
+    losses, counts = log.losses_host(), log.counts_host()
+    tot = np.zeros(4)
+    cm = np.zeros((2, 2), dtype=int)
+    for c in counts:
+        f1, f1w, acc, jac, contrib = _batch_scores(c)
+        tot += (f1, f1w, acc, jac)
+        cm += contrib
+    res = (float(losses.sum() / n_batches), *(tot / n_batches).tolist(), cm)
+    if exp_kwargs["return_train_preds"]:
+        return (*res, log.cat_host("probs").tolist(), log.cat_host("preds").tolist(), log.cat_host("labels").tolist(),
+                subjects_all)
+    return res
+
+
+def _rescore(outputs, y):
+    r = ops.bce_logits(outputs.detach().contiguous().float(), y.contiguous().float(), want_grad=False, want_probs=True)
+    return r["probs"], r["preds"], r["counts"]
+
+
+def _frame_batches(loader, device):
+    """One video per step (reference train_frame.ipynb: DataLoader(batch_size=1))."""
+    for batch in loader:
+        images, kin, g, e7, subject = batch[:5]
+        who = subject[0] if isinstance(subject, (tuple, list)) else subject
+        yield images.to(device), kin.to(device), g.to(device), e7.to(device), who
+
+
+def validate_single_epoch(model, feature_extractor, test_dataloader, criterion, device, exp_kwargs):
+    """Reference modeling_utils.py:688-790 -> 13-tuple (loss, f1, f1_weighted, acc, jaccard, cm,
+    inference_rate, preds, probs, labels, labels_specific, gesture_labels, subjects); scores are POOLED
+    over all samples (:782-786)."""
+    device = torch.device(device)
+    _set_train(model, feature_extractor, exp_kwargs, False)
+    log = _EpochLog()
+    frame = exp_kwargs["dataset_type"] == "frame"
+    subjects_all, labels_all = [], []
+    fwd_ms = 0.0
+    with torch.no_grad():
+        batches = _frame_batches(test_dataloader, device) if frame else \
+            _window_batches(test_dataloader, exp_kwargs, device, _image_dtype(feature_extractor))
+        for images, kin, g, e7, who in batches:
+            y = define_error_labels(e7, exp_kwargs).float()
+            inputs = define_inputs(images, kin, feature_extractor, exp_kwargs, device)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            outputs = model(inputs)
+            t1.record()
+            if frame:
+                r = ops.ce_frame(outputs.contiguous().float(), y.reshape(-1), want_grad=False)
+                preds, probs = r["preds"], None
+                e_rows = e7[0]
+                subjects_all += [(who,)] * int(preds.numel())
+            else:
+                outputs = outputs.squeeze(1) if outputs.dim() > 1 and outputs.size(1) == 1 else outputs
+                r = ops.bce_logits(outputs.contiguous().float(), y.contiguous(), _bce_pos_weight(criterion), want_grad=False,
+                                   want_probs=True)
+                preds, probs = r["preds"], r["probs"]
+                e_rows = e7
+                subjects_all += _subjects(test_dataloader, who)
+            labels_all.append(e_rows)
+            log.add(r["loss"], r["counts"], preds=preds, labels=y.reshape(-1), gest=g.reshape(-1).float(),
+                    **({} if probs is None else {"probs": probs}))
+            last_events = (t0, t1)
+    if log.losses:
+        torch.cuda.synchronize()
+        fwd_ms = last_events[0].elapsed_time(last_events[1])   # device time of the LAST batch's forward (:779)
+    n_batches = max(len(log.losses), 1)
+    cm = log.counts_host().sum(0).reshape(2, 2) if log.counts else np.zeros((2, 2), dtype=np.int64)
+    preds = log.cat_host("preds").tolist()
+    probs = log.cat_host("probs").tolist() if not frame else [None] * len(preds)
+    e_all = torch.cat(labels_all).cpu() if labels_all else torch.zeros(0, 7)
+    return (float(log.losses_host().sum() / n_batches), M.f1_binary(cm), M.f1_avg(cm, "weighted"), M.accuracy(cm),
+            M.jaccard_binary(cm), M.sklearn_cm(cm), fwd_ms, preds, probs, [row for row in e_all],
+            log.cat_host("labels").tolist(), log.cat_host("gest").tolist(), subjects_all)
+
+
+# =====================================================================================================
+# error-specific (6-class) loops
+# =====================================================================================================
+def _class_targets(e7, exp_kwargs):
+    spec = define_error_labels(e7, exp_kwargs).float()
+    return torch.argmax(spec, dim=2 if exp_kwargs["dataset_type"] == "frame" else 1).view(-1)
+
+
+def _es_summary(cm6: np.ndarray):
+    cmb = M.binarise(cm6)
+    return (M.f1_binary(cmb), M.f1_avg(cm6, "macro"), M.accuracy(cmb), M.accuracy(cm6), M.jaccard_binary(cmb),
+            M.jaccard_avg(cm6, "macro"), M.sklearn_cm(cmb), M.sklearn_cm(cm6))
+
+
+def train_single_epoch_ES(model, feature_extractor, train_dataloader, criterion, optimizer, scheduler, device, exp_kwargs):
+    """Reference modeling_utils.py:410-539 (window path).  The committed code hands CrossEntropyLoss a
+    float class index and raises on CPU/CUDA; the index is used as ``long`` here, which is
+    what the call means.  Scores are pooled over the epoch (:519-528)."""
+    device = torch.device(device)
+    _set_train(model, feature_extractor, exp_kwargs, True)
+    crit = criterion if isinstance(criterion, FusedCrossEntropyLoss) else FusedCrossEntropyLoss(
+        getattr(criterion, "weight", None), getattr(criterion, "reduction", "mean"))
+    log = _EpochLog()
+    C = None
+    cm = None
+    for images, kin, g, e7, who in _window_batches(train_dataloader, exp_kwargs, device, _image_dtype(feature_extractor)):
+        y = _class_targets(e7, exp_kwargs)
+        outputs = model(define_inputs(images, kin, feature_extractor, exp_kwargs, device))
+        C = outputs.shape[1]
+        loss = crit(outputs, y, cm_classes=max(C, 6))
+        optimizer.zero_grad()
+        loss.backward()
+        _allreduce_grads(optimizer)
+        optimizer.step()
+        cm = crit.last[2] if cm is None else cm + crit.last[2]
+        log.add(loss, None, preds=crit.last[1], labels=y)
+    if scheduler is not None:
+        scheduler.step()
+    n_batches = max(len(log.losses), 1)
+    cm6 = cm.cpu().numpy() if cm is not None else np.zeros((6, 6), dtype=np.int64)
+    res = (float(log.losses_host().sum()) / n_batches, *_es_summary(cm6))
+    if exp_kwargs["return_train_preds"]:
+        preds, labels = log.cat_host("preds").astype(int).tolist(), log.cat_host("labels").astype(int).tolist()
+        return (*res, [], preds, labels, [int(v != 0) for v in labels], [int(v != 0) for v in preds])
+    return res
+
+
+def validate_single_epoch_ES(model, feature_extractor, test_dataloader, criterion, device, exp_kwargs):
+    """Reference modeling_utils.py:793-904 -> 17-tuple."""
+    device = torch.device(device)
+    _set_train(model, feature_extractor, exp_kwargs, False)
+    crit = criterion if isinstance(criterion, FusedCrossEntropyLoss) else FusedCrossEntropyLoss(
+        getattr(criterion, "weight", None), getattr(criterion, "reduction", "mean"))
+    log = _EpochLog()
+    subjects_all, cm, fwd_ms, last_events = [], None, 0.0, None
+    with torch.no_grad():
+        for images, kin, g, e7, who in _window_batches(test_dataloader, exp_kwargs, device, _image_dtype(feature_extractor)):
+            y = _class_targets(e7, exp_kwargs)
+            inputs = define_inputs(images, kin, feature_extractor, exp_kwargs, device)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            outputs = model(inputs)
+            t1.record()
+            last_events = (t0, t1)
+            w = None if crit.weight is None else crit.weight.to(device)
+            r = ops.ce_logits(outputs.contiguous().float(), y.to(torch.int32), w, None, want_grad=False, want_probs=True,
+                              cm_classes=max(outputs.shape[1], 6))
+            cm = r["cm"] if cm is None else cm + r["cm"]
+            log.add(r["loss"], None, preds=r["preds"], labels=y, probs=r["probs"][:, 1], gest=g.reshape(-1).float())
+            subjects_all += _subjects(test_dataloader, who)
+    if last_events is not None:
+        torch.cuda.synchronize()
+        fwd_ms = last_events[0].elapsed_time(last_events[1])
+    n_batches = max(len(log.losses), 1)
+    cm6 = cm.cpu().numpy() if cm is not None else np.zeros((6, 6), dtype=np.int64)
+    preds, labels = log.cat_host("preds").astype(int).tolist(), log.cat_host("labels").astype(int).tolist()
+    return (float(log.losses_host().sum()) / n_batches, *_es_summary(cm6), fwd_ms, log.cat_host("probs").tolist(), preds,
+            labels, [int(v != 0) for v in labels], [int(v != 0) for v in preds], log.cat_host("gest").tolist(), subjects_all)
+
+
+# =====================================================================================================
+# cascade ("sequential") loops: a frozen binary model gates a 5-class error-type model
+# =====================================================================================================
+def _seq_summary(cm_all: np.ndarray, cm_spec: np.ndarray):
+    return (M.f1_avg(cm_all, "macro"), M.f1_avg(cm_spec, "macro"), M.f1_avg(cm_spec, "weighted"), M.accuracy(cm_all),
+            M.accuracy(cm_spec), M.jaccard_avg(cm_all, "macro"), M.jaccard_avg(cm_spec, "macro"),
+            M.jaccard_avg(cm_spec, "weighted"), M.sklearn_cm(cm_all), M.sklearn_cm(cm_spec))
+
+
+def train_single_epoch_Sequential(model, feature_extractor, train_dataloader, criterion, optimizer, device, scheduler,
+                                  exp_kwargs):
+    """Reference modeling_utils.py:543-684 -> 11-tuple.  Labels 0..5, mask = (label != 0), CE on
+    label-1 for the masked rows, sum / mask.sum().  The committed code feeds target -1 for unmasked
+    rows (raises off-MPS); those rows carry zero weight, so the target is clamped to 0."""
+    device = torch.device(device)
+    _set_train(model, feature_extractor, exp_kwargs, True)
+    crit = FusedCrossEntropyLoss()
+    log = _EpochLog()
+    cm = None
+    for images, kin, g, e7, who in _window_batches(train_dataloader, exp_kwargs, device, _image_dtype(feature_extractor)):
+        y = _class_targets(e7, exp_kwargs)
+        mask = (y != 0).float()
+        outputs = model(define_inputs(images, kin, feature_extractor, exp_kwargs, device))
+        loss = crit(outputs, y, mask=mask, target_shift=-1, reduction=1, pred_shift=1, pred_mask_mode=1, cm_classes=6)
+        optimizer.zero_grad()
+        loss.backward()
+        _allreduce_grads(optimizer)
+        optimizer.step()
+        cm = crit.last[2] if cm is None else cm + crit.last[2]
+        log.add(loss, None)
+    if scheduler is not None:
+        scheduler.step()
+    n_batches = max(len(log.losses), 1)
+    cm_all = cm.cpu().numpy() if cm is not None else np.zeros((6, 6), dtype=np.int64)
+    cm_spec = cm_all.copy()
+    cm_spec[0, :] = 0          # error-specific lists hold only the rows whose true label is an error (:658-662)
+    return (float(log.losses_host().sum()) / n_batches, *_seq_summary(cm_all, cm_spec))
+
+
+def validate_single_epoch_Sequential(model, feature_extractor, binary_model, binary_feature_extractor, test_dataloader,
+                                     device, exp_kwargs):
+    """Reference modeling_utils.py:907-1053 -> 19-tuple.  The binary model's RAW logit is thresholded
+    at 0.5 (:979-980); the loss keeps the reference's [B]*[B,1] broadcast: sum of all per-sample losses if
+    any window fired, else their mean (:989-996)."""
+    device = torch.device(device)
+    for m in (model, feature_extractor, binary_model, binary_feature_extractor):
+        m.eval()
+    log = _EpochLog()
+    cm_all = cm_spec = None
+    total_ms, last_w = 0.0, 1
+    with torch.no_grad():
+        for images, kin, g, e7, who in _window_batches(test_dataloader, exp_kwargs, device, _image_dtype(feature_extractor)):
+            y = _class_targets(e7, exp_kwargs)
+            fired = (binary_model(define_inputs(images, kin, binary_feature_extractor, exp_kwargs, device)) > 0.5).float().reshape(-1)
+            inputs = define_inputs(images, kin, feature_extractor, exp_kwargs, device)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            outputs = model(inputs)
+            t1.record()
+            r = ops.ce_logits(outputs.contiguous().float(), y.to(torch.int32), None, fired.contiguous(), target_shift=-1,
+                              reduction=3, want_grad=False, want_probs=True, pred_shift=1, pred_mask_mode=2, cm_classes=6)
+            cm_all = r["cm"] if cm_all is None else cm_all + r["cm"]
+            sel = (fired > 0) & (y > 0)
+            spec = ops.confusion(y.to(torch.int32)[sel].contiguous(), r["preds"][sel].contiguous(), 6)
+            cm_spec = spec if cm_spec is None else cm_spec + spec
+            log.add(r["loss"], None, preds=r["preds"], labels=y, sel=sel.float(), probs=r["probs"])
+            torch.cuda.synchronize()
+            total_ms += t0.elapsed_time(t1)
+            last_w = images.shape[1]
+    n_batches = max(len(log.losses), 1)
+    z = np.zeros((6, 6), dtype=np.int64)
+    cm_all = cm_all.cpu().numpy() if cm_all is not None else z
+    cm_spec = cm_spec.cpu().numpy() if cm_spec is not None else z
+    preds, labels = log.cat_host("preds").astype(int), log.cat_host("labels").astype(int)
+    sel = log.cat_host("sel") > 0
+    probs = log.cat_host("probs").reshape(len(preds), -1) if len(preds) else np.zeros((0, 5))
+    return (float(log.losses_host().sum()) / n_batches, *_seq_summary(cm_all, cm_spec), total_ms / last_w,
+            preds.tolist(), preds[sel].tolist(), probs[sel].tolist(), labels.tolist(), labels[sel].tolist(), [], [])
+
+
+# =====================================================================================================
+# frame -> window post-processing, fold aggregation, checkpoint IO
+# =====================================================================================================
+def window_predictions(predictions, e_labels, gestures, subjects, window_size=10, stride=6, binary=True):
+    """Reference modeling_utils.py:2695-2777: re-window frame-level predictions with the walk of
+    ``window_data`` (K0 kernel), window value = mean of the frame predictions thresholded ``>= 0.5`` or
+    rounded half-to-even (vote kernel).  Subjects are visited in SORTED order (``np.unique``, :2722)."""
+    dev = cuda_device()
+    subjects = np.asarray(subjects)
+    predictions, e_labels, gestures = np.asarray(predictions), np.asarray(e_labels), np.asarray(gestures)
+    uniq, inv = np.unique(subjects, return_inverse=True)
+    order = np.argsort(inv, kind="stable")
+    counts = np.bincount(inv, minlength=len(uniq))
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)).to(dev)
+    g = torch.from_numpy(gestures[order].astype(np.float32)).to(dev)
+    r = ops.window_index(g, offsets, window_size, stride)
+    starts = r["starts"]
+    votes = ops.window_vote(torch.from_numpy(predictions[order].astype(np.float32)).to(dev), starts, window_size, binary)
+    first = order[starts.cpu().numpy()]
+    pw = votes.cpu().to(torch.float32 if binary else torch.float64).reshape(-1, 1)
+    ew = torch.tensor(e_labels[first]).reshape(-1, 1)
+    gw = torch.tensor(gestures[first]).reshape(-1, 1)
+    return pw, ew, gw, pd.DataFrame([str(s) for s in subjects[first]], columns=["subject"])
+
+
+def frame2window(outs, test_all_preds, test_all_labels, test_all_gest_labels, test_all_subjects, window_size=10, stride=6,
+                 binary=True):
+    """Reference modeling_utils.py:2780-2825."""
+    wp, wl, wg, ws = {}, {}, {}, {}
+    for out in outs:
+        if out in test_all_preds:
+            wp[out], wl[out], wg[out], ws[out] = window_predictions(
+                np.array(test_all_preds[out]), np.array(test_all_labels[out]), np.array(test_all_gest_labels[out]),
+                np.array(test_all_subjects[out]), window_size=window_size, stride=stride, binary=binary)
+    return wp, wl, wg, ws
+
+
+def _pooled_cm(labels: np.ndarray, preds: np.ndarray, n_classes: int) -> np.ndarray:
+    dev = cuda_device()
+    t = torch.from_numpy(labels.astype(np.int32)).to(dev)
+    p = torch.from_numpy(preds.astype(np.int32)).to(dev)
+    return ops.confusion(t, p, n_classes).cpu().numpy()
+
+
+def _weighted_mean_std(values, weights):
+    values = np.asarray(values, dtype=np.float64)
+    mean = np.average(values, weights=weights)
+    return mean, np.average((values - mean) ** 2, weights=weights) ** 0.5
+
+
+def compute_window_metrics(outs, test_all_preds, test_all_labels, test_all_gest_labels, test_all_subjects, window_size=10,
+                           stride=6, binary=True):
+    """Reference modeling_utils.py:2828-2917 -> (summary DataFrame, summed confusion matrix)."""
+    wp, wl, wg, ws = frame2window(outs, test_all_preds, test_all_labels, test_all_gest_labels, test_all_subjects,
+                                  window_size=window_size, stride=stride, binary=binary)
+    f1s, accs, jacs, cms, samples = [], [], [], [], []
+    for out in wp:
+        preds, labels = wp[out].numpy().flatten(), wl[out].numpy().flatten()
+        cm = _pooled_cm(labels, preds, 2 if binary else 6)
+        f1s.append(M.f1_binary(cm) if binary else M.f1_avg(cm, "weighted"))
+        jacs.append(M.jaccard_binary(cm) if binary else M.jaccard_avg(cm, "weighted"))
+        accs.append(M.accuracy(cm))
+        cms.append(M.sklearn_cm(cm))
+        samples.append(len(wp[out]))
+    (mf, sf), (ma, sa), (mj, sj) = (_weighted_mean_std(v, samples) for v in (f1s, accs, jacs))
+    summary_df = pd.DataFrame({"F1": [f"{mf:.3f} ± {sf:.3f}"], "Accuracy": [f"{ma:.3f} ± {sa:.3f}"],
+                               "Jaccard": [f"{mj:.3f} ± {sj:.3f}"]}, index=["Windowed Metrics"])
+    return summary_df, np.sum(np.array(cms), axis=0)
+
+
+def create_summary_df(LOSO_f1_train, LOSO_f1_test, LOSO_acc_train, LOSO_acc_test, LOSO_jaccard_train, LOSO_jaccard_test,
+                      samples_train, samples_test, inference_rates, train_times) -> pd.DataFrame:
+    """Reference modeling_utils.py:2979-3025: sample-weighted mean ± std across folds."""
+    df = pd.DataFrame(index=["Train", "Test"], columns=["F1", "Accuracy", "Jaccard", "Train Time", "Inference Rate"])
+    cells = {("Train", "F1"): (LOSO_f1_train, samples_train), ("Test", "F1"): (LOSO_f1_test, samples_test),
+             ("Train", "Accuracy"): (LOSO_acc_train, samples_train), ("Test", "Accuracy"): (LOSO_acc_test, samples_test),
+             ("Train", "Jaccard"): (LOSO_jaccard_train, samples_train), ("Test", "Jaccard"): (LOSO_jaccard_test, samples_test)}
+    for (row, col), (vals, w) in cells.items():
+        mean, std = _weighted_mean_std(vals, w)
+        df.loc[row, col] = f"{mean:.3f} ± {std:.3f}"
+    df.loc["Train", "Train Time"] = f"{np.mean(train_times):.2f} ± {np.std(train_times):.2f}"
+    df.loc["Test", "Train Time"] = np.nan
+    df.loc["Train", "Inference Rate"] = np.nan
+    df.loc["Test", "Inference Rate"] = f"{np.mean(inference_rates):.2f} ± {np.std(inference_rates):.2f}"
+    return df
+
+
+def soft_vote_ensemble(probs_a, probs_b, labels):
+    """Soft vote of two window models + scores (reference ensemble.ipynb cell 6): returns
+    (preds, acc, f1, jaccard, cm)."""
+    dev = cuda_device()
+    to = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32)).to(dev)
+    preds, counts = ops.soft_vote(to(probs_a), to(probs_b), to(labels))
+    cm = counts.cpu().numpy().reshape(2, 2)
+    return preds.cpu().numpy().astype(int), M.accuracy(cm), M.f1_binary(cm), M.jaccard_binary(cm), cm
+
+
+def cascade_ensemble(binary_preds, multiclass_preds):
+    """Cascade of a binary and a multi-class model (reference ensemble.ipynb cell 15, lines 53-63)."""
+    dev = cuda_device()
+    to = lambda x: torch.as_tensor(np.asarray(x, dtype=np.int32)).to(dev)
+    return ops.cascade(to(binary_preds), to(multiclass_preds)).cpu().numpy()
+
+
+def save_model(best_model: dict, model_path: str) -> None:
+    """Reference modeling_utils.py:3028-3040: ``{'feature_extractor': state_dict, 'model': state_dict}``."""
+    torch.save({"feature_extractor": best_model["feature_extractor"], "model": best_model["model"]}, model_path)
+    print(f"Model saved to {model_path}")
+
+
+def load_model_local(model_path: str, feature_extractor, model, device=None):
+    """Counterpart of the reference's load_model_local (modeling_utils.py:2241): load a
+    ``save_model`` file (from the reference or from this package -- the keys are the same)."""
+    blob = torch.load(model_path, map_location="cpu")
+    if feature_extractor is not None and blob.get("feature_extractor") is not None:
+        feature_extractor.load_state_dict(blob["feature_extractor"])
+    model.load_state_dict(blob["model"])
+    return feature_extractor, model

@@ -1,0 +1,191 @@
+"""Drop-in for the reference ``MED/modeling/models.py`` (FeatureExtractor, CNN, LSTM).
+
+Same constructor signatures, ``forward`` contracts, ``.name`` attributes, ``state_dict`` keys and
+seed-42 initialisation order as the reference (models.py:6-220), so checkpoints interchange.
+
+* ``FeatureExtractor`` -- ~98 % (CNN head) / ~75 % (LSTM head) of the model FLOPs -- runs on the
+  hand-written kernels of libb200med.so: fp32 SIMT GEMMs in ``precision="fp32"`` (1e-5 parity mode)
+  or bf16 tcgen05/TMEM GEMMs in ``precision="bf16"`` (2e-2 throughput mode), forward and backward.
+* ``CNN`` / ``LSTM`` heads (0.36 / 11 MFLOP per window) keep stock torch layers on the GPU in this
+  round; their fused sm_100a kernels are SURVEY section 8f rows 2-3 ("next").
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+
+def _split_k(tiles: int, k_blocks: int) -> int:
+    """Enough K-splits to put ~2 CTAs of work on every SM, at least 8 k-blocks per split."""
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return max(1, min(want, k_blocks // 8 if k_blocks >= 16 else 1))
+
+
+class _MLPFunction(torch.autograd.Function):
+    """y = L_n(...relu(L_1(x))) with every product on the b200med GEMM kernels (K2)."""
+
+    @staticmethod
+    def forward(ctx, x, precision, *params):
+        weights, biases = params[0::2], params[1::2]
+        n = len(weights)
+        ctx.precision, ctx.n = precision, n
+        M = x.shape[0]
+        if precision == "fp32":
+            h = x if x.dtype == torch.float32 else x.float()
+            acts = [h.contiguous()]
+            for i in range(n):
+                acts.append(ops.linear_fwd_f32(acts[-1], weights[i], biases[i], relu=i < n - 1))
+            ctx.save_for_backward(*acts[:-1], *weights)
+            return acts[-1]
+        # bf16: activations and weight copies in bf16, fp32 accumulation in TMEM, fp32 final output
+        h = x if x.dtype == torch.bfloat16 else ops.to_bf16(x.contiguous())
+        wb = [ops.to_bf16(w.detach().contiguous()) for w in weights]
+        acts = [h.contiguous()]
+        for i in range(n):
+            N, K = weights[i].shape
+            last = i == n - 1
+            acts.append(ops.gemm_bf16(acts[-1], wb[i], M, N, K, True, True, bias=biases[i], relu=not last,
+                                      out_dtype=torch.float32 if last else torch.bfloat16))
+        ctx.save_for_backward(*acts[:-1], *wb)
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, dy):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        acts, weights = saved[:n], saved[n:]
+        grads = [None] * (2 * n)
+        need_dx = ctx.needs_input_grad[0]
+        M = dy.shape[0]
+        if ctx.precision == "fp32":
+            g = dy.contiguous().float()
+            for i in reversed(range(n)):
+                grads[2 * i], grads[2 * i + 1] = ops.linear_bwd_weight_f32(g, acts[i])
+                if i > 0:
+                    g = ops.linear_bwd_data_f32(g, weights[i], relu_out=acts[i])
+                elif need_dx:
+                    g = ops.linear_bwd_data_f32(g, weights[i], relu_out=None)
+            return (g if need_dx else None, None, *grads)
+        g = ops.to_bf16(dy.contiguous().float())
+        for i in reversed(range(n)):
+            N, K = weights[i].shape
+            # dW[N,K] = g[M,N]^T acts_i[M,K]: both operands reduce over their ROW index -> MN-major
+            tiles = ((N + 127) // 128) * ((K + 255) // 256)
+            grads[2 * i] = ops.gemm_bf16(g, acts[i], N, K, M, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
+                                         split_k=_split_k(tiles, (M + 63) // 64))
+            grads[2 * i + 1] = ops.colsum(g)
+            if i > 0:    # dh[M,K] = g[M,N] W[N,K], masked by relu'(acts_i)
+                g = ops.gemm_bf16(g, weights[i], M, K, N, a_kmajor=True, b_kmajor=False, mask=acts[i])
+            elif need_dx:
+                g = ops.to_f32(ops.gemm_bf16(g, weights[i], M, K, N, a_kmajor=True, b_kmajor=False))
+        return (g if need_dx else None, None, *grads)
+
+
+class FeatureExtractor(nn.Module):
+    """Per-frame MLP input_dim -> hidden_dims... -> output_dim, ReLU between layers
+    (reference models.py:6-47; xavier-normal weights, every bias 0.1)."""
+
+    def __init__(self, input_dim: int = 2048, output_dim: int = 32, hidden_dims: list = None, precision: str = "fp32"):
+        super().__init__()
+        self.precision = precision
+        self.linear = nn.Sequential()
+        dims = [input_dim] + list(hidden_dims)
+        for i in range(len(hidden_dims)):
+            self.linear.add_module(f"linear_{i}", nn.Linear(dims[i], dims[i + 1]))
+            self.linear.add_module(f"relu_{i}", nn.ReLU())
+        self.linear.add_module("output", nn.Linear(dims[-1], output_dim))
+        self.initialize_weights()
+
+    def initialize_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_normal_(m.weight)
+                nn.init.constant_(m.bias, 0.1)
+
+    def _params(self):
+        out = []
+        for m in self.linear:
+            if isinstance(m, nn.Linear):
+                out += [m.weight, m.bias]
+        return out
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("b200med FeatureExtractor runs on CUDA tensors only (no CPU fallback)")
+        lead = x.shape[:-1]
+        y = _MLPFunction.apply(x.reshape(-1, x.shape[-1]), self.precision, *self._params())
+        return y.reshape(*lead, y.shape[-1])
+
+
+class CNN(nn.Module):
+    """Window CNN head (reference models.py:49-131): 2 (W=10) or 3 (W=30) conv/pool/dropout/BN blocks,
+    then Linear 256/32/16/C with ReLU + BN.  Like the reference, only W in {10, 30} defines layers."""
+
+    def __init__(self, in_features: int = 58, window_size: int = 30, n_classes: int = 1):
+        super().__init__()
+        self.name = "SimpleCNN"
+        self.window_size, self.in_features, self.n_classes = window_size, in_features, n_classes
+        widths = {10: [64, 128], 30: [64, 128, 256]}.get(window_size)
+        if widths is None:
+            # the reference defines no conv stack for other window sizes and fails with this error (models.py:66-97)
+            raise AttributeError("'CNN' object has no attribute 'convolutional_layers'")
+        mods, cin, length = [], in_features, window_size
+        for cout in widths:
+            mods += [nn.Conv1d(cin, cout, kernel_size=3, stride=1), nn.MaxPool1d(2, 2), nn.Dropout(p=0.2),
+                     nn.BatchNorm1d(cout)]
+            cin, length = cout, (length - 2) // 2
+        self.convolutional_layers = nn.Sequential(*mods, nn.Flatten())
+        self.linear_layers = nn.Sequential(
+            nn.Linear(cin * length, 256), nn.ReLU(), nn.BatchNorm1d(256),
+            nn.Linear(256, 32), nn.ReLU(), nn.BatchNorm1d(32),
+            nn.Linear(32, 16), nn.ReLU(), nn.BatchNorm1d(16),
+            nn.Linear(16, n_classes))
+        self.initialize_weights()
+
+    def forward(self, x):
+        return self.linear_layers(self.convolutional_layers(x))
+
+    def initialize_weights(self):
+        # reference quirk kept for weight parity: only the LAST module's bias becomes 0.1 (models.py:130-131)
+        last = None
+        for m in self.modules():
+            if isinstance(m, nn.Conv1d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.Linear):
+                nn.init.xavier_normal_(m.weight)
+            last = m
+        if last.bias is not None:
+            nn.init.constant_(last.bias, 0.1)
+
+
+class LSTM(nn.Module):
+    """Window LSTM head (reference models.py:135-220): [B,F,W] -> transpose -> nn.LSTM(F, H, layers,
+    dropout .2) -> ReLU -> last step -> Linear 256/64/C with ReLU + BN."""
+
+    def __init__(self, in_features: int = 58, window_size: int = 30, num_layers: int = 3, hidden_size: int = 128,
+                 n_classes: int = 1):
+        super().__init__()
+        self.name = "SimpleLSTM"
+        self.window_size, self.in_features = window_size, in_features
+        self.layer_dim, self.hidden_size, self.n_classes = num_layers, hidden_size, n_classes
+        self.lstm = nn.LSTM(input_size=in_features, hidden_size=hidden_size, num_layers=num_layers, batch_first=True,
+                            dropout=0.2)
+        self.linear_layers = nn.Sequential(
+            nn.Flatten(), nn.Linear(hidden_size, 256), nn.ReLU(), nn.BatchNorm1d(256),
+            nn.Linear(256, 64), nn.ReLU(), nn.BatchNorm1d(64), nn.Linear(64, n_classes))
+        self.initialize_weights()
+
+    def forward(self, l):
+        out, _ = self.lstm(l.transpose(1, 2).contiguous())
+        return self.linear_layers(F.relu(out)[:, -1, :])
+
+    def initialize_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_normal_(m.weight)
+                nn.init.constant_(m.bias, 0)

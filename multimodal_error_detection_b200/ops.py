@@ -1,0 +1,322 @@
+"""Tensor-level wrappers over the C ABI.  torch is used only for device memory and streams.
+
+Every function takes CUDA tensors, launches on ``torch.cuda.current_stream()`` and raises if it is
+handed CPU tensors -- the product path has no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, StreamDesc, call
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need(t: torch.Tensor, dtype=None, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"b200med: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"b200med: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"b200med: {name} must be contiguous")
+    return t
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"b200med: unsupported dtype {t.dtype}")
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes: int, device, tag: str = "default", zero: bool = False) -> torch.Tensor:
+    """Grow-only scratch buffers keyed by (device, stream, tag); stream-ordered reuse is safe."""
+    key = (str(device), torch.cuda.current_stream().cuda_stream, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        n = max(int(nbytes), 256)
+        buf = torch.zeros(n, dtype=torch.uint8, device=device) if zero else torch.empty(n, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------- K0
+def window_index(g: torch.Tensor, subj_offsets: torch.Tensor, W: int, S: int, e5: Optional[torch.Tensor] = None):
+    """Window start rows (int32) of a flat table with contiguous subjects, plus the first-frame
+    labels.  Returns dict(starts, g_win, e5_win, subj_win, win_offsets).  Raises IndexError when a
+    subject has no non-zero gesture, as the reference does (dataset_utils.py:211-212)."""
+    g = _need(g.reshape(-1), torch.float32, "g")
+    off = _need(subj_offsets, torch.int64, "subj_offsets")
+    n_subj = off.numel() - 1
+    dev = g.device
+    win_off = torch.empty(n_subj + 1, dtype=torch.int64, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    call("b200med_window_count", _ptr(g), _ptr(off), n_subj, W, S, _ptr(win_off), _ptr(status), _stream())
+    host = torch.stack([win_off[-1], status[0].to(torch.int64)]).cpu()  # one sync: index build is one-off
+    total, bad = int(host[0]), int(host[1])
+    if bad >= 0:
+        raise IndexError(f"index 0 is out of bounds: subject #{bad} has no non-zero gesture")
+    starts = torch.empty(total, dtype=torch.int32, device=dev)
+    g_win = torch.empty(total, dtype=torch.float32, device=dev)
+    subj_win = torch.empty(total, dtype=torch.int32, device=dev)
+    e5_win = None
+    if e5 is not None:
+        e5 = _need(e5, torch.float32, "e5")
+        e5_win = torch.empty(total, 5, dtype=torch.float32, device=dev)
+    call("b200med_window_fill", _ptr(g), _ptr(off), _ptr(win_off), n_subj, W, S, _ptr(e5), _ptr(starts), _ptr(g_win),
+         _ptr(e5_win), _ptr(subj_win), _stream())
+    return dict(starts=starts, g_win=g_win, e5_win=e5_win, subj_win=subj_win, win_offsets=win_off)
+
+
+def powerset(e5: torch.Tensor, delete_nd: bool = True):
+    e5 = _need(e5, torch.float32, "e5")
+    n = e5.shape[0]
+    e7 = torch.empty(n, 7, dtype=torch.int32, device=e5.device)
+    mask = torch.empty(n, dtype=torch.uint8, device=e5.device)
+    call("b200med_powerset", _ptr(e5), n, int(bool(delete_nd)), _ptr(e7), _ptr(mask), _stream())
+    return e7, mask.bool()
+
+
+# ------------------------------------------------------------------------------------------- K1
+class GatherStream:
+    """One modality stream for :func:`gather_norm` (see b200med_stream_desc)."""
+
+    def __init__(self, table, mean=None, std=None, out=None, out_col=0, exact_div=True):
+        self.table, self.mean, self.std, self.out, self.out_col, self.exact_div = table, mean, std, out, out_col, exact_div
+
+
+def gather_norm(streams: Sequence[GatherStream], starts: torch.Tensor, W: int, variant: int = 0):
+    """out_s[b*W+t, col_s:col_s+D_s] = (table_s[starts[b]+t] - mean_s) / std_s for every stream."""
+    starts = _need(starts, torch.int32, "starts")
+    B = starts.numel()
+    arr = (StreamDesc * len(streams))()
+    keep = []
+    for i, s in enumerate(streams):
+        table = _need(s.table, None, "table")
+        out = _need(s.out, None, "out")
+        D = table.shape[-1]
+        out2 = out.view(-1, out.shape[-1])
+        if out2.shape[0] != B * W:
+            raise ValueError(f"out has {out2.shape[0]} rows, expected B*W = {B * W}")
+        mean = std = None
+        stat_rows = 1
+        if s.mean is not None:
+            mean = _need(s.mean.reshape(-1, D), torch.float32, "mean")
+            std = _need(s.std.reshape(-1, D), torch.float32, "std")
+            stat_rows = mean.shape[0]
+            keep += [mean, std]
+        arr[i] = StreamDesc(table.data_ptr(), 0 if mean is None else mean.data_ptr(), 0 if std is None else std.data_ptr(),
+                            out.data_ptr(), D, _dt(table), _dt(out), out2.shape[1], s.out_col, stat_rows,
+                            int(bool(s.exact_div)), 0)
+    call("b200med_gather_norm", arr, len(streams), _ptr(starts), B, W, variant, _stream())
+
+
+def expand_stat(stat, D: int, W: int, device) -> torch.Tensor:
+    """Bring a standardisation statistic of any shape broadcastable against [W, D] (scalar, [D],
+    [1, D], [W, D]; the on-disk format is unpinned by the reference) to [1|W, D]."""
+    t = torch.as_tensor(stat, dtype=torch.float32)
+    if t.dim() == 2 and t.shape[0] == W and W > 1:
+        t = t.expand(W, D)
+    else:
+        t = torch.broadcast_to(t.reshape(-1) if t.numel() in (1, D) else t, (D,)).reshape(1, D)
+    return t.contiguous().to(device)
+
+
+def standardise_rows(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, out=None, out_col=0):
+    x = _need(x, torch.float32, "x")
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    call("b200med_standardise_rows", _ptr(x), _ptr(_need(mean.reshape(-1), torch.float32)), _ptr(_need(std.reshape(-1), torch.float32)),
+         _ptr(out), rows, D, out.shape[-1], out_col, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- K2 fp32
+def linear_fwd_f32(x, w, b, relu: bool):
+    x = _need(x, torch.float32, "x"); w = _need(w, torch.float32, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    call("b200med_linear_fwd_f32", _ptr(x), _ptr(w), _ptr(b), _ptr(y), M, N, K, int(relu), _stream())
+    return y
+
+
+def linear_bwd_data_f32(dy, w, relu_out=None):
+    dy = _need(dy, torch.float32, "dy"); w = _need(w, torch.float32, "w")
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+    call("b200med_linear_bwd_data_f32", _ptr(dy), _ptr(w), _ptr(relu_out), _ptr(dx), M, N, K, _stream())
+    return dx
+
+
+def linear_bwd_weight_f32(dy, x, want_bias=True):
+    dy = _need(dy, torch.float32, "dy"); x = _need(x, torch.float32, "x")
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+    db = torch.empty(N, dtype=torch.float32, device=dy.device) if want_bias else None
+    ws = workspace(_lib.load().b200med_linear_bwd_weight_ws_bytes(M, N, K), dy.device, "wgrad_f32")
+    call("b200med_linear_bwd_weight_f32", _ptr(dy), _ptr(x), _ptr(dw), _ptr(db), M, N, K, 0, _ptr(ws), _stream())
+    return dw, db
+
+
+# ------------------------------------------------------------------------------------------- K2 bf16 (tcgen05)
+def has_tcgen05() -> bool:
+    return bool(_lib.load().b200med_has_tcgen05())
+
+
+def gemm_bf16(A, B, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, mask=None, relu=False,
+              out_dtype=torch.bfloat16, split_k=1, out=None):
+    """D[M,N] = A[M,K] B[N,K]^T on tcgen05.  K-major operand = stored [rows, K]; MN-major = stored [K, rows]."""
+    A = _need(A, torch.bfloat16, "A"); Bm = _need(B, torch.bfloat16, "B")
+    lda, ldb = A.shape[-1], Bm.shape[-1]
+    D = out if out is not None else torch.empty(M, N, dtype=out_dtype, device=A.device)
+    ws = None
+    if split_k > 1:
+        ws = workspace(_lib.load().b200med_gemm_bf16_ws_bytes(M, N, K, split_k), A.device, "splitk")
+    call("b200med_gemm_bf16", _ptr(A), _ptr(Bm), _ptr(D), _ptr(bias), _ptr(mask), M, N, K, lda, ldb, D.shape[-1],
+         int(a_kmajor), int(b_kmajor), _dt(D), int(relu), split_k, _ptr(ws), _stream())
+    return D
+
+
+def colsum(dy: torch.Tensor) -> torch.Tensor:
+    dy = _need(dy, None, "dy")
+    M, N = dy.shape
+    db = torch.empty(N, dtype=torch.float32, device=dy.device)
+    ws = workspace(_lib.load().b200med_colsum_ws_bytes(M, N), dy.device, "colsum")
+    call("b200med_colsum", _ptr(dy), _dt(dy), _ptr(db), M, N, N, _ptr(ws), _stream())
+    return db
+
+
+def to_bf16(x: torch.Tensor, out=None) -> torch.Tensor:
+    x = _need(x, torch.float32, "x")
+    y = out if out is not None else torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    call("b200med_cast_f32_to_bf16", _ptr(x), _ptr(y), x.numel(), _stream())
+    return y
+
+
+def to_f32(x: torch.Tensor) -> torch.Tensor:
+    x = _need(x, torch.bfloat16, "x")
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    call("b200med_cast_bf16_to_f32", _ptr(x), _ptr(y), x.numel(), _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------- K3
+def _loss_ws(device):
+    return workspace(_lib.load().b200med_loss_ws_bytes(0), device, "loss", zero=True)
+
+
+def bce_logits(logits, labels, pos_weight=1.0, grad_scale=1.0, want_grad=True, want_probs=False, want_preds=True,
+               counts=None, accumulate=False):
+    """Fused BCE-with-logits: returns dict(loss[1], dlogits, probs, preds, counts[4]=(tn,fp,fn,tp))."""
+    logits = _need(logits.reshape(-1), torch.float32, "logits")
+    labels = _need(labels.reshape(-1), torch.float32, "labels")
+    B, dev = logits.numel(), logits.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dl = torch.empty(B, dtype=torch.float32, device=dev) if want_grad else None
+    pr = torch.empty(B, dtype=torch.float32, device=dev) if want_probs else None
+    pd = torch.empty(B, dtype=torch.float32, device=dev) if want_preds else None
+    if counts is None:
+        counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    call("b200med_bce_logits", _ptr(logits), _ptr(labels), B, float(pos_weight), float(grad_scale), _ptr(loss), _ptr(dl),
+         _ptr(pr), _ptr(pd), _ptr(counts), int(accumulate), _ptr(_loss_ws(dev)), _stream())
+    return dict(loss=loss, dlogits=dl, probs=pr, preds=pd, counts=counts)
+
+
+def ce_logits(logits, target, class_weight=None, mask=None, target_shift=0, reduction=0, grad_scale=1.0,
+              want_grad=True, want_probs=False, pred_shift=0, pred_mask_mode=0, cm=None, cm_classes=None,
+              accumulate=False):
+    logits = _need(logits, torch.float32, "logits")
+    target = _need(target.reshape(-1), torch.int32, "target")
+    B, Cn = logits.shape
+    dev = logits.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dl = torch.empty(B, Cn, dtype=torch.float32, device=dev) if want_grad else None
+    pr = torch.empty(B, Cn, dtype=torch.float32, device=dev) if want_probs else None
+    pd = torch.empty(B, dtype=torch.int32, device=dev)
+    cm_classes = cm_classes or Cn
+    if cm is None:
+        cm = torch.zeros(cm_classes, cm_classes, dtype=torch.int64, device=dev)
+    call("b200med_ce_logits", _ptr(logits), _ptr(target), _ptr(class_weight), _ptr(mask), B, Cn, target_shift, reduction,
+         float(grad_scale), _ptr(loss), _ptr(dl), _ptr(pr), _ptr(pd), pred_shift, pred_mask_mode, _ptr(cm), cm_classes,
+         int(accumulate), _ptr(_loss_ws(dev)), _stream())
+    return dict(loss=loss, dlogits=dl, probs=pr, preds=pd, cm=cm)
+
+
+def ce_frame(logits, e, grad_scale=1.0, want_grad=True, counts=None, accumulate=False):
+    """logits [stages, 1, 2, T] (or [stages, 2, T]); e [T] soft error labels."""
+    logits = _need(logits, torch.float32, "logits")
+    stages, T = logits.shape[0], logits.shape[-1]
+    if logits.numel() != stages * 2 * T:
+        raise ValueError("frame loss expects 2 classes and batch size 1")
+    e = _need(e.reshape(-1), torch.float32, "e")
+    dev = logits.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dl = torch.empty_like(logits) if want_grad else None
+    pd = torch.empty(T, dtype=torch.float32, device=dev)
+    if counts is None:
+        counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    call("b200med_ce_frame", _ptr(logits), _ptr(e), stages, T, float(grad_scale), _ptr(loss), _ptr(dl), _ptr(pd),
+         _ptr(counts), int(accumulate), _ptr(_loss_ws(dev)), _stream())
+    return dict(loss=loss, dlogits=dl, preds=pd, counts=counts)
+
+
+# ------------------------------------------------------------------------------------------- optimiser
+def adam_advance(state: torch.Tensor, beta1: float, beta2: float):
+    call("b200med_adam_advance", _ptr(_need(state, torch.float32, "state")), beta1, beta2, _stream())
+
+
+def adam_step(p, g, m, v, state, beta1, beta2, eps, weight_decay, grad_scale=1.0):
+    call("b200med_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(state), beta1, beta2, eps, weight_decay,
+         grad_scale, _stream())
+
+
+# ------------------------------------------------------------------------------------------- post-processing
+def window_vote(frame_preds, starts, W: int, binary: bool = True):
+    fp = _need(frame_preds.reshape(-1), torch.float32, "frame_preds")
+    starts = _need(starts, torch.int32, "starts")
+    out = torch.empty(starts.numel(), dtype=torch.float32, device=fp.device)
+    call("b200med_window_vote", _ptr(fp), _ptr(starts), starts.numel(), W, int(binary), _ptr(out), _stream())
+    return out
+
+
+def soft_vote(pa, pb, labels=None):
+    pa = _need(pa.reshape(-1), torch.float32, "pa"); pb = _need(pb.reshape(-1), torch.float32, "pb")
+    n = pa.numel()
+    preds = torch.empty(n, dtype=torch.float32, device=pa.device)
+    counts = torch.zeros(4, dtype=torch.int64, device=pa.device)
+    lab = None if labels is None else _need(labels.reshape(-1), torch.float32, "labels")
+    call("b200med_soft_vote", _ptr(pa), _ptr(pb), _ptr(lab), n, _ptr(preds), _ptr(counts), 0, _ptr(None), _stream())
+    return preds, counts
+
+
+def cascade(binary, multiclass):
+    b = _need(binary.reshape(-1), torch.int32, "binary"); m = _need(multiclass.reshape(-1), torch.int32, "multiclass")
+    out = torch.empty_like(m)
+    call("b200med_cascade", _ptr(b), _ptr(m), b.numel(), _ptr(out), _stream())
+    return out
+
+
+def confusion(target, pred, n_classes: int, cm=None, accumulate=False):
+    t = _need(target.reshape(-1), torch.int32, "target"); p = _need(pred.reshape(-1), torch.int32, "pred")
+    if cm is None:
+        cm = torch.zeros(n_classes, n_classes, dtype=torch.int64, device=t.device)
+    call("b200med_confusion", _ptr(t), _ptr(p), t.numel(), n_classes, _ptr(cm), int(accumulate), _stream())
+    return cm

@@ -16,7 +16,7 @@ WINDOW_CASES = [
 
 def base_kwargs(**over):
     kw = dict(dataset_type="window", error_type="global", pos_weight=False, n_epochs=2, batch_size=64,
-              lr=1e-3, lr_scheduler=True, weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32,
+              lr=3e-4, lr_scheduler=True, weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32,
               data_type="multimodal", delete_ND=True, return_train_preds=False, siamese=False,
               model_name="SimpleCNN")
     kw.update(over)

@@ -194,9 +194,9 @@ def gen_epochs():
             with quiet:
                 dtr = FD(path, csv_filename="train.csv", delete_ND=kw["delete_ND"])
                 dte = FD(path, csv_filename="test.csv", delete_ND=kw["delete_ND"])
-            gen = torch.Generator().manual_seed(42)
-            tr = du.DataLoader(dtr, batch_size=1, shuffle=True, generator=gen)
-            te = du.DataLoader(dte, batch_size=1, shuffle=False, generator=gen)
+            # as in train_frame.ipynb cell 2 (lines 58-66): one fresh seed-42 generator per loader
+            tr = du.DataLoader(dtr, batch_size=1, shuffle=True, generator=torch.Generator().manual_seed(42))
+            te = du.DataLoader(dte, batch_size=1, shuffle=False, generator=torch.Generator().manual_seed(42))
             item = dtr[1]
             rec = {"n_train": len(dtr), "n_frames": int(dtr.get_n_frames()),
                    "item1_shapes": [list(x.shape) for x in item if isinstance(x, torch.Tensor)],

@@ -1,0 +1,264 @@
+"""GPU parity of the drop-in modules and loops (reference signatures) against the golden fixtures
+recorded from the unmodified reference: weights bit-exact, logits / loss / gradients within 1e-5
+relative (fp32 mode) or 2e-2 (bf16 mode), epoch scores identical to 3 decimals."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from hashing import digest, state_digest
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _objects(kw, W, counts):
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    fe, model, crit, opt, sched = mu.define_model_objects(kw, cases.IN_FEATURES, torch.device(DEV), counts, W)
+    return mu, fe, model, crit, opt, sched
+
+
+def _no_dropout(*mods):
+    for mod in mods:
+        for m in mod.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if isinstance(m, torch.nn.LSTM):
+                m.dropout = 0.0
+
+
+@pytest.mark.parametrize("name", list(cases.MODEL_CASES))
+def test_model_parity_fp32(name, golden_dir):
+    meta = json.load(open(os.path.join(golden_dir, "models.json")))[name]
+    gold = np.load(os.path.join(golden_dir, "models.npz"))
+    kw, W, counts = cases.MODEL_CASES[name]
+    mu, fe, model, crit, opt, sched = _objects(kw, W, counts)
+    # same state_dict keys and bit-identical seed-42 weights as the reference
+    assert list(model.state_dict().keys()) == meta["model_keys"] and list(fe.state_dict().keys()) == meta["fe_keys"]
+    assert state_digest({k: v.cpu() for k, v in model.state_dict().items()}) == meta["model_sd"]
+    assert state_digest({k: v.cpu() for k, v in fe.state_dict().items()}) == meta["fe_sd"]
+    assert sum(p.numel() for p in list(fe.parameters()) + list(model.parameters())) == meta["n_params"]
+    images, kin, y = (t.to(DEV) for t in cases.model_inputs(name))
+    model.eval(); fe.eval()
+    with torch.no_grad():
+        if not (kw["data_type"] == "video" and kw["video_dims"] == 2048):
+            assert rel(fe(images).cpu().numpy(), gold[f"{name}/fe_out"]) < 1e-5
+        logits = model(mu.define_inputs(images, kin, fe, kw, DEV))
+    assert rel(logits.cpu().numpy(), gold[f"{name}/logits_eval"]) < 1e-5
+    _no_dropout(model, fe)
+    model.train(); fe.train()
+    out = model(mu.define_inputs(images, kin, fe, kw, DEV))
+    assert rel(out.detach().cpu().numpy(), gold[f"{name}/logits_train"]) < 1e-5
+    loss, _ = mu.compute_loss(out, y if kw["error_type"] == "global" else y.long(), crit, kw["dataset_type"])
+    opt.zero_grad(); loss.backward()
+    assert abs(loss.item() - float(gold[f"{name}/loss"])) <= 1e-5 * abs(float(gold[f"{name}/loss"]))
+    norms = []
+    for prefix, mod in (("fe", fe), ("model", model)):
+        for k, p in mod.named_parameters():
+            norms.append(float(p.grad.double().norm()))
+            key = f"{name}/grad/{prefix}.{k}"
+            if key in gold.files:
+                g = gold[key]
+                scale = max(float(np.abs(g).max()), 1e-3 * float(gold[f"{name}/grad_norms"][len(norms) - 1]), 1e-12)
+                assert np.abs(p.grad.reshape(-1)[:16].cpu().numpy() - g).max() <= 2e-5 * scale, key
+    gn = gold[f"{name}/grad_norms"]
+    # parameters the reference leaves without a gradient (an unused FE, Appendix A-11) have zero grad here
+    assert np.allclose(norms, gn, rtol=2e-5, atol=1e-7 * float(gn.max())), np.abs(np.asarray(norms) - gn).max()
+    opt.step(); sched.step()
+    assert abs(opt.param_groups[0]["lr"] - meta["lr_after_sched"]) < 1e-12
+    w0 = next(fe.parameters()).detach().reshape(-1)[:64].cpu().numpy()
+    assert np.abs(w0 - gold[f"{name}/fe_w0_after_step"]).max() < 1e-6
+    wl = list(model.parameters())[-2].detach().reshape(-1)[:64].cpu().numpy()
+    assert np.abs(wl - gold[f"{name}/head_last_after_step"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["cnn_w10", "lstm_w16_pw", "lstm_w10_c6"])
+def test_model_parity_bf16(name, golden_dir):
+    """Throughput mode: FeatureExtractor on the tcgen05 kernels; logits and FE gradients within 2e-2."""
+    from multimodal_error_detection_b200 import ops
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    gold = np.load(os.path.join(golden_dir, "models.npz"))
+    kw, W, counts = cases.MODEL_CASES[name]
+    mu, fe, model, crit, opt, sched = _objects(dict(kw, precision="bf16"), W, counts)
+    images, kin, y = (t.to(DEV) for t in cases.model_inputs(name))
+    _no_dropout(model, fe)
+    model.train(); fe.train()
+    feat = fe(images)
+    assert rel(feat.detach().float().cpu().numpy(), gold[f"{name}/fe_out"]) < 2e-2
+    out = model(mu.define_inputs(images, kin, fe, kw, DEV))
+    assert rel(out.detach().cpu().numpy(), gold[f"{name}/logits_train"]) < 2e-2
+    loss, _ = mu.compute_loss(out, y if kw["error_type"] == "global" else y.long(), crit, kw["dataset_type"])
+    opt.zero_grad(); loss.backward()
+    assert abs(loss.item() - float(gold[f"{name}/loss"])) <= 2e-2 * abs(float(gold[f"{name}/loss"]))
+    gn = gold[f"{name}/grad_norms"]
+    names = json.load(open(os.path.join(golden_dir, "models.json")))[name]["grad_names"]
+    for (k, p) in fe.named_parameters():
+        want = gn[names.index(f"fe.{k}")]
+        assert abs(float(p.grad.double().norm()) - want) <= 3e-2 * want + 1e-7, k
+
+
+def _scores_close(got, want, what):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert abs(got[0] - want[0]) <= 2e-4 * max(1.0, abs(want[0])), (what, "loss", got[0], want[0])
+    assert np.all(np.round(got[1:], 3) == np.round(want[1:], 3)) or np.abs(got[1:] - want[1:]).max() < 5e-4, (what, got, want)
+
+
+@pytest.mark.parametrize("name", list(cases.EPOCH_CASES))
+def test_window_epochs_fp32(name, golden_dir, fold_on_disk):
+    """retrieve_dataloaders_window -> define_model_objects -> train_single_epoch / validate_single_epoch, two
+    epochs, against the reference's own run on the same on-disk fold."""
+    from multimodal_error_detection_b200.dataset import dataset_utils as du
+    gold = json.load(open(os.path.join(golden_dir, "epochs.json")))[name]
+    kw, W, S = cases.EPOCH_CASES[name]
+    path, fold = fold_on_disk
+    tr, te = du.retrieve_dataloaders_window(path, kw, window_size=W, stride=S)
+    ds = tr.dataset
+    assert len(ds) == gold["n_train"] and len(te.dataset) == gold["n_test"]
+    assert [float(v) for v in ds.binary_error_distribution] == gold["binary_error_distribution"]
+    assert np.allclose(ds.specific_error_distribution, gold["specific_error_distribution"], rtol=1e-6)
+    item = ds[3]
+    assert digest(item[0]) == gold["item3_image_digest"] and digest(item[1]) == gold["item3_kin_digest"]   # bit-exact fp32 batch
+    assert item[3].tolist() == gold["item3_e7"] and item[4] == gold["item3_subject"]
+    from multimodal_error_detection_b200.dataset.CustomWindowDataset import DeviceWindowLoader
+    first = next(iter(DeviceWindowLoader(ds, kw["batch_size"], shuffle=True, generator=torch.Generator().manual_seed(42))))
+    assert digest(first[3]) == gold["first_batch_e7_digest"] and digest(first[0]) == gold["first_batch_image_digest"]
+    mu, fe, model, crit, opt, sched = _objects(kw, W, ds.binary_error_distribution)
+    _no_dropout(model, fe)
+    for ep in range(kw["n_epochs"]):
+        t = mu.train_single_epoch(model, fe, tr, crit, opt, sched, DEV, kw)
+        v = mu.validate_single_epoch(model, fe, te, crit, DEV, kw)
+        g = gold["epochs"][ep]
+        _scores_close(t[:5], g["train"], f"{name} train ep{ep}")
+        assert np.abs(np.asarray(t[5]) - np.asarray(g["train_cm"])).sum() <= 2, (t[5], g["train_cm"])
+        _scores_close(v[:5], g["val"], f"{name} val ep{ep}")
+        assert np.abs(np.asarray(v[5]) - np.asarray(g["val_cm"])).sum() <= 2
+        assert np.abs(np.asarray(v[8]) - np.asarray(g["val_probs"])).max() < 1e-4
+        assert v[10] == g["val_labels"]
+        assert abs(opt.param_groups[0]["lr"] - g["lr"]) < 1e-12
+        if kw["return_train_preds"]:
+            assert t[8] == g["train_labels"] and list(t[9]) == g["train_subjects"]
+    assert np.abs(next(fe.parameters()).detach().reshape(-1)[:32].cpu().numpy() - np.asarray(gold["final_fe_w0"])).max() < 5e-5
+
+
+def test_frame_epochs_fp32(golden_dir, fold_on_disk):
+    from multimodal_error_detection_b200.dataset.CustomFrameDataset import CustomFrameDataset, FrameLoader
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    name = "tecno_multimodal"
+    gold = json.load(open(os.path.join(golden_dir, "epochs.json")))[name]
+    kw = cases.FRAME_EPOCH_CASES[name]
+    path, fold = fold_on_disk
+    dtr = CustomFrameDataset(path, csv_filename="train.csv", delete_ND=kw["delete_ND"])
+    dte = CustomFrameDataset(path, csv_filename="test.csv", delete_ND=kw["delete_ND"])
+    assert len(dtr) == gold["n_train"] and dtr.get_n_frames() == gold["n_frames"]
+    item = dtr[1]
+    assert [list(x.shape) for x in item if isinstance(x, torch.Tensor)] == gold["item1_shapes"]
+    assert digest(item[1]) == gold["item1_kin_digest"] and digest(item[3]) == gold["item1_e7_digest"]
+    assert digest(item[0]) == gold["item1_image_digest"] and item[5][0].tolist() == gold["item1_skill"]
+    assert item[4] == gold["item1_subject"]
+    tr = FrameLoader(dtr, shuffle=True, generator=torch.Generator().manual_seed(42))
+    te = FrameLoader(dte, shuffle=False, generator=torch.Generator().manual_seed(42))
+    _, fe, model, crit, opt, sched = _objects(kw, 0, (0.4, 0.6))
+    _no_dropout(model, fe)
+    for ep in range(kw["n_epochs"]):
+        t = mu.train_single_epoch(model, fe, tr, crit, opt, sched, DEV, kw)
+        v = mu.validate_single_epoch(model, fe, te, crit, DEV, kw)
+        g = gold["epochs"][ep]
+        _scores_close(t[:5], g["train"], f"frame train ep{ep}")
+        _scores_close(v[:5], g["val"], f"frame val ep{ep}")
+        assert v[10] == g["val_labels"] and v[11] == g["val_gestures"]
+        mism = np.mean(np.asarray(v[7]) != np.asarray(g["val_preds"]))
+        assert mism < 2e-3, mism
+    # frame -> window post-processing of the last validation pass
+    subj = [s[0] for s in v[12]]
+    pw, ew, gw, sw = mu.window_predictions(np.asarray(g["val_preds"]), np.asarray(v[10]), np.asarray(v[11]), np.asarray(subj),
+                                           window_size=10, stride=6, binary=True)
+    assert pw.reshape(-1).tolist() == gold["window_preds"] and ew.reshape(-1).tolist() == gold["window_labels"]
+    assert sw["subject"].tolist() == gold["window_subjects"]
+
+
+def test_es_and_sequential_epochs_fp32(golden_dir, fold_on_disk):
+    from multimodal_error_detection_b200.dataset import dataset_utils as du
+    gold = json.load(open(os.path.join(golden_dir, "epochs_es.json")))
+    path, fold = fold_on_disk
+    kw = cases.ES_CASE
+    tr, te = du.retrieve_dataloaders_window(path, kw, window_size=10, stride=6)
+    assert len(tr.dataset) == gold["es"]["n_train"]
+    mu, fe, model, crit, opt, sched = _objects(kw, 10, tr.dataset.binary_error_distribution)
+    _no_dropout(model, fe)
+    for ep in range(kw["n_epochs"]):
+        t = mu.train_single_epoch_ES(model, fe, tr, crit, opt, sched, DEV, kw)
+        v = mu.validate_single_epoch_ES(model, fe, te, crit, DEV, kw)
+        g = gold["es"]["epochs"][ep]
+        _scores_close(t[:7], g["train"], f"ES train ep{ep}")
+        assert np.abs(np.asarray(t[8]) - np.asarray(g["train_cm_macro"])).sum() <= 2
+        _scores_close(v[:7], g["val"], f"ES val ep{ep}")
+        assert v[12] == g["val_labels"]
+        assert np.mean(np.asarray(v[11]) != np.asarray(g["val_preds"])) < 0.01
+        assert np.abs(np.asarray(v[10]) - np.asarray(g["val_probs"])).max() < 1e-4
+    # cascade
+    kwb, kws = cases.SEQ_BINARY_CASE, cases.SEQ_CASE
+    _, bfe, bmodel, bcrit, bopt, bsched = _objects(kwb, 10, tr.dataset.binary_error_distribution)
+    _no_dropout(bmodel, bfe)
+    for _ in range(kwb["n_epochs"]):
+        mu.train_single_epoch(bmodel, bfe, tr, bcrit, bopt, bsched, DEV, kwb)
+    tr2, te2 = du.retrieve_dataloaders_window(path, kws, window_size=10, stride=6)
+    _, fe, model, crit, opt, sched = _objects(kws, 10, tr.dataset.binary_error_distribution)
+    _no_dropout(model, fe)
+    for ep in range(kws["n_epochs"]):
+        t = mu.train_single_epoch_Sequential(model, fe, tr2, None, opt, DEV, sched, kws)
+        v = mu.validate_single_epoch_Sequential(model, fe, bmodel, bfe, te2, DEV, kws)
+        g = gold["sequential"]["epochs"][ep]
+        _scores_close(t[:9], g["train"], f"SEQ train ep{ep}")
+        assert np.abs(np.asarray(t[9]) - np.asarray(g["train_cm_all"])).sum() <= 2
+        assert abs(v[0] - g["val"][0]) <= 1e-3 * abs(g["val"][0])
+        assert v[15] == g["val_labels_all"]
+        assert np.mean(np.asarray(v[12]) != np.asarray(g["val_preds_all"])) < 0.02
+
+
+def test_window_data_dropin(fold_on_disk):
+    """window_data keeps the reference's 5-tuple contract (materialised on the device)."""
+    from multimodal_error_detection_b200.dataset import dataset_utils as du
+    from multimodal_error_detection_b200 import synthetic
+    from oracle import window_index as O
+    path, fold = fold_on_disk
+    flat = du.load_data(path, "train.csv")
+    iw, kw_, gw, ew, sw = du.window_data(*flat, window_size=10, stride=6)
+    image, kin, g, e5, names, _ = synthetic.flat_tables(fold.train)
+    oi, ok, og, oe, os_ = O.window_data(image, kin, g, e5, names, 10, 6)
+    assert np.array_equal(iw.cpu().numpy(), oi) and np.array_equal(kw_.cpu().numpy(), ok)
+    assert np.array_equal(gw.cpu().numpy(), og) and np.array_equal(ew.cpu().numpy(), oe) and sw["subject"].tolist() == os_
+    # interleaved subjects are regrouped like the reference's per-subject row lists
+    perm = np.random.Generator(np.random.PCG64(0)).permutation(len(names))
+    blocks = np.sort(perm.reshape(-1)[: len(names) // 2])
+    order = np.concatenate([blocks, np.setdiff1d(np.arange(len(names)), blocks)])
+    import pandas as pd
+    iw2, *_rest, sw2 = du.window_data(torch.from_numpy(image[order]), torch.from_numpy(kin[order]), torch.from_numpy(g[order]),
+                                      torch.from_numpy(e5[order]), pd.DataFrame({"subject": names[order]}), 10, 6)
+    oi2, _, _, _, os2 = O.window_data(image[order], kin[order], g[order], e5[order], names[order], 10, 6)
+    assert np.array_equal(iw2.cpu().numpy(), oi2) and sw2["subject"].tolist() == os2
+
+
+def test_checkpoint_interchange(tmp_path):
+    """save_model files interchange with reference-layout state_dicts (same keys / shapes)."""
+    from oracle import nets
+    kw, W, counts = cases.MODEL_CASES["lstm_w10"]
+    mu, fe, model, crit, opt, sched = _objects(kw, W, counts)
+    ofe, omodel, *_ = nets.build_objects(kw, cases.IN_FEATURES, counts, W)
+    with torch.no_grad():
+        for p in list(ofe.parameters()) + list(omodel.parameters()):
+            p.add_(0.01)
+    path = str(tmp_path / "m.pth")
+    mu.save_model({"feature_extractor": ofe.state_dict(), "model": omodel.state_dict()}, path)
+    mu.load_model_local(path, fe, model)
+    assert state_digest({k: v.cpu() for k, v in fe.state_dict().items()}) == state_digest(ofe.state_dict())
+    assert state_digest({k: v.cpu() for k, v in model.state_dict().items()}) == state_digest(omodel.state_dict())
+    assert fe.linear.linear_0.weight.data_ptr() >= opt.flat_param.data_ptr()   # still views of the flat buffer

@@ -1,0 +1,148 @@
+"""CPU tests of the host-side logic: C-ABI symbol export, metric closed forms vs sklearn, subject
+factorisation, statistic broadcasting, batch sharding, world_size-2 gloo gradient exchange."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from multimodal_error_detection_b200 import build
+    return build.build()
+
+
+def test_cabi_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "b200med.h")).read()
+    declared = set(re.findall(r"\b(b200med_[a-z0-9_]+)\s*\(", header))
+    declared.discard("b200med_stream_desc")
+    lib = ctypes.CDLL(built_lib)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    from multimodal_error_detection_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().b200med_version() == 100
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a GPU every compute entry point must fail loudly."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from multimodal_error_detection_b200.dataset import dataset_utils
+    from multimodal_error_detection_b200.modeling import models
+    with pytest.raises(RuntimeError):
+        dataset_utils.powerset_error_labels(torch.zeros(4, 5))
+    fe = models.FeatureExtractor(64, 8, [16])
+    with pytest.raises(RuntimeError):
+        fe(torch.zeros(2, 64))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "multimodal_error_detection_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+@pytest.mark.parametrize("C", [2, 6])
+def test_metrics_match_sklearn(C):
+    from sklearn.metrics import accuracy_score, confusion_matrix, f1_score, jaccard_score
+    from multimodal_error_detection_b200 import metrics as M
+    rng = np.random.Generator(np.random.PCG64(C))
+    for trial in range(30):
+        n = int(rng.integers(1, 80))
+        hi = C if trial % 3 else max(1, C - 2)          # sometimes leave classes absent
+        y, p = rng.integers(0, hi, n), rng.integers(0, hi, n)
+        cm = confusion_matrix(y, p, labels=list(range(C)))
+        assert abs(M.accuracy(cm) - accuracy_score(y, p)) < 1e-12
+        for avg in ("macro", "weighted"):
+            assert abs(M.f1_avg(cm, avg) - f1_score(y, p, average=avg, zero_division=0)) < 1e-12
+            assert abs(M.jaccard_avg(cm, avg) - jaccard_score(y, p, average=avg, zero_division=0)) < 1e-12
+        assert np.array_equal(M.sklearn_cm(cm), confusion_matrix(y, p))
+        if C == 2 and len(set(y) | set(p)) == 2:
+            assert abs(M.f1_binary(cm) - f1_score(y, p, average="binary", zero_division=0)) < 1e-12
+            assert abs(M.jaccard_binary(cm) - jaccard_score(y, p, average="binary", zero_division=0)) < 1e-12
+        if C == 6:
+            yb, pb = (y != 0).astype(int), (p != 0).astype(int)
+            assert np.array_equal(M.binarise(cm), confusion_matrix(yb, pb, labels=[0, 1]))
+
+
+def test_factorize_subjects_appearance_order():
+    from multimodal_error_detection_b200.table import factorize_subjects
+    codes, uniq = factorize_subjects(["z", "z", "a", "m", "a", "z"])
+    assert uniq == ["z", "a", "m"] and codes.tolist() == [0, 0, 1, 2, 1, 0]
+
+
+def test_expand_stat_shapes():
+    from multimodal_error_detection_b200.ops import expand_stat
+    D, W = 6, 4
+    for stat in (2.0, torch.arange(D).float(), torch.arange(D).float().reshape(1, D)):
+        assert expand_stat(stat, D, W, "cpu").shape == (1, D)
+    per_step = torch.arange(W * D).float().reshape(W, D)
+    assert torch.equal(expand_stat(per_step, D, W, "cpu"), per_step)
+
+
+def test_shard_batch_partitions():
+    from multimodal_error_detection_b200.parallel import shard_batch
+    idx = torch.arange(13)
+    for world in (1, 2, 4, 8):
+        parts = [shard_batch(idx, r, world) for r in range(world)]
+        assert torch.equal(torch.cat(parts), idx)
+
+
+def test_sampler_matches_torch_dataloader():
+    """Batch composition = a stock DataLoader with the reference's generator recipe (dataset_utils.py:526)."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from multimodal_error_detection_b200.dataset.CustomWindowDataset import _IndexOnly
+    n, B = 37, 8
+    ref = DataLoader(TensorDataset(torch.arange(n)), batch_size=B, shuffle=True, generator=torch.Generator().manual_seed(42))
+    mine = DataLoader(_IndexOnly(n), batch_size=B, shuffle=True, generator=torch.Generator().manual_seed(42),
+                      collate_fn=lambda items: torch.as_tensor(items))
+    for _ in range(3):  # generator state carries across epochs in both
+        assert [b[0].tolist() for b in ref] == [b.tolist() for b in mine]
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from multimodal_error_detection_b200 import parallel
+rank, _, world = parallel.init_from_env("gloo")
+torch.manual_seed(0)
+w = torch.nn.Linear(16, 1)
+x, y = torch.randn(12, 16), (torch.rand(12) > 0.5).float()
+def grads(rows):
+    w.zero_grad()
+    # SUM-reduced per-rank loss, scaled by the GLOBAL batch: what the all-reduce + 1/world Adam scale computes
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(w(x[rows]).squeeze(1), y[rows], reduction="sum") / 12
+    loss.backward()
+    return torch.cat([p.grad.reshape(-1) for p in w.parameters()])
+full = grads(torch.arange(12))
+mine = grads(parallel.shard_batch(torch.arange(12), rank, world)).clone()
+parallel.allreduce_sum_(mine)
+assert torch.allclose(mine, full, atol=1e-6), (mine, full)
+t = parallel.max_over_ranks(float(rank + 1), device="cpu")
+assert t == world
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_gradient_exchange(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29731",
+                   CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
