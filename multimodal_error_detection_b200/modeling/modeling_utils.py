@@ -193,6 +193,8 @@ def define_model_objects(exp_kwargs: dict, in_features_dict: dict, device, class
         torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(42)
     model = instantiate_model(exp_kwargs, in_features_dict[exp_kwargs["data_type"]], window_size, device).to(device)
+    if hasattr(model, "use_cudnn"):
+        model.use_cudnn = precision != "fp32"
     if exp_kwargs["data_type"] != "kinematics":
         feature_extractor = FeatureExtractor(input_dim=2048, output_dim=exp_kwargs["video_dims"], hidden_dims=[512, 256],
                                              precision=precision).to(device)
@@ -290,7 +292,9 @@ def _allreduce_grads(optimizer):
     """Data-parallel exchange: ONE sum all-reduce of the flat gradient buffer."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(optimizer.flat_grad, op=dist.ReduceOp.SUM)
+        optimizer._refresh_active()                      # gradients of first-time parameters move into the chunks
+        for buf in optimizer.grad_buffers():             # one chunk (+ one for a cuDNN-flattened LSTM)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         optimizer.grad_scale = 1.0 / dist.get_world_size()
 
 

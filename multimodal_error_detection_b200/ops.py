@@ -63,6 +63,10 @@ def window_index(g: torch.Tensor, subj_offsets: torch.Tensor, W: int, S: int, e5
     off = _need(subj_offsets, torch.int64, "subj_offsets")
     n_subj = off.numel() - 1
     dev = g.device
+    if g.numel() == 0 or n_subj <= 0:
+        z = lambda dt, *shape: torch.zeros(*shape, dtype=dt, device=dev)
+        return dict(starts=z(torch.int32, 0), g_win=z(torch.float32, 0), e5_win=None if e5 is None else z(torch.float32, 0, 5),
+                    subj_win=z(torch.int32, 0), win_offsets=z(torch.int64, max(n_subj, 0) + 1))
     win_off = torch.empty(n_subj + 1, dtype=torch.int64, device=dev)
     status = torch.empty(1, dtype=torch.int32, device=dev)
     call("b200med_window_count", _ptr(g), _ptr(off), n_subj, W, S, _ptr(win_off), _ptr(status), _stream())

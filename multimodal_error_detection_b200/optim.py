@@ -2,16 +2,39 @@
 
 Replaces ``torch.optim.Adam(FE.params + model.params, lr, weight_decay)`` of the reference
 (MED/modeling/modeling_utils.py:221-222): L2-coupled weight decay, betas (0.9, 0.999), eps 1e-8.
-All parameters are re-homed as views into ONE contiguous fp32 buffer (and their ``.grad`` into one
-gradient buffer), so a step is one kernel launch and the data-parallel gradient exchange is one
-all-reduce of one buffer.  It subclasses ``torch.optim.Optimizer`` so the stock
-``CosineAnnealingLR`` the reference uses (modeling_utils.py:257-258) drives ``param_groups[0]['lr']``.
+Parameters are re-homed as views into a few contiguous fp32 CHUNKS (and their ``.grad`` into matching
+gradient chunks), so a step is one kernel launch per chunk and the data-parallel gradient exchange is
+one all-reduce per chunk:
+
+* chunk 0 packs every ordinary parameter (16-byte aligned segments);
+* a module that already keeps its weights in ONE storage of its own -- ``nn.LSTM`` after
+  ``flatten_parameters()``, whose cuDNN kernels need that exact layout -- is adopted in place as a
+  further chunk, so cuDNN never has to re-compact the weights.
+
+Like ``torch.optim.Adam``, a parameter that has never received a gradient is skipped entirely (no
+decay, no moments): the reference registers an unused FeatureExtractor when ``video_dims == 2048``
+(SURVEY Appendix A-11).  The class subclasses ``torch.optim.Optimizer`` so the stock
+``CosineAnnealingLR`` of the reference (modeling_utils.py:257-258) drives ``param_groups[0]['lr']``.
 """
 from __future__ import annotations
+
+from typing import List
 
 import torch
 
 from . import ops
+
+
+class _Chunk:
+    """One contiguous fp32 parameter buffer with its gradient / moment twins."""
+
+    def __init__(self, param_buf: torch.Tensor):
+        self.param = param_buf
+        self.grad = torch.zeros_like(param_buf)
+        self.exp_avg = torch.zeros_like(param_buf)
+        self.exp_avg_sq = torch.zeros_like(param_buf)
+        self.members = []        # (param, offset, numel)
+        self.runs = []           # active [begin, end) ranges, multiples of 4 elements
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -19,31 +42,51 @@ class FusedAdam(torch.optim.Optimizer):
         params = [p for p in params]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._flat_ready = False
+        self._active = None            # per-parameter "has received a gradient" flags, known after the first step
         self.grad_scale = 1.0          # set to 1/world_size when gradients were SUM-all-reduced
         self._lr_on_device = None
+        self.chunks: List[_Chunk] = []
 
+    # ------------------------------------------------------------------------------------ layout
     def _flatten(self):
         ps = [p for g in self.param_groups for p in g["params"]]
         dev = ps[0].device
         if dev.type != "cuda":
             raise RuntimeError("b200med FusedAdam needs CUDA parameters (no CPU fallback)")
-        # 16-byte aligned segments so that the kernel's float4 path and tensor views both work
-        offs, total = [], 0
+        # parameters that already share one storage (cuDNN-flattened LSTM weights) are adopted in place
+        by_storage = {}
         for p in ps:
+            by_storage.setdefault(p.data.untyped_storage().data_ptr(), []).append(p)
+        packed, self.chunks = [], []
+        main = None
+        for p in ps:
+            group = by_storage[p.data.untyped_storage().data_ptr()]
+            if len(group) == 1 or p.dtype != torch.float32:
+                packed.append(p)
+        offs, total = [], 0
+        for p in packed:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4
-        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        for p, o in zip(ps, offs):
-            n = p.numel()
-            self.flat_param[o:o + n].copy_(p.data.reshape(-1))
-            p.data = self.flat_param[o:o + n].view_as(p.data)
-            gview = self.flat_grad[o:o + n].view_as(p.data)
-            if p.grad is not None:
-                gview.copy_(p.grad)
-            p.grad = gview
+        if packed:
+            main = _Chunk(torch.zeros(total, dtype=torch.float32, device=dev))
+            for p, o in zip(packed, offs):
+                n = p.numel()
+                main.param[o:o + n].copy_(p.data.reshape(-1))
+                p.data = main.param[o:o + n].view_as(p.data)
+                main.members.append((p, o, n))
+            self.chunks.append(main)
+        seen = set()
+        for p in ps:
+            key = p.data.untyped_storage().data_ptr()
+            group = by_storage.get(key, [])
+            if len(group) > 1 and p.dtype == torch.float32 and key not in seen:
+                seen.add(key)
+                n_store = p.data.untyped_storage().nbytes() // 4
+                buf = torch.empty(0, dtype=torch.float32, device=dev).set_(p.data.untyped_storage(), 0, (n_store,), (1,))
+                ch = _Chunk(buf)
+                for q in group:
+                    ch.members.append((q, q.data.storage_offset(), q.numel()))
+                self.chunks.append(ch)
         self.state_dev = torch.zeros(4, dtype=torch.float32, device=dev)   # {step, lr, bc1, sqrt(bc2)}
         self.n_params = sum(p.numel() for p in ps)
         self._flat_ready = True
@@ -53,10 +96,56 @@ class FusedAdam(torch.optim.Optimizer):
             self._flatten()
         return self
 
+    # flat views of chunk 0, kept for callers that want "the" buffers (tests, DESIGN.md examples)
+    @property
+    def flat_param(self):
+        return self.prepare().chunks[0].param
+
+    @property
+    def flat_grad(self):
+        return self.prepare().chunks[0].grad
+
+    def grad_buffers(self):
+        return [c.grad for c in self.prepare().chunks]
+
+    # ------------------------------------------------------------------------------------ step protocol
     def zero_grad(self, set_to_none: bool = False):
-        # gradients live in the flat buffer; keep the views, zero the storage (one memset)
         self.prepare()
-        self.flat_grad.zero_()
+        if self._active is None:
+            # before the first step nothing is known about which parameters take part: use None like torch
+            for c in self.chunks:
+                for p, _, _ in c.members:
+                    p.grad = None
+            return
+        for c in self.chunks:
+            c.grad.zero_()        # gradients live in the chunk; the views stay in place (one memset per chunk)
+
+    def _refresh_active(self):
+        """Adopt the gradients of parameters seen for the first time and rebuild the active ranges."""
+        changed = self._active is None
+        if self._active is None:
+            self._active = {}
+        for c in self.chunks:
+            for p, o, n in c.members:
+                if not self._active.get(id(p), False) and p.grad is not None:
+                    view = c.grad[o:o + n].view_as(p.data)
+                    if p.grad.data_ptr() != view.data_ptr():
+                        view.copy_(p.grad)
+                        p.grad = view
+                    self._active[id(p)] = True
+                    changed = True
+        if changed:
+            for c in self.chunks:
+                runs = []
+                for p, o, n in sorted(c.members, key=lambda m: m[1]):
+                    if not self._active.get(id(p), False):
+                        continue
+                    b, e = o // 4 * 4, (o + n + 3) // 4 * 4
+                    if runs and b <= runs[-1][1]:
+                        runs[-1][1] = max(runs[-1][1], e)
+                    else:
+                        runs.append([b, e])
+                c.runs = [(b, min(e, c.param.numel())) for b, e in runs]
 
     def sync_lr(self):
         lr = float(self.param_groups[0]["lr"])
@@ -67,9 +156,12 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         self.prepare()
+        self._refresh_active()
         g = self.param_groups[0]
         self.sync_lr()
         b1, b2 = g["betas"]
         ops.adam_advance(self.state_dev, b1, b2)
-        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.state_dev, b1, b2, g["eps"],
-                      g["weight_decay"], self.grad_scale)
+        for c in self.chunks:
+            for b, e in c.runs:
+                ops.adam_step(c.param[b:e], c.grad[b:e], c.exp_avg[b:e], c.exp_avg_sq[b:e], self.state_dev, b1, b2,
+                              g["eps"], g["weight_decay"], self.grad_scale)

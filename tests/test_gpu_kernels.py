@@ -236,7 +236,7 @@ GEMM_CASES = [
     (5120, 256, 32, True, False, 1),       # layer 3 data gradient (K = 32 < BLOCK_K)
     (5120, 512, 256, True, False, 1),      # layer 2 data gradient
     (300, 200, 136, True, True, 1),        # ragged M / N / K tails
-    (129, 72, 200, False, True, 1),        # MN-major A, K-major B
+    (136, 72, 200, False, True, 1),        # MN-major A, K-major B
     (1000, 128, 1000, True, False, 3),     # K tail under split-K
 ]
 
