@@ -153,6 +153,35 @@ int b200med_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stream);
 int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * LSTM head (MED/modeling/models.py:135-210) in throughput mode: every time step is one b200med_gemm_bf16
+ * over [x_t | h_{t-1}] plus one fused cell kernel.  Time-major buffers, see csrc/lstm.cu.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* x [B,F,W] f32 (the reference's [batch, features, time] head input) -> A0 [W,B,Kp] bf16 columns [0,F);
+ * zeroes the padding columns [F+H,Kp) and the h_{-1} columns [F,F+H) of step 0.                    */
+int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int32_t F, int32_t W, int32_t H,
+                             int32_t Kp, void *stream);
+/* dx [B,F,W] f32 <- dA0 [W,B,Kp] f32 columns [0,F).                                                 */
+int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int32_t F, int32_t W, int32_t Kp,
+                           void *stream);
+/* A[r, col0:col0+ncols] = 0 for r < rows (bf16 matrix with leading dimension ld).                   */
+int b200med_zero_cols_bf16(void *A, int64_t rows, int32_t ld, int32_t col0, int32_t ncols, void *stream);
+/* One cell step.  G [B,4H] f32: gate pre-activations in (i,f,g,o order, nn.LSTM), replaced in place by the
+ * activated gates.  c_prev [B,H] or NULL (t = 0); c_out [B,H].  h_t is written as bf16 to h_next (row stride
+ * ld_next; the h_{t-1} columns of the next step's operand) and, through dropout(drop_p), to x_up (the input
+ * columns of the layer above), and as f32 to h_out [B,H]; each may be NULL.  The dropout mask is a pure
+ * function of (*seed, drop_base + b*H + j), regenerated by the backward kernel.                      */
+int b200med_lstm_cell_fwd(float *G, const float *c_prev, float *c_out, void *h_next, int32_t ld_next,
+                          void *x_up, int32_t ld_up, float *h_out, int64_t B, int32_t H, float drop_p,
+                          const uint32_t *seed, uint64_t drop_base, void *stream);
+/* Backward of one cell step: dh = dropout'(dh_up) + dh_rec; dc [B,H] accumulates in place (dc_init: treat the
+ * incoming dc as 0); dG [B,4H] bf16 OUT gate gradients.                                              */
+int b200med_lstm_cell_bwd(const float *Gact, const float *c, const float *c_prev, const float *dh_up,
+                          int32_t ld_up, const float *dh_rec, int32_t ld_rec, float *dc, int32_t dc_init,
+                          void *dG, int64_t B, int32_t H, float drop_p, const uint32_t *seed,
+                          uint64_t drop_base, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K3  Fused loss + gradient + metric counts (latency-bound; deterministic reductions)
  * ---------------------------------------------------------------------------------------------- */
 

@@ -1,0 +1,191 @@
+// LSTM head (MED/modeling/models.py:135-210, nn.LSTM(58, 128, num_layers=3, dropout=.2)) in throughput mode.
+//
+// cuDNN runs this recurrence as fp32 SIMT "blockPersist" kernels: 23 ms of a 28 ms train step at B=8192
+// (profiles/r1_launch_shares_cudnn_lstm.md).  Here every time step of every layer is ONE tcgen05 GEMM
+//     gates[B, 4H] = [x_t | h_{t-1}] [B, Kp] * [W_ih | W_hh]^T [4H, Kp]  (+ b_ih + b_hh)
+// (K2 kernel, bf16 operands, fp32 accumulation in TMEM) followed by ONE fused cell kernel below; the
+// backward is the mirror image plus one big weight-gradient GEMM per layer over all W*B rows.
+//
+// Buffers are TIME-MAJOR so that each step's operand is a contiguous [B, Kp] matrix:
+//   A_l   [W, B, Kp_l] bf16   columns [0,in_l) = layer input x_t, [in_l, in_l+H) = h_{t-1}, rest = 0 padding
+//   G_l   [W, B, 4H]   f32    gate pre-activations, overwritten in place by the ACTIVATED gates (i, f, g, o)
+//   C_l   [W, B, H]    f32    cell states
+//   dG_l  [W, B, 4H]   bf16   gate gradients (operand of the data- and weight-gradient GEMMs)
+//   dA_l  [W, B, Kp_l] f32    [dx_t | dh_{t-1}] produced by the data-gradient GEMM
+// These cell kernels are HBM-bound: forward 4H*4 B read+write + ~6 H B per (b, t); they move 20-40 MB per
+// step at B=8192, i.e. a few microseconds each.
+#include "common.cuh"
+
+namespace b200med {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) {
+    // tanh(x) = 2*sigmoid(2x) - 1; |error| ~1e-6, far below the bf16 operand rounding of this mode
+    return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f;
+}
+
+// Counter-based dropout mask: keep(index) is a pure function of (seed, index), so the backward pass
+// regenerates it instead of storing it.
+__device__ __forceinline__ bool dropout_keep(uint32_t seed, unsigned long long index, float p) {
+    uint64_t z = index + 0x9E3779B97F4A7C15ull * (uint64_t)(seed + 1u);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    const float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);  // 24 random bits -> [0, 1)
+    return u >= p;
+}
+
+// x [B, F, W] f32 (the reference's [batch, features, time] layout) -> A0 [W, B, Kp] bf16 columns [0, F);
+// also zeroes the padding columns [F+H, Kp) of every step and the h_{-1} columns [F, F+H) of step 0.
+__global__ void lstm_pack_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, long long B, int F, int W,
+                                 int H, int Kp) {
+    const long long total = B * (long long)W * Kp;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % Kp);
+        const long long r = e / Kp;
+        const long long b = r % B;
+        const int t = (int)(r / B);
+        if (k < F) A0[e] = __float2bfloat16_rn(x[(b * F + k) * W + t]);
+        else if (k >= F + H || t == 0) A0[e] = __float2bfloat16_rn(0.0f);
+    }
+}
+
+// dx [B, F, W] f32 <- dA0 [W, B, Kp] f32 columns [0, F)
+__global__ void lstm_unpack_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, int F, int W, int Kp) {
+    const long long total = B * (long long)F * W;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(e % W);
+        const long long r = e / W;
+        const int k = (int)(r % F);
+        const long long b = r / F;
+        dx[e] = dA0[((long long)t * B + b) * Kp + k];
+    }
+}
+
+__global__ void zero_cols_bf16_kernel(__nv_bfloat16 *__restrict__ A, long long rows, int ld, int col0, int ncols) {
+    const long long total = rows * ncols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+        A[(e / ncols) * ld + col0 + (int)(e % ncols)] = __float2bfloat16_rn(0.0f);
+}
+
+// One thread per (b, j): gates -> (c_t, h_t); the activated gates replace the pre-activations in G.
+__global__ void __launch_bounds__(256)
+lstm_cell_fwd_kernel(float *__restrict__ G, const float *__restrict__ c_prev, float *__restrict__ c_out,
+                     __nv_bfloat16 *__restrict__ h_next, int ld_next, __nv_bfloat16 *__restrict__ x_up, int ld_up,
+                     float *__restrict__ h_out, long long B, int H, float drop_p, const uint32_t *__restrict__ seed_dev,
+                     unsigned long long drop_base) {
+    const uint32_t seed = seed_dev ? *seed_dev : 0u;
+    const long long total = B * (long long)H;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / H;
+        const int j = (int)(e - b * H);
+        float *g = G + b * 4 * H;
+        const float i_ = sigmoidf_(g[j]), f_ = sigmoidf_(g[H + j]), g_ = tanhf_(g[2 * H + j]), o_ = sigmoidf_(g[3 * H + j]);
+        const float c = f_ * (c_prev ? c_prev[e] : 0.0f) + i_ * g_;
+        const float h = o_ * tanhf_(c);
+        g[j] = i_; g[H + j] = f_; g[2 * H + j] = g_; g[3 * H + j] = o_;
+        c_out[e] = c;
+        if (h_next) h_next[b * ld_next + j] = __float2bfloat16_rn(h);
+        if (x_up) {
+            float hv = h;
+            if (drop_p > 0.0f) hv = dropout_keep(seed, drop_base + (unsigned long long)e, drop_p) ? h / (1.0f - drop_p) : 0.0f;
+            x_up[b * ld_up + j] = __float2bfloat16_rn(hv);
+        }
+        if (h_out) h_out[e] = h;
+    }
+}
+
+// Backward of one cell step.  dh = dh_up (gradient arriving from the layer above through its dropout, or
+// the head's gradient) + dh_rec (from step t+1 of this layer); dc accumulates in place.
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_kernel(const float *__restrict__ Gact, const float *__restrict__ c, const float *__restrict__ c_prev,
+                     const float *__restrict__ dh_up, int ld_up, const float *__restrict__ dh_rec, int ld_rec,
+                     float *__restrict__ dc, int dc_init, __nv_bfloat16 *__restrict__ dG, long long B, int H,
+                     float drop_p, const uint32_t *__restrict__ seed_dev, unsigned long long drop_base) {
+    const uint32_t seed = seed_dev ? *seed_dev : 0u;
+    const long long total = B * (long long)H;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / H;
+        const int j = (int)(e - b * H);
+        const float *g = Gact + b * 4 * H;
+        const float i_ = g[j], f_ = g[H + j], g_ = g[2 * H + j], o_ = g[3 * H + j];
+        float dh = 0.0f;
+        if (dh_up) {
+            float v = dh_up[b * ld_up + j];
+            if (drop_p > 0.0f) v = dropout_keep(seed, drop_base + (unsigned long long)e, drop_p) ? v / (1.0f - drop_p) : 0.0f;
+            dh += v;
+        }
+        if (dh_rec) dh += dh_rec[b * ld_rec + j];
+        const float tc = tanhf_(c[e]);
+        const float dct = (dc_init ? 0.0f : dc[e]) + dh * o_ * (1.0f - tc * tc);
+        const float cp = c_prev ? c_prev[e] : 0.0f;
+        __nv_bfloat16 *d = dG + b * 4 * H;
+        d[j] = __float2bfloat16_rn(dct * g_ * i_ * (1.0f - i_));
+        d[H + j] = __float2bfloat16_rn(dct * cp * f_ * (1.0f - f_));
+        d[2 * H + j] = __float2bfloat16_rn(dct * i_ * (1.0f - g_ * g_));
+        d[3 * H + j] = __float2bfloat16_rn(dh * tc * o_ * (1.0f - o_));
+        dc[e] = dct * f_;
+    }
+}
+
+static unsigned grid_for(long long total) {
+    const long long want = (total + 255) / 256, cap = (long long)num_sms() * 8;
+    return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace b200med
+
+using namespace b200med;
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int32_t F,
+                                                                               int32_t W, int32_t H, int32_t Kp, void *stream) {
+    B200MED_REQUIRE(B >= 1 && F >= 1 && W >= 1 && H >= 1 && Kp >= F + H, "bad shape");
+    B200MED_REQUIRE(x && A0, "null pointer");
+    lstm_pack_kernel<<<grid_for(B * (long long)W * Kp), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<__nv_bfloat16 *>(A0), B, F, W, H, Kp);
+    return after_launch("lstm_pack_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int32_t F,
+                                                                             int32_t W, int32_t Kp, void *stream) {
+    B200MED_REQUIRE(B >= 1 && F >= 1 && W >= 1 && Kp >= F, "bad shape");
+    B200MED_REQUIRE(dA0 && dx, "null pointer");
+    lstm_unpack_kernel<<<grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream>>>(dA0, dx, B, F, W, Kp);
+    return after_launch("lstm_unpack_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_zero_cols_bf16(void *A, int64_t rows, int32_t ld, int32_t col0,
+                                                                             int32_t ncols, void *stream) {
+    B200MED_REQUIRE(rows >= 0 && ncols >= 0 && col0 >= 0 && col0 + ncols <= ld, "bad shape");
+    if (rows == 0 || ncols == 0) return B200MED_OK;
+    B200MED_REQUIRE(A, "null pointer");
+    zero_cols_bf16_kernel<<<grid_for(rows * ncols), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16 *>(A), rows, ld,
+                                                                                    col0, ncols);
+    return after_launch("zero_cols_bf16_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_fwd(float *G, const float *c_prev, float *c_out,
+                                                                            void *h_next, int32_t ld_next, void *x_up,
+                                                                            int32_t ld_up, float *h_out, int64_t B, int32_t H,
+                                                                            float drop_p, const uint32_t *seed, uint64_t drop_base,
+                                                                            void *stream) {
+    B200MED_REQUIRE(B >= 1 && H >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
+    B200MED_REQUIRE(G && c_out, "null pointer");
+    lstm_cell_fwd_kernel<<<grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream>>>(
+        G, c_prev, c_out, reinterpret_cast<__nv_bfloat16 *>(h_next), ld_next, reinterpret_cast<__nv_bfloat16 *>(x_up), ld_up,
+        h_out, B, H, drop_p, seed, drop_base);
+    return after_launch("lstm_cell_fwd_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_bwd(const float *Gact, const float *c, const float *c_prev,
+                                                                            const float *dh_up, int32_t ld_up, const float *dh_rec,
+                                                                            int32_t ld_rec, float *dc, int32_t dc_init, void *dG,
+                                                                            int64_t B, int32_t H, float drop_p, const uint32_t *seed,
+                                                                            uint64_t drop_base, void *stream) {
+    B200MED_REQUIRE(B >= 1 && H >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
+    B200MED_REQUIRE(Gact && c && dc && dG, "null pointer");
+    lstm_cell_bwd_kernel<<<grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream>>>(
+        Gact, c, c_prev, dh_up, ld_up, dh_rec, ld_rec, dc, dc_init, reinterpret_cast<__nv_bfloat16 *>(dG), B, H, drop_p, seed,
+        drop_base);
+    return after_launch("lstm_cell_bwd_kernel");
+}

@@ -1,0 +1,127 @@
+"""nn.LSTM(batch_first, multi-layer, inter-layer dropout) forward + backward on the b200med kernels
+(throughput mode of the LSTM head, reference MED/modeling/models.py:161, 204-206).
+
+Every time step of every layer = one tcgen05 GEMM over ``[x_t | h_{t-1}]`` (K2 kernel) + one fused cell
+kernel (csrc/lstm.cu); the weight gradients of a layer are ONE MN-major GEMM over all ``W*B`` rows.
+Only ``h_{W-1}`` of the top layer is returned: that is all the reference head consumes
+(``F.relu(out)[:, -1, :]``, models.py:205-206).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import ops
+from ._lib import call
+
+
+def _raw(ptr: int) -> C.c_void_p:
+    return C.c_void_p(ptr)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _split_k(tiles: int, k_blocks: int) -> int:
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return max(1, min(want, k_blocks // 8 if k_blocks >= 16 else 1))
+
+
+class LSTMStackFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, drop_p, seed_dev, *params):
+        """x [B, F, W] f32 (the head input); params = (w_ih, w_hh, b_ih, b_hh) per layer; returns h_{W-1} [B, H]."""
+        B, F, W = x.shape
+        L = len(params) // 4
+        H = params[1].shape[1]
+        dev = x.device
+        st = _stream()
+        A, G, Cs, Wcat, Kp, ins = [], [], [], [], [], []
+        for l in range(L):
+            w_ih, w_hh, b_ih, b_hh = params[4 * l:4 * l + 4]
+            in_l = F if l == 0 else H
+            kp = (in_l + H + 7) // 8 * 8
+            wc = torch.zeros(4 * H, kp, dtype=torch.float32, device=dev)
+            wc[:, :in_l] = w_ih.detach()
+            wc[:, in_l:in_l + H] = w_hh.detach()
+            Wcat.append((ops.to_bf16(wc), (b_ih.detach() + b_hh.detach()).contiguous()))
+            A.append(torch.empty(W, B, kp, dtype=torch.bfloat16, device=dev))
+            G.append(torch.empty(W, B, 4 * H, dtype=torch.float32, device=dev))
+            Cs.append(torch.empty(W, B, H, dtype=torch.float32, device=dev))
+            Kp.append(kp); ins.append(in_l)
+        call("b200med_lstm_pack_inputs", _raw(x.contiguous().data_ptr()), _raw(A[0].data_ptr()), B, F, W, H, Kp[0], st)
+        for l in range(1, L):
+            call("b200med_zero_cols_bf16", _raw(A[l][0].data_ptr()), B, Kp[l], ins[l], H, st)
+            if Kp[l] > ins[l] + H:
+                call("b200med_zero_cols_bf16", _raw(A[l].data_ptr()), W * B, Kp[l], ins[l] + H, Kp[l] - ins[l] - H, st)
+        out = torch.empty(B, H, dtype=torch.float32, device=dev)
+        seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
+        for l in range(L):
+            wb, bias = Wcat[l]
+            p = drop_p if l < L - 1 else 0.0
+            for t in range(W):
+                ops.gemm_bf16(A[l][t], wb, B, 4 * H, Kp[l], True, True, bias=bias, out=G[l][t])
+                call("b200med_lstm_cell_fwd", _raw(G[l][t].data_ptr()), _raw(Cs[l][t - 1].data_ptr() if t else 0),
+                     _raw(Cs[l][t].data_ptr()),
+                     _raw(A[l][t + 1].data_ptr() + 2 * ins[l] if t + 1 < W else 0), Kp[l],
+                     _raw(A[l + 1][t].data_ptr() if l < L - 1 else 0), Kp[l + 1] if l < L - 1 else 0,
+                     _raw(out.data_ptr() if (l == L - 1 and t == W - 1) else 0), B, H, float(p), _raw(seed_ptr),
+                     (l * W + t) * B * H, st)
+        ctx.save_for_backward(*A, *G, *Cs, *[w for w, _ in Wcat])
+        ctx.meta = (B, F, W, L, H, Kp, ins, float(drop_p), seed_dev)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, F, W, L, H, Kp, ins, drop_p, seed_dev = ctx.meta
+        saved = ctx.saved_tensors
+        A, G, Cs, Wb = saved[:L], saved[L:2 * L], saved[2 * L:3 * L], saved[3 * L:4 * L]
+        dev = dout.device
+        st = _stream()
+        seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
+        dout = dout.contiguous().float()
+        grads = [None] * (4 * L)
+        dA_up, kp_up = None, 0
+        for l in reversed(range(L)):
+            dG = torch.empty(W, B, 4 * H, dtype=torch.bfloat16, device=dev)
+            dA = torch.empty(W, B, Kp[l], dtype=torch.float32, device=dev)
+            dc = torch.empty(B, H, dtype=torch.float32, device=dev)
+            for t in reversed(range(W)):
+                if l == L - 1:
+                    up_ptr, up_ld, p = (dout.data_ptr() if t == W - 1 else 0), H, 0.0
+                else:
+                    up_ptr, up_ld, p = dA_up[t].data_ptr(), kp_up, drop_p
+                rec_ptr = dA[t + 1].data_ptr() + 4 * ins[l] if t + 1 < W else 0
+                call("b200med_lstm_cell_bwd", _raw(G[l][t].data_ptr()), _raw(Cs[l][t].data_ptr()),
+                     _raw(Cs[l][t - 1].data_ptr() if t else 0), _raw(up_ptr), up_ld, _raw(rec_ptr), Kp[l],
+                     _raw(dc.data_ptr()), int(t == W - 1), _raw(dG[t].data_ptr()), B, H, float(p), _raw(seed_ptr),
+                     (l * W + t) * B * H, st)
+                # [dx_t | dh_{t-1}] [B, Kp] = dG_t [B, 4H] * Wcat [4H, Kp]   (B operand MN-major)
+                ops.gemm_bf16(dG[t], Wb[l], B, Kp[l], 4 * H, True, False, out_dtype=torch.float32, out=dA[t])
+            # dWcat [4H, Kp] = dG^T A over all W*B rows (both operands MN-major), deterministic split-K
+            tiles = ((4 * H + 127) // 128) * ((Kp[l] + 255) // 256)
+            dW = ops.gemm_bf16(dG.view(W * B, 4 * H), A[l].view(W * B, Kp[l]), 4 * H, Kp[l], W * B, False, False,
+                               out_dtype=torch.float32, split_k=_split_k(tiles, (W * B + 63) // 64))
+            db = ops.colsum(dG.view(W * B, 4 * H))
+            grads[4 * l] = dW[:, :ins[l]].contiguous()
+            grads[4 * l + 1] = dW[:, ins[l]:ins[l] + H].contiguous()
+            grads[4 * l + 2] = db
+            grads[4 * l + 3] = db.clone()
+            dA_up, kp_up = dA, Kp[l]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, F, W, dtype=torch.float32, device=dev)
+            call("b200med_lstm_unpack_dx", _raw(dA_up.data_ptr()), _raw(dx.data_ptr()), B, F, W, Kp[0], st)
+        return (dx, None, None, *grads)
+
+
+def lstm_last_hidden(x: torch.Tensor, lstm: torch.nn.LSTM, training: bool, seed_dev=None) -> torch.Tensor:
+    """h_{W-1} of the top layer for head input x [B, F, W]."""
+    params = []
+    for l in range(lstm.num_layers):
+        params += [getattr(lstm, f"weight_ih_l{l}"), getattr(lstm, f"weight_hh_l{l}"),
+                   getattr(lstm, f"bias_ih_l{l}"), getattr(lstm, f"bias_hh_l{l}")]
+    p = float(lstm.dropout) if training else 0.0
+    return LSTMStackFunction.apply(x, p, seed_dev, *params)

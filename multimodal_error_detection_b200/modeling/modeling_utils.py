@@ -195,6 +195,8 @@ def define_model_objects(exp_kwargs: dict, in_features_dict: dict, device, class
     model = instantiate_model(exp_kwargs, in_features_dict[exp_kwargs["data_type"]], window_size, device).to(device)
     if hasattr(model, "use_cudnn"):
         model.use_cudnn = precision != "fp32"
+        if precision == "bf16" and ops.has_tcgen05() and exp_kwargs.get("lstm_impl", "b200") == "b200":
+            model.impl = "b200"
     if exp_kwargs["data_type"] != "kinematics":
         feature_extractor = FeatureExtractor(input_dim=2048, output_dim=exp_kwargs["video_dims"], hidden_dims=[512, 256],
                                              precision=precision).to(device)
@@ -336,6 +338,8 @@ def train_single_epoch(model, feature_extractor, train_dataloader, criterion, op
     (probs, preds, labels, subjects) lists when ``return_train_preds``."""
     device = torch.device(device)
     _set_train(model, feature_extractor, exp_kwargs, True)
+    if _graph_step_ok(train_dataloader, feature_extractor, criterion, exp_kwargs):
+        return _train_epoch_graph(model, feature_extractor, train_dataloader, criterion, optimizer, scheduler, device, exp_kwargs)
     log = _EpochLog()
     subjects_all = []
     frame = exp_kwargs["dataset_type"] == "frame"
@@ -376,6 +380,78 @@ def train_single_epoch(model, feature_extractor, train_dataloader, criterion, op
     if exp_kwargs["return_train_preds"]:
         return (*res, log.cat_host("probs").tolist(), log.cat_host("preds").tolist(), log.cat_host("labels").tolist(),
                 subjects_all)
+    return res
+
+
+def _graph_step_ok(loader, feature_extractor, criterion, exp_kwargs) -> bool:
+    """The CUDA-graph step serves the binary window path over a DeviceWindowLoader.  Default: on in the bf16
+    throughput mode, off in the fp32 parity mode; ``exp_kwargs['cuda_graph']`` overrides."""
+    want = exp_kwargs.get("cuda_graph", getattr(feature_extractor, "precision", "fp32") == "bf16")
+    return bool(want) and isinstance(loader, DeviceWindowLoader) and exp_kwargs["dataset_type"] == "window" \
+        and exp_kwargs["error_type"] == "global" and isinstance(criterion, FusedBCEWithLogitsLoss) \
+        and exp_kwargs["data_type"] != "kinematics"
+
+
+def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, scheduler, device, exp_kwargs):
+    """train_single_epoch with every full batch replayed from ONE captured CUDA graph (engine.WindowTrainStep): per
+    step the host copies the batch's window indices (pinned, 8 B per window) and replays; the short last batch runs
+    eagerly.  Same return tuple and the same arithmetic as the eager loop."""
+    from ..engine import WindowTrainStep
+    ds, B = loader.dataset, loader.batch_size
+    key = (id(ds), id(model), id(feature_extractor), id(criterion), B)
+    stepper = getattr(optimizer, "_b200_stepper", None)
+    if stepper is None or stepper.key != key:
+        stepper = WindowTrainStep(ds, feature_extractor, model, criterion, optimizer, exp_kwargs, B)
+        stepper.key = key
+        optimizer._b200_stepper = stepper
+    log = _EpochLog()
+    subjects_all = []
+    want_preds = exp_kwargs["return_train_preds"]
+    for idx in loader.index_batches():
+        n = idx.numel()
+        if n == 0:
+            continue
+        if n == B:
+            stepper.load(idx.pin_memory())
+            if stepper.graph is None and not getattr(stepper, "graph_failed", False):
+                try:
+                    stepper.capture()
+                except Exception as e:      # capture is an optimisation: fall back to eager launches, loudly
+                    stepper.graph, stepper.graph_failed = None, True
+                    print(f"b200med: CUDA graph capture failed ({type(e).__name__}: {e}); running the step eagerly")
+            stepper.run()
+            loss, counts = stepper.loss.clone(), stepper.counts.clone()
+            extra = dict(preds=stepper.preds.clone(), labels=stepper.labels.clone(), probs=stepper.probs.clone()) if want_preds else {}
+        else:
+            didx = idx.pin_memory().to(device, non_blocking=True)
+            images, kin = ds.gather_batch(didx, image_dtype=_image_dtype(feature_extractor),
+                                          exact=_image_dtype(feature_extractor) == torch.float32)
+            y = define_error_labels(ds.e_labels_data.index_select(0, didx), exp_kwargs).float()
+            outputs = model(define_inputs(images, kin, feature_extractor, exp_kwargs, device))
+            loss, outputs = compute_loss(outputs, y, criterion, "window")
+            optimizer.zero_grad()
+            loss.backward()
+            _allreduce_grads(optimizer)
+            optimizer.step()
+            probs, preds, counts = criterion.last
+            loss = loss.detach().reshape(1)
+            extra = dict(preds=preds, labels=y.reshape(-1), probs=probs) if want_preds else {}
+        if exp_kwargs.get("host_sync") == "step":
+            loss.item()
+        log.add(loss, counts, **extra)
+        if want_preds:
+            subjects_all += ds.subjects_of(idx.tolist())
+    if scheduler is not None:
+        scheduler.step()
+    n_batches = max(len(log.losses), 1)
+    tot, cm = np.zeros(4), np.zeros((2, 2), dtype=int)
+    for c in log.counts_host():
+        f1, f1w, acc, jac, contrib = _batch_scores(c)
+        tot += (f1, f1w, acc, jac)
+        cm += contrib
+    res = (float(log.losses_host().sum() / n_batches), *(tot / n_batches).tolist(), cm)
+    if want_preds:
+        return (*res, log.cat_host("probs").tolist(), log.cat_host("preds").tolist(), log.cat_host("labels").tolist(), subjects_all)
     return res
 
 

@@ -178,12 +178,21 @@ class LSTM(nn.Module):
         # cuDNN's LSTM cell uses fast-math sigmoid/tanh (~20x the round-off of the CPU reference, measured);
         # the fp32 parity mode therefore runs the recurrence on the exact-math ATen kernels.
         self.use_cudnn = True
+        self.impl = "torch"            # "b200": recurrence on the b200med kernels (set by define_model_objects in bf16 mode)
+        self.register_buffer("_drop_seed", torch.zeros(1, dtype=torch.int32), persistent=False)  # not in state_dict
         self.linear_layers = nn.Sequential(
             nn.Flatten(), nn.Linear(hidden_size, 256), nn.ReLU(), nn.BatchNorm1d(256),
             nn.Linear(256, 64), nn.ReLU(), nn.BatchNorm1d(64), nn.Linear(64, n_classes))
         self.initialize_weights()
 
     def forward(self, l):
+        if self.impl == "b200" and l.is_cuda:
+            # throughput mode: tcgen05 gate GEMMs + fused cell kernels (lstm_stack.py); only h_{W-1} is needed
+            from ..lstm_stack import lstm_last_hidden
+            if self.training and self.lstm.dropout > 0:
+                self._drop_seed.add_(1)
+            h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed)
+            return self.linear_layers(F.relu(h))
         with torch.backends.cudnn.flags(enabled=self.use_cudnn):
             out, _ = self.lstm(l.transpose(1, 2).contiguous())
         return self.linear_layers(F.relu(out)[:, -1, :])

@@ -10,10 +10,12 @@ run t_models_fp32 python -m pytest tests/test_gpu_models.py -m gpu -q -k "not bf
 run t_models_bf16 python -m pytest tests/test_gpu_models.py -m gpu -q -k "bf16" --timeout 300
 run smoke python __graft_entry__.py --smoke
 TAIL=5 run bench_fp32 python bench.py --steps 5 --warmup 3 --precision fp32 --batch 2048 --videos 256 --cpu-windows 1024
+TAIL=3 run bench_cudnn python bench.py --steps 10 --warmup 3 --lstm-impl cudnn --no-graph --no-e2e --cpu-windows 512
+TAIL=3 run bench_eager python bench.py --steps 10 --warmup 3 --no-graph --no-e2e --cpu-windows 512
 TAIL=5 run bench python bench.py --steps 10 --warmup 3
 if [ -n "$PROFILE" ]; then
   # launch list (device time per launch; compare SHARES) and one full capture of the dominant HBM kernel
-  PCMD="python bench.py --steps 2 --warmup 3 --no-e2e --cpu-windows 512"
+  PCMD="python bench.py --steps 2 --warmup 3 --no-e2e --cpu-windows 512 --no-graph"
   $PCMD > gpurun_out/plain.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv $PCMD > gpurun_out/ncu_launches.log 2>&1
   echo "ncu launches exit $?"
