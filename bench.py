@@ -338,7 +338,16 @@ def run_gpu(args):
                 "clocks": clocks, "final_loss": final_loss}
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # graphs that captured NCCL work must be gone before the communicator is torn down; a wedged teardown must not
+        # turn a finished run into a hang, so the process leaves through os._exit after a final barrier
+        stepper.graph = None
+        opt._b200_stepper = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

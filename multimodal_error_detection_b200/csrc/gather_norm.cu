@@ -180,7 +180,6 @@ gather_norm_kernel(const __grid_constant__ GatherParams p) {
 // the table).  Thread 0 is the producer: it arms the stage's mbarrier with the byte count and issues
 // ONE cp.async.bulk per chunk; all threads consume.  A stage is re-armed only after the CTA-wide
 // barrier that follows its consumption, so no separate "empty" barrier is needed.
-constexpr int kTmaStages = 3;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -200,24 +199,25 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <typename OutT, bool EXACT>
-__global__ void __launch_bounds__(kThreads, 2)
+// R = rows per stage (stage = R*D*4 bytes), S = ring depth, T = threads per CTA.
+template <typename OutT, bool EXACT, int R, int S, int T>
+__global__ void __launch_bounds__(T)
 gather_norm_tma_kernel(const __grid_constant__ GatherParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kTmaStages];
+    __shared__ __align__(8) uint64_t full_bar[S];
     const StreamParams &sp = p.s[0];
     const int D = sp.dim;
     const int W = p.W;
     const int chunks = sp.chunks;
     const long long n_units = (long long)p.B * chunks;  // unit = (window, row chunk), all columns
-    const size_t stage_bytes = (size_t)kRowsPerUnit * D * sizeof(float);
-    float *stage_ptr[kTmaStages];
+    const size_t stage_bytes = (size_t)R * D * sizeof(float);
+    float *stage_ptr[S];
 #pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) stage_ptr[s] = reinterpret_cast<float *>(smem_raw + s * stage_bytes);
+    for (int s = 0; s < S; ++s) stage_ptr[s] = reinterpret_cast<float *>(smem_raw + s * stage_bytes);
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kTmaStages; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < S; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -225,8 +225,8 @@ gather_norm_tma_kernel(const __grid_constant__ GatherParams p) {
     auto issue = [&](long long unit, int stage) {
         const int chunk = (int)(unit % chunks);
         const long long b = unit / chunks;
-        const int t0 = chunk * kRowsPerUnit;
-        const int rows = min(kRowsPerUnit, W - t0);
+        const int t0 = chunk * R;
+        const int rows = min(R, W - t0);
         const uint32_t bytes = (uint32_t)((size_t)rows * D * sizeof(float));
         const float *src = reinterpret_cast<const float *>(sp.table) + ((long long)p.starts[b] + t0) * D;
         mbar_expect_tx(&full_bar[stage], bytes);
@@ -235,47 +235,74 @@ gather_norm_tma_kernel(const __grid_constant__ GatherParams p) {
 
     // prologue: fill the ring
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTmaStages; ++s) {
+        for (int s = 0; s < S; ++s) {
             const long long u = blockIdx.x + (long long)s * gridDim.x;
             if (u < n_units) issue(u, s);
         }
     }
 
-    const int nvec = D / 4;  // float4 per row
+    // Consumer mapping: a thread owns groups of 8 consecutive columns (two LDS.128 in, one 128-bit bf16 store or two
+    // 128-bit f32 stores out); for D = 8*T (the 2048-d image stream with 256 threads) that is exactly one group, whose
+    // mean / 1/std stay in registers for the whole kernel.
+    const int ngroups = D / 8;
+    const bool per_step = sp.stat_rows > 1;
+    float mu[8], sd[8];
+    auto load_stats = [&](int grp, int srow) {
+        if (sp.mean) {
+            const float4 *m4 = reinterpret_cast<const float4 *>(sp.mean + (long long)srow * D + grp * 8);
+            const float4 *s4 = reinterpret_cast<const float4 *>(sp.stdv + (long long)srow * D + grp * 8);
+            const float4 a0 = __ldg(m4), a1 = __ldg(m4 + 1), b0 = __ldg(s4), b1 = __ldg(s4 + 1);
+            mu[0] = a0.x; mu[1] = a0.y; mu[2] = a0.z; mu[3] = a0.w; mu[4] = a1.x; mu[5] = a1.y; mu[6] = a1.z; mu[7] = a1.w;
+            sd[0] = b0.x; sd[1] = b0.y; sd[2] = b0.z; sd[3] = b0.w; sd[4] = b1.x; sd[5] = b1.y; sd[6] = b1.z; sd[7] = b1.w;
+            if (!EXACT) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sd[k] = 1.0f / sd[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { mu[k] = 0.0f; sd[k] = 1.0f; }
+        }
+    };
+    const bool single_group = ngroups <= T;
+    if (single_group && !per_step && (int)threadIdx.x < ngroups) load_stats(threadIdx.x, 0);
+
     int it = 0;
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
-        const int stage = it % kTmaStages;
-        const uint32_t parity = (uint32_t)((it / kTmaStages) & 1);
+        const int stage = it % S;
+        const uint32_t parity = (uint32_t)((it / S) & 1);
         const int chunk = (int)(unit % chunks);
         const long long b = unit / chunks;
-        const int t0 = chunk * kRowsPerUnit;
-        const int rows = min(kRowsPerUnit, W - t0);
+        const int t0 = chunk * R;
+        const int rows = min(R, W - t0);
         mbar_wait(&full_bar[stage], parity);
-        const float4 *buf = reinterpret_cast<const float4 *>(stage_ptr[stage]);
+        const float *buf = stage_ptr[stage];
         OutT *dst_base = reinterpret_cast<OutT *>(sp.out) + ((long long)b * W + t0) * sp.out_ld + sp.out_col;
-        for (int r = 0; r < rows; ++r) {
-            const int srow = sp.stat_rows > 1 ? (t0 + r) : 0;
-            for (int v = threadIdx.x; v < nvec; v += kThreads) {
-                const float4 x = buf[r * nvec + v];
-                float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), sd = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (sp.mean) {
-                    mu = __ldg(reinterpret_cast<const float4 *>(sp.mean + (long long)srow * D) + v);
-                    sd = __ldg(reinterpret_cast<const float4 *>(sp.stdv + (long long)srow * D) + v);
-                    if (!EXACT) sd = make_float4(1.0f / sd.x, 1.0f / sd.y, 1.0f / sd.z, 1.0f / sd.w);
-                }
-                const float y0 = standardise<EXACT>(x.x, mu.x, sd.x), y1 = standardise<EXACT>(x.y, mu.y, sd.y),
-                            y2 = standardise<EXACT>(x.z, mu.z, sd.z), y3 = standardise<EXACT>(x.w, mu.w, sd.w);
-                OutT *d = dst_base + (long long)r * sp.out_ld + v * 4;
-                if constexpr (sizeof(OutT) == 4) {
-                    stg_stream(reinterpret_cast<float4 *>(d), make_float4(y0, y1, y2, y3));
-                } else {
-                    *reinterpret_cast<uint2 *>(d) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+        for (int grp = threadIdx.x; grp < ngroups; grp += T) {
+            if (!single_group && !per_step) load_stats(grp, 0);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r < rows) {
+                    if (per_step) load_stats(grp, t0 + r);
+                    const float4 x0 = *reinterpret_cast<const float4 *>(buf + (size_t)r * D + grp * 8);
+                    const float4 x1 = *reinterpret_cast<const float4 *>(buf + (size_t)r * D + grp * 8 + 4);
+                    const float y0 = standardise<EXACT>(x0.x, mu[0], sd[0]), y1 = standardise<EXACT>(x0.y, mu[1], sd[1]),
+                                y2 = standardise<EXACT>(x0.z, mu[2], sd[2]), y3 = standardise<EXACT>(x0.w, mu[3], sd[3]),
+                                y4 = standardise<EXACT>(x1.x, mu[4], sd[4]), y5 = standardise<EXACT>(x1.y, mu[5], sd[5]),
+                                y6 = standardise<EXACT>(x1.z, mu[6], sd[6]), y7 = standardise<EXACT>(x1.w, mu[7], sd[7]);
+                    OutT *d = dst_base + (long long)r * sp.out_ld + grp * 8;
+                    if constexpr (sizeof(OutT) == 4) {
+                        stg_stream(reinterpret_cast<float4 *>(d), make_float4(y0, y1, y2, y3));
+                        stg_stream(reinterpret_cast<float4 *>(d) + 1, make_float4(y4, y5, y6, y7));
+                    } else {
+                        stg_stream(reinterpret_cast<uint4 *>(d), make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3),
+                                                                           pack_bf16x2(y4, y5), pack_bf16x2(y6, y7)));
+                    }
                 }
             }
         }
         __syncthreads();  // everyone is done reading this stage
         if (threadIdx.x == 0) {
-            const long long next = unit + (long long)kTmaStages * gridDim.x;
+            const long long next = unit + (long long)S * gridDim.x;
             if (next < n_units) issue(next, stage);
         }
     }
@@ -342,27 +369,47 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const 
 
     // TMA staging: only for a single wide f32 stream (the image stream); other streams of the call
     // go through the LDG kernel in a second launch.
-    if (variant == 2 && p.s[0].path == 1) {
+    // variant 0 = measured best per output type (bench_gather, B200): f32 output -> LDG path (0.84-0.85 of the copy
+    // peak at B=8192); bf16 output -> TMA staging ring, 8-row stages when W is a multiple of 8 (0.85), else 2-row stages.
+    if (variant == 0 && p.s[0].path == 1 && p.s[0].out_dtype == B200MED_BF16 && B * (long long)W >= 4096)
+        variant = (W % 8 == 0) ? 5 : 4;
+    if (variant >= 2 && variant != 3 && p.s[0].path == 1) {
         GatherParams pt = p;
         pt.n_streams = 1;
-        pt.s[0].chunks = (W + kRowsPerUnit - 1) / kRowsPerUnit;
-        const size_t smem = (size_t)kTmaStages * kRowsPerUnit * pt.s[0].dim * sizeof(float);
+        // variant -> (rows per stage, stages, threads): 2 = (4,3,256)  4 = (2,4,256)  5 = (8,3,256)  6 = (4,3,512)  7 = (2,6,256)
+        int R = 4, S = 3, T = 256;
+        if (variant == 4) { R = 2; S = 4; }
+        else if (variant == 5) { R = 8; S = 3; }
+        else if (variant == 6) { T = 512; }
+        else if (variant == 7) { R = 2; S = 6; }
+        pt.s[0].chunks = (W + R - 1) / R;
+        const size_t smem = (size_t)S * R * pt.s[0].dim * sizeof(float);
         B200MED_REQUIRE(smem <= 200 * 1024, "row too wide for the TMA staging ring");
         const long long n_units = (long long)B * pt.s[0].chunks;
-        const long long cap_t = 2LL * num_sms();
+        const int per_sm = (int)((220 * 1024) / (smem + 1024));
+        const long long cap_t = (long long)(per_sm < 1 ? 1 : per_sm) * num_sms();
         const int grid = (int)(n_units < cap_t ? n_units : cap_t);
-        auto launch = [&](auto kern) -> int {
+        auto launch = [&](auto kern, int threads) -> int {
             if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                    "cudaFuncSetAttribute(gather_norm_tma)")) return e;
-            kern<<<grid, kThreads, smem, st>>>(pt);
+            kern<<<grid, threads, smem, st>>>(pt);
             return after_launch("gather_norm_tma_kernel");
         };
-        int e;
-        if (pt.s[0].out_dtype == B200MED_F32)
-            e = pt.s[0].exact_div ? launch(gather_norm_tma_kernel<float, true>) : launch(gather_norm_tma_kernel<float, false>);
-        else
-            e = pt.s[0].exact_div ? launch(gather_norm_tma_kernel<__nv_bfloat16, true>)
-                                  : launch(gather_norm_tma_kernel<__nv_bfloat16, false>);
+        const bool f32 = pt.s[0].out_dtype == B200MED_F32, ex = pt.s[0].exact_div != 0;
+        int e = B200MED_E_UNSUPPORTED;
+#define B200MED_TMA_CASE(RR, SS, TT)                                                                              \
+        if (R == RR && S == SS && T == TT) {                                                                          \
+            if (f32) e = ex ? launch(gather_norm_tma_kernel<float, true, RR, SS, TT>, TT)                             \
+                            : launch(gather_norm_tma_kernel<float, false, RR, SS, TT>, TT);                           \
+            else e = ex ? launch(gather_norm_tma_kernel<__nv_bfloat16, true, RR, SS, TT>, TT)                         \
+                        : launch(gather_norm_tma_kernel<__nv_bfloat16, false, RR, SS, TT>, TT);                       \
+        }
+        B200MED_TMA_CASE(4, 3, 256)
+        B200MED_TMA_CASE(2, 4, 256)
+        B200MED_TMA_CASE(8, 3, 256)
+        B200MED_TMA_CASE(4, 3, 512)
+        B200MED_TMA_CASE(2, 6, 256)
+#undef B200MED_TMA_CASE
         if (e) return e;
         if (n_streams == 1) return B200MED_OK;
         // remaining streams
