@@ -360,7 +360,7 @@ def main():
     ap.add_argument("--videos", type=int, default=1024)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--lstm-impl", default="b200", choices=["b200", "cudnn"])
+    ap.add_argument("--lstm-impl", default="b200", choices=["b200", "b200_per_step", "cudnn"])
     ap.add_argument("--gather-variant", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-windows", type=int, default=4096)

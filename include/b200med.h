@@ -34,6 +34,13 @@ extern "C" {
 
 #define B200MED_F32 0
 #define B200MED_BF16 1
+#define B200MED_F16 2   /* GEMM output only (RBI32 layout): bounded quantities such as LSTM gate pre-activations */
+
+/* Output layouts of b200med_gemm_bf16: plain row-major, or row-block-interleaved [M/32][N/V][32][V] with
+ * V = elements per 16 bytes (4 for f32, 8 for bf16) -- the layout in which kernels that own one matrix ROW per
+ * thread (TMEM lane = row) read and write 512 contiguous bytes per warp access (see csrc/lstm_rec.cu).    */
+#define B200MED_LAYOUT_ROWMAJOR 0
+#define B200MED_LAYOUT_RBI32 1
 
 int b200med_version(void);
 const char *b200med_last_error(void);
@@ -131,15 +138,18 @@ int b200med_linear_bwd_weight_f32(const float *dy, const float *x, float *dw, fl
  *   a_kmajor / b_kmajor: 1 if the operand is stored [rows, K] (K contiguous); 0 if it is stored
  *   [K, rows] (rows contiguous, "MN-major") -- used by the weight-gradient GEMM whose reduction
  *   dimension is the row index of both activations.
- *   out_dtype: B200MED_BF16 or B200MED_F32.  bias [N] f32 or NULL.  relu: apply max(.,0).
+ *   out_dtype: B200MED_BF16, B200MED_F32 or (RBI32 layout only) B200MED_F16, saturated.  bias [N] f32 or NULL.
+ *   relu: apply max(.,0).
  *   mask [M,N] bf16 or NULL: multiply the result by (mask > 0) (ReLU backward).
  *   split_k > 1: K is split over split_k CTAs whose fp32 partial tiles are summed in a fixed
- *   order (deterministic); needs workspace >= b200med_gemm_bf16_ws_bytes().                       */
+ *   order (deterministic); needs workspace >= b200med_gemm_bf16_ws_bytes().
+ *   out_layout: B200MED_LAYOUT_ROWMAJOR, or B200MED_LAYOUT_RBI32 (needs split_k = 1, no mask, N a multiple of
+ *   the vector width, D allocated for M rounded up to 32 rows; ldd is ignored).                    */
 int64_t b200med_gemm_bf16_ws_bytes(int64_t M, int64_t N, int64_t K, int32_t split_k);
 int b200med_gemm_bf16(const void *A, const void *B, void *D, const float *bias, const void *mask,
                       int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd,
                       int32_t a_kmajor, int32_t b_kmajor, int32_t out_dtype, int32_t relu,
-                      int32_t split_k, void *workspace, void *stream);
+                      int32_t split_k, int32_t out_layout, void *workspace, void *stream);
 /* 1 if the tcgen05 path can run on the current device (compute capability 10.x). */
 int b200med_has_tcgen05(void);
 
@@ -157,12 +167,13 @@ int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream);
  * over [x_t | h_{t-1}] plus one fused cell kernel.  Time-major buffers, see csrc/lstm.cu.
  * ---------------------------------------------------------------------------------------------- */
 
-/* x [B,F,W] f32 (the reference's [batch, features, time] head input) -> A0 [W,B,Kp] bf16 columns [0,F);
- * zeroes the padding columns [F+H,Kp) and the h_{-1} columns [F,F+H) of step 0.                    */
-int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int32_t F, int32_t W, int32_t H,
-                             int32_t Kp, void *stream);
-/* dx [B,F,W] f32 <- dA0 [W,B,Kp] f32 columns [0,F).                                                 */
-int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int32_t F, int32_t W, int32_t Kp,
+/* x [B,F,W] f32 (the reference's [batch, features, time] head input) -> A0 [W,Bpad,Kp] bf16 columns [0,F) of the
+ * rows b < B (Bpad >= B: rows per time step in the buffer); the h_{t-1} columns are [hoff,hoff+H) (hoff >= F);
+ * zeroes the padding columns [F,hoff) and [hoff+H,Kp) and the h_{-1} columns of step 0.              */
+int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int64_t Bpad, int32_t F, int32_t W, int32_t H,
+                             int32_t Kp, int32_t hoff, void *stream);
+/* dx [B,F,W] f32 <- dA0 [W,Bpad,Kp] f32 (row-major) columns [0,F).                                   */
+int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int64_t Bpad, int32_t F, int32_t W, int32_t Kp,
                            void *stream);
 /* A[r, col0:col0+ncols] = 0 for r < rows (bf16 matrix with leading dimension ld).                   */
 int b200med_zero_cols_bf16(void *A, int64_t rows, int32_t ld, int32_t col0, int32_t ncols, void *stream);
@@ -180,6 +191,26 @@ int b200med_lstm_cell_bwd(const float *Gact, const float *c, const float *c_prev
                           int32_t ld_up, const float *dh_rec, int32_t ld_rec, float *dc, int32_t dc_init,
                           void *dG, int64_t B, int32_t H, float drop_p, const uint32_t *seed,
                           uint64_t drop_base, void *stream);
+
+/* Persistent recurrence, one launch per layer and direction (csrc/lstm_rec.cu; hidden_size H = 128 only).
+ * A CTA owns 128 windows and walks all W steps: W_hh (bf16 [4H,H], nn.LSTM weight_hh_l{k} layout) stays in
+ * shared memory, the gate accumulator in TMEM, c_t in registers.  Time-major buffers with the batch padded to
+ * Bpad (multiple of 32) rows per step.  "RBI" = row-block-interleaved layout [rows/32][cols/V][32][V], V = elements
+ * per 16 bytes (what b200med_gemm_bf16 writes with out_layout = B200MED_LAYOUT_RBI32).
+ *   forward:  xg RBI fp16 [W*Bpad,4H] = x_t W_ih^T + b_ih + b_hh for every step (one GEMM beforehand).
+ *             gact RBI fp16 [W*Bpad,4H] OUT activated gates, c RBI f32 [W*Bpad,H] OUT cell states (both NULL =
+ *             inference, nothing saved).  a_next = A_l [W,Bpad,ld_next] bf16 row-major: h_t is TMA-stored to
+ *             A_l[t+1][:, hoff:hoff+H]; a_up = A_{l+1} [W,Bpad,ld_up]: dropout(h_t) -> A_{l+1}[t][:, 0:H]; h_{W-1} ->
+ *             h_out [B,H] f32; each may be NULL.  Dropout mask = f(*seed, drop_base + (t*Bpad+b)*H + j).
+ *   backward: dh_t = dropout'(dh_up[t,b,:]) (+ dh_top [B,H] at t = W-1) + dG_{t+1} W_hh;  dh_up RBI f32
+ *             [W*Bpad, up_cols]; dG [W,Bpad,4H] bf16 row-major OUT (TMA store) with PERMUTED gate columns:
+ *             column' = (u/64)*256 + ((u%64)/16)*64 + gate*16 + u%16 holds gate column gate*H + u.                   */
+int b200med_lstm_rec_fwd(const void *xg, const void *whh_bf16, void *gact, float *c, void *a_next, int32_t ld_next,
+                         int32_t hoff, void *a_up, int32_t ld_up, float *h_out, int64_t B, int64_t Bpad, int32_t W,
+                         int32_t H, float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream);
+int b200med_lstm_rec_bwd(const void *gact, const float *c, const void *whh_bf16, const float *dh_top,
+                         const float *dh_up, int32_t up_cols, void *dG, int64_t B, int64_t Bpad, int32_t W, int32_t H,
+                         float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3  Fused loss + gradient + metric counts (latency-bound; deterministic reductions)

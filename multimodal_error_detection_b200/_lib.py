@@ -11,7 +11,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libb200med.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 
 
 class StreamDesc(C.Structure):
@@ -39,14 +39,17 @@ SIGNATURES = {
     "b200med_linear_bwd_weight_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
     "b200med_gemm_bf16_ws_bytes": (_i64, [_i64, _i64, _i64, _i32]),
     "b200med_gemm_bf16": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32,
-                                    _i32, _p, _p]),
+                                    _i32, _i32, _p, _p]),
     "b200med_has_tcgen05": (C.c_int, []),
     "b200med_colsum": (C.c_int, [_p, _i32, _p, _i64, _i32, _i64, _p, _p]),
     "b200med_colsum_ws_bytes": (_i64, [_i64, _i32]),
     "b200med_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_cast_bf16_to_f32": (C.c_int, [_p, _p, _i64, _p]),
-    "b200med_lstm_pack_inputs": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p]),
-    "b200med_lstm_unpack_dx": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p]),
+    "b200med_lstm_pack_inputs": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _p]),
+    "b200med_lstm_rec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p,
+                                       C.c_uint64, _p]),
+    "b200med_lstm_rec_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_lstm_unpack_dx": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "b200med_zero_cols_bf16": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p]),
     "b200med_lstm_cell_fwd": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _p, _i64, _i32, _f, _p, C.c_uint64, _p]),
     "b200med_lstm_cell_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _i64, _i32, _f, _p, C.c_uint64, _p]),

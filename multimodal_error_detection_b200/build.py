@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libb200med.so")
 SOURCES = ["api_common.cu", "window_index.cu", "gather_norm.cu", "gemm_f32.cu", "gemm_tcgen05.cu",
-           "loss_metrics.cu", "adam.cu", "ensemble.cu", "lstm.cu"]
+           "loss_metrics.cu", "adam.cu", "ensemble.cu", "lstm.cu", "lstm_rec.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -38,7 +38,7 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(PKG), "include", "b200med.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tcgen05.cuh"), os.path.join(os.path.dirname(PKG), "include", "b200med.h")]
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

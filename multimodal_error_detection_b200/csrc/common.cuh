@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -75,6 +76,14 @@ __device__ __forceinline__ void stg_stream(uint4 *p, const uint4 &v) {
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// fp16 pair, saturated to the finite range (used for bounded quantities: LSTM gate pre-activations / activations)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    lo = fminf(fmaxf(lo, -65504.0f), 65504.0f);
+    hi = fminf(fmaxf(hi, -65504.0f), 65504.0f);
+    __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
 }
 

@@ -19,8 +19,7 @@
 // Roofline: tensor pipe.  128x256x16 per instruction = 128 cycles at cta_group::1, operand traffic
 // 12 KB per instruction = 96 B/cycle of shared-memory bandwidth (below the 128 B/cycle port), which
 // is why BLOCK_N = 256 is the default tile for the wide layers.
-#include "common.cuh"
-#include <cuda.h>
+#include "tcgen05.cuh"
 
 namespace b200med {
 
@@ -29,81 +28,6 @@ constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 192;
 constexpr uint32_t kATileBytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
-
-__device__ __forceinline__ uint32_t s_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s_addr(bar)) : "memory");
-}
-// Bounded spin: a mis-programmed pipeline traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
-        if (!done && spins > (1u << 22)) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        :: "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
-//   bits [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
-//   [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// Instruction descriptor for kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
-// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 :: "r"(s_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct GemmParams {
     long long M, N, K;
@@ -114,6 +38,8 @@ struct GemmParams {
     int split_k;            // >= 1
     int kb_per_split;       // k-blocks per split
     int tiles_m, tiles_n;
+    int out_f16;            // 1: fp16 output (16-bit paths write half instead of bfloat16); needs split_k == 1
+    int out_rbi;            // 1: row-block-interleaved output [M/32][N/V][32][V] (split_k == 1, no mask)
     const float *bias;      // [N] or null (ignored when split_k > 1)
     const __nv_bfloat16 *mask;  // [M, ldd] or null (ignored when split_k > 1)
     void *D;                // output, or the fp32 partial workspace when split_k > 1
@@ -294,7 +220,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             }
                         }
                     }
-                    if (p.out_f32 || partial) {
+                    if (p.out_rbi) {
+                        // one 16-byte vector per lane and column group: a warp writes 512 contiguous bytes
+                        const long long rb = m >> 5;
+                        const int rl = (int)(m & 31);
+                        if (p.out_f32) {
+                            float *base = reinterpret_cast<float *>(p.D);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                if (n_base + 4 * q < p.N)
+                                    *reinterpret_cast<float4 *>(base + ((rb * (p.N >> 2) + ((n_base >> 2) + q)) * 32 + rl) * 4) =
+                                        make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                        } else {
+                            __nv_bfloat16 *base = reinterpret_cast<__nv_bfloat16 *>(p.D);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (n_base + 8 * q < p.N)
+                                    *reinterpret_cast<uint4 *>(base + ((rb * (p.N >> 3) + ((n_base >> 3) + q)) * 32 + rl) * 8) =
+                                        p.out_f16
+                                            ? make_uint4(pack_f16x2(f[8 * q], f[8 * q + 1]), pack_f16x2(f[8 * q + 2], f[8 * q + 3]),
+                                                         pack_f16x2(f[8 * q + 4], f[8 * q + 5]), pack_f16x2(f[8 * q + 6], f[8 * q + 7]))
+                                            : make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
+                                                         pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+                        }
+                    } else if (p.out_f32 || partial) {
                         float *dst = reinterpret_cast<float *>(p.D) +
                                      (partial ? (long long)z * p.M * p.N + m * p.N : m * p.ldd) + n_base;
                         if (full && (((uintptr_t)dst) % 16 == 0)) {
@@ -355,45 +304,6 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ part, int split, 
     }
 }
 
-// ---- host side ---------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, `ld` elements between rows.
-static int make_tmap(CUtensorMap *map, const void *ptr, long long inner, long long outer, long long ld,
-                     int box_inner, int box_outer) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200MED_E_CUDA; }
-    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (CUresult %d) inner=%lld outer=%lld ld=%lld box=%dx%d", (int)r, inner,
-                  outer, ld, box_inner, box_outer);
-        return B200MED_E_CUDA;
-    }
-    return B200MED_OK;
-}
-
 static int pick_block_n(long long N, int b_kmajor) {
     if (N >= 256) return 256;
     if (N > 64) return 128;
@@ -436,13 +346,17 @@ extern "C" __attribute__((visibility("default"))) int64_t b200med_gemm_bf16_ws_b
 extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const void *A, const void *B, void *D, const float *bias, const void *mask,
                                  int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd,
                                  int32_t a_kmajor, int32_t b_kmajor, int32_t out_dtype, int32_t relu,
-                                 int32_t split_k, void *workspace, void *stream) {
+                                 int32_t split_k, int32_t out_layout, void *workspace, void *stream) {
     B200MED_REQUIRE(M >= 1 && N >= 1 && K >= 1, "bad shape");
     B200MED_REQUIRE(A && B && D, "null pointer");
     B200MED_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "operand leading dimensions must be multiples of 8 elements (16 bytes)");
     B200MED_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "operands must be 16-byte aligned");
-    B200MED_REQUIRE(out_dtype == B200MED_BF16 || out_dtype == B200MED_F32, "bad out dtype");
-    B200MED_REQUIRE(ldd >= N, "ldd < N");
+    B200MED_REQUIRE(out_dtype == B200MED_BF16 || out_dtype == B200MED_F32 || out_dtype == B200MED_F16, "bad out dtype");
+    B200MED_REQUIRE(out_dtype != B200MED_F16 || out_layout == B200MED_LAYOUT_RBI32, "fp16 output is only implemented for the RBI32 layout");
+    B200MED_REQUIRE(out_layout == B200MED_LAYOUT_ROWMAJOR || out_layout == B200MED_LAYOUT_RBI32, "bad out_layout");
+    B200MED_REQUIRE(out_layout == B200MED_LAYOUT_RBI32 || ldd >= N, "ldd < N");
+    B200MED_REQUIRE(out_layout == B200MED_LAYOUT_ROWMAJOR || (split_k <= 1 && !mask && N % (out_dtype == B200MED_F32 ? 4 : 8) == 0),
+                    "RBI32 output needs split_k = 1, no mask and N a multiple of the 16-byte vector width");
     if (!b200med_has_tcgen05()) { set_error("tcgen05 path needs a compute-capability 10.x device"); return B200MED_E_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
 
@@ -469,6 +383,8 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
     p.bias = split_k > 1 ? nullptr : bias;
     p.mask = split_k > 1 ? nullptr : reinterpret_cast<const __nv_bfloat16 *>(mask);
     p.D = split_k > 1 ? workspace : D;
+    p.out_rbi = out_layout == B200MED_LAYOUT_RBI32;
+    p.out_f16 = out_dtype == B200MED_F16;
 
     int e;
     switch (block_n) {

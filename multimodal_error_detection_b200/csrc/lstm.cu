@@ -35,30 +35,32 @@ __device__ __forceinline__ bool dropout_keep(uint32_t seed, unsigned long long i
     return u >= p;
 }
 
-// x [B, F, W] f32 (the reference's [batch, features, time] layout) -> A0 [W, B, Kp] bf16 columns [0, F);
-// also zeroes the padding columns [F+H, Kp) of every step and the h_{-1} columns [F, F+H) of step 0.
-__global__ void lstm_pack_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, long long B, int F, int W,
-                                 int H, int Kp) {
+// x [B, F, W] f32 (the reference's [batch, features, time] layout) -> A0 [W, Bpad, Kp] bf16 columns [0, F), rows b < B;
+// also zeroes the padding columns [F, hoff) and [hoff+H, Kp) of every step and the h_{-1} columns [hoff, hoff+H) of step 0.
+__global__ void lstm_pack_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad,
+                                 int F, int W, int H, int Kp, int hoff) {
     const long long total = B * (long long)W * Kp;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(e % Kp);
         const long long r = e / Kp;
         const long long b = r % B;
         const int t = (int)(r / B);
-        if (k < F) A0[e] = __float2bfloat16_rn(x[(b * F + k) * W + t]);
-        else if (k >= F + H || t == 0) A0[e] = __float2bfloat16_rn(0.0f);
+        __nv_bfloat16 *dst = A0 + ((long long)t * Bpad + b) * Kp + k;
+        if (k < F) *dst = __float2bfloat16_rn(x[(b * F + k) * W + t]);
+        else if (k < hoff || k >= hoff + H || t == 0) *dst = __float2bfloat16_rn(0.0f);
     }
 }
 
-// dx [B, F, W] f32 <- dA0 [W, B, Kp] f32 columns [0, F)
-__global__ void lstm_unpack_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, int F, int W, int Kp) {
+// dx [B, F, W] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F)
+__global__ void lstm_unpack_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F,
+                                   int W, int Kp) {
     const long long total = B * (long long)F * W;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(e % W);
         const long long r = e / W;
         const int k = (int)(r % F);
         const long long b = r / F;
-        dx[e] = dA0[((long long)t * B + b) * Kp + k];
+        dx[e] = dA0[((long long)t * Bpad + b) * Kp + k];
     }
 }
 
@@ -137,20 +139,21 @@ static unsigned grid_for(long long total) {
 
 using namespace b200med;
 
-extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int32_t F,
-                                                                               int32_t W, int32_t H, int32_t Kp, void *stream) {
-    B200MED_REQUIRE(B >= 1 && F >= 1 && W >= 1 && H >= 1 && Kp >= F + H, "bad shape");
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int64_t Bpad,
+                                                                               int32_t F, int32_t W, int32_t H, int32_t Kp,
+                                                                               int32_t hoff, void *stream) {
+    B200MED_REQUIRE(B >= 1 && Bpad >= B && F >= 1 && W >= 1 && H >= 1 && hoff >= F && Kp >= hoff + H, "bad shape");
     B200MED_REQUIRE(x && A0, "null pointer");
     lstm_pack_kernel<<<grid_for(B * (long long)W * Kp), 256, 0, (cudaStream_t)stream>>>(
-        x, reinterpret_cast<__nv_bfloat16 *>(A0), B, F, W, H, Kp);
+        x, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, F, W, H, Kp, hoff);
     return after_launch("lstm_pack_kernel");
 }
 
-extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int32_t F,
-                                                                             int32_t W, int32_t Kp, void *stream) {
-    B200MED_REQUIRE(B >= 1 && F >= 1 && W >= 1 && Kp >= F, "bad shape");
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int64_t Bpad,
+                                                                             int32_t F, int32_t W, int32_t Kp, void *stream) {
+    B200MED_REQUIRE(B >= 1 && Bpad >= B && F >= 1 && W >= 1 && Kp >= F, "bad shape");
     B200MED_REQUIRE(dA0 && dx, "null pointer");
-    lstm_unpack_kernel<<<grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream>>>(dA0, dx, B, F, W, Kp);
+    lstm_unpack_kernel<<<grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream>>>(dA0, dx, B, Bpad, F, W, Kp);
     return after_launch("lstm_unpack_kernel");
 }
 

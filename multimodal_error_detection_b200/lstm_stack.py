@@ -1,8 +1,11 @@
 """nn.LSTM(batch_first, multi-layer, inter-layer dropout) forward + backward on the b200med kernels
 (throughput mode of the LSTM head, reference MED/modeling/models.py:161, 204-206).
 
-Every time step of every layer = one tcgen05 GEMM over ``[x_t | h_{t-1}]`` (K2 kernel) + one fused cell
-kernel (csrc/lstm.cu); the weight gradients of a layer are ONE MN-major GEMM over all ``W*B`` rows.
+hidden_size 128 (every reference config): ``LSTMRecFunction`` -- per layer ONE batched tcgen05 GEMM for the x-part
+of the gates over all ``W*B`` rows + ONE persistent recurrence kernel that keeps W_hh in shared memory, the gates in
+TMEM and walks all W steps (csrc/lstm_rec.cu); the backward mirrors it (persistent kernel -> dG, then batched
+dX = dG W_ih and dW = dG^T [x|h] GEMMs).  Other hidden sizes: ``LSTMStackFunction`` -- one GEMM over
+``[x_t | h_{t-1}]`` + one fused cell kernel per time step (csrc/lstm.cu).
 Only ``h_{W-1}`` of the top layer is returned: that is all the reference head consumes
 (``F.relu(out)[:, -1, :]``, models.py:205-206).
 """
@@ -51,7 +54,7 @@ class LSTMStackFunction(torch.autograd.Function):
             G.append(torch.empty(W, B, 4 * H, dtype=torch.float32, device=dev))
             Cs.append(torch.empty(W, B, H, dtype=torch.float32, device=dev))
             Kp.append(kp); ins.append(in_l)
-        call("b200med_lstm_pack_inputs", _raw(x.contiguous().data_ptr()), _raw(A[0].data_ptr()), B, F, W, H, Kp[0], st)
+        call("b200med_lstm_pack_inputs", _raw(x.contiguous().data_ptr()), _raw(A[0].data_ptr()), B, B, F, W, H, Kp[0], F, st)
         for l in range(1, L):
             call("b200med_zero_cols_bf16", _raw(A[l][0].data_ptr()), B, Kp[l], ins[l], H, st)
             if Kp[l] > ins[l] + H:
@@ -113,15 +116,128 @@ class LSTMStackFunction(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, F, W, dtype=torch.float32, device=dev)
-            call("b200med_lstm_unpack_dx", _raw(dA_up.data_ptr()), _raw(dx.data_ptr()), B, F, W, Kp[0], st)
+            call("b200med_lstm_unpack_dx", _raw(dA_up.data_ptr()), _raw(dx.data_ptr()), B, B, F, W, Kp[0], st)
         return (dx, None, None, *grads)
 
 
-def lstm_last_hidden(x: torch.Tensor, lstm: torch.nn.LSTM, training: bool, seed_dev=None) -> torch.Tensor:
+_PERM = {}
+
+
+def _dg_perm(H: int, device):
+    """Column permutation of the recurrence kernel's dG output (csrc/lstm_rec.cu): returns (orig_of_col', col'_of_orig)."""
+    key = (H, str(device))
+    if key not in _PERM:
+        cp = torch.arange(4 * H)
+        uh, c, g, i = cp // 256, (cp % 256) // 64, (cp % 64) // 16, cp % 16
+        orig = g * H + uh * 64 + c * 16 + i
+        inv = torch.empty_like(orig)
+        inv[orig] = cp
+        _PERM[key] = (orig.to(device), inv.to(device))
+    return _PERM[key]
+
+
+class LSTMRecFunction(torch.autograd.Function):
+    """Persistent-recurrence path (hidden_size 128).  Layer buffers, time-major with the batch padded to Bp (multiple
+    of 32) rows per step:
+    A_l [W, Bp, inp_l + H] bf16 row-major = [x_t (padded to a multiple of 64) | h_{t-1}] (operand of the x-part GEMM and of dW),
+    dG_l [W, Bp, 4H] bf16 row-major; row-block-interleaved (csrc/lstm_rec.cu): xg / gact_l [W*Bp, 4H] fp16, c_l [W*Bp, H] f32,
+    dX_l [W*Bp, inp_l] f32."""
+
+    @staticmethod
+    def forward(ctx, x, drop_p, seed_dev, *params):
+        B, F, W = x.shape
+        L = len(params) // 4
+        H = params[1].shape[1]
+        dev = x.device
+        st = _stream()
+        Bp = (B + 31) // 32 * 32
+        ins = [F if l == 0 else H for l in range(L)]
+        inp = [(i + 63) // 64 * 64 for i in ins]
+        Kp = [ip + H for ip in inp]
+        need_grad = any(ctx.needs_input_grad)
+        alloc = torch.empty if Bp == B else torch.zeros          # pad rows must hold finite values
+        A = [alloc(W, Bp, Kp[l], dtype=torch.bfloat16, device=dev) for l in range(L)]
+        call("b200med_lstm_pack_inputs", _raw(x.contiguous().data_ptr()), _raw(A[0].data_ptr()), B, Bp, F, W, H, Kp[0], inp[0], st)
+        for l in range(1, L):
+            call("b200med_zero_cols_bf16", _raw(A[l][0].data_ptr()), Bp, Kp[l], inp[l], H, st)
+        out = torch.empty(B, H, dtype=torch.float32, device=dev)
+        seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
+        Wih, Whh, Gact, Cs = [], [], [], []
+        xg = torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev)
+        for l in range(L):
+            w_ih, w_hh, b_ih, b_hh = params[4 * l:4 * l + 4]
+            if inp[l] == ins[l]:
+                wih = ops.to_bf16(w_ih.detach().contiguous())
+            else:
+                wpad = torch.zeros(4 * H, inp[l], dtype=torch.float32, device=dev)
+                wpad[:, :ins[l]] = w_ih.detach()
+                wih = ops.to_bf16(wpad)
+            whh = ops.to_bf16(w_hh.detach().contiguous())
+            bias = (b_ih.detach() + b_hh.detach()).contiguous()
+            Wih.append(wih); Whh.append(whh)
+            # x-part of the gates for every step at once: [W*Bp, inp] x [4H, inp]^T + bias
+            ops.gemm_bf16(A[l].view(W * Bp, Kp[l]), wih, W * Bp, 4 * H, inp[l], True, True, bias=bias, out=xg, rbi=True)
+            gact = torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev) if need_grad else None
+            cs = torch.empty(W * Bp, H, dtype=torch.float32, device=dev) if need_grad else None
+            top = l == L - 1
+            call("b200med_lstm_rec_fwd", _raw(xg.data_ptr()), _raw(whh.data_ptr()),
+                 _raw(gact.data_ptr() if need_grad else 0), _raw(cs.data_ptr() if need_grad else 0),
+                 _raw(A[l].data_ptr() if need_grad else 0), Kp[l], inp[l],
+                 _raw(0 if top else A[l + 1].data_ptr()), 0 if top else Kp[l + 1],
+                 _raw(out.data_ptr() if top else 0), B, Bp, W, H, 0.0 if top else float(drop_p), _raw(seed_ptr),
+                 l * W * Bp * H, st)
+            Gact.append(gact); Cs.append(cs)
+        if need_grad:
+            ctx.save_for_backward(*A, *Gact, *Cs, *Wih, *Whh)
+        ctx.meta = (B, Bp, F, W, L, H, Kp, ins, inp, float(drop_p), seed_dev)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, Bp, F, W, L, H, Kp, ins, inp, drop_p, seed_dev = ctx.meta
+        saved = ctx.saved_tensors
+        A, Gact, Cs, Wih, Whh = (saved[i * L:(i + 1) * L] for i in range(5))
+        dev = dout.device
+        st = _stream()
+        seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
+        dout = dout.contiguous().float()
+        grads = [None] * (4 * L)
+        dX_up = None
+        orig_of, colp_of = _dg_perm(H, dev)
+        for l in reversed(range(L)):
+            top = l == L - 1
+            dG = torch.empty(W * Bp, 4 * H, dtype=torch.bfloat16, device=dev)   # gate columns permuted (see _dg_perm)
+            call("b200med_lstm_rec_bwd", _raw(Gact[l].data_ptr()), _raw(Cs[l].data_ptr()), _raw(Whh[l].data_ptr()),
+                 _raw(dout.data_ptr() if top else 0), _raw(0 if top else dX_up.data_ptr()), 0 if top else inp[l + 1],
+                 _raw(dG.data_ptr()), B, Bp, W, H, 0.0 if top else drop_p, _raw(seed_ptr), l * W * Bp * H, st)
+            if l > 0 or ctx.needs_input_grad[0]:
+                # dX [W*Bp, inp] = dG [W*Bp, 4H] * W_ih [4H, inp]   (B operand MN-major); interleaved rows for the layer
+                # below's recurrence kernel, row-major for the unpack into [B, F, W]
+                dX_up = ops.gemm_bf16(dG, Wih[l].index_select(0, orig_of), W * Bp, inp[l], 4 * H, True, False,
+                                      out_dtype=torch.float32, rbi=l > 0)
+            # dWcat [4H, Kp] = dG^T [x | h_prev] over all W*Bp rows (both operands MN-major), deterministic split-K
+            tiles = ((4 * H + 127) // 128) * ((Kp[l] + 255) // 256)
+            dW = ops.gemm_bf16(dG, A[l].view(W * Bp, Kp[l]), 4 * H, Kp[l], W * Bp, False, False,
+                               out_dtype=torch.float32, split_k=_split_k(tiles, (W * Bp + 63) // 64))
+            db = ops.colsum(dG).index_select(0, colp_of)
+            dW = dW.index_select(0, colp_of)
+            grads[4 * l] = dW[:, :ins[l]].contiguous()
+            grads[4 * l + 1] = dW[:, inp[l]:inp[l] + H].contiguous()
+            grads[4 * l + 2] = db
+            grads[4 * l + 3] = db.clone()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, F, W, dtype=torch.float32, device=dev)
+            call("b200med_lstm_unpack_dx", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, F, W, inp[0], st)
+        return (dx, None, None, *grads)
+
+
+def lstm_last_hidden(x: torch.Tensor, lstm: torch.nn.LSTM, training: bool, seed_dev=None, impl: str = "auto") -> torch.Tensor:
     """h_{W-1} of the top layer for head input x [B, F, W]."""
     params = []
     for l in range(lstm.num_layers):
         params += [getattr(lstm, f"weight_ih_l{l}"), getattr(lstm, f"weight_hh_l{l}"),
                    getattr(lstm, f"bias_ih_l{l}"), getattr(lstm, f"bias_hh_l{l}")]
     p = float(lstm.dropout) if training else 0.0
-    return LSTMStackFunction.apply(x, p, seed_dev, *params)
+    fn = LSTMRecFunction if (lstm.hidden_size == 128 and impl != "per_step") else LSTMStackFunction
+    return fn.apply(x, p, seed_dev, *params)

@@ -195,8 +195,8 @@ def define_model_objects(exp_kwargs: dict, in_features_dict: dict, device, class
     model = instantiate_model(exp_kwargs, in_features_dict[exp_kwargs["data_type"]], window_size, device).to(device)
     if hasattr(model, "use_cudnn"):
         model.use_cudnn = precision != "fp32"
-        if precision == "bf16" and ops.has_tcgen05() and exp_kwargs.get("lstm_impl", "b200") == "b200":
-            model.impl = "b200"
+        if precision == "bf16" and ops.has_tcgen05() and exp_kwargs.get("lstm_impl", "b200") in ("b200", "b200_per_step"):
+            model.impl = exp_kwargs.get("lstm_impl", "b200")
     if exp_kwargs["data_type"] != "kinematics":
         feature_extractor = FeatureExtractor(input_dim=2048, output_dim=exp_kwargs["video_dims"], hidden_dims=[512, 256],
                                              precision=precision).to(device)

@@ -186,12 +186,13 @@ class LSTM(nn.Module):
         self.initialize_weights()
 
     def forward(self, l):
-        if self.impl == "b200" and l.is_cuda:
-            # throughput mode: tcgen05 gate GEMMs + fused cell kernels (lstm_stack.py); only h_{W-1} is needed
+        if self.impl in ("b200", "b200_per_step") and l.is_cuda:
+            # throughput mode: persistent tcgen05 recurrence kernels (lstm_stack.py); only h_{W-1} is needed
             from ..lstm_stack import lstm_last_hidden
             if self.training and self.lstm.dropout > 0:
                 self._drop_seed.add_(1)
-            h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed)
+            h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed,
+                                 impl="per_step" if self.impl == "b200_per_step" else "auto")
             return self.linear_layers(F.relu(h))
         with torch.backends.cudnn.flags(enabled=self.use_cudnn):
             out, _ = self.lstm(l.transpose(1, 2).contiguous())

@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, StreamDesc, call
+from ._lib import BF16, F16, F32, StreamDesc, call
 
 
 def _stream() -> C.c_void_p:
@@ -37,6 +37,8 @@ def _dt(t: torch.Tensor) -> int:
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16
     raise TypeError(f"b200med: unsupported dtype {t.dtype}")
 
 
@@ -186,8 +188,9 @@ def has_tcgen05() -> bool:
 
 
 def gemm_bf16(A, B, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, mask=None, relu=False,
-              out_dtype=torch.bfloat16, split_k=1, out=None):
-    """D[M,N] = A[M,K] B[N,K]^T on tcgen05.  K-major operand = stored [rows, K]; MN-major = stored [K, rows]."""
+              out_dtype=torch.bfloat16, split_k=1, out=None, rbi=False):
+    """D[M,N] = A[M,K] B[N,K]^T on tcgen05.  K-major operand = stored [rows, K]; MN-major = stored [K, rows].
+    rbi=True: D is written row-block-interleaved ([M/32][N/V][32][V], see b200med.h) -- M must be a multiple of 32."""
     A = _need(A, torch.bfloat16, "A"); Bm = _need(B, torch.bfloat16, "B")
     lda, ldb = A.shape[-1], Bm.shape[-1]
     D = out if out is not None else torch.empty(M, N, dtype=out_dtype, device=A.device)
@@ -195,7 +198,7 @@ def gemm_bf16(A, B, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, mask=None,
     if split_k > 1:
         ws = workspace(_lib.load().b200med_gemm_bf16_ws_bytes(M, N, K, split_k), A.device, "splitk")
     call("b200med_gemm_bf16", _ptr(A), _ptr(Bm), _ptr(D), _ptr(bias), _ptr(mask), M, N, K, lda, ldb, D.shape[-1],
-         int(a_kmajor), int(b_kmajor), _dt(D), int(relu), split_k, _ptr(ws), _stream())
+         int(a_kmajor), int(b_kmajor), _dt(D), int(relu), split_k, int(bool(rbi)), _ptr(ws), _stream())
     return D
 
 

@@ -265,6 +265,24 @@ def test_gemm_bf16_tcgen05(case, ops):
     assert err < 2e-2, f"bf16-out rel err {err:.3e}"
 
 
+@pytest.mark.parametrize("M,N,K,f32", [(4096, 512, 64, False), (4096, 512, 128, False), (2048, 128, 512, True), (96, 64, 136, True)])
+def test_gemm_bf16_tcgen05_interleaved_output(M, N, K, f32, ops):
+    """out_layout = RBI32: the same product, written row-block-interleaved ([M/32][N/V][32][V], V = elements per 16
+    bytes) -- bit-identical to the row-major result after undoing the permutation."""
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    g = torch.Generator().manual_seed(M + N + K)
+    A = dev((torch.randn(M, K, generator=g) / K ** 0.25).to(torch.bfloat16))
+    B = dev((torch.randn(N, K, generator=g) / K ** 0.25).to(torch.bfloat16))
+    bias = dev(torch.randn(N, generator=g))
+    dt = torch.float32 if f32 else torch.bfloat16
+    plain = ops.gemm_bf16(A, B, M, N, K, True, True, bias=bias, out_dtype=dt)
+    tiled = ops.gemm_bf16(A, B, M, N, K, True, True, bias=bias, out_dtype=dt, rbi=True)
+    V = 4 if f32 else 8
+    back = tiled.view(M // 32, N // V, 32, V).permute(0, 2, 1, 3).reshape(M, N)
+    assert torch.equal(back, plain)
+
+
 # ------------------------------------------------------------------------------------------- K3
 @pytest.mark.parametrize("B", [1, 12, 512, 8192, 20000])
 @pytest.mark.parametrize("pw", [1.0, 0.6666])
