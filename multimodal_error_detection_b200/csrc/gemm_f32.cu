@@ -116,6 +116,68 @@ __global__ void colsum_partial_kernel(const T *__restrict__ x, float *__restrict
     }
 }
 
+// Vectorised variant: 16-byte loads (V = 8 bf16 / 4 f32 columns per thread), a warp covers 32*V columns of one row,
+// the 8 warps of a block walk 8 rows at a time.  Needs N % V == 0, ld % V == 0 and a 16-byte aligned base.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_partial_vec_kernel(const T *__restrict__ x, float *__restrict__ part, long long M, int N, long long ld,
+                          long long rows_per_slab) {
+    constexpr int V = 16 / sizeof(T);
+    __shared__ float sh[8][32 * V + 1];
+    const int lane = threadIdx.x & 31, lane_row = threadIdx.x >> 5;
+    const int col = (blockIdx.x * 32 + lane) * V;
+    const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+    float s[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = 0.0f;
+    if (col < N) {
+#pragma unroll 4
+        for (long long m = m0 + lane_row; m < m1; m += 8) {
+            const uint4 u = ldg_stream_u4(reinterpret_cast<const uint4 *>(x + m * ld + col));
+            if constexpr (sizeof(T) == 2) {
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s[2 * j] += __uint_as_float(w[j] << 16);
+                    s[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                }
+            } else {
+                s[0] += __uint_as_float(u.x); s[1] += __uint_as_float(u.y); s[2] += __uint_as_float(u.z); s[3] += __uint_as_float(u.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) sh[lane_row][lane * V + j] = s[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * V; c += 256) {
+        const int gc = blockIdx.x * 32 * V + c;
+        if (gc < N) {
+            float t = 0.0f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) t += sh[r][c];
+            part[(long long)blockIdx.y * N + gc] = t;
+        }
+    }
+}
+
+// out[e] = sum_z part[z*n + e] in a fixed order: 8 strided partial sums per column (z = r, r+8, ...) added r = 0..7.
+__global__ void __launch_bounds__(256)
+slab_reduce8_kernel(const float *__restrict__ part, float *__restrict__ out, int n, int slabs) {
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+    float s = 0.0f;
+    if (c < n)
+        for (int z = r; z < slabs; z += 8) s += part[(long long)z * n + c];
+    sh[r][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (r == 0 && c < n) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x & 31];
+        out[c] = t;
+    }
+}
+
 __global__ void cast_f32_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __float2bfloat16_rn(x[i]);
@@ -215,14 +277,24 @@ extern "C" __attribute__((visibility("default"))) int b200med_colsum(const void 
     float *cpart = reinterpret_cast<float *>(workspace);
     const int cs = (int)colsum_slabs(M);
     const long long rows = (M + cs - 1) / cs;
-    dim3 grid((unsigned)((N + 31) / 32), (unsigned)cs);
-    if (dtype == B200MED_F32)
-        colsum_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(dy), cpart, M, N, ld, rows);
-    else
-        colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rows);
-    if (int e = after_launch("colsum_partial_kernel")) return e;
-    slab_reduce_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(cpart, db, N, cs, N, 0);
-    return after_launch("slab_reduce_kernel");
+    const int V = dtype == B200MED_F32 ? 4 : 8;
+    if (N % V == 0 && ld % V == 0 && (uintptr_t)dy % 16 == 0) {
+        dim3 grid((unsigned)((N + 32 * V - 1) / (32 * V)), (unsigned)cs);
+        if (dtype == B200MED_F32)
+            colsum_partial_vec_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(dy), cpart, M, N, ld, rows);
+        else
+            colsum_partial_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rows);
+        if (int e = after_launch("colsum_partial_vec_kernel")) return e;
+    } else {
+        dim3 grid((unsigned)((N + 31) / 32), (unsigned)cs);
+        if (dtype == B200MED_F32)
+            colsum_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(dy), cpart, M, N, ld, rows);
+        else
+            colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rows);
+        if (int e = after_launch("colsum_partial_kernel")) return e;
+    }
+    slab_reduce8_kernel<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(cpart, db, N, cs);
+    return after_launch("slab_reduce8_kernel");
 }
 
 extern "C" __attribute__((visibility("default"))) int b200med_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stream) {

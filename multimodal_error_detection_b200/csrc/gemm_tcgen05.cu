@@ -26,7 +26,7 @@ namespace b200med {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kATileBytes = BLOCK_M * BLOCK_K * 2;  // 16 KB
 
 struct GemmParams {
@@ -78,7 +78,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
         for (int s = 0; s < Cfg::kStages; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < Cfg::kAccStages; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < Cfg::kAccStages; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -165,8 +165,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // Two warps per TMEM lane quarter, each draining half of the tile's columns in 32-column chunks; the tcgen05.ld
+        // of chunk i+1 is in flight while chunk i goes through bias / ReLU / mask / conversion and its stores.
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+        const int half = (warp - 2) >> 2;
+        constexpr int kChunks = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;       // chunks per warp
+        const int c_first = BLOCK_N >= 64 ? half * (BLOCK_N / 2) : 0;
+        const bool has_work = BLOCK_N >= 64 || half == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -178,10 +184,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const long long m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
             const bool partial = p.split_k > 1;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c_first);
+            uint32_t vbuf[2][32];
+            if (has_work) {
+                tmem_ld32_nowait(t_addr, vbuf[0]);
+                tmem_wait_ld();
+            }
+#pragma unroll
+            for (int ci = 0; ci < kChunks; ++ci) {
+                if (!has_work) break;
+                const int c0 = c_first + ci * 32;
+                uint32_t (&v)[32] = vbuf[ci & 1];
+                if (ci + 1 < kChunks) tmem_ld32_nowait(t_addr + (uint32_t)((ci + 1) * 32), vbuf[(ci + 1) & 1]);
                 const long long n_base = n0 + c0;
                 if (row_ok && n_base < p.N) {
                     float f[32];
@@ -190,9 +204,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const bool full = n_base + 32 <= p.N;
                     if (!partial) {
                         if (p.bias) {
+                            if (full && (((uintptr_t)(p.bias + n_base)) % 16 == 0)) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (full || n_base + j < p.N) f[j] += __ldg(p.bias + n_base + j);
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n_base) + q);
+                                    f[4 * q] += b4.x; f[4 * q + 1] += b4.y; f[4 * q + 2] += b4.z; f[4 * q + 3] += b4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (full || n_base + j < p.N) f[j] += __ldg(p.bias + n_base + j);
+                            }
                         }
                         if (p.relu) {
 #pragma unroll
@@ -270,6 +292,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         }
                     }
                 }
+                if (ci + 1 < kChunks) tmem_wait_ld();
             }
             // all of this warp's TMEM reads are complete (tcgen05.wait::ld above) -> release the accumulator
             tcgen05_fence_before();

@@ -37,30 +37,62 @@ __device__ __forceinline__ bool dropout_keep(uint32_t seed, unsigned long long i
 
 // x [B, F, W] f32 (the reference's [batch, features, time] layout) -> A0 [W, Bpad, Kp] bf16 columns [0, F), rows b < B;
 // also zeroes the padding columns [F, hoff) and [hoff+H, Kp) of every step and the h_{-1} columns [hoff, hoff+H) of step 0.
-__global__ void lstm_pack_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad,
-                                 int F, int W, int H, int Kp, int hoff) {
-    const long long total = B * (long long)W * Kp;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(e % Kp);
-        const long long r = e / Kp;
-        const long long b = r % B;
-        const int t = (int)(r / B);
-        __nv_bfloat16 *dst = A0 + ((long long)t * Bpad + b) * Kp + k;
-        if (k < F) *dst = __float2bfloat16_rn(x[(b * F + k) * W + t]);
-        else if (k < hoff || k >= hoff + H || t == 0) *dst = __float2bfloat16_rn(0.0f);
+// One block per 4 windows: x[b] (F*W contiguous floats) is read coalesced into shared memory and written back one
+// (t, b) row per warp pass (time-major rows, 2 columns per lane).
+constexpr int kPackWin = 4;
+__global__ void __launch_bounds__(256)
+lstm_pack_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int F, int W, int H,
+                 int Kp, int hoff) {
+    extern __shared__ float sh_pack[];            // [kPackWin][F][W + 1] (padded rows: column reads spread over the banks)
+    const int FW = F * W, W1 = W + 1, FW1 = F * W1;
+    for (long long b0 = (long long)blockIdx.x * kPackWin; b0 < B; b0 += (long long)gridDim.x * kPackWin) {
+        const int nb = (int)min((long long)kPackWin, B - b0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nb * FW; e += blockDim.x) {
+            const int bl = e / FW, r = e - bl * FW, k = r / W;
+            sh_pack[bl * FW1 + k * W1 + (r - k * W)] = x[b0 * FW + e];
+        }
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int r = warp; r < nb * W; r += nwarps) {
+            const int bl = r / W, t = r - bl * W;
+            __nv_bfloat16 *dst = A0 + ((long long)t * Bpad + b0 + bl) * Kp;
+            const float *src = sh_pack + bl * FW1 + t;  // element k at src[k*W1]
+            for (int k = lane * 2; k < Kp; k += 64) {    // Kp is a multiple of 8: pairs never straddle the end
+                const bool x0 = k < F, x1 = k + 1 < F;
+                const bool h0 = k >= hoff && k < hoff + H, h1 = k + 1 >= hoff && k + 1 < hoff + H;
+                if ((h0 || h1) && t != 0) {
+                    // the h_{t-1} columns of steps t > 0 belong to the recurrence: leave them alone
+                    if (!h0) dst[k] = __float2bfloat16_rn(x0 ? src[k * W1] : 0.0f);
+                    if (!h1) dst[k + 1] = __float2bfloat16_rn(x1 ? src[(k + 1) * W1] : 0.0f);
+                } else {
+                    *reinterpret_cast<__nv_bfloat162 *>(dst + k) =
+                        __floats2bfloat162_rn(x0 ? src[k * W1] : 0.0f, x1 ? src[(k + 1) * W1] : 0.0f);
+                }
+            }
+        }
     }
 }
 
-// dx [B, F, W] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F)
-__global__ void lstm_unpack_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F,
-                                   int W, int Kp) {
-    const long long total = B * (long long)F * W;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const int t = (int)(e % W);
-        const long long r = e / W;
-        const int k = (int)(r % F);
-        const long long b = r / F;
-        dx[e] = dA0[((long long)t * Bpad + b) * Kp + k];
+// dx [B, F, W] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F): the mirror transpose through shared memory.
+__global__ void __launch_bounds__(256)
+lstm_unpack_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F, int W, int Kp) {
+    extern __shared__ float sh_pack[];            // [kPackWin][F][W + 1]
+    const int FW = F * W, W1 = W + 1, FW1 = F * W1;
+    for (long long b0 = (long long)blockIdx.x * kPackWin; b0 < B; b0 += (long long)gridDim.x * kPackWin) {
+        const int nb = (int)min((long long)kPackWin, B - b0);
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int r = warp; r < nb * W; r += nwarps) {
+            const int bl = r / W, t = r - bl * W;
+            const float *src = dA0 + ((long long)t * Bpad + b0 + bl) * Kp;
+            for (int k = lane; k < F; k += 32) sh_pack[bl * FW1 + k * W1 + t] = src[k];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nb * FW; e += blockDim.x) {
+            const int bl = e / FW, r = e - bl * FW, k = r / W;
+            dx[b0 * FW + e] = sh_pack[bl * FW1 + k * W1 + (r - k * W)];
+        }
     }
 }
 
@@ -144,7 +176,9 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_inputs(c
                                                                                int32_t hoff, void *stream) {
     B200MED_REQUIRE(B >= 1 && Bpad >= B && F >= 1 && W >= 1 && H >= 1 && hoff >= F && Kp >= hoff + H, "bad shape");
     B200MED_REQUIRE(x && A0, "null pointer");
-    lstm_pack_kernel<<<grid_for(B * (long long)W * Kp), 256, 0, (cudaStream_t)stream>>>(
+    B200MED_REQUIRE(Kp % 8 == 0 && (size_t)kPackWin * F * (W + 1) * 4 <= 48 * 1024, "bad shape");
+    const long long blocks = (B + kPackWin - 1) / kPackWin, cap = (long long)num_sms() * 8;
+    lstm_pack_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, (size_t)kPackWin * F * (W + 1) * 4, (cudaStream_t)stream>>>(
         x, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, F, W, H, Kp, hoff);
     return after_launch("lstm_pack_kernel");
 }
@@ -153,7 +187,10 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(con
                                                                              int32_t F, int32_t W, int32_t Kp, void *stream) {
     B200MED_REQUIRE(B >= 1 && Bpad >= B && F >= 1 && W >= 1 && Kp >= F, "bad shape");
     B200MED_REQUIRE(dA0 && dx, "null pointer");
-    lstm_unpack_kernel<<<grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream>>>(dA0, dx, B, Bpad, F, W, Kp);
+    B200MED_REQUIRE((size_t)kPackWin * F * (W + 1) * 4 <= 48 * 1024, "bad shape");
+    const long long blocks = (B + kPackWin - 1) / kPackWin, cap = (long long)num_sms() * 8;
+    lstm_unpack_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, (size_t)kPackWin * F * (W + 1) * 4, (cudaStream_t)stream>>>(
+        dA0, dx, B, Bpad, F, W, Kp);
     return after_launch("lstm_unpack_kernel");
 }
 

@@ -29,7 +29,6 @@
 // contiguous bytes.  Tensors consumed by TMA-fed GEMMs (A_l, dG) stay row-major and are written by TMA store.
 // The batch is padded to a multiple of 32 rows per time step (pad rows carry zeros / finite values and zero gradients).
 #include "tcgen05.cuh"
-#include <stdlib.h>
 
 namespace b200med {
 
@@ -51,8 +50,7 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 __device__ __forceinline__ uint32_t drop_hash(uint32_t seed, uint32_t pair_index) {
     uint32_t h = pair_index * 0x9E3779B1u + seed * 0x85EBCA77u + 0x165667B1u;
     h ^= h >> 15; h *= 0x2C1B3C6Du;
-    h ^= h >> 12; h *= 0x297A2D39u;
-    h ^= h >> 15;
+    h ^= h >> 13;
     return h;
 }
 // scale (1/(1-p)) or 0 for N consecutive elements starting at the EVEN element index e0
@@ -93,8 +91,18 @@ __device__ __forceinline__ void unpack_f16x8(const uint4 &u, float *f) {
         f[2 * i] = v.x; f[2 * i + 1] = v.y;
     }
 }
+// activated gates lie in [-1, 1]: no saturation needed
+__device__ __forceinline__ uint32_t pack_f16x2_nosat(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
 __device__ __forceinline__ uint4 pack_f16x8(const float *f) {
-    return make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+    return make_uint4(pack_f16x2_nosat(f[0], f[1]), pack_f16x2_nosat(f[2], f[3]), pack_f16x2_nosat(f[4], f[5]),
+                      pack_f16x2_nosat(f[6], f[7]));
+}
+// L2 prefetch of a contiguous range (a 32-row block of a row-block-interleaved matrix is contiguous over all columns)
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t *v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -109,30 +117,32 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *v) {
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ unsigned char *align_1024(unsigned char *p) {
     return reinterpret_cast<unsigned char *>(((uintptr_t)p + 1023) & ~(uintptr_t)1023);
 }
 
 // =========================================================================================== forward
 struct RecFwdParams {
-    const __half *xg;          // row-block-interleaved fp16 [W*Bpad, 4H]: x-part pre-activations + bias
-    __half *gact;              // row-block-interleaved fp16 [W*Bpad, 4H] activated gates (null: do not save)
-    float *c;                  // row-block-interleaved [W*Bpad, H] cell states (null: do not save)
+    const __half *xg;          // row-block-interleaved fp16 [W*Bpad, 4H]: x-part pre-activations + bias (i, f, o rows HALVED)
+    __half *gact;              // row-block-interleaved fp16 [W*Bpad, 4H] activated gates        (kSave)
+    float *c;                  // row-block-interleaved [W*Bpad, H] cell states                    (kSave)
     float *h_out;              // [B, H] row-major h_{W-1} (null: skip)
     long long B, Bpad;
     int W;
-    int has_next, hoff;        // TMA-store h_t into A_l[t+1][:, hoff:hoff+H]
-    int has_up;                // TMA-store dropout(h_t) into A_{l+1}[t][:, 0:H]
-    float drop_p;
+    int hoff;                  // kSave: TMA-store h_t into A_l[t+1][:, hoff:hoff+H]
+    float drop_p;              // kUp: TMA-store dropout(h_t) into A_{l+1}[t][:, 0:H]
     const uint32_t *seed;
     uint32_t drop_base;
-    int debug;
 };
 
+constexpr int kFwdThreads = 512;   // 16 warps: lane quarter = warp % 4 (TMEM rule), unit quarter = warp / 4 (32 units each)
 constexpr size_t kRecFwdSmem = 1024 + kWhhBytes + 32768 + 32768 + 64;
 
-__global__ void __launch_bounds__(kRecThreads, 1)
+// kSave: training (gates, c, h saved for the backward); kUp: a layer above consumes dropout(h_t); kDrop: drop_p > 0.
+// W_hh / W_ih / bias rows of the sigmoid gates (i, f, o) arrive pre-multiplied by 0.5 (host, exact), so that
+// sigmoid(z) = 0.5 * tanh(z/2) + 0.5 is one MUFU and one FMA.
+template <bool kSave, bool kUp, bool kDrop>
+__global__ void __launch_bounds__(kFwdThreads, 1)
 lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_constant__ CUtensorMap tmap_next,
                     const __grid_constant__ CUtensorMap tmap_up, const RecFwdParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -147,7 +157,7 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         bar_init(w_full, 1);
-        bar_init(h_ready, 8);
+        bar_init(h_ready, kFwdThreads / 32);
         bar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,39 +182,35 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
     const uint32_t idesc = make_idesc(128, 256, false, false);
     const uint32_t ha = s_addr(h_sm), wa = s_addr(w_sm);
 
-    const int q = warp & 3, uh = warp >> 2;
+    const int q = warp & 3, uq = warp >> 2;
     const int row = q * 32 + lane;
     const long long b = (long long)m0 + row;
-    const bool ok = b < p.Bpad;
-    const uint32_t seed = p.seed ? *p.seed : 0u;
-    const bool drop = p.drop_p > 0.0f;
-    const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    // Bpad is a multiple of 32 and a warp owns 32 consecutive rows: validity is warp-uniform
+    const bool ok = __shfl_sync(0xffffffffu, (int)(b < p.Bpad), 0) != 0;
+    const uint32_t seed = (kDrop && p.seed) ? *p.seed : 0u;
+    const float keep_scale = kDrop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
     const uint32_t thr16 = (uint32_t)(p.drop_p * 65536.0f);
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    unsigned char *h_row = h_sm + uh * 16384 + row * 128;
-    unsigned char *u_row = u_sm + uh * 16384 + row * 128;
-    const bool write_h = p.has_next != 0, write_u = p.has_up != 0;
-    float cst[64];
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(uq * 32);
+    // this thread's 32 units live in k-block uq/2, 16-byte slots (uq%2)*4 .. +3 of its row
+    unsigned char *h_row = h_sm + (uq >> 1) * 16384 + row * 128;
+    unsigned char *u_row = u_sm + (uq >> 1) * 16384 + row * 128;
+    const int slot0 = (uq & 1) * 4;
+    float cst[32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) cst[j] = 0.0f;
+    for (int j = 0; j < 32; ++j) cst[j] = 0.0f;
 
     // row-block index of this warp's 32 rows at step t: (t*Bpad + m0)/32 + q
     auto rblk = [&](int t) -> long long { return ((long long)t * p.Bpad + m0) / 32 + q; };
-    uint4 xc[4][2];
-    auto load_xg = [&](uint4 (&x)[4][2], int t, int c) {
-        const __half *base = p.xg + ((rblk(t) * 64 + (uh * 64 + c * 16) / 8) * 32 + lane) * 8;
+    uint4 xc[4];
+    auto load_xg = [&](uint4 (&x)[4], int t, int c) {
+        const __half *base = p.xg + ((rblk(t) * 64 + (uq * 32 + c * 8) / 8) * 32 + lane) * 8;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            if (ok) {
-                x[g][0] = ldg_u4(base + g * 16 * 256);        // gate g: + 128 columns = 16 vec groups of 256 elements
-                x[g][1] = ldg_u4(base + g * 16 * 256 + 256);
-            } else {
-                x[g][0] = make_uint4(0, 0, 0, 0);
-                x[g][1] = make_uint4(0, 0, 0, 0);
-            }
-        }
+        for (int g = 0; g < 4; ++g) x[g] = ldg_u4(base + g * 16 * 256);   // gate g: + 128 columns = 16 groups of 256 elements
     };
-    load_xg(xc, 0, 0);
+    if (ok) {
+        if (uq == 0 && lane == 0) prefetch_l2_bulk(p.xg + rblk(0) * (32 * 4 * kRecH), 32 * 4 * kRecH * 2);
+        load_xg(xc, 0, 0);
+    }
 
     for (int t = 0; t < W; ++t) {
         const bool have_acc = t > 0;
@@ -213,110 +219,92 @@ lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
             bar_wait(acc_full, (uint32_t)((t - 1) & 1));
             tcgen05_fence_after();
         }
-        const long long rb = rblk(t);
+        if (ok) {
+            const long long rb = rblk(t);
+            if (uq == 0 && lane == 0 && t + 1 < W) prefetch_l2_bulk(p.xg + rblk(t + 1) * (32 * 4 * kRecH), 32 * 4 * kRecH * 2);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int u0 = uh * 64 + c * 16;
-            uint4 xn[4][2];
-            if (c < 3) load_xg(xn, t, c + 1);
-            else if (t + 1 < W) load_xg(xn, t + 1, 0);
-            uint32_t acc[4][16];
-            if (have_acc) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) tmem_ld16_nowait(t_lane + (uint32_t)(g * kRecH + u0), acc[g]);
-                tmem_wait_ld();
-            }
-            auto pre = [&](int g, float (&out)[16]) {
-                unpack_f16x8(xc[g][0], &out[0]);
-                unpack_f16x8(xc[g][1], &out[8]);
+            for (int c = 0; c < 4; ++c) {
+                const int u0 = uq * 32 + c * 8;
+                uint4 xn[4];
+                if (c < 3) load_xg(xn, t, c + 1);
+                else if (t + 1 < W) load_xg(xn, t + 1, 0);
+                float gi[8], gg[8], gf[8], go[8];
+                unpack_f16x8(xc[0], gi); unpack_f16x8(xc[2], gg);
                 if (have_acc) {
+                    uint32_t a0[8], a2[8];
+                    tmem_ld8_nowait(t_lane + (uint32_t)(0 * kRecH + c * 8), a0);
+                    tmem_ld8_nowait(t_lane + (uint32_t)(2 * kRecH + c * 8), a2);
+                    tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) out[j] += __uint_as_float(acc[g][j]);
+                    for (int j = 0; j < 8; ++j) { gi[j] += __uint_as_float(a0[j]); gg[j] += __uint_as_float(a2[j]); }
                 }
-            };
-            __half *gdst = p.gact + ((rb * 64 + u0 / 8) * 32 + lane) * 8;
-            auto save_gate = [&](int g, const float (&a)[16]) {
-                if (p.gact && ok) {
-                    *reinterpret_cast<uint4 *>(gdst + g * 16 * 256) = pack_f16x8(&a[0]);
-                    *reinterpret_cast<uint4 *>(gdst + g * 16 * 256 + 256) = pack_f16x8(&a[8]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { gi[j] = fmaf(0.5f, tanh_fast(gi[j]), 0.5f); gg[j] = tanh_fast(gg[j]); }
+                unpack_f16x8(xc[1], gf); unpack_f16x8(xc[3], go);
+                if (have_acc) {
+                    uint32_t a1[8], a3[8];
+                    tmem_ld8_nowait(t_lane + (uint32_t)(1 * kRecH + c * 8), a1);
+                    tmem_ld8_nowait(t_lane + (uint32_t)(3 * kRecH + c * 8), a3);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { gf[j] += __uint_as_float(a1[j]); go[j] += __uint_as_float(a3[j]); }
                 }
-            };
-            auto sig = [&](float x) { return sigmoid_fast(x); };
-            auto tnh = [&](float x) { return tanh_fast(x); };
-            float a[16], ig[16];
-            pre(0, a);
+                float h[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = sig(a[j]);
-            save_gate(0, a);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ig[j] = a[j];
-            pre(2, a);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = tnh(a[j]);
-            save_gate(2, a);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) ig[j] *= a[j];
-            pre(1, a);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = sig(a[j]);
-            save_gate(1, a);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) cst[c * 16 + j] = fmaf(a[j], cst[c * 16 + j], ig[j]);
-            if (p.c && ok) {
-                float *cdst = p.c + ((rb * 32 + u0 / 4) * 32 + lane) * 4;
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    *reinterpret_cast<float4 *>(cdst + v * 128) =
-                        make_float4(cst[c * 16 + 4 * v], cst[c * 16 + 4 * v + 1], cst[c * 16 + 4 * v + 2], cst[c * 16 + 4 * v + 3]);
-            }
-            pre(3, a);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = sig(a[j]);
-            save_gate(3, a);
-            float h[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) h[j] = a[j] * tnh(cst[c * 16 + j]);
-            if (feed || write_h) {
+                for (int j = 0; j < 8; ++j) {
+                    gf[j] = fmaf(0.5f, tanh_fast(gf[j]), 0.5f);
+                    go[j] = fmaf(0.5f, tanh_fast(go[j]), 0.5f);
+                    cst[c * 8 + j] = fmaf(gf[j], cst[c * 8 + j], gi[j] * gg[j]);
+                    h[j] = go[j] * tanh_fast(cst[c * 8 + j]);
+                }
+                if (kSave) {
+                    __half *gdst = p.gact + ((rb * 64 + u0 / 8) * 32 + lane) * 8;
+                    *reinterpret_cast<uint4 *>(gdst) = pack_f16x8(gi);
+                    *reinterpret_cast<uint4 *>(gdst + 16 * 256) = pack_f16x8(gf);
+                    *reinterpret_cast<uint4 *>(gdst + 32 * 256) = pack_f16x8(gg);
+                    *reinterpret_cast<uint4 *>(gdst + 48 * 256) = pack_f16x8(go);
+                    float *cdst = p.c + ((rb * 32 + u0 / 4) * 32 + lane) * 4;
+                    *reinterpret_cast<float4 *>(cdst) = make_float4(cst[c * 8], cst[c * 8 + 1], cst[c * 8 + 2], cst[c * 8 + 3]);
+                    *reinterpret_cast<float4 *>(cdst + 128) = make_float4(cst[c * 8 + 4], cst[c * 8 + 5], cst[c * 8 + 6], cst[c * 8 + 7]);
+                }
                 // operand tile of the next step's MMA and source of the TMA store (128B swizzle: 16-byte slot ^ row%8)
-                *reinterpret_cast<uint4 *>(h_row + (((c * 2) ^ (row & 7)) << 4)) = pack_bf16x8(&h[0]);
-                *reinterpret_cast<uint4 *>(h_row + (((c * 2 + 1) ^ (row & 7)) << 4)) = pack_bf16x8(&h[8]);
-            }
-            if (write_u) {
-                float hv[16];
-                if (drop) {
-                    float sc[16];
-                    drop_scales<16>(seed, p.drop_base + (uint32_t)(((long long)t * p.Bpad + b) * kRecH + u0), thr16, keep_scale, sc);
+                *reinterpret_cast<uint4 *>(h_row + (((slot0 + c) ^ (row & 7)) << 4)) = pack_bf16x8(h);
+                if (kUp) {
+                    float hv[8];
+                    if (kDrop) {
+                        float sc[8];
+                        drop_scales<8>(seed, p.drop_base + (uint32_t)(((long long)t * p.Bpad + b) * kRecH + u0), thr16, keep_scale, sc);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) hv[j] = h[j] * sc[j];
-                } else {
+                        for (int j = 0; j < 8; ++j) hv[j] = h[j] * sc[j];
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) hv[j] = h[j];
+                        for (int j = 0; j < 8; ++j) hv[j] = h[j];
+                    }
+                    *reinterpret_cast<uint4 *>(u_row + (((slot0 + c) ^ (row & 7)) << 4)) = pack_bf16x8(hv);
                 }
-                *reinterpret_cast<uint4 *>(u_row + (((c * 2) ^ (row & 7)) << 4)) = pack_bf16x8(&hv[0]);
-                *reinterpret_cast<uint4 *>(u_row + (((c * 2 + 1) ^ (row & 7)) << 4)) = pack_bf16x8(&hv[8]);
-            }
-            if (p.h_out && b < p.B && t == W - 1) {
-                float4 *dst = reinterpret_cast<float4 *>(p.h_out + b * kRecH + u0);
+                if (p.h_out && t == W - 1 && b < p.B) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.h_out + b * kRecH + u0);
+                    dst[0] = make_float4(h[0], h[1], h[2], h[3]);
+                    dst[1] = make_float4(h[4], h[5], h[6], h[7]);
+                }
 #pragma unroll
-                for (int v = 0; v < 4; ++v) dst[v] = make_float4(h[4 * v], h[4 * v + 1], h[4 * v + 2], h[4 * v + 3]);
+                for (int g = 0; g < 4; ++g) xc[g] = xn[g];
             }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) { xc[g][0] = xn[g][0]; xc[g][1] = xn[g][1]; }
         }
-        if (feed || write_h || write_u) {
+        if (feed || kSave || kUp) {
             fence_proxy_async_smem();    // h_t / dropout(h_t) (generic-proxy stores) -> visible to tcgen05.mma and TMA
             tcgen05_fence_before();      // this step's tcgen05.ld are complete before the next MMA overwrites TMEM
             __syncwarp();
             if (lane == 0) bar_arrive(h_ready);
             if (warp == 0) {
                 if (lane == 0) {
-                    bar_wait(h_ready, (uint32_t)(t & 1));      // all 8 warps have published their part of h_t
+                    bar_wait(h_ready, (uint32_t)(t & 1));      // all 16 warps have published their part of h_t
                     tcgen05_fence_after();
-                    if (write_h && feed) {
+                    if (kSave && feed) {
                         tma_store_3d(&tmap_next, h_sm, p.hoff, m0, t + 1);
                         tma_store_3d(&tmap_next, h_sm + 16384, p.hoff + 64, m0, t + 1);
                     }
-                    if (write_u) {
+                    if (kUp) {
                         tma_store_3d(&tmap_up, u_sm, 0, m0, t);
                         tma_store_3d(&tmap_up, u_sm + 16384, 64, m0, t);
                     }
@@ -366,8 +354,6 @@ struct RecBwdParams {
     float drop_p;
     const uint32_t *seed;
     uint32_t drop_base;
-    __nv_bfloat16 *dG_direct;   // debug (B200MED_REC_DEBUG=1): row-major dG written with plain stores instead of TMA
-    int debug;
 };
 
 constexpr size_t kRecBwdSmem = 1024 + kWhhBytes + 65536 + 128;
@@ -422,7 +408,8 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
     const int q = warp & 3, uh = warp >> 2;
     const int row = q * 32 + lane;
     const long long b = (long long)m0 + row;
-    const bool ok = b < p.Bpad;
+    // Bpad is a multiple of 32 and a warp owns 32 consecutive rows: validity is warp-uniform
+    const bool ok = __shfl_sync(0xffffffffu, (int)(b < p.Bpad), 0) != 0;
     const uint32_t seed = p.seed ? *p.seed : 0u;
     const bool drop = p.drop_p > 0.0f;
     const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
@@ -473,6 +460,12 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
             tcgen05_fence_after();
         }
         const uint32_t acc_prev = t_lane + (uint32_t)(((step - 1) & 1) * 128);
+        if (ok && uh == 0 && lane == 0 && t > 0) {
+            const long long rbp = rblk(t - 1);
+            prefetch_l2_bulk(p.gact + rbp * (32 * 4 * kRecH), 32 * 4 * kRecH * 2);
+            if (t > 1) prefetch_l2_bulk(p.c + rblk(t - 2) * (32 * kRecH), 32 * kRecH * 4);
+            if (p.dh_up) prefetch_l2_bulk(p.dh_up + rbp * (32 * (long long)p.up_cols), 32 * (uint32_t)p.up_cols * 4);
+        }
 #pragma unroll
         for (int sc = 0; sc < 8; ++sc) {
             const int u = uh * 64 + sc * 8;
@@ -519,11 +512,6 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
 #pragma unroll
             for (int g = 0; g < 4; ++g)
                 *reinterpret_cast<uint4 *>(a_row + (((g * 2 + s) ^ (row & 7)) << 4)) = pk[g];
-            if ((p.debug & 1) && ok) {
-                __nv_bfloat16 *dst = p.dG_direct + ((long long)t * p.Bpad + b) * (4 * kRecH) + uh * 256 + (sc >> 1) * 64 + (sc & 1) * 8;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(dst + g * 16) = pk[g];
-            }
             if (s == 1) {
                 fence_proxy_async_smem();
                 tcgen05_fence_before();
@@ -534,12 +522,10 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
                         bar_wait(&chunk_ready[slot], (uint32_t)(n & 1));
                         tcgen05_fence_after();
                         // dG_t[:, (4 gates) x (16 units of this chunk, both unit halves)] -> HBM
-                        if (!(p.debug & 1)) {
-                            tma_store_3d(&tmap_dg, a_sm + slot * 32768, c * 64, m0, t);
-                            tma_store_3d(&tmap_dg, a_sm + slot * 32768 + 16384, 256 + c * 64, m0, t);
-                        }
+                        tma_store_3d(&tmap_dg, a_sm + slot * 32768, c * 64, m0, t);
+                        tma_store_3d(&tmap_dg, a_sm + slot * 32768 + 16384, 256 + c * 64, m0, t);
                         bulk_commit();
-                        if (feed && !(p.debug & 2)) {
+                        if (feed) {
                             if (n == 0 && slot == 0) bar_wait(w_full, 0);
                             // dh_{t-1} += dG_t[:, this chunk's 128 K columns] * W_hh[those rows, :]
                             const uint32_t acc = tmem_base + (uint32_t)((step & 1) * 128);
@@ -611,18 +597,23 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_rec_fwd(
     p.xg = reinterpret_cast<const __half *>(xg);
     p.gact = reinterpret_cast<__half *>(gact);
     p.c = c; p.h_out = h_out; p.B = B; p.Bpad = Bpad; p.W = W;
-    p.has_next = a_next != nullptr; p.hoff = hoff; p.has_up = a_up != nullptr;
-    p.drop_p = drop_p; p.seed = seed; p.drop_base = (uint32_t)drop_base;
-    const char *dbg = getenv("B200MED_REC_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (int e = check_cuda(cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecFwdSmem),
-                               "cudaFuncSetAttribute(lstm_rec_fwd)")) return e;
-        attr_set = true;
-    }
+    p.hoff = hoff;
+    p.drop_p = a_up ? drop_p : 0.0f; p.seed = seed; p.drop_base = (uint32_t)drop_base;
     const unsigned grid = (unsigned)((Bpad + kRecRows - 1) / kRecRows);
-    lstm_rec_fwd_kernel<<<grid, kRecThreads, kRecFwdSmem, (cudaStream_t)stream>>>(tm, tn, tu, p);
+    const bool save = gact != nullptr, up = a_up != nullptr, drp = up && drop_p > 0.0f;
+    B200MED_REQUIRE(save == (c != nullptr) && save == (a_next != nullptr), "gact, c and a_next are saved together (training) or not at all");
+    auto launch = [&](auto kern) -> int {
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecFwdSmem),
+                               "cudaFuncSetAttribute(lstm_rec_fwd)")) return e;
+        kern<<<grid, kFwdThreads, kRecFwdSmem, (cudaStream_t)stream>>>(tm, tn, tu, p);
+        return B200MED_OK;
+    };
+    int e;
+    if (save) e = up ? (drp ? launch(lstm_rec_fwd_kernel<true, true, true>) : launch(lstm_rec_fwd_kernel<true, true, false>))
+                     : launch(lstm_rec_fwd_kernel<true, false, false>);
+    else e = up ? (drp ? launch(lstm_rec_fwd_kernel<false, true, true>) : launch(lstm_rec_fwd_kernel<false, true, false>))
+                : launch(lstm_rec_fwd_kernel<false, false, false>);
+    if (e) return e;
     return after_launch("lstm_rec_fwd_kernel");
 }
 
@@ -641,9 +632,6 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_rec_bwd(
     p.gact = reinterpret_cast<const __half *>(gact);
     p.c = c; p.dh_top = dh_top; p.dh_up = dh_up; p.up_cols = up_cols;
     p.B = B; p.Bpad = Bpad; p.W = W; p.drop_p = drop_p; p.seed = seed; p.drop_base = (uint32_t)drop_base;
-    p.dG_direct = reinterpret_cast<__nv_bfloat16 *>(dG);
-    const char *dbg = getenv("B200MED_REC_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
     static bool attr_set = false;
     if (!attr_set) {
         if (int e = check_cuda(cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecBwdSmem),

@@ -121,6 +121,15 @@ class LSTMStackFunction(torch.autograd.Function):
 
 
 _PERM = {}
+_SIDE = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
 
 
 def _dg_perm(H: int, device):
@@ -164,23 +173,25 @@ class LSTMRecFunction(torch.autograd.Function):
         seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
         Wih, Whh, Gact, Cs = [], [], [], []
         xg = torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev)
+        # rows of the sigmoid gates (i, f, o) are halved for the forward kernels: sigmoid(z) = 0.5 * tanh(z / 2) + 0.5
+        half = torch.ones(4 * H, 1, dtype=torch.float32, device=dev)
+        half[:2 * H] = 0.5
+        half[3 * H:] = 0.5
         for l in range(L):
             w_ih, w_hh, b_ih, b_hh = params[4 * l:4 * l + 4]
-            if inp[l] == ins[l]:
-                wih = ops.to_bf16(w_ih.detach().contiguous())
-            else:
-                wpad = torch.zeros(4 * H, inp[l], dtype=torch.float32, device=dev)
-                wpad[:, :ins[l]] = w_ih.detach()
-                wih = ops.to_bf16(wpad)
-            whh = ops.to_bf16(w_hh.detach().contiguous())
-            bias = (b_ih.detach() + b_hh.detach()).contiguous()
-            Wih.append(wih); Whh.append(whh)
+            wpad = torch.zeros(4 * H, inp[l], dtype=torch.float32, device=dev)
+            wpad[:, :ins[l]] = w_ih.detach()
+            Wih.append(ops.to_bf16(wpad) if need_grad else None)                      # unscaled copies: backward operands
+            Whh.append(ops.to_bf16(w_hh.detach().contiguous()) if need_grad else None)
+            wih_f = ops.to_bf16(wpad * half)
+            whh_f = ops.to_bf16(w_hh.detach() * half)
+            bias = ((b_ih.detach() + b_hh.detach()) * half[:, 0]).contiguous()
             # x-part of the gates for every step at once: [W*Bp, inp] x [4H, inp]^T + bias
-            ops.gemm_bf16(A[l].view(W * Bp, Kp[l]), wih, W * Bp, 4 * H, inp[l], True, True, bias=bias, out=xg, rbi=True)
+            ops.gemm_bf16(A[l].view(W * Bp, Kp[l]), wih_f, W * Bp, 4 * H, inp[l], True, True, bias=bias, out=xg, rbi=True)
             gact = torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev) if need_grad else None
             cs = torch.empty(W * Bp, H, dtype=torch.float32, device=dev) if need_grad else None
             top = l == L - 1
-            call("b200med_lstm_rec_fwd", _raw(xg.data_ptr()), _raw(whh.data_ptr()),
+            call("b200med_lstm_rec_fwd", _raw(xg.data_ptr()), _raw(whh_f.data_ptr()),
                  _raw(gact.data_ptr() if need_grad else 0), _raw(cs.data_ptr() if need_grad else 0),
                  _raw(A[l].data_ptr() if need_grad else 0), Kp[l], inp[l],
                  _raw(0 if top else A[l + 1].data_ptr()), 0 if top else Kp[l + 1],
@@ -204,27 +215,38 @@ class LSTMRecFunction(torch.autograd.Function):
         grads = [None] * (4 * L)
         dX_up = None
         orig_of, colp_of = _dg_perm(H, dev)
+        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        keep = []        # tensors read on the side stream stay referenced until the join (no early reuse of their memory)
         for l in reversed(range(L)):
             top = l == L - 1
             dG = torch.empty(W * Bp, 4 * H, dtype=torch.bfloat16, device=dev)   # gate columns permuted (see _dg_perm)
+            keep.append(dG)
             call("b200med_lstm_rec_bwd", _raw(Gact[l].data_ptr()), _raw(Cs[l].data_ptr()), _raw(Whh[l].data_ptr()),
                  _raw(dout.data_ptr() if top else 0), _raw(0 if top else dX_up.data_ptr()), 0 if top else inp[l + 1],
                  _raw(dG.data_ptr()), B, Bp, W, H, 0.0 if top else drop_p, _raw(seed_ptr), l * W * Bp * H, st)
+            # The weight / bias gradients of this layer are off the critical path (dG_l -> dX_l -> recurrence of layer l-1):
+            # they run on a side stream, next to the next recurrence kernel which only fills 64 of the 148 SMs.
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                # dWcat [4H, Kp] = dG^T [x | h_prev] over all W*Bp rows (both operands MN-major), deterministic split-K
+                tiles = ((4 * H + 127) // 128) * ((Kp[l] + 255) // 256)
+                dW = ops.gemm_bf16(dG, A[l].view(W * Bp, Kp[l]), 4 * H, Kp[l], W * Bp, False, False,
+                                   out_dtype=torch.float32, split_k=_split_k(tiles, (W * Bp + 63) // 64))
+                db = ops.colsum(dG).index_select(0, colp_of)
+                dW = dW.index_select(0, colp_of)
+                grads[4 * l] = dW[:, :ins[l]].contiguous()
+                grads[4 * l + 1] = dW[:, inp[l]:inp[l] + H].contiguous()
+                grads[4 * l + 2] = db
+                grads[4 * l + 3] = db.clone()
             if l > 0 or ctx.needs_input_grad[0]:
                 # dX [W*Bp, inp] = dG [W*Bp, 4H] * W_ih [4H, inp]   (B operand MN-major); interleaved rows for the layer
                 # below's recurrence kernel, row-major for the unpack into [B, F, W]
                 dX_up = ops.gemm_bf16(dG, Wih[l].index_select(0, orig_of), W * Bp, inp[l], 4 * H, True, False,
                                       out_dtype=torch.float32, rbi=l > 0)
-            # dWcat [4H, Kp] = dG^T [x | h_prev] over all W*Bp rows (both operands MN-major), deterministic split-K
-            tiles = ((4 * H + 127) // 128) * ((Kp[l] + 255) // 256)
-            dW = ops.gemm_bf16(dG, A[l].view(W * Bp, Kp[l]), 4 * H, Kp[l], W * Bp, False, False,
-                               out_dtype=torch.float32, split_k=_split_k(tiles, (W * Bp + 63) // 64))
-            db = ops.colsum(dG).index_select(0, colp_of)
-            dW = dW.index_select(0, colp_of)
-            grads[4 * l] = dW[:, :ins[l]].contiguous()
-            grads[4 * l + 1] = dW[:, inp[l]:inp[l] + H].contiguous()
-            grads[4 * l + 2] = db
-            grads[4 * l + 3] = db.clone()
+        main.wait_stream(side)
+        keep.clear()
+        for g in grads:
+            g.record_stream(main)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, F, W, dtype=torch.float32, device=dev)

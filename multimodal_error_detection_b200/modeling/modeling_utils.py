@@ -191,6 +191,9 @@ def define_model_objects(exp_kwargs: dict, in_features_dict: dict, device, class
     if precision == "fp32":      # TF32 convolutions / matmuls cannot hold 1e-5
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
+    else:                        # throughput mode (2e-2 bar): the small head layers left on torch may use the tensor cores
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(42)
     model = instantiate_model(exp_kwargs, in_features_dict[exp_kwargs["data_type"]], window_size, device).to(device)
     if hasattr(model, "use_cudnn"):

@@ -445,4 +445,5 @@ def test_graph_epoch_matches_eager_epoch(fold_on_disk):
         assert abs(a[0] - b[0]) < 1e-6 * max(1.0, abs(a[0])), (a[0], b[0])
         assert np.array_equal(a[5], b[5])
         assert a[7] == b[7] and a[8] == b[8] and a[9] == b[9]
-        assert np.abs(np.asarray(a[6]) - np.asarray(b[6])).max() < 1e-5
+        # torch's conv / BN backward kernels use atomics: two runs of the SAME loop differ by ~2e-5 in the second epoch's probabilities
+        assert np.abs(np.asarray(a[6]) - np.asarray(b[6])).max() < 1e-4
