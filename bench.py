@@ -139,6 +139,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm may use all the host threads there are
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     cores = torch.get_num_threads()
     batch = 512
     n = batch * max(1, args.steps)
@@ -274,8 +279,12 @@ def run_gpu(args):
     k1_iso_ms = statistics.mean(iso)
     hbm_peak, tf_peak, peak_src = measured_peaks()
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
-    roofline = {"kernel": "gather_norm_kernel (K1: window gather + standardise + concat)", "bound": "hbm",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+    # DRAM traffic per step's K1 from the ncu --set full capture of this very configuration
+    # (profiles/r1_ncu_gather_norm_tma_bf16.md: image launch 1.0626 GB read + 0.4970 GB written, kinematics launch 13.4 MB)
+    traffic = 1.0626e9 + 0.4970e9 + 13.4e6 if (args.precision == "bf16" and B == 8192 and args.gather_variant == 0) else None
+    roofline = {"kernel": "gather_norm_tma_kernel + gather_norm_kernel (K1: window gather + standardise + concat, image + kinematics streams)",
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_gather_norm_tma_bf16.md" if traffic else None,
                 "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms, "ms_per_launch_isolated": k1_iso_ms,
                 "share_of_step": k1_ms / step_ms, "how": k1_how, "peak_source": peak_src}
 
@@ -320,6 +329,10 @@ def run_gpu(args):
         cpu = None
         if True:
             try:
+                try:       # torchrun exports OMP_NUM_THREADS=1; the CPU baseline runs on rank 0 with every host thread
+                    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+                except Exception:
+                    pass
                 wps, dt, n_done, build_s = cpu_train_windows_per_sec(args.cpu_windows, 512)
                 cpu = {"value": wps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                        "sample": f"{n_done} windows (W={W}) of the same workload, B=512, one oracle train_epoch = {dt:.1f}s "

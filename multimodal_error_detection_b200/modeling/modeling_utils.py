@@ -256,6 +256,34 @@ def compute_loss(outputs: torch.Tensor, e_labels: torch.Tensor, criterion, datas
 # =====================================================================================================
 # epoch bookkeeping: everything stays on the device until the epoch ends
 # =====================================================================================================
+class _HostLossRing:
+    """Per-step device -> host read of the loss with a lag of one step: push() enqueues an asynchronous copy of this
+    step's loss into pinned memory and then reads (on the host) the PREVIOUS step's value, whose copy has had a whole
+    step to land.  `values` ends up with every step's loss, in order."""
+
+    def __init__(self, device):
+        self.buf = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.k = 0
+        self.values = []
+
+    def push(self, loss: torch.Tensor):
+        slot = self.k & 1
+        self.buf[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.ev[slot].record()
+        if self.k > 0:
+            self._read(slot ^ 1)
+        self.k += 1
+
+    def _read(self, slot):
+        self.ev[slot].synchronize()
+        self.values.append(float(self.buf[slot]))
+
+    def drain(self):
+        if self.k > 0:
+            self._read((self.k - 1) & 1)
+
+
 class _EpochLog:
     def __init__(self):
         self.losses, self.counts, self.extra = [], [], {}
@@ -410,6 +438,11 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
     log = _EpochLog()
     subjects_all = []
     want_preds = exp_kwargs["return_train_preds"]
+    # host_sync == "step": the reference reads the loss on the host every batch (`train_loss += loss.item()`, :366).  Here
+    # every step's loss is copied to pinned host memory asynchronously and read one step later, so the read of step k-1
+    # overlaps the execution of step k instead of draining the GPU queue.
+    step_sync = exp_kwargs.get("host_sync") == "step"
+    ring = _HostLossRing(device) if step_sync else None
     for idx in loader.index_batches():
         n = idx.numel()
         if n == 0:
@@ -439,11 +472,13 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
             probs, preds, counts = criterion.last
             loss = loss.detach().reshape(1)
             extra = dict(preds=preds, labels=y.reshape(-1), probs=probs) if want_preds else {}
-        if exp_kwargs.get("host_sync") == "step":
-            loss.item()
+        if step_sync:
+            ring.push(loss)
         log.add(loss, counts, **extra)
         if want_preds:
             subjects_all += ds.subjects_of(idx.tolist())
+    if step_sync:
+        ring.drain()
     if scheduler is not None:
         scheduler.step()
     n_batches = max(len(log.losses), 1)
