@@ -204,7 +204,7 @@ int b200med_lstm_cell_bwd(const float *Gact, const float *c, const float *c_prev
  *             h_out [B,H] f32; each may be NULL.  Dropout mask = f(*seed, drop_base + (t*Bpad+b)*H + j).
  *   backward: dh_t = dropout'(dh_up[t,b,:]) (+ dh_top [B,H] at t = W-1) + dG_{t+1} W_hh;  dh_up RBI f32
  *             [W*Bpad, up_cols]; dG [W,Bpad,4H] bf16 row-major OUT (TMA store) with PERMUTED gate columns:
- *             column' = (u/64)*256 + ((u%64)/16)*64 + gate*16 + u%16 holds gate column gate*H + u.                   */
+ *             column' = ((u%32)/8)*128 + (u/32)*32 + gate*8 + u%8 holds gate column gate*H + u.                      */
 int b200med_lstm_rec_fwd(const void *xg, const void *whh_bf16, void *gact, float *c, void *a_next, int32_t ld_next,
                          int32_t hoff, void *a_up, int32_t ld_up, float *h_out, int64_t B, int64_t Bpad, int32_t W,
                          int32_t H, float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream);

@@ -13,10 +13,10 @@
 //
 //   backward  dG_t = cell'(gates_t, c_t, c_{t-1}, dh_t, dc_t);   dh_{t-1} = dG_t [128, 4H] * W_hh [4H, H]
 //             K = 4H = 512: the bf16 dG_t tile (128 KB) does not fit beside W_hh, so the epilogue hands it to the MMA
-//             in four 32 KB chunks (16 units x 4 gates x 2 unit-halves = 8 K-steps each) through a 2-deep ring; the same
+//             in four 32 KB chunks (8 units x 4 gates x 4 unit-quarters = 8 K-steps each) through a 2-deep ring; the same
 //             ring slots are TMA-STOREd to dG in HBM for the batched dX = dG * W_ih and dW = dG^T [x|h] GEMMs.  So that a
-//             ring slot is a contiguous 64-column block of a row-major matrix, dG's COLUMNS ARE PERMUTED:
-//                 column' = unit_half*256 + chunk*64 + gate*16 + i   <->   gate column = gate*H + unit_half*64 + chunk*16 + i
+//             ring slot is a contiguous 128-column block of a row-major matrix, dG's COLUMNS ARE PERMUTED:
+//                 column' = chunk*128 + unit_quarter*32 + gate*8 + i   <->   gate column = gate*H + unit_quarter*32 + chunk*8 + i
 //             (the host permutes W_ih's rows / un-permutes dW's rows and db accordingly, lstm_stack.py).  W_hh is loaded
 //             once by TMA as 16-row boxes in exactly the MMA's K order (MN-major B operand).  The dh accumulator is
 //             double-buffered in TMEM (2 x 128 columns).
@@ -34,8 +34,7 @@ namespace b200med {
 
 constexpr int kRecH = 128;         // hidden size this kernel's shared-memory / TMEM plan is built for
 constexpr int kRecRows = 128;      // windows per CTA (= TMEM lanes)
-constexpr int kRecThreads = 256;   // 8 warps of cell epilogue (2 per SM sub-partition -> 255 registers each); lane 0 of
-                                   // warp 0 also issues the TMA copies and the tcgen05.mma instructions
+// lane 0 of warp 0 also issues the TMA copies and the tcgen05.mma instructions (no dedicated MMA warp: registers are per sub-partition)
 constexpr uint32_t kWhhBytes = 4 * kRecH * kRecH * 2;  // 128 KB
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -356,17 +355,21 @@ struct RecBwdParams {
     uint32_t drop_base;
 };
 
+constexpr int kBwdThreads = 512;   // 16 warps: lane quarter = warp % 4, unit quarter = warp / 4 (32 units each)
 constexpr size_t kRecBwdSmem = 1024 + kWhhBytes + 65536 + 128;
 
-__global__ void __launch_bounds__(kRecThreads, 1)
+// K order of the dh GEMM (and column order of dG in HBM): k' = chunk*128 + unit_quarter*32 + gate*8 + i stands for gate
+// column gate*H + unit_quarter*32 + chunk*8 + i.  Chunk c of a step = the 8 units every thread finishes in its c-th pass.
+template <bool kDrop>
+__global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_constant__ CUtensorMap tmap_dg,
                     const RecBwdParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = align_1024(smem_dyn);
     unsigned char *b_sm = smem;                 // W_hh as MN-major B operand: [k-block 0..7][n-half 0..1][64 k][128 B]
-    unsigned char *a_sm = smem + kWhhBytes;     // dG chunk ring: [slot 0..1][unit-half 0..1][128 rows][128 B]
+    unsigned char *a_sm = smem + kWhhBytes;     // dG chunk ring: [slot 0..1][k-block 0..1][128 rows][128 B]
     uint64_t *w_full = reinterpret_cast<uint64_t *>(a_sm + 65536);
-    uint64_t *chunk_ready = w_full + 1;         // [2], 8 arrivals (one per warp)
+    uint64_t *chunk_ready = w_full + 1;         // [2], 16 arrivals (one per warp)
     uint64_t *slot_free = w_full + 3;           // [2], 2 arrivals: MMA done with the slot, TMA store done reading it
     uint64_t *acc_full = w_full + 5;            // tcgen05.commit
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 6);
@@ -374,7 +377,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         bar_init(w_full, 1);
-        bar_init(&chunk_ready[0], 8); bar_init(&chunk_ready[1], 8);
+        bar_init(&chunk_ready[0], kBwdThreads / 32); bar_init(&chunk_ready[1], kBwdThreads / 32);
         bar_init(&slot_free[0], 2); bar_init(&slot_free[1], 2);
         bar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -393,36 +396,36 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
     if (threadIdx.x == 0 && W > 1) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_whh) : "memory");
         bar_expect_tx(w_full, kWhhBytes);
-        // K order of the MMA = (chunk c, unit half uh, gate, 16 units): gate row k = gate*H + 64*uh + 16*c + i
-        for (int kb = 0; kb < 8; ++kb) {
-            const int c = kb >> 1, uh = kb & 1;
-            for (int g = 0; g < 4; ++g)
-                for (int nh = 0; nh < 2; ++nh)
-                    tma_load_2d(b_sm + kb * 16384 + nh * 8192 + g * 2048, &tmap_whh, w_full, nh * 64,
-                                g * kRecH + uh * 64 + c * 16);
-        }
+        // 8-row boxes of W_hh in the MMA's K order (see above): k-block kb' = 2*chunk + (unit_quarter >> 1)
+        for (int c = 0; c < 4; ++c)
+            for (int uqq = 0; uqq < 4; ++uqq)
+                for (int g = 0; g < 4; ++g)
+                    for (int nh = 0; nh < 2; ++nh)
+                        tma_load_2d(b_sm + (2 * c + (uqq >> 1)) * 16384 + nh * 8192 + ((uqq & 1) * 4 + g) * 1024, &tmap_whh,
+                                    w_full, nh * 64, g * kRecH + uqq * 32 + c * 8);
     }
     const uint32_t idesc = make_idesc(128, 128, false, true);
     const uint32_t aa = s_addr(a_sm), ba = s_addr(b_sm);
 
-    const int q = warp & 3, uh = warp >> 2;
+    const int q = warp & 3, uq = warp >> 2;
     const int row = q * 32 + lane;
     const long long b = (long long)m0 + row;
     // Bpad is a multiple of 32 and a warp owns 32 consecutive rows: validity is warp-uniform
     const bool ok = __shfl_sync(0xffffffffu, (int)(b < p.Bpad), 0) != 0;
-    const uint32_t seed = p.seed ? *p.seed : 0u;
-    const bool drop = p.drop_p > 0.0f;
-    const float keep_scale = drop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const uint32_t seed = (kDrop && p.seed) ? *p.seed : 0u;
+    const float keep_scale = kDrop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
     const uint32_t thr16 = (uint32_t)(p.drop_p * 65536.0f);
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    float dc[64];
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(uq * 32);
+    unsigned char *a_row = a_sm + (uq >> 1) * 16384 + row * 128;     // + slot * 32768
+    const int slot16 = (uq & 1) * 4;                                 // 16-byte slot of gate 0 within the 128-byte row
+    float dc[32];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) dc[j] = 0.0f;
+    for (int j = 0; j < 32; ++j) dc[j] = 0.0f;
 
     auto rblk = [&](int t) -> long long { return ((long long)t * p.Bpad + m0) / 32 + q; };
     struct Regs { uint4 ga[4]; float4 ct[2], cp[2], du[2]; };
-    auto load = [&](Regs &r, int t, int sc) {
-        const int u = uh * 64 + sc * 8;
+    auto load = [&](Regs &r, int t, int c) {
+        const int u = uq * 32 + c * 8;
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok) {
             const long long rb = rblk(t);
@@ -460,21 +463,21 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
             tcgen05_fence_after();
         }
         const uint32_t acc_prev = t_lane + (uint32_t)(((step - 1) & 1) * 128);
-        if (ok && uh == 0 && lane == 0 && t > 0) {
+        if (ok && uq == 0 && lane == 0 && t > 0) {
             const long long rbp = rblk(t - 1);
             prefetch_l2_bulk(p.gact + rbp * (32 * 4 * kRecH), 32 * 4 * kRecH * 2);
             if (t > 1) prefetch_l2_bulk(p.c + rblk(t - 2) * (32 * kRecH), 32 * kRecH * 4);
             if (p.dh_up) prefetch_l2_bulk(p.dh_up + rbp * (32 * (long long)p.up_cols), 32 * (uint32_t)p.up_cols * 4);
         }
 #pragma unroll
-        for (int sc = 0; sc < 8; ++sc) {
-            const int u = uh * 64 + sc * 8;
+        for (int c = 0; c < 4; ++c) {
+            const int u = uq * 32 + c * 8;
             Regs nxt;
-            if (sc < 7) load(nxt, t, sc + 1);
+            if (c < 3) load(nxt, t, c + 1);
             else if (t > 0) load(nxt, t - 1, 0);
             uint32_t rec[8];
             if (have_rec) {
-                tmem_ld8_nowait(acc_prev + (uint32_t)u, rec);
+                tmem_ld8_nowait(acc_prev + (uint32_t)(c * 8), rec);
                 tmem_wait_ld();
             }
             float gi[8], gf[8], gg[8], go[8];
@@ -483,7 +486,7 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
             const float ct[8] = {cur.ct[0].x, cur.ct[0].y, cur.ct[0].z, cur.ct[0].w, cur.ct[1].x, cur.ct[1].y, cur.ct[1].z, cur.ct[1].w};
             const float cp[8] = {cur.cp[0].x, cur.cp[0].y, cur.cp[0].z, cur.cp[0].w, cur.cp[1].x, cur.cp[1].y, cur.cp[1].z, cur.cp[1].w};
             float dh[8] = {cur.du[0].x, cur.du[0].y, cur.du[0].z, cur.du[0].w, cur.du[1].x, cur.du[1].y, cur.du[1].z, cur.du[1].w};
-            if (drop) {
+            if (kDrop) {
                 float sc8[8];
                 drop_scales<8>(seed, p.drop_base + (uint32_t)(((long long)t * p.Bpad + b) * kRecH + u), thr16, keep_scale, sc8);
 #pragma unroll
@@ -497,60 +500,57 @@ lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_c
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float tc = tanh_fast(ct[j]);
-                const float dct = fmaf(dh[j] * go[j], 1.0f - tc * tc, dc[sc * 8 + j]);
+                const float dct = fmaf(dh[j] * go[j], 1.0f - tc * tc, dc[c * 8 + j]);
                 di[j] = dct * gg[j] * gi[j] * (1.0f - gi[j]);
                 df[j] = dct * cp[j] * gf[j] * (1.0f - gf[j]);
                 dg[j] = dct * gi[j] * (1.0f - gg[j] * gg[j]);
                 d_o[j] = dh[j] * tc * go[j] * (1.0f - go[j]);
-                dc[sc * 8 + j] = dct * gf[j];
+                dc[c * 8 + j] = dct * gf[j];
             }
             const uint4 pk[4] = {pack_bf16x8(di), pack_bf16x8(df), pack_bf16x8(dg), pack_bf16x8(d_o)};
-            const int c = sc >> 1, s = sc & 1, slot = c & 1;
+            const int slot = c & 1;
             const int n = 2 * step + (c >> 1);            // this is the n-th fill of the ring slot
-            if (s == 0 && n > 0) bar_wait(&slot_free[slot], (uint32_t)((n - 1) & 1));
-            unsigned char *a_row = a_sm + slot * 32768 + uh * 16384 + row * 128;
+            if (n > 0) bar_wait(&slot_free[slot], (uint32_t)((n - 1) & 1));
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-                *reinterpret_cast<uint4 *>(a_row + (((g * 2 + s) ^ (row & 7)) << 4)) = pk[g];
-            if (s == 1) {
-                fence_proxy_async_smem();
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) bar_arrive(&chunk_ready[slot]);
-                if (warp == 0) {
-                    if (lane == 0) {
-                        bar_wait(&chunk_ready[slot], (uint32_t)(n & 1));
-                        tcgen05_fence_after();
-                        // dG_t[:, (4 gates) x (16 units of this chunk, both unit halves)] -> HBM
-                        tma_store_3d(&tmap_dg, a_sm + slot * 32768, c * 64, m0, t);
-                        tma_store_3d(&tmap_dg, a_sm + slot * 32768 + 16384, 256 + c * 64, m0, t);
-                        bulk_commit();
-                        if (feed) {
-                            if (n == 0 && slot == 0) bar_wait(w_full, 0);
-                            // dh_{t-1} += dG_t[:, this chunk's 128 K columns] * W_hh[those rows, :]
-                            const uint32_t acc = tmem_base + (uint32_t)((step & 1) * 128);
+                *reinterpret_cast<uint4 *>(a_row + slot * 32768 + (((slot16 + g) ^ (row & 7)) << 4)) = pk[g];
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&chunk_ready[slot]);
+            if (warp == 0) {
+                if (lane == 0) {
+                    bar_wait(&chunk_ready[slot], (uint32_t)(n & 1));
+                    tcgen05_fence_after();
+                    // dG_t[:, columns' c*128 .. +128] -> HBM
+                    tma_store_3d(&tmap_dg, a_sm + slot * 32768, c * 128, m0, t);
+                    tma_store_3d(&tmap_dg, a_sm + slot * 32768 + 16384, c * 128 + 64, m0, t);
+                    bulk_commit();
+                    if (feed) {
+                        if (n == 0 && slot == 0) bar_wait(w_full, 0);
+                        // dh_{t-1} += dG_t[:, this chunk's 128 K columns] * W_hh[those rows, :]
+                        const uint32_t acc = tmem_base + (uint32_t)((step & 1) * 128);
 #pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {
+                        for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-                                for (int g = 0; g < 4; ++g) {
-                                    const uint64_t da = make_smem_desc(aa + slot * 32768 + hh * 16384 + g * 32, 16, 1024);
-                                    const uint64_t db = make_smem_desc(ba + (2 * c + hh) * 16384 + g * 2048, 8192, 1024);
-                                    umma_bf16(acc, da, db, idesc, (c | hh | g) ? 1u : 0u);
-                                }
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t da = make_smem_desc(aa + slot * 32768 + kb * 16384 + ks * 32, 16, 1024);
+                                const uint64_t db = make_smem_desc(ba + (2 * c + kb) * 16384 + ks * 2048, 8192, 1024);
+                                umma_bf16(acc, da, db, idesc, (c | kb | ks) ? 1u : 0u);
                             }
-                            umma_commit(&slot_free[slot]);
-                            if (c == 3) umma_commit(acc_full);
-                        } else {
-                            bar_arrive(&slot_free[slot]);
                         }
-                        // the PREVIOUS chunk's store has finished reading its slot once at most one group is pending
-                        if (step > 0 || c > 0) {
-                            bulk_wait_read<1>();
-                            bar_arrive(&slot_free[slot ^ 1]);
-                        }
+                        umma_commit(&slot_free[slot]);
+                        if (c == 3) umma_commit(acc_full);
+                    } else {
+                        bar_arrive(&slot_free[slot]);
                     }
-                    __syncwarp();
+                    // the PREVIOUS chunk's store has finished reading its slot once at most one group is pending
+                    if (step > 0 || c > 0) {
+                        bulk_wait_read<1>();
+                        bar_arrive(&slot_free[slot ^ 1]);
+                    }
                 }
+                __syncwarp();
             }
             cur = nxt;
         }
@@ -626,19 +626,19 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_rec_bwd(
     B200MED_REQUIRE(!dh_up || (up_cols >= H && up_cols % 4 == 0 && (uintptr_t)dh_up % 16 == 0), "bad dh_up");
     if (!b200med_has_tcgen05()) { set_error("tcgen05 path needs a compute-capability 10.x device"); return B200MED_E_UNSUPPORTED; }
     CUtensorMap tm, tg;
-    if (int e = make_tmap(&tm, whh_bf16, kRecH, 4 * kRecH, kRecH, 64, 16)) return e;    // box {64 n, 16 gate rows}
+    if (int e = make_tmap(&tm, whh_bf16, kRecH, 4 * kRecH, kRecH, 64, 8)) return e;     // box {64 n, 8 gate rows}
     if (int e = make_tmap_a(&tg, dG, W, Bpad, 4 * kRecH)) return e;   // dG [W, Bpad, 4H] row-major, box {64, 128, 1}
     RecBwdParams p{};
     p.gact = reinterpret_cast<const __half *>(gact);
     p.c = c; p.dh_top = dh_top; p.dh_up = dh_up; p.up_cols = up_cols;
-    p.B = B; p.Bpad = Bpad; p.W = W; p.drop_p = drop_p; p.seed = seed; p.drop_base = (uint32_t)drop_base;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (int e = check_cuda(cudaFuncSetAttribute(lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecBwdSmem),
-                               "cudaFuncSetAttribute(lstm_rec_bwd)")) return e;
-        attr_set = true;
-    }
+    p.B = B; p.Bpad = Bpad; p.W = W; p.drop_p = dh_up ? drop_p : 0.0f; p.seed = seed; p.drop_base = (uint32_t)drop_base;
     const unsigned grid = (unsigned)((Bpad + kRecRows - 1) / kRecRows);
-    lstm_rec_bwd_kernel<<<grid, kRecThreads, kRecBwdSmem, (cudaStream_t)stream>>>(tm, tg, p);
+    auto launch = [&](auto kern) -> int {
+        if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecBwdSmem),
+                               "cudaFuncSetAttribute(lstm_rec_bwd)")) return e;
+        kern<<<grid, kBwdThreads, kRecBwdSmem, (cudaStream_t)stream>>>(tm, tg, p);
+        return B200MED_OK;
+    };
+    if (int e = (dh_up && drop_p > 0.0f) ? launch(lstm_rec_bwd_kernel<true>) : launch(lstm_rec_bwd_kernel<false>)) return e;
     return after_launch("lstm_rec_bwd_kernel");
 }

@@ -137,8 +137,8 @@ def _dg_perm(H: int, device):
     key = (H, str(device))
     if key not in _PERM:
         cp = torch.arange(4 * H)
-        uh, c, g, i = cp // 256, (cp % 256) // 64, (cp % 64) // 16, cp % 16
-        orig = g * H + uh * 64 + c * 16 + i
+        c, uq, g, i = cp // 128, (cp % 128) // 32, (cp % 32) // 8, cp % 8
+        orig = g * H + uq * 32 + c * 8 + i
         inv = torch.empty_like(orig)
         inv[orig] = cp
         _PERM[key] = (orig.to(device), inv.to(device))

@@ -117,8 +117,11 @@ class FusedAdam(torch.optim.Optimizer):
                 for p, _, _ in c.members:
                     p.grad = None
             return
+        # Detach the views: autograd then ASSIGNS each parameter's incoming gradient (no `grad += g` kernel per tensor);
+        # _refresh_active() gathers them into the chunk with one multi-tensor copy before the all-reduce / Adam step.
         for c in self.chunks:
-            c.grad.zero_()        # gradients live in the chunk; the views stay in place (one memset per chunk)
+            for p, _, _ in c.members:
+                p.grad = None
 
     def _refresh_active(self):
         """Adopt the gradients of parameters seen for the first time and rebuild the active ranges."""
@@ -134,6 +137,24 @@ class FusedAdam(torch.optim.Optimizer):
                         p.grad = view
                     self._active[id(p)] = True
                     changed = True
+        # gather this step's gradients into the chunks (one multi-tensor copy; untouched active parameters read as zero)
+        dst, src, zero = [], [], []
+        for c in self.chunks:
+            for p, o, n in c.members:
+                if not self._active.get(id(p), False):
+                    continue
+                view = c.grad[o:o + n].view_as(p.data)
+                if p.grad is None:
+                    zero.append(view)
+                    p.grad = view
+                elif p.grad.data_ptr() != view.data_ptr():
+                    dst.append(view)
+                    src.append(p.grad.detach())
+                    p.grad = view
+        if dst:
+            torch._foreach_copy_(dst, src)
+        if zero:
+            torch._foreach_zero_(zero)
         if changed:
             for c in self.chunks:
                 runs = []
