@@ -312,15 +312,19 @@ def run_gpu(args):
     if not args.no_e2e:
         kw_e2e = dict(kw, host_sync="step")
         loader = DeviceWindowLoader(ds, B, shuffle=True, generator=torch.Generator().manual_seed(42), rank=0, world_size=1)
-        steps_e2e = min(K, len(loader))
-        loader.max_batches = Wm                                  # untimed warm-up pass (also captures the step's CUDA graph)
+        full = max(1, n_windows // B)                            # full batches per pass: every timed step is a B-window graph replay
+        loader.max_batches = min(Wm, full)                       # untimed warm-up pass (also captures the step's CUDA graph)
         mu.train_single_epoch(model, fe, loader, crit, opt, None, device, kw_e2e)
-        loader.max_batches = steps_e2e
         torch.cuda.synchronize(); parallel.barrier()
         t0 = time.perf_counter()
-        res = mu.train_single_epoch(model, fe, loader, crit, opt, None, device, kw_e2e)
+        left, res = K, None
+        while left > 0:                                          # K steps = as many passes over the loader as it takes
+            loader.max_batches = min(left, full)
+            res = mu.train_single_epoch(model, fe, loader, crit, opt, None, device, kw_e2e)
+            left -= loader.max_batches
         torch.cuda.synchronize()
         dt = parallel.max_over_ranks(time.perf_counter() - t0, device)
+        steps_e2e = K
         e2e = {"value": world * steps_e2e * B / dt, "unit": UNIT, "h2d_bytes_per_step": B * 8, "d2h_bytes_per_step": 4,
                "steps": steps_e2e, "api": "modeling_utils.train_single_epoch(DeviceWindowLoader)", "loss": res[0],
                "table_upload_bytes_once": int(n_frames * (IMAGE_DIM + KIN_DIM + 6) * 4)}

@@ -55,7 +55,11 @@ struct GemmCfg {
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N>
+// EPI selects the epilogue at compile time (smaller code, no mode branches in the drain loop):
+//   0 row-major output with bias / ReLU / ReLU-mask, 1 row-block-interleaved output with bias / ReLU, 2 split-K fp32 partial.
+constexpr int kEpiRowMajor = 0, kEpiRbi = 1, kEpiPartial = 2;
+
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
@@ -183,7 +187,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tcgen05_fence_after();
             const long long m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
-            const bool partial = p.split_k > 1;
+            constexpr bool partial = EPI == kEpiPartial;
             const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N + c_first);
             uint32_t vbuf[2][32];
             if (has_work) {
@@ -220,7 +224,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
                         }
-                        if (p.mask) {
+                        if (EPI == kEpiRowMajor && p.mask) {
                             const __nv_bfloat16 *mk = p.mask + m * p.ldd + n_base;
                             if (full && (((uintptr_t)mk) % 16 == 0)) {
 #pragma unroll
@@ -242,7 +246,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             }
                         }
                     }
-                    if (p.out_rbi) {
+                    if (EPI == kEpiRbi) {
                         // one 16-byte vector per lane and column group: a warp writes 512 contiguous bytes
                         const long long rb = m >> 5;
                         const int rl = (int)(m & 31);
@@ -334,10 +338,10 @@ static int pick_block_n(long long N, int b_kmajor) {
     return 32;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI>
 static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &p, cudaStream_t st) {
     using Cfg = GemmCfg<BLOCK_N>;
-    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N>;
+    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>;
     static bool attr_set = false;
     if (!attr_set) {
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes),
@@ -410,12 +414,24 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
     p.out_f16 = out_dtype == B200MED_F16;
 
     int e;
+    const int epi = split_k > 1 ? kEpiPartial : (p.out_rbi ? kEpiRbi : kEpiRowMajor);
+#define B200MED_GEMM_CASE(BN)                                                                   \
+    case BN:                                                                                    \
+        e = epi == kEpiPartial ? launch_gemm_tc<BN, kEpiPartial>(ta, tb, p, st)                 \
+            : epi == kEpiRbi   ? launch_gemm_tc<BN, kEpiRbi>(ta, tb, p, st)                     \
+                               : launch_gemm_tc<BN, kEpiRowMajor>(ta, tb, p, st);               \
+        break;
     switch (block_n) {
-        case 256: e = launch_gemm_tc<256>(ta, tb, p, st); break;
-        case 128: e = launch_gemm_tc<128>(ta, tb, p, st); break;
-        case 64: e = launch_gemm_tc<64>(ta, tb, p, st); break;
-        default: e = launch_gemm_tc<32>(ta, tb, p, st); break;
+        B200MED_GEMM_CASE(256)
+        B200MED_GEMM_CASE(128)
+        B200MED_GEMM_CASE(64)
+        default:
+            e = epi == kEpiPartial ? launch_gemm_tc<32, kEpiPartial>(ta, tb, p, st)
+                : epi == kEpiRbi   ? launch_gemm_tc<32, kEpiRbi>(ta, tb, p, st)
+                                   : launch_gemm_tc<32, kEpiRowMajor>(ta, tb, p, st);
+            break;
     }
+#undef B200MED_GEMM_CASE
     if (e) return e;
     if (split_k > 1) {
         const long long total = M * N;

@@ -341,7 +341,7 @@ def test_lstm_stack_bf16_vs_torch(impl, B, W):
     xo = x.clone().requires_grad_(True)
     h = lstm_last_hidden(xo, lstm, training=True, seed_dev=None, impl=impl)
     h.backward(gh)
-    nrel = lambda a, b: float((a.float() - b).norm() / b.norm())
+    nrel = lambda a, b: float((a.float() - b).norm() / b.norm().clamp_min(1e-12))   # W = 1: the W_hh gradients are exactly 0
     errs = {"h": nrel(h.detach(), ref_h), "dx": nrel(xo.grad, ref_dx)}
     errs.update({k: nrel(p.grad, ref[k]) for k, p in lstm.named_parameters()})
     print(impl, B, W, {k: round(v, 5) for k, v in errs.items()})
