@@ -57,7 +57,7 @@ class WindowTrainStep:
         outputs = self.model(inputs)
         loss, _ = mu.compute_loss(outputs, labels, self.crit, "window")
         self.opt.zero_grad()
-        loss.backward()
+        mu._backward(loss, self.opt)
         mu._allreduce_grads(self.opt)
         self.opt.step()
         probs, preds, counts = self.crit.last

@@ -122,6 +122,21 @@ class LSTMStackFunction(torch.autograd.Function):
 
 _PERM = {}
 _SIDE = {}
+# Deferred join of the side stream.  The weight / bias gradients of the LSTM layers are computed on a side stream; with
+# DEFER_JOIN the backward returns them WITHOUT making the main stream wait (autograd only stores the tensors when
+# `.grad is None`), so the side work of layer 0 overlaps the FeatureExtractor backward.  Whoever consumes the gradients
+# (FusedAdam._refresh_active -> all-reduce / Adam) calls join_pending() first.  Off by default: a caller that reads
+# `.grad` right after backward() gets the join inside the backward.
+DEFER_JOIN = False
+_PENDING = []
+
+
+def join_pending():
+    """Make the current stream wait for gradient work still running on the side stream."""
+    while _PENDING:
+        side, keep = _PENDING.pop()
+        torch.cuda.current_stream().wait_stream(side)
+        keep.clear()
 
 
 def _side_stream(device) -> torch.cuda.Stream:
@@ -243,8 +258,11 @@ class LSTMRecFunction(torch.autograd.Function):
                 # below's recurrence kernel, row-major for the unpack into [B, F, W]
                 dX_up = ops.gemm_bf16(dG, Wih[l].index_select(0, orig_of), W * Bp, inp[l], 4 * H, True, False,
                                       out_dtype=torch.float32, rbi=l > 0)
-        main.wait_stream(side)
-        keep.clear()
+        if DEFER_JOIN:
+            _PENDING.append((side, keep))      # joined by the gradient consumer (join_pending)
+        else:
+            main.wait_stream(side)
+            keep.clear()
         for g in grads:
             g.record_stream(main)
         dx = None

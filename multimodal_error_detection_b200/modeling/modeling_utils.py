@@ -321,6 +321,18 @@ def _set_train(model, feature_extractor, exp_kwargs, train: bool):
         m.train(train)
 
 
+def _backward(loss, optimizer=None):
+    """loss.backward() inside a train loop: the LSTM weight-gradient GEMMs stay on their side stream past the end of the
+    backward (lstm_stack.DEFER_JOIN); the next consumer of the gradients (_allreduce_grads / optimizer.step, both through
+    FusedAdam._refresh_active) joins it."""
+    from .. import lstm_stack
+    lstm_stack.DEFER_JOIN = isinstance(optimizer, FusedAdam)      # only FusedAdam joins the side stream before using the gradients
+    try:
+        loss.backward()
+    finally:
+        lstm_stack.DEFER_JOIN = False
+
+
 def _allreduce_grads(optimizer):
     """Data-parallel exchange: ONE sum all-reduce of the flat gradient buffer."""
     import torch.distributed as dist
@@ -382,7 +394,7 @@ def train_single_epoch(model, feature_extractor, train_dataloader, criterion, op
         outputs = model(inputs)
         loss, outputs = compute_loss(outputs, y, criterion, exp_kwargs["dataset_type"])
         optimizer.zero_grad()
-        loss.backward()
+        _backward(loss, optimizer)
         _allreduce_grads(optimizer)
         optimizer.step()
         if exp_kwargs.get("host_sync") == "step":
@@ -466,7 +478,7 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
             outputs = model(define_inputs(images, kin, feature_extractor, exp_kwargs, device))
             loss, outputs = compute_loss(outputs, y, criterion, "window")
             optimizer.zero_grad()
-            loss.backward()
+            _backward(loss, optimizer)
             _allreduce_grads(optimizer)
             optimizer.step()
             probs, preds, counts = criterion.last
@@ -586,7 +598,7 @@ def train_single_epoch_ES(model, feature_extractor, train_dataloader, criterion,
         C = outputs.shape[1]
         loss = crit(outputs, y, cm_classes=max(C, 6))
         optimizer.zero_grad()
-        loss.backward()
+        _backward(loss, optimizer)
         _allreduce_grads(optimizer)
         optimizer.step()
         cm = crit.last[2] if cm is None else cm + crit.last[2]
@@ -660,7 +672,7 @@ def train_single_epoch_Sequential(model, feature_extractor, train_dataloader, cr
         outputs = model(define_inputs(images, kin, feature_extractor, exp_kwargs, device))
         loss = crit(outputs, y, mask=mask, target_shift=-1, reduction=1, pred_shift=1, pred_mask_mode=1, cm_classes=6)
         optimizer.zero_grad()
-        loss.backward()
+        _backward(loss, optimizer)
         _allreduce_grads(optimizer)
         optimizer.step()
         cm = crit.last[2] if cm is None else cm + crit.last[2]

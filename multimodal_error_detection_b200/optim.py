@@ -125,6 +125,8 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _refresh_active(self):
         """Adopt the gradients of parameters seen for the first time and rebuild the active ranges."""
+        from . import lstm_stack
+        lstm_stack.join_pending()      # gradient GEMMs still running on the side stream (lstm_stack.DEFER_JOIN)
         changed = self._active is None
         if self._active is None:
             self._active = {}
