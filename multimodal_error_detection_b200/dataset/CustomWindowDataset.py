@@ -145,15 +145,31 @@ class DeviceWindowLoader:
         self.dataset, self.batch_size, self.shuffle, self.generator = dataset, batch_size, shuffle, generator
         self.rank, self.world_size = rank, world_size
         self.max_batches = None        # optional cap on batches per pass (bounded benchmark epochs)
+        # the real thing, kept as the definition of "the reference's order" (tests compare index_batches() against it)
         self._order = DataLoader(_IndexOnly(len(dataset)), batch_size=batch_size, shuffle=shuffle, generator=generator,
                                  collate_fn=lambda items: torch.as_tensor(items, dtype=torch.int64))
 
     def __len__(self):
         return len(self._order)
 
+    def _global_batches(self):
+        """The batches torch's DataLoader would produce, without its per-sample Python loop (8192 `__getitem__` calls and a
+        list round trip per batch cost more host time than the GPU needs for the step).  Mirrors the generator consumption
+        of torch.utils.data exactly: `_BaseDataLoaderIter.__init__` draws a base seed (`random_` on an int64 scalar), then
+        RandomSampler draws `randperm(n)` and -- once the pass is exhausted -- a second, discarded `randperm(n)`
+        (`num_samples % n` tail).  tests/test_host_logic.py pins this against the real DataLoader."""
+        n, B = len(self.dataset), self.batch_size
+        torch.empty((), dtype=torch.int64).random_(generator=self.generator)
+        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
+        for lo in range(0, n, B):
+            yield order[lo:lo + B]
+        if self.shuffle:
+            torch.randperm(n, generator=self.generator)
+
     def index_batches(self):
-        """Host int64 index tensors, one per (rank-local) batch."""
-        for k, idx in enumerate(self._order):
+        """Host int64 index tensors, one per (rank-local) batch (the consumer pins them: torch's caching host allocator
+        keeps a pinned block alive until the asynchronous upload that reads it has run)."""
+        for k, idx in enumerate(self._global_batches()):
             if self.max_batches is not None and k >= self.max_batches:
                 break
             if self.world_size > 1:

@@ -111,6 +111,40 @@ def test_sampler_matches_torch_dataloader():
         assert [b[0].tolist() for b in ref] == [b.tolist() for b in mine]
 
 
+def test_index_batches_mirror_the_dataloader_exactly():
+    """DeviceWindowLoader.index_batches() (vectorised: one randperm per pass) yields the batches of the stock DataLoader
+    bit for bit, epoch after epoch, including the generator state left behind by a full pass, by an abandoned pass
+    (max_batches) and in the unshuffled case; world_size 2 shards every global batch contiguously."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from multimodal_error_detection_b200.dataset.CustomWindowDataset import DeviceWindowLoader
+
+    class _DS:
+        def __init__(self, n): self.n = n
+        def __len__(self): return self.n
+
+    for n, B in ((37, 8), (64, 16), (5, 8)):
+        ref = DataLoader(TensorDataset(torch.arange(n)), batch_size=B, shuffle=True, generator=torch.Generator().manual_seed(42))
+        mine = DeviceWindowLoader(_DS(n), B, shuffle=True, generator=torch.Generator().manual_seed(42))
+        assert len(mine) == len(ref)
+        for epoch in range(4):
+            cap = 2 if epoch == 1 else None             # epoch 1 is abandoned after two batches in both
+            mine.max_batches = cap
+            want = []
+            for k, b in enumerate(ref):
+                if cap is not None and k >= cap:
+                    break
+                want.append(b[0].tolist())
+            got = [b.tolist() for b in mine.index_batches()]
+            assert got == want, (n, B, epoch)
+    seq = DeviceWindowLoader(_DS(21), 8, shuffle=False)
+    assert [b.tolist() for b in seq.index_batches()] == [list(range(0, 8)), list(range(8, 16)), list(range(16, 21))]
+    a = DeviceWindowLoader(_DS(37), 8, shuffle=True, generator=torch.Generator().manual_seed(42))
+    r0 = DeviceWindowLoader(_DS(37), 8, shuffle=True, generator=torch.Generator().manual_seed(42), rank=0, world_size=2)
+    r1 = DeviceWindowLoader(_DS(37), 8, shuffle=True, generator=torch.Generator().manual_seed(42), rank=1, world_size=2)
+    for g, x, y in zip(a.index_batches(), r0.index_batches(), r1.index_batches()):
+        assert torch.cat([x, y]).tolist() == g.tolist()
+
+
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
