@@ -304,7 +304,7 @@ def run_gpu(args):
             if i >= 3:
                 ts.append(a.elapsed_time(b))
         tf = 2.0 * M * 512 * IMAGE_DIM / (statistics.mean(ts) * 1e-3) / 1e12
-        gemm = {"kernel": "gemm_bf16_tcgen05_kernel<256> (K2: FE layer-1 forward, M=B*W, N=512, K=2048)", "bound": "tensor",
+        gemm = {"kernel": "gemm_bf16_tcgen05_kernel<256, row-major epilogue, CTA pair / cta_group::2> (K2: FE layer-1 forward, M=B*W, N=512, K=2048)", "bound": "tensor",
                 "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "ms_per_launch": statistics.mean(ts)}
 
     # ---- e2e: the public train_single_epoch over K steps; pinned-host index batches in, loss out EVERY step

@@ -20,6 +20,7 @@
 // 12 KB per instruction = 96 B/cycle of shared-memory bandwidth (below the 128 B/cycle port), which
 // is why BLOCK_N = 256 is the default tile for the wide layers.
 #include "tcgen05.cuh"
+#include <stdlib.h>
 
 namespace b200med {
 
@@ -45,11 +46,13 @@ struct GemmParams {
     void *D;                // output, or the fp32 partial workspace when split_k > 1
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kPair = false>
 struct GemmCfg {
-    static constexpr uint32_t kBTileBytes = BLOCK_N * BLOCK_K * 2;
+    // CTA pair: each CTA stages its own 128 rows of A and HALF of the B tile's rows
+    static constexpr int kBRows = kPair ? BLOCK_N / 2 : BLOCK_N;
+    static constexpr uint32_t kBTileBytes = kBRows * BLOCK_K * 2;
     static constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
-    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int kStages = kPair ? 6 : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8));
     static constexpr int kAccStages = 2;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two: BLOCK_N in {32,64,128,256}
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -59,11 +62,20 @@ struct GemmCfg {
 //   0 row-major output with bias / ReLU / ReLU-mask, 1 row-block-interleaved output with bias / ReLU, 2 split-K fp32 partial.
 constexpr int kEpiRowMajor = 0, kEpiRbi = 1, kEpiPartial = 2;
 
-template <int BLOCK_N, int EPI>
+// kPair: the kernel is launched as clusters of 2 CTAs; a pair owns a 256 x BLOCK_N output tile (cta_group::2 MMA, M = 256):
+// CTA r stages rows [128 r, 128 r + 128) of the A tile and rows [BLOCK_N/2 r, +BLOCK_N/2) of the B tile, so every byte of B
+// is fetched from L2 once per 256 output rows instead of once per 128 -- the 1-CTA kernel needs 96 B/cycle/SM of L2 -> SMEM
+// traffic at full MMA rate, the pair 64 B/cycle/SM.
+template <int BLOCK_N, int EPI, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N>;
+    using Cfg = GemmCfg<BLOCK_N, kPair>;
+    constexpr int kTileM = kPair ? 2 * BLOCK_M : BLOCK_M;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const long long cta_id = kPair ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+    const long long cta_stride = kPair ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
@@ -81,17 +93,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_b) : "memory");
-        for (int s = 0; s < Cfg::kStages; ++s) { bar_init(&full_bar[s], 1); bar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < Cfg::kAccStages; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], 8); }
+        // pair: the leader's full barrier collects its own arrive.expect_tx and the peer's arrive; its acc_empty barrier
+        // collects the 8 epilogue warps of both CTAs
+        for (int s = 0; s < Cfg::kStages; ++s) { bar_init(&full_bar[s], kPair ? 2 : 1); bar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < Cfg::kAccStages; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], kPair ? 16 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(s_addr(tmem_slot)), "r"(Cfg::kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(s_addr(tmem_slot)), "r"(Cfg::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(s_addr(tmem_slot)), "r"(Cfg::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();      // both CTAs' barriers are initialised before any remote arrive / TMA signal
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -100,31 +121,50 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (long long tile = cta_id; tile < total_tiles; tile += cta_stride) {
                 const int z = (int)(tile / tiles_mn);
                 const long long mn = tile % tiles_mn;
-                const int m0 = (int)(mn / p.tiles_n) * BLOCK_M, n0 = (int)(mn % p.tiles_n) * BLOCK_N;
+                const int m0 = (int)(mn / p.tiles_n) * kTileM + (int)rank * BLOCK_M;
+                const int n0 = (int)(mn % p.tiles_n) * BLOCK_N + (int)rank * (kPair ? Cfg::kBRows : 0);
                 const int kb0 = z * p.kb_per_split;
                 const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     bar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *sa = smem + (size_t)stage * Cfg::kStageBytes;
                     unsigned char *sb = sa + kATileBytes;
-                    bar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     const int k0 = kb * BLOCK_K;
-                    if (p.a_kmajor) {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);           // box {64 k, 128 m}
-                    } else {
+                    if constexpr (kPair) {
+                        const uint32_t lbar = mapa_rank(&full_bar[stage], 0);         // the leader's barrier for this stage
+                        if (leader) bar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        if (p.a_kmajor) {
+                            tma_load_2d_pair(sa, &tmap_a, lbar, k0, m0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BLOCK_M / 64; ++j)                          // boxes {64 m, 64 k}
-                            tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
-                    }
-                    if (p.b_kmajor) {
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);           // box {64 k, BLOCK_N n}
-                    } else {
+                            for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_2d_pair(sa + j * 8192, &tmap_a, lbar, m0 + 64 * j, k0);
+                        }
+                        if (p.b_kmajor) {
+                            tma_load_2d_pair(sb, &tmap_b, lbar, k0, n0);              // box {64 k, BLOCK_N / 2 n}
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++j)
-                            tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+                            for (int j = 0; j < Cfg::kBRows / 64; ++j) tma_load_2d_pair(sb + j * 8192, &tmap_b, lbar, n0 + 64 * j, k0);
+                        }
+                        if (!leader) bar_arrive_cluster(lbar);
+                    } else {
+                        bar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        if (p.a_kmajor) {
+                            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);           // box {64 k, 128 m}
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BLOCK_M / 64; ++j)                          // boxes {64 m, 64 k}
+                                tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+                        }
+                        if (p.b_kmajor) {
+                            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);           // box {64 k, BLOCK_N n}
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); ++j)
+                                tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+                        }
                     }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -132,8 +172,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, !p.a_kmajor, !p.b_kmajor);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc(kTileM, BLOCK_N, !p.a_kmajor, !p.b_kmajor);
             // K-major, SW128: 8-row groups are 1024 B apart (SBO); LBO unused (1).  One UMMA_K step = 32 B.
             // MN-major, SW128: 64-element MN atoms are 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
             // one UMMA_K step = 16 k-rows = 2048 B.
@@ -143,11 +183,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (long long tile = cta_id; tile < total_tiles; tile += cta_stride) {
                 const int z = (int)(tile / tiles_mn);
                 const int kb0 = z * p.kb_per_split;
                 const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-                bar_wait(&acc_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+                bar_wait(&acc_empty[acc], acc_phase ^ 1);  // epilogue (of both CTAs of a pair) has drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -159,12 +199,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
                         const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-                        umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if constexpr (kPair) umma_bf16_pair(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
+                    // frees the smem slot (in both CTAs of a pair) when these MMAs have read it
+                    if constexpr (kPair) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&acc_full[acc]);         // accumulator complete -> epilogue
+                // accumulator complete -> epilogue
+                if constexpr (kPair) umma_commit_pair(&acc_full[acc]); else umma_commit(&acc_full[acc]);
                 if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -179,10 +222,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const bool has_work = BLOCK_N >= 64 || half == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (long long tile = cta_id; tile < total_tiles; tile += cta_stride) {
             const int z = (int)(tile / tiles_mn);
             const long long mn = tile % tiles_mn;
-            const long long m0 = (mn / p.tiles_n) * BLOCK_M, n0 = (mn % p.tiles_n) * BLOCK_N;
+            const long long m0 = (mn / p.tiles_n) * kTileM + rank * BLOCK_M, n0 = (mn % p.tiles_n) * BLOCK_N;
             bar_wait(&acc_full[acc], acc_phase);
             tcgen05_fence_after();
             const long long m = m0 + quarter * 32 + lane;
@@ -301,16 +344,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // all of this warp's TMEM reads are complete (tcgen05.wait::ld above) -> release the accumulator
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) bar_arrive(&acc_empty[acc]);
+            if (lane == 0) {
+                if (kPair && !leader) bar_arrive_cluster(mapa_rank(&acc_empty[acc], 0));   // the MMA issuer lives in the leader
+                else bar_arrive(&acc_empty[acc]);
+            }
             if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();      // no CTA of the pair leaves while its partner may still signal it
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+        if constexpr (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
     }
 }
 
@@ -338,10 +388,10 @@ static int pick_block_n(long long N, int b_kmajor) {
     return 32;
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, bool kPair = false>
 static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &p, cudaStream_t st) {
-    using Cfg = GemmCfg<BLOCK_N>;
-    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI>;
+    using Cfg = GemmCfg<BLOCK_N, kPair>;
+    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes),
@@ -349,9 +399,29 @@ static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const Ge
         attr_set = true;
     }
     const long long tiles = (long long)p.tiles_m * p.tiles_n * p.split_k;
-    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
-    return after_launch("gemm_bf16_tcgen05_kernel");
+    if constexpr (kPair) {
+        const long long pairs = num_sms() / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs)));
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (const char *pol = getenv("B200MED_CLUSTER_POLICY")) {
+            attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
+            attr[1].val.clusterSchedulingPolicyPreference = (cudaClusterSchedulingPolicy)atoi(pol);
+            cfg.numAttrs = 2;
+        }
+        if (int e = check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, p), "cudaLaunchKernelEx(gemm_bf16_tcgen05 pair)")) return e;
+        return after_launch("gemm_bf16_tcgen05_kernel(pair)");
+    } else {
+        const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+        kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+        return after_launch("gemm_bf16_tcgen05_kernel");
+    }
 }
 
 }  // namespace b200med
@@ -395,17 +465,24 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
     split_k = (nkb + kb_per - 1) / kb_per;
     B200MED_REQUIRE(split_k == 1 || workspace, "split_k > 1 needs a workspace");
 
+    // CTA-pair mode (cta_group::2, 256 x 256 tiles): the wide GEMMs whose K loop is long enough to be bound by the
+    // L2 -> shared-memory operand traffic of the 1-CTA kernel (FE layer 1 forward 231 -> 210 us, weight gradient 260 -> 238 us,
+    // measured A/B on one box).  B200MED_GEMM_PAIR=0 switches it off.
+    static const bool pair_allowed = []() { const char *e = getenv("B200MED_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+    const bool pair = pair_allowed && block_n == 256 && M >= 256 && N % 256 == 0 && nkb / split_k >= 8;
+
     CUtensorMap ta, tb;
     // K-major operand: rows x K, K contiguous -> box {64 k, rows}.  MN-major: K x rows -> box {64 rows, 64 k}.
     if (int e = a_kmajor ? make_tmap(&ta, A, K, M, lda, BLOCK_K, BLOCK_M) : make_tmap(&ta, A, M, K, lda, 64, BLOCK_K)) return e;
-    if (int e = b_kmajor ? make_tmap(&tb, B, K, N, ldb, BLOCK_K, block_n) : make_tmap(&tb, B, N, K, ldb, 64, BLOCK_K)) return e;
+    if (int e = b_kmajor ? make_tmap(&tb, B, K, N, ldb, BLOCK_K, pair ? block_n / 2 : block_n)
+                         : make_tmap(&tb, B, N, K, ldb, 64, BLOCK_K)) return e;
 
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.ldd = ldd;
     p.a_kmajor = a_kmajor; p.b_kmajor = b_kmajor;
     p.out_f32 = out_dtype == B200MED_F32; p.relu = relu;
     p.split_k = split_k; p.kb_per_split = kb_per;
-    p.tiles_m = (int)((M + BLOCK_M - 1) / BLOCK_M);
+    p.tiles_m = pair ? (int)((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) : (int)((M + BLOCK_M - 1) / BLOCK_M);
     p.tiles_n = (int)((N + block_n - 1) / block_n);
     p.bias = split_k > 1 ? nullptr : bias;
     p.mask = split_k > 1 ? nullptr : reinterpret_cast<const __nv_bfloat16 *>(mask);
@@ -421,6 +498,11 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
             : epi == kEpiRbi   ? launch_gemm_tc<BN, kEpiRbi>(ta, tb, p, st)                     \
                                : launch_gemm_tc<BN, kEpiRowMajor>(ta, tb, p, st);               \
         break;
+    if (pair) {
+        e = epi == kEpiPartial ? launch_gemm_tc<256, kEpiPartial, true>(ta, tb, p, st)
+            : epi == kEpiRbi   ? launch_gemm_tc<256, kEpiRbi, true>(ta, tb, p, st)
+                               : launch_gemm_tc<256, kEpiRowMajor, true>(ta, tb, p, st);
+    } else
     switch (block_n) {
         B200MED_GEMM_CASE(256)
         B200MED_GEMM_CASE(128)

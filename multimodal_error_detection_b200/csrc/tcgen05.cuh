@@ -104,6 +104,60 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// ---- CTA pair (cta_group::2) primitives: two CTAs of a cluster run ONE MMA over M = 256 rows; each loads its own half
+// of both operands; the leader (cluster rank 0) issues the MMA, completion is multicast to both CTAs' mbarriers.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of THIS CTA) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(s_addr(p)), "r"(rank));
+    return r;
+}
+// Remote arrive with the default (.release.cta) semantics: `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR per arrive,
+// which serialised the pair pipeline (one per k-block, ~1 us each, measured).  What the arrivals of this file publish was
+// written by TMA / read by tcgen05.ld (async proxy, ordered by the mbarrier / tcgen05 fences), not by generic stores.
+__device__ __forceinline__ void bar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire (the arrival comes from the other CTA of the cluster)
+__device__ __forceinline__ void bar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
+        if (!done && spins > (1u << 22)) __trap();
+    }
+}
+// TMA load whose completion is signalled on an mbarrier of the PAIR's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(s_addr(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(s_addr(bar)), "h"((uint16_t)3) : "memory");
+}
+
 // TMA stores (shared -> global, bulk async-group completion) of 128B-swizzled tiles
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
