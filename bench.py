@@ -194,6 +194,7 @@ def run_gpu(args):
     device = torch.device("cuda", local_rank)
     B, K, Wm = args.batch, args.steps, max(3, args.warmup)
     kw = exp_kwargs(B, args.precision)
+    kw["prefetch_sms"] = args.prefetch_sms
     ds, n_frames = build_gpu_job(args, rank, device)
     n_windows = len(ds)
     fe, model, crit, opt, sched = mu.define_model_objects(kw, {"multimodal": 58, "video": 32, "kinematics": 26}, device,
@@ -207,7 +208,10 @@ def run_gpu(args):
     perm = perm.repeat((need + n_windows - 1) // n_windows)[:need].reshape(K + Wm, B)
     idx_all = perm.to(device).contiguous()                                # [K+Wm, B] int64 window indices, resident in HBM
     starts_all = ds._starts[idx_all].contiguous()
-    stepper = WindowTrainStep(ds, fe, model, crit, opt, kw, B, gather_variant=args.gather_variant)
+    # prefetch: K1 of step k+1 is issued inside step k (side stream, under the LSTM recurrence); every step still gathers
+    # exactly one batch.  The K1 roofline below is timed with the gather at the START of the step (prefetch off).
+    prefetch = bool(args.prefetch and args.precision == "bf16")
+    stepper = WindowTrainStep(ds, fe, model, crit, opt, kw, B, gather_variant=args.gather_variant, prefetch=prefetch)
     graph_note = "eager"
     if args.graph:
         try:
@@ -215,13 +219,23 @@ def run_gpu(args):
             stepper.capture()
             graph_note = "cuda_graph"
         except Exception as e:  # capture is an optimisation, never a correctness dependency
-            stepper.graph = None
+            stepper.graphs = [None, None]
             graph_note = f"eager (graph capture failed: {type(e).__name__})"
     from multimodal_error_detection_b200.modeling import modeling_utils as _mu
     _mu._set_train(model, fe, kw, True)
+
+    def step(i):
+        """One train step on batch i of idx_all (prefetch mode: batch i+1 is gathered inside it)."""
+        if stepper.prefetch:
+            if not stepper._primed:
+                stepper.load(idx_all[i])
+            stepper.run(idx_all[i + 1] if i + 1 < idx_all.shape[0] else None)
+        else:
+            stepper.load(idx_all[i])
+            stepper.run()
+
     for i in range(Wm):
-        stepper.load(idx_all[i])
-        stepper.run()
+        step(i)
     torch.cuda.synchronize()
     parallel.barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -233,10 +247,9 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ev[0].record()
     for i in range(K):
-        stepper.load(idx_all[Wm + i])
-        if stepper.graph is None:
+        if stepper.graph is None and not stepper.prefetch:
             stepper.gather_events = gather_ev[i]
-        stepper.run()
+        step(Wm + i)
     ev[1].record()
     torch.cuda.synchronize()
     parallel.barrier()
@@ -250,21 +263,23 @@ def run_gpu(args):
     # ---- roofline of the dominant HBM kernel (K1), timed with CUDA events on the launch stream
     out_es = 2 if args.precision == "bf16" else 4
     k1_bytes = B * W * (IMAGE_DIM * (4 + out_es) + KIN_DIM * 8)
-    if stepper.graph is None:
+    if stepper.graph is None and not stepper.prefetch:
         k1_ms = statistics.mean(a.elapsed_time(b) for a, b in gather_ev)
         k1_how = "CUDA events around the K1 launch inside each of the K timed steps"
     else:
-        # the timed steps were graph replays (no events inside); time K1 inside the same step launched eagerly
-        g, stepper.graph = stepper.graph, None
+        # the timed steps were graph replays (no events inside) and / or had K1 of the next step running on a side stream
+        # under the LSTM kernels; time K1 inside the same train step launched eagerly with the gather at its start
+        g, pf, stepper.graphs, stepper.prefetch = stepper.graphs, stepper.prefetch, [None, None], False
         n_ev = min(K, 8)
         for i in range(n_ev):
             stepper.load(idx_all[Wm + i])
             stepper.gather_events = gather_ev[i]
             stepper.run()
         torch.cuda.synchronize()
-        stepper.graph, stepper.gather_events = g, None
+        stepper.graphs, stepper.prefetch, stepper.gather_events, stepper._primed = g, pf, None, False
         k1_ms = statistics.mean(a.elapsed_time(b) for a, b in gather_ev[:n_ev])
-        k1_how = "CUDA events around the K1 launch inside the same train step launched eagerly (the timed steps are graph replays)"
+        k1_how = ("CUDA events around the K1 launch inside the same train step launched eagerly with the gather at the start "
+                  "of the step (the timed steps are graph replays" + (" with K1 of step k+1 prefetched under step k's LSTM kernels)" if pf else ")"))
     iso = []
     for i in range(min(K, 10) + 3):      # isolated launches; every launch touches a fresh 1.1 GB slice (> L2)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -310,7 +325,7 @@ def run_gpu(args):
     # ---- e2e: the public train_single_epoch over K steps; pinned-host index batches in, loss out EVERY step
     e2e = None
     if not args.no_e2e:
-        kw_e2e = dict(kw, host_sync="step")
+        kw_e2e = dict(kw, host_sync="step", prefetch_gather=prefetch)
         loader = DeviceWindowLoader(ds, B, shuffle=True, generator=torch.Generator().manual_seed(42), rank=0, world_size=1)
         full = max(1, n_windows // B)                            # full batches per pass: every timed step is a B-window graph replay
         loader.max_batches = min(Wm, full)                       # untimed warm-up pass (also captures the step's CUDA graph)
@@ -349,6 +364,7 @@ def run_gpu(args):
                 "config": {"workload": workload_name(B, args.videos), "global_batch": world * B, "window": W, "stride": S,
                            "frames_per_gpu": n_frames, "windows_per_gpu": n_windows, "params": n_params,
                            "parallelism": f"dp{world}", "launch": graph_note, "lstm_impl": args.lstm_impl,
+                           "gather_prefetch": bool(prefetch),
                            "l2": "every step gathers a fresh ~1.1 GB slice of a >2 GB table (inputs larger than the 126 MB L2)",
                            "gather_variant": args.gather_variant},
                 "roofline": roofline, "roofline_gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
@@ -357,7 +373,7 @@ def run_gpu(args):
     if world > 1:
         # graphs that captured NCCL work must be gone before the communicator is torn down; a wedged teardown must not
         # turn a finished run into a hang, so the process leaves through os._exit after a final barrier
-        stepper.graph = None
+        stepper.graphs = [None, None]
         opt._b200_stepper = None
         import gc
         gc.collect()
@@ -380,6 +396,9 @@ def main():
     ap.add_argument("--lstm-impl", default="b200", choices=["b200", "b200_per_step", "cudnn"])
     ap.add_argument("--gather-variant", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--prefetch-sms", type=int, default=56, help="SMs the prefetching gather may occupy (side stream)")
+    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
+                    help="gather each step's batch at the start of the step instead of inside the previous step")
     ap.add_argument("--cpu-windows", type=int, default=4096)
     args = ap.parse_args()
     global LSTM_IMPL

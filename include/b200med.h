@@ -105,7 +105,8 @@ typedef struct b200med_stream_desc {
  * per-sample standardisation in CustomWindowDataset.__getitem__ (CustomWindowDataset.py:53-60),
  * default_collate, and the H2D copy in define_inputs (modeling_utils.py:40,42).
  *   streams_host: HOST array of n_streams descriptors (pointers inside are device pointers).
- *   variant: 0 = auto, 1 = LDG path, 2 = TMA bulk-copy staging path.                             */
+ *   variant: bits 0..7: 0 = auto, 1 = LDG path, 2.. = TMA bulk-copy staging ring shapes; bits 8..23: optional cap on
+ *   the number of SMs the launch occupies (0 = all) for a gather that shares the GPU with other kernels.       */
 int b200med_gather_norm(const b200med_stream_desc *streams_host, int32_t n_streams,
                         const int32_t *starts, int64_t B, int32_t W, int32_t variant, void *stream);
 

@@ -329,6 +329,11 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const 
     B200MED_REQUIRE(B >= 0 && W >= 1, "need B >= 0 and W >= 1");
     if (B == 0) return B200MED_OK;
     B200MED_REQUIRE(starts, "null starts");
+    // bits 8..23 of `variant`: optional cap on the number of SMs the launch may occupy (0 = all).  A gather that is issued
+    // on a side stream next to other kernels leaves them the rest of the GPU (one CTA per SM, 192 KB of shared memory).
+    const int sm_cap = (variant >> 8) & 0xFFFF;
+    variant &= 0xFF;
+    const int sms = sm_cap > 0 && sm_cap < num_sms() ? sm_cap : num_sms();
     GatherParams p{};
     p.n_streams = n_streams;
     p.W = W;
@@ -387,7 +392,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const 
         B200MED_REQUIRE(smem <= 200 * 1024, "row too wide for the TMA staging ring");
         const long long n_units = (long long)B * pt.s[0].chunks;
         const int per_sm = (int)((220 * 1024) / (smem + 1024));
-        const long long cap_t = (long long)(per_sm < 1 ? 1 : per_sm) * num_sms();
+        const long long cap_t = (long long)(per_sm < 1 ? 1 : per_sm) * sms;
         const int grid = (int)(n_units < cap_t ? n_units : cap_t);
         auto launch = [&](auto kern, int threads) -> int {
             if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -447,7 +452,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const 
         if (k < B200MED_MAX_STREAMS) q.s[k].unit_begin = u;  // sentinel: s[1].unit_begin must exist
         q.total_units = u;
     }
-    const long long max_grid = (long long)num_sms() * 8;  // up to 8 CTAs of 256 threads per SM
+    const long long max_grid = (long long)sms * 8;  // up to 8 CTAs of 256 threads per SM
     const int grid = (int)(q.total_units < max_grid ? q.total_units : max_grid);
     if (wide_idx < 0) {
         gather_norm_kernel<float, true, false><<<grid, kThreads, 0, st>>>(q);

@@ -6,6 +6,12 @@ kernels; launched one by one from Python the host, not the GPU, sets the pace).
 
 The only per-step input is the batch's WINDOW INDICES (8 bytes per window, copied from pinned host
 memory or staged on the device); frames never leave HBM.
+
+Software pipelining of K1 (``prefetch=True``): the batch buffers are double-buffered and the gather of step k+1 is
+issued on a side stream right after the FeatureExtractor forward of step k, so it runs under the LSTM recurrence of
+step k (whose kernels hold a CTA on 64 of the 148 SMs only).  Protocol: ``prime(idx_0)`` once, then
+``run(next_idx=idx_{k+1})`` per step; every step still performs exactly one gather.  With ``prefetch=False`` the gather
+of step k runs at the start of step k on the main stream (this is also how bench.py times K1 for the roofline).
 """
 from __future__ import annotations
 
@@ -18,17 +24,21 @@ from .modeling import modeling_utils as mu
 
 class WindowTrainStep:
     def __init__(self, dataset: CustomWindowDataset, feature_extractor, model, criterion, optimizer, exp_kwargs: dict,
-                 batch_size: int, gather_variant: int = 0):
+                 batch_size: int, gather_variant: int = 0, prefetch: bool = False):
         self.ds, self.fe, self.model, self.crit, self.opt, self.kw = dataset, feature_extractor, model, criterion, optimizer, exp_kwargs
         self.B, self.W = batch_size, dataset.W
         dev = dataset._starts.device
         self.device = dev
         self.image_dtype = mu._image_dtype(feature_extractor)
-        self.idx = torch.zeros(batch_size, dtype=torch.int64, device=dev)          # the step's only input
+        self.prefetch = prefetch
+        self.prefetch_sms = int(exp_kwargs.get("prefetch_sms", 56))     # SMs the prefetching gather may occupy
+        self.parity = 0                # which of the two batch buffers holds the CURRENT step's batch
+        self._primed = False           # prefetch mode: buffer[parity] already holds the gathered batch
+        self.idx2 = [torch.zeros(batch_size, dtype=torch.int64, device=dev) for _ in range(2)]     # the step's only input
         self.label_col = mu.define_error_labels(dataset.e_labels_data, exp_kwargs).float().contiguous()
         D_img, D_kin = dataset._image_table.shape[1], dataset._kin_table.shape[1]
-        self.images = torch.empty(batch_size, self.W, D_img, dtype=self.image_dtype, device=dev)
-        self.kin = torch.empty(batch_size, self.W, D_kin, dtype=torch.float32, device=dev)
+        self.images2 = [torch.empty(batch_size, self.W, D_img, dtype=self.image_dtype, device=dev) for _ in range(2)]
+        self.kin2 = [torch.empty(batch_size, self.W, D_kin, dtype=torch.float32, device=dev) for _ in range(2)]
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.counts = torch.zeros(4, dtype=torch.int64, device=dev)
         self.probs = torch.zeros(batch_size, dtype=torch.float32, device=dev)
@@ -36,24 +46,60 @@ class WindowTrainStep:
         self.labels = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.gather_variant = gather_variant
         self.gather_events = None      # optional (start, end) CUDA events around K1 (eager mode only)
-        self.graph = None
+        self.graphs = [None, None]     # one captured step per buffer parity
         self.launches_per_step = None
+        self._side = torch.cuda.Stream(device=dev)
         optimizer.prepare()
 
-    def load(self, idx: torch.Tensor):
-        """Stage one batch of window indices (pinned host -> device, or device -> device)."""
-        self.idx.copy_(idx, non_blocking=True)
+    # the current batch buffers (what the last / next run() trains on)
+    @property
+    def idx(self):
+        return self.idx2[self.parity]
 
-    def _body(self):
-        starts = self.ds._starts.index_select(0, self.idx)
-        labels = self.label_col.index_select(0, self.idx)
+    @property
+    def images(self):
+        return self.images2[self.parity]
+
+    @property
+    def kin(self):
+        return self.kin2[self.parity]
+
+    @property
+    def graph(self):
+        """Truthy when the step is replayed from captured graphs."""
+        return self.graphs[0]
+
+    def _gather(self, which: int, sm_cap: int = 0):
+        starts = self.ds._starts.index_select(0, self.idx2[which])
         if self.gather_events is not None:
             self.gather_events[0].record()
-        self.ds.gather_batch(None, image_out=self.images, kin_out=self.kin, starts=starts,
-                             exact=self.image_dtype == torch.float32, variant=self.gather_variant)
+        self.ds.gather_batch(None, image_out=self.images2[which], kin_out=self.kin2[which], starts=starts,
+                             exact=self.image_dtype == torch.float32, variant=self.gather_variant | (sm_cap << 8))
         if self.gather_events is not None:
             self.gather_events[1].record()
-        inputs = mu.define_inputs(self.images, self.kin, self.fe, self.kw, self.device)
+
+    def load(self, idx: torch.Tensor):
+        """Stage the CURRENT step's window indices (pinned host -> device, or device -> device).  In prefetch mode this
+        also gathers the batch right away (start of a sequence; same as :meth:`prime`)."""
+        self.idx2[self.parity].copy_(idx, non_blocking=True)
+        if self.prefetch:
+            self._gather(self.parity)
+            self._primed = True
+
+    prime = load
+
+    def _body(self, cur: int):
+        nxt = 1 - cur
+        labels = self.label_col.index_select(0, self.idx2[cur])
+        if not self.prefetch:
+            self._gather(cur)
+        inputs = mu.define_inputs(self.images2[cur], self.kin2[cur], self.fe, self.kw, self.device)
+        if self.prefetch:
+            # K1 of the NEXT step: forked here so that it runs under the LSTM recurrence of this step
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._gather(nxt, self.prefetch_sms)      # leaves the other SMs to the main stream's kernels
         outputs = self.model(inputs)
         loss, _ = mu.compute_loss(outputs, labels, self.crit, "window")
         self.opt.zero_grad()
@@ -66,32 +112,39 @@ class WindowTrainStep:
         self.probs.copy_(probs)
         self.preds.copy_(preds)
         self.labels.copy_(labels)
+        if self.prefetch:
+            torch.cuda.current_stream().wait_stream(self._side)
 
     def capture(self, warmup: int = 3):
-        """Run `warmup` real steps on a side stream (the current contents of ``idx`` are used), then record the
-        step into a CUDA graph."""
+        """Run `warmup` real steps on a side stream (the current contents of the index buffers are used), then record
+        the step into one CUDA graph per buffer parity."""
         mu._set_train(self.model, self.fe, self.kw, True)
         # the warm-up steps are real optimiser steps: snapshot every piece of training state and put it back
-        # afterwards, so that capturing the graph leaves the training trajectory untouched
+        # afterwards, so that capturing the graphs leaves the training trajectory untouched
         self.opt._refresh_active()
         mods = [m for m in (self.fe, self.model) if m is not None]
         snap = [t.clone() for c in self.opt.chunks for t in (c.param, c.exp_avg, c.exp_avg_sq)] + [self.opt.state_dev.clone()]
         bufs = [b for m in mods for b in m.buffers()]
         snap_bufs = [b.clone() for b in bufs]
-        first_step = self.opt._active is None or not any(self.opt._active.values())
+        keep = [t.clone() for t in (*self.idx2, *self.images2, *self.kin2)]
+        self.idx2[1 - self.parity].copy_(self.idx2[self.parity])          # valid indices for the prefetch of the warm-up steps
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._body()
+            for k in range(warmup):
+                self._body((self.parity + k) & 1 if self.prefetch else self.parity)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self._body()
-        self.launches_per_step = _lib.launch_count() - n0     # b200med kernels recorded in (and replayed by) the graph
-        self.graph = graph
+        graphs = [None, None]
+        pars = (0, 1) if self.prefetch else (self.parity,)
+        for par in pars:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body(par)
+            graphs[par] = g
+        self.launches_per_step = (_lib.launch_count() - n0) // len(pars)   # b200med kernels recorded in (and replayed by) a graph
+        self.graphs = graphs
         with torch.no_grad():
             it = iter(snap)
             for c in self.opt.chunks:
@@ -100,13 +153,25 @@ class WindowTrainStep:
             self.opt.state_dev.copy_(next(it))
             for b, sb in zip(bufs, snap_bufs):
                 b.copy_(sb)
+            for t, k in zip((*self.idx2, *self.images2, *self.kin2), keep):
+                t.copy_(k)
         self.opt._lr_on_device = None      # the device-side lr was part of the restored state: push it again on the next run
         return self
 
-    def run(self):
+    def run(self, next_idx: torch.Tensor = None):
+        """One train step on the current batch.  Prefetch mode: ``next_idx`` = the window indices of the NEXT step (its
+        gather runs inside this step); without it the next step has to :meth:`load` its batch itself."""
+        if self.prefetch and not self._primed:
+            raise RuntimeError("WindowTrainStep(prefetch=True): call load()/prime() with the first batch of a sequence")
+        cur = self.parity
+        if self.prefetch and next_idx is not None:
+            self.idx2[1 - cur].copy_(next_idx, non_blocking=True)
         self.opt.sync_lr()             # lr lives in a device scalar; refresh it outside the graph when the scheduler moved it
-        if self.graph is not None:
-            self.graph.replay()
+        if self.graphs[cur] is not None:
+            self.graphs[cur].replay()
         else:
-            self._body()
+            self._body(cur)
+        if self.prefetch:
+            self.parity = 1 - cur
+            self._primed = next_idx is not None
         return self.loss

@@ -444,7 +444,8 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
     key = (id(ds), id(model), id(feature_extractor), id(criterion), B)
     stepper = getattr(optimizer, "_b200_stepper", None)
     if stepper is None or stepper.key != key:
-        stepper = WindowTrainStep(ds, feature_extractor, model, criterion, optimizer, exp_kwargs, B)
+        stepper = WindowTrainStep(ds, feature_extractor, model, criterion, optimizer, exp_kwargs, B,
+                                  prefetch=bool(exp_kwargs.get("prefetch_gather", _image_dtype(feature_extractor) == torch.bfloat16)))
         stepper.key = key
         optimizer._b200_stepper = stepper
     log = _EpochLog()
@@ -455,19 +456,30 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
     # overlaps the execution of step k instead of draining the GPU queue.
     step_sync = exp_kwargs.get("host_sync") == "step"
     ring = _HostLossRing(device) if step_sync else None
-    for idx in loader.index_batches():
+    def _with_lookahead(it):
+        """(batch, next batch or None) pairs."""
+        prev = None
+        for cur in it:
+            if prev is not None:
+                yield prev, cur
+            prev = cur
+        if prev is not None:
+            yield prev, None
+
+    for idx, idx_next in _with_lookahead(i for i in loader.index_batches() if i.numel() > 0):
         n = idx.numel()
-        if n == 0:
-            continue
         if n == B:
-            stepper.load(idx.pin_memory())
+            if not (stepper.prefetch and stepper._primed):
+                stepper.load(idx.pin_memory())           # start of a sequence (or no prefetch): stage (and gather) this batch
             if stepper.graph is None and not getattr(stepper, "graph_failed", False):
                 try:
                     stepper.capture()
                 except Exception as e:      # capture is an optimisation: fall back to eager launches, loudly
-                    stepper.graph, stepper.graph_failed = None, True
+                    stepper.graphs, stepper.graph_failed = [None, None], True
                     print(f"b200med: CUDA graph capture failed ({type(e).__name__}: {e}); running the step eagerly")
-            stepper.run()
+            # prefetch mode: the NEXT full batch is gathered inside this step (under the LSTM recurrence)
+            nxt = idx_next.pin_memory() if (stepper.prefetch and idx_next is not None and idx_next.numel() == B) else None
+            stepper.run(nxt)
             loss, counts = stepper.loss.clone(), stepper.counts.clone()
             extra = dict(preds=stepper.preds.clone(), labels=stepper.labels.clone(), probs=stepper.probs.clone()) if want_preds else {}
         else:
