@@ -46,21 +46,26 @@ struct GemmParams {
     void *D;                // output, or the fp32 partial workspace when split_k > 1
 };
 
-template <int BLOCK_N, bool kPair = false>
+// kStage: the epilogue stages the bf16 output tile in shared memory (and fetches the ReLU-mask tile into the same buffer)
+template <int BLOCK_N, bool kPair = false, bool kStage = false>
 struct GemmCfg {
     // CTA pair: each CTA stages its own 128 rows of A and HALF of the B tile's rows
     static constexpr int kBRows = kPair ? BLOCK_N / 2 : BLOCK_N;
     static constexpr uint32_t kBTileBytes = kBRows * BLOCK_K * 2;
     static constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
-    static constexpr int kStages = kPair ? 6 : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8));
+    static constexpr uint32_t kStagingBytes = kStage ? BLOCK_M * BLOCK_N * 2 : 0;     // 64-column boxes of [128 rows][128 B]
+    static constexpr int kStages = kStage ? (kPair ? 5 : ((BLOCK_N >= 256) ? 3 : 5))
+                                          : (kPair ? 6 : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)));
     static constexpr int kAccStages = 2;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two: BLOCK_N in {32,64,128,256}
-    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // EPI selects the epilogue at compile time (smaller code, no mode branches in the drain loop):
 //   0 row-major output with bias / ReLU / ReLU-mask, 1 row-block-interleaved output with bias / ReLU, 2 split-K fp32 partial.
-constexpr int kEpiRowMajor = 0, kEpiRbi = 1, kEpiPartial = 2;
+//   3 row-major bf16 output staged in shared memory and written by TMA store (bias / ReLU; the ReLU-mask tile is TMA-loaded
+//     into the same staging buffer): a warp's 16-byte accesses hit 8 conflict-free shared-memory slots instead of 32 lines.
+constexpr int kEpiRowMajor = 0, kEpiRbi = 1, kEpiPartial = 2, kEpiTmaBf16 = 3;
 
 // kPair: the kernel is launched as clusters of 2 CTAs; a pair owns a 256 x BLOCK_N output tile (cta_group::2 MMA, M = 256):
 // CTA r stages rows [128 r, 128 r + 128) of the A tile and rows [BLOCK_N/2 r, +BLOCK_N/2) of the B tile, so every byte of B
@@ -69,8 +74,9 @@ constexpr int kEpiRowMajor = 0, kEpiRbi = 1, kEpiPartial = 2;
 template <int BLOCK_N, int EPI, bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_mask,
                          const GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N, kPair>;
+    using Cfg = GemmCfg<BLOCK_N, kPair, EPI == kEpiTmaBf16>;
     constexpr int kTileM = kPair ? 2 * BLOCK_M : BLOCK_M;
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
@@ -79,11 +85,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+    unsigned char *staging = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;      // 1024-byte aligned (stages are multiples of 1 KB)
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(staging + Cfg::kStagingBytes);
     uint64_t *empty_bar = full_bar + Cfg::kStages;
     uint64_t *acc_full = empty_bar + Cfg::kStages;
     uint64_t *acc_empty = acc_full + Cfg::kAccStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + Cfg::kAccStages);
+    uint64_t *mask_bar = acc_empty + Cfg::kAccStages;        // TMA-store epilogue: "the mask tile is in the staging buffer"
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mask_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb_total = (int)((p.K + BLOCK_K - 1) / BLOCK_K);
@@ -97,6 +105,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // collects the 8 epilogue warps of both CTAs
         for (int s = 0; s < Cfg::kStages; ++s) { bar_init(&full_bar[s], kPair ? 2 : 1); bar_init(&empty_bar[s], 1); }
         for (int s = 0; s < Cfg::kAccStages; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], kPair ? 16 : 8); }
+        bar_init(mask_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -222,12 +231,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const bool has_work = BLOCK_N >= 64 || half == 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        constexpr bool staged = EPI == kEpiTmaBf16;
+        constexpr int kBoxes = BLOCK_N / 64;                      // TMA boxes of 64 columns x 128 rows per tile
+        const bool elect = warp == 2 && lane == 0;                // issues the TMA stores / mask loads of this CTA
+        const bool use_mask = staged && p.mask != nullptr;
+        uint32_t mask_phase = 0;
+        auto load_mask_tile = [&](long long t) {
+            const long long mn_ = t % tiles_mn;
+            const int m_ = (int)(mn_ / p.tiles_n) * kTileM + (int)rank * BLOCK_M, n_ = (int)(mn_ % p.tiles_n) * BLOCK_N;
+            bar_expect_tx(mask_bar, Cfg::kStagingBytes);
+#pragma unroll
+            for (int bx = 0; bx < kBoxes; ++bx) tma_load_2d(staging + bx * 16384, &tmap_mask, mask_bar, n_ + 64 * bx, m_);
+        };
+        if (use_mask && elect && cta_id < total_tiles) load_mask_tile(cta_id);
         for (long long tile = cta_id; tile < total_tiles; tile += cta_stride) {
             const int z = (int)(tile / tiles_mn);
             const long long mn = tile % tiles_mn;
             const long long m0 = (mn / p.tiles_n) * kTileM + rank * BLOCK_M, n0 = (mn % p.tiles_n) * BLOCK_N;
             bar_wait(&acc_full[acc], acc_phase);
             tcgen05_fence_after();
+            if constexpr (staged) {
+                if (use_mask) {
+                    bar_wait(mask_bar, mask_phase);               // the mask tile has landed (and the previous store has been read)
+                    mask_phase ^= 1;
+                } else {
+                    if (elect) bulk_wait_read<0>();               // the previous tile's TMA store has finished reading the buffer
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            }
             const long long m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
             constexpr bool partial = EPI == kEpiPartial;
@@ -267,6 +298,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
                         }
+                        if constexpr (staged) {
+                            // this lane's 64 bytes of the tile row: four 16-byte slots of box c0/64, 128B swizzle
+                            unsigned char *srow = staging + (c0 >> 6) * 16384 + (quarter * 32 + lane) * 128;
+                            const int slot0 = (c0 & 63) >> 3, sw = (quarter * 32 + lane) & 7;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 *sp = reinterpret_cast<uint4 *>(srow + (((slot0 + q) ^ sw) << 4));
+                                if (use_mask) {
+                                    const uint4 u = *sp;
+                                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                    for (int h = 0; h < 4; ++h) {
+                                        const uint32_t lo = w[h] & 0xFFFFu, hi = w[h] >> 16;
+                                        if (!((lo & 0x8000u) == 0 && (lo & 0x7FFFu) != 0)) f[q * 8 + h * 2] = 0.0f;
+                                        if (!((hi & 0x8000u) == 0 && (hi & 0x7FFFu) != 0)) f[q * 8 + h * 2 + 1] = 0.0f;
+                                    }
+                                }
+                                *sp = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
+                                                 pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+                            }
+                        }
                         if (EPI == kEpiRowMajor && p.mask) {
                             const __nv_bfloat16 *mk = p.mask + m * p.ldd + n_base;
                             if (full && (((uintptr_t)mk) % 16 == 0)) {
@@ -289,7 +341,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                             }
                         }
                     }
-                    if (EPI == kEpiRbi) {
+                    if constexpr (staged) {
+                        // output already sits in the staging tile
+                    } else if (EPI == kEpiRbi) {
                         // one 16-byte vector per lane and column group: a warp writes 512 contiguous bytes
                         const long long rb = m >> 5;
                         const int rl = (int)(m & 31);
@@ -349,6 +403,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 else bar_arrive(&acc_empty[acc]);
             }
             if (++acc == Cfg::kAccStages) { acc = 0; acc_phase ^= 1; }
+            if constexpr (staged) {
+                fence_proxy_async_smem();                         // staged tile (generic stores) -> visible to the TMA store
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (elect) {
+#pragma unroll
+                    for (int bx = 0; bx < kBoxes; ++bx)
+                        if (n0 + 64 * bx < p.N) tma_store_2d(&tmap_d, staging + bx * 16384, (int)n0 + 64 * bx, (int)m0);
+                    bulk_commit();
+                    if (use_mask && tile + cta_stride < total_tiles) {
+                        bulk_wait_read<0>();                      // the store has read the buffer: the next mask tile may land
+                        load_mask_tile(tile + cta_stride);
+                    }
+                }
+            }
+        }
+        if constexpr (staged) {
+            if (elect) bulk_wait_all();
         }
     }
 
@@ -389,8 +460,9 @@ static int pick_block_n(long long N, int b_kmajor) {
 }
 
 template <int BLOCK_N, int EPI, bool kPair = false>
-static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const GemmParams &p, cudaStream_t st) {
-    using Cfg = GemmCfg<BLOCK_N, kPair>;
+static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &td, const CUtensorMap &tm,
+                          const GemmParams &p, cudaStream_t st) {
+    using Cfg = GemmCfg<BLOCK_N, kPair, EPI == kEpiTmaBf16>;
     auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI, kPair>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -415,11 +487,11 @@ static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const Ge
             attr[1].val.clusterSchedulingPolicyPreference = (cudaClusterSchedulingPolicy)atoi(pol);
             cfg.numAttrs = 2;
         }
-        if (int e = check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, p), "cudaLaunchKernelEx(gemm_bf16_tcgen05 pair)")) return e;
+        if (int e = check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tm, p), "cudaLaunchKernelEx(gemm_bf16_tcgen05 pair)")) return e;
         return after_launch("gemm_bf16_tcgen05_kernel(pair)");
     } else {
         const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-        kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+        kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, td, tm, p);
         return after_launch("gemm_bf16_tcgen05_kernel");
     }
 }
@@ -491,29 +563,32 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
     p.out_f16 = out_dtype == B200MED_F16;
 
     int e;
-    const int epi = split_k > 1 ? kEpiPartial : (p.out_rbi ? kEpiRbi : kEpiRowMajor);
-#define B200MED_GEMM_CASE(BN)                                                                   \
-    case BN:                                                                                    \
-        e = epi == kEpiPartial ? launch_gemm_tc<BN, kEpiPartial>(ta, tb, p, st)                 \
-            : epi == kEpiRbi   ? launch_gemm_tc<BN, kEpiRbi>(ta, tb, p, st)                     \
-                               : launch_gemm_tc<BN, kEpiRowMajor>(ta, tb, p, st);               \
-        break;
-    if (pair) {
-        e = epi == kEpiPartial ? launch_gemm_tc<256, kEpiPartial, true>(ta, tb, p, st)
-            : epi == kEpiRbi   ? launch_gemm_tc<256, kEpiRbi, true>(ta, tb, p, st)
-                               : launch_gemm_tc<256, kEpiRowMajor, true>(ta, tb, p, st);
-    } else
-    switch (block_n) {
-        B200MED_GEMM_CASE(256)
-        B200MED_GEMM_CASE(128)
-        B200MED_GEMM_CASE(64)
-        default:
-            e = epi == kEpiPartial ? launch_gemm_tc<32, kEpiPartial>(ta, tb, p, st)
-                : epi == kEpiRbi   ? launch_gemm_tc<32, kEpiRbi>(ta, tb, p, st)
-                                   : launch_gemm_tc<32, kEpiRowMajor>(ta, tb, p, st);
-            break;
+    // staged TMA-store epilogue: bf16 row-major output (and mask) whose rows TMA can address
+    static const bool stage_allowed = []() { const char *v = getenv("B200MED_GEMM_TMA_EPILOGUE"); return !(v && v[0] == '0'); }();
+    const bool staged = stage_allowed && split_k == 1 && !p.out_rbi && out_dtype == B200MED_BF16 && block_n >= 128 &&
+                        ldd % 8 == 0 && (uintptr_t)D % 16 == 0 && (!mask || (uintptr_t)mask % 16 == 0);
+    const int epi = split_k > 1 ? kEpiPartial : (p.out_rbi ? kEpiRbi : (staged ? kEpiTmaBf16 : kEpiRowMajor));
+    CUtensorMap td = ta, tm = ta;
+    if (staged) {
+        if (int e2 = make_tmap(&td, D, N, M, ldd, 64, BLOCK_M)) return e2;               // box {64 columns, 128 rows}
+        if (mask) if (int e2 = make_tmap(&tm, mask, N, M, ldd, 64, BLOCK_M)) return e2;
     }
-#undef B200MED_GEMM_CASE
+#define B200MED_GEMM_EPI(BN, PAIR)                                                                                  \
+    (epi == kEpiPartial ? launch_gemm_tc<BN, kEpiPartial, PAIR>(ta, tb, td, tm, p, st)                                  \
+     : epi == kEpiRbi   ? launch_gemm_tc<BN, kEpiRbi, PAIR>(ta, tb, td, tm, p, st)                                      \
+                        : launch_gemm_tc<BN, kEpiRowMajor, PAIR>(ta, tb, td, tm, p, st))
+    if (pair) {
+        e = epi == kEpiTmaBf16 ? launch_gemm_tc<256, kEpiTmaBf16, true>(ta, tb, td, tm, p, st) : B200MED_GEMM_EPI(256, true);
+    } else if (block_n == 256) {
+        e = epi == kEpiTmaBf16 ? launch_gemm_tc<256, kEpiTmaBf16, false>(ta, tb, td, tm, p, st) : B200MED_GEMM_EPI(256, false);
+    } else if (block_n == 128) {
+        e = epi == kEpiTmaBf16 ? launch_gemm_tc<128, kEpiTmaBf16, false>(ta, tb, td, tm, p, st) : B200MED_GEMM_EPI(128, false);
+    } else if (block_n == 64) {
+        e = B200MED_GEMM_EPI(64, false);
+    } else {
+        e = B200MED_GEMM_EPI(32, false);
+    }
+#undef B200MED_GEMM_EPI
     if (e) return e;
     if (split_k > 1) {
         const long long total = M * N;

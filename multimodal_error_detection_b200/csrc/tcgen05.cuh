@@ -159,6 +159,10 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
 }
 
 // TMA stores (shared -> global, bulk async-group completion) of 128B-swizzled tiles
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"(s_addr(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                  :: "l"(map), "r"(s_addr(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
