@@ -480,3 +480,31 @@ def test_graph_epoch_matches_eager_epoch(fold_on_disk):
         assert a[7] == b[7] and a[8] == b[8] and a[9] == b[9]
         # torch's conv / BN backward kernels use atomics: two runs of the SAME loop differ by ~2e-5 in the second epoch's probabilities
         assert np.abs(np.asarray(a[6]) - np.asarray(b[6])).max() < 1e-4
+
+
+def test_bf16_lstm_graph_prefetch_epoch_matches_eager(fold_on_disk):
+    """The production configuration -- bf16, LSTM head on the persistent recurrence kernels, one CUDA graph per buffer
+    parity, K1 of batch k+1 prefetched on a side stream inside step k -- against the plain eager loop (gather at the start
+    of every step, no graph) on the same fold: identical confusion counts and predictions, losses to 1e-4 over two epochs
+    (five full batches + one ragged batch per epoch: exercises the look-ahead at the end of a pass and the re-prime)."""
+    from multimodal_error_detection_b200 import ops
+    from multimodal_error_detection_b200.dataset import dataset_utils as du
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    path, fold = fold_on_disk
+    res = {}
+    for mode in ("eager", "graph_prefetch", "graph"):
+        kw = dict(cases.EPOCH_CASES["lstm_w16"][0], precision="bf16", batch_size=64, return_train_preds=True,
+                  cuda_graph=mode != "eager", prefetch_gather=mode == "graph_prefetch")
+        tr, te = du.retrieve_dataloaders_window(path, kw, window_size=16, stride=4)
+        mu, fe, model, crit, opt, sched = _objects(kw, 16, tr.dataset.binary_error_distribution)
+        _no_dropout(model, fe)
+        res[mode] = [mu.train_single_epoch(model, fe, tr, crit, opt, sched, DEV, kw) for _ in range(2)]
+        if mode != "eager":
+            assert opt._b200_stepper.graph is not None and opt._b200_stepper.prefetch == (mode == "graph_prefetch")
+    for mode in ("graph_prefetch", "graph"):
+        for a, b in zip(res["eager"], res[mode]):
+            assert abs(a[0] - b[0]) < 1e-4 * max(1.0, abs(a[0])), (mode, a[0], b[0])
+            assert np.array_equal(a[5], b[5]), mode
+            assert a[8] == b[8] and a[9] == b[9], mode
+            assert np.abs(np.asarray(a[6]) - np.asarray(b[6])).max() < 1e-3, mode
