@@ -172,10 +172,10 @@ int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream);
  * rows b < B (Bpad >= B: rows per time step in the buffer); the h_{t-1} columns are [hoff,hoff+H) (hoff >= F);
  * zeroes the padding columns [F,hoff) and [hoff+H,Kp) and the h_{-1} columns of step 0.              */
 int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int64_t Bpad, int32_t F, int32_t W, int32_t H,
-                             int32_t Kp, int32_t hoff, void *stream);
+                             int32_t Kp, int32_t hoff, int32_t x_layout, void *stream);
 /* dx [B,F,W] f32 <- dA0 [W,Bpad,Kp] f32 (row-major) columns [0,F).                                   */
 int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int64_t Bpad, int32_t F, int32_t W, int32_t Kp,
-                           void *stream);
+                           int32_t x_layout, void *stream);
 /* A[r, col0:col0+ncols] = 0 for r < rows (bf16 matrix with leading dimension ld).                   */
 int b200med_zero_cols_bf16(void *A, int64_t rows, int32_t ld, int32_t col0, int32_t ncols, void *stream);
 /* One cell step.  G [B,4H] f32: gate pre-activations in (i,f,g,o order, nn.LSTM), replaced in place by the

@@ -96,6 +96,44 @@ lstm_unpack_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long l
     }
 }
 
+// Same, for a head input that is stored [B, W, F] (the reference builds it as cat(...).permute(0, 2, 1): the permuted tensor
+// is a VIEW of this layout): one warp per (b, t) row, no transpose.
+__global__ void __launch_bounds__(256)
+lstm_pack_bwf_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int F, int W, int H,
+                     int Kp, int hoff) {
+    const int lane = threadIdx.x & 31;
+    const long long nrows = B * W, warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+        const long long b = r / W;
+        const int t = (int)(r - b * W);
+        const float *src = x + r * F;
+        __nv_bfloat16 *dst = A0 + ((long long)t * Bpad + b) * Kp;
+        for (int k = lane * 2; k < Kp; k += 64) {
+            const bool x0 = k < F, x1 = k + 1 < F;
+            const bool h0 = k >= hoff && k < hoff + H, h1 = k + 1 >= hoff && k + 1 < hoff + H;
+            if ((h0 || h1) && t != 0) {
+                if (!h0) dst[k] = __float2bfloat16_rn(x0 ? src[k] : 0.0f);
+                if (!h1) dst[k + 1] = __float2bfloat16_rn(x1 ? src[k + 1] : 0.0f);
+            } else {
+                *reinterpret_cast<__nv_bfloat162 *>(dst + k) = __floats2bfloat162_rn(x0 ? src[k] : 0.0f, x1 ? src[k + 1] : 0.0f);
+            }
+        }
+    }
+}
+
+// dx [B, W, F] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F)
+__global__ void __launch_bounds__(256)
+lstm_unpack_bwf_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F, int W, int Kp) {
+    const int lane = threadIdx.x & 31;
+    const long long nrows = B * W, warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+        const long long b = r / W;
+        const int t = (int)(r - b * W);
+        const float *src = dA0 + ((long long)t * Bpad + b) * Kp;
+        for (int k = lane; k < F; k += 32) dx[r * F + k] = src[k];
+    }
+}
+
 __global__ void zero_cols_bf16_kernel(__nv_bfloat16 *__restrict__ A, long long rows, int ld, int col0, int ncols) {
     const long long total = rows * ncols;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
@@ -173,8 +211,16 @@ using namespace b200med;
 
 extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int64_t Bpad,
                                                                                int32_t F, int32_t W, int32_t H, int32_t Kp,
-                                                                               int32_t hoff, void *stream) {
+                                                                               int32_t hoff, int32_t x_layout, void *stream) {
     B200MED_REQUIRE(B >= 1 && Bpad >= B && F >= 1 && W >= 1 && H >= 1 && hoff >= F && Kp >= hoff + H, "bad shape");
+    B200MED_REQUIRE(x_layout == 0 || x_layout == 1, "x_layout: 0 = [B,F,W], 1 = [B,W,F]");
+    if (x_layout == 1) {
+        B200MED_REQUIRE(x && A0 && Kp % 8 == 0, "bad argument");
+        const long long blocks = (B * (long long)W + 7) / 8, cap1 = (long long)num_sms() * 8;
+        lstm_pack_bwf_kernel<<<(unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream>>>(
+            x, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, F, W, H, Kp, hoff);
+        return after_launch("lstm_pack_bwf_kernel");
+    }
     B200MED_REQUIRE(x && A0, "null pointer");
     B200MED_REQUIRE(Kp % 8 == 0 && (size_t)kPackWin * F * (W + 1) * 4 <= 48 * 1024, "bad shape");
     const long long blocks = (B + kPackWin - 1) / kPackWin, cap = (long long)num_sms() * 8;
@@ -184,8 +230,16 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_inputs(c
 }
 
 extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int64_t Bpad,
-                                                                             int32_t F, int32_t W, int32_t Kp, void *stream) {
+                                                                             int32_t F, int32_t W, int32_t Kp, int32_t x_layout,
+                                                                             void *stream) {
     B200MED_REQUIRE(B >= 1 && Bpad >= B && F >= 1 && W >= 1 && Kp >= F, "bad shape");
+    B200MED_REQUIRE(x_layout == 0 || x_layout == 1, "x_layout: 0 = [B,F,W], 1 = [B,W,F]");
+    if (x_layout == 1) {
+        B200MED_REQUIRE(dA0 && dx, "null pointer");
+        const long long blocks = (B * (long long)W + 7) / 8, cap1 = (long long)num_sms() * 8;
+        lstm_unpack_bwf_kernel<<<(unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream>>>(dA0, dx, B, Bpad, F, W, Kp);
+        return after_launch("lstm_unpack_bwf_kernel");
+    }
     B200MED_REQUIRE(dA0 && dx, "null pointer");
     B200MED_REQUIRE((size_t)kPackWin * F * (W + 1) * 4 <= 48 * 1024, "bad shape");
     const long long blocks = (B + kPackWin - 1) / kPackWin, cap = (long long)num_sms() * 8;

@@ -54,7 +54,7 @@ class LSTMStackFunction(torch.autograd.Function):
             G.append(torch.empty(W, B, 4 * H, dtype=torch.float32, device=dev))
             Cs.append(torch.empty(W, B, H, dtype=torch.float32, device=dev))
             Kp.append(kp); ins.append(in_l)
-        call("b200med_lstm_pack_inputs", _raw(x.contiguous().data_ptr()), _raw(A[0].data_ptr()), B, B, F, W, H, Kp[0], F, st)
+        call("b200med_lstm_pack_inputs", _raw(x.contiguous().data_ptr()), _raw(A[0].data_ptr()), B, B, F, W, H, Kp[0], F, 0, st)
         for l in range(1, L):
             call("b200med_zero_cols_bf16", _raw(A[l][0].data_ptr()), B, Kp[l], ins[l], H, st)
             if Kp[l] > ins[l] + H:
@@ -116,7 +116,7 @@ class LSTMStackFunction(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, F, W, dtype=torch.float32, device=dev)
-            call("b200med_lstm_unpack_dx", _raw(dA_up.data_ptr()), _raw(dx.data_ptr()), B, B, F, W, Kp[0], st)
+            call("b200med_lstm_unpack_dx", _raw(dA_up.data_ptr()), _raw(dx.data_ptr()), B, B, F, W, Kp[0], 0, st)
         return (dx, None, None, *grads)
 
 
@@ -181,7 +181,10 @@ class LSTMRecFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         alloc = torch.empty if Bp == B else torch.zeros          # pad rows must hold finite values
         A = [alloc(W, Bp, Kp[l], dtype=torch.bfloat16, device=dev) for l in range(L)]
-        call("b200med_lstm_pack_inputs", _raw(x.contiguous().data_ptr()), _raw(A[0].data_ptr()), B, Bp, F, W, H, Kp[0], inp[0], st)
+        # the reference hands the head cat(...).permute(0, 2, 1): a view of a contiguous [B, W, F] tensor -- read it as such
+        bwf = x.transpose(1, 2).is_contiguous() and not x.is_contiguous()
+        xsrc = x.transpose(1, 2) if bwf else x.contiguous()
+        call("b200med_lstm_pack_inputs", _raw(xsrc.data_ptr()), _raw(A[0].data_ptr()), B, Bp, F, W, H, Kp[0], inp[0], int(bwf), st)
         for l in range(1, L):
             call("b200med_zero_cols_bf16", _raw(A[l][0].data_ptr()), Bp, Kp[l], inp[l], H, st)
         out = torch.empty(B, H, dtype=torch.float32, device=dev)
@@ -215,12 +218,12 @@ class LSTMRecFunction(torch.autograd.Function):
             Gact.append(gact); Cs.append(cs)
         if need_grad:
             ctx.save_for_backward(*A, *Gact, *Cs, *Wih, *Whh)
-        ctx.meta = (B, Bp, F, W, L, H, Kp, ins, inp, float(drop_p), seed_dev)
+        ctx.meta = (B, Bp, F, W, L, H, Kp, ins, inp, float(drop_p), seed_dev, bwf)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        B, Bp, F, W, L, H, Kp, ins, inp, drop_p, seed_dev = ctx.meta
+        B, Bp, F, W, L, H, Kp, ins, inp, drop_p, seed_dev, bwf = ctx.meta
         saved = ctx.saved_tensors
         A, Gact, Cs, Wih, Whh = (saved[i * L:(i + 1) * L] for i in range(5))
         dev = dout.device
@@ -267,8 +270,10 @@ class LSTMRecFunction(torch.autograd.Function):
             g.record_stream(main)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty(B, F, W, dtype=torch.float32, device=dev)
-            call("b200med_lstm_unpack_dx", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, F, W, inp[0], st)
+            dx = torch.empty((B, W, F) if bwf else (B, F, W), dtype=torch.float32, device=dev)
+            call("b200med_lstm_unpack_dx", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, F, W, inp[0], int(bwf), st)
+            if bwf:
+                dx = dx.transpose(1, 2)          # gradient of the permuted view, in the layout of its base tensor
         return (dx, None, None, *grads)
 
 

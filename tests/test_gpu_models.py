@@ -349,6 +349,13 @@ def test_lstm_stack_bf16_vs_torch(impl, B, W):
     with torch.no_grad():           # inference: nothing saved, same h
         h2 = lstm_last_hidden(x, lstm, training=False, seed_dev=None, impl=impl)
     assert nrel(h2, ref_h) < 2e-2
+    # the reference's head input is cat(...).permute(0, 2, 1), a VIEW of a [B, W, F] tensor: same result, gradient lands
+    # in the base tensor's layout, bit-identical to the contiguous-input path
+    lstm.zero_grad()
+    leaf = x.transpose(1, 2).contiguous().requires_grad_(True)
+    h3 = lstm_last_hidden(leaf.transpose(1, 2), lstm, training=True, seed_dev=None, impl=impl)
+    h3.backward(gh)
+    assert torch.equal(h3.detach(), h.detach()) and torch.equal(leaf.grad.transpose(1, 2), xo.grad)
 
 
 def test_lstm_rec_full_size_vs_per_step_path():
