@@ -478,15 +478,10 @@ static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CU
         cfg.blockDim = dim3(kGemmThreads);
         cfg.dynamicSmemBytes = Cfg::kSmemBytes;
         cfg.stream = st;
-        cudaLaunchAttribute attr[2];
+        cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        if (const char *pol = getenv("B200MED_CLUSTER_POLICY")) {
-            attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
-            attr[1].val.clusterSchedulingPolicyPreference = (cudaClusterSchedulingPolicy)atoi(pol);
-            cfg.numAttrs = 2;
-        }
+        cfg.attrs = attr; cfg.numAttrs = 1;      // (the cluster scheduling policy makes no difference here, measured)
         if (int e = check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tm, p), "cudaLaunchKernelEx(gemm_bf16_tcgen05 pair)")) return e;
         return after_launch("gemm_bf16_tcgen05_kernel(pair)");
     } else {
