@@ -58,7 +58,8 @@ struct GemmCfg {
                                           : (kPair ? 6 : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)));
     static constexpr int kAccStages = 2;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two: BLOCK_N in {32,64,128,256}
-    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                         1024 /*bias of the current column tile*/;
 };
 
 // EPI selects the epilogue at compile time (smaller code, no mode branches in the drain loop):
@@ -92,6 +93,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t *acc_empty = acc_full + Cfg::kAccStages;
     uint64_t *mask_bar = acc_empty + Cfg::kAccStages;        // TMA-store epilogue: "the mask tile is in the staging buffer"
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mask_bar + 1);
+    float *bias_sm = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full_bar) + 256);   // [256]: bias of the tile's columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb_total = (int)((p.K + BLOCK_K - 1) / BLOCK_K);
@@ -232,6 +234,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr bool staged = EPI == kEpiTmaBf16;
+        constexpr bool partial_k = EPI == kEpiPartial;
         constexpr int kBoxes = BLOCK_N / 64;                      // TMA boxes of 64 columns x 128 rows per tile
         const bool elect = warp == 2 && lane == 0;                // issues the TMA stores / mask loads of this CTA
         const bool use_mask = staged && p.mask != nullptr;
@@ -248,6 +251,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int z = (int)(tile / tiles_mn);
             const long long mn = tile % tiles_mn;
             const long long m0 = (mn / p.tiles_n) * kTileM + rank * BLOCK_M, n0 = (mn % p.tiles_n) * BLOCK_N;
+            if (!partial_k && p.bias) {
+                // the tile's bias slice goes through shared memory once (LDS broadcast in the drain loop instead of eight
+                // dependent global loads per 32-column chunk, which were the top stall of the small-K GEMMs)
+                asm volatile("bar.sync 2, 256;" ::: "memory");        // everyone is done with the previous tile's slice
+                const int e_tid = threadIdx.x - 64;
+                if (e_tid < BLOCK_N) bias_sm[e_tid] = n0 + e_tid < p.N ? __ldg(p.bias + n0 + e_tid) : 0.0f;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
             bar_wait(&acc_full[acc], acc_phase);
             tcgen05_fence_after();
             if constexpr (staged) {
@@ -282,16 +293,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     const bool full = n_base + 32 <= p.N;
                     if (!partial) {
                         if (p.bias) {
-                            if (full && (((uintptr_t)(p.bias + n_base)) % 16 == 0)) {
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.bias + n_base) + q);
-                                    f[4 * q] += b4.x; f[4 * q + 1] += b4.y; f[4 * q + 2] += b4.z; f[4 * q + 3] += b4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (full || n_base + j < p.N) f[j] += __ldg(p.bias + n_base + j);
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b4 = *reinterpret_cast<const float4 *>(bias_sm + c0 + 4 * q);
+                                f[4 * q] += b4.x; f[4 * q + 1] += b4.y; f[4 * q + 2] += b4.z; f[4 * q + 3] += b4.w;
                             }
                         }
                         if (p.relu) {
