@@ -271,15 +271,39 @@ def run_gpu(args):
         # under the LSTM kernels; time K1 inside the same train step launched eagerly with the gather at its start
         g, pf, stepper.graphs, stepper.prefetch = stepper.graphs, stepper.prefetch, [None, None], False
         n_ev = min(K, 8)
-        for i in range(n_ev):
-            stepper.load(idx_all[Wm + i])
-            stepper.gather_events = gather_ev[i]
-            stepper.run()
-        torch.cuda.synchronize()
+        k1_ms = None
+        if g[0] is not None:
+            # preferred: the same step captured as a CUDA graph with EXTERNAL event records around K1, so that K1 is timed
+            # inside back-to-back replays (an eagerly launched step leaves the GPU idle between launches)
+            try:
+                ext = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+                stepper.gather_events = ext
+                stepper.load(idx_all[Wm])
+                stepper.capture()
+                ts = []
+                for i in range(n_ev + 2):
+                    stepper.load(idx_all[Wm + (i % K)])
+                    stepper.run()
+                    torch.cuda.synchronize()
+                    ts.append(ext[0].elapsed_time(ext[1]))
+                k1_ms = statistics.mean(ts[2:])
+                k1_how = ("external CUDA events recorded around the K1 launches inside the replayed CUDA graph of the same train step "
+                          "with the gather at the start of the step" +
+                          (" (the timed steps prefetch K1 of step k+1 under step k's LSTM kernels)" if pf else ""))
+            except Exception as e:      # external events in graphs are a torch >= 2.4 feature: fall back to eager timing
+                k1_ms = None
+                print(f"bench: in-graph K1 timing unavailable ({type(e).__name__}: {e}); timing K1 in eager steps", file=sys.stderr)
+            stepper.graphs, stepper.gather_events = [None, None], None
+        if k1_ms is None:
+            for i in range(n_ev):
+                stepper.load(idx_all[Wm + i])
+                stepper.gather_events = gather_ev[i]
+                stepper.run()
+            torch.cuda.synchronize()
+            k1_ms = statistics.mean(a.elapsed_time(b) for a, b in gather_ev[:n_ev])
+            k1_how = ("CUDA events around the K1 launch inside the same train step launched eagerly with the gather at the start "
+                      "of the step (the timed steps are graph replays" + (" with K1 of step k+1 prefetched under step k's LSTM kernels)" if pf else ")"))
         stepper.graphs, stepper.prefetch, stepper.gather_events, stepper._primed = g, pf, None, False
-        k1_ms = statistics.mean(a.elapsed_time(b) for a, b in gather_ev[:n_ev])
-        k1_how = ("CUDA events around the K1 launch inside the same train step launched eagerly with the gather at the start "
-                  "of the step (the timed steps are graph replays" + (" with K1 of step k+1 prefetched under step k's LSTM kernels)" if pf else ")"))
     iso = []
     for i in range(min(K, 10) + 3):      # isolated launches; every launch touches a fresh 1.1 GB slice (> L2)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
