@@ -46,6 +46,9 @@ int b200med_version(void);
 const char *b200med_last_error(void);
 /* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
 int64_t b200med_launch_count(void);
+/* Limit the number of SMs the persistent kernels launched BY THE CALLING THREAD fill from now on (grids are sized from it);
+ * 0 = all.  Returns the previous limit.  For work issued on a side stream next to a kernel that must keep its SMs.   */
+int b200med_set_sm_limit(int32_t sms);
 
 /* ------------------------------------------------------------------------------------------------
  * K0  Window index + label transforms (integer work, bit-exact bar)

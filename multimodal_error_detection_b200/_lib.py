@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200med_version": (C.c_int, []),
     "b200med_last_error": (C.c_char_p, []),
     "b200med_launch_count": (_i64, []),
+    "b200med_set_sm_limit": (C.c_int, [_i32]),
     "b200med_window_count": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "b200med_window_fill": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "b200med_powerset": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),

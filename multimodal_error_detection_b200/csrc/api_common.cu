@@ -5,6 +5,7 @@
 namespace b200med {
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+thread_local int g_sm_limit = 0;
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -17,3 +18,8 @@ void set_error(const char *fmt, ...) {
 extern "C" __attribute__((visibility("default"))) int b200med_version(void) { return B200MED_VERSION; }
 extern "C" __attribute__((visibility("default"))) const char *b200med_last_error(void) { return b200med::g_err; }
 extern "C" __attribute__((visibility("default"))) int64_t b200med_launch_count(void) { return (int64_t)b200med::g_launches.load(); }
+extern "C" __attribute__((visibility("default"))) int b200med_set_sm_limit(int32_t sms) {
+    const int prev = b200med::g_sm_limit;
+    b200med::g_sm_limit = sms > 0 ? sms : 0;
+    return prev;
+}

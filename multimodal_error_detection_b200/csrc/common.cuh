@@ -12,6 +12,7 @@ namespace b200med {
 
 void set_error(const char *fmt, ...);
 extern std::atomic<long long> g_launches;
+extern thread_local int g_sm_limit;   // b200med_set_sm_limit(): SMs the persistent kernels launched by this thread may fill
 
 inline int check_cuda(cudaError_t e, const char *what) {
     if (e == cudaSuccess) return B200MED_OK;
@@ -32,7 +33,7 @@ inline int num_sms() {
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
             sms = 148;
     }
-    return sms;
+    return (g_sm_limit > 0 && g_sm_limit < sms) ? g_sm_limit : sms;
 }
 
 #define B200MED_REQUIRE(cond, msg)                       \

@@ -45,7 +45,8 @@ class WindowTrainStep:
         self.preds = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.labels = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.gather_variant = gather_variant
-        self.gather_events = None      # optional (start, end) CUDA events around K1 (eager mode only)
+        self.gather_events = None      # optional (start, end) CUDA events around K1
+        self.phase_events = None       # optional list of 9 (external) CUDA events at the phase boundaries of the step
         self.graphs = [None, None]     # one captured step per buffer parity
         self.launches_per_step = None
         self._side = torch.cuda.Stream(device=dev)
@@ -88,12 +89,21 @@ class WindowTrainStep:
 
     prime = load
 
+    def _mark(self, k: int):
+        if self.phase_events is not None:
+            self.phase_events[k].record()
+
     def _body(self, cur: int):
         nxt = 1 - cur
+        self._mark(0)
         labels = self.label_col.index_select(0, self.idx2[cur])
         if not self.prefetch:
             self._gather(cur)
+        self._mark(1)
         inputs = mu.define_inputs(self.images2[cur], self.kin2[cur], self.fe, self.kw, self.device)
+        self._mark(2)
+        if self.phase_events is not None and inputs.requires_grad:
+            inputs.register_hook(lambda g: self._mark(5))      # gradient w.r.t. the head input = end of the head's backward
         if self.prefetch:
             # K1 of the NEXT step: forked here so that it runs under the LSTM recurrence of this step
             main = torch.cuda.current_stream()
@@ -101,11 +111,15 @@ class WindowTrainStep:
             with torch.cuda.stream(self._side):
                 self._gather(nxt, self.prefetch_sms)      # leaves the other SMs to the main stream's kernels
         outputs = self.model(inputs)
+        self._mark(3)
         loss, _ = mu.compute_loss(outputs, labels, self.crit, "window")
         self.opt.zero_grad()
+        self._mark(4)
         mu._backward(loss, self.opt)
+        self._mark(6)
         mu._allreduce_grads(self.opt)
         self.opt.step()
+        self._mark(7)
         probs, preds, counts = self.crit.last
         self.loss.copy_(loss.detach().reshape(1))
         self.counts.copy_(counts)
@@ -114,6 +128,7 @@ class WindowTrainStep:
         self.labels.copy_(labels)
         if self.prefetch:
             torch.cuda.current_stream().wait_stream(self._side)
+        self._mark(8)
 
     def capture(self, warmup: int = 3):
         """Run `warmup` real steps on a side stream (the current contents of the index buffers are used), then record

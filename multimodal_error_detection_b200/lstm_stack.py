@@ -129,6 +129,7 @@ _SIDE = {}
 # `.grad` right after backward() gets the join inside the backward.
 DEFER_JOIN = False
 _PENDING = []
+SIDE_SMS = 80        # SMs the side-stream GEMMs may fill: the recurrence kernel of the next layer needs 64 of the 148
 
 
 def join_pending():
@@ -245,7 +246,7 @@ class LSTMRecFunction(torch.autograd.Function):
             # The weight / bias gradients of this layer are off the critical path (dG_l -> dX_l -> recurrence of layer l-1):
             # they run on a side stream, next to the next recurrence kernel which only fills 64 of the 148 SMs.
             side.wait_stream(main)
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side), ops.sm_limit(SIDE_SMS):
                 # dWcat [4H, Kp] = dG^T [x | h_prev] over all W*Bp rows (both operands MN-major), deterministic split-K
                 tiles = ((4 * H + 127) // 128) * ((Kp[l] + 255) // 256)
                 dW = ops.gemm_bf16(dG, A[l].view(W * Bp, Kp[l]), 4 * H, Kp[l], W * Bp, False, False,

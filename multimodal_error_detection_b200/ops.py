@@ -45,6 +45,22 @@ def _dt(t: torch.Tensor) -> int:
 _ws_cache = {}
 
 
+class sm_limit:
+    """``with ops.sm_limit(n):`` -- persistent kernels launched inside fill at most n SMs (side-stream work that runs next to a
+    kernel which must keep its SMs)."""
+
+    def __init__(self, sms: int):
+        self.sms = int(sms)
+
+    def __enter__(self):
+        self.prev = _lib.load().b200med_set_sm_limit(self.sms)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().b200med_set_sm_limit(self.prev)
+        return False
+
+
 def workspace(nbytes: int, device, tag: str = "default", zero: bool = False) -> torch.Tensor:
     """Grow-only scratch buffers keyed by (device, stream, tag); stream-ordered reuse is safe."""
     key = (str(device), torch.cuda.current_stream().cuda_stream, tag)
