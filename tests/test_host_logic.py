@@ -145,6 +145,22 @@ def test_index_batches_mirror_the_dataloader_exactly():
         assert torch.cat([x, y]).tolist() == g.tolist()
 
 
+def test_lstm_dg_column_permutation():
+    """Host side of the recurrence kernels' dG layout (csrc/lstm_rec.cu): column' = chunk*128 + unit_quarter*32 + gate*8 + i
+    holds gate column gate*H + unit_quarter*32 + chunk*8 + i -- a permutation, and the two index tensors are inverses."""
+    from multimodal_error_detection_b200.lstm_stack import _dg_perm
+    H = 128
+    orig_of, colp_of = _dg_perm(H, "cpu")
+    assert sorted(orig_of.tolist()) == list(range(4 * H))
+    assert torch.equal(orig_of[colp_of], torch.arange(4 * H)) and torch.equal(colp_of[orig_of], torch.arange(4 * H))
+    for colp in (0, 7, 8, 31, 32, 127, 128, 300, 511):
+        c, uq, g, i = colp // 128, (colp % 128) // 32, (colp % 32) // 8, colp % 8
+        assert int(orig_of[colp]) == g * H + uq * 32 + c * 8 + i
+    # un-permuting the rows of a permuted matrix restores it (what the backward does to dW and db)
+    m = torch.arange(4 * H * 3, dtype=torch.float32).reshape(4 * H, 3)
+    assert torch.equal(m.index_select(0, orig_of).index_select(0, colp_of), m)
+
+
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
