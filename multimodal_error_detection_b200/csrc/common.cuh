@@ -86,12 +86,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// fp16 pair, saturated to the finite range (used for bounded quantities: LSTM gate pre-activations / activations)
+// fp16 pair, saturated to the finite range by the conversion itself (F2FP.SATFINITE: one instruction; used for bounded
+// quantities -- LSTM gate pre-activations / activations)
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-    lo = fminf(fmaxf(lo, -65504.0f), 65504.0f);
-    hi = fminf(fmaxf(hi, -65504.0f), 65504.0f);
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t *>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
 }  // namespace b200med

@@ -58,8 +58,10 @@ struct GemmCfg {
                                           : (kPair ? 6 : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)));
     static constexpr int kAccStages = 2;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two: BLOCK_N in {32,64,128,256}
-    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/ +
-                                         1024 /*bias of the current column tile*/;
+    static constexpr size_t kBaseBytes = (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    // bias in shared memory: the whole vector (N <= 512, loaded once) where 2 KB fit, else the current column tile's slice
+    static constexpr int kBiasFloats = (kBaseBytes + 2048 <= 232448) ? 512 : 256;
+    static constexpr size_t kSmemBytes = kBaseBytes + kBiasFloats * 4;
 };
 
 // EPI selects the epilogue at compile time (smaller code, no mode branches in the drain loop):
@@ -247,11 +249,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             for (int bx = 0; bx < kBoxes; ++bx) tma_load_2d(staging + bx * 16384, &tmap_mask, mask_bar, n_ + 64 * bx, m_);
         };
         if (use_mask && elect && cta_id < total_tiles) load_mask_tile(cta_id);
+        // N <= 512 (every GEMM of the train step that has a bias): the whole bias vector is loaded once per CTA
+        const bool bias_all = !partial_k && p.bias && p.N <= Cfg::kBiasFloats;
+        if (bias_all) {
+            for (int e = threadIdx.x - 64; e < Cfg::kBiasFloats; e += 256) bias_sm[e] = e < p.N ? __ldg(p.bias + e) : 0.0f;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
         for (long long tile = cta_id; tile < total_tiles; tile += cta_stride) {
             const int z = (int)(tile / tiles_mn);
             const long long mn = tile % tiles_mn;
             const long long m0 = (mn / p.tiles_n) * kTileM + rank * BLOCK_M, n0 = (mn % p.tiles_n) * BLOCK_N;
-            if (!partial_k && p.bias) {
+            if (!partial_k && p.bias && !bias_all) {
                 // the tile's bias slice goes through shared memory once (LDS broadcast in the drain loop instead of eight
                 // dependent global loads per 32-column chunk, which were the top stall of the small-K GEMMs)
                 asm volatile("bar.sync 2, 256;" ::: "memory");        // everyone is done with the previous tile's slice
@@ -259,6 +267,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 if (e_tid < BLOCK_N) bias_sm[e_tid] = n0 + e_tid < p.N ? __ldg(p.bias + n0 + e_tid) : 0.0f;
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
+            const float *bias_tile = bias_all ? bias_sm + n0 : bias_sm;
             bar_wait(&acc_full[acc], acc_phase);
             tcgen05_fence_after();
             if constexpr (staged) {
@@ -295,7 +304,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         if (p.bias) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                const float4 b4 = *reinterpret_cast<const float4 *>(bias_sm + c0 + 4 * q);
+                                const float4 b4 = *reinterpret_cast<const float4 *>(bias_tile + c0 + 4 * q);
                                 f[4 * q] += b4.x; f[4 * q + 1] += b4.y; f[4 * q + 2] += b4.z; f[4 * q + 3] += b4.w;
                             }
                         }
