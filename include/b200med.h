@@ -260,6 +260,59 @@ int b200med_ce_frame(const float *logits, const float *e, int32_t stages, int64_
                      int32_t accumulate, void *workspace, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * TeCNo frame head: the dilated residual stack of MultiStageModel (MED/modeling/models_TCN.py:17-137),
+ * num_f_maps = 64, kernel size 3, fp32.  Activations are TIME-major [T, 64]; stage logits are [C, T]
+ * (the reference's [1, C, T]).  The 1x1 input convolution of a stage (models_TCN.py:84, 93) is
+ * b200med_linear_fwd_f32 on the [T, F] rows (F = 58 / 2048 for stage 1, C for the later stages).
+ * tloc / trem (int32 [T] or NULL): frame index inside its video / frames left after it, for several videos
+ * concatenated along T (taps never cross a video); NULL = the T rows are one video.
+ * ---------------------------------------------------------------------------------------------- */
+#define B200MED_TCN_PACK_FLOATS 32896   /* per layer: WdF[k][ci][co] | W1F[ci][co] | WdB[k][co][ci] | W1B[co][ci] | b_d | b_1 */
+#define B200MED_TCN_GRAD_FLOATS 16512   /* per layer: dWd[co][ci][k] | dW1[co][ci] | db_d[64] | db_1[64] (torch layouts)     */
+
+/* Number of partial-gradient slots (= CTAs) b200med_tcn_layer_bwd_hidden uses for T frames.            */
+int32_t b200med_tcn_slots(int64_t T);
+/* Transpose the weights of n_layers DilatedResidualLayers into the kernel layouts, one launch.
+ * param_ptrs: DEVICE array [n_layers][4] of device pointers {conv_dilated.weight [64,64,3],
+ * conv_dilated.bias [64], conv_1x1.weight [64,64,1], conv_1x1.bias [64]} (models_TCN.py:111-127);
+ * packed [n_layers * B200MED_TCN_PACK_FLOATS] OUT, 16-byte aligned.                                     */
+int b200med_tcn_pack(const void *const *param_ptrs, int32_t n_layers, float *packed, void *stream);
+/* One DilatedResidualLayer.forward (models_TCN.py:130-137) in one launch:
+ *   y = relu(conv_dilated(x)) (causal: taps t-2d, t-d, t == the reference's pad-and-slice; else t-d, t, t+d),
+ *   out = x + dropout(conv_1x1(y)).   x, out [T,64]; y_save [T,64] OUT or NULL (kept for the backward);
+ *   pack = this layer's record of b200med_tcn_pack.  Dropout: counter-based mask keyed by (seed, drop_base + t*64 + c),
+ *   drop_p = 0 in eval mode.                                                                                */
+int b200med_tcn_layer_fwd(const float *x, const float *pack, float *out, float *y_save, int64_t T,
+                          int32_t dilation, int32_t causal, const int32_t *tloc, const int32_t *trem,
+                          float drop_p, uint64_t seed, uint64_t drop_base, void *stream);
+/* Backward of the layer, part 1: dz = dout * mask, dpre [T,64] OUT = (dz W1) * (y > 0), and the partial
+ * weight / bias gradients of the layer: partials [n_slots][B200MED_TCN_GRAD_FLOATS] OUT (n_slots =
+ * b200med_tcn_slots(T)), summed by b200med_tcn_reduce_grads.  x = the layer's input, y = its y_save.       */
+int b200med_tcn_layer_bwd_hidden(const float *dout, const float *x, const float *y, const float *pack,
+                                 float *dpre, float *partials, int32_t n_slots, int64_t T,
+                                 int32_t dilation, int32_t causal, const int32_t *tloc,
+                                 const int32_t *trem, float drop_p, uint64_t seed, uint64_t drop_base,
+                                 void *stream);
+/* Backward of the layer, part 2: dx [T,64] = dout + conv_dilated^T(dpre).                                  */
+int b200med_tcn_layer_bwd_input(const float *dpre, const float *dout, const float *pack, float *dx,
+                                int64_t T, int32_t dilation, int32_t causal, const int32_t *tloc,
+                                const int32_t *trem, void *stream);
+/* grads [n_layers][B200MED_TCN_GRAD_FLOATS] = sum over slots (ascending: deterministic) of
+ * partials [n_layers][n_slots][B200MED_TCN_GRAD_FLOATS].                                                   */
+int b200med_tcn_reduce_grads(const float *partials, int32_t n_layers, int32_t n_slots, float *grads,
+                             void *stream);
+/* conv_out_classes (models_TCN.py:90, 96): logits [C,T] = W [C,64] x[T,64]^T + b, 1 <= C <= 8.            */
+int b200med_tcn_out_fwd(const float *x, const float *w, const float *b, float *logits, int64_t T,
+                        int32_t C, void *stream);
+/* dx [T,64] = dlogits[C,T]^T W; dlogits_t [T,C] = row-major copy (operand of b200med_linear_bwd_weight_f32). */
+int b200med_tcn_out_bwd(const float *dlogits, const float *w, float *dx, float *dlogits_t, int64_t T,
+                        int32_t C, void *stream);
+/* F.softmax(out, dim=1) between stages (models_TCN.py:48): p [T,C] = softmax over c of logits [C,T].     */
+int b200med_tcn_softmax_fwd(const float *logits, float *p, int64_t T, int32_t C, void *stream);
+int b200med_tcn_softmax_bwd(const float *p, const float *dp, float *dlogits, int64_t T, int32_t C,
+                            void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimiser: Adam with coupled L2 decay, torch.optim.Adam semantics (modeling_utils.py:221-222)
  * ---------------------------------------------------------------------------------------------- */
 

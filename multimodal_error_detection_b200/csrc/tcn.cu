@@ -1,0 +1,557 @@
+// TeCNo frame head: the dilated residual stack of MultiStageModel (MED/modeling/models_TCN.py:76-137) as fused fp32
+// kernels (path row a10).
+//
+// Layout.  The reference runs Conv1d over [1, C, T] (channel-major).  Here every activation of a stage is TIME-major,
+// A[T, 64]: one frame = one 256-byte row, so a kernel tap "t + off" is a row offset, a tile of 16 frames is 4 KB of
+// contiguous memory, and the 1x1 input convolution is the plain GEMM x[T, F] W[64, F]^T on the table rows as they lie
+// in HBM (no [F, T] transpose of the 2048-d frame features is ever made).  Only the stage logits are written [C, T],
+// the layout the reference returns and the frame loss kernel (b200med_ce_frame) reads.
+//
+// One DilatedResidualLayer = ONE launch (torch: conv, ReLU, slice, conv, dropout, add = 6):
+//   y   = relu(b_d + sum_k Wd[:, :, k] x[t + off_k])           off = {-2d, -d, 0} causal, {-d, 0, +d} otherwise
+//   out = x + dropout(b_1 + W1 y)
+// A CTA owns 16 consecutive frames and all 64 channels.  The layer's weights (48 KB + 16 KB, pre-transposed once per step
+// by tcn_pack_kernel so that the output channel is the contiguous index) arrive in shared memory by ONE cp.async.bulk
+// (TMA 1-D copy, mbarrier complete_tx) issued by thread 0 while all threads stage the three tap tiles with 128-bit loads;
+// each thread then owns a 2-frame x 4-channel register tile (LDS.128 for both operands, 32 FMA per 6 LDS.128).
+// Backward per layer = two launches:
+//   tcn_layer_bwd_hidden: dz = dout * mask, dpre = (dz W1) * (y > 0), and the layer's weight/bias gradient PARTIALS
+//                         (outer products of the 16-frame tiles, 144 register accumulators per thread, summed later in
+//                         fixed slot order by tcn_reduce_grads_kernel: deterministic, no atomics);
+//   tcn_layer_bwd_input:  dx = dout + sum_k Wd[:, :, k]^T dpre[t - off_k]   (the same 3-tap tile product, transposed pack).
+// Ragged batches: `tloc` / `trem` (frame index inside its video / frames left after it) let several videos be
+// concatenated along T without taps crossing a video boundary (ensemble inference, BASELINE config 5); NULL = one video.
+#include "tcgen05.cuh"
+
+namespace b200med {
+
+constexpr int kF = 64;            // feature maps (mstcn_f_maps)
+constexpr int kTT = 16;           // frames per CTA tile
+constexpr int kTcnThreads = 128;  // 16 channel groups (4 channels) x 8 frame pairs
+constexpr int kWd = 3 * kF * kF;  // 12288
+constexpr int kW1 = kF * kF;      // 4096
+// pack of one layer (floats): WdF [k][ci][co] | W1F [ci][co] | WdB [k][co][ci] | W1B [co][ci] | b_d [64] | b_1 [64]
+constexpr int kOffWdF = 0, kOffW1F = kWd, kOffWdB = kWd + kW1, kOffW1B = 2 * kWd + kW1, kOffBias = 2 * kWd + 2 * kW1;
+constexpr int kPackFloats = kOffBias + 2 * kF;  // 32896 == B200MED_TCN_PACK_FLOATS
+// gradient record of one layer (floats): dWd [co][ci][k] | dW1 [co][ci] | db_d [64] | db_1 [64]  (torch parameter layouts)
+constexpr int kGradFloats = kWd + kW1 + 2 * kF;  // 16512 == B200MED_TCN_GRAD_FLOATS
+constexpr int kMaxSlots = 64;
+constexpr int kMaxClasses = 8;
+static_assert(kPackFloats == B200MED_TCN_PACK_FLOATS && kGradFloats == B200MED_TCN_GRAD_FLOATS, "header constants");
+
+struct TcnGeom {
+    long long T;
+    const int32_t *tloc, *trem;
+    int off0, off1, off2;
+    int centre;  // tap whose offset is 0
+    __device__ __forceinline__ int off(int k) const { return k == 0 ? off0 : (k == 1 ? off1 : off2); }
+};
+
+__device__ __forceinline__ bool tap_ok(const TcnGeom &g, long long t, int off) {
+    const long long tl = g.tloc ? (long long)g.tloc[t] : t;
+    const long long tr = g.trem ? (long long)g.trem[t] : g.T - 1 - t;
+    return tl + off >= 0 && off <= tr;
+}
+
+__device__ __forceinline__ bool tcn_keep(unsigned long long seed, unsigned long long index, float p) {
+    uint64_t z = index + 0x9E3779B97F4A7C15ull * (seed + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f) >= p;
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(s_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(s_addr(bar)) : "memory");
+}
+
+// Arm `bar` and start the weight copy (thread 0 only; the caller syncs the CTA before anyone waits).
+__device__ __forceinline__ void start_weight_copy(float *dst, const float *src, uint32_t bytes, uint64_t *bar) {
+    if (threadIdx.x == 0) {
+        bar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        bar_expect_tx(bar, bytes);
+        bulk_g2s(dst, src, bytes, bar);
+    }
+}
+
+// xs[k][r][0..63] = src[t0 + r + sign*off_k][:] (zero where the tap leaves the video or the tile leaves the table).
+__device__ __forceinline__ void stage_taps(float *xs, const float *__restrict__ src, const TcnGeom &g, long long t0, int sign) {
+    for (int e = threadIdx.x; e < 3 * kTT * (kF / 4); e += kTcnThreads) {
+        const int k = e / (kTT * (kF / 4)), r = (e / (kF / 4)) % kTT, c4 = e % (kF / 4);
+        const long long t = t0 + r;
+        const int off = sign * g.off(k);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < g.T && tap_ok(g, t, off)) v = __ldg(reinterpret_cast<const float4 *>(src + (t + off) * kF) + c4);
+        *reinterpret_cast<float4 *>(xs + (k * kTT + r) * kF + c4 * 4) = v;
+    }
+}
+
+// acc[j][c] += sum_i rowj[i] * w[i*64 + c],  i = 0..63; w already points at this thread's 4 output channels.
+__device__ __forceinline__ void mac_tile(float (&acc)[2][4], const float *row0, const float *row1, const float *w) {
+#pragma unroll 4
+    for (int i = 0; i < kF; i += 4) {
+        const float4 a = *reinterpret_cast<const float4 *>(row0 + i);
+        const float4 b = *reinterpret_cast<const float4 *>(row1 + i);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w + (i + j) * kF);
+            acc[0][0] = fmaf(av[j], wv.x, acc[0][0]); acc[0][1] = fmaf(av[j], wv.y, acc[0][1]);
+            acc[0][2] = fmaf(av[j], wv.z, acc[0][2]); acc[0][3] = fmaf(av[j], wv.w, acc[0][3]);
+            acc[1][0] = fmaf(bv[j], wv.x, acc[1][0]); acc[1][1] = fmaf(bv[j], wv.y, acc[1][1]);
+            acc[1][2] = fmaf(bv[j], wv.z, acc[1][2]); acc[1][3] = fmaf(bv[j], wv.w, acc[1][3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight pack
+// ptrs [L][4] = {conv_dilated.weight [64,64,3], conv_dilated.bias [64], conv_1x1.weight [64,64,1], conv_1x1.bias [64]}
+__global__ void __launch_bounds__(256)
+tcn_pack_kernel(const float *const *__restrict__ ptrs, float *__restrict__ packed) {
+    const int layer = blockIdx.y;
+    const float *wd = ptrs[layer * 4 + 0], *bd = ptrs[layer * 4 + 1], *w1 = ptrs[layer * 4 + 2], *b1 = ptrs[layer * 4 + 3];
+    float *out = packed + (long long)layer * kPackFloats;
+    const int stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = first; i < kWd; i += stride) {
+        const int co = i / (3 * kF), r = i % (3 * kF), ci = r / 3, k = r % 3;
+        const float v = wd[i];
+        out[kOffWdF + (k * kF + ci) * kF + co] = v;
+        out[kOffWdB + (k * kF + co) * kF + ci] = v;
+    }
+    for (int i = first; i < kW1; i += stride) {
+        const int co = i / kF, ci = i % kF;
+        const float v = w1[i];
+        out[kOffW1F + ci * kF + co] = v;
+        out[kOffW1B + i] = v;
+    }
+    for (int i = first; i < kF; i += stride) {
+        out[kOffBias + i] = bd[i];
+        out[kOffBias + kF + i] = b1[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layer forward
+__global__ void __launch_bounds__(kTcnThreads)
+tcn_layer_fwd_kernel(const float *__restrict__ x, const float *__restrict__ pack, float *__restrict__ out,
+                     float *__restrict__ y_save, TcnGeom g, float drop_p, unsigned long long seed,
+                     unsigned long long drop_base) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    float *ws = smem;                   // WdF | W1F : 16384 floats
+    float *xs = ws + kWd + kW1;         // [3][16][64]
+    float *ys = xs + 3 * kTT * kF;      // [16][64]
+    const long long t0 = (long long)blockIdx.x * kTT;
+    start_weight_copy(ws, pack + kOffWdF, (kWd + kW1) * 4, &bar);
+    stage_taps(xs, x, g, t0, +1);
+    __syncthreads();
+    bar_wait(&bar, 0);
+
+    const int cg = threadIdx.x & 15, tq = threadIdx.x >> 4, r0 = 2 * tq;
+    float acc[2][4] = {};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        mac_tile(acc, xs + (k * kTT + r0) * kF, xs + (k * kTT + r0 + 1) * kF, ws + k * kW1 + cg * 4);
+    const float4 bd = __ldg(reinterpret_cast<const float4 *>(pack + kOffBias) + cg);
+    const float bdv[4] = {bd.x, bd.y, bd.z, bd.w};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float4 y;
+        y.x = fmaxf(acc[j][0] + bdv[0], 0.f); y.y = fmaxf(acc[j][1] + bdv[1], 0.f);
+        y.z = fmaxf(acc[j][2] + bdv[2], 0.f); y.w = fmaxf(acc[j][3] + bdv[3], 0.f);
+        *reinterpret_cast<float4 *>(ys + (r0 + j) * kF + cg * 4) = y;
+        const long long t = t0 + r0 + j;
+        if (y_save && t < g.T) *reinterpret_cast<float4 *>(y_save + t * kF + cg * 4) = y;
+    }
+    __syncthreads();
+    float z[2][4] = {};
+    mac_tile(z, ys + r0 * kF, ys + (r0 + 1) * kF, ws + kWd + cg * 4);
+    const float4 b1 = __ldg(reinterpret_cast<const float4 *>(pack + kOffBias + kF) + cg);
+    const float b1v[4] = {b1.x, b1.y, b1.z, b1.w};
+    const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const long long t = t0 + r0 + j;
+        if (t >= g.T) continue;
+        const float4 xc = *reinterpret_cast<const float4 *>(xs + (g.centre * kTT + r0 + j) * kF + cg * 4);
+        const float xv[4] = {xc.x, xc.y, xc.z, xc.w};
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v = z[j][c] + b1v[c];
+            if (drop_p > 0.f) v = tcn_keep(seed, drop_base + (unsigned long long)(t * kF + cg * 4 + c), drop_p) ? v * scale : 0.f;
+            o[c] = xv[c] + v;
+        }
+        *reinterpret_cast<float4 *>(out + t * kF + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layer backward (hidden)
+// Per 16-frame tile: dz = dout * dropout mask, dpre = (dz W1) * (y > 0) -> global; partial weight gradients of the tile
+// accumulate in registers over the tiles this CTA (= slot) owns:
+//   dWd[co][ci][k] += dpre[t][co] x[t + off_k][ci],  dW1[co][ci] += dz[t][co] y[t][ci],  db_d += dpre[t],  db_1 += dz[t].
+__global__ void __launch_bounds__(kTcnThreads)
+tcn_layer_bwd_hidden_kernel(const float *__restrict__ dout, const float *__restrict__ x, const float *__restrict__ y,
+                            const float *__restrict__ pack, float *__restrict__ dpre, float *__restrict__ partials,
+                            TcnGeom g, float drop_p, unsigned long long seed, unsigned long long drop_base) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    float *w1b = smem;                  // [co][ci] 4096
+    float *xs = w1b + kW1;              // [3][16][64]
+    float *ys = xs + 3 * kTT * kF;      // [16][64]
+    float *dzs = ys + kTT * kF;         // [16][64]
+    float *dps = dzs + kTT * kF;        // [16][64]
+    start_weight_copy(w1b, pack + kOffW1B, kW1 * 4, &bar);
+    __syncthreads();   // the barrier is initialised before any thread can reach a wait
+
+    const int cg = threadIdx.x & 15, tq = threadIdx.x >> 4, r0 = 2 * tq;
+    const int cog = threadIdx.x & 7, cig = threadIdx.x >> 3;   // weight-gradient tile: 8 co x (3 taps x 4 ci + 4 ci)
+    float gD[8][3][4] = {}, g1[8][4] = {}, gbd[8] = {}, gb1[8] = {};
+    const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const long long ntiles = (g.T + kTT - 1) / kTT;
+    bool first = true;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long t0 = tile * kTT;
+        stage_taps(xs, x, g, t0, +1);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long t = t0 + r0 + j;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f), yv = d;
+            if (t < g.T) {
+                d = __ldg(reinterpret_cast<const float4 *>(dout + t * kF) + cg);
+                yv = __ldg(reinterpret_cast<const float4 *>(y + t * kF) + cg);
+                if (drop_p > 0.f) {
+                    const unsigned long long base = drop_base + (unsigned long long)(t * kF + cg * 4);
+                    d.x = tcn_keep(seed, base + 0, drop_p) ? d.x * scale : 0.f;
+                    d.y = tcn_keep(seed, base + 1, drop_p) ? d.y * scale : 0.f;
+                    d.z = tcn_keep(seed, base + 2, drop_p) ? d.z * scale : 0.f;
+                    d.w = tcn_keep(seed, base + 3, drop_p) ? d.w * scale : 0.f;
+                }
+            }
+            *reinterpret_cast<float4 *>(dzs + (r0 + j) * kF + cg * 4) = d;
+            *reinterpret_cast<float4 *>(ys + (r0 + j) * kF + cg * 4) = yv;
+        }
+        __syncthreads();
+        if (first) { bar_wait(&bar, 0); first = false; }
+        float acc[2][4] = {};
+        mac_tile(acc, dzs + r0 * kF, dzs + (r0 + 1) * kF, w1b + cg * 4);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float4 yv = *reinterpret_cast<const float4 *>(ys + (r0 + j) * kF + cg * 4);
+            float4 p;
+            p.x = yv.x > 0.f ? acc[j][0] : 0.f; p.y = yv.y > 0.f ? acc[j][1] : 0.f;
+            p.z = yv.z > 0.f ? acc[j][2] : 0.f; p.w = yv.w > 0.f ? acc[j][3] : 0.f;
+            *reinterpret_cast<float4 *>(dps + (r0 + j) * kF + cg * 4) = p;
+            const long long t = t0 + r0 + j;
+            if (t < g.T) *reinterpret_cast<float4 *>(dpre + t * kF + cg * 4) = p;
+        }
+        __syncthreads();
+        // weight-gradient partials of this tile (rows beyond T hold zeros in dzs / dps)
+#pragma unroll 2
+        for (int r = 0; r < kTT; ++r) {
+            const float4 p0 = *reinterpret_cast<const float4 *>(dps + r * kF + cog * 8);
+            const float4 p1 = *reinterpret_cast<const float4 *>(dps + r * kF + cog * 8 + 4);
+            const float4 z0 = *reinterpret_cast<const float4 *>(dzs + r * kF + cog * 8);
+            const float4 z1 = *reinterpret_cast<const float4 *>(dzs + r * kF + cog * 8 + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            const float zv[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+            const float4 yv4 = *reinterpret_cast<const float4 *>(ys + r * kF + cig * 4);
+            const float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
+            float xv[3][4];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(xs + (k * kTT + r) * kF + cig * 4);
+                xv[k][0] = t4.x; xv[k][1] = t4.y; xv[k][2] = t4.z; xv[k][3] = t4.w;
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) gD[a][k][i] = fmaf(pv[a], xv[k][i], gD[a][k][i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) g1[a][i] = fmaf(zv[a], yv[i], g1[a][i]);
+                gbd[a] += pv[a];
+                gb1[a] += zv[a];
+            }
+        }
+        __syncthreads();
+    }
+    if (first) bar_wait(&bar, 0);   // a CTA without tiles must still drain its copy before exiting
+    float *part = partials + (long long)blockIdx.x * kGradFloats;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int co = cog * 8 + a;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) part[co * (3 * kF) + (cig * 4 + i) * 3 + k] = gD[a][k][i];
+            part[kWd + co * kF + cig * 4 + i] = g1[a][i];
+        }
+        if (cig == 0) {
+            part[kWd + kW1 + co] = gbd[a];
+            part[kWd + kW1 + kF + co] = gb1[a];
+        }
+    }
+}
+
+// grads[layer][e] = sum over slots (ascending) of partials[layer][slot][e]
+__global__ void __launch_bounds__(256)
+tcn_reduce_grads_kernel(const float *__restrict__ partials, float *__restrict__ grads, int n_slots) {
+    const int layer = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= kGradFloats) return;
+    const float *p = partials + (long long)layer * n_slots * kGradFloats + e;
+    float s = 0.f;
+    for (int z = 0; z < n_slots; ++z) s += p[(long long)z * kGradFloats];
+    grads[(long long)layer * kGradFloats + e] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ layer backward (input)
+// dx[t][ci] = dout[t][ci] + sum_k sum_co Wd[co][ci][k] dpre[t - off_k][co]
+__global__ void __launch_bounds__(kTcnThreads)
+tcn_layer_bwd_input_kernel(const float *__restrict__ dpre, const float *__restrict__ dout, const float *__restrict__ pack,
+                           float *__restrict__ dx, TcnGeom g) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t bar;
+    float *ws = smem;             // WdB [k][co][ci]
+    float *xs = ws + kWd;         // taps of dpre
+    const long long t0 = (long long)blockIdx.x * kTT;
+    start_weight_copy(ws, pack + kOffWdB, kWd * 4, &bar);
+    stage_taps(xs, dpre, g, t0, -1);
+    __syncthreads();
+    bar_wait(&bar, 0);
+    const int cg = threadIdx.x & 15, tq = threadIdx.x >> 4, r0 = 2 * tq;
+    float acc[2][4] = {};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        mac_tile(acc, xs + (k * kTT + r0) * kF, xs + (k * kTT + r0 + 1) * kF, ws + k * kW1 + cg * 4);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const long long t = t0 + r0 + j;
+        if (t >= g.T) continue;
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(dout + t * kF) + cg);
+        *reinterpret_cast<float4 *>(dx + t * kF + cg * 4) =
+            make_float4(d.x + acc[j][0], d.y + acc[j][1], d.z + acc[j][2], d.w + acc[j][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stage ends
+// logits[c][t] = b[c] + sum_ci W[c][ci] x[t][ci]      (conv_out_classes, models_TCN.py:90,96; C <= 8)
+__global__ void __launch_bounds__(128)
+tcn_out_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
+                   float *__restrict__ logits, long long T, int C) {
+    __shared__ float ws[kMaxClasses * kF];
+    __shared__ float bs[kMaxClasses];
+    for (int i = threadIdx.x; i < C * kF; i += blockDim.x) ws[i] = w[i];
+    if (threadIdx.x < C) bs[threadIdx.x] = b[threadIdx.x];
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    float acc[kMaxClasses];
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) acc[c] = c < C ? bs[c] : 0.f;
+    const float4 *row = reinterpret_cast<const float4 *>(x + t * kF);
+#pragma unroll 4
+    for (int i = 0; i < kF / 4; ++i) {
+        const float4 v = __ldg(row + i);
+#pragma unroll
+        for (int c = 0; c < kMaxClasses; ++c)
+            if (c < C) {
+                const float *wc = ws + c * kF + i * 4;
+                acc[c] = fmaf(v.x, wc[0], acc[c]); acc[c] = fmaf(v.y, wc[1], acc[c]);
+                acc[c] = fmaf(v.z, wc[2], acc[c]); acc[c] = fmaf(v.w, wc[3], acc[c]);
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+        if (c < C) logits[(long long)c * T + t] = acc[c];
+}
+
+// dx[t][ci] = sum_c W[c][ci] dl[c][t];   dl_t[t][c] = dl[c][t] (row-major copy for the weight-gradient GEMM)
+__global__ void __launch_bounds__(256)
+tcn_out_bwd_kernel(const float *__restrict__ dl, const float *__restrict__ w, float *__restrict__ dx,
+                   float *__restrict__ dl_t, long long T, int C) {
+    __shared__ float ws[kMaxClasses * kF];
+    for (int i = threadIdx.x; i < C * kF; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long t = idx / (kF / 4);
+    const int c4 = (int)(idx % (kF / 4));
+    if (t >= T) return;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+        if (c < C) {
+            const float d = __ldg(dl + (long long)c * T + t);
+            const float *wc = ws + c * kF + c4 * 4;
+            o[0] = fmaf(d, wc[0], o[0]); o[1] = fmaf(d, wc[1], o[1]);
+            o[2] = fmaf(d, wc[2], o[2]); o[3] = fmaf(d, wc[3], o[3]);
+            if (c4 == 0) dl_t[t * C + c] = d;
+        }
+    *reinterpret_cast<float4 *>(dx + t * kF + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// p[t][c] = softmax_c(logits[c][t])   (F.softmax(out, dim=1) between stages, models_TCN.py:48)
+__global__ void __launch_bounds__(128)
+tcn_softmax_fwd_kernel(const float *__restrict__ logits, float *__restrict__ p, long long T, int C) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    float v[kMaxClasses], m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+        if (c < C) { v[c] = logits[(long long)c * T + t]; m = fmaxf(m, v[c]); }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+        if (c < C) { v[c] = expf(v[c] - m); s += v[c]; }
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+        if (c < C) p[t * C + c] = v[c] / s;
+}
+
+// dlogits[c][t] = p[t][c] * (dp[t][c] - sum_j p[t][j] dp[t][j])
+__global__ void __launch_bounds__(128)
+tcn_softmax_bwd_kernel(const float *__restrict__ p, const float *__restrict__ dp, float *__restrict__ dlogits, long long T,
+                       int C) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    float pv[kMaxClasses], dv[kMaxClasses], dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+        if (c < C) { pv[c] = p[t * C + c]; dv[c] = dp[t * C + c]; dot = fmaf(pv[c], dv[c], dot); }
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c)
+        if (c < C) dlogits[(long long)c * T + t] = pv[c] * (dv[c] - dot);
+}
+
+static int make_geom(TcnGeom &g, int64_t T, int32_t dilation, int32_t causal, const int32_t *tloc, const int32_t *trem) {
+    g.T = T; g.tloc = tloc; g.trem = trem;
+    if (causal) { g.off0 = -2 * dilation; g.off1 = -dilation; g.off2 = 0; g.centre = 2; }
+    else        { g.off0 = -dilation;     g.off1 = 0;         g.off2 = dilation; g.centre = 1; }
+    return 0;
+}
+
+constexpr size_t kSmemFwd = (size_t)(kWd + kW1 + 3 * kTT * kF + kTT * kF) * 4;     // 81920
+constexpr size_t kSmemBwdH = (size_t)(kW1 + 3 * kTT * kF + 3 * kTT * kF) * 4;      // 40960
+constexpr size_t kSmemBwdI = (size_t)(kWd + 3 * kTT * kF) * 4;                     // 61440
+
+// > 48 KB of dynamic shared memory needs the opt-in; once per kernel and process (one device per process).
+template <typename K>
+static int opt_in_smem(K kernel, size_t bytes) {
+    static bool done = false;   // one instantiation per kernel type
+    if (done) return B200MED_OK;
+    const int e = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                             "cudaFuncSetAttribute(tcn)");
+    done = e == B200MED_OK;
+    return e;
+}
+
+}  // namespace b200med
+
+using namespace b200med;
+#define TCN_API extern "C" __attribute__((visibility("default")))
+
+TCN_API int32_t b200med_tcn_slots(int64_t T) {
+    const long long tiles = (T + kTT - 1) / kTT;
+    return (int32_t)(tiles < 1 ? 1 : (tiles < kMaxSlots ? tiles : kMaxSlots));
+}
+
+TCN_API int b200med_tcn_pack(const void *const *param_ptrs, int32_t n_layers, float *packed, void *stream) {
+    B200MED_REQUIRE(n_layers >= 1, "bad layer count");
+    B200MED_REQUIRE(param_ptrs && packed, "null pointer");
+    B200MED_REQUIRE((uintptr_t)packed % 16 == 0, "packed must be 16-byte aligned");
+    tcn_pack_kernel<<<dim3(8, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float *const *>(param_ptrs), packed);
+    return after_launch("tcn_pack_kernel");
+}
+
+TCN_API int b200med_tcn_layer_fwd(const float *x, const float *pack, float *out, float *y_save, int64_t T, int32_t dilation,
+                                  int32_t causal, const int32_t *tloc, const int32_t *trem, float drop_p, uint64_t seed,
+                                  uint64_t drop_base, void *stream) {
+    B200MED_REQUIRE(T >= 0 && dilation >= 1, "bad shape");
+    B200MED_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability must be in [0, 1)");
+    if (T == 0) return B200MED_OK;
+    B200MED_REQUIRE(x && pack && out, "null pointer");
+    B200MED_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)pack % 16 == 0 && (uintptr_t)out % 16 == 0 &&
+                    (uintptr_t)y_save % 16 == 0, "pointers must be 16-byte aligned");
+    TcnGeom g; make_geom(g, T, dilation, causal, tloc, trem);
+    if (int e = opt_in_smem(tcn_layer_fwd_kernel, kSmemFwd)) return e;
+    tcn_layer_fwd_kernel<<<(unsigned)((T + kTT - 1) / kTT), kTcnThreads, kSmemFwd, (cudaStream_t)stream>>>(
+        x, pack, out, y_save, g, drop_p, seed, drop_base);
+    return after_launch("tcn_layer_fwd_kernel");
+}
+
+TCN_API int b200med_tcn_layer_bwd_hidden(const float *dout, const float *x, const float *y, const float *pack, float *dpre,
+                                         float *partials, int32_t n_slots, int64_t T, int32_t dilation, int32_t causal,
+                                         const int32_t *tloc, const int32_t *trem, float drop_p, uint64_t seed,
+                                         uint64_t drop_base, void *stream) {
+    B200MED_REQUIRE(T >= 1 && dilation >= 1 && n_slots >= 1, "bad shape");
+    B200MED_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability must be in [0, 1)");
+    B200MED_REQUIRE(dout && x && y && pack && dpre && partials, "null pointer");
+    B200MED_REQUIRE((uintptr_t)dout % 16 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)pack % 16 == 0 &&
+                    (uintptr_t)dpre % 16 == 0, "pointers must be 16-byte aligned");
+    TcnGeom g; make_geom(g, T, dilation, causal, tloc, trem);
+    if (int e = opt_in_smem(tcn_layer_bwd_hidden_kernel, kSmemBwdH)) return e;
+    tcn_layer_bwd_hidden_kernel<<<(unsigned)n_slots, kTcnThreads, kSmemBwdH, (cudaStream_t)stream>>>(
+        dout, x, y, pack, dpre, partials, g, drop_p, seed, drop_base);
+    return after_launch("tcn_layer_bwd_hidden_kernel");
+}
+
+TCN_API int b200med_tcn_layer_bwd_input(const float *dpre, const float *dout, const float *pack, float *dx, int64_t T,
+                                        int32_t dilation, int32_t causal, const int32_t *tloc, const int32_t *trem,
+                                        void *stream) {
+    B200MED_REQUIRE(T >= 1 && dilation >= 1, "bad shape");
+    B200MED_REQUIRE(dpre && dout && pack && dx, "null pointer");
+    B200MED_REQUIRE((uintptr_t)dpre % 16 == 0 && (uintptr_t)dout % 16 == 0 && (uintptr_t)pack % 16 == 0 && (uintptr_t)dx % 16 == 0,
+                    "pointers must be 16-byte aligned");
+    TcnGeom g; make_geom(g, T, dilation, causal, tloc, trem);
+    if (int e = opt_in_smem(tcn_layer_bwd_input_kernel, kSmemBwdI)) return e;
+    tcn_layer_bwd_input_kernel<<<(unsigned)((T + kTT - 1) / kTT), kTcnThreads, kSmemBwdI, (cudaStream_t)stream>>>(
+        dpre, dout, pack, dx, g);
+    return after_launch("tcn_layer_bwd_input_kernel");
+}
+
+TCN_API int b200med_tcn_reduce_grads(const float *partials, int32_t n_layers, int32_t n_slots, float *grads, void *stream) {
+    B200MED_REQUIRE(n_layers >= 1 && n_slots >= 1, "bad shape");
+    B200MED_REQUIRE(partials && grads, "null pointer");
+    tcn_reduce_grads_kernel<<<dim3((kGradFloats + 255) / 256, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>(
+        partials, grads, n_slots);
+    return after_launch("tcn_reduce_grads_kernel");
+}
+
+TCN_API int b200med_tcn_out_fwd(const float *x, const float *w, const float *b, float *logits, int64_t T, int32_t C,
+                                void *stream) {
+    B200MED_REQUIRE(T >= 0 && C >= 1 && C <= kMaxClasses, "1 <= C <= 8 classes");
+    if (T == 0) return B200MED_OK;
+    B200MED_REQUIRE(x && w && b && logits, "null pointer");
+    B200MED_REQUIRE((uintptr_t)x % 16 == 0, "x must be 16-byte aligned");
+    tcn_out_fwd_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, w, b, logits, T, C);
+    return after_launch("tcn_out_fwd_kernel");
+}
+
+TCN_API int b200med_tcn_out_bwd(const float *dlogits, const float *w, float *dx, float *dlogits_t, int64_t T, int32_t C,
+                                void *stream) {
+    B200MED_REQUIRE(T >= 1 && C >= 1 && C <= kMaxClasses, "1 <= C <= 8 classes");
+    B200MED_REQUIRE(dlogits && w && dx && dlogits_t, "null pointer");
+    B200MED_REQUIRE((uintptr_t)dx % 16 == 0, "dx must be 16-byte aligned");
+    const long long n = T * (kF / 4);
+    tcn_out_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dlogits, w, dx, dlogits_t, T, C);
+    return after_launch("tcn_out_bwd_kernel");
+}
+
+TCN_API int b200med_tcn_softmax_fwd(const float *logits, float *p, int64_t T, int32_t C, void *stream) {
+    B200MED_REQUIRE(T >= 0 && C >= 1 && C <= kMaxClasses, "1 <= C <= 8 classes");
+    if (T == 0) return B200MED_OK;
+    B200MED_REQUIRE(logits && p, "null pointer");
+    tcn_softmax_fwd_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(logits, p, T, C);
+    return after_launch("tcn_softmax_fwd_kernel");
+}
+
+TCN_API int b200med_tcn_softmax_bwd(const float *p, const float *dp, float *dlogits, int64_t T, int32_t C, void *stream) {
+    B200MED_REQUIRE(T >= 1 && C >= 1 && C <= kMaxClasses, "1 <= C <= 8 classes");
+    B200MED_REQUIRE(p && dp && dlogits, "null pointer");
+    tcn_softmax_bwd_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p, dp, dlogits, T, C);
+    return after_launch("tcn_softmax_bwd_kernel");
+}

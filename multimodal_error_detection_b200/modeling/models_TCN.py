@@ -4,8 +4,14 @@ hard-code the Apple ``mps`` device and need CLIP weights).
 
 Same constructor signature, ``state_dict`` keys (``stage1.conv_1x1``, ``stage1.layers.{i}.conv_dilated``,
 ``stage1.layers.{i}.conv_1x1``, ``stage1.conv_out_classes``, ``stages.{s}...``), construction order
-(=> same seed-42 weights) and output layout ``[stages, 1, C, T]``.  The dilated causal stack runs on
-stock torch conv layers on the GPU in this round (its fused time-tiled kernel is SURVEY section 8f row 2).
+(=> same seed-42 weights) and output layout ``[stages, 1, C, T]``.
+
+The modules below only HOLD the parameters (so ``state_dict`` / ``load_state_dict`` / the optimiser see the reference's
+tensors); the arithmetic of a stage runs on the fused sm_100a kernels of ``csrc/tcn.cu`` through
+:class:`multimodal_error_detection_b200.tcn.TcnStageFunction` -- one launch per DilatedResidualLayer, time-major
+activations, the inter-stage softmax folded into the consuming stage.  The kernels are specialised for the reference's
+configuration (64 feature maps, kernel size 3, batch of one video, <= 8 classes); any other shape still runs, on the
+stock torch convolution layers (``impl == "torch"``), and says so in ``MultiStageModel.impl``.
 """
 from __future__ import annotations
 
@@ -14,6 +20,8 @@ import copy
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from .. import tcn
 
 
 class DilatedResidualLayer(nn.Module):
@@ -26,6 +34,7 @@ class DilatedResidualLayer(nn.Module):
         self.dropout = nn.Dropout()
 
     def forward(self, x):
+        """Stock-layer form (only used for shapes the fused kernels are not specialised for)."""
         y = F.relu(self.conv_dilated(x))
         if self.causal_conv:
             y = y[:, :, :-(self.dilation * 2)]   # drop the right overhang -> causal
@@ -35,12 +44,43 @@ class DilatedResidualLayer(nn.Module):
 class SingleStageModel(nn.Module):
     def __init__(self, num_layers, num_f_maps, dim, num_classes, causal_conv=False):
         super().__init__()
+        self.num_layers, self.num_f_maps, self.dim, self.num_classes, self.causal_conv = \
+            num_layers, num_f_maps, dim, num_classes, causal_conv
         self.conv_1x1 = nn.Conv1d(dim, num_f_maps, 1)
         self.layers = nn.ModuleList([copy.deepcopy(DilatedResidualLayer(2 ** i, num_f_maps, num_f_maps, causal_conv=causal_conv))
                                      for i in range(num_layers)])
         self.conv_out_classes = nn.Conv1d(num_f_maps, num_classes, 1)
+        self._cfgs = {}
 
-    def forward(self, x):
+    # ------------------------------------------------------------------------------ fused path
+    def fused_supported(self) -> bool:
+        return (len(self.layers) >= 1 and tcn.supported(self.num_f_maps, self.layers[0].kernel_size, self.num_classes, self.dim)
+                and all(l.dilation == 2 ** i and l.kernel_size == 3 for i, l in enumerate(self.layers)))
+
+    def fused_ok(self, x: torch.Tensor) -> bool:
+        return x.dim() == 3 and x.shape[0] == 1 and x.dtype == torch.float32 and self.fused_supported()
+
+    def _stage_params(self):
+        ps = [self.conv_1x1.weight, self.conv_1x1.bias]
+        for l in self.layers:
+            ps += [l.conv_dilated.weight, l.conv_dilated.bias, l.conv_1x1.weight, l.conv_1x1.bias]
+        return ps + [self.conv_out_classes.weight, self.conv_out_classes.bias]
+
+    def run_fused(self, x: torch.Tensor, softmax_in: bool = False, seed: int = 0, layer_base: int = 0, geom=(None, None)):
+        """x [1, F, T] (or the previous stage's logits [1, C, T] with ``softmax_in``) -> logits [1, C, T]."""
+        tcn.require_cuda(x)
+        cfg = self._cfgs.get(softmax_in)
+        if cfg is None:
+            cfg = self._cfgs[softmax_in] = tcn.StageConfig(len(self.layers), self.causal_conv, softmax_in)
+        cfg.layer_base, cfg.seed = layer_base, seed
+        cfg.drop_p = [float(l.dropout.p) if (self.training and l.dropout.training) else 0.0 for l in self.layers]
+        cfg.tloc, cfg.trem = geom
+        xin = x[0] if softmax_in else x[0].t()      # [C, T] logits, or [T, F] rows (a free view of the [1, T, F] batch)
+        return tcn.TcnStageFunction.apply(xin, cfg, *self._stage_params()).unsqueeze(0)
+
+    def forward(self, x, fused: bool = True):
+        if fused and self.fused_ok(x):
+            return self.run_fused(x)
         out = self.conv_1x1(x)
         for layer in self.layers:
             out = layer(out)
@@ -58,11 +98,41 @@ class MultiStageModel(nn.Module):
                                                                     causal_conv=mstcn_causal_conv))
                                      for _ in range(mstcn_stages - 1)])
         self.smoothing = False
+        self.impl = "b200"       # what the last forward ran on: "b200" (csrc/tcn.cu) or "torch" (unsupported shape)
+        self.use_fused = True    # scripts/bench_frame.py switches it off to time the stock torch layers as the A/B baseline
 
-    def forward(self, x):
-        out = self.stage1(x)
+    def _seed(self) -> int:
+        if not self.training:
+            return 0
+        return int(torch.randint(0, 2 ** 62, (1,)).item())     # host generator: reproducible under torch.manual_seed
+
+    def forward(self, x, geom=(None, None)):
+        if self.use_fused and self.stage1.fused_ok(x) and all(s.fused_supported() for s in self.stages):
+            self.impl = "b200"
+            seed = self._seed()
+            out = self.stage1.run_fused(x, False, seed, 0, geom)
+            outs = [out]
+            for i, s in enumerate(self.stages):
+                out = s.run_fused(out, True, seed, (i + 1) * self.num_layers, geom)
+                outs.append(out)
+            return torch.stack(outs, dim=0)
+        if geom[0] is not None:
+            raise ValueError("ragged batches need the fused TeCNo kernels (64 feature maps, kernel size 3, <= 8 classes)")
+        self.impl = "torch"
+        out = self.stage1(x, fused=False)
         outs = [out]
         for s in self.stages:
-            out = s(F.softmax(out, dim=1))
+            out = s(F.softmax(out, dim=1), fused=False)
             outs.append(out)
         return torch.stack(outs, dim=0)
+
+    @torch.no_grad()
+    def forward_ragged(self, frames: torch.Tensor, lengths) -> torch.Tensor:
+        """Batched inference over several videos concatenated along time: frames [sum(T_v), F] (rows of the frame
+        table), lengths = T_v per video -> logits [stages, C, sum(T_v)]; taps never cross a video boundary, so the
+        result equals running every video on its own (the reference's DataLoader(batch_size=1) loop)."""
+        geom = tcn.ragged_geometry(lengths, frames.device)
+        if int(sum(int(n) for n in lengths)) != frames.shape[0]:
+            raise ValueError("lengths must sum to the number of frame rows")
+        x = frames.contiguous().float().unsqueeze(0).permute(0, 2, 1)
+        return self.forward(x, geom)[:, 0]

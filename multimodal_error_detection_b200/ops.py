@@ -169,11 +169,13 @@ def standardise_rows(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, out
 
 
 # ------------------------------------------------------------------------------------------- K2 fp32
-def linear_fwd_f32(x, w, b, relu: bool):
+def linear_fwd_f32(x, w, b, relu: bool, out=None):
     x = _need(x, torch.float32, "x"); w = _need(w, torch.float32, "w")
     M, K = x.shape
     N = w.shape[0]
-    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    if w.shape[1] != K:
+        raise ValueError(f"linear_fwd_f32: x has {K} columns, w has {w.shape[1]}")
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device) if out is None else _need(out, torch.float32, "out")
     call("b200med_linear_fwd_f32", _ptr(x), _ptr(w), _ptr(b), _ptr(y), M, N, K, int(relu), _stream())
     return y
 
@@ -343,3 +345,93 @@ def confusion(target, pred, n_classes: int, cm=None, accumulate=False):
         cm = torch.zeros(n_classes, n_classes, dtype=torch.int64, device=t.device)
     call("b200med_confusion", _ptr(t), _ptr(p), t.numel(), n_classes, _ptr(cm), int(accumulate), _stream())
     return cm
+
+
+# ------------------------------------------------------------------------------------------- TeCNo frame head
+TCN_PACK_FLOATS, TCN_GRAD_FLOATS, TCN_MAPS = 32896, 16512, 64
+
+
+def _geom(tloc, trem):
+    return (_ptr(None if tloc is None else _need(tloc, torch.int32, "tloc")),
+            _ptr(None if trem is None else _need(trem, torch.int32, "trem")))
+
+
+def tcn_slots(T: int) -> int:
+    return int(_lib.load().b200med_tcn_slots(int(T)))
+
+
+def tcn_pack(ptr_table: torch.Tensor, n_layers: int, out=None) -> torch.Tensor:
+    """ptr_table: int64 CUDA tensor [n_layers, 4] of parameter addresses (see b200med_tcn_pack)."""
+    ptr_table = _need(ptr_table, torch.int64, "ptr_table")
+    if ptr_table.numel() != n_layers * 4:
+        raise ValueError("ptr_table must hold 4 addresses per layer")
+    if out is None:
+        out = torch.empty(n_layers, TCN_PACK_FLOATS, dtype=torch.float32, device=ptr_table.device)
+    call("b200med_tcn_pack", _ptr(ptr_table), n_layers, _ptr(out), _stream())
+    return out
+
+
+def tcn_layer_fwd(x, pack, out, y_save, dilation: int, causal: bool, drop_p=0.0, seed=0, drop_base=0, tloc=None, trem=None):
+    x = _need(x, torch.float32, "x")
+    T = x.shape[0]
+    tl, tr = _geom(tloc, trem)
+    call("b200med_tcn_layer_fwd", _ptr(x), _ptr(pack), _ptr(out), _ptr(y_save), T, int(dilation), int(bool(causal)), tl, tr,
+         float(drop_p), C.c_uint64(int(seed)), C.c_uint64(int(drop_base)), _stream())
+    return out
+
+
+def tcn_layer_bwd_hidden(dout, x, y, pack, dpre, partials, n_slots, dilation, causal, drop_p=0.0, seed=0, drop_base=0,
+                         tloc=None, trem=None):
+    dout = _need(dout, torch.float32, "dout")
+    tl, tr = _geom(tloc, trem)
+    call("b200med_tcn_layer_bwd_hidden", _ptr(dout), _ptr(x), _ptr(y), _ptr(pack), _ptr(dpre), _ptr(partials), int(n_slots),
+         dout.shape[0], int(dilation), int(bool(causal)), tl, tr, float(drop_p), C.c_uint64(int(seed)),
+         C.c_uint64(int(drop_base)), _stream())
+    return dpre
+
+
+def tcn_layer_bwd_input(dpre, dout, pack, dx, dilation, causal, tloc=None, trem=None):
+    dpre = _need(dpre, torch.float32, "dpre")
+    tl, tr = _geom(tloc, trem)
+    call("b200med_tcn_layer_bwd_input", _ptr(dpre), _ptr(dout), _ptr(pack), _ptr(dx), dpre.shape[0], int(dilation),
+         int(bool(causal)), tl, tr, _stream())
+    return dx
+
+
+def tcn_reduce_grads(partials, n_layers: int, n_slots: int) -> torch.Tensor:
+    grads = torch.empty(n_layers, TCN_GRAD_FLOATS, dtype=torch.float32, device=partials.device)
+    call("b200med_tcn_reduce_grads", _ptr(partials), n_layers, n_slots, _ptr(grads), _stream())
+    return grads
+
+
+def tcn_out_fwd(x, w, b) -> torch.Tensor:
+    x = _need(x, torch.float32, "x"); w = _need(w, torch.float32, "w"); b = _need(b, torch.float32, "b")
+    T, Cn = x.shape[0], w.shape[0]
+    logits = torch.empty(Cn, T, dtype=torch.float32, device=x.device)
+    call("b200med_tcn_out_fwd", _ptr(x), _ptr(w), _ptr(b), _ptr(logits), T, Cn, _stream())
+    return logits
+
+
+def tcn_out_bwd(dlogits, w):
+    dl = _need(dlogits, torch.float32, "dlogits"); w = _need(w, torch.float32, "w")
+    Cn, T = dl.shape
+    dx = torch.empty(T, TCN_MAPS, dtype=torch.float32, device=dl.device)
+    dl_t = torch.empty(T, Cn, dtype=torch.float32, device=dl.device)
+    call("b200med_tcn_out_bwd", _ptr(dl), _ptr(w), _ptr(dx), _ptr(dl_t), T, Cn, _stream())
+    return dx, dl_t
+
+
+def tcn_softmax_fwd(logits) -> torch.Tensor:
+    logits = _need(logits, torch.float32, "logits")
+    Cn, T = logits.shape
+    p = torch.empty(T, Cn, dtype=torch.float32, device=logits.device)
+    call("b200med_tcn_softmax_fwd", _ptr(logits), _ptr(p), T, Cn, _stream())
+    return p
+
+
+def tcn_softmax_bwd(p, dp) -> torch.Tensor:
+    p = _need(p, torch.float32, "p"); dp = _need(dp, torch.float32, "dp")
+    T, Cn = p.shape
+    dl = torch.empty(Cn, T, dtype=torch.float32, device=p.device)
+    call("b200med_tcn_softmax_bwd", _ptr(p), _ptr(dp), _ptr(dl), T, Cn, _stream())
+    return dl

@@ -1,0 +1,103 @@
+"""Frame path (BASELINE config 0, train_frame: TeCNo over per-frame features) -- A/B of the fused TeCNo kernels
+(csrc/tcn.cu) against the same model on the stock torch CUDA convolution layers, one video per step like the
+reference's DataLoader(batch_size=1), plus ragged-batched inference.  CUDA-event timing, warm-up first.
+
+    python scripts/bench_frame.py [--frames 600] [--videos 64] [--steps 30]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from multimodal_error_detection_b200 import _lib  # noqa: E402
+from multimodal_error_detection_b200.modeling import modeling_utils as mu  # noqa: E402
+
+
+def timed(fn, steps, warmup=5):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=600)
+    ap.add_argument("--videos", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=30)
+    args = ap.parse_args()
+    dev = torch.device("cuda")
+    kw = dict(dataset_type="frame", error_type="global", pos_weight=False, n_epochs=2, batch_size=1, lr=3e-4,
+              lr_scheduler=True, weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32, data_type="multimodal",
+              delete_ND=True, return_train_preds=False, siamese=False, model_name="TeCNo", mstcn_stages=2, mstcn_layers=8,
+              mstcn_f_maps=64, mstcn_f_dim=58, out_features=2, mstcn_causal_conv=True)
+    fe, model, crit, opt, sched = mu.define_model_objects(kw, {"multimodal": 58, "video": 32, "kinematics": 26}, dev, (0.4, 0.6))
+    T = args.frames
+    g = torch.Generator().manual_seed(42)
+    images = torch.randn(1, T, 2048, generator=g).clamp_min(0).to(dev)
+    kin = torch.randn(1, T, 26, generator=g).to(dev)
+    y = (torch.rand(1, T, generator=g) > 0.5).float().to(dev)
+    res = {"frames_per_video": T, "config": "TeCNo 2 stages x 8 layers x 64 maps, F=58 (FE 2048->32 + 26 kinematics), fp32"}
+
+    def train_step():
+        inputs = mu.define_inputs(images, kin, fe, kw, dev)
+        out = model(inputs)
+        loss, _ = mu.compute_loss(out, y, crit, "frame")
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    def head_only():
+        out = model(feats)
+        (out.sum()).backward()
+
+    def infer():
+        with torch.no_grad():
+            model(mu.define_inputs(images, kin, fe, kw, dev))
+
+    feats = torch.randn(1, T, 58, generator=g).to(dev).permute(0, 2, 1)
+    for name, fused in (("b200", True), ("torch_layers", False)):
+        model.use_fused = fused
+        model.train(); fe.train()
+        n0 = _lib.launch_count()
+        ms = timed(train_step, args.steps)
+        launches = (_lib.launch_count() - n0) / (args.steps + 5)
+        ms_head = timed(head_only, args.steps)
+        model.eval(); fe.eval()
+        ms_inf = timed(infer, args.steps)
+        res[name] = {"train_ms_per_video": ms, "train_frames_per_s": T / ms * 1e3, "head_fwd_bwd_ms": ms_head,
+                     "infer_ms_per_video": ms_inf, "infer_frames_per_s": T / ms_inf * 1e3, "own_launches_per_step": launches,
+                     "impl": model.impl}
+    # ragged-batched inference of the head: V videos in one pass vs one pass per video
+    model.use_fused = True
+    model.eval()
+    lengths = torch.randint(300, 901, (args.videos,), generator=g).tolist()
+    frames = torch.randn(sum(lengths), 58, generator=g).to(dev)
+
+    def ragged():
+        model.forward_ragged(frames, lengths)
+
+    def per_video():
+        s = 0
+        with torch.no_grad():
+            for n in lengths:
+                model(frames[s:s + n].unsqueeze(0).permute(0, 2, 1))
+                s += n
+
+    ms_r, ms_p = timed(ragged, 10, 2), timed(per_video, 3, 1)
+    res["head_inference"] = {"videos": args.videos, "frames": sum(lengths), "ragged_ms": ms_r, "per_video_ms": ms_p,
+                             "ragged_frames_per_s": sum(lengths) / ms_r * 1e3, "per_video_frames_per_s": sum(lengths) / ms_p * 1e3}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,232 @@
+"""GPU parity tests of the TeCNo kernels (csrc/tcn.cu), called through the C ABI: every kernel against its torch
+definition (tests/tcn_reference.py, computed in fp64 on the host), the whole MultiStageModel against the oracle TeCNo
+(forward, input gradient, every parameter gradient), ragged batches against per-video runs, dropout mask consistency
+between forward and backward.  fp32 FMA arithmetic: bars are 1e-5 relative to the largest magnitude of the compared
+tensor (1e-4 for gradients reduced over T)."""
+import pytest
+import torch
+
+import tcn_reference as ref
+from oracle import nets
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multimodal_error_detection_b200 import ops as _ops
+    return _ops
+
+
+def close(a, b, tol=1e-5):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    return err <= tol * (b.abs().max().item() + 1e-12), err
+
+
+def _layer(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    wd = torch.randn(64, 64, 3, generator=g) * 0.1
+    bd = torch.randn(64, generator=g) * 0.1
+    w1 = torch.randn(64, 64, 1, generator=g) * 0.1
+    b1 = torch.randn(64, generator=g) * 0.1
+    return wd, bd, w1, b1
+
+
+def _pack_on_device(ops, layers):
+    tensors = [t.to(DEV).contiguous() for layer in layers for t in layer]
+    table = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(DEV)
+    pack = ops.tcn_pack(table, len(layers))
+    torch.cuda.synchronize()
+    return pack, tensors
+
+
+def test_pack_layout(ops):
+    layers = [_layer(1), _layer(2), _layer(3)]
+    pack, _ = _pack_on_device(ops, layers)
+    for l, layer in enumerate(layers):
+        assert torch.equal(pack[l].cpu(), ref.pack_layer(*layer))
+
+
+GEOMS = [(77, 1, True), (77, 4, False), (600, 128, True), (333, 64, False), (16, 2, True), (5, 8, True), (1030, 1, True)]
+
+
+@pytest.mark.parametrize("T,dilation,causal", GEOMS)
+def test_layer_forward_and_backward_kernels(ops, T, dilation, causal):
+    layer = _layer(T + dilation)
+    pack, _ = _pack_on_device(ops, [layer])
+    pk = pack[0]
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn(T, 64, generator=g)
+    dout = torch.randn(T, 64, generator=g)
+    pk64 = ref.pack_layer(*[t.double() for t in layer])
+    out_r, y_r = ref.layer_fwd(x.double(), pk64, dilation, causal)
+    out = torch.empty(T, 64, device=DEV)
+    y = torch.empty(T, 64, device=DEV)
+    ops.tcn_layer_fwd(x.to(DEV), pk, out, y, dilation, causal)
+    ok, err = close(out, out_r); assert ok, f"out {err}"
+    ok, err = close(y, y_r); assert ok, f"y {err}"
+    # eval form: no y_save
+    out2 = torch.empty(T, 64, device=DEV)
+    ops.tcn_layer_fwd(x.to(DEV), pk, out2, None, dilation, causal)
+    assert torch.equal(out, out2)
+    # backward, part 1 (the reference is given the kernel's own y so the ReLU mask is identical)
+    dpre_r, grad_r = ref.layer_bwd_hidden(dout.double(), x.double(), y.cpu().double(), pk64, dilation, causal)
+    n_slots = ops.tcn_slots(T)
+    assert n_slots == max(1, min(64, (T + 15) // 16))
+    dpre = torch.empty(T, 64, device=DEV)
+    partials = torch.full((1, n_slots, ops.TCN_GRAD_FLOATS), float("nan"), device=DEV)
+    ops.tcn_layer_bwd_hidden(dout.to(DEV), x.to(DEV), y, pk, dpre, partials[0], n_slots, dilation, causal)
+    ok, err = close(dpre, dpre_r); assert ok, f"dpre {err}"
+    grads = ops.tcn_reduce_grads(partials, 1, n_slots)[0]
+    for name, a, b in (("dWd", 0, ref.WD), ("dW1", ref.WD, ref.WD + ref.W1), ("dbd", ref.WD + ref.W1, ref.WD + ref.W1 + 64),
+                       ("db1", ref.WD + ref.W1 + 64, ref.GRAD)):
+        ok, err = close(grads[a:b], grad_r[a:b], 1e-4); assert ok, f"{name} {err}"
+    # backward, part 2
+    dx_r = ref.layer_bwd_input(dpre_r, dout.double(), pk64, dilation, causal)
+    dx = torch.empty(T, 64, device=DEV)
+    ops.tcn_layer_bwd_input(dpre, dout.to(DEV), pk, dx, dilation, causal)
+    ok, err = close(dx, dx_r); assert ok, f"dx {err}"
+    # determinism of the partial sums
+    partials2 = torch.empty_like(partials)
+    ops.tcn_layer_bwd_hidden(dout.to(DEV), x.to(DEV), y, pk, dpre, partials2[0], n_slots, dilation, causal)
+    assert torch.equal(ops.tcn_reduce_grads(partials2, 1, n_slots)[0], grads)
+
+
+def test_layer_kernels_ragged(ops):
+    from multimodal_error_detection_b200 import tcn
+    lengths = [40, 9, 65, 16, 1]
+    T = sum(lengths)
+    tl, tr = tcn.ragged_geometry(lengths, DEV)
+    layer = _layer(9)
+    pack, _ = _pack_on_device(ops, [layer])
+    pk64 = ref.pack_layer(*[t.double() for t in layer])
+    g = torch.Generator().manual_seed(3)
+    x, dout = torch.randn(T, 64, generator=g), torch.randn(T, 64, generator=g)
+    for dilation, causal in ((4, True), (2, False), (32, True)):
+        out_r, y_r = ref.layer_fwd(x.double(), pk64, dilation, causal, tl.cpu(), tr.cpu())
+        out, y = torch.empty(T, 64, device=DEV), torch.empty(T, 64, device=DEV)
+        ops.tcn_layer_fwd(x.to(DEV), pack[0], out, y, dilation, causal, tloc=tl, trem=tr)
+        ok, err = close(out, out_r); assert ok, f"ragged out {err}"
+        dpre_r, _ = ref.layer_bwd_hidden(dout.double(), x.double(), y.cpu().double(), pk64, dilation, causal, tl.cpu(), tr.cpu())
+        dx_r = ref.layer_bwd_input(dpre_r, dout.double(), pk64, dilation, causal, tl.cpu(), tr.cpu())
+        dx = torch.empty(T, 64, device=DEV)
+        ops.tcn_layer_bwd_input(dpre_r.float().to(DEV), dout.to(DEV), pack[0], dx, dilation, causal, tloc=tl, trem=tr)
+        ok, err = close(dx, dx_r); assert ok, f"ragged dx {err}"
+
+
+def test_dropout_mask_is_shared_by_forward_and_backward(ops):
+    T, dilation, p = 200, 2, 0.5
+    layer = _layer(5)
+    pack, _ = _pack_on_device(ops, [layer])
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(T, 64, generator=g).to(DEV)
+    dout = torch.randn(T, 64, generator=g).to(DEV)
+    plain, y = torch.empty(T, 64, device=DEV), torch.empty(T, 64, device=DEV)
+    ops.tcn_layer_fwd(x, pack[0], plain, y, dilation, True)
+    z = plain - x                                           # conv_1x1(y) + b_1
+    dropped = torch.empty(T, 64, device=DEV)
+    ops.tcn_layer_fwd(x, pack[0], dropped, None, dilation, True, drop_p=p, seed=1234, drop_base=7 << 40)
+    kept = (dropped - x).abs() > 0
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.02, frac
+    ok, err = close((dropped - x)[kept], (z / (1 - p))[kept], 1e-5); assert ok, err
+    other = torch.empty(T, 64, device=DEV)
+    ops.tcn_layer_fwd(x, pack[0], other, None, dilation, True, drop_p=p, seed=1235, drop_base=7 << 40)
+    assert ((other - x).abs() > 0).ne(kept).float().mean().item() > 0.3       # a different seed draws a different mask
+    # backward with the same (seed, base): db_1 = sum_t dout * mask / (1 - p)
+    n_slots = ops.tcn_slots(T)
+    partials = torch.empty(1, n_slots, ops.TCN_GRAD_FLOATS, device=DEV)
+    dpre = torch.empty(T, 64, device=DEV)
+    ops.tcn_layer_bwd_hidden(dout, x, y, pack[0], dpre, partials[0], n_slots, dilation, True, drop_p=p, seed=1234,
+                             drop_base=7 << 40)
+    db1 = ops.tcn_reduce_grads(partials, 1, n_slots)[0][ref.WD + ref.W1 + 64:]
+    ok, err = close(db1, (dout * kept / (1 - p)).sum(0), 1e-4); assert ok, err
+
+
+@pytest.mark.parametrize("C", [2, 6])
+def test_stage_end_kernels(ops, C):
+    T = 301
+    g = torch.Generator().manual_seed(C)
+    x, w, b = torch.randn(T, 64, generator=g), torch.randn(C, 64, generator=g) * 0.2, torch.randn(C, generator=g)
+    logits = ops.tcn_out_fwd(x.to(DEV), w.to(DEV), b.to(DEV))
+    ok, err = close(logits, ref.out_fwd(x.double(), w.double(), b.double())); assert ok, err
+    dl = torch.randn(C, T, generator=g)
+    dx, dl_t = ops.tcn_out_bwd(dl.to(DEV), w.to(DEV))
+    dx_r, dl_t_r = ref.out_bwd(dl.double(), w.double())
+    ok, err = close(dx, dx_r); assert ok, err
+    assert torch.equal(dl_t.cpu(), dl.t().contiguous())
+    p = ops.tcn_softmax_fwd(logits)
+    ok, err = close(p, ref.softmax_fwd(logits.cpu().double())); assert ok, err
+    dp = torch.randn(T, C, generator=g)
+    dlog = ops.tcn_softmax_bwd(p, dp.to(DEV))
+    ok, err = close(dlog, ref.softmax_bwd(p.cpu().double(), dp.double())); assert ok, err
+
+
+def _models(causal, f_dim, layers=8):
+    from multimodal_error_detection_b200.modeling import models_TCN
+    torch.manual_seed(0)
+    o = nets.OracleTeCNo(2, layers, 64, f_dim, 2, causal).double()
+    m = models_TCN.MultiStageModel(2, layers, 64, f_dim, 2, causal)
+    m.load_state_dict({k: v.float() for k, v in o.state_dict().items()})
+    nets.disable_dropout(o)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return o.train(), m.to(DEV).train()
+
+
+@pytest.mark.parametrize("causal,f_dim,T", [(True, 58, 345), (False, 58, 150), (True, 2048, 410)])
+def test_model_matches_oracle(causal, f_dim, T):
+    o, m = _models(causal, f_dim)
+    g = torch.Generator().manual_seed(T)
+    base = torch.randn(1, T, f_dim, generator=g)
+    xo = base.double().requires_grad_(True)
+    xm = base.to(DEV).requires_grad_(True)
+    out_o = o(xo.permute(0, 2, 1))
+    out_m = m(xm.permute(0, 2, 1))
+    assert m.impl == "b200" and tuple(out_m.shape) == tuple(out_o.shape) == (2, 1, 2, T)
+    ok, err = close(out_m, out_o, 2e-5); assert ok, f"logits {err}"
+    w = torch.randn(out_o.shape, generator=g)
+    (out_o * w.double()).sum().backward()
+    (out_m * w.to(DEV)).sum().backward()
+    ok, err = close(xm.grad, xo.grad, 1e-4); assert ok, f"dx {err}"
+    po, pm = dict(o.named_parameters()), dict(m.named_parameters())
+    for k in po:
+        ok, err = close(pm[k].grad, po[k].grad, 2e-4); assert ok, f"{k} {err}"
+    # eval / no_grad form (ping-pong activations) gives the same logits
+    m.eval()
+    with torch.no_grad():
+        out_e = m(base.to(DEV).permute(0, 2, 1))
+    assert torch.equal(out_e, out_m.detach())
+
+
+def test_ragged_inference_equals_per_video():
+    _, m = _models(True, 58)
+    m.eval()
+    lengths = [300, 17, 451, 64, 5]
+    g = torch.Generator().manual_seed(1)
+    frames = torch.randn(sum(lengths), 58, generator=g).to(DEV)
+    cat = m.forward_ragged(frames, lengths)
+    parts, s = [], 0
+    with torch.no_grad():
+        for n in lengths:
+            parts.append(m(frames[s:s + n].unsqueeze(0).permute(0, 2, 1))[:, 0])
+            s += n
+    ok, err = close(cat, torch.cat(parts, dim=2), 1e-6); assert ok, err
+
+
+def test_train_mode_dropout_is_seeded():
+    _, m = _models(True, 58, layers=4)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.5
+    x = torch.randn(1, 58, 120, device=DEV)
+    torch.manual_seed(7); a = m(x)
+    torch.manual_seed(7); b = m(x)
+    c = m(x)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    a.sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())

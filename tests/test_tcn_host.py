@@ -1,0 +1,95 @@
+"""CPU tests of the TeCNo autograd node's host logic: the kernels are replaced by their torch definitions
+(tests/tcn_reference.py) and the node is compared with the oracle TeCNo (oracle/nets.py, pinned to the reference's
+models_TCN.py by tests/golden) -- forward, input gradient and every parameter gradient, causal and non-causal,
+one video and ragged batches."""
+import numpy as np
+import pytest
+import torch
+
+import tcn_reference as ref
+from multimodal_error_detection_b200 import tcn
+from multimodal_error_detection_b200.modeling import models_TCN
+from oracle import nets
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    monkeypatch.setattr(tcn, "ops", ref.EmulatedOps)
+    monkeypatch.setattr(tcn.StageConfig, "ptr_table", lambda self, layer_params: list(layer_params))
+    monkeypatch.setattr(tcn, "_check", lambda x, params: None)
+    monkeypatch.setattr(tcn, "require_cuda", lambda x: None)   # the emulation runs the same code path on host tensors
+
+
+def _pair(causal, f_dim=58, stages=2, layers=4):
+    torch.manual_seed(0)
+    o = nets.OracleTeCNo(stages, layers, 64, f_dim, 2, causal)
+    m = models_TCN.MultiStageModel(stages, layers, 64, f_dim, 2, causal)
+    m.load_state_dict(o.state_dict())
+    nets.disable_dropout(o)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return o.train(), m.train()
+
+
+@pytest.mark.parametrize("causal", [True, False])
+def test_stage_node_matches_oracle(emulated, causal):
+    o, m = _pair(causal)
+    T = 77
+    base = torch.randn(1, T, 58)
+    xo = base.clone().requires_grad_(True)
+    xm = base.clone().requires_grad_(True)
+    out_o = o(xo.permute(0, 2, 1))
+    out_m = m(xm.permute(0, 2, 1))
+    assert m.impl == "b200" and out_m.shape == out_o.shape == (2, 1, 2, T)
+    assert torch.allclose(out_m, out_o, rtol=1e-4, atol=1e-5)
+    w = torch.randn_like(out_o)
+    (out_o * w).sum().backward()
+    (out_m * w).sum().backward()
+    assert torch.allclose(xm.grad, xo.grad, rtol=1e-3, atol=1e-5)
+    po, pm = dict(o.named_parameters()), dict(m.named_parameters())
+    assert list(po) == list(pm)
+    for k in po:
+        scale = po[k].grad.abs().max().item() + 1e-12
+        assert (pm[k].grad - po[k].grad).abs().max().item() <= 2e-4 * scale, k
+
+
+def test_ragged_batch_equals_per_video(emulated):
+    _, m = _pair(True, layers=5)
+    m.eval()
+    lengths = [40, 9, 65]
+    frames = torch.randn(sum(lengths), 58)
+    with torch.no_grad():
+        cat = m.forward_ragged(frames, lengths)
+        parts, s = [], 0
+        for n in lengths:
+            parts.append(m(frames[s:s + n].unsqueeze(0).permute(0, 2, 1))[:, 0])
+            s += n
+    assert torch.allclose(cat, torch.cat(parts, dim=2), rtol=1e-5, atol=1e-6)
+
+
+def test_pack_and_grad_record_layouts():
+    torch.manual_seed(1)
+    wd, bd, w1, b1 = torch.randn(64, 64, 3), torch.randn(64), torch.randn(64, 64, 1), torch.randn(64)
+    p = ref.pack_layer(wd, bd, w1, b1)
+    assert p.numel() == ref.PACK == tcn.ops.TCN_PACK_FLOATS
+    k, ci, co = 2, 5, 17
+    assert p[ref.OFF_WDF + (k * 64 + ci) * 64 + co] == wd[co, ci, k]
+    assert p[ref.OFF_WDB + (k * 64 + co) * 64 + ci] == wd[co, ci, k]
+    assert p[ref.OFF_W1F + ci * 64 + co] == w1[co, ci, 0] and p[ref.OFF_W1B + co * 64 + ci] == w1[co, ci, 0]
+    assert p[ref.OFF_BIAS + co] == bd[co] and p[ref.OFF_BIAS + 64 + co] == b1[co]
+    assert ref.GRAD == tcn.ops.TCN_GRAD_FLOATS == 3 * 4096 + 4096 + 128
+
+
+def test_ragged_geometry():
+    tl, tr = tcn.ragged_geometry([3, 1, 2], "cpu")
+    assert tl.tolist() == [0, 1, 2, 0, 0, 1] and tr.tolist() == [2, 1, 0, 0, 1, 0]
+
+
+def test_unsupported_shape_uses_stock_layers_and_cpu_raises():
+    m = models_TCN.MultiStageModel(2, 3, 32, 10, 2, True).eval()     # 32 feature maps: not the specialised shape
+    out = m(torch.randn(1, 10, 20))
+    assert m.impl == "torch" and out.shape == (2, 1, 2, 20)
+    m64 = models_TCN.MultiStageModel(2, 3, 64, 10, 2, True).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m64(torch.randn(1, 10, 20))
