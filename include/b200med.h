@@ -312,6 +312,35 @@ int b200med_tcn_softmax_fwd(const float *logits, float *p, int64_t T, int32_t C,
 int b200med_tcn_softmax_bwd(const float *p, const float *dp, float *dlogits, int64_t T, int32_t C,
                             void *stream);
 
+/* One SingleStageModel.forward (models_TCN.py:92-100) in ONE call: [softmax over the previous stage's logits] ->
+ * 1x1 input convolution -> weight pack -> n_layers fused layers (dilation 2^l) -> class convolution.
+ *   x: [T, in_dim] frame rows, or the previous logits [C, T] when softmax_in (then p_in [T, C] OUT keeps the softmax);
+ *   in_w [64, in_dim], in_b [64], out_w [C, 64], out_b [C]: the Conv1d parameters as stored by torch;
+ *   layer_ptrs: as b200med_tcn_pack; drop_p_host: HOST array [n_layers] or NULL (eval);
+ *   dropout counter base of layer l = (layer_base + l) << 40;
+ *   keep = 1 (training): acts [n_layers+1][T][64] and ys [n_layers][T][64] OUT are kept for the backward;
+ *   keep = 0: acts [2][T][64] is a ping-pong pair, ys may be NULL;  pack [n_layers * B200MED_TCN_PACK_FLOATS] OUT;
+ *   logits [C, T] OUT.                                                                                      */
+int b200med_tcn_stage_fwd(const float *x, int32_t in_dim, int32_t softmax_in, const float *in_w,
+                          const float *in_b, const void *const *layer_ptrs, int32_t n_layers,
+                          const float *out_w, const float *out_b, int32_t C, int64_t T, int32_t causal,
+                          const int32_t *tloc, const int32_t *trem, const float *drop_p_host,
+                          uint64_t seed, uint64_t layer_base, int32_t keep, float *p_in, float *acts,
+                          float *ys, float *pack, float *logits, void *stream);
+/* The stage's backward in ONE call (autograd of the reference's layers).  xin = what the input convolution read
+ * (x, or p_in with softmax_in); acts / ys / pack: as left by b200med_tcn_stage_fwd(keep = 1);
+ * workspace >= b200med_tcn_stage_bwd_ws_bytes(), 256-byte aligned.  OUT: d_in_w [64, in_dim], d_in_b [64],
+ * layer_grads [n_layers][B200MED_TCN_GRAD_FLOATS], d_out_w [C, 64], d_out_b [C], and dx ([T, in_dim], or [C, T] with
+ * softmax_in; NULL = the input needs no gradient).  Deterministic.                                              */
+int64_t b200med_tcn_stage_bwd_ws_bytes(int64_t T, int32_t in_dim, int32_t C, int32_t n_layers);
+int b200med_tcn_stage_bwd(const float *dlogits, const float *xin, int32_t in_dim, int32_t softmax_in,
+                          const float *in_w, const float *out_w, int32_t C, int32_t n_layers, int64_t T,
+                          int32_t causal, const int32_t *tloc, const int32_t *trem,
+                          const float *drop_p_host, uint64_t seed, uint64_t layer_base, const float *acts,
+                          const float *ys, const float *pack, void *workspace, float *d_in_w,
+                          float *d_in_b, float *layer_grads, float *d_out_w, float *d_out_b, float *dx,
+                          void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimiser: Adam with coupled L2 decay, torch.optim.Adam semantics (modeling_utils.py:221-222)
  * ---------------------------------------------------------------------------------------------- */

@@ -555,3 +555,98 @@ TCN_API int b200med_tcn_softmax_bwd(const float *p, const float *dp, float *dlog
     tcn_softmax_bwd_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p, dp, dlogits, T, C);
     return after_launch("tcn_softmax_bwd_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------ whole stage, one call
+// The per-kernel entry points above cost one host round trip each (~100 per train step when driven from Python: the
+// step was launch-bound at 2.2 ms for 0.3 ms of kernels).  These two run a whole SingleStageModel forward / backward
+// from C: same kernels, same order, one call.
+
+static inline size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
+
+TCN_API int b200med_tcn_stage_fwd(const float *x, int32_t in_dim, int32_t softmax_in, const float *in_w, const float *in_b,
+                                  const void *const *layer_ptrs, int32_t n_layers, const float *out_w, const float *out_b,
+                                  int32_t C, int64_t T, int32_t causal, const int32_t *tloc, const int32_t *trem,
+                                  const float *drop_p_host, uint64_t seed, uint64_t layer_base, int32_t keep, float *p_in,
+                                  float *acts, float *ys, float *pack, float *logits, void *stream) {
+    B200MED_REQUIRE(T >= 1 && n_layers >= 1 && n_layers <= 30 && in_dim >= 1, "bad shape");
+    B200MED_REQUIRE(x && in_w && in_b && layer_ptrs && out_w && out_b && acts && pack && logits, "null pointer");
+    B200MED_REQUIRE(!keep || ys, "keep = 1 needs the y buffer");
+    B200MED_REQUIRE(!softmax_in || (p_in && in_dim == C), "softmax_in needs p_in and in_dim == C");
+    const float *xin = x;
+    if (softmax_in) {
+        if (int e = b200med_tcn_softmax_fwd(x, p_in, T, C, stream)) return e;
+        xin = p_in;
+    }
+    if (int e = b200med_linear_fwd_f32(xin, in_w, in_b, acts, T, kF, in_dim, 0, stream)) return e;
+    if (int e = b200med_tcn_pack(layer_ptrs, n_layers, pack, stream)) return e;
+    const size_t plane = (size_t)T * kF;
+    for (int l = 0; l < n_layers; ++l) {
+        const float *src = acts + (keep ? (size_t)l : (size_t)(l & 1)) * plane;
+        float *dst = acts + (keep ? (size_t)(l + 1) : (size_t)((l + 1) & 1)) * plane;
+        if (int e = b200med_tcn_layer_fwd(src, pack + (size_t)l * kPackFloats, dst, keep ? ys + (size_t)l * plane : nullptr, T,
+                                          1 << l, causal, tloc, trem, drop_p_host ? drop_p_host[l] : 0.f, seed,
+                                          (layer_base + (uint64_t)l) << 40, stream))
+            return e;
+    }
+    const float *last = acts + (keep ? (size_t)n_layers : (size_t)(n_layers & 1)) * plane;
+    return b200med_tcn_out_fwd(last, out_w, out_b, logits, T, C, stream);
+}
+
+TCN_API int64_t b200med_tcn_stage_bwd_ws_bytes(int64_t T, int32_t in_dim, int32_t C, int32_t n_layers) {
+    const int64_t slots = b200med_tcn_slots(T);
+    int64_t wg = b200med_linear_bwd_weight_ws_bytes(T, C, kF);
+    const int64_t wg2 = b200med_linear_bwd_weight_ws_bytes(T, kF, in_dim);
+    if (wg2 > wg) wg = wg2;
+    int64_t n = 0;
+    n += 3 * (int64_t)align_up((size_t)T * kF * 4, 256);                         // dA, spare, dpre
+    n += (int64_t)align_up((size_t)T * C * 4, 256);                              // dlogits^T
+    n += (int64_t)align_up((size_t)n_layers * slots * kGradFloats * 4, 256);     // weight-gradient partials
+    n += (int64_t)align_up((size_t)T * in_dim * 4, 256);                         // d(softmax output) before the softmax backward
+    n += (int64_t)align_up((size_t)wg, 256);
+    return n + 256;
+}
+
+// layer_grads [n_layers][B200MED_TCN_GRAD_FLOATS]; dx: [T, in_dim] (or [C, T] with softmax_in) or NULL when the input needs no gradient.
+TCN_API int b200med_tcn_stage_bwd(const float *dlogits, const float *xin, int32_t in_dim, int32_t softmax_in, const float *in_w,
+                                  const float *out_w, int32_t C, int32_t n_layers, int64_t T, int32_t causal,
+                                  const int32_t *tloc, const int32_t *trem, const float *drop_p_host, uint64_t seed,
+                                  uint64_t layer_base, const float *acts, const float *ys, const float *pack, void *workspace,
+                                  float *d_in_w, float *d_in_b, float *layer_grads, float *d_out_w, float *d_out_b, float *dx,
+                                  void *stream) {
+    B200MED_REQUIRE(T >= 1 && n_layers >= 1 && n_layers <= 30 && in_dim >= 1, "bad shape");
+    B200MED_REQUIRE(dlogits && xin && in_w && out_w && acts && ys && pack && workspace && d_in_w && d_in_b && layer_grads &&
+                    d_out_w && d_out_b, "null pointer");
+    B200MED_REQUIRE((uintptr_t)workspace % 256 == 0, "workspace must be 256-byte aligned");
+    const int slots = b200med_tcn_slots(T);
+    const size_t plane = (size_t)T * kF;
+    char *w = reinterpret_cast<char *>(workspace);
+    auto take = [&](size_t bytes) { char *p = w; w += align_up(bytes, 256); return p; };
+    float *dA = reinterpret_cast<float *>(take(plane * 4));
+    float *spare = reinterpret_cast<float *>(take(plane * 4));
+    float *dpre = reinterpret_cast<float *>(take(plane * 4));
+    float *dl_t = reinterpret_cast<float *>(take((size_t)T * C * 4));
+    float *partials = reinterpret_cast<float *>(take((size_t)n_layers * slots * kGradFloats * 4));
+    float *dxin = reinterpret_cast<float *>(take((size_t)T * in_dim * 4));
+    void *wg = w;
+    if (int e = b200med_tcn_out_bwd(dlogits, out_w, dA, dl_t, T, C, stream)) return e;
+    if (int e = b200med_linear_bwd_weight_f32(dl_t, acts + (size_t)n_layers * plane, d_out_w, d_out_b, T, C, kF, 0, wg, stream)) return e;
+    for (int l = n_layers - 1; l >= 0; --l) {
+        const float *pk = pack + (size_t)l * kPackFloats;
+        if (int e = b200med_tcn_layer_bwd_hidden(dA, acts + (size_t)l * plane, ys + (size_t)l * plane, pk, dpre,
+                                                 partials + (size_t)l * slots * kGradFloats, slots, T, 1 << l, causal, tloc, trem,
+                                                 drop_p_host ? drop_p_host[l] : 0.f, seed, (layer_base + (uint64_t)l) << 40, stream))
+            return e;
+        if (int e = b200med_tcn_layer_bwd_input(dpre, dA, pk, spare, T, 1 << l, causal, tloc, trem, stream)) return e;
+        float *t = dA; dA = spare; spare = t;
+    }
+    if (int e = b200med_tcn_reduce_grads(partials, n_layers, slots, layer_grads, stream)) return e;
+    if (int e = b200med_linear_bwd_weight_f32(dA, xin, d_in_w, d_in_b, T, kF, in_dim, 0, wg, stream)) return e;
+    if (dx) {
+        if (softmax_in) {
+            if (int e = b200med_linear_bwd_data_f32(dA, in_w, nullptr, dxin, T, kF, in_dim, stream)) return e;
+            return b200med_tcn_softmax_bwd(xin, dxin, dx, T, C, stream);
+        }
+        return b200med_linear_bwd_data_f32(dA, in_w, nullptr, dx, T, kF, in_dim, stream);
+    }
+    return B200MED_OK;
+}

@@ -435,3 +435,56 @@ def tcn_softmax_bwd(p, dp) -> torch.Tensor:
     dl = torch.empty(Cn, T, dtype=torch.float32, device=p.device)
     call("b200med_tcn_softmax_bwd", _ptr(p), _ptr(dp), _ptr(dl), T, Cn, _stream())
     return dl
+
+
+def _f32_array(values):
+    return None if values is None else (C.c_float * len(values))(*[float(v) for v in values])
+
+
+def tcn_stage_fwd(x, softmax_in, in_w, in_b, ptr_table, n_layers, out_w, out_b, causal, drop_p=None, seed=0, layer_base=0,
+                  keep=True, tloc=None, trem=None):
+    """Whole SingleStageModel forward in one C call -> dict(logits [C,T], xin, acts, ys, pack)."""
+    x = _need(x, torch.float32, "x")
+    in_w = _need(in_w, torch.float32, "in_w"); out_w = _need(out_w, torch.float32, "out_w")
+    n_cls, in_dim = out_w.shape[0], in_w.shape[1]
+    T = x.shape[1] if softmax_in else x.shape[0]
+    if (x.shape[0] if softmax_in else x.shape[1]) != in_dim:
+        raise ValueError(f"stage input has {x.shape[0] if softmax_in else x.shape[1]} features, conv_1x1 expects {in_dim}")
+    dev = x.device
+    p_in = torch.empty(T, n_cls, dtype=torch.float32, device=dev) if softmax_in else None
+    acts = torch.empty((n_layers + 1) if keep else 2, T, TCN_MAPS, dtype=torch.float32, device=dev)
+    ys = torch.empty(n_layers, T, TCN_MAPS, dtype=torch.float32, device=dev) if keep else None
+    pack = torch.empty(n_layers, TCN_PACK_FLOATS, dtype=torch.float32, device=dev)
+    logits = torch.empty(n_cls, T, dtype=torch.float32, device=dev)
+    tl, tr = _geom(tloc, trem)
+    if T:
+        call("b200med_tcn_stage_fwd", _ptr(x), in_dim, int(bool(softmax_in)), _ptr(in_w), _ptr(_need(in_b, torch.float32, "in_b")),
+             _ptr(_need(ptr_table, torch.int64, "ptr_table")), n_layers, _ptr(out_w), _ptr(_need(out_b, torch.float32, "out_b")),
+             n_cls, T, int(bool(causal)), tl, tr, _f32_array(drop_p), C.c_uint64(int(seed)), C.c_uint64(int(layer_base)),
+             int(bool(keep)), _ptr(p_in), _ptr(acts), _ptr(ys), _ptr(pack), _ptr(logits), _stream())
+    return dict(logits=logits, xin=p_in if softmax_in else x, acts=acts, ys=ys, pack=pack)
+
+
+def tcn_stage_bwd(dlogits, xin, softmax_in, in_w, out_w, n_layers, causal, acts, ys, pack, want_dx, drop_p=None, seed=0,
+                  layer_base=0, tloc=None, trem=None):
+    """Whole stage backward in one C call -> dict(dx, d_in_w [64,in_dim], d_in_b, layer_grads [L,GRAD], d_out_w [C,64], d_out_b)."""
+    dl = _need(dlogits, torch.float32, "dlogits")
+    n_cls, T = dl.shape
+    in_dim = in_w.shape[1]
+    dev = dl.device
+    d_in_w = torch.empty(TCN_MAPS, in_dim, dtype=torch.float32, device=dev)
+    d_in_b = torch.empty(TCN_MAPS, dtype=torch.float32, device=dev)
+    layer_grads = torch.empty(n_layers, TCN_GRAD_FLOATS, dtype=torch.float32, device=dev)
+    d_out_w = torch.empty(n_cls, TCN_MAPS, dtype=torch.float32, device=dev)
+    d_out_b = torch.empty(n_cls, dtype=torch.float32, device=dev)
+    dx = None
+    if want_dx:
+        dx = torch.empty((n_cls, T) if softmax_in else (T, in_dim), dtype=torch.float32, device=dev)
+    ws = workspace(_lib.load().b200med_tcn_stage_bwd_ws_bytes(T, in_dim, n_cls, n_layers), dev, "tcn_bwd")
+    tl, tr = _geom(tloc, trem)
+    call("b200med_tcn_stage_bwd", _ptr(dl), _ptr(_need(xin, torch.float32, "xin")), in_dim, int(bool(softmax_in)),
+         _ptr(_need(in_w, torch.float32, "in_w")), _ptr(_need(out_w, torch.float32, "out_w")), n_cls, n_layers, T,
+         int(bool(causal)), tl, tr, _f32_array(drop_p), C.c_uint64(int(seed)), C.c_uint64(int(layer_base)), _ptr(acts),
+         _ptr(ys), _ptr(pack), _ptr(ws), _ptr(d_in_w), _ptr(d_in_b), _ptr(layer_grads), _ptr(d_out_w), _ptr(d_out_b), _ptr(dx),
+         _stream())
+    return dict(dx=dx, d_in_w=d_in_w, d_in_b=d_in_b, layer_grads=layer_grads, d_out_w=d_out_w, d_out_b=d_out_b)

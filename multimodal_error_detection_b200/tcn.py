@@ -4,7 +4,9 @@ One autograd node per SingleStageModel (reference MED/modeling/models_TCN.py:76-
 (fp32 GEMM on the [T, F] frame rows) -> L fused DilatedResidualLayer launches -> 1x1 class convolution, with the
 inter-stage ``softmax(dim=1)`` (models_TCN.py:48) folded into the consuming stage.  Activations are time-major
 [T, 64]; the stage returns logits [C, T].  Backward = 2 launches per layer + one reduction of the weight-gradient
-partials per stage (deterministic).  There is no torch / cuDNN convolution on this path.
+partials per stage (deterministic).  There is no torch / cuDNN convolution on this path.  A stage forward / backward is
+ONE C call each (``b200med_tcn_stage_fwd`` / ``_bwd`` sequence the kernels in C: driven launch by launch from Python
+the step was host-bound, 2.2 ms for ~0.3 ms of kernels).
 """
 from __future__ import annotations
 
@@ -63,61 +65,30 @@ class TcnStageFunction(torch.autograd.Function):
         L = cfg.n_layers
         _check(x, params)
         in_w, in_b, out_w, out_b = params[0], params[1], params[-2], params[-1]
-        layer_params = params[2:2 + 4 * L]
-        x = x.detach().contiguous().float()
-        p_in = ops.tcn_softmax_fwd(x) if cfg.softmax_in else None
-        xin = p_in if cfg.softmax_in else x
-        T = xin.shape[0]
-        dev = x.device
         keep = any(ctx.needs_input_grad)
-        acts = torch.empty((L + 1) if keep else 2, T, MAPS, dtype=torch.float32, device=dev)
-        ys = torch.empty(L, T, MAPS, dtype=torch.float32, device=dev) if keep else None
-        ops.linear_fwd_f32(xin, in_w.detach().view(MAPS, -1), in_b.detach(), relu=False, out=acts[0])
-        pack = ops.tcn_pack(cfg.ptr_table(layer_params), L)
-        for l in range(L):
-            src, dst = (acts[l], acts[l + 1]) if keep else (acts[l & 1], acts[(l + 1) & 1])
-            ops.tcn_layer_fwd(src, pack[l], dst, None if ys is None else ys[l], 2 ** l, cfg.causal, cfg.drop_p[l], cfg.seed,
-                              (cfg.layer_base + l) << 40, cfg.tloc, cfg.trem)
-        last = acts[L] if keep else acts[L & 1]
-        n_cls = out_w.shape[0]
-        logits = ops.tcn_out_fwd(last, out_w.detach().view(n_cls, MAPS), out_b.detach())
+        r = ops.tcn_stage_fwd(x.detach().contiguous().float(), cfg.softmax_in, in_w.detach().view(MAPS, -1), in_b.detach(),
+                              cfg.ptr_table(params[2:2 + 4 * L]), L, out_w.detach().view(out_w.shape[0], MAPS), out_b.detach(),
+                              cfg.causal, cfg.drop_p, cfg.seed, cfg.layer_base, keep, cfg.tloc, cfg.trem)
         if keep:
-            ctx.cfg, ctx.geom = cfg, (list(cfg.drop_p), cfg.seed, cfg.tloc, cfg.trem)
-            ctx.save_for_backward(xin, acts, ys, pack, in_w, out_w)
-        return logits
+            ctx.cfg, ctx.geom = cfg, (list(cfg.drop_p), cfg.seed, cfg.layer_base, cfg.tloc, cfg.trem)
+            ctx.save_for_backward(r["xin"], r["acts"], r["ys"], r["pack"], in_w, out_w)
+        return r["logits"]
 
     @staticmethod
     def backward(ctx, dlogits):
         cfg = ctx.cfg
         L = cfg.n_layers
-        drop_p, seed, tloc, trem = ctx.geom
+        drop_p, seed, layer_base, tloc, trem = ctx.geom
         xin, acts, ys, pack, in_w, out_w = ctx.saved_tensors
-        T, dev = xin.shape[0], xin.device
-        n_cls = out_w.shape[0]
-        dA, dl_t = ops.tcn_out_bwd(dlogits.contiguous().float(), out_w.detach().view(n_cls, MAPS))
-        d_out_w, d_out_b = ops.linear_bwd_weight_f32(dl_t, acts[L])
-        n_slots = ops.tcn_slots(T)
-        partials = torch.empty(L, n_slots, ops.TCN_GRAD_FLOATS, dtype=torch.float32, device=dev)
-        dpre = torch.empty(T, MAPS, dtype=torch.float32, device=dev)
-        spare = torch.empty(T, MAPS, dtype=torch.float32, device=dev)
-        for l in reversed(range(L)):
-            ops.tcn_layer_bwd_hidden(dA, acts[l], ys[l], pack[l], dpre, partials[l], n_slots, 2 ** l, cfg.causal, drop_p[l],
-                                     seed, (cfg.layer_base + l) << 40, tloc, trem)
-            ops.tcn_layer_bwd_input(dpre, dA, pack[l], spare, 2 ** l, cfg.causal, tloc, trem)
-            dA, spare = spare, dA
-        grads = ops.tcn_reduce_grads(partials, L, n_slots)
-        d_in_w, d_in_b = ops.linear_bwd_weight_f32(dA, xin)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = ops.linear_bwd_data_f32(dA, in_w.detach().view(MAPS, -1))
-            if cfg.softmax_in:
-                dx = ops.tcn_softmax_bwd(xin, dx)
-        out = [dx, None, d_in_w.view_as(in_w), d_in_b]
+        r = ops.tcn_stage_bwd(dlogits.contiguous().float(), xin, cfg.softmax_in, in_w.detach().view(MAPS, -1),
+                              out_w.detach().view(out_w.shape[0], MAPS), L, cfg.causal, acts, ys, pack,
+                              ctx.needs_input_grad[0], drop_p, seed, layer_base, tloc, trem)
+        out = [r["dx"], None, r["d_in_w"].view_as(in_w), r["d_in_b"]]
         for l in range(L):
-            g = grads[l]
+            g = r["layer_grads"][l]
             out += [g[:_WD].view(MAPS, MAPS, 3), g[_WD + _W1:_WD + _W1 + MAPS], g[_WD:_WD + _W1].view(MAPS, MAPS, 1),
                     g[_WD + _W1 + MAPS:]]
-        out += [d_out_w.view_as(out_w), d_out_b]
+        out += [r["d_out_w"].view_as(out_w), r["d_out_b"]]
         return tuple(out)
 
 

@@ -138,3 +138,42 @@ class EmulatedOps:
     @staticmethod
     def linear_bwd_weight_f32(dy, x, want_bias=True):
         return dy.t() @ x, dy.sum(0)
+
+    # ---- whole-stage calls: the sequencing of b200med_tcn_stage_fwd / _bwd (csrc/tcn.cu), kernel by kernel
+    @classmethod
+    def tcn_stage_fwd(cls, x, softmax_in, in_w, in_b, params, n_layers, out_w, out_b, causal, drop_p=None, seed=0,
+                      layer_base=0, keep=True, tloc=None, trem=None):
+        assert not drop_p or max(drop_p) == 0.0
+        xin = softmax_fwd(x) if softmax_in else x
+        T = xin.shape[0]
+        acts = torch.empty(n_layers + 1 if keep else 2, T, MAPS, dtype=x.dtype)
+        ys = torch.empty(n_layers, T, MAPS, dtype=x.dtype) if keep else None
+        cls.linear_fwd_f32(xin, in_w, in_b, False, out=acts[0])
+        pack = cls.tcn_pack(params, n_layers)
+        for l in range(n_layers):
+            src, dst = (acts[l], acts[l + 1]) if keep else (acts[l & 1], acts[(l + 1) & 1])
+            cls.tcn_layer_fwd(src, pack[l], dst, ys[l] if keep else None, 2 ** l, causal, 0.0, seed, 0, tloc, trem)
+        last = acts[n_layers] if keep else acts[n_layers & 1]
+        return dict(logits=out_fwd(last, out_w, out_b), xin=xin, acts=acts, ys=ys, pack=pack)
+
+    @classmethod
+    def tcn_stage_bwd(cls, dlogits, xin, softmax_in, in_w, out_w, n_layers, causal, acts, ys, pack, want_dx, drop_p=None,
+                      seed=0, layer_base=0, tloc=None, trem=None):
+        T = xin.shape[0]
+        dA, dl_t = out_bwd(dlogits, out_w)
+        d_out_w, d_out_b = cls.linear_bwd_weight_f32(dl_t, acts[n_layers])
+        n_slots = cls.tcn_slots(T)
+        partials = torch.empty(n_layers, n_slots, GRAD, dtype=dlogits.dtype)
+        dpre, spare = torch.empty(T, MAPS, dtype=dlogits.dtype), torch.empty(T, MAPS, dtype=dlogits.dtype)
+        for l in reversed(range(n_layers)):
+            cls.tcn_layer_bwd_hidden(dA, acts[l], ys[l], pack[l], dpre, partials[l], n_slots, 2 ** l, causal, 0.0, seed, 0, tloc, trem)
+            cls.tcn_layer_bwd_input(dpre, dA, pack[l], spare, 2 ** l, causal, tloc, trem)
+            dA, spare = spare, dA
+        d_in_w, d_in_b = cls.linear_bwd_weight_f32(dA, xin)
+        dx = None
+        if want_dx:
+            dx = cls.linear_bwd_data_f32(dA, in_w)
+            if softmax_in:
+                dx = softmax_bwd(xin, dx)
+        return dict(dx=dx, d_in_w=d_in_w, d_in_b=d_in_b, layer_grads=cls.tcn_reduce_grads(partials, n_layers, n_slots),
+                    d_out_w=d_out_w, d_out_b=d_out_b)
