@@ -36,24 +36,42 @@ gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float 
     // loader mapping: when the reduction index is the contiguous one (cs == 1) let consecutive
     // threads walk r; otherwise let them walk the row index.
     const bool a_r_fast = (a_cs == 1), b_r_fast = (b_cs == 1);
-    for (long long r0 = r_begin; r0 < r_end; r0 += BK) {
+    // Register-staged software pipeline: the global loads of tile i+1 are in flight while tile i is multiplied (a GEMM with
+    // few CTAs -- the frame path's M = T ~ 600 rows -- is a chain of load latencies otherwise).  Summation order unchanged.
+    constexpr int LA = (BM * BK) / 256, LB = (BN * BK) / 256;
+    float ra[LA], rb[LB];
+    auto fetch = [&](long long r0) {
 #pragma unroll
-        for (int l = 0; l < (BM * BK) / 256; ++l) {
+        for (int l = 0; l < LA; ++l) {
             const int e = l * 256 + tid;
             const int rr = a_r_fast ? (e % BK) : (e / BM);
             const int ii = a_r_fast ? (e / BK) : (e % BM);
             const long long gi = i0 + ii, gr = r0 + rr;
-            As[rr][ii] = (gi < I && gr < r_end) ? __ldg(A + gi * a_rs + gr * a_cs) : 0.0f;
+            ra[l] = (gi < I && gr < r_end) ? __ldg(A + gi * a_rs + gr * a_cs) : 0.0f;
         }
 #pragma unroll
-        for (int l = 0; l < (BN * BK) / 256; ++l) {
+        for (int l = 0; l < LB; ++l) {
             const int e = l * 256 + tid;
             const int rr = b_r_fast ? (e % BK) : (e / BN);
             const int jj = b_r_fast ? (e / BK) : (e % BN);
             const long long gj = j0 + jj, gr = r0 + rr;
-            Bs[rr][jj] = (gj < J && gr < r_end) ? __ldg(B + gj * b_rs + gr * b_cs) : 0.0f;
+            rb[l] = (gj < J && gr < r_end) ? __ldg(B + gj * b_rs + gr * b_cs) : 0.0f;
+        }
+    };
+    if (r_begin < r_end) fetch(r_begin);
+    for (long long r0 = r_begin; r0 < r_end; r0 += BK) {
+#pragma unroll
+        for (int l = 0; l < LA; ++l) {
+            const int e = l * 256 + tid;
+            As[a_r_fast ? (e % BK) : (e / BM)][a_r_fast ? (e / BK) : (e % BM)] = ra[l];
+        }
+#pragma unroll
+        for (int l = 0; l < LB; ++l) {
+            const int e = l * 256 + tid;
+            Bs[b_r_fast ? (e % BK) : (e / BN)][b_r_fast ? (e / BK) : (e % BN)] = rb[l];
         }
         __syncthreads();
+        if (r0 + BK < r_end) fetch(r0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
@@ -187,15 +205,21 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16 *__restrict__ x, float 
         y[i] = __bfloat162float(x[i]);
 }
 
-static long long weight_slabs(long long M) {
-    // enough slabs to fill the GPU for the small [N,K] weight outputs, at least 1024 rows each
-    long long s = (M + 2047) / 2048;
+static long long weight_slabs(long long M, long long N, long long K) {
+    // Reduction slabs of the weight gradient dW[N,K] = dy^T x: enough CTAs (output tiles x slabs) for about two waves of
+    // the 148 SMs, never fewer than one slab per 2048 rows, never fewer than 32 rows per slab.  (One slab for M < 2048 --
+    // the first rule alone -- left the frame path's [64 x 64] gradients to ONE CTA walking all T rows: 84 us per launch.)
+    const long long tiles = ((N + BM - 1) / BM) * ((K + BN - 1) / BN);
+    long long s = (296 + tiles - 1) / tiles;
+    const long long by_rows = (M + 2047) / 2048, max_by_rows = (M + 31) / 32;
+    if (s < by_rows) s = by_rows;
+    if (s > max_by_rows) s = max_by_rows;
     if (s < 1) s = 1;
-    if (s > 64) s = 64;
+    if (s > 128) s = 128;
     return s;
 }
 static long long colsum_slabs(long long M) {
-    long long s = (M + 1023) / 1024;
+    long long s = (M + 63) / 64;     // >= 64 rows per slab
     if (s < 1) s = 1;
     if (s > 128) s = 128;
     return s;
@@ -234,7 +258,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_linear_bwd_data_f3
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t b200med_linear_bwd_weight_ws_bytes(int64_t M, int32_t N, int32_t K) {
-    const long long a = weight_slabs(M) * (long long)N * K * 4;
+    const long long a = weight_slabs(M, N, K) * (long long)N * K * 4;
     const long long b = colsum_slabs(M) * (long long)N * 4;
     return a + b + 256;
 }
@@ -245,7 +269,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_linear_bwd_weight_
     B200MED_REQUIRE(M >= 1 && N >= 1 && K >= 1, "bad shape");
     B200MED_REQUIRE(dy && x && dw && workspace, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int slabs = (int)weight_slabs(M);
+    const int slabs = (int)weight_slabs(M, N, K);
     float *part = reinterpret_cast<float *>(workspace);
     // dW[n,k] = sum_m dy[m,n] * x[m,k]:  A(i=n, r=m) = dy[m*N + n], B(j=k, r=m) = x[m*K + k]
     if (int e = launch_gemm(dy, x, part, N, K, M, 1, N, 1, K, K, nullptr, 0, nullptr, 0, slabs, (long long)N * K, st))

@@ -10,10 +10,14 @@
 // One DilatedResidualLayer = ONE launch (torch: conv, ReLU, slice, conv, dropout, add = 6):
 //   y   = relu(b_d + sum_k Wd[:, :, k] x[t + off_k])           off = {-2d, -d, 0} causal, {-d, 0, +d} otherwise
 //   out = x + dropout(b_1 + W1 y)
-// A CTA owns 16 consecutive frames and all 64 channels.  The layer's weights (48 KB + 16 KB, pre-transposed once per step
-// by tcn_pack_kernel so that the output channel is the contiguous index) arrive in shared memory by ONE cp.async.bulk
-// (TMA 1-D copy, mbarrier complete_tx) issued by thread 0 while all threads stage the three tap tiles with 128-bit loads;
-// each thread then owns a 2-frame x 4-channel register tile (LDS.128 for both operands, 32 FMA per 6 LDS.128).
+// A CTA (4 warps) owns TT = 4*RPW consecutive frames and all 64 channels.  The layer's weights (48 KB + 16 KB, pre-transposed
+// once per step by tcn_pack_kernel so that the output channel is the contiguous index) arrive in shared memory by ONE
+// cp.async.bulk (TMA 1-D copy, mbarrier complete_tx) issued by thread 0 while all threads stage the three tap tiles with
+// 128-bit loads.  A warp owns RPW frames; a lane owns 4 output channels (lane & 15) and HALF of the input channels
+// (lane >> 4), the two halves meet in one shuffle: with one video (T ~ 600) the kernel is a latency chain per thread, so
+// the chain is cut (RPW = 1: 150 CTAs, 512 FMA per thread) instead of the tile grown; long ragged batches use RPW = 4
+// (weights staged once per 16 frames).  First version (16 frames per CTA, 2 frames x 4 channels x all inputs per
+// thread): 38 CTAs, 25 % issue utilisation, 10 us per layer (profiles/r1_ncu_tcn.md).
 // Backward per layer = two launches:
 //   tcn_layer_bwd_hidden: dz = dout * mask, dpre = (dz W1) * (y > 0), and the layer's weight/bias gradient PARTIALS
 //                         (outer products of the 16-frame tiles, 144 register accumulators per thread, summed later in
@@ -26,8 +30,7 @@
 namespace b200med {
 
 constexpr int kF = 64;            // feature maps (mstcn_f_maps)
-constexpr int kTT = 16;           // frames per CTA tile
-constexpr int kTcnThreads = 128;  // 16 channel groups (4 channels) x 8 frame pairs
+constexpr int kTcnThreads = 128;  // 4 warps; a warp = RPW frames x (16 channel groups x 2 input-channel halves)
 constexpr int kWd = 3 * kF * kF;  // 12288
 constexpr int kW1 = kF * kF;      // 4096
 // pack of one layer (floats): WdF [k][ci][co] | W1F [ci][co] | WdB [k][co][ci] | W1B [co][ci] | b_d [64] | b_1 [64]
@@ -35,7 +38,7 @@ constexpr int kOffWdF = 0, kOffW1F = kWd, kOffWdB = kWd + kW1, kOffW1B = 2 * kWd
 constexpr int kPackFloats = kOffBias + 2 * kF;  // 32896 == B200MED_TCN_PACK_FLOATS
 // gradient record of one layer (floats): dWd [co][ci][k] | dW1 [co][ci] | db_d [64] | db_1 [64]  (torch parameter layouts)
 constexpr int kGradFloats = kWd + kW1 + 2 * kF;  // 16512 == B200MED_TCN_GRAD_FLOATS
-constexpr int kMaxSlots = 64;
+constexpr int kMaxSlots = 80;
 constexpr int kMaxClasses = 8;
 static_assert(kPackFloats == B200MED_TCN_PACK_FLOATS && kGradFloats == B200MED_TCN_GRAD_FLOATS, "header constants");
 
@@ -77,33 +80,47 @@ __device__ __forceinline__ void start_weight_copy(float *dst, const float *src, 
 }
 
 // xs[k][r][0..63] = src[t0 + r + sign*off_k][:] (zero where the tap leaves the video or the tile leaves the table).
+template <int TT>
 __device__ __forceinline__ void stage_taps(float *xs, const float *__restrict__ src, const TcnGeom &g, long long t0, int sign) {
-    for (int e = threadIdx.x; e < 3 * kTT * (kF / 4); e += kTcnThreads) {
-        const int k = e / (kTT * (kF / 4)), r = (e / (kF / 4)) % kTT, c4 = e % (kF / 4);
+    for (int e = threadIdx.x; e < 3 * TT * (kF / 4); e += kTcnThreads) {
+        const int k = e / (TT * (kF / 4)), r = (e / (kF / 4)) % TT, c4 = e % (kF / 4);
         const long long t = t0 + r;
         const int off = sign * g.off(k);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < g.T && tap_ok(g, t, off)) v = __ldg(reinterpret_cast<const float4 *>(src + (t + off) * kF) + c4);
-        *reinterpret_cast<float4 *>(xs + (k * kTT + r) * kF + c4 * 4) = v;
+        *reinterpret_cast<float4 *>(xs + (k * TT + r) * kF + c4 * 4) = v;
     }
 }
 
-// acc[j][c] += sum_i rowj[i] * w[i*64 + c],  i = 0..63; w already points at this thread's 4 output channels.
-__device__ __forceinline__ void mac_tile(float (&acc)[2][4], const float *row0, const float *row1, const float *w) {
-#pragma unroll 4
-    for (int i = 0; i < kF; i += 4) {
-        const float4 a = *reinterpret_cast<const float4 *>(row0 + i);
-        const float4 b = *reinterpret_cast<const float4 *>(row1 + i);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+// acc[j][c] += sum over this lane's half of i (32 of the 64 inputs) of rows[j][i] * w[i*64 + c]; w already points at the
+// lane's 4 output channels.  half_sum() adds the two halves (lanes l and l ^ 16): afterwards both hold the full sums.
+template <int RPW>
+__device__ __forceinline__ void mac_rows(float (&acc)[RPW][4], const float *rows, const float *w, int half) {
+#pragma unroll 2
+    for (int i = half * (kF / 2); i < (half + 1) * (kF / 2); i += 4) {
+        float xv[RPW][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 wv = *reinterpret_cast<const float4 *>(w + (i + j) * kF);
-            acc[0][0] = fmaf(av[j], wv.x, acc[0][0]); acc[0][1] = fmaf(av[j], wv.y, acc[0][1]);
-            acc[0][2] = fmaf(av[j], wv.z, acc[0][2]); acc[0][3] = fmaf(av[j], wv.w, acc[0][3]);
-            acc[1][0] = fmaf(bv[j], wv.x, acc[1][0]); acc[1][1] = fmaf(bv[j], wv.y, acc[1][1]);
-            acc[1][2] = fmaf(bv[j], wv.z, acc[1][2]); acc[1][3] = fmaf(bv[j], wv.w, acc[1][3]);
+        for (int j = 0; j < RPW; ++j) {
+            const float4 a = *reinterpret_cast<const float4 *>(rows + j * kF + i);
+            xv[j][0] = a.x; xv[j][1] = a.y; xv[j][2] = a.z; xv[j][3] = a.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w + (i + q) * kF);
+#pragma unroll
+            for (int j = 0; j < RPW; ++j) {
+                acc[j][0] = fmaf(xv[j][q], wv.x, acc[j][0]); acc[j][1] = fmaf(xv[j][q], wv.y, acc[j][1]);
+                acc[j][2] = fmaf(xv[j][q], wv.z, acc[j][2]); acc[j][3] = fmaf(xv[j][q], wv.w, acc[j][3]);
+            }
         }
     }
+}
+template <int RPW>
+__device__ __forceinline__ void half_sum(float (&acc)[RPW][4]) {
+#pragma unroll
+    for (int j = 0; j < RPW; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[j][c] += __shfl_xor_sync(0xffffffffu, acc[j][c], 16);
 }
 
 // ------------------------------------------------------------------------------------------------ weight pack
@@ -133,48 +150,54 @@ tcn_pack_kernel(const float *const *__restrict__ ptrs, float *__restrict__ packe
 }
 
 // ------------------------------------------------------------------------------------------------ layer forward
+template <int RPW>
 __global__ void __launch_bounds__(kTcnThreads)
 tcn_layer_fwd_kernel(const float *__restrict__ x, const float *__restrict__ pack, float *__restrict__ out,
                      float *__restrict__ y_save, TcnGeom g, float drop_p, unsigned long long seed,
                      unsigned long long drop_base) {
+    constexpr int TT = 4 * RPW;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
     float *ws = smem;                   // WdF | W1F : 16384 floats
-    float *xs = ws + kWd + kW1;         // [3][16][64]
-    float *ys = xs + 3 * kTT * kF;      // [16][64]
-    const long long t0 = (long long)blockIdx.x * kTT;
+    float *xs = ws + kWd + kW1;         // [3][TT][64]
+    float *ys = xs + 3 * TT * kF;       // [TT][64]
+    const long long t0 = (long long)blockIdx.x * TT;
     start_weight_copy(ws, pack + kOffWdF, (kWd + kW1) * 4, &bar);
-    stage_taps(xs, x, g, t0, +1);
+    stage_taps<TT>(xs, x, g, t0, +1);
     __syncthreads();
     bar_wait(&bar, 0);
 
-    const int cg = threadIdx.x & 15, tq = threadIdx.x >> 4, r0 = 2 * tq;
-    float acc[2][4] = {};
+    const int lane = threadIdx.x & 31, cg = lane & 15, half = lane >> 4, r0 = (threadIdx.x >> 5) * RPW;
+    float acc[RPW][4] = {};
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-        mac_tile(acc, xs + (k * kTT + r0) * kF, xs + (k * kTT + r0 + 1) * kF, ws + k * kW1 + cg * 4);
+    for (int k = 0; k < 3; ++k) mac_rows<RPW>(acc, xs + (k * TT + r0) * kF, ws + k * kW1 + cg * 4, half);
+    half_sum<RPW>(acc);
     const float4 bd = __ldg(reinterpret_cast<const float4 *>(pack + kOffBias) + cg);
     const float bdv[4] = {bd.x, bd.y, bd.z, bd.w};
+    if (half == 0) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        float4 y;
-        y.x = fmaxf(acc[j][0] + bdv[0], 0.f); y.y = fmaxf(acc[j][1] + bdv[1], 0.f);
-        y.z = fmaxf(acc[j][2] + bdv[2], 0.f); y.w = fmaxf(acc[j][3] + bdv[3], 0.f);
-        *reinterpret_cast<float4 *>(ys + (r0 + j) * kF + cg * 4) = y;
-        const long long t = t0 + r0 + j;
-        if (y_save && t < g.T) *reinterpret_cast<float4 *>(y_save + t * kF + cg * 4) = y;
+        for (int j = 0; j < RPW; ++j) {
+            float4 y;
+            y.x = fmaxf(acc[j][0] + bdv[0], 0.f); y.y = fmaxf(acc[j][1] + bdv[1], 0.f);
+            y.z = fmaxf(acc[j][2] + bdv[2], 0.f); y.w = fmaxf(acc[j][3] + bdv[3], 0.f);
+            *reinterpret_cast<float4 *>(ys + (r0 + j) * kF + cg * 4) = y;
+            const long long t = t0 + r0 + j;
+            if (y_save && t < g.T) *reinterpret_cast<float4 *>(y_save + t * kF + cg * 4) = y;
+        }
     }
-    __syncthreads();
-    float z[2][4] = {};
-    mac_tile(z, ys + r0 * kF, ys + (r0 + 1) * kF, ws + kWd + cg * 4);
+    __syncwarp();   // a warp only reads the y rows it wrote itself
+    float z[RPW][4] = {};
+    mac_rows<RPW>(z, ys + r0 * kF, ws + kWd + cg * 4, half);
+    half_sum<RPW>(z);
+    if (half != 0) return;
     const float4 b1 = __ldg(reinterpret_cast<const float4 *>(pack + kOffBias + kF) + cg);
     const float b1v[4] = {b1.x, b1.y, b1.z, b1.w};
     const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < RPW; ++j) {
         const long long t = t0 + r0 + j;
         if (t >= g.T) continue;
-        const float4 xc = *reinterpret_cast<const float4 *>(xs + (g.centre * kTT + r0 + j) * kF + cg * 4);
+        const float4 xc = *reinterpret_cast<const float4 *>(xs + (g.centre * TT + r0 + j) * kF + cg * 4);
         const float xv[4] = {xc.x, xc.y, xc.z, xc.w};
         float o[4];
 #pragma unroll
@@ -188,68 +211,73 @@ tcn_layer_fwd_kernel(const float *__restrict__ x, const float *__restrict__ pack
 }
 
 // ------------------------------------------------------------------------------------------------ layer backward (hidden)
-// Per 16-frame tile: dz = dout * dropout mask, dpre = (dz W1) * (y > 0) -> global; partial weight gradients of the tile
+// Per TT-frame tile: dz = dout * dropout mask, dpre = (dz W1) * (y > 0) -> global; partial weight gradients of the tile
 // accumulate in registers over the tiles this CTA (= slot) owns:
 //   dWd[co][ci][k] += dpre[t][co] x[t + off_k][ci],  dW1[co][ci] += dz[t][co] y[t][ci],  db_d += dpre[t],  db_1 += dz[t].
+template <int RPW>
 __global__ void __launch_bounds__(kTcnThreads)
 tcn_layer_bwd_hidden_kernel(const float *__restrict__ dout, const float *__restrict__ x, const float *__restrict__ y,
                             const float *__restrict__ pack, float *__restrict__ dpre, float *__restrict__ partials,
                             TcnGeom g, float drop_p, unsigned long long seed, unsigned long long drop_base) {
+    constexpr int TT = 4 * RPW;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
     float *w1b = smem;                  // [co][ci] 4096
-    float *xs = w1b + kW1;              // [3][16][64]
-    float *ys = xs + 3 * kTT * kF;      // [16][64]
-    float *dzs = ys + kTT * kF;         // [16][64]
-    float *dps = dzs + kTT * kF;        // [16][64]
+    float *xs = w1b + kW1;              // [3][TT][64]
+    float *ys = xs + 3 * TT * kF;       // [TT][64]
+    float *dzs = ys + TT * kF;          // [TT][64]
+    float *dps = dzs + TT * kF;         // [TT][64]
     start_weight_copy(w1b, pack + kOffW1B, kW1 * 4, &bar);
     __syncthreads();   // the barrier is initialised before any thread can reach a wait
 
-    const int cg = threadIdx.x & 15, tq = threadIdx.x >> 4, r0 = 2 * tq;
+    const int lane = threadIdx.x & 31, cg = lane & 15, half = lane >> 4, r0 = (threadIdx.x >> 5) * RPW;
     const int cog = threadIdx.x & 7, cig = threadIdx.x >> 3;   // weight-gradient tile: 8 co x (3 taps x 4 ci + 4 ci)
     float gD[8][3][4] = {}, g1[8][4] = {}, gbd[8] = {}, gb1[8] = {};
     const float scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
-    const long long ntiles = (g.T + kTT - 1) / kTT;
+    const long long ntiles = (g.T + TT - 1) / TT;
     bool first = true;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long t0 = tile * kTT;
-        stage_taps(xs, x, g, t0, +1);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const long long t = t0 + r0 + j;
+        const long long t0 = tile * TT;
+        stage_taps<TT>(xs, x, g, t0, +1);
+        for (int e = threadIdx.x; e < TT * (kF / 4); e += kTcnThreads) {
+            const int r = e / (kF / 4), c4 = e % (kF / 4);
+            const long long t = t0 + r;
             float4 d = make_float4(0.f, 0.f, 0.f, 0.f), yv = d;
             if (t < g.T) {
-                d = __ldg(reinterpret_cast<const float4 *>(dout + t * kF) + cg);
-                yv = __ldg(reinterpret_cast<const float4 *>(y + t * kF) + cg);
+                d = __ldg(reinterpret_cast<const float4 *>(dout + t * kF) + c4);
+                yv = __ldg(reinterpret_cast<const float4 *>(y + t * kF) + c4);
                 if (drop_p > 0.f) {
-                    const unsigned long long base = drop_base + (unsigned long long)(t * kF + cg * 4);
+                    const unsigned long long base = drop_base + (unsigned long long)(t * kF + c4 * 4);
                     d.x = tcn_keep(seed, base + 0, drop_p) ? d.x * scale : 0.f;
                     d.y = tcn_keep(seed, base + 1, drop_p) ? d.y * scale : 0.f;
                     d.z = tcn_keep(seed, base + 2, drop_p) ? d.z * scale : 0.f;
                     d.w = tcn_keep(seed, base + 3, drop_p) ? d.w * scale : 0.f;
                 }
             }
-            *reinterpret_cast<float4 *>(dzs + (r0 + j) * kF + cg * 4) = d;
-            *reinterpret_cast<float4 *>(ys + (r0 + j) * kF + cg * 4) = yv;
+            *reinterpret_cast<float4 *>(dzs + r * kF + c4 * 4) = d;
+            *reinterpret_cast<float4 *>(ys + r * kF + c4 * 4) = yv;
         }
         __syncthreads();
         if (first) { bar_wait(&bar, 0); first = false; }
-        float acc[2][4] = {};
-        mac_tile(acc, dzs + r0 * kF, dzs + (r0 + 1) * kF, w1b + cg * 4);
+        float acc[RPW][4] = {};
+        mac_rows<RPW>(acc, dzs + r0 * kF, w1b + cg * 4, half);
+        half_sum<RPW>(acc);
+        if (half == 0) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float4 yv = *reinterpret_cast<const float4 *>(ys + (r0 + j) * kF + cg * 4);
-            float4 p;
-            p.x = yv.x > 0.f ? acc[j][0] : 0.f; p.y = yv.y > 0.f ? acc[j][1] : 0.f;
-            p.z = yv.z > 0.f ? acc[j][2] : 0.f; p.w = yv.w > 0.f ? acc[j][3] : 0.f;
-            *reinterpret_cast<float4 *>(dps + (r0 + j) * kF + cg * 4) = p;
-            const long long t = t0 + r0 + j;
-            if (t < g.T) *reinterpret_cast<float4 *>(dpre + t * kF + cg * 4) = p;
+            for (int j = 0; j < RPW; ++j) {
+                const float4 yv = *reinterpret_cast<const float4 *>(ys + (r0 + j) * kF + cg * 4);
+                float4 p;
+                p.x = yv.x > 0.f ? acc[j][0] : 0.f; p.y = yv.y > 0.f ? acc[j][1] : 0.f;
+                p.z = yv.z > 0.f ? acc[j][2] : 0.f; p.w = yv.w > 0.f ? acc[j][3] : 0.f;
+                *reinterpret_cast<float4 *>(dps + (r0 + j) * kF + cg * 4) = p;
+                const long long t = t0 + r0 + j;
+                if (t < g.T) *reinterpret_cast<float4 *>(dpre + t * kF + cg * 4) = p;
+            }
         }
         __syncthreads();
         // weight-gradient partials of this tile (rows beyond T hold zeros in dzs / dps)
 #pragma unroll 2
-        for (int r = 0; r < kTT; ++r) {
+        for (int r = 0; r < TT; ++r) {
             const float4 p0 = *reinterpret_cast<const float4 *>(dps + r * kF + cog * 8);
             const float4 p1 = *reinterpret_cast<const float4 *>(dps + r * kF + cog * 8 + 4);
             const float4 z0 = *reinterpret_cast<const float4 *>(dzs + r * kF + cog * 8);
@@ -261,7 +289,7 @@ tcn_layer_bwd_hidden_kernel(const float *__restrict__ dout, const float *__restr
             float xv[3][4];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float4 t4 = *reinterpret_cast<const float4 *>(xs + (k * kTT + r) * kF + cig * 4);
+                const float4 t4 = *reinterpret_cast<const float4 *>(xs + (k * TT + r) * kF + cig * 4);
                 xv[k][0] = t4.x; xv[k][1] = t4.y; xv[k][2] = t4.z; xv[k][3] = t4.w;
             }
 #pragma unroll
@@ -310,25 +338,28 @@ tcn_reduce_grads_kernel(const float *__restrict__ partials, float *__restrict__ 
 
 // ------------------------------------------------------------------------------------------------ layer backward (input)
 // dx[t][ci] = dout[t][ci] + sum_k sum_co Wd[co][ci][k] dpre[t - off_k][co]
+template <int RPW>
 __global__ void __launch_bounds__(kTcnThreads)
 tcn_layer_bwd_input_kernel(const float *__restrict__ dpre, const float *__restrict__ dout, const float *__restrict__ pack,
                            float *__restrict__ dx, TcnGeom g) {
+    constexpr int TT = 4 * RPW;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
     float *ws = smem;             // WdB [k][co][ci]
     float *xs = ws + kWd;         // taps of dpre
-    const long long t0 = (long long)blockIdx.x * kTT;
+    const long long t0 = (long long)blockIdx.x * TT;
     start_weight_copy(ws, pack + kOffWdB, kWd * 4, &bar);
-    stage_taps(xs, dpre, g, t0, -1);
+    stage_taps<TT>(xs, dpre, g, t0, -1);
     __syncthreads();
     bar_wait(&bar, 0);
-    const int cg = threadIdx.x & 15, tq = threadIdx.x >> 4, r0 = 2 * tq;
-    float acc[2][4] = {};
+    const int lane = threadIdx.x & 31, cg = lane & 15, half = lane >> 4, r0 = (threadIdx.x >> 5) * RPW;
+    float acc[RPW][4] = {};
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-        mac_tile(acc, xs + (k * kTT + r0) * kF, xs + (k * kTT + r0 + 1) * kF, ws + k * kW1 + cg * 4);
+    for (int k = 0; k < 3; ++k) mac_rows<RPW>(acc, xs + (k * TT + r0) * kF, ws + k * kW1 + cg * 4, half);
+    half_sum<RPW>(acc);
+    if (half != 0) return;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < RPW; ++j) {
         const long long t = t0 + r0 + j;
         if (t >= g.T) continue;
         const float4 d = __ldg(reinterpret_cast<const float4 *>(dout + t * kF) + cg);
@@ -433,18 +464,36 @@ static int make_geom(TcnGeom &g, int64_t T, int32_t dilation, int32_t causal, co
     return 0;
 }
 
-constexpr size_t kSmemFwd = (size_t)(kWd + kW1 + 3 * kTT * kF + kTT * kF) * 4;     // 81920
-constexpr size_t kSmemBwdH = (size_t)(kW1 + 3 * kTT * kF + 3 * kTT * kF) * 4;      // 40960
-constexpr size_t kSmemBwdI = (size_t)(kWd + 3 * kTT * kF) * 4;                     // 61440
+constexpr size_t smem_fwd(int TT) { return (size_t)(kWd + kW1 + 3 * TT * kF + TT * kF) * 4; }    // 69.6 / 73.7 / 81.9 KB
+constexpr size_t smem_bwd_h(int TT) { return (size_t)(kW1 + 3 * TT * kF + 3 * TT * kF) * 4; }     // 22.5 / 28.7 / 41 KB
+constexpr size_t smem_bwd_i(int TT) { return (size_t)(kWd + 3 * TT * kF) * 4; }                   // 52.2 / 55.3 / 61.4 KB
 
-// > 48 KB of dynamic shared memory needs the opt-in; once per kernel and process (one device per process).
+// Frames per warp: cut the per-thread chain while the grid is small (one video), amortise the weight staging when it is
+// large (ragged batches): RPW = 1 up to two waves of 4-frame CTAs, then 2, then 4.
+static int pick_rpw(long long T) {
+    const long long two_waves = 2LL * num_sms();
+    if ((T + 3) / 4 <= two_waves) return 1;
+    if ((T + 7) / 8 <= two_waves) return 2;
+    return 4;
+}
+// The hidden backward keeps weight-gradient partials per CTA, so it wants few, longer CTAs: 8-frame tiles up to 80 slots.
+static int pick_rpw_hidden(long long T) { return (T + 7) / 8 <= kMaxSlots ? 2 : 4; }
+
+// > 48 KB of dynamic shared memory needs the opt-in; once per kernel and process (one device per process, DESIGN.md
+// section 5).  Keyed by the kernel's address: the RPW instantiations share one function-pointer TYPE.
 template <typename K>
 static int opt_in_smem(K kernel, size_t bytes) {
-    static bool done = false;   // one instantiation per kernel type
-    if (done) return B200MED_OK;
+    static std::atomic<const void *> done[16];
+    const void *key = reinterpret_cast<const void *>(kernel);
+    for (auto &d : done)
+        if (d.load(std::memory_order_acquire) == key) return B200MED_OK;
     const int e = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
                              "cudaFuncSetAttribute(tcn)");
-    done = e == B200MED_OK;
+    if (e == B200MED_OK)
+        for (auto &d : done) {
+            const void *expected = nullptr;
+            if (d.compare_exchange_strong(expected, key)) break;
+        }
     return e;
 }
 
@@ -454,7 +503,8 @@ using namespace b200med;
 #define TCN_API extern "C" __attribute__((visibility("default")))
 
 TCN_API int32_t b200med_tcn_slots(int64_t T) {
-    const long long tiles = (T + kTT - 1) / kTT;
+    const int tt = 4 * pick_rpw_hidden(T);
+    const long long tiles = (T + tt - 1) / tt;
     return (int32_t)(tiles < 1 ? 1 : (tiles < kMaxSlots ? tiles : kMaxSlots));
 }
 
@@ -477,9 +527,17 @@ TCN_API int b200med_tcn_layer_fwd(const float *x, const float *pack, float *out,
     B200MED_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)pack % 16 == 0 && (uintptr_t)out % 16 == 0 &&
                     (uintptr_t)y_save % 16 == 0, "pointers must be 16-byte aligned");
     TcnGeom g; make_geom(g, T, dilation, causal, tloc, trem);
-    if (int e = opt_in_smem(tcn_layer_fwd_kernel, kSmemFwd)) return e;
-    tcn_layer_fwd_kernel<<<(unsigned)((T + kTT - 1) / kTT), kTcnThreads, kSmemFwd, (cudaStream_t)stream>>>(
-        x, pack, out, y_save, g, drop_p, seed, drop_base);
+#define TCN_LAUNCH_FWD(R)                                                                                          \
+    {                                                                                                             \
+        if (int e = opt_in_smem(tcn_layer_fwd_kernel<R>, smem_fwd(4 * R))) return e;                              \
+        tcn_layer_fwd_kernel<R><<<(unsigned)((T + 4 * R - 1) / (4 * R)), kTcnThreads, smem_fwd(4 * R), (cudaStream_t)stream>>>( \
+            x, pack, out, y_save, g, drop_p, seed, drop_base);                                                    \
+    }
+    switch (pick_rpw(T)) {
+        case 1: TCN_LAUNCH_FWD(1) break;
+        case 2: TCN_LAUNCH_FWD(2) break;
+        default: TCN_LAUNCH_FWD(4) break;
+    }
     return after_launch("tcn_layer_fwd_kernel");
 }
 
@@ -493,9 +551,16 @@ TCN_API int b200med_tcn_layer_bwd_hidden(const float *dout, const float *x, cons
     B200MED_REQUIRE((uintptr_t)dout % 16 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)pack % 16 == 0 &&
                     (uintptr_t)dpre % 16 == 0, "pointers must be 16-byte aligned");
     TcnGeom g; make_geom(g, T, dilation, causal, tloc, trem);
-    if (int e = opt_in_smem(tcn_layer_bwd_hidden_kernel, kSmemBwdH)) return e;
-    tcn_layer_bwd_hidden_kernel<<<(unsigned)n_slots, kTcnThreads, kSmemBwdH, (cudaStream_t)stream>>>(
-        dout, x, y, pack, dpre, partials, g, drop_p, seed, drop_base);
+    B200MED_REQUIRE(n_slots <= b200med_tcn_slots(T), "n_slots must not exceed b200med_tcn_slots(T)");
+    if (pick_rpw_hidden(T) == 2) {
+        if (int e = opt_in_smem(tcn_layer_bwd_hidden_kernel<2>, smem_bwd_h(8))) return e;
+        tcn_layer_bwd_hidden_kernel<2><<<(unsigned)n_slots, kTcnThreads, smem_bwd_h(8), (cudaStream_t)stream>>>(
+            dout, x, y, pack, dpre, partials, g, drop_p, seed, drop_base);
+    } else {
+        if (int e = opt_in_smem(tcn_layer_bwd_hidden_kernel<4>, smem_bwd_h(16))) return e;
+        tcn_layer_bwd_hidden_kernel<4><<<(unsigned)n_slots, kTcnThreads, smem_bwd_h(16), (cudaStream_t)stream>>>(
+            dout, x, y, pack, dpre, partials, g, drop_p, seed, drop_base);
+    }
     return after_launch("tcn_layer_bwd_hidden_kernel");
 }
 
@@ -507,9 +572,17 @@ TCN_API int b200med_tcn_layer_bwd_input(const float *dpre, const float *dout, co
     B200MED_REQUIRE((uintptr_t)dpre % 16 == 0 && (uintptr_t)dout % 16 == 0 && (uintptr_t)pack % 16 == 0 && (uintptr_t)dx % 16 == 0,
                     "pointers must be 16-byte aligned");
     TcnGeom g; make_geom(g, T, dilation, causal, tloc, trem);
-    if (int e = opt_in_smem(tcn_layer_bwd_input_kernel, kSmemBwdI)) return e;
-    tcn_layer_bwd_input_kernel<<<(unsigned)((T + kTT - 1) / kTT), kTcnThreads, kSmemBwdI, (cudaStream_t)stream>>>(
-        dpre, dout, pack, dx, g);
+#define TCN_LAUNCH_BWD_I(R)                                                                                        \
+    {                                                                                                             \
+        if (int e = opt_in_smem(tcn_layer_bwd_input_kernel<R>, smem_bwd_i(4 * R))) return e;                      \
+        tcn_layer_bwd_input_kernel<R><<<(unsigned)((T + 4 * R - 1) / (4 * R)), kTcnThreads, smem_bwd_i(4 * R), (cudaStream_t)stream>>>( \
+            dpre, dout, pack, dx, g);                                                                             \
+    }
+    switch (pick_rpw(T)) {
+        case 1: TCN_LAUNCH_BWD_I(1) break;
+        case 2: TCN_LAUNCH_BWD_I(2) break;
+        default: TCN_LAUNCH_BWD_I(4) break;
+    }
     return after_launch("tcn_layer_bwd_input_kernel");
 }
 
