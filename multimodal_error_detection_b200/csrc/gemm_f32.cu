@@ -13,47 +13,52 @@
 
 namespace b200med {
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BM = 64, BN = 64, BK = 16;   // the large tile (TM = 4); TM = 2 gives 32 x 32 tiles
 
 // C[i,j] = sum_r A(i,r) * B(j,r)   with A(i,r) = A[i*a_rs + r*a_cs], B(j,r) = B[j*b_rs + r*b_cs].
 // Epilogue: + bias[j], ReLU, * (mask[i,j] > 0).  blockIdx.z = reduction slab (split-R), partial
 // results go to C + z*slab_stride when gridDim.z > 1.
+// TM = micro-tile edge per thread (16 x 16 threads): TM = 4 -> 64 x 64 CTA tiles, TM = 2 -> 32 x 32 tiles for problems
+// whose 64 x 64 grid would leave most SMs idle (the frame path's M = T ~ 600 rows).  Every output is the same ascending-r
+// FMA chain in both, so the tile choice does not change a single bit of the result.
+template <int TM>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ C,
                 long long I, long long J, long long R, long long a_rs, long long a_cs, long long b_rs,
                 long long b_cs, long long ldc, const float *__restrict__ bias, int relu,
                 const float *__restrict__ mask, long long ld_mask, long long r_per_slab,
                 long long slab_stride) {
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
+    constexpr int TB = 16 * TM;   // tile edge
+    __shared__ __align__(16) float As[BK][TB + 4];
+    __shared__ __align__(16) float Bs[BK][TB + 4];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each a 4x4 micro-tile
-    const long long i0 = (long long)blockIdx.y * BM, j0 = (long long)blockIdx.x * BN;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each a TM x TM micro-tile
+    const long long i0 = (long long)blockIdx.y * TB, j0 = (long long)blockIdx.x * TB;
     const long long r_begin = (long long)blockIdx.z * r_per_slab;
     const long long r_end = min(R, r_begin + r_per_slab);
 
-    float acc[4][4] = {};
+    float acc[TM][TM] = {};
     // loader mapping: when the reduction index is the contiguous one (cs == 1) let consecutive
     // threads walk r; otherwise let them walk the row index.
     const bool a_r_fast = (a_cs == 1), b_r_fast = (b_cs == 1);
     // Register-staged software pipeline: the global loads of tile i+1 are in flight while tile i is multiplied (a GEMM with
-    // few CTAs -- the frame path's M = T ~ 600 rows -- is a chain of load latencies otherwise).  Summation order unchanged.
-    constexpr int LA = (BM * BK) / 256, LB = (BN * BK) / 256;
-    float ra[LA], rb[LB];
+    // few CTAs is a chain of load latencies otherwise).  Summation order unchanged.
+    constexpr int LD = (TB * BK) / 256;
+    float ra[LD], rb[LD];
     auto fetch = [&](long long r0) {
 #pragma unroll
-        for (int l = 0; l < LA; ++l) {
+        for (int l = 0; l < LD; ++l) {
             const int e = l * 256 + tid;
-            const int rr = a_r_fast ? (e % BK) : (e / BM);
-            const int ii = a_r_fast ? (e / BK) : (e % BM);
+            const int rr = a_r_fast ? (e % BK) : (e / TB);
+            const int ii = a_r_fast ? (e / BK) : (e % TB);
             const long long gi = i0 + ii, gr = r0 + rr;
             ra[l] = (gi < I && gr < r_end) ? __ldg(A + gi * a_rs + gr * a_cs) : 0.0f;
         }
 #pragma unroll
-        for (int l = 0; l < LB; ++l) {
+        for (int l = 0; l < LD; ++l) {
             const int e = l * 256 + tid;
-            const int rr = b_r_fast ? (e % BK) : (e / BN);
-            const int jj = b_r_fast ? (e / BK) : (e % BN);
+            const int rr = b_r_fast ? (e % BK) : (e / TB);
+            const int jj = b_r_fast ? (e / BK) : (e % TB);
             const long long gj = j0 + jj, gr = r0 + rr;
             rb[l] = (gj < J && gr < r_end) ? __ldg(B + gj * b_rs + gr * b_cs) : 0.0f;
         }
@@ -61,37 +66,42 @@ gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float 
     if (r_begin < r_end) fetch(r_begin);
     for (long long r0 = r_begin; r0 < r_end; r0 += BK) {
 #pragma unroll
-        for (int l = 0; l < LA; ++l) {
+        for (int l = 0; l < LD; ++l) {
             const int e = l * 256 + tid;
-            As[a_r_fast ? (e % BK) : (e / BM)][a_r_fast ? (e / BK) : (e % BM)] = ra[l];
-        }
-#pragma unroll
-        for (int l = 0; l < LB; ++l) {
-            const int e = l * 256 + tid;
-            Bs[b_r_fast ? (e % BK) : (e / BN)][b_r_fast ? (e / BK) : (e % BN)] = rb[l];
+            As[a_r_fast ? (e % BK) : (e / TB)][a_r_fast ? (e / BK) : (e % TB)] = ra[l];
+            Bs[b_r_fast ? (e % BK) : (e / TB)][b_r_fast ? (e / BK) : (e % TB)] = rb[l];
         }
         __syncthreads();
         if (r0 + BK < r_end) fetch(r0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            float av[TM], bv[TM];
+            if constexpr (TM == 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+                av[0] = a.x; av[1] = a.y; av[2] = a.z; av[3] = a.w;
+                bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w;
+            } else {
+                const float2 a = *reinterpret_cast<const float2 *>(&As[k][ty * 2]);
+                const float2 b = *reinterpret_cast<const float2 *>(&Bs[k][tx * 2]);
+                av[0] = a.x; av[1] = a.y;
+                bv[0] = b.x; bv[1] = b.y;
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < TM; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+                for (int v = 0; v < TM; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
         }
         __syncthreads();
     }
     float *Cz = C + (long long)blockIdx.z * slab_stride;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const long long gi = i0 + ty * 4 + u;
+    for (int u = 0; u < TM; ++u) {
+        const long long gi = i0 + ty * TM + u;
         if (gi >= I) continue;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            const long long gj = j0 + tx * 4 + v;
+        for (int v = 0; v < TM; ++v) {
+            const long long gj = j0 + tx * TM + v;
             if (gj >= J) continue;
             float y = acc[u][v];
             if (bias) y += bias[gj];
@@ -233,10 +243,17 @@ static int launch_gemm(const float *A, const float *B, float *C, long long I, lo
                        long long a_rs, long long a_cs, long long b_rs, long long b_cs, long long ldc,
                        const float *bias, int relu, const float *mask, long long ld_mask, int slabs,
                        long long slab_stride, cudaStream_t st) {
-    dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + BM - 1) / BM), (unsigned)slabs);
     const long long per = ((R + slabs - 1) / slabs + BK - 1) / BK * BK;
-    gemm_f32_kernel<<<grid, 256, 0, st>>>(A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, relu, mask, ld_mask,
-                                           per, slab_stride);
+    const long long ctas64 = ((J + BN - 1) / BN) * ((I + BM - 1) / BM) * slabs;
+    if (ctas64 < num_sms()) {   // too few 64 x 64 tiles to fill the GPU: 32 x 32 tiles (4x the CTAs, identical results)
+        dim3 grid((unsigned)((J + 31) / 32), (unsigned)((I + 31) / 32), (unsigned)slabs);
+        gemm_f32_kernel<2><<<grid, 256, 0, st>>>(A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, relu, mask, ld_mask,
+                                                  per, slab_stride);
+    } else {
+        dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + BM - 1) / BM), (unsigned)slabs);
+        gemm_f32_kernel<4><<<grid, 256, 0, st>>>(A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, relu, mask, ld_mask,
+                                                  per, slab_stride);
+    }
     return after_launch("gemm_f32_kernel");
 }
 
