@@ -281,18 +281,20 @@ int b200med_tcn_pack(const void *const *param_ptrs, int32_t n_layers, float *pac
  *   y = relu(conv_dilated(x)) (causal: taps t-2d, t-d, t == the reference's pad-and-slice; else t-d, t, t+d),
  *   out = x + dropout(conv_1x1(y)).   x, out [T,64]; y_save [T,64] OUT or NULL (kept for the backward);
  *   pack = this layer's record of b200med_tcn_pack.  Dropout: counter-based mask keyed by (seed, drop_base + t*64 + c),
- *   drop_p = 0 in eval mode.                                                                                */
+ *   drop_p = 0 in eval mode; seed_dev (DEVICE scalar or NULL) is added to seed on the device, so a step replayed from a
+ *   CUDA graph draws a fresh mask when the caller advances that scalar.                                      */
 int b200med_tcn_layer_fwd(const float *x, const float *pack, float *out, float *y_save, int64_t T,
                           int32_t dilation, int32_t causal, const int32_t *tloc, const int32_t *trem,
-                          float drop_p, uint64_t seed, uint64_t drop_base, void *stream);
+                          float drop_p, uint64_t seed, const uint64_t *seed_dev, uint64_t drop_base,
+                          void *stream);
 /* Backward of the layer, part 1: dz = dout * mask, dpre [T,64] OUT = (dz W1) * (y > 0), and the partial
  * weight / bias gradients of the layer: partials [n_slots][B200MED_TCN_GRAD_FLOATS] OUT (n_slots =
  * b200med_tcn_slots(T)), summed by b200med_tcn_reduce_grads.  x = the layer's input, y = its y_save.       */
 int b200med_tcn_layer_bwd_hidden(const float *dout, const float *x, const float *y, const float *pack,
                                  float *dpre, float *partials, int32_t n_slots, int64_t T,
                                  int32_t dilation, int32_t causal, const int32_t *tloc,
-                                 const int32_t *trem, float drop_p, uint64_t seed, uint64_t drop_base,
-                                 void *stream);
+                                 const int32_t *trem, float drop_p, uint64_t seed, const uint64_t *seed_dev,
+                                 uint64_t drop_base, void *stream);
 /* Backward of the layer, part 2: dx [T,64] = dout + conv_dilated^T(dpre).                                  */
 int b200med_tcn_layer_bwd_input(const float *dpre, const float *dout, const float *pack, float *dx,
                                 int64_t T, int32_t dilation, int32_t causal, const int32_t *tloc,
@@ -325,8 +327,8 @@ int b200med_tcn_stage_fwd(const float *x, int32_t in_dim, int32_t softmax_in, co
                           const float *in_b, const void *const *layer_ptrs, int32_t n_layers,
                           const float *out_w, const float *out_b, int32_t C, int64_t T, int32_t causal,
                           const int32_t *tloc, const int32_t *trem, const float *drop_p_host,
-                          uint64_t seed, uint64_t layer_base, int32_t keep, float *p_in, float *acts,
-                          float *ys, float *pack, float *logits, void *stream);
+                          uint64_t seed, const uint64_t *seed_dev, uint64_t layer_base, int32_t keep,
+                          float *p_in, float *acts, float *ys, float *pack, float *logits, void *stream);
 /* The stage's backward in ONE call (autograd of the reference's layers).  xin = what the input convolution read
  * (x, or p_in with softmax_in); acts / ys / pack: as left by b200med_tcn_stage_fwd(keep = 1);
  * workspace >= b200med_tcn_stage_bwd_ws_bytes(), 256-byte aligned.  OUT: d_in_w [64, in_dim], d_in_b [64],
@@ -336,8 +338,9 @@ int64_t b200med_tcn_stage_bwd_ws_bytes(int64_t T, int32_t in_dim, int32_t C, int
 int b200med_tcn_stage_bwd(const float *dlogits, const float *xin, int32_t in_dim, int32_t softmax_in,
                           const float *in_w, const float *out_w, int32_t C, int32_t n_layers, int64_t T,
                           int32_t causal, const int32_t *tloc, const int32_t *trem,
-                          const float *drop_p_host, uint64_t seed, uint64_t layer_base, const float *acts,
-                          const float *ys, const float *pack, void *workspace, float *d_in_w,
+                          const float *drop_p_host, uint64_t seed, const uint64_t *seed_dev,
+                          uint64_t layer_base, const float *acts, const float *ys, const float *pack,
+                          void *workspace, float *d_in_w,
                           float *d_in_b, float *layer_grads, float *d_out_w, float *d_out_b, float *dx,
                           void *stream);
 

@@ -61,8 +61,8 @@ SIGNATURES = {
     "b200med_ce_frame": (C.c_int, [_p, _p, _i32, _i64, _f, _p, _p, _p, _p, _i32, _p, _p]),
     "b200med_tcn_slots": (_i32, [_i64]),
     "b200med_tcn_pack": (C.c_int, [_p, _i32, _p, _p]),
-    "b200med_tcn_layer_fwd": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _f, C.c_uint64, C.c_uint64, _p]),
-    "b200med_tcn_layer_bwd_hidden": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _f, C.c_uint64,
+    "b200med_tcn_layer_fwd": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _f, C.c_uint64, _p, C.c_uint64, _p]),
+    "b200med_tcn_layer_bwd_hidden": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i64, _i32, _i32, _p, _p, _f, C.c_uint64, _p,
                                                C.c_uint64, _p]),
     "b200med_tcn_layer_bwd_input": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "b200med_tcn_reduce_grads": (C.c_int, [_p, _i32, _i32, _p, _p]),
@@ -70,11 +70,11 @@ SIGNATURES = {
     "b200med_tcn_out_bwd": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _p]),
     "b200med_tcn_softmax_fwd": (C.c_int, [_p, _p, _i64, _i32, _p]),
     "b200med_tcn_softmax_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
-    "b200med_tcn_stage_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _i64, _i32, _p, _p, _p, C.c_uint64,
+    "b200med_tcn_stage_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _i64, _i32, _p, _p, _p, C.c_uint64, _p,
                                         C.c_uint64, _i32, _p, _p, _p, _p, _p, _p]),
     "b200med_tcn_stage_bwd_ws_bytes": (_i64, [_i64, _i32, _i32, _i32]),
-    "b200med_tcn_stage_bwd": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _i32, _i32, _i64, _i32, _p, _p, _p, C.c_uint64, C.c_uint64,
-                                        _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200med_tcn_stage_bwd": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _i32, _i32, _i64, _i32, _p, _p, _p, C.c_uint64, _p,
+                                        C.c_uint64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200med_adam_advance": (C.c_int, [_p, _f, _f, _p]),
     "b200med_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p]),
     "b200med_window_vote": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p]),

@@ -154,8 +154,9 @@ template <int RPW>
 __global__ void __launch_bounds__(kTcnThreads)
 tcn_layer_fwd_kernel(const float *__restrict__ x, const float *__restrict__ pack, float *__restrict__ out,
                      float *__restrict__ y_save, TcnGeom g, float drop_p, unsigned long long seed,
-                     unsigned long long drop_base) {
+                     const unsigned long long *__restrict__ seed_dev, unsigned long long drop_base) {
     constexpr int TT = 4 * RPW;
+    if (seed_dev) seed += *seed_dev;   // per-step counter in device memory: a replayed CUDA graph draws a fresh mask
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
     float *ws = smem;                   // WdF | W1F : 16384 floats
@@ -218,8 +219,10 @@ template <int RPW>
 __global__ void __launch_bounds__(kTcnThreads)
 tcn_layer_bwd_hidden_kernel(const float *__restrict__ dout, const float *__restrict__ x, const float *__restrict__ y,
                             const float *__restrict__ pack, float *__restrict__ dpre, float *__restrict__ partials,
-                            TcnGeom g, float drop_p, unsigned long long seed, unsigned long long drop_base) {
+                            TcnGeom g, float drop_p, unsigned long long seed,
+                            const unsigned long long *__restrict__ seed_dev, unsigned long long drop_base) {
     constexpr int TT = 4 * RPW;
+    if (seed_dev) seed += *seed_dev;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
     float *w1b = smem;                  // [co][ci] 4096
@@ -519,7 +522,7 @@ TCN_API int b200med_tcn_pack(const void *const *param_ptrs, int32_t n_layers, fl
 
 TCN_API int b200med_tcn_layer_fwd(const float *x, const float *pack, float *out, float *y_save, int64_t T, int32_t dilation,
                                   int32_t causal, const int32_t *tloc, const int32_t *trem, float drop_p, uint64_t seed,
-                                  uint64_t drop_base, void *stream) {
+                                  const uint64_t *seed_dev, uint64_t drop_base, void *stream) {
     B200MED_REQUIRE(T >= 0 && dilation >= 1, "bad shape");
     B200MED_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability must be in [0, 1)");
     if (T == 0) return B200MED_OK;
@@ -531,7 +534,7 @@ TCN_API int b200med_tcn_layer_fwd(const float *x, const float *pack, float *out,
     {                                                                                                             \
         if (int e = opt_in_smem(tcn_layer_fwd_kernel<R>, smem_fwd(4 * R))) return e;                              \
         tcn_layer_fwd_kernel<R><<<(unsigned)((T + 4 * R - 1) / (4 * R)), kTcnThreads, smem_fwd(4 * R), (cudaStream_t)stream>>>( \
-            x, pack, out, y_save, g, drop_p, seed, drop_base);                                                    \
+            x, pack, out, y_save, g, drop_p, seed, reinterpret_cast<const unsigned long long *>(seed_dev), drop_base); \
     }
     switch (pick_rpw(T)) {
         case 1: TCN_LAUNCH_FWD(1) break;
@@ -544,7 +547,7 @@ TCN_API int b200med_tcn_layer_fwd(const float *x, const float *pack, float *out,
 TCN_API int b200med_tcn_layer_bwd_hidden(const float *dout, const float *x, const float *y, const float *pack, float *dpre,
                                          float *partials, int32_t n_slots, int64_t T, int32_t dilation, int32_t causal,
                                          const int32_t *tloc, const int32_t *trem, float drop_p, uint64_t seed,
-                                         uint64_t drop_base, void *stream) {
+                                         const uint64_t *seed_dev, uint64_t drop_base, void *stream) {
     B200MED_REQUIRE(T >= 1 && dilation >= 1 && n_slots >= 1, "bad shape");
     B200MED_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout probability must be in [0, 1)");
     B200MED_REQUIRE(dout && x && y && pack && dpre && partials, "null pointer");
@@ -555,11 +558,11 @@ TCN_API int b200med_tcn_layer_bwd_hidden(const float *dout, const float *x, cons
     if (pick_rpw_hidden(T) == 2) {
         if (int e = opt_in_smem(tcn_layer_bwd_hidden_kernel<2>, smem_bwd_h(8))) return e;
         tcn_layer_bwd_hidden_kernel<2><<<(unsigned)n_slots, kTcnThreads, smem_bwd_h(8), (cudaStream_t)stream>>>(
-            dout, x, y, pack, dpre, partials, g, drop_p, seed, drop_base);
+            dout, x, y, pack, dpre, partials, g, drop_p, seed, reinterpret_cast<const unsigned long long *>(seed_dev), drop_base);
     } else {
         if (int e = opt_in_smem(tcn_layer_bwd_hidden_kernel<4>, smem_bwd_h(16))) return e;
         tcn_layer_bwd_hidden_kernel<4><<<(unsigned)n_slots, kTcnThreads, smem_bwd_h(16), (cudaStream_t)stream>>>(
-            dout, x, y, pack, dpre, partials, g, drop_p, seed, drop_base);
+            dout, x, y, pack, dpre, partials, g, drop_p, seed, reinterpret_cast<const unsigned long long *>(seed_dev), drop_base);
     }
     return after_launch("tcn_layer_bwd_hidden_kernel");
 }
@@ -639,8 +642,8 @@ static inline size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; 
 TCN_API int b200med_tcn_stage_fwd(const float *x, int32_t in_dim, int32_t softmax_in, const float *in_w, const float *in_b,
                                   const void *const *layer_ptrs, int32_t n_layers, const float *out_w, const float *out_b,
                                   int32_t C, int64_t T, int32_t causal, const int32_t *tloc, const int32_t *trem,
-                                  const float *drop_p_host, uint64_t seed, uint64_t layer_base, int32_t keep, float *p_in,
-                                  float *acts, float *ys, float *pack, float *logits, void *stream) {
+                                  const float *drop_p_host, uint64_t seed, const uint64_t *seed_dev, uint64_t layer_base,
+                                  int32_t keep, float *p_in, float *acts, float *ys, float *pack, float *logits, void *stream) {
     B200MED_REQUIRE(T >= 1 && n_layers >= 1 && n_layers <= 30 && in_dim >= 1, "bad shape");
     B200MED_REQUIRE(x && in_w && in_b && layer_ptrs && out_w && out_b && acts && pack && logits, "null pointer");
     B200MED_REQUIRE(!keep || ys, "keep = 1 needs the y buffer");
@@ -657,7 +660,7 @@ TCN_API int b200med_tcn_stage_fwd(const float *x, int32_t in_dim, int32_t softma
         const float *src = acts + (keep ? (size_t)l : (size_t)(l & 1)) * plane;
         float *dst = acts + (keep ? (size_t)(l + 1) : (size_t)((l + 1) & 1)) * plane;
         if (int e = b200med_tcn_layer_fwd(src, pack + (size_t)l * kPackFloats, dst, keep ? ys + (size_t)l * plane : nullptr, T,
-                                          1 << l, causal, tloc, trem, drop_p_host ? drop_p_host[l] : 0.f, seed,
+                                          1 << l, causal, tloc, trem, drop_p_host ? drop_p_host[l] : 0.f, seed, seed_dev,
                                           (layer_base + (uint64_t)l) << 40, stream))
             return e;
     }
@@ -683,7 +686,8 @@ TCN_API int64_t b200med_tcn_stage_bwd_ws_bytes(int64_t T, int32_t in_dim, int32_
 TCN_API int b200med_tcn_stage_bwd(const float *dlogits, const float *xin, int32_t in_dim, int32_t softmax_in, const float *in_w,
                                   const float *out_w, int32_t C, int32_t n_layers, int64_t T, int32_t causal,
                                   const int32_t *tloc, const int32_t *trem, const float *drop_p_host, uint64_t seed,
-                                  uint64_t layer_base, const float *acts, const float *ys, const float *pack, void *workspace,
+                                  const uint64_t *seed_dev, uint64_t layer_base, const float *acts, const float *ys,
+                                  const float *pack, void *workspace,
                                   float *d_in_w, float *d_in_b, float *layer_grads, float *d_out_w, float *d_out_b, float *dx,
                                   void *stream) {
     B200MED_REQUIRE(T >= 1 && n_layers >= 1 && n_layers <= 30 && in_dim >= 1, "bad shape");
@@ -707,7 +711,8 @@ TCN_API int b200med_tcn_stage_bwd(const float *dlogits, const float *xin, int32_
         const float *pk = pack + (size_t)l * kPackFloats;
         if (int e = b200med_tcn_layer_bwd_hidden(dA, acts + (size_t)l * plane, ys + (size_t)l * plane, pk, dpre,
                                                  partials + (size_t)l * slots * kGradFloats, slots, T, 1 << l, causal, tloc, trem,
-                                                 drop_p_host ? drop_p_host[l] : 0.f, seed, (layer_base + (uint64_t)l) << 40, stream))
+                                                 drop_p_host ? drop_p_host[l] : 0.f, seed, seed_dev,
+                                                 (layer_base + (uint64_t)l) << 40, stream))
             return e;
         if (int e = b200med_tcn_layer_bwd_input(dpre, dA, pk, spare, T, 1 << l, causal, tloc, trem, stream)) return e;
         float *t = dA; dA = spare; spare = t;

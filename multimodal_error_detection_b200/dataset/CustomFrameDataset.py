@@ -111,9 +111,14 @@ class FrameLoader:
     def __len__(self):
         return len(self._order)
 
-    def __iter__(self):
+    def indices(self):
+        """This rank's video indices in the order of one pass (advances the sampler's generator like a pass does)."""
         for k, i in enumerate(self._order):
             if self.world_size > 1 and k % self.world_size != self.rank:
                 continue
+            yield i
+
+    def __iter__(self):
+        for i in self.indices():
             images, kin, g, e7, subject, skill = self.dataset[i]
             yield images.unsqueeze(0), kin.unsqueeze(0), g.unsqueeze(0), e7.unsqueeze(0), (subject,), skill.unsqueeze(0)

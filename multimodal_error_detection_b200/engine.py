@@ -190,3 +190,93 @@ class WindowTrainStep:
             self.parity = 1 - cur
             self._primed = next_idx is not None
         return self.loss
+
+
+class _TrainState:
+    """Snapshot / restore of everything a train step mutates (flat parameters, Adam moments and step scalars, module
+    buffers): the warm-up steps that precede a graph capture are real optimiser steps and must leave no trace."""
+
+    def __init__(self, optimizer, modules):
+        optimizer._refresh_active()
+        self.opt = optimizer
+        self.bufs = [b for m in modules if m is not None for b in m.buffers()]
+        self.snap = [t.clone() for c in optimizer.chunks for t in (c.param, c.exp_avg, c.exp_avg_sq)] + [optimizer.state_dev.clone()]
+        self.snap_bufs = [b.clone() for b in self.bufs]
+
+    def restore(self):
+        with torch.no_grad():
+            it = iter(self.snap)
+            for c in self.opt.chunks:
+                for t in (c.param, c.exp_avg, c.exp_avg_sq):
+                    t.copy_(next(it))
+            self.opt.state_dev.copy_(next(it))
+            for b, sb in zip(self.bufs, self.snap_bufs):
+                b.copy_(sb)
+        self.opt._lr_on_device = None      # the device-side lr was part of the restored state: push it again on the next run
+
+
+class FrameTrainStep:
+    """One frame-classifier train step on ONE video (what ``train_single_epoch`` does per DataLoader(batch_size=1) item,
+    reference MED/modeling/modeling_utils.py:335-366) captured in a CUDA graph.  The video's tensors are resident
+    (CustomFrameDataset caches them on the device), so the graph reads them in place: a replay has NO input.  A step is
+    ~100 short kernels (0.9 ms of device time under ncu) that take 2.3 ms when launched one by one from Python; every
+    video of a fold keeps its own graph (its T is baked into the grids), all graphs share one memory pool -- they never
+    run concurrently -- and are replayed once per epoch."""
+
+    def __init__(self, images, kin, e7, feature_extractor, model, criterion, optimizer, exp_kwargs: dict, pool=None):
+        self.images, self.kin, self.e7 = images, kin, e7
+        self.fe, self.model, self.crit, self.opt, self.kw = feature_extractor, model, criterion, optimizer, exp_kwargs
+        dev = images.device
+        self.device = dev
+        T = images.shape[1]
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.counts = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.preds = torch.zeros(T, dtype=torch.float32, device=dev)
+        self.labels = mu.define_error_labels(e7, exp_kwargs).float().contiguous()
+        self.graph, self.pool, self.launches_per_step = None, pool, None
+        optimizer.prepare()
+        if getattr(model, "graph_seed", False) is None:
+            model.graph_seed = (int(torch.randint(0, 2 ** 62, (1,)).item()), torch.zeros(1, dtype=torch.int64, device=dev))
+
+    def _body(self):
+        inputs = mu.define_inputs(self.images, self.kin, self.fe, self.kw, self.device)
+        outputs = self.model(inputs)
+        loss, _ = mu.compute_loss(outputs, self.labels, self.crit, "frame")
+        self.opt.zero_grad()
+        mu._backward(loss, self.opt)
+        mu._allreduce_grads(self.opt)
+        self.opt.step()
+        preds, counts = mu.compute_loss.last_frame
+        self.loss.copy_(loss.detach().reshape(1))
+        self.counts.copy_(counts)
+        self.preds.copy_(preds.reshape(-1))
+
+    def capture(self, warmup: int = 2):
+        mu._set_train(self.model, self.fe, self.kw, True)
+        state = _TrainState(self.opt, (self.fe, self.model))
+        seed_counter = None if getattr(self.model, "graph_seed", None) is None else self.model.graph_seed[1].clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self.pool):
+            self._body()
+        self.launches_per_step = _lib.launch_count() - n0
+        self.graph = g
+        state.restore()
+        if seed_counter is not None:
+            self.model.graph_seed[1].copy_(seed_counter)
+        return self
+
+    def run(self):
+        self.opt.sync_lr()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss

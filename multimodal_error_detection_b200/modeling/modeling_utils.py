@@ -383,6 +383,9 @@ def train_single_epoch(model, feature_extractor, train_dataloader, criterion, op
     _set_train(model, feature_extractor, exp_kwargs, True)
     if _graph_step_ok(train_dataloader, feature_extractor, criterion, exp_kwargs):
         return _train_epoch_graph(model, feature_extractor, train_dataloader, criterion, optimizer, scheduler, device, exp_kwargs)
+    if _frame_graph_ok(train_dataloader, exp_kwargs):
+        return _train_epoch_frame_graph(model, feature_extractor, train_dataloader, criterion, optimizer, scheduler, device,
+                                        exp_kwargs)
     log = _EpochLog()
     subjects_all = []
     frame = exp_kwargs["dataset_type"] == "frame"
@@ -433,6 +436,64 @@ def _graph_step_ok(loader, feature_extractor, criterion, exp_kwargs) -> bool:
     return bool(want) and isinstance(loader, DeviceWindowLoader) and exp_kwargs["dataset_type"] == "window" \
         and exp_kwargs["error_type"] == "global" and isinstance(criterion, FusedBCEWithLogitsLoss) \
         and exp_kwargs["data_type"] != "kinematics"
+
+
+def _frame_graph_ok(loader, exp_kwargs) -> bool:
+    """Frame path: one CUDA graph per resident video, replayed once per epoch (engine.FrameTrainStep).  Opt-in through
+    ``exp_kwargs['cuda_graph']``: capturing costs three eager steps per video, which pays off from the second epoch on."""
+    from ..dataset.CustomFrameDataset import FrameLoader
+    return bool(exp_kwargs.get("cuda_graph", False)) and isinstance(loader, FrameLoader) and exp_kwargs["dataset_type"] == "frame" \
+        and exp_kwargs["error_type"] == "global"
+
+
+def _train_epoch_frame_graph(model, feature_extractor, loader, criterion, optimizer, scheduler, device, exp_kwargs):
+    """train_single_epoch for the frame path with every video's step replayed from its own captured CUDA graph.  Same
+    return tuple and the same arithmetic as the eager loop (videos whose capture fails run eagerly, loudly)."""
+    from ..engine import FrameTrainStep
+    key = (id(loader.dataset), id(model), id(feature_extractor), id(criterion))
+    cache = getattr(optimizer, "_b200_frame_steps", None)
+    if cache is None or cache["key"] != key:
+        cache = optimizer._b200_frame_steps = {"key": key, "steps": {}, "pool": torch.cuda.graph_pool_handle(), "failed": False}
+    log = _EpochLog()
+    subjects_all = []
+    want_preds = exp_kwargs["return_train_preds"]
+    for i in loader.indices():
+        step = cache["steps"].get(i)
+        if step is None:
+            images, kin, g, e7, subject, skill = loader.dataset[i]
+            step = FrameTrainStep(images.unsqueeze(0), kin.unsqueeze(0), e7.unsqueeze(0), feature_extractor, model, criterion,
+                                  optimizer, exp_kwargs, pool=cache["pool"])
+            step.subject = subject
+            if not cache["failed"]:
+                try:
+                    step.capture()
+                except Exception as e:      # capture is an optimisation: fall back to eager launches, loudly
+                    cache["failed"] = True
+                    print(f"b200med: CUDA graph capture of the frame step failed ({type(e).__name__}: {e}); running eagerly")
+            cache["steps"][i] = step
+        step.run()
+        if exp_kwargs.get("host_sync") == "step":
+            step.loss.item()
+        if want_preds:
+            log.add(step.loss.clone(), step.counts.clone(), preds=step.preds.clone(), labels=step.labels.reshape(-1))
+            subjects_all += [step.subject] * int(step.preds.numel())
+        else:
+            log.add(step.loss.clone(), step.counts.clone())
+    if scheduler is not None:
+        scheduler.step()
+    n_batches = max(len(log.losses), 1)
+    losses, counts = log.losses_host(), log.counts_host()
+    tot = np.zeros(4)
+    cm = np.zeros((2, 2), dtype=int)
+    for c in counts:
+        f1, f1w, acc, jac, contrib = _batch_scores(c)
+        tot += (f1, f1w, acc, jac)
+        cm += contrib
+    res = (float(losses.sum() / n_batches), *(tot / n_batches).tolist(), cm)
+    if want_preds:
+        return (*res, log.cat_host("probs").tolist(), log.cat_host("preds").tolist(), log.cat_host("labels").tolist(),
+                subjects_all)
+    return res
 
 
 def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, scheduler, device, exp_kwargs):

@@ -66,13 +66,14 @@ class SingleStageModel(nn.Module):
             ps += [l.conv_dilated.weight, l.conv_dilated.bias, l.conv_1x1.weight, l.conv_1x1.bias]
         return ps + [self.conv_out_classes.weight, self.conv_out_classes.bias]
 
-    def run_fused(self, x: torch.Tensor, softmax_in: bool = False, seed: int = 0, layer_base: int = 0, geom=(None, None)):
+    def run_fused(self, x: torch.Tensor, softmax_in: bool = False, seed: int = 0, layer_base: int = 0, geom=(None, None),
+                  seed_dev=None):
         """x [1, F, T] (or the previous stage's logits [1, C, T] with ``softmax_in``) -> logits [1, C, T]."""
         tcn.require_cuda(x)
         cfg = self._cfgs.get(softmax_in)
         if cfg is None:
             cfg = self._cfgs[softmax_in] = tcn.StageConfig(len(self.layers), self.causal_conv, softmax_in)
-        cfg.layer_base, cfg.seed = layer_base, seed
+        cfg.layer_base, cfg.seed, cfg.seed_dev = layer_base, seed, seed_dev
         cfg.drop_p = [float(l.dropout.p) if (self.training and l.dropout.training) else 0.0 for l in self.layers]
         cfg.tloc, cfg.trem = geom
         xin = x[0] if softmax_in else x[0].t()      # [C, T] logits, or [T, F] rows (a free view of the [1, T, F] batch)
@@ -100,6 +101,9 @@ class MultiStageModel(nn.Module):
         self.smoothing = False
         self.impl = "b200"       # what the last forward ran on: "b200" (csrc/tcn.cu) or "torch" (unsupported shape)
         self.use_fused = True    # scripts/bench_frame.py switches it off to time the stock torch layers as the A/B baseline
+        # CUDA-graph training (engine.FrameTrainStep): a host seed fixed at capture + an int64 DEVICE counter advanced inside
+        # the captured step, so that every replay draws a fresh dropout mask
+        self.graph_seed = None   # (host seed, device counter tensor) or None
 
     def _seed(self) -> int:
         if not self.training:
@@ -109,11 +113,16 @@ class MultiStageModel(nn.Module):
     def forward(self, x, geom=(None, None)):
         if self.use_fused and self.stage1.fused_ok(x) and all(s.fused_supported() for s in self.stages):
             self.impl = "b200"
-            seed = self._seed()
-            out = self.stage1.run_fused(x, False, seed, 0, geom)
+            seed_dev = None
+            if self.training and self.graph_seed is not None:
+                seed, seed_dev = self.graph_seed
+                seed_dev.add_(1)
+            else:
+                seed = self._seed()
+            out = self.stage1.run_fused(x, False, seed, 0, geom, seed_dev)
             outs = [out]
             for i, s in enumerate(self.stages):
-                out = s.run_fused(out, True, seed, (i + 1) * self.num_layers, geom)
+                out = s.run_fused(out, True, seed, (i + 1) * self.num_layers, geom, seed_dev)
                 outs.append(out)
             return torch.stack(outs, dim=0)
         if geom[0] is not None:

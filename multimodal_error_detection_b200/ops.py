@@ -371,21 +371,26 @@ def tcn_pack(ptr_table: torch.Tensor, n_layers: int, out=None) -> torch.Tensor:
     return out
 
 
-def tcn_layer_fwd(x, pack, out, y_save, dilation: int, causal: bool, drop_p=0.0, seed=0, drop_base=0, tloc=None, trem=None):
+def _seed_dev(seed_dev):
+    return _ptr(None if seed_dev is None else _need(seed_dev, torch.int64, "seed_dev"))
+
+
+def tcn_layer_fwd(x, pack, out, y_save, dilation: int, causal: bool, drop_p=0.0, seed=0, drop_base=0, tloc=None, trem=None,
+                  seed_dev=None):
     x = _need(x, torch.float32, "x")
     T = x.shape[0]
     tl, tr = _geom(tloc, trem)
     call("b200med_tcn_layer_fwd", _ptr(x), _ptr(pack), _ptr(out), _ptr(y_save), T, int(dilation), int(bool(causal)), tl, tr,
-         float(drop_p), C.c_uint64(int(seed)), C.c_uint64(int(drop_base)), _stream())
+         float(drop_p), C.c_uint64(int(seed)), _seed_dev(seed_dev), C.c_uint64(int(drop_base)), _stream())
     return out
 
 
 def tcn_layer_bwd_hidden(dout, x, y, pack, dpre, partials, n_slots, dilation, causal, drop_p=0.0, seed=0, drop_base=0,
-                         tloc=None, trem=None):
+                         tloc=None, trem=None, seed_dev=None):
     dout = _need(dout, torch.float32, "dout")
     tl, tr = _geom(tloc, trem)
     call("b200med_tcn_layer_bwd_hidden", _ptr(dout), _ptr(x), _ptr(y), _ptr(pack), _ptr(dpre), _ptr(partials), int(n_slots),
-         dout.shape[0], int(dilation), int(bool(causal)), tl, tr, float(drop_p), C.c_uint64(int(seed)),
+         dout.shape[0], int(dilation), int(bool(causal)), tl, tr, float(drop_p), C.c_uint64(int(seed)), _seed_dev(seed_dev),
          C.c_uint64(int(drop_base)), _stream())
     return dpre
 
@@ -442,7 +447,7 @@ def _f32_array(values):
 
 
 def tcn_stage_fwd(x, softmax_in, in_w, in_b, ptr_table, n_layers, out_w, out_b, causal, drop_p=None, seed=0, layer_base=0,
-                  keep=True, tloc=None, trem=None):
+                  keep=True, tloc=None, trem=None, seed_dev=None):
     """Whole SingleStageModel forward in one C call -> dict(logits [C,T], xin, acts, ys, pack)."""
     x = _need(x, torch.float32, "x")
     in_w = _need(in_w, torch.float32, "in_w"); out_w = _need(out_w, torch.float32, "out_w")
@@ -460,13 +465,13 @@ def tcn_stage_fwd(x, softmax_in, in_w, in_b, ptr_table, n_layers, out_w, out_b, 
     if T:
         call("b200med_tcn_stage_fwd", _ptr(x), in_dim, int(bool(softmax_in)), _ptr(in_w), _ptr(_need(in_b, torch.float32, "in_b")),
              _ptr(_need(ptr_table, torch.int64, "ptr_table")), n_layers, _ptr(out_w), _ptr(_need(out_b, torch.float32, "out_b")),
-             n_cls, T, int(bool(causal)), tl, tr, _f32_array(drop_p), C.c_uint64(int(seed)), C.c_uint64(int(layer_base)),
-             int(bool(keep)), _ptr(p_in), _ptr(acts), _ptr(ys), _ptr(pack), _ptr(logits), _stream())
+             n_cls, T, int(bool(causal)), tl, tr, _f32_array(drop_p), C.c_uint64(int(seed)), _seed_dev(seed_dev),
+             C.c_uint64(int(layer_base)), int(bool(keep)), _ptr(p_in), _ptr(acts), _ptr(ys), _ptr(pack), _ptr(logits), _stream())
     return dict(logits=logits, xin=p_in if softmax_in else x, acts=acts, ys=ys, pack=pack)
 
 
 def tcn_stage_bwd(dlogits, xin, softmax_in, in_w, out_w, n_layers, causal, acts, ys, pack, want_dx, drop_p=None, seed=0,
-                  layer_base=0, tloc=None, trem=None):
+                  layer_base=0, tloc=None, trem=None, seed_dev=None):
     """Whole stage backward in one C call -> dict(dx, d_in_w [64,in_dim], d_in_b, layer_grads [L,GRAD], d_out_w [C,64], d_out_b)."""
     dl = _need(dlogits, torch.float32, "dlogits")
     n_cls, T = dl.shape
@@ -484,7 +489,7 @@ def tcn_stage_bwd(dlogits, xin, softmax_in, in_w, out_w, n_layers, causal, acts,
     tl, tr = _geom(tloc, trem)
     call("b200med_tcn_stage_bwd", _ptr(dl), _ptr(_need(xin, torch.float32, "xin")), in_dim, int(bool(softmax_in)),
          _ptr(_need(in_w, torch.float32, "in_w")), _ptr(_need(out_w, torch.float32, "out_w")), n_cls, n_layers, T,
-         int(bool(causal)), tl, tr, _f32_array(drop_p), C.c_uint64(int(seed)), C.c_uint64(int(layer_base)), _ptr(acts),
-         _ptr(ys), _ptr(pack), _ptr(ws), _ptr(d_in_w), _ptr(d_in_b), _ptr(layer_grads), _ptr(d_out_w), _ptr(d_out_b), _ptr(dx),
-         _stream())
+         int(bool(causal)), tl, tr, _f32_array(drop_p), C.c_uint64(int(seed)), _seed_dev(seed_dev),
+         C.c_uint64(int(layer_base)), _ptr(acts), _ptr(ys), _ptr(pack), _ptr(ws), _ptr(d_in_w), _ptr(d_in_b), _ptr(layer_grads),
+         _ptr(d_out_w), _ptr(d_out_b), _ptr(dx), _stream())
     return dict(dx=dx, d_in_w=d_in_w, d_in_b=d_in_b, layer_grads=layer_grads, d_out_w=d_out_w, d_out_b=d_out_b)

@@ -27,6 +27,7 @@ class StageConfig:
         self.n_layers, self.causal, self.softmax_in, self.layer_base = n_layers, bool(causal), bool(softmax_in), layer_base
         self.drop_p: List[float] = [0.0] * n_layers     # per layer, 0 in eval mode
         self.seed = 0
+        self.seed_dev: Optional[torch.Tensor] = None     # int64 device scalar added to the seed on the device (CUDA graphs)
         self.tloc: Optional[torch.Tensor] = None         # ragged batch geometry (None = one video)
         self.trem: Optional[torch.Tensor] = None
         self._ptr_key, self._ptr_table = None, None
@@ -68,9 +69,9 @@ class TcnStageFunction(torch.autograd.Function):
         keep = any(ctx.needs_input_grad)
         r = ops.tcn_stage_fwd(x.detach().contiguous().float(), cfg.softmax_in, in_w.detach().view(MAPS, -1), in_b.detach(),
                               cfg.ptr_table(params[2:2 + 4 * L]), L, out_w.detach().view(out_w.shape[0], MAPS), out_b.detach(),
-                              cfg.causal, cfg.drop_p, cfg.seed, cfg.layer_base, keep, cfg.tloc, cfg.trem)
+                              cfg.causal, cfg.drop_p, cfg.seed, cfg.layer_base, keep, cfg.tloc, cfg.trem, cfg.seed_dev)
         if keep:
-            ctx.cfg, ctx.geom = cfg, (list(cfg.drop_p), cfg.seed, cfg.layer_base, cfg.tloc, cfg.trem)
+            ctx.cfg, ctx.geom = cfg, (list(cfg.drop_p), cfg.seed, cfg.layer_base, cfg.tloc, cfg.trem, cfg.seed_dev)
             ctx.save_for_backward(r["xin"], r["acts"], r["ys"], r["pack"], in_w, out_w)
         return r["logits"]
 
@@ -78,11 +79,11 @@ class TcnStageFunction(torch.autograd.Function):
     def backward(ctx, dlogits):
         cfg = ctx.cfg
         L = cfg.n_layers
-        drop_p, seed, layer_base, tloc, trem = ctx.geom
+        drop_p, seed, layer_base, tloc, trem, seed_dev = ctx.geom
         xin, acts, ys, pack, in_w, out_w = ctx.saved_tensors
         r = ops.tcn_stage_bwd(dlogits.contiguous().float(), xin, cfg.softmax_in, in_w.detach().view(MAPS, -1),
                               out_w.detach().view(out_w.shape[0], MAPS), L, cfg.causal, acts, ys, pack,
-                              ctx.needs_input_grad[0], drop_p, seed, layer_base, tloc, trem)
+                              ctx.needs_input_grad[0], drop_p, seed, layer_base, tloc, trem, seed_dev)
         out = [r["dx"], None, r["d_in_w"].view_as(in_w), r["d_in_b"]]
         for l in range(L):
             g = r["layer_grads"][l]

@@ -77,6 +77,15 @@ def main():
         res[name] = {"train_ms_per_video": ms, "train_frames_per_s": T / ms * 1e3, "head_fwd_bwd_ms": ms_head,
                      "infer_ms_per_video": ms_inf, "infer_frames_per_s": T / ms_inf * 1e3, "own_launches_per_step": launches,
                      "impl": model.impl}
+    # the same train step replayed from a CUDA graph (engine.FrameTrainStep; what train_single_epoch does with cuda_graph=True)
+    from multimodal_error_detection_b200.engine import FrameTrainStep
+    model.use_fused = True
+    model.train(); fe.train()
+    e7 = torch.zeros(1, T, 7, dtype=torch.int32, device=dev)
+    e7[0, :, 6] = y[0].to(torch.int32)
+    step = FrameTrainStep(images, kin, e7, fe, model, crit, opt, kw).capture()
+    ms = timed(step.run, args.steps)
+    res["b200_graph"] = {"train_ms_per_video": ms, "train_frames_per_s": T / ms * 1e3, "own_launches_per_step": step.launches_per_step}
     # ragged-batched inference of the head: V videos in one pass vs one pass per video
     model.use_fused = True
     model.eval()

@@ -142,7 +142,7 @@ class EmulatedOps:
     # ---- whole-stage calls: the sequencing of b200med_tcn_stage_fwd / _bwd (csrc/tcn.cu), kernel by kernel
     @classmethod
     def tcn_stage_fwd(cls, x, softmax_in, in_w, in_b, params, n_layers, out_w, out_b, causal, drop_p=None, seed=0,
-                      layer_base=0, keep=True, tloc=None, trem=None):
+                      layer_base=0, keep=True, tloc=None, trem=None, seed_dev=None):
         assert not drop_p or max(drop_p) == 0.0
         xin = softmax_fwd(x) if softmax_in else x
         T = xin.shape[0]
@@ -158,7 +158,7 @@ class EmulatedOps:
 
     @classmethod
     def tcn_stage_bwd(cls, dlogits, xin, softmax_in, in_w, out_w, n_layers, causal, acts, ys, pack, want_dx, drop_p=None,
-                      seed=0, layer_base=0, tloc=None, trem=None):
+                      seed=0, layer_base=0, tloc=None, trem=None, seed_dev=None):
         T = xin.shape[0]
         dA, dl_t = out_bwd(dlogits, out_w)
         d_out_w, d_out_b = cls.linear_bwd_weight_f32(dl_t, acts[n_layers])

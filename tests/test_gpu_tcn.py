@@ -232,3 +232,48 @@ def test_train_mode_dropout_is_seeded():
     assert torch.equal(a, b) and not torch.equal(a, c)
     a.sum().backward()
     assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_frame_graph_epoch_matches_eager_epoch(fold_on_disk):
+    """Frame path: train_single_epoch with every video's step replayed from its own CUDA graph (engine.FrameTrainStep) gives
+    the same epochs as the eager loop -- capturing (three real steps per video, rolled back) must not disturb the training
+    state -- and every video really ran from a graph."""
+    import numpy as np
+    import cases
+    from multimodal_error_detection_b200.dataset.CustomFrameDataset import CustomFrameDataset, FrameLoader
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    path, fold = fold_on_disk
+    res = {}
+    for graph in (False, True):
+        kw = dict(cases.FRAME_EPOCH_CASES["tecno_multimodal"], cuda_graph=graph, return_train_preds=True)
+        ds = CustomFrameDataset(path, csv_filename="train.csv", delete_ND=kw["delete_ND"])
+        tr = FrameLoader(ds, shuffle=True, generator=torch.Generator().manual_seed(42))
+        fe, model, crit, opt, sched = mu.define_model_objects(kw, cases.IN_FEATURES, torch.device(DEV), (0.4, 0.6), 0)
+        for mod in list(model.modules()) + list(fe.modules()):
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        res[graph] = [mu.train_single_epoch(model, fe, tr, crit, opt, sched, DEV, kw) for _ in range(3)]
+        if graph:
+            steps = opt._b200_frame_steps
+            assert not steps["failed"] and len(steps["steps"]) == len(ds)
+            assert all(s.graph is not None and s.launches_per_step > 50 for s in steps["steps"].values())
+    for a, b in zip(res[False], res[True]):
+        assert abs(a[0] - b[0]) < 1e-6 * max(1.0, abs(a[0])), (a[0], b[0])
+        assert np.array_equal(a[5], b[5])
+        assert a[7] == b[7] and a[8] == b[8] and a[9] == b[9]
+
+
+def test_frame_graph_dropout_draws_a_fresh_mask_per_replay(fold_on_disk):
+    """Dropout inside the captured step: the mask seed is a host constant plus a device counter advanced inside the graph,
+    so two replays of the same video with frozen weights (lr = 0) give different losses."""
+    import cases
+    from multimodal_error_detection_b200.dataset.CustomFrameDataset import CustomFrameDataset, FrameLoader
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    path, fold = fold_on_disk
+    kw = dict(cases.FRAME_EPOCH_CASES["tecno_multimodal"], cuda_graph=True, lr=0.0, lr_scheduler=False, weight_decay=0.0)
+    ds = CustomFrameDataset(path, csv_filename="train.csv", delete_ND=kw["delete_ND"])
+    tr = FrameLoader(ds, shuffle=False)
+    fe, model, crit, opt, sched = mu.define_model_objects(kw, cases.IN_FEATURES, torch.device(DEV), (0.4, 0.6), 0)
+    losses = [mu.train_single_epoch(model, fe, tr, crit, opt, sched, DEV, kw)[0] for _ in range(3)]
+    assert not opt._b200_frame_steps["failed"]
+    assert len({round(l, 7) for l in losses}) == 3, losses
