@@ -310,21 +310,31 @@ tcn_layer_bwd_hidden_kernel(const float *__restrict__ dout, const float *__restr
         __syncthreads();
     }
     if (first) bar_wait(&bar, 0);   // a CTA without tiles must still drain its copy before exiting
-    float *part = partials + (long long)blockIdx.x * kGradFloats;
+    // The record goes out through shared memory: written straight from the accumulators every lane of a store hits its own
+    // 32-byte sector (ncu, first version: 27 sectors per request, 58 % of the stalls lg_throttle, 18 us per launch).  Rows
+    // are padded (193 / 65 floats) against bank conflicts; the copy out is one coalesced sweep.
+    __syncthreads();
+    float *st = smem;
+    constexpr int kRowD = 3 * kF + 1, kRow1 = kF + 1, kSt1 = kF * kRowD, kStB = kSt1 + kF * kRow1;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int co = cog * 8 + a;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) part[co * (3 * kF) + (cig * 4 + i) * 3 + k] = gD[a][k][i];
-            part[kWd + co * kF + cig * 4 + i] = g1[a][i];
+            for (int k = 0; k < 3; ++k) st[co * kRowD + (cig * 4 + i) * 3 + k] = gD[a][k][i];
+            st[kSt1 + co * kRow1 + cig * 4 + i] = g1[a][i];
         }
         if (cig == 0) {
-            part[kWd + kW1 + co] = gbd[a];
-            part[kWd + kW1 + kF + co] = gb1[a];
+            st[kStB + co] = gbd[a];
+            st[kStB + kF + co] = gb1[a];
         }
     }
+    __syncthreads();
+    float *part = partials + (long long)blockIdx.x * kGradFloats;
+    for (int e = threadIdx.x; e < kWd; e += kTcnThreads) part[e] = st[(e / (3 * kF)) * kRowD + e % (3 * kF)];
+    for (int e = threadIdx.x; e < kW1; e += kTcnThreads) part[kWd + e] = st[kSt1 + (e / kF) * kRow1 + e % kF];
+    for (int e = threadIdx.x; e < 2 * kF; e += kTcnThreads) part[kWd + kW1 + e] = st[kStB + e];
 }
 
 // grads[layer][e] = sum over slots (ascending) of partials[layer][slot][e]
@@ -468,7 +478,11 @@ static int make_geom(TcnGeom &g, int64_t T, int32_t dilation, int32_t causal, co
 }
 
 constexpr size_t smem_fwd(int TT) { return (size_t)(kWd + kW1 + 3 * TT * kF + TT * kF) * 4; }    // 69.6 / 73.7 / 81.9 KB
-constexpr size_t smem_bwd_h(int TT) { return (size_t)(kW1 + 3 * TT * kF + 3 * TT * kF) * 4; }     // 22.5 / 28.7 / 41 KB
+// working set (W1 + tap / y / dz / dpre tiles), and at the end the padded gradient record staged for a coalesced copy out
+constexpr size_t smem_bwd_h(int TT) {
+    const size_t work = (size_t)(kW1 + 3 * TT * kF + 3 * TT * kF) * 4, record = (size_t)(kF * (3 * kF + 1) + kF * (kF + 1) + 2 * kF) * 4;
+    return work > record ? work : record;   // 66.6 KB
+}
 constexpr size_t smem_bwd_i(int TT) { return (size_t)(kWd + 3 * TT * kF) * 4; }                   // 52.2 / 55.3 / 61.4 KB
 
 // Frames per warp: cut the per-thread chain while the grid is small (one video), amortise the weight staging when it is
