@@ -1,0 +1,112 @@
+"""Ensemble inference (BASELINE config 5): frame model + window model over a
+device-resident frame table, fused on the device.
+
+The reference fuses STORED per-sample outputs in ``ensemble.ipynb`` (cell 6: soft vote ``(p_a + p_b) / 2 >= 0.5``; cell 15:
+cascade) and bridges frame -> window predictions with ``window_predictions`` (MED/modeling/modeling_utils.py:2695-2777).
+Here the two forwards run too:
+
+* frame model (TeCNo): videos are concatenated along time and run in ragged passes (``MultiStageModel.forward_ragged``:
+  taps never cross a video) instead of one ``DataLoader(batch_size=1)`` step per video;
+* window model: K1 gather -> FeatureExtractor -> head per batch of window indices, probabilities from the K3 kernel;
+* bridge + fusion: window vote of the frame predictions over the SAME window index (K0), soft vote, confusion counts.
+
+Everything is sharded by video (a window never crosses a video): each rank owns a contiguous range of videos, the only
+exchange is the sum of the confusion counts.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .table import FrameTable, WindowIndex
+
+
+@torch.no_grad()
+def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwargs: dict, kin_stats: Optional[dict] = None,
+                            frames_per_pass: int = 1 << 16) -> torch.Tensor:
+    """Frame-level predictions [N] f32 (argmax of the LAST stage, modeling_utils.py:370 / :751) for every frame of the
+    table.  Frame-path inputs: raw image features through the FeatureExtractor, kinematics standardised
+    (CustomFrameDataset.py:93-95), concatenated on the feature axis (modeling_utils.py:41-42)."""
+    model.eval()
+    if feature_extractor is not None:
+        feature_extractor.eval()
+    off = table.offsets_host
+    lengths = np.diff(off)
+    N, dev = table.n_frames, table.device
+    preds = torch.empty(N, dtype=torch.float32, device=dev)
+    dt = exp_kwargs["data_type"]
+    v = 0
+    while v < len(lengths):
+        w, n = v, 0
+        while w < len(lengths) and (w == v or n + lengths[w] <= frames_per_pass):
+            n += int(lengths[w]); w += 1
+        r0, r1 = int(off[v]), int(off[w])
+        cols = []
+        if dt in ("multimodal", "video"):
+            img = table.image[r0:r1]
+            cols.append(img if (dt == "video" and exp_kwargs["video_dims"] == 2048) else feature_extractor(img).float())
+        if dt in ("multimodal", "kinematics"):
+            kin = table.kin[r0:r1]
+            if kin_stats is not None:
+                D = kin.shape[1]
+                kin = ops.standardise_rows(kin.contiguous(), ops.expand_stat(kin_stats["mean"], D, 1, dev),
+                                           ops.expand_stat(kin_stats["std"], D, 1, dev))
+            cols.append(kin)
+        frames = cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
+        logits = model.forward_ragged(frames, [int(x) for x in lengths[v:w]])        # [stages, C, n]
+        preds[r0:r1] = torch.argmax(logits[-1], dim=0).float()
+        v = w
+    return preds
+
+
+@torch.no_grad()
+def window_model_probabilities(dataset, feature_extractor, model, exp_kwargs: dict, batch_size: int = 8192) -> torch.Tensor:
+    """sigmoid(logit) [n] f32 of the binary window model for every window of the dataset (validate_single_epoch's forward,
+    modeling_utils.py:735-752, without the per-sample host loop)."""
+    from .modeling import modeling_utils as mu
+    model.eval()
+    if feature_extractor is not None:
+        feature_extractor.eval()
+    n, dev = len(dataset), dataset._starts.device
+    probs = torch.empty(n, dtype=torch.float32, device=dev)
+    image_dtype = mu._image_dtype(feature_extractor)
+    zeros = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+    for lo in range(0, n, batch_size):
+        hi = min(n, lo + batch_size)
+        idx = torch.arange(lo, hi, device=dev)
+        images, kin = dataset.gather_batch(idx, image_dtype=image_dtype, exact=image_dtype == torch.float32)
+        out = model(mu.define_inputs(images, kin, feature_extractor, exp_kwargs, dev))
+        r = ops.bce_logits(out.reshape(-1).float().contiguous(), zeros[: hi - lo], want_grad=False, want_probs=True)
+        probs[lo:hi] = r["probs"]
+    return probs
+
+
+@torch.no_grad()
+def fuse(frame_preds: torch.Tensor, index: WindowIndex, window_probs: torch.Tensor, window_labels: Optional[torch.Tensor] = None):
+    """Bridge + fusion on the device: window value of the frame predictions (mean over the window ``>= 0.5``,
+    modeling_utils.py:2752-2754) on the window model's own index, then the soft vote of ensemble.ipynb cell 6 with the
+    confusion counts (tn, fp, fn, tp) against ``window_labels``."""
+    frame_windows = ops.window_vote(frame_preds, index.starts, index.W, True)
+    fused, counts = ops.soft_vote(window_probs, frame_windows, window_labels)
+    return dict(frame_windows=frame_windows, fused=fused, counts=counts)
+
+
+def ensemble_inference(table: FrameTable, dataset, frame_objects, window_objects, kin_stats=None, batch_size: int = 8192,
+                       frames_per_pass: int = 1 << 16):
+    """frame_objects / window_objects = (feature_extractor, model, exp_kwargs); ``dataset`` = the window dataset built
+    over ``table`` (its ``index`` is the window index after Needle-Drop deletion).  Returns the dict of :func:`fuse` plus
+    the two models' raw outputs; with torch.distributed initialised the counts are summed over the ranks."""
+    from . import parallel
+    f_fe, f_model, f_kw = frame_objects
+    w_fe, w_model, w_kw = window_objects
+    frame_preds = frame_model_predictions(table, f_fe, f_model, f_kw, kin_stats, frames_per_pass)
+    window_probs = window_model_probabilities(dataset, w_fe, w_model, w_kw, batch_size)
+    from .modeling import modeling_utils as mu
+    labels = mu.define_error_labels(dataset.e_labels_data, w_kw).float().contiguous()
+    out = fuse(frame_preds, dataset.index, window_probs, labels)
+    out["counts"] = parallel.allreduce_sum_(out["counts"])
+    out.update(frame_preds=frame_preds, window_probs=window_probs, labels=labels)
+    return out
