@@ -211,6 +211,32 @@ def build_gpu_job(args, rank, device):
     return ds, N
 
 
+def other_configs():
+    """Auxiliary, bounded measurements of the BASELINE configs the headline line does not cover (they are parity-test
+    cases, not bench lines): config 0 (train_frame: FE + TeCNo, one video per step, eager / CUDA graph / stock torch layers)
+    and config 5 (ensemble inference: frame model + window model + device-side fusion).  Failures are reported, never fatal."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    out = {}
+    try:
+        import bench_frame
+        r = bench_frame.measure(frames=600, videos=32, steps=20)
+        out["train_frame"] = {"unit": "frames/s", "frames_per_video": 600,
+                              "cuda_graph": r["b200_graph"]["train_frames_per_s"], "eager": r["b200"]["train_frames_per_s"],
+                              "stock_torch_layers": r["torch_layers"]["train_frames_per_s"],
+                              "ms_per_video_cuda_graph": r["b200_graph"]["train_ms_per_video"],
+                              "inference_ragged_frames_per_s": r["head_inference"]["ragged_frames_per_s"], "config": r["config"]}
+    except Exception as e:
+        out["train_frame"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        import bench_ensemble
+        r = bench_ensemble.measure(videos=512, reps=2, dist_init=False)
+        out["ensemble_inference"] = {k: r[k] for k in ("value", "unit", "frames_per_s", "videos_per_gpu", "frames_per_gpu", "ms_total",
+                                                       "ms_frame_model", "ms_window_model", "ms_vote_fusion_counts", "config")}
+    except Exception as e:
+        out["ensemble_inference"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 def run_gpu(args):
     from multimodal_error_detection_b200 import _lib, ops, parallel
     from multimodal_error_detection_b200.dataset.CustomWindowDataset import DeviceWindowLoader
@@ -410,6 +436,9 @@ def run_gpu(args):
                                  f"(host window build {build_s:.2f}s for the sample not included)"}
             except Exception as e:
                 cpu = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {e}"}
+        other = None
+        if world == 1 and not args.no_aux and args.precision == "bf16":
+            other = other_configs()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": step_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
@@ -420,7 +449,7 @@ def run_gpu(args):
                            "l2": "every step gathers a fresh ~1.1 GB slice of a >2 GB table (inputs larger than the 126 MB L2)",
                            "gather_variant": args.gather_variant},
                 "roofline": roofline, "roofline_gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks, "final_loss": final_loss}
+                "clocks": clocks, "final_loss": final_loss, "other_configs": other}
         print(json.dumps(line), flush=True)
     if world > 1:
         # graphs that captured NCCL work must be gone before the communicator is torn down; a wedged teardown must not
@@ -448,6 +477,8 @@ def main():
     ap.add_argument("--lstm-impl", default="b200", choices=["b200", "b200_per_step", "cudnn"])
     ap.add_argument("--gather-variant", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary measurements of the other BASELINE configs "
+                    "(frame path, ensemble inference; N = 1 only, reported under 'other_configs')")
     ap.add_argument("--prefetch-sms", type=int, default=56, help="SMs the prefetching gather may occupy (side stream)")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="gather each step's batch at the start of the step instead of inside the previous step")

@@ -26,14 +26,13 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--videos", type=int, default=2048)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--frames-per-pass", type=int, default=1 << 16)
-    args = ap.parse_args()
-    rank, local_rank, world = parallel.init_from_env()
+def measure(videos: int = 2048, reps: int = 3, batch: int = 8192, frames_per_pass: int = 1 << 16, dist_init: bool = True):
+    """-> result dict on rank 0 (None elsewhere)."""
+    args = argparse.Namespace(videos=videos, reps=reps, batch=batch, frames_per_pass=frames_per_pass)
+    if dist_init:
+        rank, local_rank, world = parallel.init_from_env()
+    else:
+        rank, local_rank, world = 0, torch.cuda.current_device(), 1
     device = torch.device("cuda", local_rank)
     ds, n_frames = bench.build_gpu_job(args, rank, device)
     table = ds.index.table
@@ -85,7 +84,7 @@ def main():
     per_video_ms = a.elapsed_time(b) / sample
     if rank == 0:
         counts = out["counts"].tolist()
-        print(json.dumps({
+        return ({
             "metric": "ensemble_inference_videos_per_sec", "value": world * args.videos / tot_ms * 1e3, "unit": "videos/s",
             "frames_per_s": world * n_frames / tot_ms * 1e3, "n_gpus": world, "videos_per_gpu": args.videos,
             "frames_per_gpu": n_frames, "windows_per_gpu": len(ds), "ms_total": tot_ms,
@@ -94,7 +93,20 @@ def main():
             "frame_model_ragged_ms_per_video": ms[0] / args.videos,
             "config": "frame: FE(2048-512-256-32, bf16 tcgen05) + TeCNo(2x8x64, fp32, ragged passes of <= %d frames); window: W=16 S=4 "
                       "FE + LSTM(58,16,3,128) bf16, batch %d; window vote + soft vote + confusion counts on the device" % (args.frames_per_pass, args.batch),
-            "counts_tn_fp_fn_tp": counts, "scaling": "weak", "data": "synthetic"}), flush=True)
+            "counts_tn_fp_fn_tp": counts, "scaling": "weak", "data": "synthetic"})
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--videos", type=int, default=2048)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--frames-per-pass", type=int, default=1 << 16)
+    a = ap.parse_args()
+    res = measure(a.videos, a.reps, a.batch, a.frames_per_pass)
+    if res is not None:
+        print(json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":

@@ -29,13 +29,9 @@ def timed(fn, steps, warmup=5):
     return a.elapsed_time(b) / steps
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=600)
-    ap.add_argument("--videos", type=int, default=64)
-    ap.add_argument("--steps", type=int, default=30)
-    args = ap.parse_args()
-    dev = torch.device("cuda")
+def measure(frames: int = 600, videos: int = 64, steps: int = 30) -> dict:
+    args = argparse.Namespace(frames=frames, videos=videos, steps=steps)
+    dev = torch.device("cuda", torch.cuda.current_device())
     kw = dict(dataset_type="frame", error_type="global", pos_weight=False, n_epochs=2, batch_size=1, lr=3e-4,
               lr_scheduler=True, weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32, data_type="multimodal",
               delete_ND=True, return_train_preds=False, siamese=False, model_name="TeCNo", mstcn_stages=2, mstcn_layers=8,
@@ -105,7 +101,16 @@ def main():
     ms_r, ms_p = timed(ragged, 10, 2), timed(per_video, 3, 1)
     res["head_inference"] = {"videos": args.videos, "frames": sum(lengths), "ragged_ms": ms_r, "per_video_ms": ms_p,
                              "ragged_frames_per_s": sum(lengths) / ms_r * 1e3, "per_video_frames_per_s": sum(lengths) / ms_p * 1e3}
-    print(json.dumps(res))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=600)
+    ap.add_argument("--videos", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=30)
+    a = ap.parse_args()
+    print(json.dumps(measure(a.frames, a.videos, a.steps)))
 
 
 if __name__ == "__main__":
