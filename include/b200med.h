@@ -344,6 +344,17 @@ int b200med_tcn_stage_bwd(const float *dlogits, const float *xin, int32_t in_dim
                           float *d_in_b, float *layer_grads, float *d_out_w, float *d_out_b, float *dx,
                           void *stream);
 
+/* The same stage forward for INFERENCE on the tensor cores (eval mode; bulk ragged batches): the dilated residual layers
+ * run as bf16 tcgen05 MMAs over 128-frame tiles (taps = TMA box loads at row offsets of the bf16 activation copy), the
+ * residual stream stays fp32.  res [2][T][64] f32, opn [2][T][64] bf16 (128-byte aligned), wb16 [n_layers][256][64] bf16 and
+ * pack are caller-allocated scratch; p_in as in b200med_tcn_stage_fwd; logits [C, T] OUT.  2e-2 bar of the bf16 mode.      */
+int b200med_tcn_stage_fwd_bf16(const float *x, int32_t in_dim, int32_t softmax_in, const float *in_w,
+                               const float *in_b, const void *const *layer_ptrs, int32_t n_layers,
+                               const float *out_w, const float *out_b, int32_t C, int64_t T,
+                               int32_t causal, const int32_t *tloc, const int32_t *trem, float *p_in,
+                               float *res, void *opn, float *pack, void *wb16, float *logits,
+                               void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimiser: Adam with coupled L2 decay, torch.optim.Adam semantics (modeling_utils.py:221-222)
  * ---------------------------------------------------------------------------------------------- */

@@ -470,6 +470,172 @@ tcn_softmax_bwd_kernel(const float *__restrict__ p, const float *__restrict__ dp
         if (c < C) dlogits[(long long)c * T + t] = pv[c] * (dv[c] - dot);
 }
 
+// ------------------------------------------------------------------------------------------------ bf16 tcgen05 layer (inference)
+// Bulk inference (ragged batches of many videos: ensemble inference, BASELINE config 5) is bound by the fp32 SIMT issue rate
+// of the kernels above (~17 TFLOP/s measured).  The layer is a dense contraction -- [128 frames x 192] x [192 x 64], then
+// [128 x 64] x [64 x 64] -- so the inference path runs it on the tensor cores: one CTA per 128-frame tile,
+//   * A operand of tap k = rows t0 + off_k .. + 127 of the bf16 activation copy [T, 64]: one frame is one 128-byte row = one
+//     row of the 128B swizzle atom, so a tap is ONE TMA box load at a row offset (rows before / after the table are zero-filled
+//     by TMA; rows that belong to a neighbouring video of a ragged batch are zeroed in shared memory before the MMA);
+//   * B operand = the layer's weights as bf16 [tap*64 + co][ci] (K-major), one TMA box of 256 x 64;
+//   * D1 (64 TMEM columns) = sum of 3 taps x 4 K-steps of tcgen05.mma (M = 128, N = 64, K = 16); epilogue 1: tcgen05.ld, + b_d,
+//     ReLU, bf16, written as the K-major swizzled A operand of the 1x1 convolution; D2 = 4 more MMAs; epilogue 2: + b_1 + the
+//     fp32 residual, staged through padded shared memory so that the tile leaves as two coalesced sweeps (fp32 residual stream
+//     [T, 64] for the next layer's epilogue and the class convolution, bf16 copy [T, 64] for the next layer's TMA).
+// The residual stream stays fp32: only the MMA operands are rounded to bf16 (2e-2 bar of the bf16 mode).
+constexpr int kTileF = 128;                                  // frames per CTA = UMMA M
+constexpr int kATapBytes = kTileF * kF * 2;                  // 16 KB
+constexpr int kWTileBytes = 4 * kF * kF * 2;                 // 32 KB: 3 taps + 1x1
+constexpr int kStageRow = kF + 1;                            // padded fp32 staging row (bank-conflict-free row-per-thread access)
+constexpr size_t kSmemBf16 = 3 * kATapBytes + kWTileBytes + kATapBytes + 1024 /*align*/ + 512 /*bias*/ + 64 /*barriers, TMEM slot*/;   // 99 904 B: two CTAs per SM
+static_assert(kTileF * kStageRow * 4 <= 3 * kATapBytes, "the fp32 staging tile reuses the tap buffers");
+
+__global__ void __launch_bounds__(kTileF)
+tcn_layer_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                          const float *__restrict__ res_in, float *__restrict__ res_out, __nv_bfloat16 *__restrict__ opn_out,
+                          const float *__restrict__ bias /* b_d | b_1 */, int layer, TcnGeom g) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char *a_sm = smem;                               // [3][128 rows][128 B]
+    unsigned char *w_sm = a_sm + 3 * kATapBytes;              // [256 rows][128 B]
+    unsigned char *y_sm = w_sm + kWTileBytes;                 // [128 rows][128 B]
+    float *bias_sm = reinterpret_cast<float *>(y_sm + kATapBytes);            // [128]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(bias_sm + 2 * kF);
+    uint64_t *mma_bar = full_bar + 1;                         // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_bar + 2);
+    float *stage = reinterpret_cast<float *>(a_sm);          // [128][65] fp32, valid once the tap MMAs have completed
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long t0 = (long long)blockIdx.x * kTileF;
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_w) : "memory");
+        bar_init(full_bar, 1); bar_init(&mma_bar[0], 1); bar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s_addr(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    bias_sm[tid] = __ldg(bias + tid);                         // 128 threads, 128 floats
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {
+        bar_expect_tx(full_bar, 3 * kATapBytes + kWTileBytes);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tma_load_2d(a_sm + k * kATapBytes, &tmap_a, full_bar, 0, (int)(t0 + g.off(k)));
+        tma_load_2d(w_sm, &tmap_w, full_bar, 0, layer * 4 * kF);
+    }
+    bar_wait(full_bar, 0);
+    // ragged batches: a tap row that belongs to another video is zero (TMA already zero-filled rows outside the table)
+    {
+        const long long t = t0 + tid;
+        if (t < g.T) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (!tap_ok(g, t, g.off(k))) {
+                    uint4 *row = reinterpret_cast<uint4 *>(a_sm + k * kATapBytes + tid * 128);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) row[c] = make_uint4(0u, 0u, 0u, 0u);
+                }
+        }
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    const uint32_t idesc = make_idesc(kTileF, kF, false, false);
+    if (tid == 0) {
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int s = 0; s < 4; ++s)       // K-major, SW128: 8-row groups 1024 B apart (SBO), one UMMA_K step = 32 B
+                umma_bf16(tmem_base, make_smem_desc(s_addr(a_sm + k * kATapBytes) + s * 32, 16, 1024),
+                          make_smem_desc(s_addr(w_sm + k * kF * 128) + s * 32, 16, 1024), idesc, (k | s) ? 1u : 0u);
+        umma_commit(&mma_bar[0]);
+    }
+    // epilogue 1: y = relu(D1 + b_d) -> bf16 -> K-major swizzled operand tile of the 1x1 convolution (row = this thread)
+    bar_wait(&mma_bar[0], 0);
+    tcgen05_fence_after();
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    {
+        uint32_t v[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            tmem_ld32(t_lane + (uint32_t)(h * 32), v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = fmaxf(__uint_as_float(v[c * 8 + j]) + bias_sm[h * 32 + c * 8 + j], 0.f);
+                const int slot = h * 4 + c;
+                *reinterpret_cast<uint4 *>(y_sm + tid * 128 + ((slot ^ (tid & 7)) << 4)) =
+                    make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            }
+        }
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tcgen05_fence_after();
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+            umma_bf16(tmem_base + kF, make_smem_desc(s_addr(y_sm) + s * 32, 16, 1024),
+                      make_smem_desc(s_addr(w_sm + 3 * kF * 128) + s * 32, 16, 1024), idesc, s ? 1u : 0u);
+        umma_commit(&mma_bar[1]);
+    }
+    // the tap buffers are free (their MMAs completed before mma_bar[0]): stage the fp32 residual tile there, coalesced
+    const long long rows = min((long long)kTileF, g.T - t0);
+    for (int e = tid; e < rows * (kF / 4); e += kTileF) {
+        const int r = e / (kF / 4), c4 = e % (kF / 4);
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(res_in + (t0 + r) * kF) + c4);
+        float *d = stage + r * kStageRow + c4 * 4;
+        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+    }
+    __syncthreads();
+    // epilogue 2: out = residual + D2 + b_1 (row = this thread), written back into the staging tile
+    bar_wait(&mma_bar[1], 0);
+    tcgen05_fence_after();
+    {
+        uint32_t v[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            tmem_ld32(t_lane + (uint32_t)(kF + h * 32), v);
+            if (tid < rows) {
+                float *d = stage + tid * kStageRow + h * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) d[j] += __uint_as_float(v[j]) + bias_sm[kF + h * 32 + j];
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    // coalesced sweeps out: fp32 residual stream and its bf16 copy
+    for (int e = tid; e < rows * (kF / 4); e += kTileF) {
+        const int r = e / (kF / 4), c4 = e % (kF / 4);
+        const float *d = stage + r * kStageRow + c4 * 4;
+        *reinterpret_cast<float4 *>(res_out + (t0 + r) * kF + c4 * 4) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<uint2 *>(opn_out + (t0 + r) * kF + c4 * 4) = make_uint2(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]));
+    }
+    if (warp == 0) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
+// wb16[layer][tap*64 + co][ci] (tap 3 = the 1x1 convolution) = bf16 of the fp32 pack's WdB | W1B block
+__global__ void __launch_bounds__(256)
+tcn_pack_bf16_kernel(const float *__restrict__ pack, __nv_bfloat16 *__restrict__ wb16) {
+    const int layer = blockIdx.y;
+    const float *src = pack + (long long)layer * kPackFloats + kOffWdB;
+    __nv_bfloat16 *dst = wb16 + (long long)layer * 4 * kF * kF;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * kF * kF; i += gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
 static int make_geom(TcnGeom &g, int64_t T, int32_t dilation, int32_t causal, const int32_t *tloc, const int32_t *trem) {
     g.T = T; g.tloc = tloc; g.trem = trem;
     if (causal) { g.off0 = -2 * dilation; g.off1 = -dilation; g.off2 = 0; g.centre = 2; }
@@ -741,4 +907,46 @@ TCN_API int b200med_tcn_stage_bwd(const float *dlogits, const float *xin, int32_
         return b200med_linear_bwd_data_f32(dA, in_w, nullptr, dx, T, kF, in_dim, stream);
     }
     return B200MED_OK;
+}
+
+
+// Inference-only stage forward on the bf16 tcgen05 layer kernel (eval mode: no dropout, nothing kept for a backward).
+//   res [2][T][64] f32 and opn [2][T][64] bf16: ping-pong residual stream / operand copy; wb16 [n_layers][256][64] bf16.
+TCN_API int b200med_tcn_stage_fwd_bf16(const float *x, int32_t in_dim, int32_t softmax_in, const float *in_w, const float *in_b,
+                                       const void *const *layer_ptrs, int32_t n_layers, const float *out_w, const float *out_b,
+                                       int32_t C, int64_t T, int32_t causal, const int32_t *tloc, const int32_t *trem,
+                                       float *p_in, float *res, void *opn, float *pack, void *wb16, float *logits, void *stream) {
+    B200MED_REQUIRE(T >= 1 && n_layers >= 1 && n_layers <= 30 && in_dim >= 1, "bad shape");
+    B200MED_REQUIRE(T + 2 * (1LL << (n_layers - 1)) < (1LL << 31), "T too large for 32-bit TMA coordinates");
+    B200MED_REQUIRE(x && in_w && in_b && layer_ptrs && out_w && out_b && res && opn && pack && wb16 && logits, "null pointer");
+    B200MED_REQUIRE(!softmax_in || (p_in && in_dim == C), "softmax_in needs p_in and in_dim == C");
+    B200MED_REQUIRE((uintptr_t)opn % 128 == 0 && (uintptr_t)wb16 % 128 == 0 && (uintptr_t)res % 16 == 0, "buffers must be 128-byte aligned");
+    if (!b200med_has_tcgen05()) { set_error("the bf16 TeCNo path needs a compute-capability 10.x device"); return B200MED_E_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const float *xin = x;
+    if (softmax_in) {
+        if (int e = b200med_tcn_softmax_fwd(x, p_in, T, C, stream)) return e;
+        xin = p_in;
+    }
+    const size_t plane = (size_t)T * kF;
+    __nv_bfloat16 *opn16 = reinterpret_cast<__nv_bfloat16 *>(opn);
+    if (int e = b200med_linear_fwd_f32(xin, in_w, in_b, res, T, kF, in_dim, 0, stream)) return e;
+    if (int e = b200med_cast_f32_to_bf16(res, opn16, (int64_t)plane, stream)) return e;
+    if (int e = b200med_tcn_pack(layer_ptrs, n_layers, pack, stream)) return e;
+    tcn_pack_bf16_kernel<<<dim3(8, (unsigned)n_layers), 256, 0, st>>>(pack, reinterpret_cast<__nv_bfloat16 *>(wb16));
+    if (int e = after_launch("tcn_pack_bf16_kernel")) return e;
+    CUtensorMap map_a[2], map_w;
+    for (int i = 0; i < 2; ++i)
+        if (int e = make_tmap(&map_a[i], opn16 + (size_t)i * plane, kF, T, kF, kF, kTileF)) return e;
+    if (int e = make_tmap(&map_w, wb16, kF, (long long)n_layers * 4 * kF, kF, kF, 4 * kF)) return e;
+    if (int e = opt_in_smem(tcn_layer_fwd_bf16_kernel, kSmemBf16)) return e;
+    for (int l = 0; l < n_layers; ++l) {
+        TcnGeom g; make_geom(g, T, 1 << l, causal, tloc, trem);
+        const int src = l & 1, dst = (l + 1) & 1;
+        tcn_layer_fwd_bf16_kernel<<<(unsigned)((T + kTileF - 1) / kTileF), kTileF, kSmemBf16, st>>>(
+            map_a[src], map_w, res + (size_t)src * plane, res + (size_t)dst * plane, opn16 + (size_t)dst * plane,
+            pack + (size_t)l * kPackFloats + kOffBias, l, g);
+        if (int e = after_launch("tcn_layer_fwd_bf16_kernel")) return e;
+    }
+    return b200med_tcn_out_fwd(res + (size_t)(n_layers & 1) * plane, out_w, out_b, logits, T, C, stream);
 }

@@ -196,6 +196,8 @@ def define_model_objects(exp_kwargs: dict, in_features_dict: dict, device, class
         torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(42)
     model = instantiate_model(exp_kwargs, in_features_dict[exp_kwargs["data_type"]], window_size, device).to(device)
+    if isinstance(model, MultiStageModel):
+        model.precision = precision
     if hasattr(model, "use_cudnn"):
         model.use_cudnn = precision != "fp32"
         if precision == "bf16" and ops.has_tcgen05() and exp_kwargs.get("lstm_impl", "b200") in ("b200", "b200_per_step"):

@@ -67,13 +67,14 @@ class SingleStageModel(nn.Module):
         return ps + [self.conv_out_classes.weight, self.conv_out_classes.bias]
 
     def run_fused(self, x: torch.Tensor, softmax_in: bool = False, seed: int = 0, layer_base: int = 0, geom=(None, None),
-                  seed_dev=None):
+                  seed_dev=None, precision: str = "fp32"):
         """x [1, F, T] (or the previous stage's logits [1, C, T] with ``softmax_in``) -> logits [1, C, T]."""
         tcn.require_cuda(x)
         cfg = self._cfgs.get(softmax_in)
         if cfg is None:
             cfg = self._cfgs[softmax_in] = tcn.StageConfig(len(self.layers), self.causal_conv, softmax_in)
         cfg.layer_base, cfg.seed, cfg.seed_dev = layer_base, seed, seed_dev
+        cfg.precision = precision
         cfg.drop_p = [float(l.dropout.p) if (self.training and l.dropout.training) else 0.0 for l in self.layers]
         cfg.tloc, cfg.trem = geom
         xin = x[0] if softmax_in else x[0].t()      # [C, T] logits, or [T, F] rows (a free view of the [1, T, F] batch)
@@ -104,6 +105,9 @@ class MultiStageModel(nn.Module):
         # CUDA-graph training (engine.FrameTrainStep): a host seed fixed at capture + an int64 DEVICE counter advanced inside
         # the captured step, so that every replay draws a fresh dropout mask
         self.graph_seed = None   # (host seed, device counter tensor) or None
+        # "bf16" (set by define_model_objects from exp_kwargs['precision']): INFERENCE runs the layers on the tcgen05 kernel
+        # (bf16 operands, fp32 accumulation and residual stream, 2e-2 bar); training always uses the fp32 kernels
+        self.precision = "fp32"
 
     def _seed(self) -> int:
         if not self.training:
@@ -119,10 +123,10 @@ class MultiStageModel(nn.Module):
                 seed_dev.add_(1)
             else:
                 seed = self._seed()
-            out = self.stage1.run_fused(x, False, seed, 0, geom, seed_dev)
+            out = self.stage1.run_fused(x, False, seed, 0, geom, seed_dev, self.precision)
             outs = [out]
             for i, s in enumerate(self.stages):
-                out = s.run_fused(out, True, seed, (i + 1) * self.num_layers, geom, seed_dev)
+                out = s.run_fused(out, True, seed, (i + 1) * self.num_layers, geom, seed_dev, self.precision)
                 outs.append(out)
             return torch.stack(outs, dim=0)
         if geom[0] is not None:

@@ -493,3 +493,25 @@ def tcn_stage_bwd(dlogits, xin, softmax_in, in_w, out_w, n_layers, causal, acts,
          C.c_uint64(int(layer_base)), _ptr(acts), _ptr(ys), _ptr(pack), _ptr(ws), _ptr(d_in_w), _ptr(d_in_b), _ptr(layer_grads),
          _ptr(d_out_w), _ptr(d_out_b), _ptr(dx), _stream())
     return dict(dx=dx, d_in_w=d_in_w, d_in_b=d_in_b, layer_grads=layer_grads, d_out_w=d_out_w, d_out_b=d_out_b)
+
+
+def tcn_stage_fwd_bf16(x, softmax_in, in_w, in_b, ptr_table, n_layers, out_w, out_b, causal, tloc=None, trem=None) -> torch.Tensor:
+    """Inference-only stage forward on the bf16 tcgen05 layer kernel -> logits [C, T]."""
+    x = _need(x, torch.float32, "x")
+    in_w = _need(in_w, torch.float32, "in_w"); out_w = _need(out_w, torch.float32, "out_w")
+    n_cls, in_dim = out_w.shape[0], in_w.shape[1]
+    T = x.shape[1] if softmax_in else x.shape[0]
+    dev = x.device
+    logits = torch.empty(n_cls, T, dtype=torch.float32, device=dev)
+    if T == 0:
+        return logits
+    p_in = torch.empty(T, n_cls, dtype=torch.float32, device=dev) if softmax_in else None
+    res = torch.empty(2, T, TCN_MAPS, dtype=torch.float32, device=dev)
+    opn = torch.empty(2, T, TCN_MAPS, dtype=torch.bfloat16, device=dev)
+    pack = torch.empty(n_layers, TCN_PACK_FLOATS, dtype=torch.float32, device=dev)
+    wb16 = torch.empty(n_layers, 4 * TCN_MAPS, TCN_MAPS, dtype=torch.bfloat16, device=dev)
+    tl, tr = _geom(tloc, trem)
+    call("b200med_tcn_stage_fwd_bf16", _ptr(x), in_dim, int(bool(softmax_in)), _ptr(in_w), _ptr(_need(in_b, torch.float32, "in_b")),
+         _ptr(_need(ptr_table, torch.int64, "ptr_table")), n_layers, _ptr(out_w), _ptr(_need(out_b, torch.float32, "out_b")), n_cls, T,
+         int(bool(causal)), tl, tr, _ptr(p_in), _ptr(res), _ptr(opn), _ptr(pack), _ptr(wb16), _ptr(logits), _stream())
+    return logits

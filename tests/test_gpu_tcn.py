@@ -277,3 +277,31 @@ def test_frame_graph_dropout_draws_a_fresh_mask_per_replay(fold_on_disk):
     losses = [mu.train_single_epoch(model, fe, tr, crit, opt, sched, DEV, kw)[0] for _ in range(3)]
     assert not opt._b200_frame_steps["failed"]
     assert len({round(l, 7) for l in losses}) == 3, losses
+
+
+@pytest.mark.parametrize("causal,lengths", [(True, [345]), (True, [300, 17, 451, 64, 5, 129]), (False, [200, 77, 130])])
+def test_bf16_tcgen05_inference_matches_fp32(ops, causal, lengths):
+    """Inference in the bf16 mode (dilated residual layers as tcgen05 MMAs over 128-frame tiles, taps as TMA box loads at row
+    offsets, fp32 residual stream) against the fp32 SIMT kernels on the same weights: logits within the 2e-2 bar of the bf16
+    mode, frame predictions equal except near ties; ragged batches never leak across video boundaries."""
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    _, m = _models(causal, 58)
+    m.eval()
+    g = torch.Generator().manual_seed(len(lengths))
+    frames = torch.randn(sum(lengths), 58, generator=g).to(DEV)
+    ref = m.forward_ragged(frames, lengths)
+    m.precision = "bf16"
+    out = m.forward_ragged(frames, lengths)
+    m.precision = "fp32"
+    assert out.shape == ref.shape
+    for s in range(ref.shape[0]):
+        ok, err = close(out[s], ref[s], 2e-2); assert ok, f"stage {s}: {err}"
+    agree = (out[-1].argmax(0) == ref[-1].argmax(0)).float().mean().item()
+    assert agree > 0.98, agree
+    # a video's logits do not depend on its neighbours in the batch
+    if len(lengths) > 1:
+        m.precision = "bf16"
+        alone = m.forward_ragged(frames[:lengths[0]], lengths[:1])
+        m.precision = "fp32"
+        ok, err = close(out[:, :, :lengths[0]], alone, 1e-6); assert ok, err
