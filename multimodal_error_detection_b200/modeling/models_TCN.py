@@ -74,7 +74,7 @@ class SingleStageModel(nn.Module):
         if cfg is None:
             cfg = self._cfgs[softmax_in] = tcn.StageConfig(len(self.layers), self.causal_conv, softmax_in)
         cfg.layer_base, cfg.seed, cfg.seed_dev = layer_base, seed, seed_dev
-        cfg.precision = precision
+        cfg.precision, cfg.grad_enabled = precision, torch.is_grad_enabled()
         cfg.drop_p = [float(l.dropout.p) if (self.training and l.dropout.training) else 0.0 for l in self.layers]
         cfg.tloc, cfg.trem = geom
         xin = x[0] if softmax_in else x[0].t()      # [C, T] logits, or [T, F] rows (a free view of the [1, T, F] batch)

@@ -27,6 +27,7 @@ class StageConfig:
         self.n_layers, self.causal, self.softmax_in, self.layer_base = n_layers, bool(causal), bool(softmax_in), layer_base
         self.drop_p: List[float] = [0.0] * n_layers     # per layer, 0 in eval mode
         self.seed = 0
+        self.grad_enabled = True                          # torch.is_grad_enabled() at call time (set by the caller)
         self.precision = "fp32"                          # "bf16": inference runs the layers on the tcgen05 kernel
         self.seed_dev: Optional[torch.Tensor] = None     # int64 device scalar added to the seed on the device (CUDA graphs)
         self.tloc: Optional[torch.Tensor] = None         # ragged batch geometry (None = one video)
@@ -67,7 +68,9 @@ class TcnStageFunction(torch.autograd.Function):
         L = cfg.n_layers
         _check(x, params)
         in_w, in_b, out_w, out_b = params[0], params[1], params[-2], params[-1]
-        keep = any(ctx.needs_input_grad)
+        # needs_input_grad ignores torch.no_grad() (it mirrors requires_grad), and inside forward() grad mode is always off:
+        # the caller records the grad mode in the config
+        keep = cfg.grad_enabled and any(ctx.needs_input_grad)
         if cfg.precision == "bf16" and not keep and max(cfg.drop_p) == 0.0 and ops.has_tcgen05():
             # inference in the bf16 mode: layers as tcgen05 MMAs over 128-frame tiles, fp32 residual stream
             return ops.tcn_stage_fwd_bf16(x.detach().contiguous().float(), cfg.softmax_in, in_w.detach().view(MAPS, -1), in_b.detach(),

@@ -294,7 +294,7 @@ def test_bf16_tcgen05_inference_matches_fp32(ops, causal, lengths):
     m.precision = "bf16"
     out = m.forward_ragged(frames, lengths)
     m.precision = "fp32"
-    assert out.shape == ref.shape
+    assert out.shape == ref.shape and not torch.equal(out, ref)      # really another arithmetic
     for s in range(ref.shape[0]):
         ok, err = close(out[s], ref[s], 2e-2); assert ok, f"stage {s}: {err}"
     agree = (out[-1].argmax(0) == ref[-1].argmax(0)).float().mean().item()
