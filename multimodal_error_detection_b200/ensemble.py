@@ -26,7 +26,7 @@ from .table import FrameTable, WindowIndex
 
 @torch.no_grad()
 def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwargs: dict, kin_stats: Optional[dict] = None,
-                            frames_per_pass: int = 1 << 16) -> torch.Tensor:
+                            frames_per_pass: int = 1 << 17) -> torch.Tensor:
     """Frame-level predictions [N] f32 (argmax of the LAST stage, modeling_utils.py:370 / :751) for every frame of the
     table.  Frame-path inputs: raw image features through the FeatureExtractor, kinematics standardised
     (CustomFrameDataset.py:93-95), concatenated on the feature axis (modeling_utils.py:41-42)."""
@@ -38,6 +38,10 @@ def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwa
     N, dev = table.n_frames, table.device
     preds = torch.empty(N, dtype=torch.float32, device=dev)
     dt = exp_kwargs["data_type"]
+    # ragged geometry of the WHOLE table, once, on the device (a pass takes slices: no host work, no copy per pass)
+    lens_dev = torch.from_numpy(lengths.astype(np.int64)).to(dev)
+    tloc = (torch.arange(N, device=dev) - torch.repeat_interleave(table.offsets[:-1], lens_dev, output_size=N)).to(torch.int32)
+    trem = (torch.repeat_interleave(lens_dev, lens_dev, output_size=N) - 1 - tloc).to(torch.int32)
     v = 0
     while v < len(lengths):
         w, n = v, 0
@@ -56,8 +60,8 @@ def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwa
                                            ops.expand_stat(kin_stats["std"], D, 1, dev))
             cols.append(kin)
         frames = cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
-        logits = model.forward_ragged(frames, [int(x) for x in lengths[v:w]])        # [stages, C, n]
-        preds[r0:r1] = torch.argmax(logits[-1], dim=0).float()
+        logits = model(frames.contiguous().float().unsqueeze(0).permute(0, 2, 1), (tloc[r0:r1], trem[r0:r1]))   # [stages, 1, C, n]
+        preds[r0:r1] = torch.argmax(logits[-1, 0], dim=0).float()
         v = w
     return preds
 
@@ -95,7 +99,7 @@ def fuse(frame_preds: torch.Tensor, index: WindowIndex, window_probs: torch.Tens
 
 
 def ensemble_inference(table: FrameTable, dataset, frame_objects, window_objects, kin_stats=None, batch_size: int = 8192,
-                       frames_per_pass: int = 1 << 16):
+                       frames_per_pass: int = 1 << 17):
     """frame_objects / window_objects = (feature_extractor, model, exp_kwargs); ``dataset`` = the window dataset built
     over ``table`` (its ``index`` is the window index after Needle-Drop deletion).  Returns the dict of :func:`fuse` plus
     the two models' raw outputs; with torch.distributed initialised the counts are summed over the ranks."""

@@ -26,7 +26,7 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-def measure(videos: int = 2048, reps: int = 3, batch: int = 8192, frames_per_pass: int = 1 << 16, dist_init: bool = True):
+def measure(videos: int = 2048, reps: int = 3, batch: int = 8192, frames_per_pass: int = 1 << 17, dist_init: bool = True):
     """-> result dict on rank 0 (None elsewhere)."""
     args = argparse.Namespace(videos=videos, reps=reps, batch=batch, frames_per_pass=frames_per_pass)
     if dist_init:
@@ -91,7 +91,7 @@ def measure(videos: int = 2048, reps: int = 3, batch: int = 8192, frames_per_pas
             "ms_frame_model": ms[0], "ms_window_model": ms[1], "ms_vote_fusion_counts": ms[2],
             "frame_model_one_forward_per_video_ms": per_video_ms,
             "frame_model_ragged_ms_per_video": ms[0] / args.videos,
-            "config": "frame: FE(2048-512-256-32, bf16 tcgen05) + TeCNo(2x8x64, fp32, ragged passes of <= %d frames); window: W=16 S=4 "
+            "config": "frame: FE(2048-512-256-32, bf16 tcgen05) + TeCNo(2x8x64, bf16 tcgen05 layers + fp32 residual stream, ragged passes of <= %d frames); window: W=16 S=4 "
                       "FE + LSTM(58,16,3,128) bf16, batch %d; window vote + soft vote + confusion counts on the device" % (args.frames_per_pass, args.batch),
             "counts_tn_fp_fn_tp": counts, "scaling": "weak", "data": "synthetic"})
     return None
@@ -102,7 +102,7 @@ def main():
     ap.add_argument("--videos", type=int, default=2048)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--frames-per-pass", type=int, default=1 << 16)
+    ap.add_argument("--frames-per-pass", type=int, default=1 << 17)
     a = ap.parse_args()
     res = measure(a.videos, a.reps, a.batch, a.frames_per_pass)
     if res is not None:
