@@ -529,6 +529,17 @@ tcn_layer_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
         for (int k = 0; k < 3; ++k) tma_load_2d(a_sm + k * kATapBytes, &tmap_a, full_bar, 0, (int)(t0 + g.off(k)));
         tma_load_2d(w_sm, &tmap_w, full_bar, 0, layer * 4 * kF);
     }
+    // The fp32 residual tile (this CTA's rows of res_in: one contiguous 32 KB block) is fetched into registers NOW, so its
+    // DRAM / L2 latency runs under the TMA loads, the tap MMAs and epilogue 1 (first version: fetched after the tap MMAs,
+    // 68 % of the warp stalls were long_scoreboard -- profiles/r1_ncu_tcn.md); it is parked in shared memory once the tap
+    // buffers are free.
+    const long long rows = min((long long)kTileF, g.T - t0);
+    float4 pre[kF / 4];
+#pragma unroll
+    for (int i = 0; i < kF / 4; ++i) {
+        const int e = tid + i * kTileF, r = e / (kF / 4), c4 = e % (kF / 4);
+        pre[i] = r < rows ? __ldg(reinterpret_cast<const float4 *>(res_in + (t0 + r) * kF) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     bar_wait(full_bar, 0);
     // ragged batches: a tap row that belongs to another video is zero (TMA already zero-filled rows outside the table)
     {
@@ -588,13 +599,12 @@ tcn_layer_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
                       make_smem_desc(s_addr(w_sm + 3 * kF * 128) + s * 32, 16, 1024), idesc, s ? 1u : 0u);
         umma_commit(&mma_bar[1]);
     }
-    // the tap buffers are free (their MMAs completed before mma_bar[0]): stage the fp32 residual tile there, coalesced
-    const long long rows = min((long long)kTileF, g.T - t0);
-    for (int e = tid; e < rows * (kF / 4); e += kTileF) {
-        const int r = e / (kF / 4), c4 = e % (kF / 4);
-        const float4 x = __ldg(reinterpret_cast<const float4 *>(res_in + (t0 + r) * kF) + c4);
+    // the tap buffers are free (their MMAs completed before mma_bar[0]): park the prefetched residual tile there
+#pragma unroll
+    for (int i = 0; i < kF / 4; ++i) {
+        const int e = tid + i * kTileF, r = e / (kF / 4), c4 = e % (kF / 4);
         float *d = stage + r * kStageRow + c4 * 4;
-        d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+        d[0] = pre[i].x; d[1] = pre[i].y; d[2] = pre[i].z; d[3] = pre[i].w;
     }
     __syncthreads();
     // epilogue 2: out = residual + D2 + b_1 (row = this thread), written back into the staging tile
