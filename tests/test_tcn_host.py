@@ -93,3 +93,47 @@ def test_unsupported_shape_uses_stock_layers_and_cpu_raises():
     m64 = models_TCN.MultiStageModel(2, 3, 64, 10, 2, True).eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m64(torch.randn(1, 10, 20))
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from multimodal_error_detection_b200 import parallel
+from multimodal_error_detection_b200.dataset.CustomFrameDataset import FrameLoader
+rank, _, world = parallel.init_from_env("gloo")
+
+class Videos:                      # stands in for CustomFrameDataset: only len() and the index order matter here
+    def __len__(self): return 7
+    def __getitem__(self, i): raise AssertionError("indices() must not touch the data")
+
+mine = list(FrameLoader(Videos(), shuffle=True, generator=torch.Generator().manual_seed(42), rank=rank, world_size=world).indices())
+order = list(FrameLoader(Videos(), shuffle=True, generator=torch.Generator().manual_seed(42)).indices())
+assert mine == order[rank::world], (mine, order)          # every rank walks the same seed-42 order and takes every world-th video
+# the only exchange of the frame / ensemble paths besides the gradient all-reduce: the sum of the confusion counts
+counts = torch.tensor([rank + 1, 10 * (rank + 1), 0, 5], dtype=torch.int64)
+parallel.allreduce_sum_(counts)
+assert counts.tolist() == [3, 30, 0, 10], counts
+got = [None] * world
+dist.all_gather_object(got, mine)
+assert sorted(sum(got, [])) == list(range(7))              # the shards partition the fold
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_frame_sharding_and_count_reduce(tmp_path):
+    """N > 1 path of the frame / ensemble code on the host: videos are dealt round-robin over the ranks from one shared
+    shuffled order (SURVEY section 8e), confusion counts are summed."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29741",
+                   CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script), root], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
