@@ -58,6 +58,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.costs = []
         self.nvml = self.handle = None
         try:
             import pynvml
@@ -68,6 +69,10 @@ class ClockSampler(threading.Thread):
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
+            t0 = time.perf_counter()
+            self._sample_nvml()                      # priming query: only its COST is kept (the GPU is idle right now)
+            self.rows.clear()
+            self.first_cost = time.perf_counter() - t0
         except Exception:
             self.nvml = None
 
@@ -87,7 +92,14 @@ class ClockSampler(threading.Thread):
             self.rows.append([float(c[0]), float(c[1])] + [v.lower().startswith("active") for v in c[2:6]])
 
     def run(self):
+        # Sparse on purpose: an NVML query is an RM call that takes ~0.1 ms on a one-GPU box but was measured at ~9 ms per
+        # query on a two-GPU box, where sampling every 2 ms stretched the timed steps from 2.8 to 6.5 ms.  The interval backs
+        # off to 25x the cost of the last query, so that sampling stays below ~4 % of the region whatever a query costs.
+        base = float(os.environ.get("B200MED_CLOCK_INTERVAL_MS", "10")) * 1e-3
+        if self.nvml is not None and self._stop_evt.wait(max(base, 25.0 * getattr(self, "first_cost", 0.0))):
+            return
         while not self._stop_evt.is_set():
+            t0 = time.perf_counter()
             try:
                 if self.nvml is not None:
                     self._sample_nvml()
@@ -95,16 +107,24 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.002 if self.nvml is not None else 0.1)
+            cost = time.perf_counter() - t0
+            self.costs.append(cost)
+            self._stop_evt.wait(max(base if self.nvml is not None else 0.1, 25.0 * cost))
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
+        if not self.rows:                            # region shorter than the (backed-off) interval: one sample at its very end
+            try:
+                self._sample_nvml() if self.nvml is not None else self._sample_smi()
+            except Exception:
+                pass
         sm = [r[0] for r in self.rows]
         mx = [r[1] for r in self.rows]
         reasons = sorted({n for r in self.rows for n, v in zip(self.NAMES, r[2:6]) if v})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi",
+                "query_ms": 1e3 * statistics.median(self.costs) if self.costs else None}
 
 
 def measured_peaks():
@@ -292,22 +312,27 @@ def run_gpu(args):
         step(i)
     torch.cuda.synchronize()
     parallel.barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("B200MED_NO_CLOCKS")) else None
     if sampler:
         sampler.start()
     launches0 = _lib.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     gather_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     torch.cuda.synchronize()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K)]      # per-step marks (diagnostics: spread of the steps)
     ev[0].record()
     for i in range(K):
         if stepper.graph is None and not stepper.prefetch:
             stepper.gather_events = gather_ev[i]
         step(Wm + i)
+        step_ev[i].record()
     ev[1].record()
     torch.cuda.synchronize()
     parallel.barrier()
     step_ms = parallel.max_over_ranks(ev[0].elapsed_time(ev[1]) / K, device)
+    marks = [ev[0]] + step_ev
+    per_step = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(K))
+    step_spread = {"min": per_step[0], "median": per_step[K // 2], "max": per_step[-1]}
     stepper.gather_events = None
     launches = (_lib.launch_count() - launches0) if stepper.graph is None else stepper.launches_per_step * K
     clocks = sampler.stop() if sampler else None
@@ -449,7 +474,8 @@ def run_gpu(args):
                            "l2": "every step gathers a fresh ~1.1 GB slice of a >2 GB table (inputs larger than the 126 MB L2)",
                            "gather_variant": args.gather_variant},
                 "roofline": roofline, "roofline_gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-                "clocks": clocks, "final_loss": final_loss, "other_configs": other}
+                "clocks": clocks, "final_loss": final_loss, "ms_per_step_spread_rank0": step_spread,
+                "other_configs": other}
         print(json.dumps(line), flush=True)
     if world > 1:
         # graphs that captured NCCL work must be gone before the communicator is torn down; a wedged teardown must not
