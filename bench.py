@@ -310,16 +310,17 @@ def run_gpu(args):
 
     for i in range(Wm):
         step(i)
+    # NVML init + the priming query cost ~10 ms on a multi-GPU box: they happen BEFORE the barrier, or rank 0 would enter the
+    # timed region late and every other rank's first step would wait for it inside NCCL (measured: +7.6 ms on 20 steps)
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("B200MED_NO_CLOCKS")) else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    gather_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K)]      # per-step marks (diagnostics: spread of the steps)
     torch.cuda.synchronize()
     parallel.barrier()
-    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("B200MED_NO_CLOCKS")) else None
     if sampler:
         sampler.start()
     launches0 = _lib.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    gather_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    torch.cuda.synchronize()
-    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K)]      # per-step marks (diagnostics: spread of the steps)
     ev[0].record()
     for i in range(K):
         if stepper.graph is None and not stepper.prefetch:
