@@ -61,10 +61,16 @@ class SingleStageModel(nn.Module):
         return x.dim() == 3 and x.shape[0] == 1 and x.dtype == torch.float32 and self.fused_supported()
 
     def _stage_params(self):
-        ps = [self.conv_1x1.weight, self.conv_1x1.bias]
-        for l in self.layers:
-            ps += [l.conv_dilated.weight, l.conv_dilated.bias, l.conv_1x1.weight, l.conv_1x1.bias]
-        return ps + [self.conv_out_classes.weight, self.conv_out_classes.bias]
+        # cached: ~40 nn.Module attribute lookups per call otherwise (the eager frame step is host-bound).  The Parameter
+        # objects are stable (load_state_dict / .to() / the optimiser's re-homing change .data in place).
+        cache = self.__dict__.get("_param_cache")
+        if cache is None:
+            ps = [self.conv_1x1.weight, self.conv_1x1.bias]
+            for l in self.layers:
+                ps += [l.conv_dilated.weight, l.conv_dilated.bias, l.conv_1x1.weight, l.conv_1x1.bias]
+            ps += [self.conv_out_classes.weight, self.conv_out_classes.bias]
+            cache = self.__dict__["_param_cache"] = (ps, [l.dropout for l in self.layers])
+        return cache[0]
 
     def run_fused(self, x: torch.Tensor, softmax_in: bool = False, seed: int = 0, layer_base: int = 0, geom=(None, None),
                   seed_dev=None, precision: str = "fp32"):
@@ -75,10 +81,11 @@ class SingleStageModel(nn.Module):
             cfg = self._cfgs[softmax_in] = tcn.StageConfig(len(self.layers), self.causal_conv, softmax_in)
         cfg.layer_base, cfg.seed, cfg.seed_dev = layer_base, seed, seed_dev
         cfg.precision, cfg.grad_enabled = precision, torch.is_grad_enabled()
-        cfg.drop_p = [float(l.dropout.p) if (self.training and l.dropout.training) else 0.0 for l in self.layers]
+        params = self._stage_params()
+        cfg.drop_p = [float(d.p) if (self.training and d.training) else 0.0 for d in self.__dict__["_param_cache"][1]]
         cfg.tloc, cfg.trem = geom
         xin = x[0] if softmax_in else x[0].t()      # [C, T] logits, or [T, F] rows (a free view of the [1, T, F] batch)
-        return tcn.TcnStageFunction.apply(xin, cfg, *self._stage_params()).unsqueeze(0)
+        return tcn.TcnStageFunction.apply(xin, cfg, *params).unsqueeze(0)
 
     def forward(self, x, fused: bool = True):
         if fused and self.fused_ok(x):
