@@ -67,9 +67,10 @@ def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwa
 
 
 @torch.no_grad()
-def window_model_probabilities(dataset, feature_extractor, model, exp_kwargs: dict, batch_size: int = 8192) -> torch.Tensor:
+def window_model_probabilities(dataset, feature_extractor, model, exp_kwargs: dict, batch_size: int = 18944) -> torch.Tensor:
     """sigmoid(logit) [n] f32 of the binary window model for every window of the dataset (validate_single_epoch's forward,
-    modeling_utils.py:735-752, without the per-sample host loop)."""
+    modeling_utils.py:735-752, without the per-sample host loop).  Default batch = 148 SMs x 128 windows: the persistent LSTM
+    recurrence kernels own 128 windows per CTA, so this is the batch that puts one CTA on every SM."""
     from .modeling import modeling_utils as mu
     model.eval()
     if feature_extractor is not None:
@@ -98,7 +99,7 @@ def fuse(frame_preds: torch.Tensor, index: WindowIndex, window_probs: torch.Tens
     return dict(frame_windows=frame_windows, fused=fused, counts=counts)
 
 
-def ensemble_inference(table: FrameTable, dataset, frame_objects, window_objects, kin_stats=None, batch_size: int = 8192,
+def ensemble_inference(table: FrameTable, dataset, frame_objects, window_objects, kin_stats=None, batch_size: int = 18944,
                        frames_per_pass: int = 1 << 17):
     """frame_objects / window_objects = (feature_extractor, model, exp_kwargs); ``dataset`` = the window dataset built
     over ``table`` (its ``index`` is the window index after Needle-Drop deletion).  Returns the dict of :func:`fuse` plus

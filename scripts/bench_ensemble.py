@@ -26,7 +26,7 @@ def ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-def measure(videos: int = 2048, reps: int = 3, batch: int = 8192, frames_per_pass: int = 1 << 17, dist_init: bool = True):
+def measure(videos: int = 2048, reps: int = 3, batch: int = 18944, frames_per_pass: int = 1 << 17, dist_init: bool = True):
     """-> result dict on rank 0 (None elsewhere)."""
     args = argparse.Namespace(videos=videos, reps=reps, batch=batch, frames_per_pass=frames_per_pass)
     if dist_init:
@@ -101,7 +101,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--videos", type=int, default=2048)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--batch", type=int, default=18944,
+                    help="window-model inference batch: 148 SMs x 128 windows fills every SM with one recurrence CTA")
     ap.add_argument("--frames-per-pass", type=int, default=1 << 17)
     a = ap.parse_args()
     res = measure(a.videos, a.reps, a.batch, a.frames_per_pass)
