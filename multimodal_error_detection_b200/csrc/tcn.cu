@@ -20,11 +20,13 @@
 // thread): 38 CTAs, 25 % issue utilisation, 10 us per layer (profiles/r1_ncu_tcn.md).
 // Backward per layer = two launches:
 //   tcn_layer_bwd_hidden: dz = dout * mask, dpre = (dz W1) * (y > 0), and the layer's weight/bias gradient PARTIALS
-//                         (outer products of the 16-frame tiles, 144 register accumulators per thread, summed later in
-//                         fixed slot order by tcn_reduce_grads_kernel: deterministic, no atomics);
+//                         (outer products of the frame tiles, 144 register accumulators per thread, the record staged
+//                         through shared memory and copied out coalesced, slots summed later in fixed order by
+//                         tcn_reduce_grads_kernel: deterministic, no atomics);
 //   tcn_layer_bwd_input:  dx = dout + sum_k Wd[:, :, k]^T dpre[t - off_k]   (the same 3-tap tile product, transposed pack).
 // Ragged batches: `tloc` / `trem` (frame index inside its video / frames left after it) let several videos be
 // concatenated along T without taps crossing a video boundary (ensemble inference, BASELINE config 5); NULL = one video.
+// Bulk inference in the bf16 mode runs the layer on the tensor cores instead (tcn_layer_fwd_bf16_kernel, further down).
 #include "tcgen05.cuh"
 
 namespace b200med {
