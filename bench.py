@@ -472,7 +472,7 @@ def run_gpu(args):
                            "frames_per_gpu": n_frames, "windows_per_gpu": n_windows, "params": n_params,
                            "parallelism": f"dp{world}", "launch": graph_note, "lstm_impl": args.lstm_impl,
                            "gather_prefetch": bool(prefetch),
-                           "l2": "every step gathers a fresh ~1.1 GB slice of a >2 GB table (inputs larger than the 126 MB L2)",
+                           "l2": "every step gathers a fresh ~1.1 GB slice of a ~10 GB table (inputs larger than the 126 MB L2)",
                            "gather_variant": args.gather_variant},
                 "roofline": roofline, "roofline_gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
                 "clocks": clocks, "final_loss": final_loss, "ms_per_step_spread_rank0": step_spread,
@@ -498,7 +498,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--videos", type=int, default=1024)
+    ap.add_argument("--videos", type=int, default=2048,
+                    help="videos per GPU in the synthetic table (2048 -> ~1.2 M frames, 10 GB, ~21 full batches per pass: the K = 20 "
+                         "steps of the e2e measurement fit in one pass of the loader, like an epoch of a real fold does)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--lstm-impl", default="b200", choices=["b200", "b200_per_step", "cudnn"])
