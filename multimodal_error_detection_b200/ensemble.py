@@ -24,6 +24,19 @@ from . import ops
 from .table import FrameTable, WindowIndex
 
 
+def video_passes(lengths, frames_per_pass: int):
+    """Group consecutive videos into ragged passes of at most ``frames_per_pass`` frames (a video longer than the budget
+    is a pass of its own): list of (first video, one past the last video)."""
+    passes, v, n_videos = [], 0, len(lengths)
+    while v < n_videos:
+        w, n = v, 0
+        while w < n_videos and (w == v or n + int(lengths[w]) <= frames_per_pass):
+            n += int(lengths[w]); w += 1
+        passes.append((v, w))
+        v = w
+    return passes
+
+
 @torch.no_grad()
 def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwargs: dict, kin_stats: Optional[dict] = None,
                             frames_per_pass: int = 1 << 17) -> torch.Tensor:
@@ -42,11 +55,7 @@ def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwa
     lens_dev = torch.from_numpy(lengths.astype(np.int64)).to(dev)
     tloc = (torch.arange(N, device=dev) - torch.repeat_interleave(table.offsets[:-1], lens_dev, output_size=N)).to(torch.int32)
     trem = (torch.repeat_interleave(lens_dev, lens_dev, output_size=N) - 1 - tloc).to(torch.int32)
-    v = 0
-    while v < len(lengths):
-        w, n = v, 0
-        while w < len(lengths) and (w == v or n + lengths[w] <= frames_per_pass):
-            n += int(lengths[w]); w += 1
+    for v, w in video_passes(lengths, frames_per_pass):
         r0, r1 = int(off[v]), int(off[w])
         cols = []
         if dt in ("multimodal", "video"):
@@ -62,7 +71,6 @@ def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwa
         frames = cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
         logits = model(frames.contiguous().float().unsqueeze(0).permute(0, 2, 1), (tloc[r0:r1], trem[r0:r1]))   # [stages, 1, C, n]
         preds[r0:r1] = torch.argmax(logits[-1, 0], dim=0).float()
-        v = w
     return preds
 
 

@@ -137,3 +137,26 @@ def test_gloo_world2_frame_sharding_and_count_reduce(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script), root], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_video_passes_partition():
+    from multimodal_error_detection_b200.ensemble import video_passes
+    assert video_passes([], 10) == []
+    assert video_passes([3, 4, 5], 100) == [(0, 3)]
+    assert video_passes([3, 4, 5], 7) == [(0, 2), (2, 3)]
+    assert video_passes([30, 4, 5, 40, 1], 9) == [(0, 1), (1, 3), (3, 4), (4, 5)]       # over-long videos run alone
+    lens = np.random.default_rng(0).integers(1, 50, size=200)
+    passes = video_passes(lens, 120)
+    assert passes[0][0] == 0 and passes[-1][1] == 200 and all(a[1] == b[0] for a, b in zip(passes, passes[1:]))
+    assert all(lens[a:b].sum() <= 120 or b - a == 1 for a, b in passes)
+
+
+def test_header_constants_match_the_binding():
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "b200med.h")).read()
+    consts = dict(re.findall(r"#define (B200MED_TCN_\w+) (\d+)", header))
+    from multimodal_error_detection_b200 import ops
+    assert int(consts["B200MED_TCN_PACK_FLOATS"]) == ops.TCN_PACK_FLOATS == ref.PACK
+    assert int(consts["B200MED_TCN_GRAD_FLOATS"]) == ops.TCN_GRAD_FLOATS == ref.GRAD
