@@ -101,10 +101,15 @@ class FrameLoader:
     cell 2, lines 58-66): same shuffled video order (a real torch sampler over the indices), batches are the
     device-resident trial tensors with a leading batch dimension of 1."""
 
-    def __init__(self, dataset: CustomFrameDataset, shuffle: bool = False, generator=None, rank: int = 0, world_size: int = 1):
+    def __init__(self, dataset: CustomFrameDataset, shuffle: bool = False, generator=None, rank: int = 0, world_size: int = 1,
+                 even_shards: bool = None):
         from torch.utils.data import DataLoader
         from .CustomWindowDataset import _IndexOnly
         self.dataset, self.rank, self.world_size = dataset, rank, world_size
+        # Data-parallel TRAINING all-reduces the gradients once per video, so every rank must take the same number of steps:
+        # the shuffled order is padded with its own head up to a multiple of world_size (default for shuffle=True).
+        # Validation has no collective per video and shards the videos exactly (default for shuffle=False).
+        self.even_shards = shuffle if even_shards is None else bool(even_shards)
         self._order = DataLoader(_IndexOnly(len(dataset)), batch_size=1, shuffle=shuffle, generator=generator,
                                  collate_fn=lambda items: int(items[0]))
 
@@ -113,10 +118,13 @@ class FrameLoader:
 
     def indices(self):
         """This rank's video indices in the order of one pass (advances the sampler's generator like a pass does)."""
-        for k, i in enumerate(self._order):
-            if self.world_size > 1 and k % self.world_size != self.rank:
-                continue
-            yield i
+        if self.world_size <= 1:
+            yield from self._order
+            return
+        order = list(self._order)
+        if self.even_shards and len(order) % self.world_size:
+            order += order[:self.world_size - len(order) % self.world_size]
+        yield from order[self.rank::self.world_size]
 
     def __iter__(self):
         for i in self.indices():

@@ -21,6 +21,7 @@ import torch
 from torch.utils.data import DataLoader, Dataset
 
 from .. import ops
+from ..parallel import shard_batch
 from ..table import WindowIndex, cuda_device
 
 
@@ -173,8 +174,9 @@ class DeviceWindowLoader:
             if self.max_batches is not None and k >= self.max_batches:
                 break
             if self.world_size > 1:
-                per = (idx.numel() + self.world_size - 1) // self.world_size
-                idx = idx[self.rank * per:(self.rank + 1) * per]
+                if idx.numel() < self.world_size:
+                    continue       # fewer windows than ranks: dropped on EVERY rank (a rank without a step would stall the all-reduce)
+                idx = shard_batch(idx, self.rank, self.world_size)
             yield idx
 
     def __iter__(self):

@@ -33,11 +33,13 @@ def init_from_env(backend: str = None) -> tuple:
 
 
 def shard_batch(idx: torch.Tensor, rank: int, world_size: int) -> torch.Tensor:
-    """Contiguous share of a global batch for one rank (ceil split; trailing ranks may get fewer)."""
+    """Contiguous share of a global batch for one rank.  Even split (sizes differ by at most one), so that a rank's share is
+    empty only if the batch has fewer samples than there are ranks -- the loaders drop such a batch on EVERY rank
+    (every step ends in a gradient all-reduce: a rank that skipped it would leave the others waiting)."""
     if world_size <= 1:
         return idx
-    per = (idx.numel() + world_size - 1) // world_size
-    return idx[rank * per:(rank + 1) * per]
+    n = idx.numel()
+    return idx[rank * n // world_size:(rank + 1) * n // world_size]
 
 
 def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:

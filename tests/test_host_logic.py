@@ -97,6 +97,8 @@ def test_shard_batch_partitions():
     for world in (1, 2, 4, 8):
         parts = [shard_batch(idx, r, world) for r in range(world)]
         assert torch.equal(torch.cat(parts), idx)
+        sizes = [p.numel() for p in parts]
+        assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1          # even split: no rank is left without a step
 
 
 def test_sampler_matches_torch_dataloader():
@@ -143,6 +145,11 @@ def test_index_batches_mirror_the_dataloader_exactly():
     r1 = DeviceWindowLoader(_DS(37), 8, shuffle=True, generator=torch.Generator().manual_seed(42), rank=1, world_size=2)
     for g, x, y in zip(a.index_batches(), r0.index_batches(), r1.index_batches()):
         assert torch.cat([x, y]).tolist() == g.tolist()
+    # 8 ranks, 37 windows in batches of 16: the last global batch (5 windows < 8 ranks) is dropped on every rank, so all
+    # ranks take the same number of steps (each step ends in a gradient all-reduce)
+    per_rank = [[b.numel() for b in DeviceWindowLoader(_DS(37), 16, shuffle=True, generator=torch.Generator().manual_seed(42),
+                                                      rank=r, world_size=8).index_batches()] for r in range(8)]
+    assert all(len(p) == 2 and min(p) >= 1 for p in per_rank) and [sum(x) for x in zip(*per_rank)] == [16, 16]
 
 
 def test_lstm_dg_column_permutation():

@@ -106,9 +106,13 @@ class Videos:                      # stands in for CustomFrameDataset: only len(
     def __len__(self): return 7
     def __getitem__(self, i): raise AssertionError("indices() must not touch the data")
 
-mine = list(FrameLoader(Videos(), shuffle=True, generator=torch.Generator().manual_seed(42), rank=rank, world_size=world).indices())
+train = list(FrameLoader(Videos(), shuffle=True, generator=torch.Generator().manual_seed(42), rank=rank, world_size=world).indices())
 order = list(FrameLoader(Videos(), shuffle=True, generator=torch.Generator().manual_seed(42)).indices())
-assert mine == order[rank::world], (mine, order)          # every rank walks the same seed-42 order and takes every world-th video
+# training: every rank walks the same seed-42 order and takes every world-th video; the order is padded with its own head so
+# that all ranks take the SAME number of steps (one gradient all-reduce per video: an odd video out would hang the others)
+assert train == (order + order[:1])[rank::world] and len(train) == 4, (train, order)
+mine = list(FrameLoader(Videos(), shuffle=False, rank=rank, world_size=world).indices())
+assert mine == list(range(7))[rank::world]                 # validation: exact shards, no padding
 # the only exchange of the frame / ensemble paths besides the gradient all-reduce: the sum of the confusion counts
 counts = torch.tensor([rank + 1, 10 * (rank + 1), 0, 5], dtype=torch.int64)
 parallel.allreduce_sum_(counts)
