@@ -238,13 +238,14 @@ class FrameTrainStep:
         if getattr(model, "graph_seed", False) is None:
             model.graph_seed = (int(torch.randint(0, 2 ** 62, (1,)).item()), torch.zeros(1, dtype=torch.int64, device=dev))
 
-    def _body(self):
+    def _body(self, exchange: bool = True):
         inputs = mu.define_inputs(self.images, self.kin, self.fe, self.kw, self.device)
         outputs = self.model(inputs)
         loss, _ = mu.compute_loss(outputs, self.labels, self.crit, "frame")
         self.opt.zero_grad()
         mu._backward(loss, self.opt)
-        mu._allreduce_grads(self.opt)
+        if exchange:
+            mu._allreduce_grads(self.opt)
         self.opt.step()
         preds, counts = mu.compute_loss.last_frame
         self.loss.copy_(loss.detach().reshape(1))
@@ -257,9 +258,14 @@ class FrameTrainStep:
         seed_counter = None if getattr(self.model, "graph_seed", None) is None else self.model.graph_seed[1].clone()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
+        # The warm-up steps run WITHOUT the gradient all-reduce (they are rolled back anyway).  Under data parallelism the
+        # ranks capture different videos at different times -- the shuffled order deals the videos anew every epoch, so in
+        # epoch 2 one rank may capture a video while its peer replays a cached graph -- and a real collective inside a
+        # capture-time warm-up would pair with the peer's NEXT step (measured on two GPUs: replicas drifted apart).  With
+        # collective-free captures every rank issues exactly one all-reduce per step, the one inside the replayed graph.
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self._body()
+                self._body(exchange=False)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         n0 = _lib.launch_count()

@@ -456,6 +456,11 @@ def _train_epoch_frame_graph(model, feature_extractor, loader, criterion, optimi
     cache = getattr(optimizer, "_b200_frame_steps", None)
     if cache is None or cache["key"] != key:
         cache = optimizer._b200_frame_steps = {"key": key, "steps": {}, "pool": torch.cuda.graph_pool_handle(), "failed": False}
+        # data parallel: bring the communicator up once, at the same point on every rank, before any capture records a collective
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(torch.zeros(1, device=device))
+            torch.cuda.synchronize()
     log = _EpochLog()
     subjects_all = []
     want_preds = exp_kwargs["return_train_preds"]
