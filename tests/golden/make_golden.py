@@ -320,7 +320,46 @@ def gen_window_predictions():
     print("window_predictions:", len(out))
 
 
+# ---------------------------------------------------------------- TeCNo: non-causal variant, several videos (a10, ragged batches)
+TECNO_EXTRA = dict(stages=2, layers=4, maps=64, dim=58, classes=2, weight_seed=123, input_seed=7, lengths=[40, 9, 65])
+
+
+def gen_tecno_extra():
+    """Reference MultiStageModel (models_TCN.py:17-137), causal and NOT causal, on three videos one forward each (the
+    reference's DataLoader(batch_size=1) schedule): eval logits per video, and train-mode (dropout off) input / parameter
+    gradient norms of sum(out * w) on the longest video.  Weights are not stored: the test rebuilds them from the seed and
+    checks the state digest."""
+    c = TECNO_EXTRA
+    out, meta = {}, dict(c)
+    for causal in (True, False):
+        tag = "causal" if causal else "noncausal"
+        torch.manual_seed(c["weight_seed"])
+        with quiet:
+            model = ref.models_TCN.MultiStageModel(c["stages"], c["layers"], c["maps"], c["dim"], c["classes"], causal)
+        meta[f"{tag}/state"] = state_digest(model.state_dict())
+        gen = torch.Generator().manual_seed(c["input_seed"])
+        videos = [torch.randn(1, n, c["dim"], generator=gen) for n in c["lengths"]]
+        model.eval()
+        with torch.no_grad():
+            for i, x in enumerate(videos):
+                out[f"{tag}/logits{i}"] = model(x.permute(0, 2, 1)).numpy()
+        no_dropout(model)
+        model.train()
+        x = videos[-1].clone().requires_grad_(True)
+        y = model(x.permute(0, 2, 1))
+        w = torch.randn(y.shape, generator=gen)
+        (y * w).sum().backward()
+        out[f"{tag}/dx"] = x.grad.numpy()
+        out[f"{tag}/w"] = w.numpy()
+        meta[f"{tag}/grad_names"] = [k for k, _ in model.named_parameters()]
+        out[f"{tag}/grad_norms"] = np.asarray([float(p.grad.double().norm()) for _, p in model.named_parameters()])
+        out[f"{tag}/grad_sums"] = np.asarray([float(p.grad.double().sum()) for _, p in model.named_parameters()])
+    np.savez_compressed(os.path.join(HERE, "tecno_extra.npz"), **out)
+    json.dump(meta, open(os.path.join(HERE, "tecno_extra.json"), "w"), indent=1)
+    print("tecno_extra:", len(out))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["window_index", "powerset", "models", "epochs", "epochs_es", "window_predictions"]
+    which = sys.argv[1:] or ["window_index", "powerset", "models", "epochs", "epochs_es", "window_predictions", "tecno_extra"]
     for w in which:
         globals()[f"gen_{w}"]()

@@ -164,3 +164,45 @@ def test_header_constants_match_the_binding():
     from multimodal_error_detection_b200 import ops
     assert int(consts["B200MED_TCN_PACK_FLOATS"]) == ops.TCN_PACK_FLOATS == ref.PACK
     assert int(consts["B200MED_TCN_GRAD_FLOATS"]) == ops.TCN_GRAD_FLOATS == ref.GRAD
+
+
+@pytest.mark.parametrize("tag", ["causal", "noncausal"])
+def test_stage_node_matches_the_executed_reference(emulated, golden_dir, tag):
+    """tests/golden/tecno_extra.* were recorded by EXECUTING the reference MultiStageModel (tests/golden/make_golden.py
+    gen_tecno_extra): causal and non-causal, three videos one forward each.  The product model rebuilt from the same seed has
+    the same weights (state digest); with the kernels replaced by their torch definitions it reproduces the reference's
+    logits per video, its logits in ONE ragged pass over the three videos, and its gradients."""
+    import json
+    import os
+    from hashing import state_digest
+    meta = json.load(open(os.path.join(golden_dir, "tecno_extra.json")))
+    gold = np.load(os.path.join(golden_dir, "tecno_extra.npz"))
+    causal = tag == "causal"
+    torch.manual_seed(meta["weight_seed"])
+    m = models_TCN.MultiStageModel(meta["stages"], meta["layers"], meta["maps"], meta["dim"], meta["classes"], causal)
+    assert state_digest(m.state_dict()) == meta[f"{tag}/state"]          # same construction order -> same seeded weights
+    gen = torch.Generator().manual_seed(meta["input_seed"])
+    videos = [torch.randn(1, n, meta["dim"], generator=gen) for n in meta["lengths"]]
+    m.eval()
+    with torch.no_grad():
+        for i, x in enumerate(videos):
+            out = m(x.permute(0, 2, 1))
+            assert m.impl == "b200"
+            assert np.abs(out.numpy() - gold[f"{tag}/logits{i}"]).max() <= 2e-5 * np.abs(gold[f"{tag}/logits{i}"]).max()
+        ragged = m.forward_ragged(torch.cat([v[0] for v in videos]), meta["lengths"])       # [stages, C, sum T]
+    want = np.concatenate([gold[f"{tag}/logits{i}"][:, 0] for i in range(len(videos))], axis=2)
+    assert np.abs(ragged.numpy() - want).max() <= 2e-5 * np.abs(want).max()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m.train()
+    x = videos[-1].clone().requires_grad_(True)
+    y = m(x.permute(0, 2, 1))
+    (y * torch.from_numpy(gold[f"{tag}/w"])).sum().backward()
+    assert np.abs(x.grad.numpy() - gold[f"{tag}/dx"]).max() <= 1e-4 * np.abs(gold[f"{tag}/dx"]).max()
+    names = [k for k, _ in m.named_parameters()]
+    assert names == meta[f"{tag}/grad_names"]
+    norms = np.asarray([float(p.grad.double().norm()) for _, p in m.named_parameters()])
+    sums = np.asarray([float(p.grad.double().sum()) for _, p in m.named_parameters()])
+    assert np.allclose(norms, gold[f"{tag}/grad_norms"], rtol=1e-4, atol=1e-6 * gold[f"{tag}/grad_norms"].max())
+    assert np.allclose(sums, gold[f"{tag}/grad_sums"], rtol=1e-3, atol=1e-4 * gold[f"{tag}/grad_norms"].max())
