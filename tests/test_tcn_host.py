@@ -206,3 +206,30 @@ def test_stage_node_matches_the_executed_reference(emulated, golden_dir, tag):
     sums = np.asarray([float(p.grad.double().sum()) for _, p in m.named_parameters()])
     assert np.allclose(norms, gold[f"{tag}/grad_norms"], rtol=1e-4, atol=1e-6 * gold[f"{tag}/grad_norms"].max())
     assert np.allclose(sums, gold[f"{tag}/grad_sums"], rtol=1e-3, atol=1e-4 * gold[f"{tag}/grad_norms"].max())
+
+
+def test_cabi_argument_errors_of_the_tcn_entry_points():
+    """Error convention of the C ABI (include/b200med.h): bad arguments return B200MED_E_ARG (-1) with a message BEFORE any
+    CUDA call is made -- checked here without a GPU; the Python binding maps -1 to ValueError."""
+    import ctypes as C
+    from multimodal_error_detection_b200 import _lib
+    lib = _lib.load()
+    null, one = C.c_void_p(0), C.c_void_p(256)            # `one`: a non-null, 16-byte aligned address that is never dereferenced
+    rc = lib.b200med_tcn_layer_fwd(one, one, one, null, -1, 1, 1, null, null, 0.0, 0, null, 0, null)
+    assert rc == -1 and b"bad shape" in lib.b200med_last_error()
+    rc = lib.b200med_tcn_layer_fwd(one, one, one, null, 8, 0, 1, null, null, 0.0, 0, null, 0, null)
+    assert rc == -1                                                                       # dilation 0
+    rc = lib.b200med_tcn_layer_fwd(one, one, one, null, 8, 1, 1, null, null, 1.0, 0, null, 0, null)
+    assert rc == -1 and b"dropout" in lib.b200med_last_error()
+    rc = lib.b200med_tcn_layer_fwd(null, one, one, null, 8, 1, 1, null, null, 0.0, 0, null, 0, null)
+    assert rc == -1 and b"null pointer" in lib.b200med_last_error()
+    rc = lib.b200med_tcn_layer_fwd(C.c_void_p(260), one, one, null, 8, 1, 1, null, null, 0.0, 0, null, 0, null)
+    assert rc == -1 and b"aligned" in lib.b200med_last_error()
+    assert lib.b200med_tcn_layer_fwd(one, one, one, null, 0, 1, 1, null, null, 0.0, 0, null, 0, null) == 0   # T = 0: nothing to do
+    rc = lib.b200med_tcn_out_fwd(one, one, one, one, 8, 9, null)
+    assert rc == -1 and b"classes" in lib.b200med_last_error()
+    rc = lib.b200med_tcn_layer_bwd_hidden(one, one, one, one, one, one, 0, 8, 1, 1, null, null, 0.0, 0, null, 0, null)
+    assert rc == -1                                                                       # zero slots
+    assert lib.b200med_tcn_slots(600) == 75 and lib.b200med_tcn_slots(641) == 41 and lib.b200med_tcn_slots(5000) == 80
+    with pytest.raises(ValueError, match="bad shape"):
+        _lib.call("b200med_tcn_reduce_grads", one, 0, 1, one, null)
