@@ -138,6 +138,10 @@ class MultiStageModel(nn.Module):
             return torch.stack(outs, dim=0)
         if geom[0] is not None:
             raise ValueError("ragged batches need the fused TeCNo kernels (64 feature maps, kernel size 3, <= 8 classes)")
+        if self.use_fused and self.impl != "torch":
+            import warnings
+            warnings.warn("b200med: this MultiStageModel shape (feature maps != 64, kernel size != 3, > 8 classes or batch > 1) is not "
+                          "covered by the fused TeCNo kernels and runs on stock torch layers", RuntimeWarning, stacklevel=2)
         self.impl = "torch"
         out = self.stage1(x, fused=False)
         outs = [out]
