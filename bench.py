@@ -33,14 +33,12 @@ import torch
 W, S = 16, 4
 IMAGE_DIM, KIN_DIM = 2048, 26
 METRIC, UNIT = "train_windows_per_sec", "windows/s"
-LSTM_IMPL = "b200"
 
 
 def exp_kwargs(batch, precision):
     return dict(dataset_type="window", error_type="global", pos_weight=True, n_epochs=15, batch_size=batch, lr=1e-3,
                 lr_scheduler=True, weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32, data_type="multimodal",
-                delete_ND=True, return_train_preds=False, siamese=False, model_name="SimpleLSTM", precision=precision,
-                lstm_impl=LSTM_IMPL)
+                delete_ND=True, return_train_preds=False, siamese=False, model_name="SimpleLSTM", precision=precision)
 
 
 def workload_name(batch, videos):
@@ -127,6 +125,18 @@ class ClockSampler(threading.Thread):
                 "query_ms": 1e3 * statistics.median(self.costs) if self.costs else None}
 
 
+def k1_traffic(precision, batch, window, variant):
+    path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    try:
+        rec = json.load(open(path))
+        c = rec["config"]
+        if (c["precision"], c["batch"], c["window"], c["gather_variant"]) == (precision, batch, window, variant):
+            return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), f"profiles/k1_traffic.json ({rec['source']})"
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -162,48 +172,64 @@ def oracle_dataset(n_windows, seed):
 
 def cpu_train_windows_per_sec(n_windows, batch, steps=None, warmup=0):
     """The reference's train_single_epoch cost structure (oracle port) on the host cores:
-    windows/s = windows processed / wall time, data loading and sklearn metrics included."""
+    windows/s = windows processed / wall time, data loading and sklearn metrics included.  The sample holds `n_windows`
+    materialised windows (the reference's representation); `steps` train steps of `batch` windows are timed as repeated
+    passes of the oracle's epoch loop over that sample (default: one pass)."""
     from oracle import loops, nets
     kw = exp_kwargs(batch, "fp32")
     ds, build_s = oracle_dataset(n_windows, seed=7)
     fe, model, crit, opt, sched = nets.build_objects(kw, {"multimodal": 58, "video": 32, "kinematics": 26},
                                                      ds.binary_error_distribution, W)
     loader, _ = loops.make_loaders(ds, ds, batch)
+    per_pass = len(loader)
+    steps = per_pass if steps is None else max(1, int(steps))
     if warmup:
         it = iter(loader)
         model.train(); fe.train()
-        for _ in range(min(warmup, len(loader))):
+        for _ in range(min(warmup, per_pass)):
             images, kin, g, e7, subj = next(it)
             out = model(loops.fuse_inputs(images, kin, fe, kw))
             loss, _ = loops.loss_fn(out, loops.select_labels(e7, kw).float(), crit, "window")
             opt.zero_grad(); loss.backward(); opt.step()
+    passes = (steps + per_pass - 1) // per_pass
     t0 = time.perf_counter()
-    loops.train_epoch(model, fe, loader, crit, opt, None, kw)
+    for _ in range(passes):
+        loops.train_epoch(model, fe, loader, crit, opt, None, kw)
     dt = time.perf_counter() - t0
-    return len(ds) / dt, dt, len(ds), build_s
+    done = passes * len(ds)
+    return done / dt, dt, done, build_s, passes * per_pass
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm may use all the host threads there are
+def host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU arms may use all the host threads there are."""
     try:
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except Exception:
         pass
-    cores = torch.get_num_threads()
-    batch = 512
-    n = batch * max(1, args.steps)
-    wps, dt, n_done, build_s = cpu_train_windows_per_sec(n, batch, warmup=args.warmup)
-    line = {"metric": METRIC, "value": wps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    return torch.get_num_threads()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port -- the reference is pure Python,
+    nothing compiles into oracle/_ref) on all host threads, SAME config as the GPU arm: B = args.batch windows per step.
+    Each step is a bounded sample: the oracle's epoch loop over 2 * B materialised windows (2 GB at B = 8192), repeated."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_threads()
+    batch = args.batch
+    steps = max(1, args.steps)
+    wps, dt, n_done, build_s, steps_done = cpu_train_windows_per_sec(2 * batch, batch, steps=steps, warmup=min(args.warmup, 2))
+    line = {"metric": METRIC, "value": wps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done, "warmup": min(args.warmup, 2),
+            "ms_per_step": 1e3 * dt / steps_done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": workload_name(args.batch, args.videos),
-                       "note": "reference CPU path (oracle port of train_single_epoch, torch CPU fp32 + sklearn); each step "
-                               "is a bounded sample of 512 windows of the same workload"},
+                       "note": "reference CPU path (oracle port of train_single_epoch, torch CPU fp32 + sklearn); each step is "
+                               f"one batch of {batch} windows of the same workload drawn from a bounded sample of {2 * batch} "
+                               "materialised windows"},
             "cpu_baseline": {"value": wps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{n_done} windows, B={batch}, {args.steps} steps, window build {build_s:.2f}s excluded"},
+                             "sample": f"{n_done} windows, B={batch}, {steps_done} steps over a {2 * batch}-window sample, "
+                                       f"window build {build_s:.2f}s excluded"},
             "e2e": {"value": wps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -231,12 +257,75 @@ def build_gpu_job(args, rank, device):
     return ds, N
 
 
-def other_configs():
+def timed_steps(ds, kw, device, batch, steps, warmup=3, graph=True, prefetch=False):
+    """A bounded device-timed measurement of the window train step on `ds` for another configuration of the same workload
+    (fp32 parity mode, strong-scaling batch): fresh model objects, K graph replays (or eager steps), CUDA events,
+    max over ranks -> (ms per step, launch note, b200med launches per step)."""
+    from multimodal_error_detection_b200 import _lib, parallel
+    from multimodal_error_detection_b200.engine import WindowTrainStep
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    fe, model, crit, opt, sched = mu.define_model_objects(kw, {"multimodal": 58, "video": 32, "kinematics": 26}, device,
+                                                          ds.binary_error_distribution, W)
+    n = len(ds)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(43))
+    need = (steps + warmup + 1) * batch
+    idx_all = perm.repeat((need + n - 1) // n)[:need].reshape(-1, batch).to(device)
+    stepper = WindowTrainStep(ds, fe, model, crit, opt, kw, batch, prefetch=prefetch)
+    note = "eager"
+    mu._set_train(model, fe, kw, True)
+    if graph:
+        try:
+            stepper.load(idx_all[0])
+            stepper.capture()
+            note = "cuda_graph"
+        except Exception as e:
+            stepper.graphs = [None, None]
+            note = f"eager (graph capture failed: {type(e).__name__}: {e})"
+
+    def step(i):
+        if stepper.prefetch:
+            if not stepper._primed:
+                stepper.load(idx_all[i])
+            stepper.run(idx_all[i + 1])
+        else:
+            stepper.load(idx_all[i])
+            stepper.run()
+
+    for i in range(warmup):
+        step(i)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); parallel.barrier()
+    n0 = _lib.launch_count()
+    a.record()
+    for i in range(steps):
+        step(warmup + i)
+    b.record()
+    torch.cuda.synchronize(); parallel.barrier()
+    ms = parallel.max_over_ranks(a.elapsed_time(b) / steps, device)
+    launches = stepper.launches_per_step if stepper.graph is not None else (_lib.launch_count() - n0) // steps
+    stepper.graphs = [None, None]
+    return ms, note, launches
+
+
+def other_configs(args, ds, device):
     """Auxiliary, bounded measurements of the BASELINE configs the headline line does not cover (they are parity-test
-    cases, not bench lines): config 0 (train_frame: FE + TeCNo, one video per step, eager / CUDA graph / stock torch layers)
-    and config 5 (ensemble inference: frame model + window model + device-side fusion).  Failures are reported, never fatal."""
+    cases, not bench lines), N = 1: the fp32 parity mode of the SAME train step (1e-5 arithmetic: SIMT fp32 GEMMs, exact-math
+    recurrence), config 0 (train_frame: FE + TeCNo, one video per step, eager / CUDA graph / stock torch layers) and config 5
+    (ensemble inference: frame model + window model + device-side fusion) on ONE rank's shard of the 100 k-video job
+    (12 500 videos, ~62 GB table).  Failures are reported, never fatal."""
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
     out = {}
+    try:
+        Bf = 2048
+        ms, note, launches = timed_steps(ds, exp_kwargs(Bf, "fp32"), device, Bf, steps=5, warmup=3)
+        flops = Bf * W * (5_029_888 + 3 * 2 * 714_752)        # FE train + LSTM fwd/bwd per (window, step), SURVEY section 8d
+        out["train_window_fp32"] = {"value": Bf / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "batch": Bf, "launch": note,
+                                    "gpu_launches_per_step": launches, "dtype": "f32",
+                                    "bound": "fp32 SIMT issue (no tensor cores: TF32 / bf16 products cannot hold the 1e-5 bar)",
+                                    "achieved_tflops": flops / (ms * 1e-3) / 1e12,
+                                    "note": "same workload and step as the headline, exp_kwargs['precision'] = 'fp32'"}
+    except Exception as e:
+        out["train_window_fp32"] = {"error": f"{type(e).__name__}: {e}"}
     try:
         import bench_frame
         r = bench_frame.measure(frames=600, videos=32, steps=20)
@@ -247,14 +336,29 @@ def other_configs():
                               "inference_ragged_frames_per_s": r["head_inference"]["ragged_frames_per_s"], "config": r["config"]}
     except Exception as e:
         out["train_frame"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
+ENSEMBLE_KEYS = ("value", "unit", "frames_per_s", "n_gpus", "videos_per_gpu", "frames_per_gpu", "ms_total", "ms_frame_model",
+                 "ms_window_model", "ms_vote_fusion_counts", "config")
+
+
+def ensemble_config(world):
+    """BASELINE configs[4]: ensemble inference over a 100 k-video eval set, sharded by video.  Every rank owns 100 000 / 8 =
+    12 500 videos (~7.5 M frames, ~62 GB fp32 table): at N = 8 that is the whole job; at smaller N the same per-GPU shard
+    (weak scaling of the same job).  All ranks call this (one count all-reduce inside)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
     try:
         import bench_ensemble
-        r = bench_ensemble.measure(videos=512, reps=2, dist_init=False)
-        out["ensemble_inference"] = {k: r[k] for k in ("value", "unit", "frames_per_s", "videos_per_gpu", "frames_per_gpu", "ms_total",
-                                                       "ms_frame_model", "ms_window_model", "ms_vote_fusion_counts", "config")}
+        torch.cuda.empty_cache()
+        r = bench_ensemble.measure(videos=12500, reps=2, dist_init=world > 1)
+        if r is None:
+            return None
+        res = {k: r[k] for k in ENSEMBLE_KEYS}
+        res["job"] = f"{world * 12500} of the 100 000 videos of BASELINE configs[4] ({world} rank(s) x 12 500 videos)"
+        return res
     except Exception as e:
-        out["ensemble_inference"] = {"error": f"{type(e).__name__}: {e}"}
-    return out
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def run_gpu(args):
@@ -398,12 +502,13 @@ def run_gpu(args):
     k1_iso_ms = statistics.mean(iso)
     hbm_peak, tf_peak, peak_src = measured_peaks()
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
-    # DRAM traffic per step's K1 from the ncu --set full capture of this very configuration
-    # (profiles/r1_ncu_gather_norm_tma_bf16.md: image launch 1.0626 GB read + 0.4970 GB written, kinematics launch 13.4 MB)
-    traffic = 1.0626e9 + 0.4970e9 + 13.4e6 if (args.precision == "bf16" and B == 8192 and args.gather_variant == 0) else None
+    # DRAM traffic of K1 per step: NOT measurable without a profiler attached -- taken from the committed `ncu --set full`
+    # capture of this configuration (profiles/k1_traffic.json records the command, the config it was captured on and the two
+    # dram__bytes counters); null when this run's configuration is not the captured one.
+    traffic, traffic_src = k1_traffic(args.precision, B, W, args.gather_variant)
     roofline = {"kernel": "gather_norm_tma_kernel + gather_norm_kernel (K1: window gather + standardise + concat, image + kinematics streams)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_gather_norm_tma_bf16.md" if traffic else None,
+                "traffic_source": traffic_src,
                 "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms, "ms_per_launch_isolated": k1_iso_ms,
                 "share_of_step": k1_ms / step_ms, "how": k1_how, "peak_source": peak_src}
 
@@ -448,29 +553,41 @@ def run_gpu(args):
                "steps": steps_e2e, "api": "modeling_utils.train_single_epoch(DeviceWindowLoader)", "loss": res[0],
                "table_upload_bytes_once": int(n_frames * (IMAGE_DIM + KIN_DIM + 6) * 4)}
 
+    # ---- auxiliary configurations (all ranks take part: the strong-scaling steps and the ensemble job hold collectives)
+    aux = None
+    if not args.no_aux and args.precision == "bf16":
+        aux = {}
+        if world > 1 and B % world == 0:
+            try:      # strong scaling: the SAME global batch of B windows split over the ranks
+                ms, note, launches = timed_steps(ds, dict(kw), device, B // world, steps=K, warmup=3, prefetch=prefetch)
+                aux["strong_scaling"] = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "global_batch": B,
+                                         "batch_per_gpu": B // world, "n_gpus": world, "scaling": "strong", "launch": note}
+            except Exception as e:
+                aux["strong_scaling"] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1:
+            aux.update(other_configs(args, ds, device))
+        if world in (1, 8) and not args.no_ensemble:
+            del stepper
+            opt._b200_stepper = None
+            aux["ensemble_inference"] = ensemble_config(world)
     if rank == 0:
         cpu = None
-        if True:
+        if world == 1:      # N = 1 only: at N > 1 the other ranks would spin in the final barrier and starve this rank's threads
             try:
-                try:       # torchrun exports OMP_NUM_THREADS=1; the CPU baseline runs on rank 0 with every host thread
-                    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-                except Exception:
-                    pass
-                wps, dt, n_done, build_s = cpu_train_windows_per_sec(args.cpu_windows, 512)
-                cpu = {"value": wps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                       "sample": f"{n_done} windows (W={W}) of the same workload, B=512, one oracle train_epoch = {dt:.1f}s "
-                                 f"(host window build {build_s:.2f}s for the sample not included)"}
+                cores = host_threads()
+                wps, dt, n_done, build_s, steps_done = cpu_train_windows_per_sec(2 * B, B, steps=args.cpu_steps)
+                cpu = {"value": wps, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{n_done} windows (W={W}) of the same workload, B={B}, {steps_done} steps of the oracle train loop "
+                                 f"over a {2 * B}-window sample = {dt:.1f}s (host window build {build_s:.2f}s not included)"}
             except Exception as e:
                 cpu = {"value": None, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": f"failed: {e}"}
-        other = None
-        if world == 1 and not args.no_aux and args.precision == "bf16":
-            other = other_configs()
+        other = aux
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": step_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": workload_name(B, args.videos), "global_batch": world * B, "window": W, "stride": S,
                            "frames_per_gpu": n_frames, "windows_per_gpu": n_windows, "params": n_params,
-                           "parallelism": f"dp{world}", "launch": graph_note, "lstm_impl": args.lstm_impl,
+                           "parallelism": f"dp{world}", "launch": graph_note,
                            "gather_prefetch": bool(prefetch),
                            "l2": "every step gathers a fresh ~1.1 GB slice of a ~10 GB table (inputs larger than the 126 MB L2)",
                            "gather_variant": args.gather_variant},
@@ -481,7 +598,10 @@ def run_gpu(args):
     if world > 1:
         # graphs that captured NCCL work must be gone before the communicator is torn down; a wedged teardown must not
         # turn a finished run into a hang, so the process leaves through os._exit after a final barrier
-        stepper.graphs = [None, None]
+        try:
+            stepper.graphs = [None, None]
+        except NameError:
+            pass
         opt._b200_stepper = None
         import gc
         gc.collect()
@@ -503,18 +623,17 @@ def main():
                          "steps of the e2e measurement fit in one pass of the loader, like an epoch of a real fold does)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--lstm-impl", default="b200", choices=["b200", "b200_per_step", "cudnn"])
     ap.add_argument("--gather-variant", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary measurements of the other BASELINE configs "
                     "(frame path, ensemble inference; N = 1 only, reported under 'other_configs')")
+    ap.add_argument("--no-ensemble", action="store_true", help="skip the 12 500-videos-per-GPU ensemble job (62 GB table per GPU)")
     ap.add_argument("--prefetch-sms", type=int, default=56, help="SMs the prefetching gather may occupy (side stream)")
     ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
                     help="gather each step's batch at the start of the step instead of inside the previous step")
-    ap.add_argument("--cpu-windows", type=int, default=4096)
+    ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the in-run CPU baseline (N = 1 only; B windows each)")
+    ap.add_argument("--cpu-windows", type=int, default=0, help="(ignored, kept for old command lines)")
     args = ap.parse_args()
-    global LSTM_IMPL
-    LSTM_IMPL = args.lstm_impl
     if args.impl == "reference":
         run_reference(args)
     else:

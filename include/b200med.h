@@ -98,7 +98,8 @@ typedef struct b200med_stream_desc {
     int32_t stat_rows;   /* 1: statistics broadcast over time; W: one statistics row per step       */
     int32_t exact_div;   /* 1: (x-mean)/std with IEEE division (bit-exact vs the reference);
                             0: (x-mean)*(1/std)                                                     */
-    int32_t reserved;
+    int32_t table_rows;  /* N (0 = unknown): when given, a window [start, start+W) outside the table traps
+                            (CUDA error) instead of reading past it -- the reference raises IndexError     */
 } b200med_stream_desc;
 
 #define B200MED_MAX_STREAMS 8
@@ -112,6 +113,9 @@ typedef struct b200med_stream_desc {
  *   the number of SMs the launch occupies (0 = all) for a gather that shares the GPU with other kernels.       */
 int b200med_gather_norm(const b200med_stream_desc *streams_host, int32_t n_streams,
                         const int32_t *starts, int64_t B, int32_t W, int32_t variant, void *stream);
+/* Device path the calling thread's last b200med_gather_norm took for stream 0: 1 = LDG kernel, 2.. = TMA staging ring
+ * shape (the `variant` numbering above).  Lets a parity test prove which instantiation it compared with the oracle.  */
+int b200med_gather_last_variant(void);
 
 /* Frame path: standardise whole rows in place order (no gather): out[r,:] = (x[r,:]-mean)/std.
  * Replaces the kinematics standardisation of CustomFrameDataset.__getitem__ (CustomFrameDataset.py:93-95). */
@@ -125,7 +129,24 @@ int b200med_standardise_rows(const float *x, const float *mean, const float *std
 
 /* fp32 SIMT path (parity mode, 1e-5): y[M,N] = x[M,K] W[N,K]^T + b, optional ReLU.               */
 int b200med_linear_fwd_f32(const float *x, const float *w, const float *bias, float *y, int64_t M,
-                           int32_t N, int32_t K, int32_t relu, void *stream);
+                           int32_t N, int32_t K, int32_t relu /* B200MED_GEMM_* flags: RELU, ACCUM (y += ...), RELU_A */, void *stream);
+/* General strided fp32 product on the same SIMT kernel (fixed reduction order, deterministic):
+ *     C[i, j] = epilogue( sum_r A[i*a_rs + r*a_cs] * B[j*b_rs + r*b_cs] ),   i < I, j < J, r < R
+ * epilogue: + bias[j] (or NULL), + old C[i, j] (ACCUM), ReLU (RELU), zeroed where mask[i*ld_mask + j] <= 0 (mask or NULL).
+ * RELU_A / RELU_B clamp the operand elements at zero on load (a ReLU in front of the product is never materialised).
+ * SPLIT: long reduction into a small dense C (weight gradients): R is cut into slabs whose partial products are summed in
+ * ascending order; needs workspace >= b200med_gemm_f32_ws_bytes(I, J, R), no bias / mask / RELU, ldc == J.
+ * What it serves: nn.LSTM's fp32 gate products (models.py:161), Conv1d(k=3) as a GEMM over overlapping time-major rows
+ * (models.py:67-99, see csrc/head.cu), the Linear layers of both heads (models.py:101-111, 166-186).             */
+#define B200MED_GEMM_RELU 1
+#define B200MED_GEMM_ACCUM 2
+#define B200MED_GEMM_RELU_A 4
+#define B200MED_GEMM_RELU_B 8
+#define B200MED_GEMM_SPLIT 16
+int64_t b200med_gemm_f32_ws_bytes(int64_t I, int64_t J, int64_t R);
+int b200med_gemm_f32(const float *A, const float *B, float *C, int64_t I, int64_t J, int64_t R, int64_t a_rs,
+                     int64_t a_cs, int64_t b_rs, int64_t b_cs, int64_t ldc, const float *bias, const float *mask,
+                     int64_t ld_mask, int32_t flags, void *workspace, void *stream);
 /* dx[M,K] = dy[M,N] W[N,K]; if relu_out != NULL the result is masked by (relu_out > 0), i.e. the
  * ReLU backward of the PREVIOUS layer whose forward output is relu_out [M,K].                     */
 int b200med_linear_bwd_data_f32(const float *dy, const float *w, const float *relu_out, float *dx,
@@ -195,6 +216,57 @@ int b200med_lstm_cell_bwd(const float *Gact, const float *c, const float *c_prev
                           int32_t ld_up, const float *dh_rec, int32_t ld_rec, float *dc, int32_t dc_init,
                           void *dG, int64_t B, int32_t H, float drop_p, const uint32_t *seed,
                           uint64_t drop_base, void *stream);
+
+/* fp32 parity mode of the same recurrence (exp_kwargs['precision'] = "fp32", 1e-5 bar): time-major fp32 buffers
+ * X_l [W, B, in_l], G_l [W, B, 4H], C_l / Hs_l [W, B, H]; the gate products run on b200med_gemm_f32 / b200med_linear_*_f32,
+ * these are the layout and cell kernels.  Exact-math sigmoid / tanh (expf, tanhf, IEEE division).
+ *   pack:   x ([B, F, W] when x_layout = 0, [B, W, F] when 1) -> X0 [W, B, F];  unpack: dX0 [W, B, ld] columns [0, F) -> dx.
+ *   cell_fwd_f32: G [B, 4H] pre-activations in, activated gates out; c_prev or NULL (t = 0); c_out, h_out [B, H];
+ *                 x_up [B, H] or NULL = dropout(h) for the layer above (counter-based mask, see b200med_lstm_cell_fwd).
+ *   cell_bwd_f32: dG [B, 4H] f32 OUT; dh_up [B, ld_up] (layer above's dX, masked like the forward) or NULL, dh_rec [B, H]
+ *                 (from step t+1) or NULL; dc [B, H] carried in place (dc_init = 1 at the last step).            */
+int b200med_lstm_pack_f32(const float *x, float *X0, int64_t B, int32_t F, int32_t W, int32_t x_layout, void *stream);
+int b200med_lstm_unpack_f32(const float *dX0, float *dx, int64_t B, int32_t F, int32_t W, int32_t ld, int32_t x_layout,
+                            void *stream);
+int b200med_lstm_cell_fwd_f32(float *G, const float *c_prev, float *c_out, float *h_out, float *x_up, int64_t B,
+                              int32_t H, float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream);
+int b200med_lstm_cell_bwd_f32(const float *Gact, const float *c, const float *c_prev, const float *dh_up,
+                              int32_t ld_up, const float *dh_rec, float *dc, int32_t dc_init, float *dG, int64_t B,
+                              int32_t H, float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Head layers around the GEMMs (MED/modeling/models.py:49-131 CNN; :166-186, 204-210 LSTM head MLP)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* nn.BatchNorm1d over the rows of x [M, C] (a Linear layer's [B, C], or a convolution's time-major [B*L, C]).
+ * training = 1: batch statistics (biased variance), running_mean / running_var updated with `momentum` (unbiased
+ * variance), *num_batches_tracked += 1 (any of the three may be NULL), save_mean / save_rstd [C] OUT for the backward;
+ * training = 0: y from the running statistics.  Deterministic (per-slab two-pass partials combined in fixed order, fp64).
+ * workspace >= b200med_bn_ws_bytes(M, C).                                                                    */
+int64_t b200med_bn_ws_bytes(int64_t M, int32_t C);
+int b200med_bn_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta, float eps,
+                   float momentum, int32_t training, float *running_mean, float *running_var,
+                   int64_t *num_batches_tracked, float *y, float *save_mean, float *save_rstd, void *workspace,
+                   void *stream);
+/* dx = gamma rstd (dy - mean(dy) - xhat mean(dy xhat)), dgamma = sum dy xhat, dbeta = sum dy (either may be NULL).
+ * relu_mask = 1: dx is also zeroed where x <= 0 -- x is then the output of the ReLU that precedes the BatchNorm in the
+ * reference heads, so dx is the gradient of the Linear layer's pre-activation.                                  */
+int b200med_bn_bwd(const float *dy, const float *x, int64_t M, int32_t C, const float *gamma, const float *save_mean,
+                   const float *save_rstd, int32_t relu_mask, float *dx, float *dgamma, float *dbeta, void *workspace,
+                   void *stream);
+/* MaxPool1d(2, 2) + Dropout(p) over time-major rows: z [B*L, C] with Lc valid steps per window -> p [B*(Lc/2), C];
+ * backward: dz [2 + B*L, C] -- two zero rows, then the gradient rows (to the first maximum of each pair, zero elsewhere);
+ * the zero rows are what the convolution's data-gradient product reads for steps l < 2.  models.py:67-99.       */
+int b200med_pool_drop_fwd(const float *z, float *p, int64_t B, int32_t L, int32_t Lc, int32_t C, float drop_p,
+                          const uint32_t *seed, uint64_t drop_base, void *stream);
+int b200med_pool_drop_bwd(const float *dp, const float *z, float *dz, int64_t B, int32_t L, int32_t Lc, int32_t C,
+                          float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream);
+/* Conv1d weight [Cout, Cin, 3] -> GEMM operands: fwd [Cout, 3*Cin] and / or bwd [Cin, 3*Cout] (see csrc/head.cu);
+ * conv_unpack_grad maps the gradient of `fwd` back to [Cout, Cin, 3].                                          */
+int b200med_conv_pack(const float *w, float *fwd, float *bwd, int32_t Cout, int32_t Cin, void *stream);
+int b200med_conv_unpack_grad(const float *dfwd, float *dw, int32_t Cout, int32_t Cin, void *stream);
+/* y [B, C, R] <- x [B, R, C]: nn.Flatten of the reference runs over [B, C, L] (models.py:100).                  */
+int b200med_transpose_last2(const float *x, float *y, int64_t B, int32_t R, int32_t C, void *stream);
 
 /* Persistent recurrence, one launch per layer and direction (csrc/lstm_rec.cu; hidden_size H = 128 only).
  * A CTA owns 128 windows and walks all W steps: W_hh (bf16 [4H,H], nn.LSTM weight_hh_l{k} layout) stays in
@@ -388,6 +460,17 @@ int b200med_cascade(const int32_t *binary, const int32_t *multiclass, int64_t n,
 /* Confusion counts cm[C,C] of (target, pred) i32 vectors; deterministic.                         */
 int b200med_confusion(const int32_t *target, const int32_t *pred, int64_t n, int32_t C, int64_t *cm,
                       int32_t accumulate, void *stream);
+
+/* Area under the ROC curve of n (score, binary label) pairs -- sklearn.metrics.roc_auc_score as the reference calls
+ * it on stored per-sample probabilities (MED/modeling/modeling_utils.py:1124, 1243); the "AUC" of north_star's
+ * "frame-level F1/AUC identical to 3 decimals".  Integer counting (sort of the negatives' order-preserving keys, one
+ * binary search per positive): AUC = (2 #{neg < pos} + #{neg == pos}) / (2 n_pos n_neg), ties as sklearn's trapezoids.
+ *   scores, labels [n] f32 (label > 0.5 = positive); auc [1] f64 OUT (NaN when one class is absent -- the host
+ *   wrapper raises ValueError like sklearn); stats [4] i64 OUT = {n_pos, n_neg, 2*less + equal, 0};
+ *   workspace >= b200med_roc_auc_ws_bytes(n).                                                                     */
+int64_t b200med_roc_auc_ws_bytes(int64_t n);
+int b200med_roc_auc(const float *scores, const float *labels, int64_t n, double *auc, int64_t *stats,
+                    void *workspace, void *stream);
 
 #ifdef __cplusplus
 }

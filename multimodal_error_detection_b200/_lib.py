@@ -18,7 +18,7 @@ class StreamDesc(C.Structure):
     """Mirror of ``b200med_stream_desc`` (include/b200med.h)."""
     _fields_ = [("table", C.c_void_p), ("mean", C.c_void_p), ("stdv", C.c_void_p), ("out", C.c_void_p),
                 ("dim", C.c_int32), ("table_dtype", C.c_int32), ("out_dtype", C.c_int32), ("out_ld", C.c_int32),
-                ("out_col", C.c_int32), ("stat_rows", C.c_int32), ("exact_div", C.c_int32), ("reserved", C.c_int32)]
+                ("out_col", C.c_int32), ("stat_rows", C.c_int32), ("exact_div", C.c_int32), ("table_rows", C.c_int32)]
 
 
 _p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -33,8 +33,11 @@ SIGNATURES = {
     "b200med_window_fill": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "b200med_powerset": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "b200med_gather_norm": (C.c_int, [C.POINTER(StreamDesc), _i32, _p, _i64, _i32, _i32, _p]),
+    "b200med_gather_last_variant": (C.c_int, []),
     "b200med_standardise_rows": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "b200med_linear_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "b200med_gemm_f32_ws_bytes": (_i64, [_i64, _i64, _i64]),
+    "b200med_gemm_f32": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _p, _i64, _i32, _p, _p]),
     "b200med_linear_bwd_data_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "b200med_linear_bwd_weight_ws_bytes": (_i64, [_i64, _i32, _i32]),
     "b200med_linear_bwd_weight_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
@@ -54,6 +57,18 @@ SIGNATURES = {
     "b200med_zero_cols_bf16": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p]),
     "b200med_lstm_cell_fwd": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _p, _i64, _i32, _f, _p, C.c_uint64, _p]),
     "b200med_lstm_cell_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _p, _i32, _p, _i64, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_lstm_pack_f32": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p]),
+    "b200med_lstm_unpack_f32": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p]),
+    "b200med_lstm_cell_fwd_f32": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_lstm_cell_bwd_f32": (C.c_int, [_p, _p, _p, _p, _i32, _p, _p, _i32, _p, _i64, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_bn_ws_bytes": (_i64, [_i64, _i32]),
+    "b200med_bn_fwd": (C.c_int, [_p, _i64, _i32, _p, _p, _f, _f, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "b200med_bn_bwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "b200med_pool_drop_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_pool_drop_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_conv_pack": (C.c_int, [_p, _p, _p, _i32, _i32, _p]),
+    "b200med_conv_unpack_grad": (C.c_int, [_p, _p, _i32, _i32, _p]),
+    "b200med_transpose_last2": (C.c_int, [_p, _p, _i64, _i32, _i32, _p]),
     "b200med_loss_ws_bytes": (_i64, [_i64]),
     "b200med_bce_logits": (C.c_int, [_p, _p, _i64, _f, _f, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "b200med_ce_logits": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _f, _p, _p, _p, _p, _i32, _i32, _p, _i32,
@@ -83,6 +98,8 @@ SIGNATURES = {
     "b200med_soft_vote": (C.c_int, [_p, _p, _p, _i64, _p, _p, _i32, _p, _p]),
     "b200med_cascade": (C.c_int, [_p, _p, _i64, _p, _p]),
     "b200med_confusion": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p]),
+    "b200med_roc_auc_ws_bytes": (_i64, [_i64]),
+    "b200med_roc_auc": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -32,6 +32,7 @@ struct StreamParams {
     const float *stdv;
     void *out;
     int dim, table_dtype, out_dtype, out_ld, out_col, stat_rows, exact_div, path;  // path: 0 generic, 1 wide
+    int table_rows;        // rows of the table (0 = unknown): a window that leaves the table traps instead of reading past it
     long long unit_begin;  // first global work-unit index of this stream
     int slabs;             // wide: column slabs per row; generic: unused
     int chunks;            // wide: row chunks per window
@@ -52,6 +53,14 @@ __device__ __forceinline__ float standardise(float x, float mean, float sd_or_in
     return EXACT ? __fdiv_rn(__fsub_rn(x, mean), sd_or_inv) : (x - mean) * sd_or_inv;
 }
 
+// A window start outside the table is an index bug of the caller (the reference raises IndexError): trap -- the launch
+// fails with a CUDA error -- instead of reading past the table.
+__device__ __forceinline__ long long checked_start(const StreamParams &sp, const int32_t *__restrict__ starts, long long b, int W) {
+    const long long s = starts[b];
+    if (sp.table_rows > 0 && (s < 0 || s + W > (long long)sp.table_rows)) __trap();
+    return s;
+}
+
 // ---- wide path: f32 table, VPT consecutive floats per thread, U rows in flight ------------------
 template <typename OutT, bool EXACT>
 __device__ __forceinline__ void wide_unit(const StreamParams &sp, const int32_t *__restrict__ starts, int W,
@@ -65,7 +74,7 @@ __device__ __forceinline__ void wide_unit(const StreamParams &sp, const int32_t 
     const int col = (slab * kThreads + threadIdx.x) * VPT;
     const int t0 = chunk * kRowsPerUnit;
     const int rows = min(kRowsPerUnit, W - t0);
-    const long long src_row = (long long)starts[b] + t0;
+    const long long src_row = checked_start(sp, starts, b, W) + t0;
     const float *src = reinterpret_cast<const float *>(sp.table) + src_row * sp.dim + col;
 
     float4 x[kRowsPerUnit][NV];
@@ -132,7 +141,7 @@ __device__ __forceinline__ void generic_unit(const StreamParams &sp, const int32
     const int units_per_window = (run + per_unit - 1) / per_unit;
     const long long b = unit / units_per_window;
     const int u = (int)(unit % units_per_window);
-    const long long src0 = (long long)starts[b] * sp.dim;
+    const long long src0 = checked_start(sp, starts, b, W) * sp.dim;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int e = u * per_unit + k * kThreads + threadIdx.x;
@@ -188,11 +197,18 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Bounded spin (like every mbarrier wait of this library): a bulk copy that never lands -- a bad source address -- traps
+// and surfaces as a CUDA error instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && spins > (1u << 22)) __trap();
+    }
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -228,7 +244,7 @@ gather_norm_tma_kernel(const __grid_constant__ GatherParams p) {
         const int t0 = chunk * R;
         const int rows = min(R, W - t0);
         const uint32_t bytes = (uint32_t)((size_t)rows * D * sizeof(float));
-        const float *src = reinterpret_cast<const float *>(sp.table) + ((long long)p.starts[b] + t0) * D;
+        const float *src = reinterpret_cast<const float *>(sp.table) + (checked_start(sp, p.starts, b, W) + t0) * D;
         mbar_expect_tx(&full_bar[stage], bytes);
         tma_bulk_g2s(stage_ptr[stage], src, bytes, &full_bar[stage]);
     };
@@ -323,6 +339,11 @@ __global__ void standardise_rows_kernel(const float *__restrict__ x, const float
 
 using namespace b200med;
 
+// which device path the last b200med_gather_norm call of this thread took for stream 0 (tests assert that the
+// benchmarked instantiation is the one they compared with the oracle): 1 = LDG kernel only, 2.. = TMA staging ring shape
+static thread_local int g_last_gather_variant = 0;
+extern "C" __attribute__((visibility("default"))) int b200med_gather_last_variant(void) { return g_last_gather_variant; }
+
 extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const b200med_stream_desc *streams, int32_t n_streams, const int32_t *starts,
                                    int64_t B, int32_t W, int32_t variant, void *stream) {
     B200MED_REQUIRE(streams && n_streams >= 1 && n_streams <= B200MED_MAX_STREAMS, "1..8 streams");
@@ -352,6 +373,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const 
         sp.table = d.table; sp.mean = d.mean; sp.stdv = d.stdv; sp.out = d.out;
         sp.dim = d.dim; sp.table_dtype = d.table_dtype; sp.out_dtype = d.out_dtype;
         sp.out_ld = d.out_ld; sp.out_col = d.out_col; sp.stat_rows = d.stat_rows; sp.exact_div = d.exact_div;
+        sp.table_rows = d.table_rows > 0 ? d.table_rows : 0;
         const int vpt = d.out_dtype == B200MED_BF16 ? 8 : 4;
         const size_t out_es = d.out_dtype == B200MED_BF16 ? 2 : 4;
         const bool aligned = ((uintptr_t)d.table % 16 == 0) && ((uintptr_t)d.out % 16 == 0) &&
@@ -378,7 +400,9 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const 
     // peak at B=8192); bf16 output -> TMA staging ring, 8-row stages when W is a multiple of 8 (0.85), else 2-row stages.
     if (variant == 0 && p.s[0].path == 1 && p.s[0].out_dtype == B200MED_BF16 && B * (long long)W >= 4096)
         variant = (W % 8 == 0) ? 5 : 4;
+    g_last_gather_variant = 1;
     if (variant >= 2 && variant != 3 && p.s[0].path == 1) {
+        g_last_gather_variant = variant;
         GatherParams pt = p;
         pt.n_streams = 1;
         // variant -> (rows per stage, stages, threads): 2 = (4,3,256)  4 = (2,4,256)  5 = (8,3,256)  6 = (4,3,512)  7 = (2,6,256)

@@ -14,10 +14,12 @@
 namespace b200med {
 
 constexpr int BM = 64, BN = 64, BK = 16;   // the large tile (TM = 4); TM = 2 gives 32 x 32 tiles
+constexpr int kGemmRelu = 1, kGemmAccum = 2, kGemmReluA = 4, kGemmReluB = 8, kGemmSplit = 16;   // `flags` bits (b200med.h)
 
 // C[i,j] = sum_r A(i,r) * B(j,r)   with A(i,r) = A[i*a_rs + r*a_cs], B(j,r) = B[j*b_rs + r*b_cs].
-// Epilogue: + bias[j], ReLU, * (mask[i,j] > 0).  blockIdx.z = reduction slab (split-R), partial
-// results go to C + z*slab_stride when gridDim.z > 1.
+// Epilogue: + bias[j], (+ the old C[i,j]: kGemmAccum), ReLU, * (mask[i,j] > 0).  Operand transforms on load: kGemmReluA /
+// kGemmReluB clamp the A / B elements at zero (a ReLU that precedes the product is never materialised).
+// blockIdx.z = reduction slab (split-R), partial results go to C + z*slab_stride when gridDim.z > 1.
 // TM = micro-tile edge per thread (16 x 16 threads): TM = 4 -> 64 x 64 CTA tiles, TM = 2 -> 32 x 32 tiles for problems
 // whose 64 x 64 grid would leave most SMs idle (the frame path's M = T ~ 600 rows).  Every output is the same ascending-r
 // FMA chain in both, so the tile choice does not change a single bit of the result.
@@ -53,6 +55,7 @@ gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float 
             const int ii = a_r_fast ? (e / BK) : (e % TB);
             const long long gi = i0 + ii, gr = r0 + rr;
             ra[l] = (gi < I && gr < r_end) ? __ldg(A + gi * a_rs + gr * a_cs) : 0.0f;
+            if (relu & kGemmReluA) ra[l] = fmaxf(ra[l], 0.0f);
         }
 #pragma unroll
         for (int l = 0; l < LD; ++l) {
@@ -61,6 +64,7 @@ gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float 
             const int jj = b_r_fast ? (e / BK) : (e % TB);
             const long long gj = j0 + jj, gr = r0 + rr;
             rb[l] = (gj < J && gr < r_end) ? __ldg(B + gj * b_rs + gr * b_cs) : 0.0f;
+            if (relu & kGemmReluB) rb[l] = fmaxf(rb[l], 0.0f);
         }
     };
     if (r_begin < r_end) fetch(r_begin);
@@ -105,7 +109,8 @@ gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float 
             if (gj >= J) continue;
             float y = acc[u][v];
             if (bias) y += bias[gj];
-            if (relu) y = fmaxf(y, 0.0f);
+            if (relu & kGemmAccum) y += Cz[gi * ldc + gj];
+            if (relu & kGemmRelu) y = fmaxf(y, 0.0f);
             if (mask && !(mask[gi * ld_mask + gj] > 0.0f)) y = 0.0f;
             Cz[gi * ldc + gj] = y;
         }
@@ -263,6 +268,33 @@ extern "C" __attribute__((visibility("default"))) int b200med_linear_fwd_f32(con
     if (M == 0) return B200MED_OK;
     B200MED_REQUIRE(x && w && y, "null pointer");
     return launch_gemm(x, w, y, M, N, K, K, 1, K, 1, N, bias, relu, nullptr, 0, 1, 0, (cudaStream_t)stream);
+}
+
+static long long split_slabs(long long I, long long J, long long R) { return weight_slabs(R, I, J); }
+
+extern "C" __attribute__((visibility("default"))) int64_t b200med_gemm_f32_ws_bytes(int64_t I, int64_t J, int64_t R) {
+    return split_slabs(I, J, R) * I * J * 4 + 256;
+}
+
+// General strided fp32 product (see b200med.h): C[i,j] = epilogue(sum_r A[i*a_rs + r*a_cs] * B[j*b_rs + r*b_cs]).
+extern "C" __attribute__((visibility("default"))) int b200med_gemm_f32(const float *A, const float *B, float *C, int64_t I, int64_t J, int64_t R,
+                                int64_t a_rs, int64_t a_cs, int64_t b_rs, int64_t b_cs, int64_t ldc, const float *bias,
+                                const float *mask, int64_t ld_mask, int32_t flags, void *workspace, void *stream) {
+    B200MED_REQUIRE(I >= 0 && J >= 1 && R >= 1 && ldc >= J, "bad shape");
+    if (I == 0) return B200MED_OK;
+    B200MED_REQUIRE(A && B && C, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(flags & kGemmSplit))
+        return launch_gemm(A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, flags & 15, mask, ld_mask, 1, 0, st);
+    // long reduction, small output (weight gradients): deterministic slabs, summed in ascending order
+    B200MED_REQUIRE(workspace && !bias && !mask && ldc == J && !(flags & kGemmRelu), "split-R products take no epilogue and a dense C");
+    const int slabs = (int)split_slabs(I, J, R);
+    float *part = reinterpret_cast<float *>(workspace);
+    if (int e = launch_gemm(A, B, part, I, J, R, a_rs, a_cs, b_rs, b_cs, J, nullptr, flags & (kGemmReluA | kGemmReluB), nullptr, 0,
+                            slabs, I * J, st)) return e;
+    const long long n = I * J, blocks = (n + 255) / 256;
+    slab_reduce_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(part, C, n, slabs, n, (flags & kGemmAccum) ? 1 : 0);
+    return after_launch("slab_reduce_kernel");
 }
 
 extern "C" __attribute__((visibility("default"))) int b200med_linear_bwd_data_f32(const float *dy, const float *w, const float *relu_out, float *dx,

@@ -1,0 +1,365 @@
+// Window-classifier heads (MED/modeling/models.py:49-131 CNN, :166-186 / :204-210 the LSTM head's MLP) -- the layers around
+// the GEMMs: BatchNorm1d (batch statistics, running-stat update, backward), MaxPool1d(2) + Dropout, and the weight
+// re-packing that turns Conv1d(k = 3) into a GEMM over OVERLAPPING rows of the time-major activations.
+//
+// Layout.  Activations are row-major [rows, C] with the channel contiguous: a Linear layer's [B, C]; a convolution's
+// time-major [B * L, C] (row = (window b, step l)) -- the reference's Conv1d runs over [B, C, L], but the head input is a
+// permuted VIEW of a [B, W, F] tensor (modeling_utils.py:47), so time-major is the layout the data already has.
+//   conv(k=3):  out[b, l, co] = sum_{k, ci} x[b, l+k, ci] w[co, ci, k]  = row (b, l) of a GEMM whose A row is the 3*Cin
+//               CONTIGUOUS floats starting at x[b, l, 0] (row stride Cin: rows overlap, no im2col copy) and whose B is
+//               w' [Cout, 3*Cin] with w'[co, k*Cin + ci] = w[co, ci, k] (conv_pack_kernel).  The product runs over all
+//               B*L - 2 rows; rows with l >= L - 2 straddle two windows and are never read afterwards.
+//   backward:   dx[b, l, ci] = sum_{k, co} dz[b, l-k, co] w[co, ci, k] = the same trick on dz with two zero rows in front
+//               and w'' [Cin, 3*Cout], w''[ci, k'*Cout + co] = w[co, ci, 2-k'] (dz is zero on the straddling rows).
+// BatchNorm statistics: per-slab (n, mean, M2) partials by a local two-pass, combined with Chan's formula in double and in
+// a fixed order -> deterministic, and as accurate as the CPU reference's double accumulation for the 1e-5 bar.
+#include "common.cuh"
+
+namespace b200med {
+
+constexpr int kBnCols = 32;   // columns per CTA (one per lane)
+constexpr int kBnWarps = 8;
+
+__device__ __forceinline__ bool head_keep(uint32_t seed, unsigned long long index, float p) {
+    uint64_t z = index + 0x9E3779B97F4A7C15ull * (uint64_t)(seed + 1u);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    const float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+    return u >= p;
+}
+
+// part [S][3][C] = (n, mean, M2) of every row slab
+__global__ void __launch_bounds__(kBnCols * kBnWarps)
+bn_stats_partial_kernel(const float *__restrict__ x, long long ld, long long M, int C, long long rows_per_slab,
+                        float *__restrict__ part) {
+    __shared__ double sh[kBnWarps][kBnCols];
+    __shared__ float sh_mean[kBnCols];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x * kBnCols + lane;
+    const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+    const bool ok = col < C;
+    float s = 0.0f;
+    if (ok) for (long long m = m0 + w; m < m1; m += kBnWarps) s += x[m * ld + col];
+    sh[w][lane] = (double)s;
+    __syncthreads();
+    if (w == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < kBnWarps; ++r) t += sh[r][lane];
+        sh_mean[lane] = (float)(t / (double)max(1LL, m1 - m0));
+    }
+    __syncthreads();
+    const float mu = sh_mean[lane];
+    float q = 0.0f;
+    if (ok) for (long long m = m0 + w; m < m1; m += kBnWarps) { const float d = x[m * ld + col] - mu; q = fmaf(d, d, q); }
+    __syncthreads();
+    sh[w][lane] = (double)q;
+    __syncthreads();
+    if (w == 0 && ok) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < kBnWarps; ++r) t += sh[r][lane];
+        float *p = part + (long long)blockIdx.y * 3 * C;
+        p[col] = (float)(m1 - m0);
+        p[C + col] = mu;
+        p[2 * C + col] = (float)t;
+    }
+}
+
+// Combine the slab partials of one column (Chan et al.), ascending slab order, in double.
+__device__ __forceinline__ void bn_combine(const float *__restrict__ part, int S, int C, int col, double &mean, double &m2) {
+    double n = 0.0, mu = 0.0, q = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const float *p = part + (long long)s * 3 * C;
+        const double ns = p[col], ms = p[C + col], qs = p[2 * C + col];
+        if (ns <= 0.0) continue;
+        const double d = ms - mu, tot = n + ns;
+        mu += d * ns / tot;
+        q += qs + d * d * n * ns / tot;
+        n = tot;
+    }
+    mean = mu; m2 = q;
+}
+
+// y = (x - mean) * rstd * gamma + beta with the batch statistics; the CTAs of row slab 0 also publish save_mean / save_rstd
+// and update the running statistics (momentum, unbiased variance) like nn.BatchNorm1d in training mode.
+__global__ void __launch_bounds__(kBnCols * kBnWarps)
+bn_apply_kernel(const float *__restrict__ x, long long ld, long long M, int C, long long rows_per_slab,
+                const float *__restrict__ part, int S, const float *__restrict__ gamma, const float *__restrict__ beta,
+                float eps, float momentum, float *__restrict__ y, long long ldy, float *__restrict__ save_mean,
+                float *__restrict__ save_rstd, float *__restrict__ running_mean, float *__restrict__ running_var,
+                long long *__restrict__ num_batches) {
+    __shared__ float sh_scale[kBnCols], sh_shift[kBnCols];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x * kBnCols + lane;
+    if (w == 0 && col < C) {
+        double mean, m2;
+        bn_combine(part, S, C, col, mean, m2);
+        const double var = m2 / (double)M;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float g = gamma ? gamma[col] : 1.0f, b = beta ? beta[col] : 0.0f;
+        sh_scale[lane] = rstd * g;
+        sh_shift[lane] = b - (float)mean * rstd * g;
+        if (blockIdx.y == 0) {
+            save_mean[col] = (float)mean;
+            save_rstd[col] = rstd;
+            if (running_mean) {
+                const double unbiased = M > 1 ? m2 / (double)(M - 1) : var;
+                running_mean[col] = (1.0f - momentum) * running_mean[col] + momentum * (float)mean;
+                running_var[col] = (1.0f - momentum) * running_var[col] + momentum * (float)unbiased;
+            }
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && num_batches) *num_batches += 1;
+    __syncthreads();
+    if (col >= C) return;
+    const float sc = sh_scale[lane], sf = sh_shift[lane];
+    const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+    for (long long m = m0 + w; m < m1; m += kBnWarps) y[m * ldy + col] = fmaf(x[m * ld + col], sc, sf);
+}
+
+// inference: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta
+__global__ void bn_eval_kernel(const float *__restrict__ x, long long M, int C, const float *__restrict__ rm,
+                               const float *__restrict__ rv, const float *__restrict__ gamma, const float *__restrict__ beta,
+                               float eps, float *__restrict__ y) {
+    const long long total = M * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        const float rstd = 1.0f / sqrtf(rv[c] + eps);
+        const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+        y[e] = (x[e] - rm[c]) * rstd * g + b;
+    }
+}
+
+// part [S][2][C] = (sum dy, sum dy * xhat) per slab
+__global__ void __launch_bounds__(kBnCols * kBnWarps)
+bn_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x, long long M, int C, long long rows_per_slab,
+                      const float *__restrict__ save_mean, const float *__restrict__ save_rstd, float *__restrict__ part) {
+    __shared__ float sh[2][kBnWarps][kBnCols];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x * kBnCols + lane;
+    const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+    float a = 0.0f, b = 0.0f;
+    if (col < C) {
+        const float mu = save_mean[col], rs = save_rstd[col];
+        for (long long m = m0 + w; m < m1; m += kBnWarps) {
+            const float g = dy[m * C + col];
+            a += g;
+            b = fmaf(g, (x[m * C + col] - mu) * rs, b);
+        }
+    }
+    sh[0][w][lane] = a; sh[1][w][lane] = b;
+    __syncthreads();
+    if (w == 0 && col < C) {
+        float ta = 0.0f, tb = 0.0f;
+#pragma unroll
+        for (int r = 0; r < kBnWarps; ++r) { ta += sh[0][r][lane]; tb += sh[1][r][lane]; }
+        float *p = part + (long long)blockIdx.y * 2 * C;
+        p[col] = ta; p[C + col] = tb;
+    }
+}
+
+// dx = gamma * rstd * (dy - mean(dy) - xhat * mean(dy * xhat)); relu_mask: multiplied by (x > 0) -- the ReLU that sits between
+// the Linear layer and this BatchNorm in the reference heads (x is that ReLU's output).
+__global__ void __launch_bounds__(kBnCols * kBnWarps)
+bn_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, long long M, int C, long long rows_per_slab,
+                    const float *__restrict__ part, int S, const float *__restrict__ save_mean,
+                    const float *__restrict__ save_rstd, const float *__restrict__ gamma, int relu_mask,
+                    float *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    __shared__ float sh_a[kBnCols], sh_b[kBnCols];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x * kBnCols + lane;
+    if (w == 0 && col < C) {
+        double sa = 0.0, sb = 0.0;
+        for (int s = 0; s < S; ++s) { sa += part[(long long)s * 2 * C + col]; sb += part[(long long)s * 2 * C + C + col]; }
+        if (blockIdx.y == 0) { if (dbeta) dbeta[col] = (float)sa; if (dgamma) dgamma[col] = (float)sb; }
+        sh_a[lane] = (float)(sa / (double)M);
+        sh_b[lane] = (float)(sb / (double)M);
+    }
+    __syncthreads();
+    if (col >= C) return;
+    const float mu = save_mean[col], rs = save_rstd[col], g = (gamma ? gamma[col] : 1.0f) * rs;
+    const float ma = sh_a[lane], mb = sh_b[lane];
+    const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+    for (long long m = m0 + w; m < m1; m += kBnWarps) {
+        const float xv = x[m * C + col];
+        float v = g * (dy[m * C + col] - ma - (xv - mu) * rs * mb);
+        if (relu_mask && !(xv > 0.0f)) v = 0.0f;
+        dx[m * C + col] = v;
+    }
+}
+
+// MaxPool1d(2, 2) over the steps of every window + Dropout: z [B*L rows, C] (valid steps l < Lc of every window) ->
+// p [B*Lp, C], Lp = Lc / 2.
+__global__ void pool_drop_fwd_kernel(const float *__restrict__ z, float *__restrict__ p, long long B, int L, int Lp, int C,
+                                     float drop_p, const uint32_t *__restrict__ seed_dev, unsigned long long drop_base) {
+    const uint32_t seed = seed_dev ? *seed_dev : 0u;
+    const long long total = B * (long long)Lp * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        const long long r = e / C;
+        const int j = (int)(r % Lp);
+        const long long b = r / Lp;
+        const float *src = z + ((b * L + 2 * j) * (long long)C + c);
+        float v = fmaxf(src[0], src[C]);
+        if (drop_p > 0.0f) v = head_keep(seed, drop_base + (unsigned long long)e, drop_p) ? v / (1.0f - drop_p) : 0.0f;
+        p[e] = v;
+    }
+}
+
+// dz [2 + B*L rows, C] <- dp [B*Lp, C]: the gradient goes to the FIRST maximum of each pair (torch's tie rule), through the
+// dropout mask; every other row (odd tail, the straddling rows l >= Lc) is zero, and so are the TWO EXTRA ROWS IN FRONT that
+// the data-gradient product of the convolution reads for l < 2 (csrc/head.cu header).
+__global__ void pool_drop_bwd_kernel(const float *__restrict__ dp, const float *__restrict__ z, float *__restrict__ dz,
+                                     long long B, int L, int Lp, int C, float drop_p, const uint32_t *__restrict__ seed_dev,
+                                     unsigned long long drop_base) {
+    const uint32_t seed = seed_dev ? *seed_dev : 0u;
+    const long long total = (B * (long long)L + 2) * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        const long long r = e / C - 2;
+        float v = 0.0f;
+        if (r >= 0) {
+            const int l = (int)(r % L);
+            const long long b = r / L;
+            const int j = l >> 1;
+            if (j < Lp) {
+                const float *pair = z + ((b * L + 2 * j) * (long long)C + c);
+                const bool first_wins = !(pair[C] > pair[0]);
+                if (((l & 1) == 0) == first_wins) {
+                    const long long pe = (b * Lp + j) * (long long)C + c;
+                    v = dp[pe];
+                    if (drop_p > 0.0f) v = head_keep(seed, drop_base + (unsigned long long)pe, drop_p) ? v / (1.0f - drop_p) : 0.0f;
+                }
+            }
+        }
+        dz[e] = v;
+    }
+}
+
+// w [Cout, Cin, 3] -> fwd [Cout, 3*Cin] (fwd[co, k*Cin + ci] = w[co, ci, k]) and bwd [Cin, 3*Cout]
+// (bwd[ci, k*Cout + co] = w[co, ci, 2-k]); either destination may be null.
+__global__ void conv_pack_kernel(const float *__restrict__ w, float *__restrict__ fwd, float *__restrict__ bwd, int Cout, int Cin) {
+    const int total = Cout * Cin * 3;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int k = e % 3, ci = (e / 3) % Cin, co = e / (3 * Cin);
+        const float v = w[e];
+        if (fwd) fwd[(long long)co * 3 * Cin + k * Cin + ci] = v;
+        if (bwd) bwd[(long long)ci * 3 * Cout + (2 - k) * Cout + co] = v;
+    }
+}
+// gradient of the packed forward weight [Cout, 3*Cin] -> dw [Cout, Cin, 3]
+__global__ void conv_unpack_grad_kernel(const float *__restrict__ dfwd, float *__restrict__ dw, int Cout, int Cin) {
+    const int total = Cout * Cin * 3;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int k = e % 3, ci = (e / 3) % Cin, co = e / (3 * Cin);
+        dw[e] = dfwd[(long long)co * 3 * Cin + k * Cin + ci];
+    }
+}
+
+// y [B, C, R] <- x [B, R, C] (the reference's nn.Flatten runs over [B, C, L]; the native conv stack is time-major)
+__global__ void transpose_last2_kernel(const float *__restrict__ x, float *__restrict__ y, long long B, int R, int C) {
+    const long long total = B * (long long)R * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e % R);
+        const long long q = e / R;
+        const int c = (int)(q % C);
+        const long long b = q / C;
+        y[e] = x[(b * R + r) * (long long)C + c];
+    }
+}
+
+static long long bn_slabs(long long M) {
+    long long s = (M + 255) / 256;
+    return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+static unsigned ew_grid(long long total) {
+    const long long want = (total + 255) / 256, cap = (long long)num_sms() * 8;
+    return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace b200med
+
+using namespace b200med;
+
+extern "C" __attribute__((visibility("default"))) int64_t b200med_bn_ws_bytes(int64_t M, int32_t C) { return bn_slabs(M) * 3 * (int64_t)C * 4 + 256; }
+
+extern "C" __attribute__((visibility("default"))) int b200med_bn_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta,
+                               float eps, float momentum, int32_t training, float *running_mean, float *running_var,
+                               int64_t *num_batches_tracked, float *y, float *save_mean, float *save_rstd, void *workspace,
+                               void *stream) {
+    B200MED_REQUIRE(M >= 1 && C >= 1, "bad shape");
+    B200MED_REQUIRE(x && y, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!training) {
+        B200MED_REQUIRE(running_mean && running_var, "inference needs the running statistics");
+        bn_eval_kernel<<<ew_grid(M * C), 256, 0, st>>>(x, M, C, running_mean, running_var, gamma, beta, eps, y);
+        return after_launch("bn_eval_kernel");
+    }
+    B200MED_REQUIRE(save_mean && save_rstd && workspace, "training needs save_mean, save_rstd and a workspace");
+    const int S = (int)bn_slabs(M);
+    const long long rows = (M + S - 1) / S;
+    dim3 grid((unsigned)((C + kBnCols - 1) / kBnCols), (unsigned)S);
+    float *part = reinterpret_cast<float *>(workspace);
+    bn_stats_partial_kernel<<<grid, kBnCols * kBnWarps, 0, st>>>(x, C, M, C, rows, part);
+    if (int e = after_launch("bn_stats_partial_kernel")) return e;
+    bn_apply_kernel<<<grid, kBnCols * kBnWarps, 0, st>>>(x, C, M, C, rows, part, S, gamma, beta, eps, momentum, y, C, save_mean,
+                                                         save_rstd, running_mean, running_var, (long long *)num_batches_tracked);
+    return after_launch("bn_apply_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_bn_bwd(const float *dy, const float *x, int64_t M, int32_t C, const float *gamma,
+                               const float *save_mean, const float *save_rstd, int32_t relu_mask, float *dx, float *dgamma,
+                               float *dbeta, void *workspace, void *stream) {
+    B200MED_REQUIRE(M >= 1 && C >= 1, "bad shape");
+    B200MED_REQUIRE(dy && x && save_mean && save_rstd && dx && workspace, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = (int)bn_slabs(M);
+    const long long rows = (M + S - 1) / S;
+    dim3 grid((unsigned)((C + kBnCols - 1) / kBnCols), (unsigned)S);
+    float *part = reinterpret_cast<float *>(workspace);
+    bn_bwd_partial_kernel<<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, save_mean, save_rstd, part);
+    if (int e = after_launch("bn_bwd_partial_kernel")) return e;
+    bn_bwd_apply_kernel<<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, part, S, save_mean, save_rstd, gamma, relu_mask, dx,
+                                                             dgamma, dbeta);
+    return after_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_pool_drop_fwd(const float *z, float *p, int64_t B, int32_t L, int32_t Lc, int32_t C,
+                                      float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream) {
+    B200MED_REQUIRE(B >= 1 && L >= 2 && Lc >= 2 && Lc <= L && C >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
+    B200MED_REQUIRE(z && p, "null pointer");
+    const int Lp = Lc / 2;
+    pool_drop_fwd_kernel<<<ew_grid(B * (long long)Lp * C), 256, 0, (cudaStream_t)stream>>>(z, p, B, L, Lp, C, drop_p, seed, drop_base);
+    return after_launch("pool_drop_fwd_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_pool_drop_bwd(const float *dp, const float *z, float *dz, int64_t B, int32_t L,
+                                      int32_t Lc, int32_t C, float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream) {
+    B200MED_REQUIRE(B >= 1 && L >= 2 && Lc >= 2 && Lc <= L && C >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
+    B200MED_REQUIRE(dp && z && dz, "null pointer");
+    pool_drop_bwd_kernel<<<ew_grid((B * (long long)L + 2) * C), 256, 0, (cudaStream_t)stream>>>(dp, z, dz, B, L, Lc / 2, C, drop_p, seed,
+                                                                                          drop_base);
+    return after_launch("pool_drop_bwd_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_conv_pack(const float *w, float *fwd, float *bwd, int32_t Cout, int32_t Cin, void *stream) {
+    B200MED_REQUIRE(Cout >= 1 && Cin >= 1 && w && (fwd || bwd), "bad argument");
+    conv_pack_kernel<<<ew_grid((long long)Cout * Cin * 3), 256, 0, (cudaStream_t)stream>>>(w, fwd, bwd, Cout, Cin);
+    return after_launch("conv_pack_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_conv_unpack_grad(const float *dfwd, float *dw, int32_t Cout, int32_t Cin, void *stream) {
+    B200MED_REQUIRE(Cout >= 1 && Cin >= 1 && dfwd && dw, "bad argument");
+    conv_unpack_grad_kernel<<<ew_grid((long long)Cout * Cin * 3), 256, 0, (cudaStream_t)stream>>>(dfwd, dw, Cout, Cin);
+    return after_launch("conv_unpack_grad_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_transpose_last2(const float *x, float *y, int64_t B, int32_t R, int32_t C, void *stream) {
+    B200MED_REQUIRE(B >= 0 && R >= 1 && C >= 1, "bad shape");
+    if (B == 0) return B200MED_OK;
+    B200MED_REQUIRE(x && y, "null pointer");
+    transpose_last2_kernel<<<ew_grid(B * (long long)R * C), 256, 0, (cudaStream_t)stream>>>(x, y, B, R, C);
+    return after_launch("transpose_last2_kernel");
+}

@@ -200,6 +200,88 @@ lstm_cell_bwd_kernel(const float *__restrict__ Gact, const float *__restrict__ c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- fp32 parity mode
+// The 1e-5 mode of the head (exp_kwargs['precision'] = "fp32"): same recurrence with fp32 operands on the SIMT GEMM
+// (gemm_f32.cu) and EXACT-math cells (expf / tanhf / IEEE division; cuDNN's fast-math cell is ~20x noisier than the CPU
+// reference, measured in round 1).  Buffers are time-major fp32: X_l [W, B, in_l], Hs_l [W, B, H], C_l [W, B, H],
+// G_l [W, B, 4H] (pre-activations, overwritten by the activated gates), dG_l [W, B, 4H].
+
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// x ([B, F, W] when layout == 0, [B, W, F] when layout == 1) -> X0 [W, B, F]
+__global__ void lstm_pack_f32_kernel(const float *__restrict__ x, float *__restrict__ X0, long long B, int F, int W, int layout) {
+    const long long total = B * (long long)F * W;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % F);
+        const long long r = e / F;
+        const long long b = r % B;
+        const int t = (int)(r / B);
+        X0[e] = layout ? x[(b * W + t) * F + k] : x[(b * F + k) * W + t];
+    }
+}
+// dX0 [W, B, ld] columns [0, F) -> dx in the layout of x
+__global__ void lstm_unpack_f32_kernel(const float *__restrict__ dX0, float *__restrict__ dx, long long B, int F, int W, int ld,
+                                       int layout) {
+    const long long total = B * (long long)F * W;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long b; int t, k;
+        if (layout) { k = (int)(e % F); const long long r = e / F; t = (int)(r % W); b = r / W; }
+        else { t = (int)(e % W); const long long r = e / W; k = (int)(r % F); b = r / F; }
+        dx[e] = dX0[((long long)t * B + b) * ld + k];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lstm_cell_fwd_f32_kernel(float *__restrict__ G, const float *__restrict__ c_prev, float *__restrict__ c_out,
+                         float *__restrict__ h_out, float *__restrict__ x_up, long long B, int H, float drop_p,
+                         const uint32_t *__restrict__ seed_dev, unsigned long long drop_base) {
+    const uint32_t seed = seed_dev ? *seed_dev : 0u;
+    const long long total = B * (long long)H;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / H;
+        const int j = (int)(e - b * H);
+        float *g = G + b * 4 * H;
+        const float i_ = sigmoid_exact(g[j]), f_ = sigmoid_exact(g[H + j]), g_ = tanhf(g[2 * H + j]), o_ = sigmoid_exact(g[3 * H + j]);
+        const float c = f_ * (c_prev ? c_prev[e] : 0.0f) + i_ * g_;
+        const float h = o_ * tanhf(c);
+        g[j] = i_; g[H + j] = f_; g[2 * H + j] = g_; g[3 * H + j] = o_;
+        c_out[e] = c;
+        h_out[e] = h;
+        if (x_up) x_up[e] = (drop_p > 0.0f) ? (dropout_keep(seed, drop_base + (unsigned long long)e, drop_p) ? h / (1.0f - drop_p) : 0.0f) : h;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_f32_kernel(const float *__restrict__ Gact, const float *__restrict__ c, const float *__restrict__ c_prev,
+                         const float *__restrict__ dh_up, int ld_up, const float *__restrict__ dh_rec,
+                         float *__restrict__ dc, int dc_init, float *__restrict__ dG, long long B, int H, float drop_p,
+                         const uint32_t *__restrict__ seed_dev, unsigned long long drop_base) {
+    const uint32_t seed = seed_dev ? *seed_dev : 0u;
+    const long long total = B * (long long)H;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / H;
+        const int j = (int)(e - b * H);
+        const float *g = Gact + b * 4 * H;
+        const float i_ = g[j], f_ = g[H + j], g_ = g[2 * H + j], o_ = g[3 * H + j];
+        float dh = 0.0f;
+        if (dh_up) {
+            float v = dh_up[b * ld_up + j];
+            if (drop_p > 0.0f) v = dropout_keep(seed, drop_base + (unsigned long long)e, drop_p) ? v / (1.0f - drop_p) : 0.0f;
+            dh += v;
+        }
+        if (dh_rec) dh += dh_rec[e];
+        const float tc = tanhf(c[e]);
+        const float dct = (dc_init ? 0.0f : dc[e]) + dh * o_ * (1.0f - tc * tc);
+        const float cp = c_prev ? c_prev[e] : 0.0f;
+        float *d = dG + b * 4 * H;
+        d[j] = dct * g_ * i_ * (1.0f - i_);
+        d[H + j] = dct * cp * f_ * (1.0f - f_);
+        d[2 * H + j] = dct * i_ * (1.0f - g_ * g_);
+        d[3 * H + j] = dh * tc * o_ * (1.0f - o_);
+        dc[e] = dct * f_;
+    }
+}
+
 static unsigned grid_for(long long total) {
     const long long want = (total + 255) / 256, cap = (long long)num_sms() * 8;
     return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
@@ -282,4 +364,42 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_bwd(cons
         Gact, c, c_prev, dh_up, ld_up, dh_rec, ld_rec, dc, dc_init, reinterpret_cast<__nv_bfloat16 *>(dG), B, H, drop_p, seed,
         drop_base);
     return after_launch("lstm_cell_bwd_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_f32(const float *x, float *X0, int64_t B, int32_t F, int32_t W,
+                                                                           int32_t x_layout, void *stream) {
+    B200MED_REQUIRE(B >= 1 && F >= 1 && W >= 1 && (x_layout == 0 || x_layout == 1), "bad shape");
+    B200MED_REQUIRE(x && X0, "null pointer");
+    lstm_pack_f32_kernel<<<grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream>>>(x, X0, B, F, W, x_layout);
+    return after_launch("lstm_pack_f32_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_f32(const float *dX0, float *dx, int64_t B, int32_t F, int32_t W,
+                                                                             int32_t ld, int32_t x_layout, void *stream) {
+    B200MED_REQUIRE(B >= 1 && F >= 1 && W >= 1 && ld >= F && (x_layout == 0 || x_layout == 1), "bad shape");
+    B200MED_REQUIRE(dX0 && dx, "null pointer");
+    lstm_unpack_f32_kernel<<<grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream>>>(dX0, dx, B, F, W, ld, x_layout);
+    return after_launch("lstm_unpack_f32_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_fwd_f32(float *G, const float *c_prev, float *c_out, float *h_out,
+                                                                               float *x_up, int64_t B, int32_t H, float drop_p,
+                                                                               const uint32_t *seed, uint64_t drop_base, void *stream) {
+    B200MED_REQUIRE(B >= 1 && H >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
+    B200MED_REQUIRE(G && c_out && h_out, "null pointer");
+    lstm_cell_fwd_f32_kernel<<<grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream>>>(G, c_prev, c_out, h_out, x_up, B, H, drop_p,
+                                                                                           seed, drop_base);
+    return after_launch("lstm_cell_fwd_f32_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_bwd_f32(const float *Gact, const float *c, const float *c_prev,
+                                                                               const float *dh_up, int32_t ld_up, const float *dh_rec,
+                                                                               float *dc, int32_t dc_init, float *dG, int64_t B, int32_t H,
+                                                                               float drop_p, const uint32_t *seed, uint64_t drop_base,
+                                                                               void *stream) {
+    B200MED_REQUIRE(B >= 1 && H >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
+    B200MED_REQUIRE(Gact && c && dc && dG, "null pointer");
+    lstm_cell_bwd_f32_kernel<<<grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream>>>(Gact, c, c_prev, dh_up, ld_up, dh_rec, dc,
+                                                                                           dc_init, dG, B, H, drop_p, seed, drop_base);
+    return after_launch("lstm_cell_bwd_f32_kernel");
 }

@@ -170,14 +170,28 @@ class DeviceWindowLoader:
     def index_batches(self):
         """Host int64 index tensors, one per (rank-local) batch (the consumer pins them: torch's caching host allocator
         keeps a pinned block alive until the asynchronous upload that reads it has run)."""
+        for idx, _ in self.index_batches_with_global():
+            yield idx
+
+    def index_batches_with_global(self):
+        """(rank-local index tensor, size of the GLOBAL batch it was cut from).  The second value lets a data-parallel train
+        loop weight its gradient by n_local / n_global when the shards of a short last batch differ by one window."""
         for k, idx in enumerate(self._global_batches()):
             if self.max_batches is not None and k >= self.max_batches:
                 break
+            n_global = idx.numel()
             if self.world_size > 1:
-                if idx.numel() < self.world_size:
+                if n_global < self.world_size:
                     continue       # fewer windows than ranks: dropped on EVERY rank (a rank without a step would stall the all-reduce)
                 idx = shard_batch(idx, self.rank, self.world_size)
-            yield idx
+            yield idx, n_global
+
+    def dp_weight(self, n_local: int, n_global: int) -> float:
+        """Factor that turns this rank's mean-reduced loss into its share of the GLOBAL batch mean under a SUM all-reduce
+        scaled by 1 / world_size: n_local * world_size / n_global (exactly 1 for even shards)."""
+        if self.world_size <= 1 or n_global <= 0:
+            return 1.0
+        return float(n_local) * self.world_size / float(n_global)
 
     def __iter__(self):
         ds = self.dataset

@@ -1,0 +1,202 @@
+"""The window heads of the reference (MED/modeling/models.py:49-131 CNN, :166-186 / :204-210 the LSTM head's MLP) on the
+b200med kernels, as two autograd nodes with explicit forward / backward launch sequences:
+
+* :class:`MLPTailFunction` -- ``[ReLU ->] (Linear -> ReLU -> BatchNorm1d)* -> Linear``: fp32 SIMT GEMMs with the ReLUs folded into
+  their operand loads / epilogues (``b200med_gemm_f32``), BatchNorm as deterministic two-kernel passes (``b200med_bn_fwd`` /
+  ``_bwd``, the backward also applies the ReLU mask).
+* :class:`ConvStackFunction` -- ``(Conv1d(k=3) -> MaxPool1d(2) -> Dropout -> BatchNorm1d)* -> Flatten`` on TIME-MAJOR activations:
+  the convolution is a GEMM over overlapping rows (no im2col copy, csrc/head.cu), pool + dropout one elementwise kernel.
+
+The ``nn.Module`` classes of ``modeling/models.py`` only hold the parameters (same ``state_dict`` keys as the reference); these
+functions read them.  fp32 arithmetic in both precision modes: the heads are < 3 % of the model FLOPs, and the 1e-5 parity bar of
+the fp32 mode then holds for them by construction.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _bn_tensors(bn: nn.BatchNorm1d):
+    return [bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked]
+
+
+class MLPTailFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, relu_in, training, bn_cfg, *t):
+        """x [B, K]; t = (W, b, gamma, beta, running_mean, running_var, num_batches_tracked) per hidden layer, then (W, b) of
+        the output layer; bn_cfg = [(eps, momentum)] per hidden layer."""
+        n_hidden = len(bn_cfg)
+        x = x.contiguous().float()
+        a_in, acts, ys, stats = x, [], [], []
+        for i in range(n_hidden):
+            W, b, gamma, beta, rm, rv, nbt = t[7 * i:7 * i + 7]
+            flags = ops.GEMM_RELU | (ops.GEMM_RELU_A if (i == 0 and relu_in) else 0)
+            a = ops.linear_f32(a_in, W.detach(), b.detach(), flags)
+            eps, mom = bn_cfg[i]
+            if mom is None:          # nn.BatchNorm1d(momentum=None): cumulative moving average
+                mom = 1.0 / float(nbt.item() + 1)
+            y, sm, sr = ops.bn_fwd(a, gamma.detach(), beta.detach(), eps, mom, training, rm, rv, nbt)
+            acts.append(a); ys.append(y); stats.append((sm, sr))
+            a_in = y
+        Wl, bl = t[7 * n_hidden], t[7 * n_hidden + 1]
+        flags = ops.GEMM_RELU_A if (n_hidden == 0 and relu_in) else 0
+        out = ops.linear_f32(a_in, Wl.detach(), bl.detach(), flags)
+        ctx.relu_in, ctx.training, ctx.n_hidden = relu_in, training, n_hidden
+        saved = [x] + acts + ys
+        for sm, sr in stats:
+            saved += [sm, sr] if training else []
+        ctx.save_for_backward(*saved, *[t[7 * i] for i in range(n_hidden)], *[t[7 * i + 2] for i in range(n_hidden)], Wl)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if not ctx.training:
+            raise NotImplementedError("b200med: backward through the head in eval mode (running BatchNorm statistics) is not "
+                                      "part of the reference's train / validation loops")
+        n = ctx.n_hidden
+        sv = ctx.saved_tensors
+        x, acts, ys = sv[0], sv[1:1 + n], sv[1 + n:1 + 2 * n]
+        stats = sv[1 + 2 * n:1 + 4 * n]
+        Ws, gammas, Wl = sv[1 + 4 * n:1 + 5 * n], sv[1 + 5 * n:1 + 6 * n], sv[1 + 6 * n]
+        grads = [None] * (7 * n + 2)
+        g = dout.contiguous().float()
+        last_in = ys[-1] if n else x
+        grads[7 * n] = ops.linear_wgrad_f32(g, last_in, relu_x=(n == 0 and ctx.relu_in))
+        grads[7 * n + 1] = ops.colsum(g)
+        need_dx = ctx.needs_input_grad[0]
+        if n or need_dx:
+            g = ops.linear_dgrad_f32(g, Wl, mask=x if (n == 0 and ctx.relu_in) else None)
+        for i in reversed(range(n)):
+            dz, dgamma, dbeta = ops.bn_bwd(g, acts[i], gammas[i], stats[2 * i], stats[2 * i + 1], relu_mask=True)
+            inp = ys[i - 1] if i > 0 else x
+            grads[7 * i] = ops.linear_wgrad_f32(dz, inp, relu_x=(i == 0 and ctx.relu_in))
+            grads[7 * i + 1] = ops.colsum(dz)
+            grads[7 * i + 2], grads[7 * i + 3] = dgamma, dbeta
+            if i > 0:
+                g = ops.linear_dgrad_f32(dz, Ws[i])
+            elif need_dx:
+                g = ops.linear_dgrad_f32(dz, Ws[i], mask=x if ctx.relu_in else None)
+        return (g if need_dx else None, None, None, None, *grads)
+
+
+def mlp_tail(x: torch.Tensor, seq: nn.Sequential, relu_in: bool, training: bool) -> torch.Tensor:
+    """Run ``seq`` = [Flatten,] (Linear, ReLU, BatchNorm1d)*, Linear on the fused kernels."""
+    mods = [m for m in seq if not isinstance(m, nn.Flatten)]
+    tensors, cfg, i = [], [], 0
+    while i < len(mods):
+        lin = mods[i]
+        if not isinstance(lin, nn.Linear):
+            raise ValueError(f"b200med head: unexpected layer {type(lin).__name__} (expected Linear)")
+        if i + 2 < len(mods) and isinstance(mods[i + 1], nn.ReLU) and isinstance(mods[i + 2], nn.BatchNorm1d):
+            bn = mods[i + 2]
+            tensors += [lin.weight, lin.bias] + _bn_tensors(bn)
+            cfg.append((bn.eps, bn.momentum))
+            i += 3
+        elif i == len(mods) - 1:
+            tensors += [lin.weight, lin.bias]
+            i += 1
+        else:
+            raise ValueError("b200med head: the fused MLP expects (Linear, ReLU, BatchNorm1d)* followed by one Linear")
+    return MLPTailFunction.apply(x.reshape(x.shape[0], -1), relu_in, training, cfg, *tensors)
+
+
+class ConvStackFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, layout, training, bn_cfg, drops, seed_dev, *t):
+        """x: [B, L, C] (layout 1, time-major) or [B, C, L] (layout 0, the reference's Conv1d layout);
+        t = (conv_w [Cout, Cin, 3], conv_b, gamma, beta, running_mean, running_var, num_batches_tracked) per block."""
+        nb = len(bn_cfg)
+        x = x.contiguous().float()
+        if layout == 0:
+            B, C0, L0 = x.shape
+            cur = ops.transpose_last2(x, B, C0, L0).view(B * L0, C0)
+        else:
+            B, L0, C0 = x.shape
+            cur = x.view(B * L0, C0)
+        L, Cin = L0, C0
+        ins, zs, ps, stats, wbs, geo = [], [], [], [], [], []
+        for i in range(nb):
+            w, b, gamma, beta, rm, rv, nbt = t[7 * i:7 * i + 7]
+            Cout = w.shape[0]
+            if L < 4:
+                raise ValueError(f"b200med CNN head: {L} steps left in front of a kernel-3 convolution + pool")
+            wf, wb = ops.conv_pack(w.detach(), True, training)
+            z = torch.empty(B * L, Cout, dtype=torch.float32, device=x.device)
+            # rows (b, l) over all B*L - 2 starts; those with l >= L - 2 straddle two windows and are never read
+            ops.gemm_f32(cur, wf, z, B * L - 2, Cout, 3 * Cin, Cin, 1, 3 * Cin, 1, Cout, bias=b.detach())
+            Lc = L - 2
+            p_drop = float(drops[i]) if training else 0.0
+            p = ops.pool_drop_fwd(z, B, L, Lc, Cout, p_drop, seed_dev, i << 40)
+            eps, mom = bn_cfg[i]
+            if mom is None:
+                mom = 1.0 / float(nbt.item() + 1)
+            y, sm, sr = ops.bn_fwd(p, gamma.detach(), beta.detach(), eps, mom, training, rm, rv, nbt)
+            ins.append(cur); zs.append(z); ps.append(p); stats.append((sm, sr)); wbs.append(wb)
+            geo.append((L, Lc, Cin, Cout, p_drop))
+            cur, L, Cin = y, Lc // 2, Cout
+        out = cur.view(B, L * Cin) if L == 1 else ops.transpose_last2(cur, B, L, Cin).view(B, Cin * L)
+        ctx.meta = (B, L0, C0, layout, training, nb, geo, L, Cin, seed_dev)
+        if training:
+            saved = ins + zs + ps + [s for st in stats for s in st] + wbs + [t[7 * i + 2] for i in range(nb)]
+            ctx.save_for_backward(*saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, L0, C0, layout, training, nb, geo, Lf, Cf, seed_dev = ctx.meta
+        if not training:
+            raise NotImplementedError("b200med: backward through the CNN head in eval mode is not part of the reference's loops")
+        sv = ctx.saved_tensors
+        ins, zs, ps = sv[:nb], sv[nb:2 * nb], sv[2 * nb:3 * nb]
+        stats, wbs, gammas = sv[3 * nb:5 * nb], sv[5 * nb:6 * nb], sv[6 * nb:7 * nb]
+        grads = [None] * (7 * nb)
+        g = dout.contiguous().float()
+        g = g.view(B * Lf, Cf) if Lf == 1 else ops.transpose_last2(g.view(B, Cf, Lf), B, Cf, Lf).view(B * Lf, Cf)
+        need_dx = ctx.needs_input_grad[0]
+        for i in reversed(range(nb)):
+            L, Lc, Cin, Cout, p_drop = geo[i]
+            dp, dgamma, dbeta = ops.bn_bwd(g, ps[i], gammas[i], stats[2 * i], stats[2 * i + 1], relu_mask=False)
+            dzpad = torch.empty(B * L + 2, Cout, dtype=torch.float32, device=g.device)     # two zero rows in front (written by the kernel)
+            ops.pool_drop_bwd(dp, zs[i], dzpad, B, L, Lc, Cout, p_drop, seed_dev, i << 40)
+            dz = dzpad[2:]
+            # dW' [Cout, 3*Cin] = sum over the B*L - 2 row starts of dz[i, co] * x[i*Cin + kc]  (dz is zero on straddling rows)
+            dwf = torch.empty(Cout, 3 * Cin, dtype=torch.float32, device=g.device)
+            ops.gemm_f32((dzpad, 2 * Cout), ins[i], dwf, Cout, 3 * Cin, B * L - 2, 1, Cout, 1, Cin, 3 * Cin, flags=ops.GEMM_SPLIT)
+            grads[7 * i] = ops.conv_unpack_grad(dwf, Cout, Cin)
+            grads[7 * i + 1] = ops.colsum(dz)
+            grads[7 * i + 2], grads[7 * i + 3] = dgamma, dbeta
+            if i > 0 or need_dx:
+                dx = torch.empty(B * L, Cin, dtype=torch.float32, device=g.device)
+                # dx[b, l, ci] = sum_{k', co} dzpad[(b*L + l) + k', co] * w''[ci, k'*Cout + co]
+                ops.gemm_f32(dzpad, wbs[i], dx, B * L, Cin, 3 * Cout, Cout, 1, 3 * Cout, 1, Cin)
+                g = dx
+        dxo = None
+        if need_dx:
+            dxo = g.view(B, L0, C0) if layout == 1 else ops.transpose_last2(g.view(B, L0, C0), B, L0, C0)
+        return (dxo, None, None, None, None, None, *grads)
+
+
+def conv_stack(x: torch.Tensor, seq: nn.Sequential, training: bool, seed_dev) -> torch.Tensor:
+    """Run ``seq`` = (Conv1d(k=3, stride 1), MaxPool1d(2, 2), Dropout, BatchNorm1d)*, Flatten on the fused kernels.
+    x is the reference's [B, C, L] head input; when it is a permuted view of a contiguous [B, L, C] tensor (what
+    ``define_inputs`` builds, modeling_utils.py:47) it is read in place."""
+    mods = list(seq)
+    tensors, cfg, drops, i = [], [], [], 0
+    while i < len(mods) and not isinstance(mods[i], nn.Flatten):
+        conv, pool, drop, bn = mods[i:i + 4]
+        ok = (isinstance(conv, nn.Conv1d) and conv.kernel_size == (3,) and conv.stride == (1,) and conv.padding == (0,)
+              and conv.dilation == (1,) and conv.groups == 1 and isinstance(pool, nn.MaxPool1d) and pool.kernel_size == 2
+              and pool.stride == 2 and isinstance(drop, nn.Dropout) and isinstance(bn, nn.BatchNorm1d))
+        if not ok:
+            raise ValueError("b200med CNN head: expected (Conv1d(k=3), MaxPool1d(2, 2), Dropout, BatchNorm1d) blocks")
+        tensors += [conv.weight, conv.bias] + _bn_tensors(bn)
+        cfg.append((bn.eps, bn.momentum))
+        drops.append(drop.p)
+        i += 4
+    tl = x.transpose(1, 2)
+    if tl.is_contiguous() and not x.is_contiguous():
+        return ConvStackFunction.apply(tl, 1, training, cfg, drops, seed_dev, *tensors)
+    return ConvStackFunction.apply(x, 0, training, cfg, drops, seed_dev, *tensors)

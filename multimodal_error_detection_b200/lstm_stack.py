@@ -240,6 +240,7 @@ class LSTMRecFunction(torch.autograd.Function):
             top = l == L - 1
             dG = torch.empty(W * Bp, 4 * H, dtype=torch.bfloat16, device=dev)   # gate columns permuted (see _dg_perm)
             keep.append(dG)
+            keep.append(A[l])       # read by the side-stream weight-gradient GEMM after autograd has released the saved tensors
             call("b200med_lstm_rec_bwd", _raw(Gact[l].data_ptr()), _raw(Cs[l].data_ptr()), _raw(Whh[l].data_ptr()),
                  _raw(dout.data_ptr() if top else 0), _raw(0 if top else dX_up.data_ptr()), 0 if top else inp[l + 1],
                  _raw(dG.data_ptr()), B, Bp, W, H, 0.0 if top else drop_p, _raw(seed_ptr), l * W * Bp * H, st)
@@ -278,12 +279,112 @@ class LSTMRecFunction(torch.autograd.Function):
         return (dx, None, None, *grads)
 
 
-def lstm_last_hidden(x: torch.Tensor, lstm: torch.nn.LSTM, training: bool, seed_dev=None, impl: str = "auto") -> torch.Tensor:
-    """h_{W-1} of the top layer for head input x [B, F, W]."""
+class LSTMF32Function(torch.autograd.Function):
+    """fp32 parity mode (1e-5 bar): the same recurrence with fp32 operands on the SIMT GEMM (csrc/gemm_f32.cu) and exact-math
+    cell kernels (csrc/lstm.cu).  Time-major fp32 buffers X_l [W, B, in_l], G_l [W, B, 4H], C_l / Hs_l [W, B, H]; per layer one
+    GEMM for the x-part of all steps, then per step one accumulating GEMM (h_{t-1} W_hh^T) + one cell kernel."""
+
+    @staticmethod
+    def forward(ctx, x, drop_p, seed_dev, *params):
+        B, F, W = x.shape
+        L = len(params) // 4
+        H = params[1].shape[1]
+        dev = x.device
+        st = _stream()
+        bwf = x.transpose(1, 2).is_contiguous() and not x.is_contiguous()
+        xsrc = (x.transpose(1, 2) if bwf else x.contiguous()).float()
+        X = [torch.empty(W, B, F, dtype=torch.float32, device=dev)]
+        call("b200med_lstm_pack_f32", _raw(xsrc.data_ptr()), _raw(X[0].data_ptr()), B, F, W, int(bwf), st)
+        seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
+        Gs, Cs, Hs = [], [], []
+        for l in range(L):
+            w_ih, w_hh, b_ih, b_hh = (q.detach() for q in params[4 * l:4 * l + 4])
+            in_l = F if l == 0 else H
+            G = torch.empty(W, B, 4 * H, dtype=torch.float32, device=dev)
+            ops.linear_f32(X[l].view(W * B, in_l), w_ih, b_ih + b_hh, out=G.view(W * B, 4 * H))
+            C_ = torch.empty(W, B, H, dtype=torch.float32, device=dev)
+            H_ = torch.empty(W, B, H, dtype=torch.float32, device=dev)
+            top = l == L - 1
+            Xn = None if top else torch.empty(W, B, H, dtype=torch.float32, device=dev)
+            for t in range(W):
+                if t > 0:
+                    ops.linear_f32(H_[t - 1], w_hh, None, ops.GEMM_ACCUM, out=G[t])
+                call("b200med_lstm_cell_fwd_f32", _raw(G[t].data_ptr()), _raw(C_[t - 1].data_ptr() if t else 0), _raw(C_[t].data_ptr()),
+                     _raw(H_[t].data_ptr()), _raw(0 if top else Xn[t].data_ptr()), B, H, 0.0 if top else float(drop_p),
+                     _raw(seed_ptr), (l * W + t) * B * H, st)
+            Gs.append(G); Cs.append(C_); Hs.append(H_)
+            if not top:
+                X.append(Xn)
+        out = Hs[-1][W - 1].clone()
+        ctx.save_for_backward(*X, *Gs, *Cs, *Hs, *[params[4 * l].detach() for l in range(L)], *[params[4 * l + 1].detach() for l in range(L)])
+        ctx.meta = (B, F, W, L, H, float(drop_p), seed_dev, bwf)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, F, W, L, H, drop_p, seed_dev, bwf = ctx.meta
+        sv = ctx.saved_tensors
+        X, Gs, Cs, Hs, Wih, Whh = (sv[i * L:(i + 1) * L] for i in range(6))
+        dev = dout.device
+        st = _stream()
+        seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
+        dout = dout.contiguous().float()
+        grads = [None] * (4 * L)
+        dX_up = None
+        for l in reversed(range(L)):
+            top = l == L - 1
+            in_l = F if l == 0 else H
+            dG = torch.empty(W, B, 4 * H, dtype=torch.float32, device=dev)
+            dc = torch.empty(B, H, dtype=torch.float32, device=dev)
+            dh_rec = None
+            for t in reversed(range(W)):
+                if top:
+                    up_ptr, p = (dout.data_ptr() if t == W - 1 else 0), 0.0
+                else:
+                    up_ptr, p = dX_up[t].data_ptr(), drop_p
+                call("b200med_lstm_cell_bwd_f32", _raw(Gs[l][t].data_ptr()), _raw(Cs[l][t].data_ptr()),
+                     _raw(Cs[l][t - 1].data_ptr() if t else 0), _raw(up_ptr), H, _raw(0 if dh_rec is None else dh_rec.data_ptr()),
+                     _raw(dc.data_ptr()), int(t == W - 1), _raw(dG[t].data_ptr()), B, H, float(p), _raw(seed_ptr),
+                     (l * W + t) * B * H, st)
+                if t > 0:
+                    dh_rec = ops.linear_dgrad_f32(dG[t], Whh[l])
+            dG2 = dG.view(W * B, 4 * H)
+            grads[4 * l] = ops.linear_wgrad_f32(dG2, X[l].view(W * B, in_l))
+            if W > 1:
+                grads[4 * l + 1] = ops.linear_wgrad_f32(dG[1:].view((W - 1) * B, 4 * H), Hs[l][:W - 1].view((W - 1) * B, H))
+            else:
+                grads[4 * l + 1] = torch.zeros_like(Whh[l])
+            db = ops.colsum(dG2)
+            grads[4 * l + 2] = db
+            grads[4 * l + 3] = db.clone()
+            if l > 0 or ctx.needs_input_grad[0]:
+                dX_up = ops.linear_dgrad_f32(dG2, Wih[l]).view(W, B, in_l)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((B, W, F) if bwf else (B, F, W), dtype=torch.float32, device=dev)
+            call("b200med_lstm_unpack_f32", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, F, W, F, int(bwf), st)
+            if bwf:
+                dx = dx.transpose(1, 2)
+        return (dx, None, None, *grads)
+
+
+def lstm_last_hidden(x: torch.Tensor, lstm: torch.nn.LSTM, training: bool, seed_dev=None, impl: str = "auto",
+                     precision: str = "bf16") -> torch.Tensor:
+    """h_{W-1} of the top layer for head input x [B, F, W].  precision "fp32": exact-math fp32 kernels (1e-5 mode);
+    "bf16": persistent tcgen05 recurrence (hidden_size 128) or per-step tcgen05 gate GEMMs + cell kernels (other sizes;
+    ``impl="per_step"`` forces that path -- used by the tests that hold the two implementations against each other)."""
+    if not x.is_cuda:
+        raise RuntimeError("b200med LSTM head runs on CUDA tensors only (no CPU fallback)")
+    if lstm.bidirectional or lstm.proj_size or not lstm.bias:
+        raise ValueError("b200med LSTM head: unidirectional nn.LSTM with biases and no projection (what the reference builds)")
     params = []
     for l in range(lstm.num_layers):
         params += [getattr(lstm, f"weight_ih_l{l}"), getattr(lstm, f"weight_hh_l{l}"),
                    getattr(lstm, f"bias_ih_l{l}"), getattr(lstm, f"bias_hh_l{l}")]
     p = float(lstm.dropout) if training else 0.0
+    if precision == "fp32":
+        return LSTMF32Function.apply(x, p, seed_dev, *params)
+    if precision != "bf16":
+        raise ValueError(f"precision {precision!r} is not supported (fp32 | bf16)")
     fn = LSTMRecFunction if (lstm.hidden_size == 128 and impl != "per_step") else LSTMStackFunction
     return fn.apply(x, p, seed_dev, *params)

@@ -114,7 +114,10 @@ class FusedCrossEntropyLoss(nn.Module):
     def forward(self, outputs, labels, mask=None, target_shift=0, reduction=None, pred_shift=0, pred_mask_mode=0,
                 cm_classes=None):
         w = None if self.weight is None else self.weight.to(outputs.device)
-        red = {"mean": 0, "sum": 2}.get(self.reduction, 0) if reduction is None else reduction
+        if reduction is None and self.reduction not in ("mean", "sum"):
+            raise NotImplementedError(f"FusedCrossEntropyLoss(reduction={self.reduction!r}): the K3 kernel returns a reduced loss "
+                                      "(mean / sum / masked mean); per-sample losses are not produced")
+        red = {"mean": 0, "sum": 2}[self.reduction] if reduction is None else reduction
         loss, probs, preds, cm = _CEFn.apply(outputs, labels, w, mask, target_shift, red, pred_shift, pred_mask_mode,
                                              cm_classes or outputs.shape[1])
         self.last = (probs, preds, cm)
@@ -178,6 +181,17 @@ def instantiate_model(exp_kwargs: dict, in_features: int, window_size: int, devi
     raise ValueError(f"Model {name} is not supported.")
 
 
+def _configure_precision(model, exp_kwargs: dict, precision: str) -> None:
+    """``exp_kwargs['precision']`` -> the head: "fp32" (exact-math kernels, 1e-5 bar) or "bf16" (tcgen05 kernels, 2e-2 bar).
+    Every layer of every head runs on b200med kernels in both modes; there is no other implementation to select."""
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision {precision!r} is not supported. Supported: 'fp32', 'bf16'.")
+    if precision == "bf16" and not ops.has_tcgen05():
+        raise RuntimeError("precision='bf16' needs the tcgen05 kernels (compute capability 10.x)")
+    if isinstance(model, (MultiStageModel, LSTM)):
+        model.precision = precision
+
+
 def define_model_objects(exp_kwargs: dict, in_features_dict: dict, device, class_counts: tuple, window_size: int = 0):
     """Reference modeling_utils.py:194-262 -> (feature_extractor, model, criterion, optimizer, scheduler).
 
@@ -188,20 +202,9 @@ def define_model_objects(exp_kwargs: dict, in_features_dict: dict, device, class
     if device.type != "cuda":
         raise RuntimeError("b200med runs on CUDA devices only (no CPU fallback)")
     precision = exp_kwargs.get("precision", "fp32")
-    if precision == "fp32":      # TF32 convolutions / matmuls cannot hold 1e-5
-        torch.backends.cudnn.allow_tf32 = False
-        torch.backends.cuda.matmul.allow_tf32 = False
-    else:                        # throughput mode (2e-2 bar): the small head layers left on torch may use the tensor cores
-        torch.backends.cudnn.allow_tf32 = True
-        torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(42)
     model = instantiate_model(exp_kwargs, in_features_dict[exp_kwargs["data_type"]], window_size, device).to(device)
-    if isinstance(model, MultiStageModel):
-        model.precision = precision
-    if hasattr(model, "use_cudnn"):
-        model.use_cudnn = precision != "fp32"
-        if precision == "bf16" and ops.has_tcgen05() and exp_kwargs.get("lstm_impl", "b200") in ("b200", "b200_per_step"):
-            model.impl = exp_kwargs.get("lstm_impl", "b200")
+    _configure_precision(model, exp_kwargs, precision)
     if exp_kwargs["data_type"] != "kinematics":
         feature_extractor = FeatureExtractor(input_dim=2048, output_dim=exp_kwargs["video_dims"], hidden_dims=[512, 256],
                                              precision=precision).to(device)
@@ -247,6 +250,11 @@ def compute_loss(outputs: torch.Tensor, e_labels: torch.Tensor, criterion, datas
             criterion = FusedCrossEntropyLoss(criterion.weight, criterion.reduction)
         return criterion(outputs, e_labels.long()), outputs
     if dataset_type == "frame":
+        # the frame kernel is the reference's loss as written (:278-295): 2 classes, soft targets [1-e, e], unweighted mean
+        if outputs.shape[-2] != 2:
+            raise NotImplementedError(f"frame loss: {outputs.shape[-2]} output classes (the reference's soft-target loss has 2)")
+        if getattr(criterion, "weight", None) is not None or getattr(criterion, "reduction", "mean") not in ("mean", "none"):
+            raise NotImplementedError("frame loss: class weights / sum reduction are not part of the reference's frame path")
         loss, preds, counts = _FrameCEFn.apply(outputs, e_labels.reshape(-1).to(outputs.device))
         if hasattr(criterion, "last"):
             criterion.last = (None, preds, counts)
@@ -323,14 +331,15 @@ def _set_train(model, feature_extractor, exp_kwargs, train: bool):
         m.train(train)
 
 
-def _backward(loss, optimizer=None):
+def _backward(loss, optimizer=None, weight: float = 1.0):
     """loss.backward() inside a train loop: the LSTM weight-gradient GEMMs stay on their side stream past the end of the
     backward (lstm_stack.DEFER_JOIN); the next consumer of the gradients (_allreduce_grads / optimizer.step, both through
-    FusedAdam._refresh_active) joins it."""
+    FusedAdam._refresh_active) joins it.  ``weight``: data-parallel share of this rank's batch (uneven shards of a short
+    batch), applied to the gradient only -- the reported loss stays the rank's own mean."""
     from .. import lstm_stack
     lstm_stack.DEFER_JOIN = isinstance(optimizer, FusedAdam)      # only FusedAdam joins the side stream before using the gradients
     try:
-        loss.backward()
+        (loss if weight == 1.0 else loss * weight).backward()
     finally:
         lstm_stack.DEFER_JOIN = False
 
@@ -351,17 +360,22 @@ def _window_batches(loader, exp_kwargs, device, image_dtype):
     if isinstance(loader, DeviceWindowLoader):
         ds = loader.dataset
         need_img = exp_kwargs["data_type"] != "kinematics"
-        for idx in loader.index_batches():
+        for idx, n_global in loader.index_batches_with_global():
             if idx.numel() == 0:
                 continue
+            _window_batches.dp_weight = loader.dp_weight(idx.numel(), n_global)
             didx = idx.pin_memory().to(device, non_blocking=True)      # pinned host -> device, 8 B per window
             images, kin = ds.gather_batch(didx, image_dtype=image_dtype if need_img else torch.float32,
                                           exact=image_dtype == torch.float32)
             yield images, kin, ds.g_labels_data.index_select(0, didx), ds.e_labels_data.index_select(0, didx), idx
     else:
         for batch in loader:
+            _window_batches.dp_weight = 1.0
             images, kin, g, e7, subject = batch[:5]
             yield images.to(device), kin.to(device), g.to(device), e7.to(device), subject
+
+
+_window_batches.dp_weight = 1.0      # data-parallel weight of the batch last yielded (see DeviceWindowLoader.dp_weight)
 
 
 def _subjects(loader, idx):
@@ -399,7 +413,7 @@ def train_single_epoch(model, feature_extractor, train_dataloader, criterion, op
         outputs = model(inputs)
         loss, outputs = compute_loss(outputs, y, criterion, exp_kwargs["dataset_type"])
         optimizer.zero_grad()
-        _backward(loss, optimizer)
+        _backward(loss, optimizer, 1.0 if frame else _window_batches.dp_weight)
         _allreduce_grads(optimizer)
         optimizer.step()
         if exp_kwargs.get("host_sync") == "step":
@@ -508,11 +522,15 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
     step the host copies the batch's window indices (pinned, 8 B per window) and replays; the short last batch runs
     eagerly.  Same return tuple and the same arithmetic as the eager loop."""
     from ..engine import WindowTrainStep
-    ds, B = loader.dataset, loader.batch_size
+    ds = loader.dataset
+    # the captured step serves this rank's share of a FULL global batch (data parallel: loader.batch_size is the global
+    # batch; every other batch -- the short last one, uneven shards -- runs eagerly)
+    world = max(1, int(getattr(loader, "world_size", 1)))
+    B = loader.batch_size // world if loader.batch_size % world == 0 else -1
     key = (id(ds), id(model), id(feature_extractor), id(criterion), B)
     stepper = getattr(optimizer, "_b200_stepper", None)
     if stepper is None or stepper.key != key:
-        stepper = WindowTrainStep(ds, feature_extractor, model, criterion, optimizer, exp_kwargs, B,
+        stepper = WindowTrainStep(ds, feature_extractor, model, criterion, optimizer, exp_kwargs, max(B, 1),
                                   prefetch=bool(exp_kwargs.get("prefetch_gather", _image_dtype(feature_extractor) == torch.bfloat16)))
         stepper.key = key
         optimizer._b200_stepper = stepper
@@ -534,9 +552,12 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
         if prev is not None:
             yield prev, None
 
-    for idx, idx_next in _with_lookahead(i for i in loader.index_batches() if i.numel() > 0):
+    for (idx, n_global), nxt_pair in _with_lookahead(p for p in loader.index_batches_with_global() if p[0].numel() > 0):
         n = idx.numel()
-        if n == B:
+        idx_next = None if nxt_pair is None else nxt_pair[0]
+        if nxt_pair is not None and nxt_pair[1] != loader.batch_size:
+            idx_next = None                               # the next global batch is short: it runs eagerly, no prefetch for it
+        if n == B and n_global == loader.batch_size:
             if not (stepper.prefetch and stepper._primed):
                 stepper.load(idx.pin_memory())           # start of a sequence (or no prefetch): stage (and gather) this batch
             if stepper.graph is None and not getattr(stepper, "graph_failed", False):
@@ -558,7 +579,7 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
             outputs = model(define_inputs(images, kin, feature_extractor, exp_kwargs, device))
             loss, outputs = compute_loss(outputs, y, criterion, "window")
             optimizer.zero_grad()
-            _backward(loss, optimizer)
+            _backward(loss, optimizer, loader.dp_weight(n, n_global))
             _allreduce_grads(optimizer)
             optimizer.step()
             probs, preds, counts = criterion.last
@@ -678,7 +699,7 @@ def train_single_epoch_ES(model, feature_extractor, train_dataloader, criterion,
         C = outputs.shape[1]
         loss = crit(outputs, y, cm_classes=max(C, 6))
         optimizer.zero_grad()
-        _backward(loss, optimizer)
+        _backward(loss, optimizer, _window_batches.dp_weight)
         _allreduce_grads(optimizer)
         optimizer.step()
         cm = crit.last[2] if cm is None else cm + crit.last[2]
@@ -752,7 +773,7 @@ def train_single_epoch_Sequential(model, feature_extractor, train_dataloader, cr
         outputs = model(define_inputs(images, kin, feature_extractor, exp_kwargs, device))
         loss = crit(outputs, y, mask=mask, target_shift=-1, reduction=1, pred_shift=1, pred_mask_mode=1, cm_classes=6)
         optimizer.zero_grad()
-        _backward(loss, optimizer)
+        _backward(loss, optimizer, _window_batches.dp_weight)
         _allreduce_grads(optimizer)
         optimizer.step()
         cm = crit.last[2] if cm is None else cm + crit.last[2]
@@ -911,17 +932,104 @@ def cascade_ensemble(binary_preds, multiclass_preds):
     return ops.cascade(to(binary_preds), to(multiclass_preds)).cpu().numpy()
 
 
+def roc_auc_score(y_true, y_score) -> float:
+    """``sklearn.metrics.roc_auc_score(y_true, y_score)`` for binary labels, as the reference imports it
+    (modeling_utils.py:7) and calls it on stored per-sample probabilities (:1124, :1243), computed on the device
+    (csrc/metrics.cu: integer rank counting, ties count one half).  Raises ValueError when only one class is present,
+    like sklearn."""
+    dev = cuda_device()
+    to = lambda x: (x.detach() if torch.is_tensor(x) else torch.as_tensor(np.asarray(x, dtype=np.float32))).to(dev, torch.float32)
+    auc, stats = ops.roc_auc(to(y_score).contiguous(), to(y_true).contiguous())
+    host = stats.cpu()
+    if int(host[0]) == 0 or int(host[1]) == 0:
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")
+    return float(auc.cpu())
+
+
 def save_model(best_model: dict, model_path: str) -> None:
     """Reference modeling_utils.py:3028-3040: ``{'feature_extractor': state_dict, 'model': state_dict}``."""
     torch.save({"feature_extractor": best_model["feature_extractor"], "model": best_model["model"]}, model_path)
     print(f"Model saved to {model_path}")
 
 
-def load_model_local(model_path: str, feature_extractor, model, device=None):
-    """Counterpart of the reference's load_model_local (modeling_utils.py:2241): load a
-    ``save_model`` file (from the reference or from this package -- the keys are the same)."""
-    blob = torch.load(model_path, map_location="cpu")
+def _load_blob(model_path: str) -> dict:
+    return torch.load(model_path, map_location="cpu", weights_only=False)
+
+
+def load_model_file(model_path: str, feature_extractor, model, device=None):
+    """Load one ``save_model`` file (written by the reference or by this package -- same keys and shapes) into existing
+    modules, in place: parameters that FusedAdam re-homed into its flat buffer stay views of it."""
+    blob = _load_blob(model_path)
     if feature_extractor is not None and blob.get("feature_extractor") is not None:
         feature_extractor.load_state_dict(blob["feature_extractor"])
     model.load_state_dict(blob["model"])
     return feature_extractor, model
+
+
+def load_model_local(model_folder: str, out: str, setting: str, exp_kwargs: dict, in_features: int, window_size: int,
+                     device) -> tuple:
+    """Reference modeling_utils.py:2241-2295: build the head (and the FeatureExtractor unless the data type is
+    kinematics or ``video_dims == 2048``), load ``<model_folder>/best_model_<setting>_<out>.pt`` -> (feature_extractor, model).
+    (TransSVNet checkpoints load their TeCNo trunk, :2262-2267.)"""
+    device = torch.device(device) if device is not None else cuda_device()
+    kw = dict(exp_kwargs, model_name="TeCNo") if exp_kwargs["model_name"] == "TransSVNet" else exp_kwargs
+    model = instantiate_model(kw, in_features, window_size).to(device)
+    precision = exp_kwargs.get("precision", "fp32")
+    _configure_precision(model, exp_kwargs, precision)
+    feature_extractor = None
+    if exp_kwargs["data_type"] != "kinematics" and exp_kwargs["video_dims"] != 2048:
+        feature_extractor = FeatureExtractor(input_dim=2048, output_dim=exp_kwargs["video_dims"], hidden_dims=[512, 256],
+                                             precision=precision).to(device)
+    best_model = _load_blob(os.path.join(model_folder, f"best_model_{setting}_{out}.pt"))
+    model.load_state_dict(best_model["model"])
+    if feature_extractor is not None:
+        feature_extractor.load_state_dict(best_model["feature_extractor"])
+    return feature_extractor, model
+
+
+def load_binary_model_local(model_folder: str, model_name: str, outs: list, exp_kwargs: dict, device):
+    """Reference modeling_utils.py:2298-2329: the frozen binary models of the cascade, one per fold -- always
+    ``LSTM(58, 10, hidden 128, 3 layers, 1 class)`` + FeatureExtractor -- read from
+    ``models/<data_type>/<frequency>Hz/<model_name>/best_model_LOSO_<out>.pt`` (the reference overwrites its
+    ``model_folder`` argument with that relative path, :2304; kept) -> (model_dict, fe_dict)."""
+    device = torch.device(device) if device is not None else cuda_device()
+    model_folder = f'models/{exp_kwargs["data_type"]}/{exp_kwargs["frequency"]}Hz/{model_name}/'
+    precision = exp_kwargs.get("precision", "fp32")
+    model_dict, fe_dict = {}, {}
+    for out in outs:
+        model = LSTM(in_features=58, window_size=10, hidden_size=128, num_layers=3, n_classes=1).to(device)
+        _configure_precision(model, exp_kwargs, precision)
+        feature_extractor = FeatureExtractor(input_dim=2048, output_dim=exp_kwargs["video_dims"], hidden_dims=[512, 256],
+                                             precision=precision).to(device)
+        best_model = _load_blob(os.path.join(model_folder, f"best_model_LOSO_{out}.pt"))
+        feature_extractor.load_state_dict(best_model["feature_extractor"])
+        model.load_state_dict(best_model["model"])
+        model_dict[out], fe_dict[out] = model, feature_extractor
+    print(f"Loaded binary models from {model_folder}.")
+    return model_dict, fe_dict
+
+
+def create_binary_mask(preds_binary: dict, subjects: dict, out: str, fold_data_path: str, exp_kwargs: dict = None):
+    """Reference modeling_utils.py:2920-2976: the binary model's predictions of fold ``out`` as the cascade's mask, with
+    the Needle-Drop positions recorded in the fold's ``mask_position_ND_<subject>.pth`` files removed (when
+    ``delete_ND``) so that the mask lines up with the error-specific predictions -> (binary_mask, binary_subjects).
+    Host-side index bookkeeping over a fold's prediction list (10^3..10^5 entries, once per fold)."""
+    binary_mask = np.array(preds_binary[out])
+    binary_subjects = np.array(subjects[out])
+    nd_files = []
+    if exp_kwargs["delete_ND"]:
+        for file in os.listdir(fold_data_path):
+            if file.startswith("mask_position_ND_") and file.endswith(".pth"):
+                subject = file.split(".")[0].replace("mask_position_ND_", "")
+                nd_files.append((subject, torch.load(os.path.join(fold_data_path, file))))
+    print(binary_mask.shape)
+    for subject, mask_position_ND in nd_files:
+        rows = np.where(binary_subjects == subject)[0]
+        if len(rows) == 0:
+            continue
+        print(f"Found mask_position_ND for subject {subject} in {out} set.")
+        expanded = np.zeros_like(binary_mask, dtype=bool)
+        expanded[rows] = np.asarray(mask_position_ND, dtype=bool)
+        binary_mask, binary_subjects = binary_mask[~expanded], binary_subjects[~expanded]
+    print(binary_mask.shape)
+    return binary_mask, binary_subjects

@@ -6,8 +6,9 @@ seed-42 initialisation order as the reference (models.py:6-220), so checkpoints 
 * ``FeatureExtractor`` -- ~98 % (CNN head) / ~75 % (LSTM head) of the model FLOPs -- runs on the
   hand-written kernels of libb200med.so: fp32 SIMT GEMMs in ``precision="fp32"`` (1e-5 parity mode)
   or bf16 tcgen05/TMEM GEMMs in ``precision="bf16"`` (2e-2 throughput mode), forward and backward.
-* ``CNN`` / ``LSTM`` heads (0.36 / 11 MFLOP per window) keep stock torch layers on the GPU in this
-  round; their fused sm_100a kernels are SURVEY section 8f rows 2-3 ("next").
+* ``CNN`` / ``LSTM`` heads run on the kernels of csrc/head.cu, csrc/gemm_f32.cu, csrc/lstm.cu and
+  csrc/lstm_rec.cu through ``heads.py`` / ``lstm_stack.py``; their ``nn.Module`` members only hold the parameters
+  (same ``state_dict`` keys as the reference).  There is no torch-layer path: a CPU tensor raises.
 """
 from __future__ import annotations
 
@@ -145,10 +146,19 @@ class CNN(nn.Module):
             nn.Linear(256, 32), nn.ReLU(), nn.BatchNorm1d(32),
             nn.Linear(32, 16), nn.ReLU(), nn.BatchNorm1d(16),
             nn.Linear(16, n_classes))
+        self.register_buffer("_drop_seed", torch.zeros(1, dtype=torch.int32), persistent=False)  # not in state_dict
         self.initialize_weights()
 
     def forward(self, x):
-        return self.linear_layers(self.convolutional_layers(x))
+        """x [B, F, W] -> [B, n_classes] on the fused head kernels (heads.py): convolutions as GEMMs over overlapping
+        time-major rows, pool + dropout, deterministic BatchNorm, Linear / ReLU / BatchNorm tail."""
+        if not x.is_cuda:
+            raise RuntimeError("b200med CNN head runs on CUDA tensors only (no CPU fallback)")
+        from ..heads import conv_stack, mlp_tail
+        if self.training:
+            self._drop_seed.add_(1)
+        feats = conv_stack(x, self.convolutional_layers, self.training, self._drop_seed)
+        return mlp_tail(feats, self.linear_layers, relu_in=False, training=self.training)
 
     def initialize_weights(self):
         # reference quirk kept for weight parity: only the LAST module's bias becomes 0.1 (models.py:130-131)
@@ -165,7 +175,11 @@ class CNN(nn.Module):
 
 class LSTM(nn.Module):
     """Window LSTM head (reference models.py:135-220): [B,F,W] -> transpose -> nn.LSTM(F, H, layers,
-    dropout .2) -> ReLU -> last step -> Linear 256/64/C with ReLU + BN."""
+    dropout .2) -> ReLU -> last step -> Linear 256/64/C with ReLU + BN.
+
+    ``precision`` (set by ``define_model_objects`` from ``exp_kwargs['precision']``): "fp32" = exact-math fp32 recurrence
+    kernels (1e-5 parity mode), "bf16" = persistent tcgen05 recurrence (2e-2 throughput mode).  The ``nn.LSTM`` member only
+    holds the weights; it is never called."""
 
     def __init__(self, in_features: int = 58, window_size: int = 30, num_layers: int = 3, hidden_size: int = 128,
                  n_classes: int = 1):
@@ -175,10 +189,7 @@ class LSTM(nn.Module):
         self.layer_dim, self.hidden_size, self.n_classes = num_layers, hidden_size, n_classes
         self.lstm = nn.LSTM(input_size=in_features, hidden_size=hidden_size, num_layers=num_layers, batch_first=True,
                             dropout=0.2)
-        # cuDNN's LSTM cell uses fast-math sigmoid/tanh (~20x the round-off of the CPU reference, measured);
-        # the fp32 parity mode therefore runs the recurrence on the exact-math ATen kernels.
-        self.use_cudnn = True
-        self.impl = "torch"            # "b200": recurrence on the b200med kernels (set by define_model_objects in bf16 mode)
+        self.precision = "fp32"
         self.register_buffer("_drop_seed", torch.zeros(1, dtype=torch.int32), persistent=False)  # not in state_dict
         self.linear_layers = nn.Sequential(
             nn.Flatten(), nn.Linear(hidden_size, 256), nn.ReLU(), nn.BatchNorm1d(256),
@@ -186,17 +197,15 @@ class LSTM(nn.Module):
         self.initialize_weights()
 
     def forward(self, l):
-        if self.impl in ("b200", "b200_per_step") and l.is_cuda:
-            # throughput mode: persistent tcgen05 recurrence kernels (lstm_stack.py); only h_{W-1} is needed
-            from ..lstm_stack import lstm_last_hidden
-            if self.training and self.lstm.dropout > 0:
-                self._drop_seed.add_(1)
-            h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed,
-                                 impl="per_step" if self.impl == "b200_per_step" else "auto")
-            return self.linear_layers(F.relu(h))
-        with torch.backends.cudnn.flags(enabled=self.use_cudnn):
-            out, _ = self.lstm(l.transpose(1, 2).contiguous())
-        return self.linear_layers(F.relu(out)[:, -1, :])
+        if not l.is_cuda:
+            raise RuntimeError("b200med LSTM head runs on CUDA tensors only (no CPU fallback)")
+        from ..heads import mlp_tail
+        from ..lstm_stack import lstm_last_hidden
+        if self.training and self.lstm.dropout > 0:
+            self._drop_seed.add_(1)
+        # only h_{W-1} of the top layer is needed: the reference takes F.relu(out)[:, -1, :] (models.py:205-206)
+        h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed, precision=self.precision)
+        return mlp_tail(h, self.linear_layers, relu_in=True, training=self.training)
 
     def initialize_weights(self):
         for m in self.modules():

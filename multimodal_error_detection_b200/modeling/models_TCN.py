@@ -10,8 +10,8 @@ The modules below only HOLD the parameters (so ``state_dict`` / ``load_state_dic
 tensors); the arithmetic of a stage runs on the fused sm_100a kernels of ``csrc/tcn.cu`` through
 :class:`multimodal_error_detection_b200.tcn.TcnStageFunction` -- one launch per DilatedResidualLayer, time-major
 activations, the inter-stage softmax folded into the consuming stage.  The kernels are specialised for the reference's
-configuration (64 feature maps, kernel size 3, batch of one video, <= 8 classes); any other shape still runs, on the
-stock torch convolution layers (``impl == "torch"``), and says so in ``MultiStageModel.impl``.
+configuration (64 feature maps, kernel size 3, one video per forward -- or a ragged batch through ``forward_ragged`` --,
+<= 8 classes); any other shape raises ``ValueError``: there is no second implementation to fall back to.
 """
 from __future__ import annotations
 
@@ -19,7 +19,6 @@ import copy
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import tcn
 
@@ -34,11 +33,8 @@ class DilatedResidualLayer(nn.Module):
         self.dropout = nn.Dropout()
 
     def forward(self, x):
-        """Stock-layer form (only used for shapes the fused kernels are not specialised for)."""
-        y = F.relu(self.conv_dilated(x))
-        if self.causal_conv:
-            y = y[:, :, :-(self.dilation * 2)]   # drop the right overhang -> causal
-        return x + self.dropout(self.conv_1x1(y))
+        raise RuntimeError("b200med: DilatedResidualLayer only holds parameters; a stage runs as a whole on the fused kernels "
+                           "(SingleStageModel / MultiStageModel.forward)")
 
 
 class SingleStageModel(nn.Module):
@@ -87,13 +83,16 @@ class SingleStageModel(nn.Module):
         xin = x[0] if softmax_in else x[0].t()      # [C, T] logits, or [T, F] rows (a free view of the [1, T, F] batch)
         return tcn.TcnStageFunction.apply(xin, cfg, *params).unsqueeze(0)
 
-    def forward(self, x, fused: bool = True):
-        if fused and self.fused_ok(x):
-            return self.run_fused(x)
-        out = self.conv_1x1(x)
-        for layer in self.layers:
-            out = layer(out)
-        return self.conv_out_classes(out)
+    def check_supported(self, x: torch.Tensor) -> None:
+        tcn.require_cuda(x)
+        if not self.fused_ok(x):
+            raise ValueError("b200med TeCNo kernels cover the reference's configuration -- 64 feature maps, kernel size 3, dilation "
+                             f"2^i, <= 8 classes, fp32 input [1, F, T] -- got maps={self.num_f_maps}, classes={self.num_classes}, "
+                             f"input {tuple(x.shape)} {x.dtype}")
+
+    def forward(self, x):
+        self.check_supported(x)
+        return self.run_fused(x)
 
 
 class MultiStageModel(nn.Module):
@@ -107,8 +106,7 @@ class MultiStageModel(nn.Module):
                                                                     causal_conv=mstcn_causal_conv))
                                      for _ in range(mstcn_stages - 1)])
         self.smoothing = False
-        self.impl = "b200"       # what the last forward ran on: "b200" (csrc/tcn.cu) or "torch" (unsupported shape)
-        self.use_fused = True    # scripts/bench_frame.py switches it off to time the stock torch layers as the A/B baseline
+        self.impl = "b200"       # every forward runs on csrc/tcn.cu (kept as an attribute for callers that report it)
         # CUDA-graph training (engine.FrameTrainStep): a host seed fixed at capture + an int64 DEVICE counter advanced inside
         # the captured step, so that every replay draws a fresh dropout mask
         self.graph_seed = None   # (host seed, device counter tensor) or None
@@ -122,31 +120,20 @@ class MultiStageModel(nn.Module):
         return int(torch.randint(0, 2 ** 62, (1,)).item())     # host generator: reproducible under torch.manual_seed
 
     def forward(self, x, geom=(None, None)):
-        if self.use_fused and self.stage1.fused_ok(x) and all(s.fused_supported() for s in self.stages):
-            self.impl = "b200"
-            seed_dev = None
-            if self.training and self.graph_seed is not None:
-                seed, seed_dev = self.graph_seed
-                seed_dev.add_(1)
-            else:
-                seed = self._seed()
-            out = self.stage1.run_fused(x, False, seed, 0, geom, seed_dev, self.precision)
-            outs = [out]
-            for i, s in enumerate(self.stages):
-                out = s.run_fused(out, True, seed, (i + 1) * self.num_layers, geom, seed_dev, self.precision)
-                outs.append(out)
-            return torch.stack(outs, dim=0)
-        if geom[0] is not None:
-            raise ValueError("ragged batches need the fused TeCNo kernels (64 feature maps, kernel size 3, <= 8 classes)")
-        if self.use_fused and self.impl != "torch":
-            import warnings
-            warnings.warn("b200med: this MultiStageModel shape (feature maps != 64, kernel size != 3, > 8 classes or batch > 1) is not "
-                          "covered by the fused TeCNo kernels and runs on stock torch layers", RuntimeWarning, stacklevel=2)
-        self.impl = "torch"
-        out = self.stage1(x, fused=False)
-        outs = [out]
+        self.stage1.check_supported(x)
         for s in self.stages:
-            out = s(F.softmax(out, dim=1), fused=False)
+            if not s.fused_supported():
+                raise ValueError("b200med TeCNo kernels cover 64 feature maps, kernel size 3, dilation 2^i and <= 8 classes")
+        seed_dev = None
+        if self.training and self.graph_seed is not None:
+            seed, seed_dev = self.graph_seed
+            seed_dev.add_(1)
+        else:
+            seed = self._seed()
+        out = self.stage1.run_fused(x, False, seed, 0, geom, seed_dev, self.precision)
+        outs = [out]
+        for i, s in enumerate(self.stages):
+            out = s.run_fused(out, True, seed, (i + 1) * self.num_layers, geom, seed_dev, self.precision)
             outs.append(out)
         return torch.stack(outs, dim=0)
 

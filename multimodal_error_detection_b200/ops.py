@@ -143,8 +143,13 @@ def gather_norm(streams: Sequence[GatherStream], starts: torch.Tensor, W: int, v
             keep += [mean, std]
         arr[i] = StreamDesc(table.data_ptr(), 0 if mean is None else mean.data_ptr(), 0 if std is None else std.data_ptr(),
                             out.data_ptr(), D, _dt(table), _dt(out), out2.shape[1], s.out_col, stat_rows,
-                            int(bool(s.exact_div)), 0)
+                            int(bool(s.exact_div)), min(table.numel() // D, 2 ** 31 - 1))
     call("b200med_gather_norm", arr, len(streams), _ptr(starts), B, W, variant, _stream())
+
+
+def gather_last_variant() -> int:
+    """Device path of this thread's last gather_norm call (1 = LDG kernel, 2.. = TMA staging ring shapes)."""
+    return int(_lib.load().b200med_gather_last_variant())
 
 
 def expand_stat(stat, D: int, W: int, device) -> torch.Tensor:
@@ -198,6 +203,113 @@ def linear_bwd_weight_f32(dy, x, want_bias=True):
     ws = workspace(_lib.load().b200med_linear_bwd_weight_ws_bytes(M, N, K), dy.device, "wgrad_f32")
     call("b200med_linear_bwd_weight_f32", _ptr(dy), _ptr(x), _ptr(dw), _ptr(db), M, N, K, 0, _ptr(ws), _stream())
     return dw, db
+
+
+GEMM_RELU, GEMM_ACCUM, GEMM_RELU_A, GEMM_RELU_B, GEMM_SPLIT = 1, 2, 4, 8, 16
+
+
+def gemm_f32(A, B, C_out, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc=None, bias=None, mask=None, ld_mask=0, flags=0):
+    """General strided fp32 product (b200med_gemm_f32): C[i,j] = epi(sum_r A[i*a_rs + r*a_cs] * B[j*b_rs + r*b_cs]).
+    A / B may be tensors or (tensor, element offset) pairs; strides are in elements."""
+    def base(t):
+        if isinstance(t, tuple):
+            return C.c_void_p(_need(t[0], torch.float32, "operand").data_ptr() + 4 * int(t[1]))
+        return _ptr(_need(t, torch.float32, "operand"))
+    Cn = _need(C_out, torch.float32, "C")
+    ws = None
+    if flags & GEMM_SPLIT:
+        ws = workspace(_lib.load().b200med_gemm_f32_ws_bytes(I, J, R), Cn.device, "gemm_f32_split")
+    call("b200med_gemm_f32", base(A), base(B), _ptr(Cn), I, J, R, a_rs, a_cs, b_rs, b_cs, J if ldc is None else ldc,
+         _ptr(bias), _ptr(mask), ld_mask, flags, _ptr(ws), _stream())
+    return Cn
+
+
+def linear_f32(x, w, b=None, flags=0, out=None):
+    """y [M, N] = x [M, K] w[N, K]^T (+ b) with B200MED_GEMM_* flags (RELU, ACCUM into `out`, RELU_A on x)."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device) if out is None else out
+    return gemm_f32(x, w, y, M, N, K, K, 1, K, 1, N, bias=b, flags=flags)
+
+
+def linear_dgrad_f32(dy, w, mask=None, out=None):
+    """dx [M, K] = dy [M, N] w [N, K], zeroed where mask [M, K] <= 0."""
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = torch.empty(M, K, dtype=torch.float32, device=dy.device) if out is None else out
+    return gemm_f32(dy, w, dx, M, K, N, N, 1, 1, K, K, mask=mask, ld_mask=K)
+
+
+def linear_wgrad_f32(dy, x, relu_x=False):
+    """dW [N, K] = dy [M, N]^T x [M, K] (x clamped at zero when relu_x), deterministic split reduction."""
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+    return gemm_f32(dy, x, dw, N, K, M, 1, N, 1, K, K, flags=GEMM_SPLIT | (GEMM_RELU_B if relu_x else 0))
+
+
+def bn_fwd(x, gamma, beta, eps, momentum, training, running_mean=None, running_var=None, num_batches=None):
+    """nn.BatchNorm1d over the rows of x [M, C] -> (y, save_mean, save_rstd) (the last two None in inference)."""
+    x = _need(x, torch.float32, "x")
+    M, Cn = x.shape
+    y = torch.empty_like(x)
+    sm = sr = ws = None
+    if training:
+        sm = torch.empty(Cn, dtype=torch.float32, device=x.device)
+        sr = torch.empty(Cn, dtype=torch.float32, device=x.device)
+        ws = workspace(_lib.load().b200med_bn_ws_bytes(M, Cn), x.device, "bn")
+    call("b200med_bn_fwd", _ptr(x), M, Cn, _ptr(gamma), _ptr(beta), float(eps), float(momentum), int(bool(training)),
+         _ptr(running_mean), _ptr(running_var), _ptr(num_batches), _ptr(y), _ptr(sm), _ptr(sr), _ptr(ws), _stream())
+    return y, sm, sr
+
+
+def bn_bwd(dy, x, gamma, save_mean, save_rstd, relu_mask=False, want_affine=True):
+    dy = _need(dy, torch.float32, "dy"); x = _need(x, torch.float32, "x")
+    M, Cn = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.empty(Cn, dtype=torch.float32, device=x.device) if want_affine else None
+    db = torch.empty(Cn, dtype=torch.float32, device=x.device) if want_affine else None
+    ws = workspace(_lib.load().b200med_bn_ws_bytes(M, Cn), x.device, "bn")
+    call("b200med_bn_bwd", _ptr(dy), _ptr(x), M, Cn, _ptr(gamma), _ptr(save_mean), _ptr(save_rstd), int(bool(relu_mask)), _ptr(dx),
+         _ptr(dg), _ptr(db), _ptr(ws), _stream())
+    return dx, dg, db
+
+
+def pool_drop_fwd(z, B, L, Lc, Cn, drop_p=0.0, seed_dev=None, drop_base=0):
+    p = torch.empty(B * (Lc // 2), Cn, dtype=torch.float32, device=z.device)
+    call("b200med_pool_drop_fwd", _ptr(_need(z, torch.float32, "z")), _ptr(p), B, L, Lc, Cn, float(drop_p),
+         _ptr(seed_dev), C.c_uint64(int(drop_base)), _stream())
+    return p
+
+
+def pool_drop_bwd(dp, z, dz, B, L, Lc, Cn, drop_p=0.0, seed_dev=None, drop_base=0):
+    call("b200med_pool_drop_bwd", _ptr(_need(dp, torch.float32, "dp")), _ptr(z), _ptr(dz), B, L, Lc, Cn, float(drop_p),
+         _ptr(seed_dev), C.c_uint64(int(drop_base)), _stream())
+    return dz
+
+
+def conv_pack(w, want_fwd=True, want_bwd=True):
+    w = _need(w, torch.float32, "w")
+    Cout, Cin, k = w.shape
+    if k != 3:
+        raise ValueError("the native convolution is built for kernel_size = 3")
+    fwd = torch.empty(Cout, 3 * Cin, dtype=torch.float32, device=w.device) if want_fwd else None
+    bwd = torch.empty(Cin, 3 * Cout, dtype=torch.float32, device=w.device) if want_bwd else None
+    call("b200med_conv_pack", _ptr(w), _ptr(fwd), _ptr(bwd), Cout, Cin, _stream())
+    return fwd, bwd
+
+
+def conv_unpack_grad(dfwd, Cout, Cin):
+    dw = torch.empty(Cout, Cin, 3, dtype=torch.float32, device=dfwd.device)
+    call("b200med_conv_unpack_grad", _ptr(_need(dfwd, torch.float32, "dfwd")), _ptr(dw), Cout, Cin, _stream())
+    return dw
+
+
+def transpose_last2(x, B, R, Cn):
+    """[B, R, C] -> [B, C, R]"""
+    y = torch.empty(B, Cn, R, dtype=torch.float32, device=x.device)
+    call("b200med_transpose_last2", _ptr(_need(x, torch.float32, "x")), _ptr(y), B, R, Cn, _stream())
+    return y
 
 
 # ------------------------------------------------------------------------------------------- K2 bf16 (tcgen05)
@@ -345,6 +457,19 @@ def confusion(target, pred, n_classes: int, cm=None, accumulate=False):
         cm = torch.zeros(n_classes, n_classes, dtype=torch.int64, device=t.device)
     call("b200med_confusion", _ptr(t), _ptr(p), t.numel(), n_classes, _ptr(cm), int(accumulate), _stream())
     return cm
+
+
+def roc_auc(scores, labels):
+    """Area under the ROC curve on the device -> (auc f64[1], stats i64[4] = n_pos, n_neg, 2*less+equal, 0)."""
+    sc = _need(scores.reshape(-1), torch.float32, "scores"); lb = _need(labels.reshape(-1), torch.float32, "labels")
+    if sc.numel() != lb.numel():
+        raise ValueError("scores and labels differ in length")
+    n, dev = sc.numel(), sc.device
+    auc = torch.empty(1, dtype=torch.float64, device=dev)
+    stats = torch.empty(4, dtype=torch.int64, device=dev)
+    ws = workspace(_lib.load().b200med_roc_auc_ws_bytes(n), dev, "roc_auc")
+    call("b200med_roc_auc", _ptr(sc), _ptr(lb), n, _ptr(auc), _ptr(stats), _ptr(ws), _stream())
+    return auc, stats
 
 
 # ------------------------------------------------------------------------------------------- TeCNo frame head

@@ -13,7 +13,11 @@ one all-reduce per chunk:
 
 Like ``torch.optim.Adam``, a parameter that has never received a gradient is skipped entirely (no
 decay, no moments): the reference registers an unused FeatureExtractor when ``video_dims == 2048``
-(SURVEY Appendix A-11).  The class subclasses ``torch.optim.Optimizer`` so the stock
+(SURVEY Appendix A-11).  Two documented differences from ``torch.optim.Adam``: there is ONE step counter / bias correction
+for all parameters (torch keeps one per parameter; identical whenever every trained parameter receives a gradient from the
+first step on, which holds for every reference configuration), and a parameter that has been active once keeps decaying
+with a zero gradient in a step where its ``.grad`` is None (torch would skip it; the reference's loops never produce that).
+``state_dict()`` / ``load_state_dict()`` carry the flat moments and the step scalars.  The class subclasses ``torch.optim.Optimizer`` so the stock
 ``CosineAnnealingLR`` of the reference (modeling_utils.py:257-258) drives ``param_groups[0]['lr']``.
 """
 from __future__ import annotations
@@ -188,3 +192,47 @@ class FusedAdam(torch.optim.Optimizer):
             for b, e in c.runs:
                 ops.adam_step(c.param[b:e], c.grad[b:e], c.exp_avg[b:e], c.exp_avg_sq[b:e], self.state_dev, b1, b2,
                               g["eps"], g["weight_decay"], self.grad_scale)
+
+    # ------------------------------------------------------------------------------------ checkpointing
+    def state_dict(self):
+        """torch's param_groups plus the flat Adam state: per chunk exp_avg / exp_avg_sq, the device step scalars
+        {step, lr, bc1, sqrt(bc2)} and which parameters are active (by position)."""
+        self.prepare()
+        sd = super().state_dict()
+        order = [p for g in self.param_groups for p in g["params"]]
+        sd["b200med"] = {
+            "chunks": [{"exp_avg": c.exp_avg.detach().cpu().clone(), "exp_avg_sq": c.exp_avg_sq.detach().cpu().clone()} for c in self.chunks],
+            "state_dev": self.state_dev.detach().cpu().clone(),
+            "active": None if self._active is None else [bool(self._active.get(id(p), False)) for p in order],
+            "grad_scale": self.grad_scale,
+        }
+        return sd
+
+    def load_state_dict(self, state_dict):
+        extra = state_dict.get("b200med")
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "b200med"})
+        if extra is None:
+            return
+        self.prepare()
+        if len(extra["chunks"]) != len(self.chunks):
+            raise ValueError("FusedAdam.load_state_dict: the checkpoint has a different chunk layout")
+        with torch.no_grad():
+            for c, rec in zip(self.chunks, extra["chunks"]):
+                c.exp_avg.copy_(rec["exp_avg"]); c.exp_avg_sq.copy_(rec["exp_avg_sq"])
+            self.state_dev.copy_(extra["state_dev"])
+        self._lr_on_device = None
+        self.grad_scale = extra.get("grad_scale", 1.0)
+        if extra["active"] is not None:
+            order = [p for g in self.param_groups for p in g["params"]]
+            self._active = {id(p): a for p, a in zip(order, extra["active"])}
+            for c in self.chunks:          # rebuild the active ranges
+                runs = []
+                for p, o, n in sorted(c.members, key=lambda m: m[1]):
+                    if not self._active.get(id(p), False):
+                        continue
+                    b, e = o // 4 * 4, (o + n + 3) // 4 * 4
+                    if runs and b <= runs[-1][1]:
+                        runs[-1][1] = max(runs[-1][1], e)
+                    else:
+                        runs.append([b, e])
+                c.runs = [(b, min(e, c.param.numel())) for b, e in runs]

@@ -150,6 +150,19 @@ def write_fold(fold: Fold, path: str) -> str:
     return path
 
 
+def write_fold_video_schema(fold: Fold, path: str, video_path: str) -> tuple:
+    """The reference's SECOND on-disk schema (dataset_utils.py:73-96, used with ``video_data_path``): image features
+    live in ``<video_path>/<trial>.pkl`` as a numpy ``'feature'`` array [T, 2048]; kinematics / labels stay in the fold's
+    own ``<trial>.pkl`` (whose image_feats are then ignored).  Returns (fold path, video path)."""
+    write_fold(fold, path)
+    os.makedirs(video_path, exist_ok=True)
+    for tr in fold.train + fold.test:
+        # a DIFFERENT image stream than the fold's own pickle, so that a loader reading the wrong file is caught
+        with open(os.path.join(video_path, f"{tr.name}.pkl"), "wb") as f:
+            pickle.dump({"feature": (tr.image[:, ::-1] * 0.5 + 0.25).astype(np.float32).copy()}, f)
+    return path, video_path
+
+
 def flat_tables(trials):
     """Concatenate trials into the flat per-frame arrays ``load_data`` returns, plus the
     per-frame subject names and the contiguous subject offsets."""

@@ -29,6 +29,29 @@ def timed(fn, steps, warmup=5):
     return a.elapsed_time(b) / steps
 
 
+def torch_layers_forward(model, x):
+    """The A/B baseline of this script: the SAME parameters run through stock torch CUDA convolutions (what the reference's
+    nn.Module forward does, models_TCN.py:76-137).  It lives here, not in the package: the product has one implementation."""
+    import torch.nn.functional as F
+
+    def stage(s, h):
+        h = F.conv1d(h, s.conv_1x1.weight, s.conv_1x1.bias)
+        for l in s.layers:
+            d = l.dilation
+            y = F.relu(F.conv1d(h, l.conv_dilated.weight, l.conv_dilated.bias, padding=2 * d if l.causal_conv else d, dilation=d))
+            if l.causal_conv:
+                y = y[:, :, :-(2 * d)]
+            h = h + F.dropout(F.conv1d(y, l.conv_1x1.weight, l.conv_1x1.bias), 0.5, model.training)
+        return F.conv1d(h, s.conv_out_classes.weight, s.conv_out_classes.bias)
+
+    out = stage(model.stage1, x)
+    outs = [out]
+    for s in model.stages:
+        out = stage(s, F.softmax(out, dim=1))
+        outs.append(out)
+    return torch.stack(outs, dim=0)
+
+
 def measure(frames: int = 600, videos: int = 64, steps: int = 30) -> dict:
     args = argparse.Namespace(frames=frames, videos=videos, steps=steps)
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -44,25 +67,27 @@ def measure(frames: int = 600, videos: int = 64, steps: int = 30) -> dict:
     y = (torch.rand(1, T, generator=g) > 0.5).float().to(dev)
     res = {"frames_per_video": T, "config": "TeCNo 2 stages x 8 layers x 64 maps, F=58 (FE 2048->32 + 26 kinematics), fp32"}
 
+    fwd = {"fn": model}
+
     def train_step():
         inputs = mu.define_inputs(images, kin, fe, kw, dev)
-        out = model(inputs)
+        out = fwd["fn"](inputs)
         loss, _ = mu.compute_loss(out, y, crit, "frame")
         opt.zero_grad()
         loss.backward()
         opt.step()
 
     def head_only():
-        out = model(feats)
+        out = fwd["fn"](feats)
         (out.sum()).backward()
 
     def infer():
         with torch.no_grad():
-            model(mu.define_inputs(images, kin, fe, kw, dev))
+            fwd["fn"](mu.define_inputs(images, kin, fe, kw, dev))
 
     feats = torch.randn(1, T, 58, generator=g).to(dev).permute(0, 2, 1)
     for name, fused in (("b200", True), ("torch_layers", False)):
-        model.use_fused = fused
+        fwd["fn"] = model if fused else (lambda x: torch_layers_forward(model, x))
         model.train(); fe.train()
         n0 = _lib.launch_count()
         ms = timed(train_step, args.steps)
@@ -72,10 +97,9 @@ def measure(frames: int = 600, videos: int = 64, steps: int = 30) -> dict:
         ms_inf = timed(infer, args.steps)
         res[name] = {"train_ms_per_video": ms, "train_frames_per_s": T / ms * 1e3, "head_fwd_bwd_ms": ms_head,
                      "infer_ms_per_video": ms_inf, "infer_frames_per_s": T / ms_inf * 1e3, "own_launches_per_step": launches,
-                     "impl": model.impl}
+                     "impl": "b200" if fused else "torch layers (script-local baseline)"}
     # the same train step replayed from a CUDA graph (engine.FrameTrainStep; what train_single_epoch does with cuda_graph=True)
     from multimodal_error_detection_b200.engine import FrameTrainStep
-    model.use_fused = True
     model.train(); fe.train()
     e7 = torch.zeros(1, T, 7, dtype=torch.int32, device=dev)
     e7[0, :, 6] = y[0].to(torch.int32)
@@ -83,7 +107,6 @@ def measure(frames: int = 600, videos: int = 64, steps: int = 30) -> dict:
     ms = timed(step.run, args.steps)
     res["b200_graph"] = {"train_ms_per_video": ms, "train_frames_per_s": T / ms * 1e3, "own_launches_per_step": step.launches_per_step}
     # ragged-batched inference of the head: V videos in one pass vs one pass per video
-    model.use_fused = True
     model.eval()
     lengths = torch.randint(300, 901, (args.videos,), generator=g).tolist()
     frames = torch.randn(sum(lengths), 58, generator=g).to(dev)

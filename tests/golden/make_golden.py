@@ -359,7 +359,166 @@ def gen_tecno_extra():
     print("tecno_extra:", len(out))
 
 
+# ---------------------------------------------------------------- fixed trained weights -> validation outputs ("3 decimals")
+def _freeze_fe_trunk(fe):
+    """FE layers 0 and 1 keep their seed-42 initialisation (bit-reproducible from the seed, checked by digest), so the
+    fixture carries only the tensors that training changed."""
+    for name, p in fe.named_parameters():
+        if not name.startswith("linear.output"):
+            p.requires_grad_(False)
+
+
+def _trained_tensors(fe, model):
+    out = {f"fe/{k}": v.detach().numpy().copy() for k, v in fe.state_dict().items() if k.startswith("linear.output")}
+    out.update({f"model/{k}": v.detach().numpy().copy() for k, v in model.state_dict().items()})
+    return out
+
+
+def gen_fixed_weights():
+    """The reference trains (dropout ON, a few epochs), then its validate_single_epoch[_ES|_Sequential] runs on those
+    weights: per-sample predictions / probabilities, pooled scores and sklearn's roc_auc_score are the golden."""
+    from sklearn.metrics import roc_auc_score
+    mu, du = ref.modeling_utils, ref.dataset_utils
+    fold = synthetic.make_fold(**cases.FIXED_FOLD_ARGS)
+    dev = torch.device("cpu")
+    arrays, meta = {}, {}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = synthetic.write_fold(fold, os.path.join(tmp, "fold")) + "/"
+        trained = {}
+        for name, (kw, val_cfgs, n_ep) in cases.FIXED_CASES.items():
+            kw = dict(kw, n_epochs=n_ep)
+            Wt, St = cases.FIXED_TRAIN_WS[name]
+            with quiet:
+                tr, te = du.retrieve_dataloaders_window(path, kw, window_size=Wt, stride=St)
+                counts = tr.dataset.binary_error_distribution if kw["error_type"] == "global" else tr.dataset.binary_error_distribution
+                fe, model, crit, opt, sched = mu.define_model_objects(kw, cases.IN_FEATURES, dev, counts, Wt)
+            rec = {"fe_init_sd": state_digest(fe.state_dict()), "model_init_sd": state_digest(model.state_dict()),
+                   "train_W": Wt, "train_S": St, "epochs": n_ep}
+            _freeze_fe_trunk(fe)
+            saved_ce = torch.nn.CrossEntropyLoss
+            if name == "lstm_es":
+                crit = _LongTargetCE()
+            if name == "lstm_seq":
+                torch.nn.CrossEntropyLoss = _LongTargetCE
+            try:
+                for ep in range(n_ep):
+                    with quiet, contextlib.redirect_stderr(io.StringIO()):
+                        if name == "lstm_es":
+                            mu.train_single_epoch_ES(model, fe, tr, crit, opt, sched, dev, kw)
+                        elif name == "lstm_seq":
+                            mu.train_single_epoch_Sequential(model, fe, tr, None, opt, dev, sched, kw)
+                        else:
+                            mu.train_single_epoch(model, fe, tr, crit, opt, sched, dev, kw)
+                for k, v in _trained_tensors(fe, model).items():
+                    arrays[f"{name}/{k}"] = v
+                rec["fe_trained_sd"] = state_digest(fe.state_dict())
+                rec["model_trained_sd"] = state_digest(model.state_dict())
+                trained[name] = (fe, model, crit)
+                rec["val"] = {}
+                for (W, S) in val_cfgs:
+                    tag = f"w{W}_s{S}"
+                    with quiet, contextlib.redirect_stderr(io.StringIO()):
+                        _, te = du.retrieve_dataloaders_window(path, kw, window_size=W, stride=S)
+                        if name == "lstm_es":
+                            v = mu.validate_single_epoch_ES(model, fe, te, crit, dev, kw)
+                        elif name == "lstm_seq":
+                            bfe, bmodel, _ = trained["lstm_global"]
+                            v = mu.validate_single_epoch_Sequential(model, fe, bmodel, bfe, te, dev, kw)
+                        else:
+                            v = mu.validate_single_epoch(model, fe, te, crit, dev, kw)
+                    if name == "lstm_es":
+                        r = {"scores": [float(x) for x in v[:7]], "cm_binary": v[7].tolist(), "cm_macro": v[8].tolist(),
+                             "probs": [float(x) for x in v[10]], "preds": [int(x) for x in v[11]], "labels": [int(x) for x in v[12]],
+                             "labels_binary": [int(x) for x in v[13]], "preds_binary": [int(x) for x in v[14]]}
+                    elif name == "lstm_seq":
+                        r = {"scores": [float(x) for x in v[:9]], "cm_all": v[9].tolist(), "cm_specific": v[10].tolist(),
+                             "preds_all": [int(x) for x in v[12]], "preds_specific": [int(x) for x in v[13]],
+                             "labels_all": [int(x) for x in v[15]], "labels_specific": [int(x) for x in v[16]]}
+                    else:
+                        preds, probs, labels = [float(x) for x in v[7]], [float(x) for x in v[8]], [float(x) for x in v[10]]
+                        r = {"scores": [float(x) for x in v[:5]], "cm": v[5].tolist(), "preds": preds, "probs": probs,
+                             "labels": labels, "auc": float(roc_auc_score(labels, probs)), "subjects": list(v[12])}
+                    r["n_test"] = len(te.dataset)
+                    rec["val"][tag] = r
+                    print("fixed", name, tag, r["n_test"], [round(x, 4) for x in r["scores"]], r.get("auc"))
+            finally:
+                torch.nn.CrossEntropyLoss = saved_ce
+            meta[name] = rec
+    np.savez_compressed(os.path.join(HERE, "fixed_weights.npz"), **arrays)
+    json.dump(meta, open(os.path.join(HERE, "fixed_weights.json"), "w"))
+    print("fixed_weights:", sum(v.size for v in arrays.values()), "floats")
+
+
+# ---------------------------------------------------------------- post-processing, fold aggregation, table ingest (f1, f4)
+def gen_postproc():
+    """frame2window / compute_window_metrics / create_summary_df / create_binary_mask / load_data(video_data_path) /
+    the ensemble notebook's soft vote and cascade, all by executing the reference (the two notebook cells are restated
+    from ensemble.ipynb cell 6 lines 10-34 and cell 15 lines 53-63 with the same numpy / sklearn calls)."""
+    from sklearn.metrics import accuracy_score, confusion_matrix, f1_score, jaccard_score
+    mu, du = ref.modeling_utils, ref.dataset_utils
+    res = {}
+    outs, preds_b, preds_m, labels, gests, subjects = cases.postproc_inputs()
+    for tag, preds, binary in (("binary", preds_b, True), ("multi", preds_m, False)):
+        wp, wl, wg, ws = mu.frame2window(outs, preds, labels, gests, subjects, window_size=10, stride=6, binary=binary)
+        df, cm = mu.compute_window_metrics(outs, preds, labels, gests, subjects, window_size=10, stride=6, binary=binary)
+        res[f"window_metrics_{tag}"] = {"summary": {c: df.loc["Windowed Metrics", c] for c in df.columns}, "cm": cm.tolist(),
+                                        "n_windows": {o: int(len(wp[o])) for o in wp},
+                                        "preds_digest": {o: digest(wp[o].numpy()) for o in wp},
+                                        "labels_digest": {o: digest(wl[o].numpy()) for o in wl},
+                                        "first_subjects": {o: ws[o]["subject"].tolist()[:3] for o in ws}}
+    rng = np.random.Generator(np.random.PCG64(9))
+    lists = [rng.random(5) for _ in range(6)]
+    samples_train, samples_test = rng.integers(3000, 3700, 5), rng.integers(600, 1100, 5)
+    rates, times = rng.random(5) * 2, rng.random(5) * 3
+    df = mu.create_summary_df(*lists, samples_train, samples_test, rates, times)
+    res["summary_df"] = {"inputs": {"lists": [l.tolist() for l in lists], "samples_train": samples_train.tolist(),
+                                    "samples_test": samples_test.tolist(), "rates": rates.tolist(), "times": times.tolist()},
+                         "cells": {f"{r}/{c}": (None if isinstance(df.loc[r, c], float) and np.isnan(df.loc[r, c]) else str(df.loc[r, c]))
+                                   for r in df.index for c in df.columns}}
+    # ensemble.ipynb cell 6: soft vote of two window models' probabilities
+    n = 4252
+    pa, pb = rng.random(n), rng.random(n)
+    pa[:4], pb[:4] = [0.5, 0.25, 0.75, 0.0], [0.5, 0.75, 0.25, 1.0]
+    pa, pb = pa.astype(np.float32), pb.astype(np.float32)
+    lab = (rng.random(n) > 0.45).astype(np.int64)
+    ens = ((pa.astype(np.float64) + pb.astype(np.float64)) / 2 >= 0.5).astype(int)
+    res["soft_vote"] = {"seed": 9, "n": n, "preds_digest": digest(ens.astype(np.int64)), "acc": float(accuracy_score(lab, ens)),
+                        "f1": float(f1_score(lab, ens)), "jaccard": float(jaccard_score(lab, ens)),
+                        "cm": confusion_matrix(lab, ens).tolist()}
+    np.savez_compressed(os.path.join(HERE, "postproc_inputs.npz"), pa=pa, pb=pb, lab=lab)
+    # ensemble.ipynb cell 15: cascade
+    b, m = rng.integers(0, 2, n), rng.integers(0, 6, n)
+    ens = np.zeros_like(m)
+    ens[b == 1] = m[b == 1]
+    res["cascade"] = {"digest": digest(ens.astype(np.int64)), "binary_digest": digest(b.astype(np.int64))}
+    np.savez_compressed(os.path.join(HERE, "postproc_cascade.npz"), b=b.astype(np.int64), m=m.astype(np.int64), ens=ens.astype(np.int64))
+    # create_binary_mask with mask_position_ND files, load_data with the video_data_path schema
+    fold = synthetic.make_fold(seed=5, n_train=3, n_test=2, t_lo=60, t_hi=90)
+    with tempfile.TemporaryDirectory() as tmp:
+        path, vpath = synthetic.write_fold_video_schema(fold, os.path.join(tmp, "fold"), os.path.join(tmp, "video"))
+        flat = du.load_data(path + "/", "train.csv", video_data_path=vpath + "/")
+        res["load_data_video"] = {"image": digest(flat[0]), "kin": digest(flat[1]), "g": digest(flat[2]), "e": digest(flat[3]),
+                                  "subjects": flat[4]["subject"].tolist()[::40], "n": int(flat[0].shape[0])}
+        flat0 = du.load_data(path + "/", "train.csv")
+        res["load_data_fold"] = {"image": digest(flat0[0]), "kin": digest(flat0[1]), "n": int(flat0[0].shape[0])}
+        subj = np.concatenate([[t.name] * len(t.g) for t in fold.test])
+        pb_ = {"t": (rng.random(len(subj)) > 0.5).astype(int).tolist()}
+        masks = {}
+        for t in fold.test[:1]:
+            mk = torch.from_numpy(rng.random(len(t.g)) < 0.2)
+            torch.save(mk, os.path.join(path, f"mask_position_ND_{t.name}.pth"))
+            masks[t.name] = mk.numpy().tolist()
+        with quiet:
+            bm, bs = mu.create_binary_mask(pb_, {"t": subj.tolist()}, "t", path, {"delete_ND": True})
+            bm0, bs0 = mu.create_binary_mask(pb_, {"t": subj.tolist()}, "t", path, {"delete_ND": False})
+        res["binary_mask"] = {"preds": pb_["t"], "subjects": subj.tolist(), "masks": masks, "mask_out": bm.tolist(),
+                              "subjects_out": bs.tolist(), "mask_out_keep_nd": bm0.tolist(), "fold_seed": 5}
+    json.dump(res, open(os.path.join(HERE, "postproc.json"), "w"))
+    print("postproc:", list(res))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["window_index", "powerset", "models", "epochs", "epochs_es", "window_predictions", "tecno_extra"]
+    which = sys.argv[1:] or ["window_index", "powerset", "models", "epochs", "epochs_es", "window_predictions", "tecno_extra",
+                             "fixed_weights", "postproc"]
     for w in which:
         globals()[f"gen_{w}"]()

@@ -86,13 +86,15 @@ def test_ragged_geometry():
     assert tl.tolist() == [0, 1, 2, 0, 0, 1] and tr.tolist() == [2, 1, 0, 0, 1, 0]
 
 
-def test_unsupported_shape_uses_stock_layers_and_cpu_raises():
-    m = models_TCN.MultiStageModel(2, 3, 32, 10, 2, True).eval()     # 32 feature maps: not the specialised shape
-    out = m(torch.randn(1, 10, 20))
-    assert m.impl == "torch" and out.shape == (2, 1, 2, 20)
+def test_unsupported_shape_and_cpu_raise():
+    """No second implementation: a shape outside the fused kernels is a ValueError, a CPU tensor a RuntimeError."""
     m64 = models_TCN.MultiStageModel(2, 3, 64, 10, 2, True).eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m64(torch.randn(1, 10, 20))
+    m = models_TCN.MultiStageModel(2, 3, 32, 10, 2, True).eval()     # 32 feature maps: not the specialised shape
+    with pytest.raises((ValueError, RuntimeError)):
+        m(torch.randn(1, 10, 20))
+    assert not m.stage1.fused_supported() and m64.stage1.fused_supported()
 
 
 _WORKER = r'''
