@@ -218,3 +218,50 @@ def train_epoch_sequential(model, fe, loader, optimizer, scheduler, exp_kwargs):
     if scheduler is not None:
         scheduler.step()
     return loss_sum / len(loader), ys, ps
+
+
+@torch.no_grad()
+def validate_epoch_es(model, fe, loader, criterion, exp_kwargs):
+    """Error-specific validation.  Reference MED/modeling/modeling_utils.py:793-904 (class index cast to long)
+    -> (loss, *multiclass_summary, probs of class 1, preds, labels)."""
+    model.eval()
+    if fe is not None:
+        fe.eval()
+    loss_sum, ys, ps, probs = 0.0, [], [], []
+    for batch in loader:
+        images, kin, g, e7, subj = batch[:5]
+        y = torch.argmax(select_labels(e7, exp_kwargs).float(), dim=1).view(-1)
+        out = model(fuse_inputs(images, kin, fe, exp_kwargs))
+        loss_sum += criterion(out, y.long()).item()
+        sm = torch.softmax(out, dim=1)
+        ps += torch.argmax(sm, dim=1).tolist()
+        probs += sm[:, 1].tolist()
+        ys += y.tolist()
+    return (loss_sum / len(loader), *multiclass_summary(ys, ps), probs, ps, ys)
+
+
+@torch.no_grad()
+def validate_epoch_sequential(model, fe, binary_model, binary_fe, loader, exp_kwargs):
+    """Cascade validation.  Reference MED/modeling/modeling_utils.py:907-1053: the binary model's RAW logit thresholded at
+    0.5 (:979-980) gates the 5-class model; the loss keeps the committed [B] * [B, 1] -> [B, B] broadcast (:989-996): the
+    sum over ALL per-sample losses when any window fired, else their mean.  -> (loss, preds_all, preds_specific,
+    labels_all, labels_specific)."""
+    for m in (model, fe, binary_model, binary_fe):
+        m.eval()
+    ce = nn.CrossEntropyLoss(reduction="none")
+    loss_sum, pa, ps, la, ls = 0.0, [], [], [], []
+    for batch in loader:
+        images, kin, g, e7, subj = batch[:5]
+        y = torch.argmax(select_labels(e7, exp_kwargs).float(), dim=1).view(-1)
+        fired = (binary_model(fuse_inputs(images, kin, binary_fe, exp_kwargs)) > 0.5).float()      # [B, 1]
+        out = model(fuse_inputs(images, kin, fe, exp_kwargs))
+        loss = ce(out, (y - 1).clamp(min=0)) * fired                                                # [B] * [B, 1] -> [B, B]
+        loss = loss.sum() / fired.sum() if fired.sum() > 0 else loss.mean()
+        loss_sum += loss.item()
+        pred = torch.argmax(torch.softmax(out, dim=1), dim=1) + 1
+        f = fired.reshape(-1) > 0
+        pred = torch.where(f, pred, torch.zeros_like(pred))
+        pa += pred.tolist(); la += y.tolist()
+        sel = f & (y > 0)
+        ps += pred[sel].tolist(); ls += y[sel].tolist()
+    return loss_sum / len(loader), pa, ps, la, ls

@@ -1,0 +1,61 @@
+"""Data-parallel check of the WINDOW path through the public API (run with 2+ GPUs):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/dp_window_check.py
+
+Every rank drives modeling_utils.train_single_epoch over its shard of the seed-42 global batches (DeviceWindowLoader(rank,
+world_size)) with cuda_graph=True: the captured step must be sized from the per-rank share (B / world) and actually replay,
+the short last batch runs eagerly with gradient weights n_local * world / n_global, and after two epochs the replicas hold
+bit-identical parameters (one all-reduce per step on every rank).  Prints one JSON line on rank 0."""
+import json
+import os
+import sys
+import tempfile
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from multimodal_error_detection_b200 import parallel, synthetic  # noqa: E402
+from multimodal_error_detection_b200.dataset import dataset_utils as du  # noqa: E402
+from multimodal_error_detection_b200.modeling import modeling_utils as mu  # noqa: E402
+
+
+def main():
+    rank, local_rank, world = parallel.init_from_env()
+    dev = torch.device("cuda", local_rank)
+    fold = synthetic.make_fold(seed=42, n_train=8, n_test=3, t_lo=250, t_hi=450)
+    tmp = tempfile.mkdtemp(prefix=f"dpw{rank}_")
+    path = synthetic.write_fold(fold, os.path.join(tmp, "fold")) + "/"
+    out = {}
+    for precision in ("bf16", "fp32"):
+        kw = dict(dataset_type="window", error_type="global", pos_weight=True, n_epochs=2, batch_size=64, lr=3e-4, lr_scheduler=True,
+                  weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32, data_type="multimodal", delete_ND=True,
+                  return_train_preds=False, siamese=False, model_name="SimpleLSTM", precision=precision, cuda_graph=True)
+        tr, te = du.retrieve_dataloaders_window(path, kw, window_size=16, stride=4, rank=rank, world_size=world)
+        fe, model, crit, opt, sched = mu.define_model_objects(kw, {"multimodal": 58, "video": 32, "kinematics": 26}, dev,
+                                                              tr.dataset.binary_error_distribution, 16)
+        losses = [mu.train_single_epoch(model, fe, tr, crit, opt, sched, dev, kw)[0] for _ in range(2)]
+        stepper = opt._b200_stepper
+        flat = opt.flat_param.detach().clone()
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        same = bool(torch.equal(flat, ref))
+        allsame = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(allsame, op=dist.ReduceOp.MIN)
+        out[precision] = {"graph_replayed": stepper.graph is not None, "stepper_batch": stepper.B, "global_batch": kw["batch_size"],
+                          "replicas_identical": bool(allsame.item()), "loss_rank0": losses}
+        assert stepper.B == kw["batch_size"] // world and stepper.graph is not None, out
+        assert bool(allsame.item()), "replicas drifted apart"
+        opt._b200_stepper = None
+        del stepper
+    if rank == 0:
+        print(json.dumps({"world": world, **out}), flush=True)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    sys.stdout.flush()
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,3 +65,32 @@ def test_ensemble_inference_matches_per_video_and_numpy():
     y = out["labels"].cpu().numpy()
     tn, fp_, fn, tp = [int(((y == a) & (fused == b)).sum()) for a, b in ((0, 0), (0, 1), (1, 0), (1, 1))]
     assert out["counts"].tolist() == [tn, fp_, fn, tp]
+
+
+def test_postprocessing_vs_executed_reference(golden_dir):
+    """frame2window / compute_window_metrics (binary and multi-class), soft_vote_ensemble, cascade_ensemble against the
+    outputs of the executed reference (tests/golden/postproc.json, make_golden.py::gen_postproc)."""
+    import json
+    import os
+    import cases
+    from hashing import digest
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    gold = json.load(open(os.path.join(golden_dir, "postproc.json")))
+    outs, preds_b, preds_m, labels, gests, subjects = cases.postproc_inputs()
+    for tag, preds, binary in (("binary", preds_b, True), ("multi", preds_m, False)):
+        g = gold[f"window_metrics_{tag}"]
+        wp, wl, wg, ws = mu.frame2window(outs, preds, labels, gests, subjects, window_size=10, stride=6, binary=binary)
+        assert {o: int(len(wp[o])) for o in wp} == g["n_windows"]
+        for o in wp:
+            assert digest(wp[o].numpy()) == g["preds_digest"][o] and digest(wl[o].numpy()) == g["labels_digest"][o]
+            assert ws[o]["subject"].tolist()[:3] == g["first_subjects"][o]
+        df, cm = mu.compute_window_metrics(outs, preds, labels, gests, subjects, window_size=10, stride=6, binary=binary)
+        assert {c: df.loc["Windowed Metrics", c] for c in df.columns} == g["summary"]
+        assert np.asarray(cm).tolist() == g["cm"]
+    z = np.load(os.path.join(golden_dir, "postproc_inputs.npz"))
+    g = gold["soft_vote"]
+    preds, acc, f1, jac, cm = mu.soft_vote_ensemble(z["pa"], z["pb"], z["lab"])
+    assert digest(preds.astype(np.int64)) == g["preds_digest"] and cm.tolist() == g["cm"]
+    assert abs(acc - g["acc"]) < 1e-12 and abs(f1 - g["f1"]) < 1e-12 and abs(jac - g["jaccard"]) < 1e-12
+    z = np.load(os.path.join(golden_dir, "postproc_cascade.npz"))
+    assert np.array_equal(mu.cascade_ensemble(z["b"], z["m"]).astype(np.int64), z["ens"])

@@ -200,6 +200,45 @@ def test_gather_norm_full_size_property(ops):
             assert torch.equal(out[lo:lo + 1024], (image[rows[lo:lo + 1024]] - mean) / std)
 
 
+@pytest.mark.parametrize("B,W,want_variant", [(8192, 16, 5), (512, 10, 4), (4096, 8, 5), (600, 7, 4)])
+@pytest.mark.parametrize("exact", [True, False])
+def test_gather_norm_benchmarked_instantiation_vs_oracle(B, W, want_variant, exact, ops, c_oracle):
+    """The instantiation bench.py times -- bf16 output, variant 0 (auto) at B*W >= 4096: the TMA staging-ring kernel
+    gather_norm_tma_kernel<bf16, exact, R, S, 256> (8-row stages when W % 8 == 0, else 2-row stages) -- against the C oracle
+    at the headline size (8192 x 16 x 2048) and at the parity size (512 x 10).  exact division: bit-identical to
+    RN_bf16(oracle fp32); reciprocal multiply: within one bf16 ulp.  The kinematics stream rides along in the same call
+    (fp32, bit-exact) exactly as CustomWindowDataset.gather_batch issues it.  b200med_gather_last_variant() proves which
+    device path ran."""
+    rng = np.random.Generator(np.random.PCG64(B + W))
+    N = 40_000
+    image = np.maximum(rng.standard_normal((N, 2048), dtype=np.float32), 0)
+    kin = rng.standard_normal((N, 26), dtype=np.float32)
+    mi, si = rng.standard_normal(2048, dtype=np.float32) * 0.3, rng.random(2048, dtype=np.float32) + 0.25
+    mk, sk = rng.standard_normal(26, dtype=np.float32), rng.random(26, dtype=np.float32) + 0.25
+    starts = rng.integers(0, N - W, B).astype(np.int32)
+    starts[:3] = [0, N - W, N - W - 1]                       # first and last legal rows
+    img_out = torch.full((B, W, 2048), 7.0, device="cuda", dtype=torch.bfloat16)
+    kin_out = torch.full((B, W, 26), 7.0, device="cuda")
+    ops.gather_norm([ops.GatherStream(dev(image), dev(mi), dev(si), img_out, 0, exact_div=exact),
+                     ops.GatherStream(dev(kin), dev(mk), dev(sk), kin_out, 0, exact_div=True)], dev(starts), W, 0)
+    assert ops.gather_last_variant() == want_variant, ops.gather_last_variant()
+    want32 = torch.from_numpy(_oracle_gather(c_oracle, image, mi, si, starts, W))
+    got = img_out.cpu()
+    if exact:
+        assert torch.equal(got, want32.to(torch.bfloat16))
+    else:
+        w16 = want32.to(torch.bfloat16)
+        # one bf16 ulp: the two neighbours of RN_bf16(oracle) in the bf16 grid
+        ulp = (w16.view(torch.int16).int() - got.view(torch.int16).int()).abs()
+        assert int(ulp.max()) <= 1, int(ulp.max())
+        assert float((ulp > 0).float().mean()) < 0.2
+    assert np.array_equal(kin_out.cpu().numpy(), _oracle_gather(c_oracle, kin, mk, sk, starts, W))
+    # SM cap (the prefetching launch of the train step): same bits on 56 SMs
+    img2 = torch.empty_like(img_out)
+    ops.gather_norm([ops.GatherStream(dev(image), dev(mi), dev(si), img2, 0, exact_div=exact)], dev(starts), W, 56 << 8)
+    assert ops.gather_last_variant() == want_variant and torch.equal(img2, img_out)
+
+
 # ------------------------------------------------------------------------------------------- K2 fp32
 @pytest.mark.parametrize("shape", [(5120, 512, 2048), (1234, 256, 512), (77, 32, 256), (1, 6, 64), (130, 65, 33)])
 def test_linear_f32(shape, ops):

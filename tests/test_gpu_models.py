@@ -311,7 +311,7 @@ def test_checkpoint_interchange(tmp_path):
             p.add_(0.01)
     path = str(tmp_path / "m.pth")
     mu.save_model({"feature_extractor": ofe.state_dict(), "model": omodel.state_dict()}, path)
-    mu.load_model_local(path, fe, model)
+    mu.load_model_file(path, fe, model)
     assert state_digest({k: v.cpu() for k, v in fe.state_dict().items()}) == state_digest(ofe.state_dict())
     assert state_digest({k: v.cpu() for k, v in model.state_dict().items()}) == state_digest(omodel.state_dict())
     assert fe.linear.linear_0.weight.data_ptr() >= opt.flat_param.data_ptr()   # still views of the flat buffer
@@ -515,3 +515,58 @@ def test_bf16_lstm_graph_prefetch_epoch_matches_eager(fold_on_disk):
             assert np.array_equal(a[5], b[5]), mode
             assert a[8] == b[8] and a[9] == b[9], mode
             assert np.abs(np.asarray(a[6]) - np.asarray(b[6])).max() < 1e-3, mode
+
+
+def test_bench_step_bf16_B8192_vs_fp32_oracle():
+    """The headline configuration itself -- bench.py's objects: synthetic table, W = 16 / S = 4 window index, FE + 3-layer
+    LSTM(128), BCE with pos_weight, bf16 mode, B = 8192 windows -- one train step (K1 TMA gather -> tcgen05 FE -> persistent
+    tcgen05 recurrence -> head MLP -> K3 loss -> backward) against the fp32 ORACLE on the same batch (dropout off on both
+    sides): loss within 2e-2, every parameter gradient norm-wise within 2e-2 (north_star's bf16 bar), and the gather of this
+    step is the benchmarked TMA instantiation."""
+    import argparse
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from multimodal_error_detection_b200 import ops
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    from oracle import loops, nets
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    B, W = 8192, bench.W
+    dev = torch.device(DEV)
+    ds, n_frames = bench.build_gpu_job(argparse.Namespace(videos=160), 0, dev)
+    assert len(ds) >= B
+    kw = bench.exp_kwargs(B, "bf16")
+    fe, model, crit, opt, sched = mu.define_model_objects(kw, cases.IN_FEATURES, dev, ds.binary_error_distribution, W)
+    ofe, omodel, ocrit, _, _ = nets.build_objects(dict(kw, precision="fp32"), cases.IN_FEATURES, ds.binary_error_distribution, W)
+    _no_dropout(model, fe)
+    nets.disable_dropout(omodel, ofe)
+    for m in (fe, model, ofe, omodel):
+        m.train()
+    idx = torch.randperm(len(ds), generator=torch.Generator().manual_seed(42))[:B].to(dev)
+    y = mu.define_error_labels(ds.e_labels_data.index_select(0, idx), kw).float()
+    img16, kin = ds.gather_batch(idx, image_dtype=torch.bfloat16, exact=False)
+    assert ops.gather_last_variant() == 5                               # gather_norm_tma_kernel<bf16, false, 8, 3, 256>
+    out = model(mu.define_inputs(img16, kin, fe, kw, dev))
+    loss, _ = mu.compute_loss(out, y, crit, "window")
+    opt.zero_grad(); loss.backward()
+    from multimodal_error_detection_b200 import lstm_stack
+    lstm_stack.join_pending()
+    torch.cuda.synchronize()
+    # oracle on the fp32 batch (the fp32 gather is bit-exact vs the C oracle: test_gpu_kernels.py)
+    img32, kin32 = ds.gather_batch(idx, image_dtype=torch.float32, exact=True)
+    oout = omodel(loops.fuse_inputs(img32.cpu(), kin32.cpu(), ofe, kw))
+    oloss, _ = loops.loss_fn(oout, y.cpu(), ocrit, "window")
+    oloss.backward()
+    lv, ov = float(loss), float(oloss)
+    assert abs(lv - ov) <= 2e-2 * abs(ov), (lv, ov)
+    assert rel(out.detach().cpu().numpy().reshape(-1), oout.detach().numpy().reshape(-1)) < 2e-2
+    errs = {}
+    gmax = max(float(q.grad.norm()) for q in list(ofe.parameters()) + list(omodel.parameters()))
+    for prefix, mod, omod in (("fe", fe, ofe), ("model", model, omodel)):
+        for (k, p), (_, q) in zip(mod.named_parameters(), omod.named_parameters()):
+            if float(q.grad.norm()) < 1e-4 * gmax:
+                continue                                                # zero in exact arithmetic: round-off on both sides
+            errs[f"{prefix}.{k}"] = float((p.grad.detach().cpu().double() - q.grad.double()).norm() / q.grad.double().norm())
+    print("B=8192 bf16 step vs fp32 oracle: loss", lv, ov, "gradient errors", {k: round(v, 5) for k, v in errs.items()})
+    assert max(errs.values()) < 2e-2, errs

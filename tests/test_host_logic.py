@@ -152,6 +152,34 @@ def test_index_batches_mirror_the_dataloader_exactly():
     assert all(len(p) == 2 and min(p) >= 1 for p in per_rank) and [sum(x) for x in zip(*per_rank)] == [16, 16]
 
 
+def test_data_parallel_weights_of_uneven_shards():
+    """A short last batch splits into shards that differ by one window: each rank's mean-reduced gradient is weighted by
+    n_local * world / n_global so that the SUM all-reduce scaled by 1 / world is the mean over the GLOBAL batch."""
+    from multimodal_error_detection_b200.dataset.CustomWindowDataset import DeviceWindowLoader
+
+    class _DS:
+        def __init__(self, n): self.n = n
+        def __len__(self): return self.n
+
+    world, n, B = 4, 37, 16                                   # global batches of 16, 16, 5 windows
+    loaders = [DeviceWindowLoader(_DS(n), B, shuffle=True, generator=torch.Generator().manual_seed(42), rank=r, world_size=world)
+               for r in range(world)]
+    per_rank = [list(l.index_batches_with_global()) for l in loaders]
+    assert [g for _, g in per_rank[0]] == [16, 16, 5]
+    x = torch.arange(n, dtype=torch.float64) ** 1.5           # "per-window loss"
+    for k in range(3):
+        shards = [per_rank[r][k][0] for r in range(world)]
+        n_global = per_rank[0][k][1]
+        whole = torch.cat(shards)
+        assert whole.numel() == n_global
+        # sum over ranks of weight * local mean, scaled by 1 / world == global mean
+        combined = sum(loaders[r].dp_weight(shards[r].numel(), n_global) * x[shards[r]].mean() for r in range(world)) / world
+        assert abs(float(combined) - float(x[whole].mean())) < 1e-12
+        if n_global == B:
+            assert all(loaders[r].dp_weight(shards[r].numel(), n_global) == 1.0 for r in range(world))
+    assert DeviceWindowLoader(_DS(n), B).dp_weight(5, 5) == 1.0
+
+
 def test_lstm_dg_column_permutation():
     """Host side of the recurrence kernels' dG layout (csrc/lstm_rec.cu): column' = chunk*128 + unit_quarter*32 + gate*8 + i
     holds gate column gate*H + unit_quarter*32 + chunk*8 + i -- a permutation, and the two index tensors are inverses."""

@@ -181,3 +181,103 @@ def test_c_gather_norm(c_oracle):
     want = ((torch.from_numpy(table)[torch.from_numpy(starts)[:, None] + torch.arange(10)[None]] - torch.from_numpy(mean))
             / torch.from_numpy(std)).numpy()
     assert np.array_equal(out, want)
+
+
+# ------------------------------------------------------------------------------------------- fixed trained weights
+def _oracle_loaders(path, kw, W, S):
+    """The oracle's data path on a fold written to disk: window_data -> powerset -> Needle-Drop deletion -> dataset."""
+    import pandas as pd
+    from multimodal_error_detection_b200 import synthetic
+    fold = synthetic.make_fold(**cases.FIXED_FOLD_ARGS)
+    out = []
+    for trials in (fold.train, fold.test):
+        image, kin, g, e5, names, _ = synthetic.flat_tables(trials)
+        iw, kw_, gw, ew, sw = window_index.window_data(image, kin, g, e5, names, W, S)
+        e7, nd = window_index.powerset_error_labels(ew, kw["delete_ND"])
+        keep = ~nd if kw["delete_ND"] else np.ones(len(nd), dtype=bool)
+        stats = {"image": {"mean": torch.from_numpy(fold.mean_image), "std": torch.from_numpy(fold.std_image)},
+                 "kinematics": {"mean": torch.from_numpy(fold.mean_kin), "std": torch.from_numpy(fold.std_kin)}}
+        out.append(loops.OracleWindowDataset(torch.from_numpy(iw[keep]), torch.from_numpy(kw_[keep]), torch.from_numpy(gw[keep]),
+                                             torch.from_numpy(e7[keep]), [s for s, k in zip(sw, keep) if k], stats))
+    return loops.make_loaders(out[0], out[1], kw["batch_size"])
+
+
+def _oracle_fixed(name, W):
+    import fixed
+    kw = cases.FIXED_CASES[name][0]
+    fe, model, crit, _, _ = nets.build_objects(kw, cases.IN_FEATURES, (0.4, 0.6), W)
+    fixed.load_trained(name, fe, model)
+    return kw, fe, model, crit
+
+
+@pytest.mark.parametrize("name", ["lstm_global", "cnn_global"])
+def test_fixed_weights_validation_binary(name):
+    """The reference's validate_single_epoch on reference-trained weights (tests/golden/fixed_weights.*): the oracle's
+    predictions are identical, its pooled scores and roc_auc_score equal to 3 decimals (north_star bar) -- in fact to 1e-12."""
+    import fixed
+    from sklearn.metrics import roc_auc_score
+    for (W, S) in cases.FIXED_CASES[name][1]:
+        kw, fe, model, crit = _oracle_fixed(name, W)
+        _, te = _oracle_loaders(None, kw, W, S)
+        gold = fixed.meta()[name]["val"][f"w{W}_s{S}"]
+        v = loops.validate_epoch(model, fe, te, crit, kw)
+        assert len(te.dataset) == gold["n_test"]
+        assert v[6] == gold["preds"] and v[8] == gold["labels"]
+        assert np.abs(np.asarray(v[7]) - np.asarray(gold["probs"])).max() < 1e-6
+        assert np.abs(np.asarray(v[1:5]) - np.asarray(gold["scores"][1:])).max() < 1e-12
+        assert abs(roc_auc_score(v[8], v[7]) - gold["auc"]) < 1e-9
+
+
+def test_fixed_weights_validation_es_and_cascade():
+    import fixed
+    kw, fe, model, crit = _oracle_fixed("lstm_es", 10)
+    _, te = _oracle_loaders(None, kw, 10, 6)
+    gold = fixed.meta()["lstm_es"]["val"]["w10_s6"]
+    v = loops.validate_epoch_es(model, fe, te, torch.nn.CrossEntropyLoss(), kw)
+    assert v[10] == gold["preds"] and v[11] == gold["labels"]
+    assert abs(v[0] - gold["scores"][0]) < 1e-5 * abs(gold["scores"][0])
+    assert np.abs(np.asarray(v[1:7]) - np.asarray(gold["scores"][1:])).max() < 1e-12
+    assert np.abs(np.asarray(v[9]) - np.asarray(gold["probs"])).max() < 1e-6
+    kws, sfe, smodel, _ = _oracle_fixed("lstm_seq", 10)
+    kwb, bfe, bmodel, _ = _oracle_fixed("lstm_global", 10)
+    _, te = _oracle_loaders(None, kws, 10, 6)
+    gold = fixed.meta()["lstm_seq"]["val"]["w10_s6"]
+    loss, pa, ps, la, ls = loops.validate_epoch_sequential(smodel, sfe, bmodel, bfe, te, kws)
+    assert pa == gold["preds_all"] and la == gold["labels_all"] and ps == gold["preds_specific"] and ls == gold["labels_specific"]
+    assert abs(loss - gold["scores"][0]) < 1e-5 * abs(gold["scores"][0])
+
+
+# ------------------------------------------------------------------------------------------- host-side f1 / f4 functions
+def test_load_data_both_schemas_and_binary_mask(golden_dir, tmp_path):
+    """load_data (fold schema and the video_data_path schema, dataset_utils.py:73-96 / :118-136), create_binary_mask with
+    mask_position_ND_<subject>.pth files (modeling_utils.py:2920-2976) and create_summary_df (:2979-3025): host-side
+    functions of the drop-in package against the outputs of the executed reference."""
+    from multimodal_error_detection_b200.dataset import dataset_utils as du
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    gold = json.load(open(os.path.join(golden_dir, "postproc.json")))
+    fold = synthetic.make_fold(seed=5, n_train=3, n_test=2, t_lo=60, t_hi=90)
+    path, vpath = synthetic.write_fold_video_schema(fold, str(tmp_path / "fold"), str(tmp_path / "video"))
+    flat = du.load_data(path + "/", "train.csv", video_data_path=vpath + "/")
+    g = gold["load_data_video"]
+    assert (digest(flat[0]), digest(flat[1]), digest(flat[2]), digest(flat[3])) == (g["image"], g["kin"], g["g"], g["e"])
+    assert flat[4]["subject"].tolist()[::40] == g["subjects"] and flat[0].shape[0] == g["n"]
+    flat0 = du.load_data(path + "/", "train.csv")
+    assert digest(flat0[0]) == gold["load_data_fold"]["image"] and digest(flat0[1]) == gold["load_data_fold"]["kin"]
+    assert digest(flat0[0]) != digest(flat[0])
+    # create_binary_mask
+    bm = gold["binary_mask"]
+    for subj, mk in bm["masks"].items():
+        torch.save(torch.tensor(mk), os.path.join(path, f"mask_position_ND_{subj}.pth"))
+    out_mask, out_subj = mu.create_binary_mask({"t": bm["preds"]}, {"t": bm["subjects"]}, "t", path, {"delete_ND": True})
+    assert out_mask.tolist() == bm["mask_out"] and out_subj.tolist() == bm["subjects_out"]
+    keep, _ = mu.create_binary_mask({"t": bm["preds"]}, {"t": bm["subjects"]}, "t", path, {"delete_ND": False})
+    assert keep.tolist() == bm["mask_out_keep_nd"]
+    # create_summary_df
+    sd = gold["summary_df"]
+    i = sd["inputs"]
+    df = mu.create_summary_df(*[np.asarray(l) for l in i["lists"]], np.asarray(i["samples_train"]), np.asarray(i["samples_test"]),
+                              np.asarray(i["rates"]), np.asarray(i["times"]))
+    for key, want in sd["cells"].items():
+        r, c = key.split("/")
+        got = df.loc[r, c]
+        assert (want is None and isinstance(got, float) and np.isnan(got)) or str(got) == want, (key, got, want)
