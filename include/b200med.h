@@ -267,6 +267,13 @@ int b200med_conv_pack(const float *w, float *fwd, float *bwd, int32_t Cout, int3
 int b200med_conv_unpack_grad(const float *dfwd, float *dw, int32_t Cout, int32_t Cin, void *stream);
 /* y [B, C, R] <- x [B, R, C]: nn.Flatten of the reference runs over [B, C, L] (models.py:100).                  */
 int b200med_transpose_last2(const float *x, float *y, int64_t B, int32_t R, int32_t C, void *stream);
+/* out [M, Ca + Cb] = [a | b]: the torch.cat((features, kinematics), dim=2) of define_inputs (modeling_utils.py:41-47);
+ * slice_cols: out [M, C] = x [M, ld] columns [col0, col0 + C) (its backward for the feature stream).            */
+int b200med_concat2(const float *a, const float *b, float *out, int64_t M, int32_t Ca, int32_t Cb, void *stream);
+int b200med_slice_cols(const float *x, float *out, int64_t M, int32_t ld, int32_t col0, int32_t C, void *stream);
+/* out [n, C] = src [idx[i], :] for 4-byte elements (f32 / i32): per-batch lookups by window index (start rows, labels:
+ * what DataLoader collation does per sample, dataset_utils.py:526-527).                                          */
+int b200med_take_rows(const void *src, const int64_t *idx, void *out, int64_t n, int32_t C, void *stream);
 
 /* Persistent recurrence, one launch per layer and direction (csrc/lstm_rec.cu; hidden_size H = 128 only).
  * A CTA owns 128 windows and walks all W steps: W_hh (bf16 [4H,H], nn.LSTM weight_hh_l{k} layout) stays in
@@ -287,6 +294,33 @@ int b200med_lstm_rec_fwd(const void *xg, const void *whh_bf16, void *gact, float
 int b200med_lstm_rec_bwd(const void *gact, const float *c, const void *whh_bf16, const float *dh_top,
                          const float *dh_up, int32_t up_cols, void *dG, int64_t B, int64_t Bpad, int32_t W, int32_t H,
                          float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream);
+
+/* Second-generation forward recurrence (csrc/lstm_rec2.cu): one launch of 2-CTA clusters (128 windows per cluster, 64 per
+ * CTA, `tcgen05.mma.cta_group::2` with M = 128) with the x-part of the gates fused in -- gates_t = [x_t | h_{t-1}] [W_ih | W_hh]^T
+ * + b is ONE accumulator, the XG matrix of the first generation is never written.  Same outputs as b200med_lstm_rec_fwd
+ * (gact / c row-block-interleaved, h_t TMA-stored into A_l[t+1][:, kx:kx+128], dropout(h_t) into A_up[t][:, 0:128], h_out).
+ *   a_l [W, Bpad, ld_l] bf16 = [x_t (kx = 64 | 128 columns) | h_{t-1} (128)]: x is READ from it, h_t is WRITTEN into it;
+ *   wp [512, kx + 128] bf16, bias_p [512] f32: b200med_lstm_pack_weights2 (gate rows in the kernel's operand order, i / f / o
+ *   rows halved: sigmoid(z) = 0.5 tanh(z/2) + 0.5).  nn.LSTM weights: models.py:161.                            */
+int b200med_lstm_pack_weights2(const float *w_ih, const float *w_hh, const float *b_ih, const float *b_hh, int32_t in,
+                               int32_t kx, void *wp, float *bias_p, void *stream);
+int b200med_lstm_rec2_fwd(void *a_l, int32_t ld_l, int32_t kx, const void *wp, const float *bias_p, void *gact, float *c,
+                          void *a_up, int32_t ld_up, float *h_out, int64_t B, int64_t Bpad, int32_t W, float drop_p,
+                          const uint32_t *seed, uint64_t drop_base, void *stream);
+/* Second-generation backward recurrence: dG_t (bf16, TMA-stored to dG [W, Bpad, 512] with PERMUTED columns, see lstm_rec2.cu),
+ * dh_{t-1} and the layer-input gradient dX_t = dG_t W_ih out of ONE accumulator per step (the separate dX GEMM of the first
+ * generation is gone).  wt [kx + 128, 512] bf16 from b200med_lstm_pack_weights2_bwd (perm [512] i32 OUT or NULL: the gate row
+ * behind every dG column).  dh_top [B, 128] f32 (top layer) or NULL; dh_up: dX of the layer above (row-block-interleaved
+ * [W*Bpad, 128] f32) or NULL; dx OUT: row-block-interleaved [W*Bpad, 128] f32 when kx = 128, row-major [W*Bpad, 64] when kx = 64. */
+int b200med_lstm_pack_weights2_bwd(const float *w_ih, const float *w_hh, int32_t in, int32_t kx, void *wt, int32_t *perm,
+                                   void *stream);
+int b200med_lstm_rec2_bwd(const void *gact, const float *c, const void *wt, int32_t kx, const float *dh_top,
+                          const float *dh_up, void *dG, float *dx, int64_t B, int64_t Bpad, int32_t W, float drop_p,
+                          const uint32_t *seed, uint64_t drop_base, void *stream);
+/* dwp [512, kx + 128] f32 = dG^T [x | h_prev] and dbp [512] = column sums of dG, both in generation 2's dG column order ->
+ * nn.LSTM's parameter gradients dw_ih [512, in], dw_hh [512, 128], db_ih = db_hh [512] (gate rows un-permuted).  */
+int b200med_lstm_unpack_grads2(const float *dwp, const float *dbp, int32_t in, int32_t kx, float *dw_ih, float *dw_hh,
+                               float *db_ih, float *db_hh, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3  Fused loss + gradient + metric counts (latency-bound; deterministic reductions)

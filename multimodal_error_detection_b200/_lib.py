@@ -53,6 +53,11 @@ SIGNATURES = {
     "b200med_lstm_rec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p,
                                        C.c_uint64, _p]),
     "b200med_lstm_rec_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_lstm_pack_weights2": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p]),
+    "b200med_lstm_rec2_fwd": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_lstm_pack_weights2_bwd": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p]),
+    "b200med_lstm_rec2_bwd": (C.c_int, [_p, _p, _p, _i32, _p, _p, _p, _p, _i64, _i64, _i32, _f, _p, C.c_uint64, _p]),
+    "b200med_lstm_unpack_grads2": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _p, _p, _p]),
     "b200med_lstm_unpack_dx": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]),
     "b200med_zero_cols_bf16": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p]),
     "b200med_lstm_cell_fwd": (C.c_int, [_p, _p, _p, _p, _i32, _p, _i32, _p, _i64, _i32, _f, _p, C.c_uint64, _p]),
@@ -69,6 +74,9 @@ SIGNATURES = {
     "b200med_conv_pack": (C.c_int, [_p, _p, _p, _i32, _i32, _p]),
     "b200med_conv_unpack_grad": (C.c_int, [_p, _p, _i32, _i32, _p]),
     "b200med_transpose_last2": (C.c_int, [_p, _p, _i64, _i32, _i32, _p]),
+    "b200med_concat2": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p]),
+    "b200med_slice_cols": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p]),
+    "b200med_take_rows": (C.c_int, [_p, _p, _p, _i64, _i32, _p]),
     "b200med_loss_ws_bytes": (_i64, [_i64]),
     "b200med_bce_logits": (C.c_int, [_p, _p, _i64, _f, _f, _p, _p, _p, _p, _p, _i32, _p, _p]),
     "b200med_ce_logits": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _f, _p, _p, _p, _p, _i32, _i32, _p, _i32,

@@ -270,6 +270,35 @@ __global__ void transpose_last2_kernel(const float *__restrict__ x, float *__res
     }
 }
 
+// out [M, Ca + Cb] = [a [M, Ca] | b [M, Cb]] -- torch.cat((features, kinematics), dim=2) of define_inputs (modeling_utils.py:41-47)
+__global__ void concat2_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long long M,
+                               int Ca, int Cb) {
+    const int C = Ca + Cb;
+    const long long total = M * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e / C;
+        const int c = (int)(e - m * C);
+        out[e] = c < Ca ? a[m * Ca + c] : b[m * Cb + (c - Ca)];
+    }
+}
+// da [M, Ca] = dout [M, ld] columns [col0, col0 + Ca)
+__global__ void slice_cols_kernel(const float *__restrict__ dout, float *__restrict__ da, long long M, int ld, int col0, int Ca) {
+    const long long total = M * Ca;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long m = e / Ca;
+        da[e] = dout[m * ld + col0 + (int)(e - m * Ca)];
+    }
+}
+// out [n, C] = src [idx[i], :] for 4-byte elements (window-index -> start row / label lookups of a batch)
+__global__ void take_rows_kernel(const uint32_t *__restrict__ src, const long long *__restrict__ idx, uint32_t *__restrict__ out,
+                                 long long n, int C) {
+    const long long total = n * C;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / C;
+        out[e] = src[idx[i] * C + (e - i * C)];
+    }
+}
+
 static long long bn_slabs(long long M) {
     long long s = (M + 255) / 256;
     return s < 1 ? 1 : (s > 64 ? 64 : s);
@@ -362,4 +391,33 @@ extern "C" __attribute__((visibility("default"))) int b200med_transpose_last2(co
     B200MED_REQUIRE(x && y, "null pointer");
     transpose_last2_kernel<<<ew_grid(B * (long long)R * C), 256, 0, (cudaStream_t)stream>>>(x, y, B, R, C);
     return after_launch("transpose_last2_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_concat2(const float *a, const float *b, float *out, int64_t M, int32_t Ca, int32_t Cb,
+                                                                     void *stream) {
+    B200MED_REQUIRE(M >= 0 && Ca >= 1 && Cb >= 1, "bad shape");
+    if (M == 0) return B200MED_OK;
+    B200MED_REQUIRE(a && b && out, "null pointer");
+    concat2_kernel<<<ew_grid(M * (Ca + Cb)), 256, 0, (cudaStream_t)stream>>>(a, b, out, M, Ca, Cb);
+    return after_launch("concat2_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_slice_cols(const float *x, float *out, int64_t M, int32_t ld, int32_t col0, int32_t C,
+                                                                        void *stream) {
+    B200MED_REQUIRE(M >= 0 && C >= 1 && col0 >= 0 && col0 + C <= ld, "bad shape");
+    if (M == 0) return B200MED_OK;
+    B200MED_REQUIRE(x && out, "null pointer");
+    slice_cols_kernel<<<ew_grid(M * C), 256, 0, (cudaStream_t)stream>>>(x, out, M, ld, col0, C);
+    return after_launch("slice_cols_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_take_rows(const void *src, const int64_t *idx, void *out, int64_t n, int32_t C,
+                                                                       void *stream) {
+    B200MED_REQUIRE(n >= 0 && C >= 1, "bad shape");
+    if (n == 0) return B200MED_OK;
+    B200MED_REQUIRE(src && idx && out, "null pointer");
+    take_rows_kernel<<<ew_grid(n * C), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(src),
+                                                                        reinterpret_cast<const long long *>(idx),
+                                                                        reinterpret_cast<uint32_t *>(out), n, C);
+    return after_launch("take_rows_kernel");
 }

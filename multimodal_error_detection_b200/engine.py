@@ -71,7 +71,8 @@ class WindowTrainStep:
         return self.graphs[0]
 
     def _gather(self, which: int, sm_cap: int = 0):
-        starts = self.ds._starts.index_select(0, self.idx2[which])
+        from . import ops
+        starts = ops.take_rows(self.ds._starts, self.idx2[which])
         if self.gather_events is not None:
             self.gather_events[0].record()
         self.ds.gather_batch(None, image_out=self.images2[which], kin_out=self.kin2[which], starts=starts,
@@ -96,7 +97,8 @@ class WindowTrainStep:
     def _body(self, cur: int):
         nxt = 1 - cur
         self._mark(0)
-        labels = self.label_col.index_select(0, self.idx2[cur])
+        from . import ops
+        labels = ops.take_rows(self.label_col, self.idx2[cur], out=self.labels)
         if not self.prefetch:
             self._gather(cur)
         self._mark(1)
@@ -112,7 +114,14 @@ class WindowTrainStep:
                 self._gather(nxt, self.prefetch_sms)      # leaves the other SMs to the main stream's kernels
         outputs = self.model(inputs)
         self._mark(3)
-        loss, _ = mu.compute_loss(outputs, labels, self.crit, "window")
+        static = isinstance(self.crit, mu.FusedBCEWithLogitsLoss)
+        if static:      # K3 writes the step's persistent result buffers itself (no copies at the end of the step)
+            self.crit.static_out = dict(loss=self.loss, probs=self.probs, preds=self.preds, counts=self.counts)
+        try:
+            loss, _ = mu.compute_loss(outputs, labels, self.crit, "window")
+        finally:
+            if static:
+                self.crit.static_out = None
         self.opt.zero_grad()
         self._mark(4)
         mu._backward(loss, self.opt)
@@ -120,12 +129,12 @@ class WindowTrainStep:
         mu._allreduce_grads(self.opt)
         self.opt.step()
         self._mark(7)
-        probs, preds, counts = self.crit.last
-        self.loss.copy_(loss.detach().reshape(1))
-        self.counts.copy_(counts)
-        self.probs.copy_(probs)
-        self.preds.copy_(preds)
-        self.labels.copy_(labels)
+        if not static:
+            probs, preds, counts = self.crit.last
+            self.loss.copy_(loss.detach().reshape(1))
+            self.counts.copy_(counts)
+            self.probs.copy_(probs)
+            self.preds.copy_(preds)
         if self.prefetch:
             torch.cuda.current_stream().wait_stream(self._side)
         self._mark(8)

@@ -200,3 +200,28 @@ def conv_stack(x: torch.Tensor, seq: nn.Sequential, training: bool, seed_dev) ->
     if tl.is_contiguous() and not x.is_contiguous():
         return ConvStackFunction.apply(tl, 1, training, cfg, drops, seed_dev, *tensors)
     return ConvStackFunction.apply(x, 0, training, cfg, drops, seed_dev, *tensors)
+
+
+class ConcatFeaturesFunction(torch.autograd.Function):
+    """torch.cat((features [B, W, Ca], kinematics [B, W, Cb]), dim=2) of define_inputs (modeling_utils.py:41-47) as one kernel;
+    the backward slices the feature columns out of the gradient (the kinematics come from the dataset: no gradient)."""
+
+    @staticmethod
+    def forward(ctx, feats, kin):
+        B, W, Ca = feats.shape
+        Cb = kin.shape[2]
+        ctx.dims = (B, W, Ca, Cb)
+        out = ops.concat2(feats.contiguous().float().view(B * W, Ca), kin.contiguous().float().view(B * W, Cb))
+        return out.view(B, W, Ca + Cb)
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, W, Ca, Cb = ctx.dims
+        d = dout.contiguous().float().view(B * W, Ca + Cb)
+        da = ops.slice_cols(d, 0, Ca).view(B, W, Ca) if ctx.needs_input_grad[0] else None
+        db = ops.slice_cols(d, Ca, Cb).view(B, W, Cb) if ctx.needs_input_grad[1] else None
+        return da, db
+
+
+def concat_features(feats: torch.Tensor, kin: torch.Tensor) -> torch.Tensor:
+    return ConcatFeaturesFunction.apply(feats, kin)

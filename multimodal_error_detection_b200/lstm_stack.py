@@ -122,6 +122,10 @@ class LSTMStackFunction(torch.autograd.Function):
 
 _PERM = {}
 _SIDE = {}
+# Generation of the forward recurrence kernel: 2 = 2-CTA clusters with the x-part fused in (csrc/lstm_rec2.cu), 1 = the
+# first-generation kernel behind a separate x-part GEMM (csrc/lstm_rec.cu).  Both write the same buffers; the tests hold
+# one against the other.  Not a user switch: the product runs generation 2.
+REC_GEN = 2
 # Deferred join of the side stream.  The weight / bias gradients of the LSTM layers are computed on a side stream; with
 # DEFER_JOIN the backward returns them WITHOUT making the main stream wait (autograd only stores the tensors when
 # `.grad is None`), so the side work of layer 0 overlaps the FeatureExtractor backward.  Whoever consumes the gradients
@@ -161,6 +165,20 @@ def _dg_perm(H: int, device):
     return _PERM[key]
 
 
+def _dg_perm2(device):
+    """Column order of generation 2's dG (csrc/lstm_rec2.cu): column' = chunk*256 + unit_half*128 + warp_column*32 + gate*8 + i
+    stands for gate row gate*128 + unit_half*64 + warp_column*16 + chunk*8 + i.  Returns (orig_of_col', col'_of_orig)."""
+    key = ("gen2", str(device))
+    if key not in _PERM:
+        kp = torch.arange(512)
+        c, uh, cq, g, i = kp >> 8, (kp >> 7) & 1, (kp >> 5) & 3, (kp >> 3) & 3, kp & 7
+        orig = g * 128 + uh * 64 + cq * 16 + c * 8 + i
+        inv = torch.empty_like(orig)
+        inv[orig] = kp
+        _PERM[key] = (orig.to(device), inv.to(device))
+    return _PERM[key]
+
+
 class LSTMRecFunction(torch.autograd.Function):
     """Persistent-recurrence path (hidden_size 128).  Layer buffers, time-major with the batch padded to Bp (multiple
     of 32) rows per step:
@@ -191,40 +209,63 @@ class LSTMRecFunction(torch.autograd.Function):
         out = torch.empty(B, H, dtype=torch.float32, device=dev)
         seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
         Wih, Whh, Gact, Cs = [], [], [], []
-        xg = torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev)
+        gen2 = REC_GEN == 2 and all(i in (64, 128) for i in inp)      # generation 2 stages [x | h] tiles of 64 / 128 + 128 columns
+        xg = None if gen2 else torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev)
         # rows of the sigmoid gates (i, f, o) are halved for the forward kernels: sigmoid(z) = 0.5 * tanh(z / 2) + 0.5
-        half = torch.ones(4 * H, 1, dtype=torch.float32, device=dev)
-        half[:2 * H] = 0.5
-        half[3 * H:] = 0.5
+        half = None
+        if not gen2:
+            half = torch.ones(4 * H, 1, dtype=torch.float32, device=dev)
+            half[:2 * H] = 0.5
+            half[3 * H:] = 0.5
         for l in range(L):
             w_ih, w_hh, b_ih, b_hh = params[4 * l:4 * l + 4]
-            wpad = torch.zeros(4 * H, inp[l], dtype=torch.float32, device=dev)
-            wpad[:, :ins[l]] = w_ih.detach()
-            Wih.append(ops.to_bf16(wpad) if need_grad else None)                      # unscaled copies: backward operands
-            Whh.append(ops.to_bf16(w_hh.detach().contiguous()) if need_grad else None)
-            wih_f = ops.to_bf16(wpad * half)
-            whh_f = ops.to_bf16(w_hh.detach() * half)
-            bias = ((b_ih.detach() + b_hh.detach()) * half[:, 0]).contiguous()
-            # x-part of the gates for every step at once: [W*Bp, inp] x [4H, inp]^T + bias
-            ops.gemm_bf16(A[l].view(W * Bp, Kp[l]), wih_f, W * Bp, 4 * H, inp[l], True, True, bias=bias, out=xg, rbi=True)
+            if need_grad and not gen2:                                                 # unscaled copies: backward operands
+                wpad = torch.zeros(4 * H, inp[l], dtype=torch.float32, device=dev)
+                wpad[:, :ins[l]] = w_ih.detach()
+                Wih.append(ops.to_bf16(wpad))
+                Whh.append(ops.to_bf16(w_hh.detach().contiguous()))
+            elif need_grad:                                                            # generation 2 packs its own operand in the backward
+                Wih.append(w_ih.detach()); Whh.append(w_hh.detach())
+            else:
+                Wih.append(None); Whh.append(None)
             gact = torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev) if need_grad else None
             cs = torch.empty(W * Bp, H, dtype=torch.float32, device=dev) if need_grad else None
             top = l == L - 1
-            call("b200med_lstm_rec_fwd", _raw(xg.data_ptr()), _raw(whh_f.data_ptr()),
-                 _raw(gact.data_ptr() if need_grad else 0), _raw(cs.data_ptr() if need_grad else 0),
-                 _raw(A[l].data_ptr() if need_grad else 0), Kp[l], inp[l],
-                 _raw(0 if top else A[l + 1].data_ptr()), 0 if top else Kp[l + 1],
-                 _raw(out.data_ptr() if top else 0), B, Bp, W, H, 0.0 if top else float(drop_p), _raw(seed_ptr),
-                 l * W * Bp * H, st)
+            if gen2:
+                wp = torch.empty(4 * H, Kp[l], dtype=torch.bfloat16, device=dev)
+                bias_p = torch.empty(4 * H, dtype=torch.float32, device=dev)
+                call("b200med_lstm_pack_weights2", _raw(w_ih.detach().contiguous().data_ptr()), _raw(w_hh.detach().contiguous().data_ptr()),
+                     _raw(b_ih.detach().contiguous().data_ptr()), _raw(b_hh.detach().contiguous().data_ptr()), ins[l], inp[l],
+                     _raw(wp.data_ptr()), _raw(bias_p.data_ptr()), st)
+                call("b200med_lstm_rec2_fwd", _raw(A[l].data_ptr()), Kp[l], inp[l], _raw(wp.data_ptr()), _raw(bias_p.data_ptr()),
+                     _raw(gact.data_ptr() if need_grad else 0), _raw(cs.data_ptr() if need_grad else 0),
+                     _raw(0 if top else A[l + 1].data_ptr()), 0 if top else Kp[l + 1], _raw(out.data_ptr() if top else 0),
+                     B, Bp, W, 0.0 if top else float(drop_p), _raw(seed_ptr), l * W * Bp * H, st)
+            else:
+                wpad = torch.zeros(4 * H, inp[l], dtype=torch.float32, device=dev)
+                wpad[:, :ins[l]] = w_ih.detach()
+                wih_f = ops.to_bf16(wpad * half)
+                whh_f = ops.to_bf16(w_hh.detach() * half)
+                bias = ((b_ih.detach() + b_hh.detach()) * half[:, 0]).contiguous()
+                # x-part of the gates for every step at once: [W*Bp, inp] x [4H, inp]^T + bias
+                ops.gemm_bf16(A[l].view(W * Bp, Kp[l]), wih_f, W * Bp, 4 * H, inp[l], True, True, bias=bias, out=xg, rbi=True)
+                call("b200med_lstm_rec_fwd", _raw(xg.data_ptr()), _raw(whh_f.data_ptr()),
+                     _raw(gact.data_ptr() if need_grad else 0), _raw(cs.data_ptr() if need_grad else 0),
+                     _raw(A[l].data_ptr() if need_grad else 0), Kp[l], inp[l],
+                     _raw(0 if top else A[l + 1].data_ptr()), 0 if top else Kp[l + 1],
+                     _raw(out.data_ptr() if top else 0), B, Bp, W, H, 0.0 if top else float(drop_p), _raw(seed_ptr),
+                     l * W * Bp * H, st)
             Gact.append(gact); Cs.append(cs)
         if need_grad:
             ctx.save_for_backward(*A, *Gact, *Cs, *Wih, *Whh)
         ctx.meta = (B, Bp, F, W, L, H, Kp, ins, inp, float(drop_p), seed_dev, bwf)
+        ctx.gen2 = gen2
         return out
 
     @staticmethod
     def backward(ctx, dout):
         B, Bp, F, W, L, H, Kp, ins, inp, drop_p, seed_dev, bwf = ctx.meta
+        gen2 = ctx.gen2
         saved = ctx.saved_tensors
         A, Gact, Cs, Wih, Whh = (saved[i * L:(i + 1) * L] for i in range(5))
         dev = dout.device
@@ -233,7 +274,7 @@ class LSTMRecFunction(torch.autograd.Function):
         dout = dout.contiguous().float()
         grads = [None] * (4 * L)
         dX_up = None
-        orig_of, colp_of = _dg_perm(H, dev)
+        orig_of, colp_of = _dg_perm2(dev) if gen2 else _dg_perm(H, dev)
         main, side = torch.cuda.current_stream(), _side_stream(dev)
         keep = []        # tensors read on the side stream stay referenced until the join (no early reuse of their memory)
         for l in reversed(range(L)):
@@ -241,9 +282,20 @@ class LSTMRecFunction(torch.autograd.Function):
             dG = torch.empty(W * Bp, 4 * H, dtype=torch.bfloat16, device=dev)   # gate columns permuted (see _dg_perm)
             keep.append(dG)
             keep.append(A[l])       # read by the side-stream weight-gradient GEMM after autograd has released the saved tensors
-            call("b200med_lstm_rec_bwd", _raw(Gact[l].data_ptr()), _raw(Cs[l].data_ptr()), _raw(Whh[l].data_ptr()),
-                 _raw(dout.data_ptr() if top else 0), _raw(0 if top else dX_up.data_ptr()), 0 if top else inp[l + 1],
-                 _raw(dG.data_ptr()), B, Bp, W, H, 0.0 if top else drop_p, _raw(seed_ptr), l * W * Bp * H, st)
+            if gen2:
+                # one launch: dG_t, dh_{t-1} AND dX_t = dG_t W_ih (csrc/lstm_rec2.cu); dX leaves in the layout its consumer reads
+                # (row-block-interleaved for the recurrence of the layer below, row-major for the unpack into [B, F, W])
+                wt = torch.empty(Kp[l], 4 * H, dtype=torch.bfloat16, device=dev)
+                call("b200med_lstm_pack_weights2_bwd", _raw(Wih[l].contiguous().data_ptr()), _raw(Whh[l].contiguous().data_ptr()),
+                     ins[l], inp[l], _raw(wt.data_ptr()), _raw(0), st)
+                dX = torch.empty(W * Bp, inp[l], dtype=torch.float32, device=dev)
+                call("b200med_lstm_rec2_bwd", _raw(Gact[l].data_ptr()), _raw(Cs[l].data_ptr()), _raw(wt.data_ptr()), inp[l],
+                     _raw(dout.data_ptr() if top else 0), _raw(0 if top else dX_up.data_ptr()), _raw(dG.data_ptr()),
+                     _raw(dX.data_ptr()), B, Bp, W, 0.0 if top else drop_p, _raw(seed_ptr), l * W * Bp * H, st)
+            else:
+                call("b200med_lstm_rec_bwd", _raw(Gact[l].data_ptr()), _raw(Cs[l].data_ptr()), _raw(Whh[l].data_ptr()),
+                     _raw(dout.data_ptr() if top else 0), _raw(0 if top else dX_up.data_ptr()), 0 if top else inp[l + 1],
+                     _raw(dG.data_ptr()), B, Bp, W, H, 0.0 if top else drop_p, _raw(seed_ptr), l * W * Bp * H, st)
             # The weight / bias gradients of this layer are off the critical path (dG_l -> dX_l -> recurrence of layer l-1):
             # they run on a side stream, next to the next recurrence kernel which only fills 64 of the 148 SMs.
             side.wait_stream(main)
@@ -252,13 +304,23 @@ class LSTMRecFunction(torch.autograd.Function):
                 tiles = ((4 * H + 127) // 128) * ((Kp[l] + 255) // 256)
                 dW = ops.gemm_bf16(dG, A[l].view(W * Bp, Kp[l]), 4 * H, Kp[l], W * Bp, False, False,
                                    out_dtype=torch.float32, split_k=_split_k(tiles, (W * Bp + 63) // 64))
-                db = ops.colsum(dG).index_select(0, colp_of)
-                dW = dW.index_select(0, colp_of)
-                grads[4 * l] = dW[:, :ins[l]].contiguous()
-                grads[4 * l + 1] = dW[:, inp[l]:inp[l] + H].contiguous()
-                grads[4 * l + 2] = db
-                grads[4 * l + 3] = db.clone()
-            if l > 0 or ctx.needs_input_grad[0]:
+                dbp = ops.colsum(dG)
+                if gen2:      # one kernel: un-permute the gate rows, split [x | h] columns, both bias gradients
+                    gw = [torch.empty(4 * H, ins[l], dtype=torch.float32, device=dev), torch.empty(4 * H, H, dtype=torch.float32, device=dev),
+                          torch.empty(4 * H, dtype=torch.float32, device=dev), torch.empty(4 * H, dtype=torch.float32, device=dev)]
+                    call("b200med_lstm_unpack_grads2", _raw(dW.data_ptr()), _raw(dbp.data_ptr()), ins[l], inp[l], _raw(gw[0].data_ptr()),
+                         _raw(gw[1].data_ptr()), _raw(gw[2].data_ptr()), _raw(gw[3].data_ptr()), _stream())
+                    grads[4 * l:4 * l + 4] = gw
+                else:
+                    db = dbp.index_select(0, colp_of)
+                    dW = dW.index_select(0, colp_of)
+                    grads[4 * l] = dW[:, :ins[l]].contiguous()
+                    grads[4 * l + 1] = dW[:, inp[l]:inp[l] + H].contiguous()
+                    grads[4 * l + 2] = db
+                    grads[4 * l + 3] = db.clone()
+            if gen2:
+                dX_up = dX
+            elif l > 0 or ctx.needs_input_grad[0]:
                 # dX [W*Bp, inp] = dG [W*Bp, 4H] * W_ih [4H, inp]   (B operand MN-major); interleaved rows for the layer
                 # below's recurrence kernel, row-major for the unpack into [B, F, W]
                 dX_up = ops.gemm_bf16(dG, Wih[l].index_select(0, orig_of), W * Bp, inp[l], 4 * H, True, False,

@@ -43,8 +43,8 @@ ERROR_COLUMNS = {"No Error": 0, "Out_Of_View": 1, "Multiple_Attempts": 2, "Needl
 # =====================================================================================================
 class _BCEFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, labels, pos_weight):
-        r = ops.bce_logits(logits.detach().contiguous().float(), labels.contiguous().float(), pos_weight, want_probs=True)
+    def forward(ctx, logits, labels, pos_weight, out=None):
+        r = ops.bce_logits(logits.detach().contiguous().float(), labels.contiguous().float(), pos_weight, want_probs=True, out=out)
         ctx.save_for_backward(r["dlogits"])
         ctx.shape = logits.shape
         ctx.mark_non_differentiable(r["probs"], r["preds"], r["counts"])
@@ -53,7 +53,7 @@ class _BCEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gl, *_):
         (dl,) = ctx.saved_tensors
-        return (dl * gl).reshape(ctx.shape), None, None
+        return (dl * gl).reshape(ctx.shape), None, None, None
 
 
 class _CEFn(torch.autograd.Function):
@@ -94,9 +94,11 @@ class FusedBCEWithLogitsLoss(nn.Module):
         super().__init__()
         self.pos_weight = None if pos_weight is None else float(pos_weight)
         self.last = None
+        self.static_out = None        # engine.WindowTrainStep: persistent loss / probs / preds / counts buffers the kernel fills
 
     def forward(self, outputs, labels):
-        loss, probs, preds, counts = _BCEFn.apply(outputs, labels, 1.0 if self.pos_weight is None else self.pos_weight)
+        loss, probs, preds, counts = _BCEFn.apply(outputs, labels, 1.0 if self.pos_weight is None else self.pos_weight,
+                                                  self.static_out)
         self.last = (probs, preds, counts)
         return loss
 
@@ -137,8 +139,9 @@ def define_inputs(images, kinematics, feature_extractor, exp_kwargs: dict, devic
     feature axis, permute to [B, F, W] (COG is out of scope, so the permute always happens)."""
     dt = exp_kwargs["data_type"]
     if dt == "multimodal":
+        from ..heads import concat_features
         feats = feature_extractor(images.to(device))
-        inputs = torch.cat((feats.float(), kinematics.to(device)), dim=2).permute(0, 2, 1)
+        inputs = concat_features(feats, kinematics.to(device)).permute(0, 2, 1)
     elif dt == "kinematics":
         inputs = kinematics.permute(0, 2, 1).to(device)
     elif dt == "video":

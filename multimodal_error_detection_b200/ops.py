@@ -305,6 +305,37 @@ def conv_unpack_grad(dfwd, Cout, Cin):
     return dw
 
 
+def concat2(a, b):
+    """[M, Ca] | [M, Cb] -> [M, Ca + Cb] (fp32)."""
+    a = _need(a, torch.float32, "a"); b = _need(b, torch.float32, "b")
+    M, Ca = a.shape
+    Cb = b.shape[1]
+    out = torch.empty(M, Ca + Cb, dtype=torch.float32, device=a.device)
+    call("b200med_concat2", _ptr(a), _ptr(b), _ptr(out), M, Ca, Cb, _stream())
+    return out
+
+
+def slice_cols(x, col0, Cn):
+    x = _need(x, torch.float32, "x")
+    M, ld = x.shape
+    out = torch.empty(M, Cn, dtype=torch.float32, device=x.device)
+    call("b200med_slice_cols", _ptr(x), _ptr(out), M, ld, col0, Cn, _stream())
+    return out
+
+
+def take_rows(src, idx, out=None):
+    """out[i] = src[idx[i]] for a 4-byte dtype (f32 / i32) and int64 indices."""
+    if src.element_size() != 4:
+        raise TypeError("take_rows serves 4-byte element types")
+    src = _need(src, None, "src")
+    idx = _need(idx, torch.int64, "idx")
+    Cn = 1 if src.dim() == 1 else int(src[0].numel())
+    if out is None:
+        out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    call("b200med_take_rows", _ptr(src), _ptr(idx), _ptr(out), idx.numel(), Cn, _stream())
+    return out
+
+
 def transpose_last2(x, B, R, Cn):
     """[B, R, C] -> [B, C, R]"""
     y = torch.empty(B, Cn, R, dtype=torch.float32, device=x.device)
@@ -361,15 +392,20 @@ def _loss_ws(device):
 
 
 def bce_logits(logits, labels, pos_weight=1.0, grad_scale=1.0, want_grad=True, want_probs=False, want_preds=True,
-               counts=None, accumulate=False):
-    """Fused BCE-with-logits: returns dict(loss[1], dlogits, probs, preds, counts[4]=(tn,fp,fn,tp))."""
+               counts=None, accumulate=False, out=None):
+    """Fused BCE-with-logits: returns dict(loss[1], dlogits, probs, preds, counts[4]=(tn,fp,fn,tp)).  ``out``: optional dict of
+    preallocated destination tensors (loss / probs / preds / counts) -- a captured train step lets the kernel write its
+    persistent result buffers directly."""
     logits = _need(logits.reshape(-1), torch.float32, "logits")
     labels = _need(labels.reshape(-1), torch.float32, "labels")
     B, dev = logits.numel(), logits.device
-    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    out = out or {}
+    loss = out.get("loss") if out.get("loss") is not None else torch.empty(1, dtype=torch.float32, device=dev)
     dl = torch.empty(B, dtype=torch.float32, device=dev) if want_grad else None
-    pr = torch.empty(B, dtype=torch.float32, device=dev) if want_probs else None
-    pd = torch.empty(B, dtype=torch.float32, device=dev) if want_preds else None
+    pr = (out.get("probs") if out.get("probs") is not None else torch.empty(B, dtype=torch.float32, device=dev)) if want_probs else None
+    pd = (out.get("preds") if out.get("preds") is not None else torch.empty(B, dtype=torch.float32, device=dev)) if want_preds else None
+    if counts is None:
+        counts = out.get("counts")
     if counts is None:
         counts = torch.zeros(4, dtype=torch.int64, device=dev)
     call("b200med_bce_logits", _ptr(logits), _ptr(labels), B, float(pos_weight), float(grad_scale), _ptr(loss), _ptr(dl),

@@ -317,8 +317,20 @@ def test_checkpoint_interchange(tmp_path):
     assert fe.linear.linear_0.weight.data_ptr() >= opt.flat_param.data_ptr()   # still views of the flat buffer
 
 
-@pytest.mark.parametrize("impl,B,W", [("auto", 700, 16), ("auto", 128, 10), ("auto", 1, 1), ("auto", 333, 3), ("per_step", 700, 16)])
-def test_lstm_stack_bf16_vs_torch(impl, B, W):
+@pytest.fixture(params=[2, 1], ids=["gen2", "gen1"])
+def rec_gen(request):
+    """Both generations of the persistent forward recurrence kernel (lstm_stack.REC_GEN): 2 = 2-CTA clusters with the x-part
+    fused in (the product), 1 = the first-generation kernel behind a separate x-part GEMM."""
+    from multimodal_error_detection_b200 import lstm_stack
+    old = lstm_stack.REC_GEN
+    lstm_stack.REC_GEN = request.param
+    yield request.param
+    lstm_stack.REC_GEN = old
+
+
+@pytest.mark.parametrize("impl,B,W", [("auto", 700, 16), ("auto", 128, 10), ("auto", 1, 1), ("auto", 333, 3), ("auto", 65, 2),
+                                      ("auto", 4000, 5), ("per_step", 700, 16)])
+def test_lstm_stack_bf16_vs_torch(impl, B, W, rec_gen):
     """The b200med LSTM recurrence (persistent tcgen05 recurrence kernels, or per-step gate GEMMs + fused cell
     kernels; forward and backward) against torch's exact-math fp32 nn.LSTM on the same weights: last hidden state and
     every gradient, norm-wise 2e-2 (bf16 bar).  Ragged batch sizes exercise partial 128-row tiles."""
@@ -358,7 +370,7 @@ def test_lstm_stack_bf16_vs_torch(impl, B, W):
     assert torch.equal(h3.detach(), h.detach()) and torch.equal(leaf.grad.transpose(1, 2), xo.grad)
 
 
-def test_lstm_rec_full_size_vs_per_step_path():
+def test_lstm_rec_full_size_vs_per_step_path(rec_gen):
     """BASELINE size (B = 8192 windows, W = 16, 3 layers): the persistent recurrence kernels and the per-step GEMM + cell
     kernels are two independent implementations of the same bf16-operand arithmetic -- last hidden state and every gradient
     agree norm-wise to 1e-2, the persistent path is bit-reproducible run to run, and linearity in the upstream gradient
@@ -391,7 +403,7 @@ def test_lstm_rec_full_size_vs_per_step_path():
     assert all(torch.equal(u, 2.0 * v) for u, v in zip(d[1:], a[1:]))
 
 
-def test_lstm_rec_dropout_and_determinism():
+def test_lstm_rec_dropout_and_determinism(rec_gen):
     """Persistent recurrence with inter-layer dropout: same seed -> bit-identical output and gradients (forward and
     backward regenerate the same mask); another seed -> a different output; p = 0 path differs from p = 0.2."""
     from multimodal_error_detection_b200 import ops
@@ -570,3 +582,48 @@ def test_bench_step_bf16_B8192_vs_fp32_oracle():
             errs[f"{prefix}.{k}"] = float((p.grad.detach().cpu().double() - q.grad.double()).norm() / q.grad.double().norm())
     print("B=8192 bf16 step vs fp32 oracle: loss", lv, ov, "gradient errors", {k: round(v, 5) for k, v in errs.items()})
     assert max(errs.values()) < 2e-2, errs
+
+
+def test_lstm_rec_gen2_matches_gen1_with_dropout():
+    """The two generations of the persistent recurrence share the dropout counter hash and the saved-tensor layouts: with the
+    same seed they draw the SAME masks, so last hidden state, input gradient and every weight gradient agree to bf16 noise
+    (1e-2 norm-wise) -- a wrong mask index or column permutation would show up as O(1) differences.  Also pins the dG column
+    permutation of generation 2 that lstm_stack._dg_perm2 states against the one the packing kernel emits."""
+    import ctypes as C
+    from multimodal_error_detection_b200 import lstm_stack, ops
+    from multimodal_error_detection_b200._lib import call
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    torch.manual_seed(2)
+    for B, W in ((8192, 16), (300, 7)):
+        F, H = 58, 128
+        lstm = torch.nn.LSTM(F, H, num_layers=3, batch_first=True, dropout=0.2).to(DEV)
+        x = torch.randn(B, W, F, device=DEV)
+        gh = torch.randn(B, H, device=DEV)
+        seed = torch.tensor([11], dtype=torch.int32, device=DEV)
+        res = {}
+        old = lstm_stack.REC_GEN
+        try:
+            for gen in (1, 2):
+                lstm_stack.REC_GEN = gen
+                lstm.zero_grad(set_to_none=True)
+                xo = x.clone().requires_grad_(True)
+                h = lstm_stack.lstm_last_hidden(xo.permute(0, 2, 1), lstm, training=True, seed_dev=seed)
+                h.backward(gh)
+                res[gen] = [h.detach().clone(), xo.grad.clone()] + [p.grad.clone() for p in lstm.parameters()]
+        finally:
+            lstm_stack.REC_GEN = old
+        nrel = lambda u, v: float((u - v).norm() / v.norm().clamp_min(1e-12))
+        errs = [nrel(u, v) for u, v in zip(res[2], res[1])]
+        print("gen2 vs gen1", B, W, [round(e, 5) for e in errs])
+        assert max(errs) < 1e-2, errs
+    w_ih, w_hh = lstm.weight_ih_l1.detach().contiguous(), lstm.weight_hh_l1.detach().contiguous()
+    wt = torch.empty(256, 512, dtype=torch.bfloat16, device=DEV)
+    perm = torch.empty(512, dtype=torch.int32, device=DEV)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    call("b200med_lstm_pack_weights2_bwd", P(w_ih), P(w_hh), 128, 128, P(wt), P(perm), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    orig_of, col_of = lstm_stack._dg_perm2(torch.device(DEV))
+    assert torch.equal(perm.long(), orig_of)
+    # wt row nu < 64: column nu of W_ih; 64 <= nu < 128: hidden unit nu - 64 of W_hh (first half); and so on for the second half
+    cat = torch.cat([w_ih[:, :64], w_hh[:, :64], w_ih[:, 64:], w_hh[:, 64:]], dim=1)          # [512, 256] in nu order
+    assert torch.equal(wt.float(), cat.index_select(0, orig_of).t().contiguous().to(torch.bfloat16).float())
