@@ -24,10 +24,24 @@ def fold_path(tmp_path_factory):
     return fixed.write_fold(tmp_path_factory.mktemp("fixed"))
 
 
-def _build(name, W, precision="fp32"):
+_COUNTS = {}
+
+
+def _train_counts(name, fold_path):
+    """Class balance of the TRAINING windows the reference built its criterion from (pos_weight = c0 / c1)."""
+    if name not in _COUNTS:
+        from multimodal_error_detection_b200.dataset import dataset_utils as du
+        Wt, St = cases.FIXED_TRAIN_WS[name]
+        tr, _ = du.retrieve_dataloaders_window(fold_path, cases.FIXED_CASES[name][0], window_size=Wt, stride=St)
+        _COUNTS[name] = tr.dataset.binary_error_distribution
+    return _COUNTS[name]
+
+
+def _build(name, W, precision="fp32", fold_path=None):
     from multimodal_error_detection_b200.modeling import modeling_utils as mu
     kw = dict(cases.FIXED_CASES[name][0], precision=precision)
-    fe, model, crit, opt, sched = mu.define_model_objects(kw, cases.IN_FEATURES, torch.device(DEV), (0.4, 0.6), W)
+    counts = _train_counts(name, fold_path) if fold_path is not None else (0.4, 0.6)
+    fe, model, crit, opt, sched = mu.define_model_objects(kw, cases.IN_FEATURES, torch.device(DEV), counts, W)
     fixed.load_trained(name, fe, model)
     return mu, kw, fe, model, crit
 
@@ -41,7 +55,7 @@ def _test_loader(fold_path, kw, W, S):
 @pytest.mark.parametrize("name", ["lstm_global", "cnn_global"])
 def test_validate_fixed_weights_fp32(name, fold_path):
     for (W, S) in cases.FIXED_CASES[name][1]:
-        mu, kw, fe, model, crit = _build(name, W)
+        mu, kw, fe, model, crit = _build(name, W, fold_path=fold_path)
         te = _test_loader(fold_path, kw, W, S)
         gold = fixed.meta()[name]["val"][f"w{W}_s{S}"]
         v = mu.validate_single_epoch(model, fe, te, crit, DEV, kw)
@@ -66,7 +80,7 @@ def test_validate_fixed_weights_bf16(name, fold_path):
     if not ops.has_tcgen05():
         pytest.skip("needs sm_100")
     for (W, S) in cases.FIXED_CASES[name][1]:
-        mu, kw, fe, model, crit = _build(name, W, "bf16")
+        mu, kw, fe, model, crit = _build(name, W, "bf16", fold_path=fold_path)
         te = _test_loader(fold_path, kw, W, S)
         gold = fixed.meta()[name]["val"][f"w{W}_s{S}"]
         v = mu.validate_single_epoch(model, fe, te, crit, DEV, kw)

@@ -121,7 +121,9 @@ def test_cnn_head_vs_torch(W, B, view):
     assert nrel(gx, xr.grad) < 5e-5
     gmax = max(float(q.grad.abs().max()) for q in ref.parameters())
     for (k, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        scale = max(float(q.grad.abs().max()), 1e-4 * gmax)
+        # gradients that are zero in exact arithmetic (a bias in front of a BatchNorm) are fp32 round-off of sums of O(gmax)
+        # terms on our side and fp64 round-off on the reference's: the comparison scale is floored at 1e-2 of the largest gradient
+        scale = max(float(q.grad.abs().max()), 1e-2 * gmax)
         assert float((p.grad.double().cpu() - q.grad).abs().max()) <= 1e-4 * scale, k
     for (k, b), (k2, c) in zip([kv for kv in model.named_buffers() if "_drop_seed" not in kv[0]], ref.named_buffers()):
         assert k == k2 and nrel(b.double(), c.double()) < 1e-5, k

