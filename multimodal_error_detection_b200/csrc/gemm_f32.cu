@@ -193,6 +193,46 @@ colsum_partial_vec_kernel(const T *__restrict__ x, float *__restrict__ part, lon
     }
 }
 
+// Flat variant for N / V a power of two <= 256: the 256 threads of a block tile (256 / lpr) rows x lpr column groups per pass
+// (lpr = N / V), so that narrow matrices (N = 32) keep every lane busy; 4 passes of 16-byte loads in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_partial_flat_kernel(const T *__restrict__ x, float *__restrict__ part, long long M, int N, long long ld,
+                           long long rows_per_slab) {
+    constexpr int V = 16 / sizeof(T);
+    __shared__ float sh[256][V + 1];
+    const int lpr = N / V;                      // column groups (threads) per row
+    const int rpp = 256 / lpr;                  // rows per pass
+    const int cg = threadIdx.x % lpr, r0 = threadIdx.x / lpr;
+    const long long m0 = (long long)blockIdx.x * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
+    float s[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = 0.0f;
+#pragma unroll 4
+    for (long long m = m0 + r0; m < m1; m += rpp) {
+        const uint4 u = ldg_stream_u4(reinterpret_cast<const uint4 *>(x + m * ld + cg * V));
+        if constexpr (sizeof(T) == 2) {
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s[2 * j] += __uint_as_float(w[j] << 16);
+                s[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+            }
+        } else {
+            s[0] += __uint_as_float(u.x); s[1] += __uint_as_float(u.y); s[2] += __uint_as_float(u.z); s[3] += __uint_as_float(u.w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) sh[threadIdx.x][j] = s[j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < N; c += 256) {        // fixed order over the block's row lanes: deterministic
+        const int g = c / V, j = c - g * V;
+        float t = 0.0f;
+        for (int r = 0; r < rpp; ++r) t += sh[r * lpr + g][j];
+        part[(long long)blockIdx.x * N + c] = t;
+    }
+}
+
 // out[e] = sum_z part[z*n + e] in a fixed order: 8 strided partial sums per column (z = r, r+8, ...) added r = 0..7.
 __global__ void __launch_bounds__(256)
 slab_reduce8_kernel(const float *__restrict__ part, float *__restrict__ out, int n, int slabs) {
@@ -231,6 +271,12 @@ static long long weight_slabs(long long M, long long N, long long K) {
     if (s > max_by_rows) s = max_by_rows;
     if (s < 1) s = 1;
     if (s > 128) s = 128;
+    return s;
+}
+static long long colsum_slabs_flat(long long M) {
+    long long s = (M + 255) / 256;       // >= 256 rows per slab
+    if (s < 1) s = 1;
+    if (s > 592) s = 592;                // 4 CTAs on each of the 148 SMs
     return s;
 }
 static long long colsum_slabs(long long M) {
@@ -340,7 +386,10 @@ extern "C" __attribute__((visibility("default"))) int b200med_linear_bwd_weight_
     return B200MED_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int64_t b200med_colsum_ws_bytes(int64_t M, int32_t N) { return colsum_slabs(M) * (long long)N * 4 + 256; }
+extern "C" __attribute__((visibility("default"))) int64_t b200med_colsum_ws_bytes(int64_t M, int32_t N) {
+    const long long s = colsum_slabs(M) > colsum_slabs_flat(M) ? colsum_slabs(M) : colsum_slabs_flat(M);
+    return s * (long long)N * 4 + 256;
+}
 
 extern "C" __attribute__((visibility("default"))) int b200med_colsum(const void *dy, int32_t dtype, float *db, int64_t M, int32_t N, int64_t ld,
                               void *workspace, void *stream) {
@@ -351,6 +400,19 @@ extern "C" __attribute__((visibility("default"))) int b200med_colsum(const void 
     const int cs = (int)colsum_slabs(M);
     const long long rows = (M + cs - 1) / cs;
     const int V = dtype == B200MED_F32 ? 4 : 8;
+    const int lpr = N % V == 0 ? N / V : 0;
+    if (lpr >= 1 && lpr <= 256 && (lpr & (lpr - 1)) == 0 && ld % V == 0 && (uintptr_t)dy % 16 == 0 && M >= 4096) {
+        // large matrices: flat kernel, ~4 CTAs per SM worth of row slabs (the workspace holds up to colsum_slabs_flat() slabs)
+        const int slabs = (int)colsum_slabs_flat(M);
+        const long long rps = (M + slabs - 1) / slabs;
+        if (dtype == B200MED_F32)
+            colsum_partial_flat_kernel<float><<<slabs, 256, 0, st>>>(reinterpret_cast<const float *>(dy), cpart, M, N, ld, rps);
+        else
+            colsum_partial_flat_kernel<__nv_bfloat16><<<slabs, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rps);
+        if (int e = after_launch("colsum_partial_flat_kernel")) return e;
+        slab_reduce8_kernel<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(cpart, db, N, slabs);
+        return after_launch("slab_reduce8_kernel");
+    }
     if (N % V == 0 && ld % V == 0 && (uintptr_t)dy % 16 == 0) {
         dim3 grid((unsigned)((N + 32 * V - 1) / (32 * V)), (unsigned)cs);
         if (dtype == B200MED_F32)

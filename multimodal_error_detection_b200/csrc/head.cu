@@ -29,46 +29,93 @@ __device__ __forceinline__ bool head_keep(uint32_t seed, unsigned long long inde
     return u >= p;
 }
 
-// part [S][3][C] = (n, mean, M2) of every row slab
+// ---- BatchNorm: three launches per direction -- vectorised per-slab partials, a tiny per-column finalize, an elementwise
+// apply.  V = columns per thread (4 when C % 4 == 0: 16-byte accesses, 128 columns per warp row; else 1).
+
+template <int V> struct BnVec;
+template <> struct BnVec<4> {
+    __device__ static void load(const float *p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4 *>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    __device__ static void store(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct BnVec<1> {
+    __device__ static void load(const float *p, float (&v)[1]) { v[0] = *p; }
+    __device__ static void store(float *p, const float (&v)[1]) { *p = v[0]; }
+};
+
+// part [S][3][C] = (n, mean, M2) of every row slab (local two-pass; the slab is re-read from L1 / L2)
+template <int V>
 __global__ void __launch_bounds__(kBnCols * kBnWarps)
-bn_stats_partial_kernel(const float *__restrict__ x, long long ld, long long M, int C, long long rows_per_slab,
-                        float *__restrict__ part) {
-    __shared__ double sh[kBnWarps][kBnCols];
-    __shared__ float sh_mean[kBnCols];
+bn_stats_partial_kernel(const float *__restrict__ x, long long M, int C, long long rows_per_slab, float *__restrict__ part) {
+    __shared__ double sh[kBnWarps][kBnCols * V];
+    __shared__ float sh_mean[kBnCols * V];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int col = blockIdx.x * kBnCols + lane;
+    const int col = (blockIdx.x * kBnCols + lane) * V;
     const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
     const bool ok = col < C;
-    float s = 0.0f;
-    if (ok) for (long long m = m0 + w; m < m1; m += kBnWarps) s += x[m * ld + col];
-    sh[w][lane] = (double)s;
+    float s[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = 0.0f;
+    if (ok) {
+#pragma unroll 4
+        for (long long m = m0 + w; m < m1; m += kBnWarps) {
+            float v[V];
+            BnVec<V>::load(x + m * C + col, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) s[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) sh[w][lane * V + j] = (double)s[j];
     __syncthreads();
     if (w == 0) {
-        double t = 0.0;
 #pragma unroll
-        for (int r = 0; r < kBnWarps; ++r) t += sh[r][lane];
-        sh_mean[lane] = (float)(t / (double)max(1LL, m1 - m0));
+        for (int j = 0; j < V; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < kBnWarps; ++r) t += sh[r][lane * V + j];
+            sh_mean[lane * V + j] = (float)(t / (double)max(1LL, m1 - m0));
+        }
     }
     __syncthreads();
-    const float mu = sh_mean[lane];
-    float q = 0.0f;
-    if (ok) for (long long m = m0 + w; m < m1; m += kBnWarps) { const float d = x[m * ld + col] - mu; q = fmaf(d, d, q); }
+    float mu[V], q[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { mu[j] = sh_mean[lane * V + j]; q[j] = 0.0f; }
+    if (ok) {
+#pragma unroll 4
+        for (long long m = m0 + w; m < m1; m += kBnWarps) {
+            float v[V];
+            BnVec<V>::load(x + m * C + col, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) { const float d = v[j] - mu[j]; q[j] = fmaf(d, d, q[j]); }
+        }
+    }
     __syncthreads();
-    sh[w][lane] = (double)q;
+#pragma unroll
+    for (int j = 0; j < V; ++j) sh[w][lane * V + j] = (double)q[j];
     __syncthreads();
     if (w == 0 && ok) {
-        double t = 0.0;
-#pragma unroll
-        for (int r = 0; r < kBnWarps; ++r) t += sh[r][lane];
         float *p = part + (long long)blockIdx.y * 3 * C;
-        p[col] = (float)(m1 - m0);
-        p[C + col] = mu;
-        p[2 * C + col] = (float)t;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < kBnWarps; ++r) t += sh[r][lane * V + j];
+            p[col + j] = (float)(m1 - m0);
+            p[C + col + j] = mu[j];
+            p[2 * C + col + j] = (float)t;
+        }
     }
 }
 
-// Combine the slab partials of one column (Chan et al.), ascending slab order, in double.
-__device__ __forceinline__ void bn_combine(const float *__restrict__ part, int S, int C, int col, double &mean, double &m2) {
+// Per column: combine the slab partials (Chan et al., ascending slab order, double) -> scale / shift of the normalisation,
+// save_mean / save_rstd for the backward, running statistics (momentum, unbiased variance) like nn.BatchNorm1d in training mode.
+__global__ void bn_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, float eps, float momentum, float *__restrict__ scale_shift,
+                                   float *__restrict__ save_mean, float *__restrict__ save_rstd, float *__restrict__ running_mean,
+                                   float *__restrict__ running_var, long long *__restrict__ num_batches) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col == 0 && num_batches) *num_batches += 1;
+    if (col >= C) return;
     double n = 0.0, mu = 0.0, q = 0.0;
     for (int s = 0; s < S; ++s) {
         const float *p = part + (long long)s * 3 * C;
@@ -79,44 +126,34 @@ __device__ __forceinline__ void bn_combine(const float *__restrict__ part, int S
         q += qs + d * d * n * ns / tot;
         n = tot;
     }
-    mean = mu; m2 = q;
+    const double var = q / (double)M;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[col] : 1.0f, b = beta ? beta[col] : 0.0f;
+    scale_shift[col] = rstd * g;
+    scale_shift[C + col] = b - (float)mu * rstd * g;
+    save_mean[col] = (float)mu;
+    save_rstd[col] = rstd;
+    if (running_mean) {
+        const double unbiased = M > 1 ? q / (double)(M - 1) : var;
+        running_mean[col] = (1.0f - momentum) * running_mean[col] + momentum * (float)mu;
+        running_var[col] = (1.0f - momentum) * running_var[col] + momentum * (float)unbiased;
+    }
 }
 
-// y = (x - mean) * rstd * gamma + beta with the batch statistics; the CTAs of row slab 0 also publish save_mean / save_rstd
-// and update the running statistics (momentum, unbiased variance) like nn.BatchNorm1d in training mode.
-__global__ void __launch_bounds__(kBnCols * kBnWarps)
-bn_apply_kernel(const float *__restrict__ x, long long ld, long long M, int C, long long rows_per_slab,
-                const float *__restrict__ part, int S, const float *__restrict__ gamma, const float *__restrict__ beta,
-                float eps, float momentum, float *__restrict__ y, long long ldy, float *__restrict__ save_mean,
-                float *__restrict__ save_rstd, float *__restrict__ running_mean, float *__restrict__ running_var,
-                long long *__restrict__ num_batches) {
-    __shared__ float sh_scale[kBnCols], sh_shift[kBnCols];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int col = blockIdx.x * kBnCols + lane;
-    if (w == 0 && col < C) {
-        double mean, m2;
-        bn_combine(part, S, C, col, mean, m2);
-        const double var = m2 / (double)M;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        const float g = gamma ? gamma[col] : 1.0f, b = beta ? beta[col] : 0.0f;
-        sh_scale[lane] = rstd * g;
-        sh_shift[lane] = b - (float)mean * rstd * g;
-        if (blockIdx.y == 0) {
-            save_mean[col] = (float)mean;
-            save_rstd[col] = rstd;
-            if (running_mean) {
-                const double unbiased = M > 1 ? m2 / (double)(M - 1) : var;
-                running_mean[col] = (1.0f - momentum) * running_mean[col] + momentum * (float)mean;
-                running_var[col] = (1.0f - momentum) * running_var[col] + momentum * (float)unbiased;
-            }
-        }
+// y = x * scale[c] + shift[c], elementwise (grid-stride, 16-byte accesses when V = 4)
+template <int V>
+__global__ void bn_apply_kernel(const float *__restrict__ x, long long M, int C, const float *__restrict__ scale_shift,
+                                float *__restrict__ y) {
+    const long long total = M * C / V;
+    const int cv = C / V;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cv) * V;
+        float v[V], o[V];
+        BnVec<V>::load(x + e * V, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = fmaf(v[j], __ldg(scale_shift + c + j), __ldg(scale_shift + C + c + j));
+        BnVec<V>::store(y + e * V, o);
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && num_batches) *num_batches += 1;
-    __syncthreads();
-    if (col >= C) return;
-    const float sc = sh_scale[lane], sf = sh_shift[lane];
-    const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
-    for (long long m = m0 + w; m < m1; m += kBnWarps) y[m * ldy + col] = fmaf(x[m * ld + col], sc, sf);
 }
 
 // inference: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta
@@ -133,60 +170,82 @@ __global__ void bn_eval_kernel(const float *__restrict__ x, long long M, int C, 
 }
 
 // part [S][2][C] = (sum dy, sum dy * xhat) per slab
+template <int V>
 __global__ void __launch_bounds__(kBnCols * kBnWarps)
 bn_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x, long long M, int C, long long rows_per_slab,
                       const float *__restrict__ save_mean, const float *__restrict__ save_rstd, float *__restrict__ part) {
-    __shared__ float sh[2][kBnWarps][kBnCols];
+    __shared__ float sh[2][kBnWarps][kBnCols * V];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int col = blockIdx.x * kBnCols + lane;
+    const int col = (blockIdx.x * kBnCols + lane) * V;
     const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
-    float a = 0.0f, b = 0.0f;
+    float a[V], b[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { a[j] = 0.0f; b[j] = 0.0f; }
     if (col < C) {
-        const float mu = save_mean[col], rs = save_rstd[col];
+        float mu[V], rs[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) { mu[j] = save_mean[col + j]; rs[j] = save_rstd[col + j]; }
+#pragma unroll 4
         for (long long m = m0 + w; m < m1; m += kBnWarps) {
-            const float g = dy[m * C + col];
-            a += g;
-            b = fmaf(g, (x[m * C + col] - mu) * rs, b);
+            float g[V], xv[V];
+            BnVec<V>::load(dy + m * C + col, g);
+            BnVec<V>::load(x + m * C + col, xv);
+#pragma unroll
+            for (int j = 0; j < V; ++j) { a[j] += g[j]; b[j] = fmaf(g[j], (xv[j] - mu[j]) * rs[j], b[j]); }
         }
     }
-    sh[0][w][lane] = a; sh[1][w][lane] = b;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { sh[0][w][lane * V + j] = a[j]; sh[1][w][lane * V + j] = b[j]; }
     __syncthreads();
     if (w == 0 && col < C) {
-        float ta = 0.0f, tb = 0.0f;
-#pragma unroll
-        for (int r = 0; r < kBnWarps; ++r) { ta += sh[0][r][lane]; tb += sh[1][r][lane]; }
         float *p = part + (long long)blockIdx.y * 2 * C;
-        p[col] = ta; p[C + col] = tb;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float ta = 0.0f, tb = 0.0f;
+#pragma unroll
+            for (int r = 0; r < kBnWarps; ++r) { ta += sh[0][r][lane * V + j]; tb += sh[1][r][lane * V + j]; }
+            p[col + j] = ta; p[C + col + j] = tb;
+        }
     }
 }
 
-// dx = gamma * rstd * (dy - mean(dy) - xhat * mean(dy * xhat)); relu_mask: multiplied by (x > 0) -- the ReLU that sits between
-// the Linear layer and this BatchNorm in the reference heads (x is that ReLU's output).
-__global__ void __launch_bounds__(kBnCols * kBnWarps)
-bn_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, long long M, int C, long long rows_per_slab,
-                    const float *__restrict__ part, int S, const float *__restrict__ save_mean,
-                    const float *__restrict__ save_rstd, const float *__restrict__ gamma, int relu_mask,
-                    float *__restrict__ dx, float *__restrict__ dgamma, float *__restrict__ dbeta) {
-    __shared__ float sh_a[kBnCols], sh_b[kBnCols];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int col = blockIdx.x * kBnCols + lane;
-    if (w == 0 && col < C) {
-        double sa = 0.0, sb = 0.0;
-        for (int s = 0; s < S; ++s) { sa += part[(long long)s * 2 * C + col]; sb += part[(long long)s * 2 * C + C + col]; }
-        if (blockIdx.y == 0) { if (dbeta) dbeta[col] = (float)sa; if (dgamma) dgamma[col] = (float)sb; }
-        sh_a[lane] = (float)(sa / (double)M);
-        sh_b[lane] = (float)(sb / (double)M);
-    }
-    __syncthreads();
+// Per column: dgamma = sum dy xhat, dbeta = sum dy, and the three coefficients of dx = k0 * dy - k1 - k2 * x
+// (k0 = gamma rstd, k1 = k0 (mean(dy) - mu rstd mean(dy xhat)), k2 = k0 rstd mean(dy xhat)).
+__global__ void bn_bwd_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, const float *__restrict__ gamma,
+                                       const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
+                                       float *__restrict__ coef, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= C) return;
-    const float mu = save_mean[col], rs = save_rstd[col], g = (gamma ? gamma[col] : 1.0f) * rs;
-    const float ma = sh_a[lane], mb = sh_b[lane];
-    const long long m0 = (long long)blockIdx.y * rows_per_slab, m1 = min(M, m0 + rows_per_slab);
-    for (long long m = m0 + w; m < m1; m += kBnWarps) {
-        const float xv = x[m * C + col];
-        float v = g * (dy[m * C + col] - ma - (xv - mu) * rs * mb);
-        if (relu_mask && !(xv > 0.0f)) v = 0.0f;
-        dx[m * C + col] = v;
+    double sa = 0.0, sb = 0.0;
+    for (int s = 0; s < S; ++s) { sa += part[(long long)s * 2 * C + col]; sb += part[(long long)s * 2 * C + C + col]; }
+    if (dbeta) dbeta[col] = (float)sa;
+    if (dgamma) dgamma[col] = (float)sb;
+    const float mu = save_mean[col], rs = save_rstd[col], k0 = (gamma ? gamma[col] : 1.0f) * rs;
+    const float ma = (float)(sa / (double)M), mb = (float)(sb / (double)M);
+    coef[col] = k0;
+    coef[C + col] = k0 * (ma - mu * rs * mb);
+    coef[2 * C + col] = k0 * rs * mb;
+}
+
+// dx = k0 dy - k1 - k2 x; relu_mask: zeroed where x <= 0 -- the ReLU that sits between the Linear layer and this BatchNorm in
+// the reference heads (x is that ReLU's output).
+template <int V>
+__global__ void bn_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, long long M, int C,
+                                    const float *__restrict__ coef, int relu_mask, float *__restrict__ dx) {
+    const long long total = M * C / V;
+    const int cv = C / V;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % cv) * V;
+        float g[V], xv[V], o[V];
+        BnVec<V>::load(dy + e * V, g);
+        BnVec<V>::load(x + e * V, xv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float v = fmaf(__ldg(coef + c + j), g[j], -__ldg(coef + C + c + j)) - __ldg(coef + 2 * C + c + j) * xv[j];
+            if (relu_mask && !(xv[j] > 0.0f)) v = 0.0f;
+            o[j] = v;
+        }
+        BnVec<V>::store(dx + e * V, o);
     }
 }
 
@@ -312,7 +371,7 @@ static unsigned ew_grid(long long total) {
 
 using namespace b200med;
 
-extern "C" __attribute__((visibility("default"))) int64_t b200med_bn_ws_bytes(int64_t M, int32_t C) { return bn_slabs(M) * 3 * (int64_t)C * 4 + 256; }
+extern "C" __attribute__((visibility("default"))) int64_t b200med_bn_ws_bytes(int64_t M, int32_t C) { return (bn_slabs(M) * 3 + 3) * (int64_t)C * 4 + 256; }
 
 extern "C" __attribute__((visibility("default"))) int b200med_bn_fwd(const float *x, int64_t M, int32_t C, const float *gamma, const float *beta,
                                float eps, float momentum, int32_t training, float *running_mean, float *running_var,
@@ -329,12 +388,19 @@ extern "C" __attribute__((visibility("default"))) int b200med_bn_fwd(const float
     B200MED_REQUIRE(save_mean && save_rstd && workspace, "training needs save_mean, save_rstd and a workspace");
     const int S = (int)bn_slabs(M);
     const long long rows = (M + S - 1) / S;
-    dim3 grid((unsigned)((C + kBnCols - 1) / kBnCols), (unsigned)S);
     float *part = reinterpret_cast<float *>(workspace);
-    bn_stats_partial_kernel<<<grid, kBnCols * kBnWarps, 0, st>>>(x, C, M, C, rows, part);
+    float *scale_shift = part + (long long)S * 3 * C;
+    const bool vec = C % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+    const int V = vec ? 4 : 1;
+    dim3 grid((unsigned)((C + kBnCols * V - 1) / (kBnCols * V)), (unsigned)S);
+    if (vec) bn_stats_partial_kernel<4><<<grid, kBnCols * kBnWarps, 0, st>>>(x, M, C, rows, part);
+    else bn_stats_partial_kernel<1><<<grid, kBnCols * kBnWarps, 0, st>>>(x, M, C, rows, part);
     if (int e = after_launch("bn_stats_partial_kernel")) return e;
-    bn_apply_kernel<<<grid, kBnCols * kBnWarps, 0, st>>>(x, C, M, C, rows, part, S, gamma, beta, eps, momentum, y, C, save_mean,
-                                                         save_rstd, running_mean, running_var, (long long *)num_batches_tracked);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, S, M, C, gamma, beta, eps, momentum, scale_shift, save_mean, save_rstd,
+                                                      running_mean, running_var, (long long *)num_batches_tracked);
+    if (int e = after_launch("bn_finalize_kernel")) return e;
+    if (vec) bn_apply_kernel<4><<<ew_grid(M * C / 4), 256, 0, st>>>(x, M, C, scale_shift, y);
+    else bn_apply_kernel<1><<<ew_grid(M * C), 256, 0, st>>>(x, M, C, scale_shift, y);
     return after_launch("bn_apply_kernel");
 }
 
@@ -346,12 +412,18 @@ extern "C" __attribute__((visibility("default"))) int b200med_bn_bwd(const float
     cudaStream_t st = (cudaStream_t)stream;
     const int S = (int)bn_slabs(M);
     const long long rows = (M + S - 1) / S;
-    dim3 grid((unsigned)((C + kBnCols - 1) / kBnCols), (unsigned)S);
     float *part = reinterpret_cast<float *>(workspace);
-    bn_bwd_partial_kernel<<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, save_mean, save_rstd, part);
+    float *coef = part + (long long)S * 3 * C;
+    const bool vec = C % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0);
+    const int V = vec ? 4 : 1;
+    dim3 grid((unsigned)((C + kBnCols * V - 1) / (kBnCols * V)), (unsigned)S);
+    if (vec) bn_bwd_partial_kernel<4><<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, save_mean, save_rstd, part);
+    else bn_bwd_partial_kernel<1><<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, save_mean, save_rstd, part);
     if (int e = after_launch("bn_bwd_partial_kernel")) return e;
-    bn_bwd_apply_kernel<<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, part, S, save_mean, save_rstd, gamma, relu_mask, dx,
-                                                             dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, S, M, C, gamma, save_mean, save_rstd, coef, dgamma, dbeta);
+    if (int e = after_launch("bn_bwd_finalize_kernel")) return e;
+    if (vec) bn_bwd_apply_kernel<4><<<ew_grid(M * C / 4), 256, 0, st>>>(dy, x, M, C, coef, relu_mask, dx);
+    else bn_bwd_apply_kernel<1><<<ew_grid(M * C), 256, 0, st>>>(dy, x, M, C, coef, relu_mask, dx);
     return after_launch("bn_bwd_apply_kernel");
 }
 

@@ -105,10 +105,10 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     uint64_t *x_full = bars + 1;         // [2] leader: expect_tx + peer arrive
     uint64_t *x_free = bars + 3;         // [2] tcgen05.commit multicast: the x-part MMAs have read the tile
     uint64_t *acc_full = bars + 5;       // [2] tcgen05.commit multicast: gates of a step are complete
-    uint64_t *h_ready = bars + 7;        // [2] leader: the 16 epilogue warps of BOTH CTAs have published h_t
-    uint64_t *h_local = bars + 9;        // [2] the 16 epilogue warps of this CTA have published h_t / dropout(h_t)
-    uint64_t *tile_free = bars + 11;     // [2] the TMA stores of the h / u tiles of two steps ago have read them
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 13);
+    uint64_t *h_ready = bars + 7;        // [2 buffers][2 halves] leader: the 16 epilogue warps of BOTH CTAs have published that half of h_t
+    uint64_t *h_local = bars + 11;       // [2] the 16 epilogue warps of this CTA have published h_t / dropout(h_t)
+    uint64_t *tile_free = bars + 13;     // [2] the TMA stores of the h / u tiles of two steps ago have read them
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -120,7 +120,8 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         bar_init(w_full, 2);
         for (int i = 0; i < 2; ++i) {
             bar_init(&x_full[i], 2); bar_init(&x_free[i], 1); bar_init(&acc_full[i], 1);
-            bar_init(&h_ready[i], 2 * kR2EpiWarps); bar_init(&h_local[i], kR2EpiWarps); bar_init(&tile_free[i], 1);
+            bar_init(&h_ready[2 * i], 2 * kR2EpiWarps); bar_init(&h_ready[2 * i + 1], 2 * kR2EpiWarps);
+            bar_init(&h_local[i], kR2EpiWarps); bar_init(&tile_free[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -157,7 +158,7 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             };
             auto x_part = [&](int t) {          // leader: gates_t (buffer t & 1) = x_t W_ih^T
                 const int b = t & 1;
-                bar_wait_cluster(&x_full[b], (uint32_t)((t >> 1) & 1));
+                bar_wait(&x_full[b], (uint32_t)((t >> 1) & 1));
                 tcgen05_fence_after();
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
@@ -171,52 +172,59 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                         }
                 umma_commit_pair(&x_free[b]);
             };
-            auto h_part = [&](int t) {          // leader: gates_t += h_{t-1} W_hh^T
+            // leader: gates_t += h_{t-1} W_hh^T, K-steps of hidden units [32 half, 32 half + 32) of both unit blocks: the cell math
+            // publishes h in two halves (chunk 0 = units 0..31 of each block, chunk 1 = 32..63), so the first half of the K loop
+            // runs UNDER the second half of the cell math
+            auto h_part = [&](int t, int half) {
                 const int b = t & 1, hb = (t - 1) & 1;
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k2 = 0; k2 < 2; ++k2) {
+                            const int k = half * 2 + k2;
                             const uint64_t da = make_smem_desc(ha + hb * S::kHTile + kb * 8192 + k * 32, 16, 1024);
                             const uint64_t db = make_smem_desc(wa + (KXB + kb) * 32768 + j * 16384 + k * 32, 16, 1024);
                             umma_bf16_pair(tmem_base + (uint32_t)(b * 256 + j * 128), da, db, idesc, 1u);
                         }
-                umma_commit_pair(&acc_full[b]);
+                if (half == 1) umma_commit_pair(&acc_full[b]);
             };
             load_x(0);
             if (W > 1) load_x(1);
             if (leader) {
-                bar_wait_cluster(w_full, 0);
+                bar_wait(w_full, 0);
                 x_part(0);
                 umma_commit_pair(&acc_full[0]);          // h_{-1} = 0: the gates of step 0 are the x-part alone
                 if (W > 1) x_part(1);
             }
-            if (W > 2) { bar_wait_cluster(&x_free[0], 0); load_x(2); }
+            if (W > 2) { bar_wait(&x_free[0], 0); load_x(2); }
             for (int t = 0; t < W; ++t) {
                 const int b = t & 1;
                 const uint32_t par = (uint32_t)((t >> 1) & 1);
-                bar_wait(&h_local[b], par);              // this CTA's h_t / dropout(h_t) tiles are complete (and fenced)
-                if ((kSave && t + 1 < W) || kUp) {
-                    if (kSave && t + 1 < W) {
-                        tma_store_3d(&tmap_a, h_sm + b * S::kHTile, p.kx, m0, t + 1);
-                        tma_store_3d(&tmap_a, h_sm + b * S::kHTile + 8192, p.kx + 64, m0, t + 1);
-                    }
-                    if (kUp) {
-                        tma_store_3d(&tmap_up, u_sm + b * S::kHTile, 0, m0, t);
-                        tma_store_3d(&tmap_up, u_sm + b * S::kHTile + 8192, 64, m0, t);
-                    }
+                // critical path first: the h-part MMAs of step t+1 wait for nothing but h_t (both CTAs) ...
+                if (leader && t + 1 < W) {
+                    bar_wait(&h_ready[2 * b], par);      // both CTAs: first half of h_t published
+                    tcgen05_fence_after();
+                    h_part(t + 1, 0);
+                    bar_wait(&h_ready[2 * b + 1], par);  // second half published, TMEM buffer b drained
+                    tcgen05_fence_after();
+                    h_part(t + 1, 1);
+                }
+                // ... then this CTA's h_t / dropout(h_t) tiles leave for HBM (they are complete and fenced: h_local)
+                bar_wait(&h_local[b], par);
+                if (kSave && t + 1 < W) {
+                    tma_store_3d(&tmap_a, h_sm + b * S::kHTile, p.kx, m0, t + 1);
+                    tma_store_3d(&tmap_a, h_sm + b * S::kHTile + 8192, p.kx + 64, m0, t + 1);
+                }
+                if (kUp) {
+                    tma_store_3d(&tmap_up, u_sm + b * S::kHTile, 0, m0, t);
+                    tma_store_3d(&tmap_up, u_sm + b * S::kHTile + 8192, 64, m0, t);
                 }
                 bulk_commit();
-                if (leader && t + 1 < W) {
-                    bar_wait_cluster(&h_ready[b], par);  // both CTAs: h_t published, TMEM buffer b drained
-                    tcgen05_fence_after();
-                    h_part(t + 1);
-                    if (t + 2 < W) x_part(t + 2);        // runs under the cell math of step t+1
-                }
+                if (leader && t + 2 < W) x_part(t + 2);  // runs under the cell math of step t+1
                 if (t + 3 < W) {                          // x tile of step t+3 into the buffer the x-part of step t+1 has read
-                    bar_wait_cluster(&x_free[(t + 1) & 1], (uint32_t)(((t + 1) >> 1) & 1));
+                    bar_wait(&x_free[(t + 1) & 1], (uint32_t)(((t + 1) >> 1) & 1));
                     load_x(t + 3);
                 }
                 bulk_wait_read<1>();                      // every store group but this step's has read its tiles
@@ -235,9 +243,9 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         const uint32_t seed = (kDrop && p.seed) ? *p.seed : 0u;
         const float keep_scale = kDrop ? 1.0f / (1.0f - p.drop_p) : 1.0f;
         const uint32_t thr16 = (uint32_t)(p.drop_p * 65536.0f);
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 16);
-        const int ubase = uh * 64 + cq * 16;              // this thread's 16 hidden units
-        const float *bsm = bias_sm + uh * 256 + cq * 16;  // + (gate >> 1) * 128 + (gate & 1) * 64 + unit offset
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 8);
+        const int ubase = uh * 64 + cq * 8;               // this thread's hidden units: [ubase, +8) (chunk 0) and [ubase + 32, +8) (chunk 1)
+        const float *bsm = bias_sm + uh * 256 + cq * 8;   // + (gate >> 1) * 128 + (gate & 1) * 64 + chunk * 32 + unit offset
         float cst[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) cst[j] = 0.0f;
@@ -245,7 +253,7 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         for (int t = 0; t < W; ++t) {
             const int b = t & 1;
             const uint32_t par = (uint32_t)((t >> 1) & 1);
-            bar_wait_cluster(&acc_full[b], par);
+            bar_wait(&acc_full[b], par);
             tcgen05_fence_after();
             if (t >= 2) bar_wait(&tile_free[b], (uint32_t)(((t - 2) >> 1) & 1));
             if (ok) {
@@ -254,19 +262,19 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 unsigned char *u_row = u_sm + b * S::kHTile + uh * 8192 + row_l * 128;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const int u0 = ubase + c * 8;
+                    const int u0 = ubase + c * 32;
                     uint32_t a[4][8];
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
-                        r2_ld8(t_lane + (uint32_t)(b * 256 + (g >> 1) * 128 + (g & 1) * 64 + c * 8), a[g]);
+                        r2_ld8(t_lane + (uint32_t)(b * 256 + (g >> 1) * 128 + (g & 1) * 64 + c * 32), a[g]);
                     tmem_wait_ld();
                     float gi[8], gf[8], gg[8], go[8], h[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float zi = __uint_as_float(a[0][j]) + bsm[c * 8 + j];
-                        const float zf = __uint_as_float(a[1][j]) + bsm[64 + c * 8 + j];
-                        const float zg = __uint_as_float(a[2][j]) + bsm[128 + c * 8 + j];
-                        const float zo = __uint_as_float(a[3][j]) + bsm[192 + c * 8 + j];
+                        const float zi = __uint_as_float(a[0][j]) + bsm[c * 32 + j];
+                        const float zf = __uint_as_float(a[1][j]) + bsm[64 + c * 32 + j];
+                        const float zg = __uint_as_float(a[2][j]) + bsm[128 + c * 32 + j];
+                        const float zo = __uint_as_float(a[3][j]) + bsm[192 + c * 32 + j];
                         gi[j] = fmaf(0.5f, r2_tanh(zi), 0.5f);
                         gf[j] = fmaf(0.5f, r2_tanh(zf), 0.5f);
                         gg[j] = r2_tanh(zg);
@@ -289,7 +297,7 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                         *reinterpret_cast<float4 *>(cdst + 128) = make_float4(cst[c * 8 + 4], cst[c * 8 + 5], cst[c * 8 + 6], cst[c * 8 + 7]);
                     }
                     // operand tile of the next step's MMA and source of the TMA store (128B swizzle: 16-byte slot ^ row % 8)
-                    const int slot = (cq * 2 + c) ^ (row_l & 7);
+                    const int slot = (c * 4 + cq) ^ (row_l & 7);
                     *reinterpret_cast<uint4 *>(h_row + (slot << 4)) =
                         make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
                     if (kUp) {
@@ -313,15 +321,26 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                         dst[0] = make_float4(h[0], h[1], h[2], h[3]);
                         dst[1] = make_float4(h[4], h[5], h[6], h[7]);
                     }
+                    if (c == 0) {            // first half of h_t is in the operand tile: its K-steps may start
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (leader) bar_arrive(&h_ready[2 * b]);
+                            else bar_arrive_cluster(mapa_rank(&h_ready[2 * b], 0));
+                        }
+                    }
                 }
+            } else if (lane == 0) {          // a warp of padding rows still takes part in the first-half handshake
+                if (leader) bar_arrive(&h_ready[2 * b]);
+                else bar_arrive_cluster(mapa_rank(&h_ready[2 * b], 0));
             }
             fence_proxy_async_smem();    // h_t / dropout(h_t) (generic-proxy stores) -> visible to tcgen05.mma and TMA
             tcgen05_fence_before();      // this step's tcgen05.ld are complete before the x-part of step t+2 overwrites the buffer
             __syncwarp();
             if (lane == 0) {
                 bar_arrive(&h_local[b]);
-                if (leader) bar_arrive(&h_ready[b]);
-                else bar_arrive_cluster(mapa_rank(&h_ready[b], 0));
+                if (leader) bar_arrive(&h_ready[2 * b + 1]);
+                else bar_arrive_cluster(mapa_rank(&h_ready[2 * b + 1], 0));
             }
         }
     }
@@ -528,7 +547,7 @@ lstm_rec2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         const bool have_rec = step > 0;
         const uint32_t acc_prev = (uint32_t)(((step - 1) & 1) * 128);
         if (have_rec) {
-            bar_wait_cluster(acc_full, (uint32_t)((step - 1) & 1));
+            bar_wait(acc_full, (uint32_t)((step - 1) & 1));
             tcgen05_fence_after();
             drain_dx(t + 1, acc_prev);
             bar_wait(tile_free, (uint32_t)((step - 1) & 1));       // the stores of the previous step's dG tile have read it
@@ -619,8 +638,8 @@ lstm_rec2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 for (int kb = 0; kb < 4; ++kb) tma_store_3d(&tmap_dg, a_sm + (c * 4 + kb) * 8192, (c * 4 + kb) * 64, m0, t);
                 bulk_commit();
                 if (leader) {
-                    if (step == 0 && c == 0) bar_wait_cluster(w_full, 0);
-                    bar_wait_cluster(&chunk_ready[c], par);
+                    if (step == 0 && c == 0) bar_wait(w_full, 0);
+                    bar_wait(&chunk_ready[c], par);
                     tcgen05_fence_after();
                     const uint32_t acc = tmem_base + (uint32_t)((step & 1) * 128);
 #pragma unroll
@@ -643,7 +662,7 @@ lstm_rec2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         }
     }
     // the accumulator of the last step holds dX_0 (dh_{-1} is not needed)
-    bar_wait_cluster(acc_full, (uint32_t)((W - 1) & 1));
+    bar_wait(acc_full, (uint32_t)((W - 1) & 1));
     tcgen05_fence_after();
     drain_dx(0, (uint32_t)(((W - 1) & 1) * 128));
     if (threadIdx.x == 0) bulk_wait_all();
