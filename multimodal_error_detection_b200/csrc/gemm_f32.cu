@@ -274,7 +274,7 @@ static long long weight_slabs(long long M, long long N, long long K) {
     return s;
 }
 static long long colsum_slabs_flat(long long M) {
-    long long s = (M + 255) / 256;       // >= 256 rows per slab
+    long long s = (M + 63) / 64;         // >= 64 rows per slab
     if (s < 1) s = 1;
     if (s > 592) s = 592;                // 4 CTAs on each of the 148 SMs
     return s;

@@ -107,25 +107,43 @@ bn_stats_partial_kernel(const float *__restrict__ x, long long M, int C, long lo
     }
 }
 
-// Per column: combine the slab partials (Chan et al., ascending slab order, double) -> scale / shift of the normalisation,
-// save_mean / save_rstd for the backward, running statistics (momentum, unbiased variance) like nn.BatchNorm1d in training mode.
-__global__ void bn_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, const float *__restrict__ gamma,
-                                   const float *__restrict__ beta, float eps, float momentum, float *__restrict__ scale_shift,
-                                   float *__restrict__ save_mean, float *__restrict__ save_rstd, float *__restrict__ running_mean,
-                                   float *__restrict__ running_var, long long *__restrict__ num_batches) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col == 0 && num_batches) *num_batches += 1;
+// fixed-order warp sum of doubles (butterfly: every lane ends with the same bits)
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Per column (ONE WARP per column, lanes over the slabs): combine the slab partials in double -- mean = sum n_s mean_s / M,
+// M2 = sum [M2_s + n_s (mean_s - mean)^2] -- -> scale / shift of the normalisation, save_mean / save_rstd for the backward,
+// running statistics (momentum, unbiased variance) like nn.BatchNorm1d in training mode.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, const float *__restrict__ gamma,
+                   const float *__restrict__ beta, float eps, float momentum, float *__restrict__ scale_shift,
+                   float *__restrict__ save_mean, float *__restrict__ save_rstd, float *__restrict__ running_mean,
+                   float *__restrict__ running_var, long long *__restrict__ num_batches) {
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (col == 0 && lane == 0 && num_batches) *num_batches += 1;
     if (col >= C) return;
-    double n = 0.0, mu = 0.0, q = 0.0;
-    for (int s = 0; s < S; ++s) {
-        const float *p = part + (long long)s * 3 * C;
-        const double ns = p[col], ms = p[C + col], qs = p[2 * C + col];
-        if (ns <= 0.0) continue;
-        const double d = ms - mu, tot = n + ns;
-        mu += d * ns / tot;
-        q += qs + d * d * n * ns / tot;
-        n = tot;
+    double ns[2], ms[2], qs[2];
+    double wsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int s = lane + 32 * k;
+        ns[k] = 0.0; ms[k] = 0.0; qs[k] = 0.0;
+        if (s < S) {
+            const float *p = part + (long long)s * 3 * C;
+            ns[k] = p[col]; ms[k] = p[C + col]; qs[k] = p[2 * C + col];
+        }
+        wsum += ns[k] * ms[k];
     }
+    const double mu = warp_sum_d(wsum) / (double)M;
+    double q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { const double d = ms[k] - mu; q += qs[k] + ns[k] * d * d; }
+    q = warp_sum_d(q);
+    if (lane != 0) return;
     const double var = q / (double)M;
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float g = gamma ? gamma[col] : 1.0f, b = beta ? beta[col] : 0.0f;
@@ -209,15 +227,19 @@ bn_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x,
     }
 }
 
-// Per column: dgamma = sum dy xhat, dbeta = sum dy, and the three coefficients of dx = k0 * dy - k1 - k2 * x
-// (k0 = gamma rstd, k1 = k0 (mean(dy) - mu rstd mean(dy xhat)), k2 = k0 rstd mean(dy xhat)).
-__global__ void bn_bwd_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, const float *__restrict__ gamma,
-                                       const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
-                                       float *__restrict__ coef, float *__restrict__ dgamma, float *__restrict__ dbeta) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+// Per column (one warp, lanes over the slabs): dgamma = sum dy xhat, dbeta = sum dy, and the three coefficients of
+// dx = k0 * dy - k1 - k2 * x  (k0 = gamma rstd, k1 = k0 (mean(dy) - mu rstd mean(dy xhat)), k2 = k0 rstd mean(dy xhat)).
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, const float *__restrict__ gamma,
+                       const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
+                       float *__restrict__ coef, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (col >= C) return;
     double sa = 0.0, sb = 0.0;
-    for (int s = 0; s < S; ++s) { sa += part[(long long)s * 2 * C + col]; sb += part[(long long)s * 2 * C + C + col]; }
+    for (int s = lane; s < S; s += 32) { sa += part[(long long)s * 2 * C + col]; sb += part[(long long)s * 2 * C + C + col]; }
+    sa = warp_sum_d(sa); sb = warp_sum_d(sb);
+    if (lane != 0) return;
     if (dbeta) dbeta[col] = (float)sa;
     if (dgamma) dgamma[col] = (float)sb;
     const float mu = save_mean[col], rs = save_rstd[col], k0 = (gamma ? gamma[col] : 1.0f) * rs;
@@ -396,7 +418,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_bn_fwd(const float
     if (vec) bn_stats_partial_kernel<4><<<grid, kBnCols * kBnWarps, 0, st>>>(x, M, C, rows, part);
     else bn_stats_partial_kernel<1><<<grid, kBnCols * kBnWarps, 0, st>>>(x, M, C, rows, part);
     if (int e = after_launch("bn_stats_partial_kernel")) return e;
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, S, M, C, gamma, beta, eps, momentum, scale_shift, save_mean, save_rstd,
+    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, S, M, C, gamma, beta, eps, momentum, scale_shift, save_mean, save_rstd,
                                                       running_mean, running_var, (long long *)num_batches_tracked);
     if (int e = after_launch("bn_finalize_kernel")) return e;
     if (vec) bn_apply_kernel<4><<<ew_grid(M * C / 4), 256, 0, st>>>(x, M, C, scale_shift, y);
@@ -420,7 +442,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_bn_bwd(const float
     if (vec) bn_bwd_partial_kernel<4><<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, save_mean, save_rstd, part);
     else bn_bwd_partial_kernel<1><<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, save_mean, save_rstd, part);
     if (int e = after_launch("bn_bwd_partial_kernel")) return e;
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, S, M, C, gamma, save_mean, save_rstd, coef, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, S, M, C, gamma, save_mean, save_rstd, coef, dgamma, dbeta);
     if (int e = after_launch("bn_bwd_finalize_kernel")) return e;
     if (vec) bn_bwd_apply_kernel<4><<<ew_grid(M * C / 4), 256, 0, st>>>(dy, x, M, C, coef, relu_mask, dx);
     else bn_bwd_apply_kernel<1><<<ew_grid(M * C), 256, 0, st>>>(dy, x, M, C, coef, relu_mask, dx);

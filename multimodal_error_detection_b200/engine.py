@@ -252,7 +252,7 @@ class FrameTrainStep:
         outputs = self.model(inputs)
         loss, _ = mu.compute_loss(outputs, self.labels, self.crit, "frame")
         self.opt.zero_grad()
-        mu._backward(loss, self.opt)
+        mu._backward(loss, self.opt, exchange=exchange)
         if exchange:
             mu._allreduce_grads(self.opt)
         self.opt.step()

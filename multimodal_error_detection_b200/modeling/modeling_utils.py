@@ -334,26 +334,107 @@ def _set_train(model, feature_extractor, exp_kwargs, train: bool):
         m.train(train)
 
 
-def _backward(loss, optimizer=None, weight: float = 1.0):
+def _dp_world() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+class _EarlyExchange:
+    """Data-parallel gradient exchange in two pieces (see models.EARLY_EXCHANGE_HOOK): everything but the FeatureExtractor's
+    first layer is all-reduced UNDER that layer's weight-gradient GEMM, the first layer's own gradient after the backward."""
+
+    def __init__(self, optimizer):
+        self.opt = optimizer
+        self.work = None            # async all-reduce of the early range
+        self.split = None           # element offset in chunk 0 where the early range starts
+
+    def hook(self, params, grads):
+        import torch.distributed as dist
+        from .. import lstm_stack
+        opt = self.opt
+        opt.prepare()
+        if len(opt.chunks) != 1:
+            return grads            # several chunks: leave the exchange to _allreduce_grads
+        chunk = opt.chunks[0]
+        slots = {id(p): (o, n) for p, o, n in chunk.members}
+        first = [id(params[0]), id(params[1])]
+        if any(i not in slots for i in first):
+            return grads
+        end_first = max(slots[i][0] + slots[i][1] for i in first)
+        split = (end_first + 3) // 4 * 4
+        if any(o < split for i, (o, n) in slots.items() if i not in first):
+            return grads            # the first layer does not lead the flat buffer: one exchange after the backward
+        lstm_stack.join_pending()   # LSTM weight gradients still on their side stream
+        dst, src = [], []
+        out = list(grads)
+        for k in range(2, len(params)):                    # the FeatureExtractor's other layers: computed a moment ago
+            if grads[k] is None or id(params[k]) not in slots:
+                continue
+            o, n = slots[id(params[k])]
+            view = chunk.grad[o:o + n].view_as(params[k])
+            dst.append(view); src.append(grads[k].detach())
+            out[k] = view
+        seen = set(id(q) for q in params)
+        for p, o, n in chunk.members:                      # the head: its gradients already sit in .grad
+            if id(p) in seen or p.grad is None:
+                continue
+            view = chunk.grad[o:o + n].view_as(p)
+            if p.grad.data_ptr() != view.data_ptr():
+                dst.append(view); src.append(p.grad.detach())
+                p.grad = view
+        if dst:
+            torch._foreach_copy_(dst, src)
+        self.split = split
+        self.work = dist.all_reduce(chunk.grad[split:], op=dist.ReduceOp.SUM, async_op=True)
+        return out
+
+    def finish(self) -> bool:
+        """All-reduce the late range and join the early one; False when the hook did not run (nothing exchanged yet)."""
+        import torch.distributed as dist
+        if self.work is None:
+            return False
+        self.opt._refresh_active()
+        dist.all_reduce(self.opt.chunks[0].grad[:self.split], op=dist.ReduceOp.SUM)
+        self.work.wait()
+        self.work = None
+        return True
+
+
+_EARLY = {"state": None}
+
+
+def _backward(loss, optimizer=None, weight: float = 1.0, exchange: bool = True):
     """loss.backward() inside a train loop: the LSTM weight-gradient GEMMs stay on their side stream past the end of the
     backward (lstm_stack.DEFER_JOIN); the next consumer of the gradients (_allreduce_grads / optimizer.step, both through
     FusedAdam._refresh_active) joins it.  ``weight``: data-parallel share of this rank's batch (uneven shards of a short
-    batch), applied to the gradient only -- the reported loss stays the rank's own mean."""
+    batch), applied to the gradient only -- the reported loss stays the rank's own mean.  With several ranks the gradient
+    exchange starts INSIDE the backward (:class:`_EarlyExchange`) unless ``exchange`` is False (collective-free warm-up steps)."""
     from .. import lstm_stack
-    lstm_stack.DEFER_JOIN = isinstance(optimizer, FusedAdam)      # only FusedAdam joins the side stream before using the gradients
+    from . import models as _models
+    fused = isinstance(optimizer, FusedAdam)
+    lstm_stack.DEFER_JOIN = fused      # only FusedAdam joins the side stream before using the gradients
+    early = None
+    if exchange and fused and _dp_world() > 1 and os.environ.get("B200MED_EARLY_EXCHANGE", "1") != "0":
+        early = _EARLY["state"] = _EarlyExchange(optimizer)
+        _models.EARLY_EXCHANGE_HOOK = early.hook
     try:
         (loss if weight == 1.0 else loss * weight).backward()
     finally:
         lstm_stack.DEFER_JOIN = False
+        _models.EARLY_EXCHANGE_HOOK = None
 
 
 def _allreduce_grads(optimizer):
-    """Data-parallel exchange: ONE sum all-reduce of the flat gradient buffer."""
+    """Data-parallel exchange: a sum all-reduce of the flat gradient buffer -- in two pieces when the
+    backward started it early (everything but the FeatureExtractor's first layer travels under that layer's weight-gradient
+    GEMM), else in one."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        optimizer._refresh_active()                      # gradients of first-time parameters move into the chunks
-        for buf in optimizer.grad_buffers():             # one chunk (+ one for a cuDNN-flattened LSTM)
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        early, _EARLY["state"] = _EARLY["state"], None
+        if early is None or early.opt is not optimizer or not early.finish():
+            optimizer._refresh_active()                      # gradients of first-time parameters move into the chunks
+            for buf in optimizer.grad_buffers():
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         optimizer.grad_scale = 1.0 / dist.get_world_size()
 
 

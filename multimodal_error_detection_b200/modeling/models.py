@@ -27,6 +27,14 @@ def _split_k(tiles: int, k_blocks: int) -> int:
     return max(1, min(want, k_blocks // 8 if k_blocks >= 16 else 1))
 
 
+# Data-parallel overlap hook (set by modeling_utils._backward when several ranks train): called inside the backward of the
+# FeatureExtractor right BEFORE the gradients of its FIRST layer -- the last and longest GEMM of the whole backward (dW1 is a
+# [512 x 2048] product over all B*W rows) -- with every other gradient of the step already computed.  The hook moves those into
+# the flat gradient buffer and starts their all-reduce, which then runs UNDER the dW1 GEMM; only the first layer's own gradient
+# is exchanged after the backward.  Signature: hook(params, grads) -> grads (entries may be replaced by flat-buffer views).
+EARLY_EXCHANGE_HOOK = None
+
+
 class _MLPFunction(torch.autograd.Function):
     """y = L_n(...relu(L_1(x))) with every product on the b200med GEMM kernels (K2)."""
 
@@ -35,6 +43,7 @@ class _MLPFunction(torch.autograd.Function):
         weights, biases = params[0::2], params[1::2]
         n = len(weights)
         ctx.precision, ctx.n = precision, n
+        ctx.params = params            # the Parameter objects: the data-parallel hook looks their flat-buffer slots up
         M = x.shape[0]
         if precision == "fp32":
             h = x if x.dtype == torch.float32 else x.float()
@@ -66,6 +75,8 @@ class _MLPFunction(torch.autograd.Function):
         if ctx.precision == "fp32":
             g = dy.contiguous().float()
             for i in reversed(range(n)):
+                if i == 0 and n > 1 and EARLY_EXCHANGE_HOOK is not None:
+                    grads = EARLY_EXCHANGE_HOOK(ctx.params, grads)
                 grads[2 * i], grads[2 * i + 1] = ops.linear_bwd_weight_f32(g, acts[i])
                 if i > 0:
                     g = ops.linear_bwd_data_f32(g, weights[i], relu_out=acts[i])
@@ -74,6 +85,8 @@ class _MLPFunction(torch.autograd.Function):
             return (g if need_dx else None, None, *grads)
         g = ops.to_bf16(dy.contiguous().float())
         for i in reversed(range(n)):
+            if i == 0 and n > 1 and EARLY_EXCHANGE_HOOK is not None:
+                grads = EARLY_EXCHANGE_HOOK(ctx.params, grads)
             N, K = weights[i].shape
             # dW[N,K] = g[M,N]^T acts_i[M,K]: both operands reduce over their ROW index -> MN-major
             tiles = ((N + 127) // 128) * ((K + 255) // 256)

@@ -28,7 +28,9 @@ def main():
     tmp = tempfile.mkdtemp(prefix=f"dpw{rank}_")
     path = synthetic.write_fold(fold, os.path.join(tmp, "fold")) + "/"
     out = {}
-    for precision in ("bf16", "fp32"):
+    finals = {}
+    for precision, early in (("bf16", "1"), ("bf16", "0"), ("fp32", "1")):
+        os.environ["B200MED_EARLY_EXCHANGE"] = early      # "0": one all-reduce after the backward (the A/B of the overlap)
         kw = dict(dataset_type="window", error_type="global", pos_weight=True, n_epochs=2, batch_size=64, lr=3e-4, lr_scheduler=True,
                   weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32, data_type="multimodal", delete_ND=True,
                   return_train_preds=False, siamese=False, model_name="SimpleLSTM", precision=precision, cuda_graph=True)
@@ -43,12 +45,17 @@ def main():
         same = bool(torch.equal(flat, ref))
         allsame = torch.tensor([int(same)], device=dev)
         dist.all_reduce(allsame, op=dist.ReduceOp.MIN)
-        out[precision] = {"graph_replayed": stepper.graph is not None, "stepper_batch": stepper.B, "global_batch": kw["batch_size"],
+        finals[(precision, early)] = flat.clone()
+        out[f"{precision}_early{early}"] = {"graph_replayed": stepper.graph is not None, "stepper_batch": stepper.B, "global_batch": kw["batch_size"],
                           "replicas_identical": bool(allsame.item()), "loss_rank0": losses}
         assert stepper.B == kw["batch_size"] // world and stepper.graph is not None, out
         assert bool(allsame.item()), "replicas drifted apart"
         opt._b200_stepper = None
         del stepper
+    # the early (two-piece) exchange and the single all-reduce give the same training run up to the summation order of NCCL
+    diff = float((finals[("bf16", "1")] - finals[("bf16", "0")]).abs().max())
+    out["early_vs_single_max_abs_param_diff"] = diff
+    assert diff < 1e-4, diff
     if rank == 0:
         print(json.dumps({"world": world, **out}), flush=True)
     torch.cuda.synchronize()
