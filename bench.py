@@ -125,8 +125,8 @@ class ClockSampler(threading.Thread):
                 "query_ms": 1e3 * statistics.median(self.costs) if self.costs else None}
 
 
-def k1_traffic(precision, batch, window, variant):
-    path = os.path.join(ROOT, "profiles", "k1_traffic.json")
+def k1_traffic(precision, batch, window, variant, fused=False):
+    path = os.path.join(ROOT, "profiles", "k1_fused_traffic.json" if fused else "k1_traffic.json")
     try:
         rec = json.load(open(path))
         c = rec["config"]
@@ -446,7 +446,11 @@ def run_gpu(args):
 
     # ---- roofline of the dominant HBM kernel (K1), timed with CUDA events on the launch stream
     out_es = 2 if args.precision == "bf16" else 4
-    k1_bytes = B * W * (IMAGE_DIM * (4 + out_es) + KIN_DIM * 8)
+    fused = bool(getattr(stepper, "fused", False))
+    k1_unfused_bytes = B * W * (IMAGE_DIM * (4 + out_es) + KIN_DIM * 8)
+    # fused gather + first FeatureExtractor layer (csrc/gather_gemm.cu): fp32 table rows in, the bf16 batch (weight-gradient
+    # operand of the backward) and the layer's bf16 output out; the events bracket that kernel alone
+    k1_bytes = B * W * (IMAGE_DIM * (4 + 2) + 512 * 2) if fused else k1_unfused_bytes
     if stepper.graph is None and not stepper.prefetch:
         k1_ms = statistics.mean(a.elapsed_time(b) for a, b in gather_ev)
         k1_how = "CUDA events around the K1 launch inside each of the K timed steps"
@@ -505,12 +509,22 @@ def run_gpu(args):
     # DRAM traffic of K1 per step: NOT measurable without a profiler attached -- taken from the committed `ncu --set full`
     # capture of this configuration (profiles/k1_traffic.json records the command, the config it was captured on and the two
     # dram__bytes counters); null when this run's configuration is not the captured one.
-    traffic, traffic_src = k1_traffic(args.precision, B, W, args.gather_variant)
-    roofline = {"kernel": "gather_norm_tma_kernel + gather_norm_kernel (K1: window gather + standardise + concat, image + kinematics streams)",
+    traffic, traffic_src = k1_traffic(args.precision, B, W, args.gather_variant, fused)
+    k1_name = ("gather_gemm_kernel (K1 fused into K2: window gather + standardise of the image stream as the A-operand producer of the "
+               "FeatureExtractor's first Linear + ReLU on tcgen05; HBM-bound: 170 flop per byte, below the ridge)") if fused else \
+        "gather_norm_tma_kernel + gather_norm_kernel (K1: window gather + standardise + concat, image + kinematics streams)"
+    roofline = {"kernel": k1_name,
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "traffic_source": traffic_src,
-                "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms, "ms_per_launch_isolated": k1_iso_ms,
-                "share_of_step": k1_ms / step_ms, "how": k1_how, "peak_source": peak_src}
+                "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
+                "share_of_step": k1_ms / step_ms, "how": k1_how, "peak_source": peak_src,
+                "bytes_per_window": k1_bytes // B,
+                "tflops_in_its_shadow": (2.0 * B * W * 512 * IMAGE_DIM / (k1_ms * 1e-3) / 1e12) if fused else None,
+                # the standalone K1 kernel (every other loop of the package gathers through it): isolated launches, fresh slices
+                "k1_standalone": {"kernel": "gather_norm_tma_kernel<bf16, 0, 8, 3, 256> + gather_norm_kernel (image + kinematics)",
+                                  "bytes_per_launch": k1_unfused_bytes, "ms_per_launch_isolated": k1_iso_ms,
+                                  "achieved": k1_unfused_bytes / (k1_iso_ms * 1e-3) / 1e9,
+                                  "frac": k1_unfused_bytes / (k1_iso_ms * 1e-3) / 1e9 / hbm_peak}}
 
     # ---- tensor-pipe evidence for K2: FE layer-1 forward GEMM alone
     gemm = None
@@ -588,7 +602,7 @@ def run_gpu(args):
                 "config": {"workload": workload_name(B, args.videos), "global_batch": world * B, "window": W, "stride": S,
                            "frames_per_gpu": n_frames, "windows_per_gpu": n_windows, "params": n_params,
                            "parallelism": f"dp{world}", "launch": graph_note,
-                           "gather_prefetch": bool(prefetch),
+                           "gather_prefetch": bool(prefetch), "gather_fused_into_layer1": fused,
                            "l2": "every step gathers a fresh ~1.1 GB slice of a ~10 GB table (inputs larger than the 126 MB L2)",
                            "gather_variant": args.gather_variant},
                 "roofline": roofline, "roofline_gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
@@ -629,8 +643,10 @@ def main():
                     "(frame path, ensemble inference; N = 1 only, reported under 'other_configs')")
     ap.add_argument("--no-ensemble", action="store_true", help="skip the 12 500-videos-per-GPU ensemble job (62 GB table per GPU)")
     ap.add_argument("--prefetch-sms", type=int, default=56, help="SMs the prefetching gather may occupy (side stream)")
-    ap.add_argument("--no-prefetch", dest="prefetch", action="store_false",
-                    help="gather each step's batch at the start of the step instead of inside the previous step")
+    ap.add_argument("--prefetch", dest="prefetch", action="store_true",
+                    help="gather the batch of step k+1 on a side stream inside step k (round 1's default: it hid K1 under LSTM kernels "
+                         "that left 84 SMs idle; the generation-2 recurrence fills 128 SMs and the overlap no longer pays -- "
+                         "profiles/r2_step_breakdown_in_graph_gen2.txt)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the in-run CPU baseline (N = 1 only; B windows each)")
     ap.add_argument("--cpu-windows", type=int, default=0, help="(ignored, kept for old command lines)")
     args = ap.parse_args()

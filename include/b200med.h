@@ -117,6 +117,17 @@ int b200med_gather_norm(const b200med_stream_desc *streams_host, int32_t n_strea
  * shape (the `variant` numbering above).  Lets a parity test prove which instantiation it compared with the oracle.  */
 int b200med_gather_last_variant(void);
 
+/* K1 + K2 fused (csrc/gather_gemm.cu): the window gather / standardise of one fp32 stream as the A-operand producer of a
+ * Linear layer on the tensor cores -- what the reference does as CustomWindowDataset.__getitem__ + collate + .to(device)
+ * (CustomWindowDataset.py:53-60, modeling_utils.py:40) followed by the FeatureExtractor's first Linear + ReLU (models.py:19-35).
+ *   xb [B*W, K] bf16 OUT = bf16((table[starts[b] + t, :] - mean) * (1 / std))     (bit-identical to b200med_gather_norm's bf16
+ *                          output with exact_div = 0; the backward's weight-gradient operand)
+ *   y  [B*W, N] bf16 OUT = relu?(xb w^T + bias),  w [N, K] bf16 row-major (nn.Linear layout), N = 512, K % 64 == 0,
+ *   W in {16, 32, 64, 128} (TMA boxes of W table rows tile the 128-row operand).  A window outside the table traps.   */
+int b200med_gather_linear_bf16(const float *table, int64_t table_rows, const float *mean, const float *stdv,
+                               const int32_t *starts, int64_t B, int32_t W, const void *w_bf16, const float *bias,
+                               int32_t relu, void *xb, void *y, int32_t N, int32_t K, void *stream);
+
 /* Frame path: standardise whole rows in place order (no gather): out[r,:] = (x[r,:]-mean)/std.
  * Replaces the kinematics standardisation of CustomFrameDataset.__getitem__ (CustomFrameDataset.py:93-95). */
 int b200med_standardise_rows(const float *x, const float *mean, const float *stdv, float *out,

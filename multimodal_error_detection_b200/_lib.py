@@ -34,6 +34,7 @@ SIGNATURES = {
     "b200med_powerset": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "b200med_gather_norm": (C.c_int, [C.POINTER(StreamDesc), _i32, _p, _i64, _i32, _i32, _p]),
     "b200med_gather_last_variant": (C.c_int, []),
+    "b200med_gather_linear_bf16": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p]),
     "b200med_standardise_rows": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "b200med_linear_fwd_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "b200med_gemm_f32_ws_bytes": (_i64, [_i64, _i64, _i64]),

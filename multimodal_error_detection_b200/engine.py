@@ -37,14 +37,24 @@ class WindowTrainStep:
         self.idx2 = [torch.zeros(batch_size, dtype=torch.int64, device=dev) for _ in range(2)]     # the step's only input
         self.label_col = mu.define_error_labels(dataset.e_labels_data, exp_kwargs).float().contiguous()
         D_img, D_kin = dataset._image_table.shape[1], dataset._kin_table.shape[1]
-        self.images2 = [torch.empty(batch_size, self.W, D_img, dtype=self.image_dtype, device=dev) for _ in range(2)]
-        self.kin2 = [torch.empty(batch_size, self.W, D_kin, dtype=torch.float32, device=dev) for _ in range(2)]
+        nbuf = 2 if prefetch else 1        # double-buffered batches only when the next step's gather runs inside this step
+        imgs = [torch.empty(batch_size, self.W, D_img, dtype=self.image_dtype, device=dev) for _ in range(nbuf)]
+        kins = [torch.empty(batch_size, self.W, D_kin, dtype=torch.float32, device=dev) for _ in range(nbuf)]
+        self.images2 = [imgs[0], imgs[-1]]
+        self.kin2 = [kins[0], kins[-1]]
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.counts = torch.zeros(4, dtype=torch.int64, device=dev)
         self.probs = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.preds = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.labels = torch.zeros(batch_size, dtype=torch.float32, device=dev)
         self.gather_variant = gather_variant
+        # K1 fused into the FeatureExtractor's first layer (csrc/gather_gemm.cu): no materialised image batch on the way in
+        from . import ops as _ops
+        first = feature_extractor.linear[0] if feature_extractor is not None else None
+        stat_rows = dataset._img_stats[0].shape[0] if dataset._img_stats is not None else 1
+        self.fused = bool(exp_kwargs.get("fused_gather", True)) and not prefetch and feature_extractor is not None \
+            and self.image_dtype == torch.bfloat16 and exp_kwargs["data_type"] == "multimodal" \
+            and _ops.gather_linear_supported(dataset._image_table, self.W, first.out_features, stat_rows)
         self.gather_events = None      # optional (start, end) CUDA events around K1
         self.phase_events = None       # optional list of 9 (external) CUDA events at the phase boundaries of the step
         self.graphs = [None, None]     # one captured step per buffer parity
@@ -99,10 +109,23 @@ class WindowTrainStep:
         self._mark(0)
         from . import ops
         labels = ops.take_rows(self.label_col, self.idx2[cur], out=self.labels)
-        if not self.prefetch:
-            self._gather(cur)
-        self._mark(1)
-        inputs = mu.define_inputs(self.images2[cur], self.kin2[cur], self.fe, self.kw, self.device)
+        if self.fused:
+            # kinematics through K1 (26 columns), the image stream gathered INSIDE the first FeatureExtractor layer
+            from .heads import concat_features
+            starts = ops.take_rows(self.ds._starts, self.idx2[cur])
+            km = self.ds._kin_stats
+            ops.gather_norm([ops.GatherStream(self.ds._kin_table, km[0] if km else None, km[1] if km else None, self.kin2[cur], 0, True)],
+                            starts, self.W)
+            self._mark(1)
+            im = self.ds._img_stats
+            feats = self.fe.forward_table(self.ds._image_table, im[0] if im else None, im[1] if im else None, starts, self.W,
+                                          events=self.gather_events)
+            inputs = concat_features(feats, self.kin2[cur]).permute(0, 2, 1)
+        else:
+            if not self.prefetch:
+                self._gather(cur)
+            self._mark(1)
+            inputs = mu.define_inputs(self.images2[cur], self.kin2[cur], self.fe, self.kw, self.device)
         self._mark(2)
         if self.phase_events is not None and inputs.requires_grad:
             inputs.register_hook(lambda g: self._mark(5))      # gradient w.r.t. the head input = end of the head's backward

@@ -615,7 +615,7 @@ def _train_epoch_graph(model, feature_extractor, loader, criterion, optimizer, s
     stepper = getattr(optimizer, "_b200_stepper", None)
     if stepper is None or stepper.key != key:
         stepper = WindowTrainStep(ds, feature_extractor, model, criterion, optimizer, exp_kwargs, max(B, 1),
-                                  prefetch=bool(exp_kwargs.get("prefetch_gather", _image_dtype(feature_extractor) == torch.bfloat16)))
+                                  prefetch=bool(exp_kwargs.get("prefetch_gather", False)))
         stepper.key = key
         optimizer._b200_stepper = stepper
     log = _EpochLog()

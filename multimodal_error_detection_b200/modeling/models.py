@@ -35,6 +35,14 @@ def _split_k(tiles: int, k_blocks: int) -> int:
 EARLY_EXCHANGE_HOOK = None
 
 
+class TableWindows:
+    """The FeatureExtractor's input as (device-resident fp32 table, per-column mean / std, window start rows, window length)
+    instead of a gathered batch: the first layer's kernel gathers and standardises the windows itself (csrc/gather_gemm.cu)."""
+
+    def __init__(self, table, mean, std, starts, W, events=None):
+        self.table, self.mean, self.std, self.starts, self.W, self.events = table, mean, std, starts, W, events
+
+
 class _MLPFunction(torch.autograd.Function):
     """y = L_n(...relu(L_1(x))) with every product on the b200med GEMM kernels (K2)."""
 
@@ -44,6 +52,22 @@ class _MLPFunction(torch.autograd.Function):
         n = len(weights)
         ctx.precision, ctx.n = precision, n
         ctx.params = params            # the Parameter objects: the data-parallel hook looks their flat-buffer slots up
+        if isinstance(x, TableWindows):
+            # K1 fused into the first layer: table rows -> standardised bf16 operand tile -> tcgen05.mma; the bf16 batch is
+            # written once (the backward's weight-gradient operand) and never read back by this layer
+            if precision != "bf16" or n < 2:
+                raise ValueError("the fused gather serves the bf16 mode of an MLP with at least two layers")
+            wb = [ops.to_bf16(w.detach().contiguous()) for w in weights]
+            xb, y1 = ops.gather_linear_bf16(x.table, x.mean, x.std, x.starts, x.W, wb[0], biases[0].detach(), relu=True, events=x.events)
+            acts = [xb, y1]
+            M = xb.shape[0]
+            for i in range(1, n):
+                N, K = weights[i].shape
+                last = i == n - 1
+                acts.append(ops.gemm_bf16(acts[-1], wb[i], M, N, K, True, True, bias=biases[i], relu=not last,
+                                          out_dtype=torch.float32 if last else torch.bfloat16))
+            ctx.save_for_backward(*acts[:-1], *wb)
+            return acts[-1]
         M = x.shape[0]
         if precision == "fp32":
             h = x if x.dtype == torch.float32 else x.float()
@@ -127,6 +151,12 @@ class FeatureExtractor(nn.Module):
             if isinstance(m, nn.Linear):
                 out += [m.weight, m.bias]
         return out
+
+    def forward_table(self, table, mean, std, starts, W: int, events=None):
+        """Features [B, W, output_dim] of the windows starting at rows ``starts`` of the fp32 ``table``, standardised with
+        (mean, std): the gather runs inside the first layer's kernel (bf16 mode; see ops.gather_linear_supported)."""
+        y = _MLPFunction.apply(TableWindows(table, mean, std, starts, W, events), self.precision, *self._params())
+        return y.reshape(starts.numel(), W, y.shape[-1])
 
     def forward(self, x):
         if not x.is_cuda:

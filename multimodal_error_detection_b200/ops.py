@@ -152,6 +152,33 @@ def gather_last_variant() -> int:
     return int(_lib.load().b200med_gather_last_variant())
 
 
+def gather_linear_supported(table, W: int, n_out: int, stat_rows: int = 1) -> bool:
+    """Shapes the fused gather + first-layer kernel (b200med_gather_linear_bf16) serves."""
+    return (table.dtype == torch.float32 and table.is_contiguous() and table.dim() == 2 and table.shape[1] % 64 == 0
+            and W in (16, 32, 64, 128) and n_out == 512 and stat_rows == 1 and has_tcgen05())
+
+
+def gather_linear_bf16(table, mean, std, starts, W: int, w_bf16, bias, relu: bool = True, events=None):
+    """(xb [B*W, K] bf16, y [B*W, 512] bf16): standardised bf16 windows of `table` and relu(xb w^T + bias) in ONE kernel."""
+    table = _need(table, torch.float32, "table")
+    starts = _need(starts, torch.int32, "starts")
+    w_bf16 = _need(w_bf16, torch.bfloat16, "w")
+    B, K, N = starts.numel(), table.shape[1], w_bf16.shape[0]
+    if mean is not None:
+        mean = _need(mean.reshape(-1), torch.float32, "mean"); std = _need(std.reshape(-1), torch.float32, "std")
+        if mean.numel() != K or std.numel() != K:
+            raise ValueError("the fused gather takes one mean / std per column")
+    xb = torch.empty(B * W, K, dtype=torch.bfloat16, device=table.device)
+    y = torch.empty(B * W, N, dtype=torch.bfloat16, device=table.device)
+    if events is not None:
+        events[0].record()
+    call("b200med_gather_linear_bf16", _ptr(table), table.shape[0], _ptr(mean), _ptr(std), _ptr(starts), B, W, _ptr(w_bf16),
+         _ptr(None if bias is None else _need(bias, torch.float32, "bias")), int(bool(relu)), _ptr(xb), _ptr(y), N, K, _stream())
+    if events is not None:
+        events[1].record()
+    return xb, y
+
+
 def expand_stat(stat, D: int, W: int, device) -> torch.Tensor:
     """Bring a standardisation statistic of any shape broadcastable against [W, D] (scalar, [D],
     [1, D], [W, D]; the on-disk format is unpinned by the reference) to [1|W, D]."""

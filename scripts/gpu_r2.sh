@@ -12,6 +12,7 @@ done
 run smoke python __graft_entry__.py --smoke
 fi
 [ -n "$SANITIZE" ] && TMO=1200 run sanitize compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_heads.py -m gpu -q -x -k "not 8192 and not 513 and not 600" --timeout 1100
+[ -n "$BREAKDOWN" ] && TAIL=24 CUT=200 run step_breakdown python scripts/step_breakdown.py
 [ -n "$LSTM_BENCH" ] && CUT=2000 TAIL=1 run bench_lstm python scripts/bench_lstm.py
 if [ -z "$SKIP_BENCH" ]; then
 CUT=4000 TAIL=2 run bench python bench.py --steps 20 --warmup 3 ${BENCH_ARGS}

@@ -239,6 +239,36 @@ def test_gather_norm_benchmarked_instantiation_vs_oracle(B, W, want_variant, exa
     assert ops.gather_last_variant() == want_variant and torch.equal(img2, img_out)
 
 
+@pytest.mark.parametrize("B,W", [(8192, 16), (100, 16), (33, 32), (7, 128), (1, 64)])
+def test_gather_linear_fused_vs_k1_then_gemm(B, W, ops):
+    """b200med_gather_linear_bf16 (K1 fused into the FeatureExtractor's first layer): the bf16 batch it emits is BIT-IDENTICAL to
+    the standalone K1 kernel's (which the tests above pin to the C oracle), and its output equals the tcgen05 GEMM on that batch
+    (same operands, same fp32 accumulation: at most an ulp of bf16 apart) -- at the headline size and on ragged tile tails."""
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    g = torch.Generator(device="cuda").manual_seed(B + W)
+    N, K = 30_000, 2048
+    table = torch.randn(N, K, device="cuda", generator=g).clamp_min_(0)
+    mean, std = torch.randn(K, device="cuda", generator=g) * 0.3, torch.rand(K, device="cuda", generator=g) + 0.25
+    starts = torch.randint(0, N - W, (B,), device="cuda", generator=g, dtype=torch.int64).to(torch.int32)
+    starts[0] = N - W                                     # last legal window
+    w = (torch.randn(512, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(512, device="cuda", generator=g)
+    xb, y = ops.gather_linear_bf16(table, mean, std, starts, W, w, bias, relu=True)
+    img = torch.empty(B, W, K, device="cuda", dtype=torch.bfloat16)
+    ops.gather_norm([ops.GatherStream(table, mean, std, img, 0, exact_div=False)], starts, W, 1)
+    assert torch.equal(xb.view(B, W, K), img)
+    y_ref = ops.gemm_bf16(img.view(B * W, K), w, B * W, 512, K, True, True, bias=bias, relu=True)
+    ulp = (y.view(torch.int16).int() - y_ref.view(torch.int16).int()).abs()
+    assert int(ulp.max()) <= 1 and float((ulp > 0).float().mean()) < 1e-2, (int(ulp.max()), float((ulp > 0).float().mean()))
+    want = torch.relu(img.view(B * W, K)[:4096].double() @ w.double().T + bias.double())
+    assert float((y[:4096].double() - want).abs().max() / want.abs().max()) < 2e-2
+    # no statistics: plain bf16 copy of the rows
+    xb0, _ = ops.gather_linear_bf16(table, None, None, starts, W, w, None, relu=False)
+    rows = starts.long()[:, None] + torch.arange(W, device="cuda")[None]
+    assert torch.equal(xb0.view(B, W, K), table[rows].to(torch.bfloat16))
+
+
 # ------------------------------------------------------------------------------------------- K2 fp32
 @pytest.mark.parametrize("shape", [(5120, 512, 2048), (1234, 256, 512), (77, 32, 256), (1, 6, 64), (130, 65, 33)])
 def test_linear_f32(shape, ops):

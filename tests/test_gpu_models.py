@@ -659,3 +659,33 @@ def test_lstm_rec_gen2_matches_gen1_with_dropout():
     # wt row nu < 64: column nu of W_ih; 64 <= nu < 128: hidden unit nu - 64 of W_hh (first half); and so on for the second half
     cat = torch.cat([w_ih[:, :64], w_hh[:, :64], w_ih[:, 64:], w_hh[:, 64:]], dim=1)          # [512, 256] in nu order
     assert torch.equal(wt.float(), cat.index_select(0, orig_of).t().contiguous().to(torch.bfloat16).float())
+
+
+def test_feature_extractor_fused_gather_matches_unfused():
+    """FeatureExtractor.forward_table (gather inside the first layer's kernel) against FeatureExtractor.forward on the batch K1
+    gathered: same features to bf16 noise, same gradients (the saved operands are bit-identical), and a train step through
+    engine.WindowTrainStep takes the fused path in the bf16 mode."""
+    from multimodal_error_detection_b200 import ops
+    from multimodal_error_detection_b200.modeling.models import FeatureExtractor
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    torch.manual_seed(0)
+    fe = FeatureExtractor(2048, 32, [512, 256], precision="bf16").to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    N, B, W = 20_000, 320, 16
+    table = torch.randn(N, 2048, device=DEV, generator=g).clamp_min_(0)
+    mean, std = torch.randn(2048, device=DEV, generator=g) * 0.2, torch.rand(2048, device=DEV, generator=g) + 0.5
+    starts = torch.randint(0, N - W, (B,), device=DEV, generator=g, dtype=torch.int64).to(torch.int32)
+    dy = torch.randn(B, W, 32, device=DEV, generator=g)
+    y1 = fe.forward_table(table, mean, std, starts, W)
+    y1.backward(dy)
+    g1 = [p.grad.clone() for p in fe.parameters()]
+    fe.zero_grad(set_to_none=True)
+    img = torch.empty(B, W, 2048, device=DEV, dtype=torch.bfloat16)
+    ops.gather_norm([ops.GatherStream(table, mean, std, img, 0, exact_div=False)], starts, W)
+    y2 = fe(img)
+    y2.backward(dy)
+    g2 = [p.grad.clone() for p in fe.parameters()]
+    nrel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
+    assert nrel(y1, y2) < 5e-3
+    assert max(nrel(a, b) for a, b in zip(g1, g2)) < 5e-3, [nrel(a, b) for a, b in zip(g1, g2)]
