@@ -13,14 +13,17 @@
 // CTA pair (cluster of 2, `tcgen05.mma.cta_group::2`, M = 256): CTA r gathers and converts rows [128 r, +128) of the pair's
 // 256-row tile and stages HALF of every W1 k-block (256 of the 512 output rows; every byte of W1 comes from L2 once per 256
 // rows), the leader issues two N = 256 MMAs per k-step into the 512 TMEM columns.  Warp roles per CTA: 0 TMA producer
-// (gather boxes + W1 tiles), 1 MMA issuer (leader) / TMEM allocator, 2..5 converters, 6..13 epilogue (bias, ReLU, bf16, stores).
+// (gather boxes), 1 MMA issuer (leader) / TMEM allocator, 2..5 converters, 6..13 epilogue (bias, ReLU, bf16, stores), 14 W1 tile
+// producer (its own warp: the gather producer must run ahead through the staging ring whatever the operand ring does).
 #include "tcgen05.cuh"
 
 namespace b200med {
 
-constexpr int kGgThreads = 14 * 32;
-constexpr int kGgFStages = 2;            // fp32 staging buffers (128 rows x 256 B)
-constexpr int kGgStages = 3;             // operand ring: A (16 KB) + B (32 KB) per stage
+constexpr int kGgThreads = 15 * 32;
+// Bytes in flight are what an HBM-bound kernel lives on: 4 fp32 staging buffers (128 KB per SM under way; with 2 the kernel
+// reached 0.61 of the copy peak, measured) and a 2-deep operand ring (the MMAs need half the time the loads need).
+constexpr int kGgFStages = 4;            // fp32 staging buffers (128 rows x 256 B)
+constexpr int kGgStages = 2;             // operand ring: A (16 KB) + B (32 KB) per stage
 constexpr int kGgN = 512;
 constexpr uint32_t kGgFBytes = 128 * 256;
 constexpr uint32_t kGgABytes = 128 * 128;
@@ -29,7 +32,9 @@ constexpr uint32_t kGgOffA = kGgFStages * kGgFBytes;
 constexpr uint32_t kGgOffB = kGgOffA + kGgStages * kGgABytes;
 constexpr uint32_t kGgOffBias = kGgOffB + kGgStages * kGgBBytes;
 constexpr uint32_t kGgOffBar = kGgOffBias + kGgN * 4;
-constexpr uint32_t kGgSmem = kGgOffBar + 256 + 1024;
+constexpr uint32_t kGgUsed = kGgOffBar + 256;
+constexpr uint32_t kGgSmem = kGgUsed + 512;          // + slack for the 1024-byte alignment (the declaration asks for it)
+static_assert(kGgSmem <= 232448, "over the 227 KB of shared memory a CTA can have");
 
 struct GatherGemmParams {
     const int32_t *starts;     // [B] first table row of every window
@@ -52,6 +57,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
                    const __grid_constant__ CUtensorMap tmap_xb, const GatherGemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    if (threadIdx.x == 0 && (uint32_t)(smem - smem_dyn) + kGgUsed > kGgSmem) __trap();
     unsigned char *f_sm = smem;
     unsigned char *a_sm = smem + kGgOffA;
     unsigned char *b_sm = smem + kGgOffB;
@@ -109,21 +115,14 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
                     st[w] = s;
                 }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int f = (int)(it % kGgFStages), s = (int)(it % kGgStages);
-                    const uint32_t fpar = (uint32_t)((it / kGgFStages) & 1), spar = (uint32_t)((it / kGgStages) & 1);
+                    const int f = (int)(it % kGgFStages);
+                    const uint32_t fpar = (uint32_t)((it / kGgFStages) & 1);
                     bar_wait(&f_empty[f], fpar ^ 1);
                     bar_expect_tx(&f_full[f], kGgFBytes);
 #pragma unroll
                     for (int w = 0; w < 8; ++w)
                         if (w < wins)
                             tma_load_2d_f32(f_sm + f * kGgFBytes + w * p.W * 256, &tmap_table, &f_full[f], kb * 64, st[w]);
-                    bar_wait(&slot_empty[s], spar ^ 1);
-                    const uint32_t lbar = mapa_rank(&b_full[s], 0);
-                    if (leader) bar_expect_tx(&b_full[s], 2 * kGgBBytes);
-                    // this CTA's half of the W1 k-block: rows [256 nh + 128 r, +128) for the two N = 256 MMAs
-                    tma_load_2d_pair(b_sm + s * kGgBBytes, &tmap_w, lbar, kb * 64, (int)rank * 128);
-                    tma_load_2d_pair(b_sm + s * kGgBBytes + 16384, &tmap_w, lbar, kb * 64, 256 + (int)rank * 128);
-                    if (!leader) bar_arrive_cluster(lbar);
                 }
             }
         }
@@ -156,6 +155,25 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
                 }
                 umma_commit_pair(acc_full);
                 acc_par ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 14) {
+        // ================================================================== W1 tile producer
+        if (lane == 0) {
+            long long it = 0;
+            for (long long tile = pair_id; tile < tiles; tile += pair_stride) {
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = (int)(it % kGgStages);
+                    const uint32_t spar = (uint32_t)((it / kGgStages) & 1);
+                    bar_wait(&slot_empty[s], spar ^ 1);
+                    const uint32_t lbar = mapa_rank(&b_full[s], 0);
+                    if (leader) bar_expect_tx(&b_full[s], 2 * kGgBBytes);
+                    // this CTA's half of the W1 k-block: rows [256 nh + 128 r, +128) for the two N = 256 MMAs
+                    tma_load_2d_pair(b_sm + s * kGgBBytes, &tmap_w, lbar, kb * 64, (int)rank * 128);
+                    tma_load_2d_pair(b_sm + s * kGgBBytes + 16384, &tmap_w, lbar, kb * 64, 256 + (int)rank * 128);
+                    if (!leader) bar_arrive_cluster(lbar);
+                }
             }
         }
         __syncwarp();
