@@ -16,13 +16,14 @@
 // (gather boxes), 1 MMA issuer (leader) / TMEM allocator, 2..5 converters, 6..13 epilogue (bias, ReLU, bf16, stores), 14 W1 tile
 // producer (its own warp: the gather producer must run ahead through the staging ring whatever the operand ring does).
 #include "tcgen05.cuh"
+#include <stdlib.h>
 
 namespace b200med {
 
 constexpr int kGgThreads = 15 * 32;
 // Bytes in flight are what an HBM-bound kernel lives on: 4 fp32 staging buffers (128 KB per SM under way; with 2 the kernel
 // reached 0.61 of the copy peak, measured) and a 2-deep operand ring (the MMAs need half the time the loads need).
-constexpr int kGgFStages = 4;            // fp32 staging buffers (128 rows x 256 B)
+constexpr int kGgFStages = 4;            // fp32 staging, in k-steps (128 rows x 256 B each)
 constexpr int kGgStages = 2;             // operand ring: A (16 KB) + B (32 KB) per stage
 constexpr int kGgN = 512;
 constexpr uint32_t kGgFBytes = 128 * 256;
@@ -44,6 +45,7 @@ struct GatherGemmParams {
     long long B, M;            // windows, rows = B*W
     int W, K, relu;
     long long table_rows;
+    int debug;                 // experiments only: 1 = no Xb store, 2 = no Y store
 };
 
 __device__ __forceinline__ void tma_load_2d_f32(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -52,6 +54,8 @@ __device__ __forceinline__ void tma_load_2d_f32(void *dst, const CUtensorMap *ma
         :: "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+// FK: k-steps per gather box (box = 64 FK fp32 columns x W rows; FK * 256 contiguous bytes per table row and request)
+template <int FK>
 __global__ void __launch_bounds__(kGgThreads, 1)
 gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_xb, const GatherGemmParams p) {
@@ -79,9 +83,11 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
     const long long tiles = (p.M + 255) / 256;
     const int nkb = p.K / 64;
     const int wins = 128 / p.W;                       // windows per CTA tile
+    constexpr int NF = kGgFStages / FK;               // staging buffers
+    constexpr uint32_t kFBuf = kGgFBytes * FK;        // bytes per staging buffer: 128 rows x (256 FK) B
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kGgFStages; ++i) { bar_init(&f_full[i], 1); bar_init(&f_empty[i], 4); }
+        for (int i = 0; i < NF; ++i) { bar_init(&f_full[i], 1); bar_init(&f_empty[i], 4); }
         for (int i = 0; i < kGgStages; ++i) { bar_init(&a_full[i], 8); bar_init(&b_full[i], 2); bar_init(&slot_empty[i], 1); }
         bar_init(acc_full, 1);
         bar_init(acc_empty, 16);
@@ -114,15 +120,15 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
                     if (s < 0 || (long long)s + p.W > p.table_rows) __trap();      // a window outside the table: the reference raises IndexError
                     st[w] = s;
                 }
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int f = (int)(it % kGgFStages);
-                    const uint32_t fpar = (uint32_t)((it / kGgFStages) & 1);
+                for (int kb = 0; kb < nkb; kb += FK, ++it) {
+                    const int f = (int)(it % NF);
+                    const uint32_t fpar = (uint32_t)((it / NF) & 1);
                     bar_wait(&f_empty[f], fpar ^ 1);
-                    bar_expect_tx(&f_full[f], kGgFBytes);
+                    bar_expect_tx(&f_full[f], kFBuf);
 #pragma unroll
                     for (int w = 0; w < 8; ++w)
                         if (w < wins)
-                            tma_load_2d_f32(f_sm + f * kGgFBytes + w * p.W * 256, &tmap_table, &f_full[f], kb * 64, st[w]);
+                            tma_load_2d_f32(f_sm + f * kFBuf + w * p.W * (256 * FK), &tmap_table, &f_full[f], kb * 64, st[w]);
                 }
             }
         }
@@ -187,8 +193,9 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
         for (long long tile = pair_id; tile < tiles; tile += pair_stride) {
             const long long m0 = tile * 256 + (long long)rank * 128;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int f = (int)(it % kGgFStages), s = (int)(it % kGgStages);
-                const uint32_t fpar = (uint32_t)((it / kGgFStages) & 1), spar = (uint32_t)((it / kGgStages) & 1);
+                const int f = (int)((it / FK) % NF), s = (int)(it % kGgStages);
+                const int sub = (int)(it % FK);                     // k-step inside the staging buffer (K % (64 FK) == 0)
+                const uint32_t fpar = (uint32_t)((it / FK / NF) & 1), spar = (uint32_t)((it / kGgStages) & 1);
                 float mu[4] = {0.f, 0.f, 0.f, 0.f}, iv[4] = {1.f, 1.f, 1.f, 1.f};
                 if (p.mean) {
                     const float4 m4 = __ldg(reinterpret_cast<const float4 *>(p.mean + kb * 64 + cg * 4));
@@ -199,13 +206,13 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
                 bar_wait(&slot_empty[s], spar ^ 1);                // the MMAs of the slot's previous use are done ...
                 if (issuer) bulk_wait_read<kGgStages - 1>();        // ... and so is the TMA store that read it
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                bar_wait(&f_full[f], fpar);
-                const unsigned char *fsrc = f_sm + f * kGgFBytes;
+                if (sub == 0) bar_wait(&f_full[f], fpar);
+                const unsigned char *fsrc = f_sm + f * kFBuf + sub * 256;
                 unsigned char *adst = a_sm + s * kGgABytes;
 #pragma unroll 4
                 for (int ps = 0; ps < 16; ++ps) {
                     const int row = cw * 32 + ps * 2 + rp;
-                    const float4 x = *reinterpret_cast<const float4 *>(fsrc + row * 256 + cg * 16);
+                    const float4 x = *reinterpret_cast<const float4 *>(fsrc + row * (256 * FK) + cg * 16);
                     const float y0 = (x.x - mu[0]) * iv[0], y1 = (x.y - mu[1]) * iv[1], y2 = (x.z - mu[2]) * iv[2], y3 = (x.w - mu[3]) * iv[3];
                     // 4 bf16 = 8 bytes: half of 16-byte slot cg/2 of the row, 128B swizzle (slot ^ row % 8)
                     unsigned char *dst = adst + row * 128 + ((((cg >> 1) ^ (row & 7)) << 4) | ((cg & 1) << 3));
@@ -214,13 +221,13 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
                 fence_proxy_async_smem();                           // generic-proxy writes -> visible to tcgen05.mma / TMA
                 __syncwarp();
                 if (lane == 0) {
-                    bar_arrive(&f_empty[f]);
+                    if (sub == FK - 1) bar_arrive(&f_empty[f]);
                     if (leader) bar_arrive(&a_full[s]);
                     else bar_arrive_cluster(mapa_rank(&a_full[s], 0));
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");     // the whole tile is written: it may leave for Xb
                 if (issuer) {
-                    tma_store_2d(&tmap_xb, adst, kb * 64, (int)m0);
+                    if (!(p.debug & 1)) tma_store_2d(&tmap_xb, adst, kb * 64, (int)m0);
                     bulk_commit();
                 }
             }
@@ -243,7 +250,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
                 uint32_t (&v)[32] = vbuf[ci & 1];
                 if (ci + 1 < 8) tmem_ld32_nowait(t_addr + (uint32_t)((ci + 1) * 32), vbuf[(ci + 1) & 1]);
                 const int c0 = half * 256 + ci * 32;
-                if (m < p.M) {
+                if (m < p.M && !(p.debug & 2)) {
                     uint32_t o[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
@@ -282,12 +289,12 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
 using namespace b200med;
 
 // fp32 table [rows, K]: box {64 columns, W rows}, no swizzle (the converters read it row-wise)
-static int make_tmap_table_f32(CUtensorMap *map, const void *ptr, long long K, long long rows, int W) {
+static int make_tmap_table_f32(CUtensorMap *map, const void *ptr, long long K, long long rows, int W, int box_cols) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200MED_E_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {64, (cuuint32_t)W};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)W};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -308,15 +315,23 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_linear_bf16
     if (!b200med_has_tcgen05()) { set_error("tcgen05 path needs a compute-capability 10.x device"); return B200MED_E_UNSUPPORTED; }
     const long long M = B * (long long)W;
     CUtensorMap tt, tw, tx;
-    if (int e = make_tmap_table_f32(&tt, table, K, table_rows, W)) return e;
+    static int fk_env = -1, dbg_env = 0;
+    if (fk_env < 0) {
+        const char *e1 = getenv("B200MED_GG_FK"), *e2 = getenv("B200MED_GG_DEBUG");
+        fk_env = e1 ? atoi(e1) : 1; dbg_env = e2 ? atoi(e2) : 0;
+    }
+    const int FK = (fk_env == 2 && K % 128 == 0) ? 2 : 1;
+    if (int e = make_tmap_table_f32(&tt, table, K, table_rows, W, 64 * FK)) return e;
     if (int e = make_tmap(&tw, w_bf16, K, N, K, 64, 128)) return e;            // W1 [512, K] bf16: box {64 k, 128 rows}
     if (int e = make_tmap(&tx, xb, K, M, K, 64, 128)) return e;                 // Xb [M, K] bf16: box {64 k, 128 rows}
     GatherGemmParams p{};
     p.starts = starts; p.mean = mean; p.stdv = stdv; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16 *>(y);
-    p.B = B; p.M = M; p.W = W; p.K = K; p.relu = relu; p.table_rows = table_rows;
+    p.B = B; p.M = M; p.W = W; p.K = K; p.relu = relu; p.table_rows = table_rows; p.debug = dbg_env;
     static bool attr_set = false;
     if (!attr_set) {
-        if (int e = check_cuda(cudaFuncSetAttribute(gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGgSmem),
+        if (int e = check_cuda(cudaFuncSetAttribute(gather_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGgSmem),
+                               "cudaFuncSetAttribute(gather_gemm)")) return e;
+        if (int e = check_cuda(cudaFuncSetAttribute(gather_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGgSmem),
                                "cudaFuncSetAttribute(gather_gemm)")) return e;
         attr_set = true;
     }
@@ -330,6 +345,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_linear_bf16
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (int e = check_cuda(cudaLaunchKernelEx(&cfg, gather_gemm_kernel, tt, tw, tx, p), "cudaLaunchKernelEx(gather_gemm)")) return e;
+    if (int e = check_cuda(FK == 2 ? cudaLaunchKernelEx(&cfg, gather_gemm_kernel<2>, tt, tw, tx, p)
+                                   : cudaLaunchKernelEx(&cfg, gather_gemm_kernel<1>, tt, tw, tx, p), "cudaLaunchKernelEx(gather_gemm)")) return e;
     return after_launch("gather_gemm_kernel");
 }
