@@ -1,7 +1,9 @@
 """Time the fused gather + first-Linear kernel alone (CUDA events, fresh windows every launch so the table reads miss L2).
 
-Experiment knobs are environment variables read once by the library: B200MED_GG_FK (k-steps per gather box: 1 or 2) and
-B200MED_GG_DEBUG (1: no Xb store, 2: no Y store, 3: neither).  `--sweep` re-runs itself once per combination.
+Experiment knobs are environment variables read once by the library: B200MED_GG_RINGS (ring depths fp32-staging / A / B as
+three digits: 323, 422, 224, 233, 332) and B200MED_GG_DEBUG (bits: 1 no Xb store, 2 no Y store, 4 no MMAs, 8 no conversion,
+16 no W1 loads, 32 no evict-first hints, 64 one MMA per k-step).  `--sweep` re-runs itself once per combination
+(GG_RINGS / GG_DEBUGS: comma-separated lists).
 """
 import argparse
 import json
@@ -34,7 +36,7 @@ def one(args):
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     med = ms[len(ms) // 2]
     alg = B * W * (K * 4 + K * 2 + 512 * 2)
-    print(json.dumps({"fk": os.environ.get("B200MED_GG_FK", "1"), "debug": os.environ.get("B200MED_GG_DEBUG", "0"), "B": B, "W": W,
+    print(json.dumps({"rings": os.environ.get("B200MED_GG_RINGS", "323"), "debug": os.environ.get("B200MED_GG_DEBUG", "0"), "B": B, "W": W,
                       "ms_median": round(med, 4), "ms_min": round(ms[0], 4), "GBps_algorithmic": round(alg / med / 1e6, 1)}))
 
 
@@ -47,9 +49,9 @@ if __name__ == "__main__":
     ap.add_argument("--sweep", action="store_true")
     args = ap.parse_args()
     if args.sweep:
-        for fk in ("1", "2"):
-            for dbg in ("0", "1", "2", "3"):
-                env = dict(os.environ, B200MED_GG_FK=fk, B200MED_GG_DEBUG=dbg)
+        for rings in os.environ.get("GG_RINGS", "323,422").split(","):
+            for dbg in os.environ.get("GG_DEBUGS", "0,1,2,3").split(","):
+                env = dict(os.environ, B200MED_GG_RINGS=rings, B200MED_GG_DEBUG=dbg)
                 subprocess.run([sys.executable, __file__, "--rows", str(args.rows), "--batch", str(args.batch), "--window", str(args.window),
                                 "--iters", str(args.iters)], env=env, check=False)
     else:

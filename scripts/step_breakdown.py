@@ -22,7 +22,7 @@ idx = torch.randperm(len(ds), generator=torch.Generator().manual_seed(0)).repeat
 names = ["index+labels, K1 (if not prefetched)", "FE forward (+cat)", "head forward (pack, x-part GEMMs, LSTM recurrence, MLP)",
          "loss", "head backward (MLP, LSTM recurrence, dX GEMMs)", "FE backward (+ joined LSTM weight gradients)",
          "gradient collect + Adam", "join of the prefetch stream"]
-for prefetch in (False, True):
+for prefetch in ((False,) if os.environ.get("ONLY_NO_PREFETCH") else (False, True)):
     st = WindowTrainStep(ds, fe, model, crit, opt, kw, A.batch, prefetch=prefetch)
     st.phase_events = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(9)]
     mu._set_train(model, fe, kw, True)
