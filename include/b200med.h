@@ -182,6 +182,10 @@ int b200med_linear_bwd_weight_f32(const float *dy, const float *x, float *dw, fl
  *   out_layout: B200MED_LAYOUT_ROWMAJOR, or B200MED_LAYOUT_RBI32 (needs split_k = 1, no mask, N a multiple of
  *   the vector width, D allocated for M rounded up to 32 rows; ldd is ignored).                    */
 int64_t b200med_gemm_bf16_ws_bytes(int64_t M, int64_t N, int64_t K, int32_t split_k);
+/* The split_k that fills the SMs the calling thread may use (b200med_set_sm_limit) in whole waves for this shape: the
+ * weight gradients dW = dY^T X of MED/modeling/modeling_utils.py:364 (loss.backward()) are [out x in] products over all
+ * B*W rows.  b_kmajor as in b200med_gemm_bf16.                                                                        */
+int32_t b200med_gemm_bf16_pick_split(int64_t M, int64_t N, int64_t K, int32_t b_kmajor);
 int b200med_gemm_bf16(const void *A, const void *B, void *D, const float *bias, const void *mask,
                       int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd,
                       int32_t a_kmajor, int32_t b_kmajor, int32_t out_dtype, int32_t relu,
@@ -197,6 +201,9 @@ int64_t b200med_colsum_ws_bytes(int64_t M, int32_t N);
 /* fp32 <-> bf16 conversion and [R,C] -> [C,R] transpose helpers used between layers. */
 int b200med_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stream);
 int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream);
+/* y = bf16(max(x, 0)): the F.relu in front of the LSTM head's Linear stack (MED/modeling/models.py:205) folded into the cast
+ * that makes the tensor-core operand (bf16 mode).                                                                      */
+int b200med_relu_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LSTM head (MED/modeling/models.py:135-210) in throughput mode: every time step is one b200med_gemm_bf16

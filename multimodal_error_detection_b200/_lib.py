@@ -43,12 +43,14 @@ SIGNATURES = {
     "b200med_linear_bwd_weight_ws_bytes": (_i64, [_i64, _i32, _i32]),
     "b200med_linear_bwd_weight_f32": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
     "b200med_gemm_bf16_ws_bytes": (_i64, [_i64, _i64, _i64, _i32]),
+    "b200med_gemm_bf16_pick_split": (_i32, [_i64, _i64, _i64, _i32]),
     "b200med_gemm_bf16": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32,
                                     _i32, _i32, _p, _p]),
     "b200med_has_tcgen05": (C.c_int, []),
     "b200med_colsum": (C.c_int, [_p, _i32, _p, _i64, _i32, _i64, _p, _p]),
     "b200med_colsum_ws_bytes": (_i64, [_i64, _i32]),
     "b200med_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
+    "b200med_relu_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_cast_bf16_to_f32": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_lstm_pack_inputs": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "b200med_lstm_rec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p,

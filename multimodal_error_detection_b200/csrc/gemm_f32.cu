@@ -255,6 +255,10 @@ __global__ void cast_f32_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __float2bfloat16_rn(x[i]);
 }
+__global__ void relu_cast_f32_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __float2bfloat16_rn(fmaxf(x[i], 0.0f));
+}
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __bfloat162float(x[i]);
@@ -439,6 +443,14 @@ extern "C" __attribute__((visibility("default"))) int b200med_cast_f32_to_bf16(c
     cast_f32_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
         x, reinterpret_cast<__nv_bfloat16 *>(y), n);
     return after_launch("cast_f32_bf16_kernel");
+}
+extern "C" __attribute__((visibility("default"))) int b200med_relu_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stream) {
+    if (n <= 0) return B200MED_OK;
+    B200MED_REQUIRE(x && y, "null pointer");
+    const long long blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
+    relu_cast_f32_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<__nv_bfloat16 *>(y), n);
+    return after_launch("relu_cast_f32_bf16_kernel");
 }
 extern "C" __attribute__((visibility("default"))) int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream) {
     if (n <= 0) return B200MED_OK;

@@ -516,6 +516,40 @@ extern "C" __attribute__((visibility("default"))) int b200med_has_tcgen05(void) 
     return major == 10 ? 1 : 0;
 }
 
+static bool gemm_pair_allowed() {
+    static const bool v = []() { const char *e = getenv("B200MED_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+    return v;
+}
+
+// Split-K choice for the weight-gradient GEMMs (small M x N, K = all rows of the batch): the persistent kernel deals
+// tiles * split work items over the SMs (or SM pairs), so the cost is WAVES x items' length, not the item count -- the first
+// heuristic ("2 items per SM") gave the layer-1 gradient 160 items on 74 pairs = 3 waves at 72 % (245 us; 9 splits = 2 full
+// waves).  Cost model in units of one 128 x 256 x 64 k-block per SM: waves * (k-blocks per split + 6 for the partial-tile
+// epilogue) + the fixed-order reduction of the partials (~3.9 per split and 2^20 output elements, measured).
+extern "C" __attribute__((visibility("default"))) int32_t b200med_gemm_bf16_pick_split(int64_t M, int64_t N, int64_t K,
+                                                                                       int32_t b_kmajor) {
+    if (M < 1 || N < 1 || K < 1) return 1;
+    const int block_n = pick_block_n(N, b_kmajor);
+    const int nkb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+    if (nkb < 16) return 1;
+    const int sms = num_sms();
+    double best = 1e300;
+    int best_s = 1;
+    for (int s = 1; s <= 160 && nkb / s >= 8; ++s) {
+        const int kb_per = (nkb + s - 1) / s;
+        if ((nkb + kb_per - 1) / kb_per != s) continue;
+        const bool pair = gemm_pair_allowed() && block_n == 256 && M >= 256 && N % 256 == 0 && nkb / s >= 8;
+        const long long tiles = pair ? ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + 255) / 256)
+                                     : ((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+        const long long units = pair ? sms / 2 : sms;
+        const long long waves = (tiles * s + units - 1) / units;
+        const double cost = (double)waves * (kb_per + 6.0) * (block_n / 256.0) +
+                            (s > 1 ? 3.9 * s * (double)M * (double)N / 1048576.0 : 0.0);
+        if (cost < best - 1e-9) { best = cost; best_s = s; }
+    }
+    return best_s;
+}
+
 extern "C" __attribute__((visibility("default"))) int64_t b200med_gemm_bf16_ws_bytes(int64_t M, int64_t N, int64_t K, int32_t split_k) {
     (void)K;
     return split_k > 1 ? (int64_t)split_k * M * N * 4 : 0;
@@ -549,8 +583,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
     // CTA-pair mode (cta_group::2, 256 x 256 tiles): the wide GEMMs whose K loop is long enough to be bound by the
     // L2 -> shared-memory operand traffic of the 1-CTA kernel (FE layer 1 forward 231 -> 210 us, weight gradient 260 -> 238 us,
     // measured A/B on one box).  B200MED_GEMM_PAIR=0 switches it off.
-    static const bool pair_allowed = []() { const char *e = getenv("B200MED_GEMM_PAIR"); return !(e && e[0] == '0'); }();
-    const bool pair = pair_allowed && block_n == 256 && M >= 256 && N % 256 == 0 && nkb / split_k >= 8;
+    const bool pair = gemm_pair_allowed() && block_n == 256 && M >= 256 && N % 256 == 0 && nkb / split_k >= 8;
 
     CUtensorMap ta, tb;
     // K-major operand: rows x K, K contiguous -> box {64 k, rows}.  MN-major: K x rows -> box {64 rows, 64 k}.

@@ -3,13 +3,14 @@ b200med kernels, as two autograd nodes with explicit forward / backward launch s
 
 * :class:`MLPTailFunction` -- ``[ReLU ->] (Linear -> ReLU -> BatchNorm1d)* -> Linear``: fp32 SIMT GEMMs with the ReLUs folded into
   their operand loads / epilogues (``b200med_gemm_f32``), BatchNorm as deterministic two-kernel passes (``b200med_bn_fwd`` /
-  ``_bwd``, the backward also applies the ReLU mask).
+  ``_bwd``, the backward also applies the ReLU mask).  In the bf16 throughput mode the hidden layers' products run on the
+  tcgen05 GEMM (bf16 operands, fp32 accumulation and outputs).
 * :class:`ConvStackFunction` -- ``(Conv1d(k=3) -> MaxPool1d(2) -> Dropout -> BatchNorm1d)* -> Flatten`` on TIME-MAJOR activations:
   the convolution is a GEMM over overlapping rows (no im2col copy, csrc/head.cu), pool + dropout one elementwise kernel.
 
 The ``nn.Module`` classes of ``modeling/models.py`` only hold the parameters (same ``state_dict`` keys as the reference); these
-functions read them.  fp32 arithmetic in both precision modes: the heads are < 3 % of the model FLOPs, and the 1e-5 parity bar of
-the fp32 mode then holds for them by construction.
+functions read them.  BatchNorm, pooling and the CNN head's convolutions are fp32 arithmetic in both precision modes, so the 1e-5
+parity bar of the fp32 mode holds for them by construction.
 """
 from __future__ import annotations
 
@@ -23,18 +24,35 @@ def _bn_tensors(bn: nn.BatchNorm1d):
     return [bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked]
 
 
+def _tc_ok(W: torch.Tensor) -> bool:
+    """Layers the bf16 tcgen05 GEMM serves in the throughput mode: K a multiple of the 64-element k-block, at least 32 outputs
+    (the 64 -> n_classes output layer is a GEMV and stays on the fp32 kernel)."""
+    return W.shape[1] % 64 == 0 and W.shape[0] >= 32
+
+
 class MLPTailFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, relu_in, training, bn_cfg, *t):
+    def forward(ctx, x, relu_in, training, bn_cfg, precision, *t):
         """x [B, K]; t = (W, b, gamma, beta, running_mean, running_var, num_batches_tracked) per hidden layer, then (W, b) of
-        the output layer; bn_cfg = [(eps, momentum)] per hidden layer."""
+        the output layer; bn_cfg = [(eps, momentum)] per hidden layer.  precision "bf16": the hidden layers' products (forward,
+        data and weight gradients) run on the tcgen05 GEMM with bf16 operands and fp32 accumulation / outputs (the fp32 SIMT
+        GEMMs of these three small layers were 0.17 ms of the 2.1 ms bf16 step); BatchNorm and the output layer stay fp32."""
         n_hidden = len(bn_cfg)
         x = x.contiguous().float()
-        a_in, acts, ys, stats = x, [], [], []
+        B = x.shape[0]
+        tc = [precision == "bf16" and ops.has_tcgen05() and _tc_ok(t[7 * i]) for i in range(n_hidden)]
+        a_in, acts, ys, stats, ins_b, wbs = x, [], [], [], [], []
         for i in range(n_hidden):
             W, b, gamma, beta, rm, rv, nbt = t[7 * i:7 * i + 7]
-            flags = ops.GEMM_RELU | (ops.GEMM_RELU_A if (i == 0 and relu_in) else 0)
-            a = ops.linear_f32(a_in, W.detach(), b.detach(), flags)
+            if tc[i]:
+                xb = ops.to_bf16(a_in, relu=(i == 0 and relu_in))
+                wb = ops.to_bf16(W.detach().contiguous())
+                a = ops.gemm_bf16(xb, wb, B, W.shape[0], W.shape[1], True, True, bias=b.detach(), relu=True, out_dtype=torch.float32)
+                ins_b.append(xb); wbs.append(wb)
+            else:
+                flags = ops.GEMM_RELU | (ops.GEMM_RELU_A if (i == 0 and relu_in) else 0)
+                a = ops.linear_f32(a_in, W.detach(), b.detach(), flags)
+                ins_b.append(None); wbs.append(None)
             eps, mom = bn_cfg[i]
             if mom is None:          # nn.BatchNorm1d(momentum=None): cumulative moving average
                 mom = 1.0 / float(nbt.item() + 1)
@@ -44,11 +62,15 @@ class MLPTailFunction(torch.autograd.Function):
         Wl, bl = t[7 * n_hidden], t[7 * n_hidden + 1]
         flags = ops.GEMM_RELU_A if (n_hidden == 0 and relu_in) else 0
         out = ops.linear_f32(a_in, Wl.detach(), bl.detach(), flags)
-        ctx.relu_in, ctx.training, ctx.n_hidden = relu_in, training, n_hidden
+        ctx.relu_in, ctx.training, ctx.n_hidden, ctx.tc = relu_in, training, n_hidden, tc
         saved = [x] + acts + ys
         for sm, sr in stats:
             saved += [sm, sr] if training else []
-        ctx.save_for_backward(*saved, *[t[7 * i] for i in range(n_hidden)], *[t[7 * i + 2] for i in range(n_hidden)], Wl)
+        ctx.n_extra = 0
+        extra = []
+        if training:
+            extra = [v for i in range(n_hidden) if tc[i] for v in (ins_b[i], wbs[i])]
+        ctx.save_for_backward(*saved, *[t[7 * i] for i in range(n_hidden)], *[t[7 * i + 2] for i in range(n_hidden)], Wl, *extra)
         return out
 
     @staticmethod
@@ -56,13 +78,19 @@ class MLPTailFunction(torch.autograd.Function):
         if not ctx.training:
             raise NotImplementedError("b200med: backward through the head in eval mode (running BatchNorm statistics) is not "
                                       "part of the reference's train / validation loops")
-        n = ctx.n_hidden
+        n, tc = ctx.n_hidden, ctx.tc
         sv = ctx.saved_tensors
         x, acts, ys = sv[0], sv[1:1 + n], sv[1 + n:1 + 2 * n]
         stats = sv[1 + 2 * n:1 + 4 * n]
         Ws, gammas, Wl = sv[1 + 4 * n:1 + 5 * n], sv[1 + 5 * n:1 + 6 * n], sv[1 + 6 * n]
+        extra = list(sv[2 + 6 * n:])
+        ins_b, wbs = [None] * n, [None] * n
+        for i in range(n):
+            if tc[i]:
+                ins_b[i], wbs[i] = extra.pop(0), extra.pop(0)
         grads = [None] * (7 * n + 2)
         g = dout.contiguous().float()
+        B = g.shape[0]
         last_in = ys[-1] if n else x
         grads[7 * n] = ops.linear_wgrad_f32(g, last_in, relu_x=(n == 0 and ctx.relu_in))
         grads[7 * n + 1] = ops.colsum(g)
@@ -72,18 +100,28 @@ class MLPTailFunction(torch.autograd.Function):
         for i in reversed(range(n)):
             dz, dgamma, dbeta = ops.bn_bwd(g, acts[i], gammas[i], stats[2 * i], stats[2 * i + 1], relu_mask=True)
             inp = ys[i - 1] if i > 0 else x
-            grads[7 * i] = ops.linear_wgrad_f32(dz, inp, relu_x=(i == 0 and ctx.relu_in))
             grads[7 * i + 1] = ops.colsum(dz)
             grads[7 * i + 2], grads[7 * i + 3] = dgamma, dbeta
+            if tc[i]:
+                N, K = Ws[i].shape
+                dzb = ops.to_bf16(dz)
+                # dW [N, K] = dz^T in: both operands reduce over their row (batch) index -> MN-major, deterministic split-K
+                grads[7 * i] = ops.gemm_bf16(dzb, ins_b[i], N, K, B, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
+                                             split_k=ops.gemm_split_k(N, K, B))
+                if i > 0 or need_dx:     # d_in [B, K] = dz [B, N] W [N, K]; the first layer's input went through the folded ReLU
+                    g = ops.gemm_bf16(dzb, wbs[i], B, K, N, a_kmajor=True, b_kmajor=False, out_dtype=torch.float32,
+                                      mask=ins_b[i] if (i == 0 and ctx.relu_in) else None)
+                continue
+            grads[7 * i] = ops.linear_wgrad_f32(dz, inp, relu_x=(i == 0 and ctx.relu_in))
             if i > 0:
                 g = ops.linear_dgrad_f32(dz, Ws[i])
             elif need_dx:
                 g = ops.linear_dgrad_f32(dz, Ws[i], mask=x if ctx.relu_in else None)
-        return (g if need_dx else None, None, None, None, *grads)
+        return (g if need_dx else None, None, None, None, None, *grads)
 
 
-def mlp_tail(x: torch.Tensor, seq: nn.Sequential, relu_in: bool, training: bool) -> torch.Tensor:
-    """Run ``seq`` = [Flatten,] (Linear, ReLU, BatchNorm1d)*, Linear on the fused kernels."""
+def mlp_tail(x: torch.Tensor, seq: nn.Sequential, relu_in: bool, training: bool, precision: str = "fp32") -> torch.Tensor:
+    """Run ``seq`` = [Flatten,] (Linear, ReLU, BatchNorm1d)*, Linear on the fused kernels (``precision``: see MLPTailFunction)."""
     mods = [m for m in seq if not isinstance(m, nn.Flatten)]
     tensors, cfg, i = [], [], 0
     while i < len(mods):
@@ -100,7 +138,7 @@ def mlp_tail(x: torch.Tensor, seq: nn.Sequential, relu_in: bool, training: bool)
             i += 1
         else:
             raise ValueError("b200med head: the fused MLP expects (Linear, ReLU, BatchNorm1d)* followed by one Linear")
-    return MLPTailFunction.apply(x.reshape(x.shape[0], -1), relu_in, training, cfg, *tensors)
+    return MLPTailFunction.apply(x.reshape(x.shape[0], -1), relu_in, training, cfg, precision, *tensors)
 
 
 class ConvStackFunction(torch.autograd.Function):

@@ -27,11 +27,6 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _split_k(tiles: int, k_blocks: int) -> int:
-    want = max(1, (2 * 148 + tiles - 1) // tiles)
-    return max(1, min(want, k_blocks // 8 if k_blocks >= 16 else 1))
-
-
 class LSTMStackFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, drop_p, seed_dev, *params):
@@ -104,9 +99,8 @@ class LSTMStackFunction(torch.autograd.Function):
                 # [dx_t | dh_{t-1}] [B, Kp] = dG_t [B, 4H] * Wcat [4H, Kp]   (B operand MN-major)
                 ops.gemm_bf16(dG[t], Wb[l], B, Kp[l], 4 * H, True, False, out_dtype=torch.float32, out=dA[t])
             # dWcat [4H, Kp] = dG^T A over all W*B rows (both operands MN-major), deterministic split-K
-            tiles = ((4 * H + 127) // 128) * ((Kp[l] + 255) // 256)
             dW = ops.gemm_bf16(dG.view(W * B, 4 * H), A[l].view(W * B, Kp[l]), 4 * H, Kp[l], W * B, False, False,
-                               out_dtype=torch.float32, split_k=_split_k(tiles, (W * B + 63) // 64))
+                               out_dtype=torch.float32, split_k=ops.gemm_split_k(4 * H, Kp[l], W * B))
             db = ops.colsum(dG.view(W * B, 4 * H))
             grads[4 * l] = dW[:, :ins[l]].contiguous()
             grads[4 * l + 1] = dW[:, ins[l]:ins[l] + H].contiguous()
@@ -301,9 +295,8 @@ class LSTMRecFunction(torch.autograd.Function):
             side.wait_stream(main)
             with torch.cuda.stream(side), ops.sm_limit(SIDE_SMS):
                 # dWcat [4H, Kp] = dG^T [x | h_prev] over all W*Bp rows (both operands MN-major), deterministic split-K
-                tiles = ((4 * H + 127) // 128) * ((Kp[l] + 255) // 256)
                 dW = ops.gemm_bf16(dG, A[l].view(W * Bp, Kp[l]), 4 * H, Kp[l], W * Bp, False, False,
-                                   out_dtype=torch.float32, split_k=_split_k(tiles, (W * Bp + 63) // 64))
+                                   out_dtype=torch.float32, split_k=ops.gemm_split_k(4 * H, Kp[l], W * Bp))
                 dbp = ops.colsum(dG)
                 if gen2:      # one kernel: un-permute the gate rows, split [x | h] columns, both bias gradients
                     gw = [torch.empty(4 * H, ins[l], dtype=torch.float32, device=dev), torch.empty(4 * H, H, dtype=torch.float32, device=dev),

@@ -21,12 +21,6 @@ import torch.nn.functional as F
 from .. import ops
 
 
-def _split_k(tiles: int, k_blocks: int) -> int:
-    """Enough K-splits to put ~2 CTAs of work on every SM, at least 8 k-blocks per split."""
-    want = max(1, (2 * 148 + tiles - 1) // tiles)
-    return max(1, min(want, k_blocks // 8 if k_blocks >= 16 else 1))
-
-
 # Data-parallel overlap hook (set by modeling_utils._backward when several ranks train): called inside the backward of the
 # FeatureExtractor right BEFORE the gradients of its FIRST layer -- the last and longest GEMM of the whole backward (dW1 is a
 # [512 x 2048] product over all B*W rows) -- with every other gradient of the step already computed.  The hook moves those into
@@ -113,9 +107,8 @@ class _MLPFunction(torch.autograd.Function):
                 grads = EARLY_EXCHANGE_HOOK(ctx.params, grads)
             N, K = weights[i].shape
             # dW[N,K] = g[M,N]^T acts_i[M,K]: both operands reduce over their ROW index -> MN-major
-            tiles = ((N + 127) // 128) * ((K + 255) // 256)
             grads[2 * i] = ops.gemm_bf16(g, acts[i], N, K, M, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
-                                         split_k=_split_k(tiles, (M + 63) // 64))
+                                         split_k=ops.gemm_split_k(N, K, M))
             grads[2 * i + 1] = ops.colsum(g)
             if i > 0:    # dh[M,K] = g[M,N] W[N,K], masked by relu'(acts_i)
                 g = ops.gemm_bf16(g, weights[i], M, K, N, a_kmajor=True, b_kmajor=False, mask=acts[i])
@@ -248,7 +241,7 @@ class LSTM(nn.Module):
             self._drop_seed.add_(1)
         # only h_{W-1} of the top layer is needed: the reference takes F.relu(out)[:, -1, :] (models.py:205-206)
         h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed, precision=self.precision)
-        return mlp_tail(h, self.linear_layers, relu_in=True, training=self.training)
+        return mlp_tail(h, self.linear_layers, relu_in=True, training=self.training, precision=self.precision)
 
     def initialize_weights(self):
         for m in self.modules():

@@ -390,6 +390,11 @@ def gemm_bf16(A, B, M, N, K, a_kmajor=True, b_kmajor=True, bias=None, mask=None,
     return D
 
 
+def gemm_split_k(M: int, N: int, K: int, b_kmajor: bool = False) -> int:
+    """split_k of a weight-gradient GEMM that fills the SMs this thread may use in whole waves (csrc/gemm_tcgen05.cu)."""
+    return int(_lib.load().b200med_gemm_bf16_pick_split(M, N, K, int(b_kmajor)))
+
+
 def colsum(dy: torch.Tensor) -> torch.Tensor:
     dy = _need(dy, None, "dy")
     M, N = dy.shape
@@ -399,10 +404,10 @@ def colsum(dy: torch.Tensor) -> torch.Tensor:
     return db
 
 
-def to_bf16(x: torch.Tensor, out=None) -> torch.Tensor:
+def to_bf16(x: torch.Tensor, out=None, relu: bool = False) -> torch.Tensor:
     x = _need(x, torch.float32, "x")
     y = out if out is not None else torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    call("b200med_cast_f32_to_bf16", _ptr(x), _ptr(y), x.numel(), _stream())
+    call("b200med_relu_cast_f32_to_bf16" if relu else "b200med_cast_f32_to_bf16", _ptr(x), _ptr(y), x.numel(), _stream())
     return y
 
 

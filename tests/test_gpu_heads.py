@@ -86,6 +86,56 @@ def test_mlp_tail_vs_torch(relu_in, dims, B):
         assert nrel(mlp_tail(x.to(DEV), seq, relu_in=relu_in, training=False), ref(torch.relu(x.double()) if relu_in else x.double())) < 1e-5
 
 
+@pytest.mark.parametrize("relu_in,dims,B", [(True, [128, 256, 64, 1], 8192), (True, [128, 256, 64, 1], 700), (False, [128, 256, 32, 16, 6], 12)])
+def test_mlp_tail_bf16_vs_torch(relu_in, dims, B):
+    """The same head tail in the bf16 throughput mode (hidden-layer products on the tcgen05 GEMM, bf16 operands, fp32
+    accumulation; BatchNorm and the output layer fp32) against the fp64 nn.Sequential: the bf16-mode bar of north_star, 2e-2
+    norm-wise relative, on the logits, the input gradient and every parameter gradient."""
+    from multimodal_error_detection_b200 import ops
+    from multimodal_error_detection_b200.heads import mlp_tail
+    if not ops.has_tcgen05():
+        pytest.skip("needs a compute-capability 10.x device")
+    torch.manual_seed(B + 1)
+    mods = []
+    for i in range(len(dims) - 2):
+        mods += [nn.Linear(dims[i], dims[i + 1]), nn.ReLU(), nn.BatchNorm1d(dims[i + 1])]
+    mods += [nn.Linear(dims[-2], dims[-1])]
+    seq = nn.Sequential(*mods)
+    for m in seq:
+        if isinstance(m, nn.BatchNorm1d):
+            nn.init.uniform_(m.weight, 0.5, 1.5); nn.init.normal_(m.bias)
+    ref = nn.Sequential(*[type(m)(*([m.in_features, m.out_features] if isinstance(m, nn.Linear) else [m.num_features] if isinstance(m, nn.BatchNorm1d) else []))
+                          for m in seq]).double()
+    ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in seq.state_dict().items()})
+    seq = seq.to(DEV).train(); ref.train()
+    x = torch.randn(B, dims[0])
+    dy = torch.randn(B, dims[-1])
+    xr = x.double().requires_grad_(True)
+    yr = ref(torch.relu(xr) if relu_in else xr)
+    yr.backward(dy.double())
+    xg = x.to(DEV).requires_grad_(True)
+    n0 = ops._lib.launch_count()
+    yg = mlp_tail(xg, seq, relu_in=relu_in, training=True, precision="bf16")
+    yg.backward(dy.to(DEV))
+    assert ops._lib.launch_count() > n0
+    assert nrel(yg, yr) < 2e-2
+
+    def frel(a, b):      # norm-wise: a unit whose pre-activation sits within bf16 rounding of zero flips its ReLU, and ONE flipped
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()      # unit moves a whole row of the input gradient
+        return float((a - b).norm() / b.norm().clamp_min(1e-30))
+    assert frel(xg.grad, xr.grad) < 2e-2
+    gmax = max(float(r.grad.norm()) for r in ref.parameters())
+    for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
+        scale = max(float(q.grad.norm()), 1e-3 * gmax)
+        assert float((p.grad.double().cpu() - q.grad).norm()) <= 2e-2 * scale, k
+    for (k, b), (_, c) in zip(seq.named_buffers(), ref.named_buffers()):
+        assert nrel(b.double(), c.double()) < 2e-2, k
+    seq.eval(); ref.eval()
+    with torch.no_grad():
+        ye = mlp_tail(x.to(DEV), seq, relu_in=relu_in, training=False, precision="bf16")
+        assert nrel(ye, ref(torch.relu(x.double()) if relu_in else x.double())) < 2e-2
+
+
 @pytest.mark.parametrize("W,B,view", [(10, 12, True), (10, 513, False), (30, 40, True), (30, 7, False)])
 def test_cnn_head_vs_torch(W, B, view):
     """The whole CNN head (conv-as-GEMM over overlapping time-major rows, pool + dropout(0), BatchNorm, MLP tail) against the
