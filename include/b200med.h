@@ -204,6 +204,13 @@ int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream);
 /* y = bf16(max(x, 0)): the F.relu in front of the LSTM head's Linear stack (MED/modeling/models.py:205) folded into the cast
  * that makes the tensor-core operand (bf16 mode).                                                                      */
 int b200med_relu_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stream);
+/* Split-bf16 operands for an fp32-like product on the bf16 tensor cores (the Linear layers of the LSTM head's tail,
+ * MED/modeling/models.py:166-186, in the bf16 mode): x [R,C] f32 (through max(.,0) when relu) = hi + lo, hi = bf16(x),
+ * lo = bf16(x - hi); the three products hi*hi' + lo*hi' + hi*lo' become ONE b200med_gemm_bf16 over a 3x longer reduction:
+ * a left operand is laid out (hi, lo, hi), a right operand (hi, hi, lo) (order 0 / 1).  row3 [R,3C]: blocks side by side in
+ * every row (reduction over columns); stack3 [3R,C]: blocks stacked (reduction over rows).  Either output may be NULL.  */
+int b200med_split_bf16x3(const float *x, void *row3, void *stack3, int64_t R, int32_t C, int32_t row_order,
+                         int32_t stack_order, int32_t relu, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LSTM head (MED/modeling/models.py:135-210) in throughput mode: every time step is one b200med_gemm_bf16
@@ -215,6 +222,15 @@ int b200med_relu_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stre
  * zeroes the padding columns [F,hoff) and [hoff+H,Kp) and the h_{-1} columns of step 0.              */
 int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int64_t Bpad, int32_t F, int32_t W, int32_t H,
                              int32_t Kp, int32_t hoff, int32_t x_layout, void *stream);
+/* The window path's head input built straight into A0 (replaces a 26-column gather, torch.cat and the pack above):
+ * define_inputs (MED/modeling/modeling_utils.py:40-47) concatenates the FeatureExtractor output with the standardised
+ * kinematics of the window (MED/dataset/CustomWindowDataset.py:56-60) and the LSTM head transposes it (models.py:204).
+ *   feats [B,W,Ca] f32; kin_table [table_rows,Cb] f32 device-resident frame table, starts [B] i32 first row of each window;
+ *   mean / stdv [stat_rows,Cb] or NULL, stat_rows = 1 or W; columns [0,Ca) <- feats, [Ca,Ca+Cb) <- (kin - mean) / std (IEEE);
+ *   padding and h_{-1} columns zeroed as in b200med_lstm_pack_inputs.  A window outside the table traps.            */
+int b200med_lstm_pack_parts(const float *feats, int32_t Ca, const float *kin_table, int64_t table_rows, int32_t Cb,
+                            const float *mean, const float *stdv, int32_t stat_rows, const int32_t *starts, void *A0,
+                            int64_t B, int64_t Bpad, int32_t W, int32_t H, int32_t Kp, int32_t hoff, void *stream);
 /* dx [B,F,W] f32 <- dA0 [W,Bpad,Kp] f32 (row-major) columns [0,F).                                   */
 int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int64_t Bpad, int32_t F, int32_t W, int32_t Kp,
                            int32_t x_layout, void *stream);

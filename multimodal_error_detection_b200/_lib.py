@@ -51,8 +51,10 @@ SIGNATURES = {
     "b200med_colsum_ws_bytes": (_i64, [_i64, _i32]),
     "b200med_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_relu_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
+    "b200med_split_bf16x3": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p]),
     "b200med_cast_bf16_to_f32": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_lstm_pack_inputs": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "b200med_lstm_pack_parts": (C.c_int, [_p, _i32, _p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]),
     "b200med_lstm_rec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p,
                                        C.c_uint64, _p]),
     "b200med_lstm_rec_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p, C.c_uint64, _p]),

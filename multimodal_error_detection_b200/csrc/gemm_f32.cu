@@ -259,6 +259,29 @@ __global__ void relu_cast_f32_bf16_kernel(const float *__restrict__ x, __nv_bflo
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __float2bfloat16_rn(fmaxf(x[i], 0.0f));
 }
+// x = hi + lo (+ 2^-17 |x|) with hi = bf16(x), lo = bf16(x - hi): three bf16 products hi*hi' + lo*hi' + hi*lo' carry an fp32-like
+// product on the bf16 tensor cores.  The three terms are folded into ONE GEMM by concatenating along its reduction dimension:
+// a LEFT operand is laid out (hi, lo, hi), a RIGHT operand (hi, hi, lo).  row3 [R, 3C]: the blocks side by side in every row
+// (reduction over columns); stack3 [3R, C]: the blocks one under the other (reduction over rows).  order 0 = left, 1 = right.
+__global__ void split_bf16x3_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ row3, __nv_bfloat16 *__restrict__ stack3,
+                                    long long R, int C, int row_order, int stack_order, int relu) {
+    const long long n = R * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = x[i];
+        if (relu) v = fmaxf(v, 0.0f);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const long long r = i / C;
+        const int c = (int)(i - r * C);
+        if (row3) {
+            __nv_bfloat16 *d = row3 + r * 3 * C + c;
+            d[0] = hi; d[C] = row_order ? hi : lo; d[2 * C] = row_order ? lo : hi;
+        }
+        if (stack3) {
+            stack3[i] = hi; stack3[n + i] = stack_order ? hi : lo; stack3[2 * n + i] = stack_order ? lo : hi;
+        }
+    }
+}
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __bfloat162float(x[i]);
@@ -451,6 +474,17 @@ extern "C" __attribute__((visibility("default"))) int b200med_relu_cast_f32_to_b
     relu_cast_f32_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
         x, reinterpret_cast<__nv_bfloat16 *>(y), n);
     return after_launch("relu_cast_f32_bf16_kernel");
+}
+extern "C" __attribute__((visibility("default"))) int b200med_split_bf16x3(const float *x, void *row3, void *stack3, int64_t R, int32_t C,
+                                                                           int32_t row_order, int32_t stack_order, int32_t relu,
+                                                                           void *stream) {
+    if (R <= 0 || C <= 0) return B200MED_OK;
+    B200MED_REQUIRE(x && (row3 || stack3), "null pointer");
+    B200MED_REQUIRE((row_order == 0 || row_order == 1) && (stack_order == 0 || stack_order == 1), "order: 0 = left operand, 1 = right operand");
+    const long long n = R * (long long)C, blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
+    split_bf16x3_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<__nv_bfloat16 *>(row3), reinterpret_cast<__nv_bfloat16 *>(stack3), R, C, row_order, stack_order, relu);
+    return after_launch("split_bf16x3_kernel");
 }
 extern "C" __attribute__((visibility("default"))) int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream) {
     if (n <= 0) return B200MED_OK;

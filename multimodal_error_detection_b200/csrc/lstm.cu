@@ -121,6 +121,52 @@ lstm_pack_bwf_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0
     }
 }
 
+// The head input of the window path built straight into the LSTM's first operand (define_inputs, MED/modeling/modeling_utils.py:40-47:
+// torch.cat((features, kinematics), dim = 2).permute(0, 2, 1), then models.py:204 transposes it back):
+//   A0[t][b][0:Ca]      = bf16(feats[b, t, :])                                   (FeatureExtractor output, fp32 [B, W, Ca])
+//   A0[t][b][Ca:Ca+Cb]  = bf16((kin_table[starts[b] + t, :] - mean) / std)       (CustomWindowDataset.py:56-60, IEEE subtract / divide)
+// plus the zero padding of lstm_pack_bwf_kernel.  One warp per (window, step) row.  Replaces gather (26 columns) + concat + pack.
+__global__ void __launch_bounds__(256)
+lstm_pack_parts_kernel(const float *__restrict__ feats, int Ca, const float *__restrict__ kin, long long table_rows, int Cb,
+                       const float *__restrict__ mean, const float *__restrict__ stdv, int stat_rows, const int32_t *__restrict__ starts,
+                       __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int W, int H, int Kp, int hoff) {
+    const int lane = threadIdx.x & 31;
+    const int F = Ca + Cb;
+    const long long nrows = B * W, warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+        const long long b = r / W;
+        const int t = (int)(r - b * W);
+        const long long row = (long long)starts[b] + t;
+        if (row < 0 || row >= table_rows) __trap();          // a window outside the table: the reference raises IndexError
+        const float *fs = feats + r * Ca;
+        const float *ks = kin + row * Cb;
+        const float *mu = mean ? mean + (stat_rows > 1 ? (long long)t * Cb : 0) : nullptr;
+        const float *sd = mean ? stdv + (stat_rows > 1 ? (long long)t * Cb : 0) : nullptr;
+        __nv_bfloat16 *dst = A0 + ((long long)t * Bpad + b) * Kp;
+        for (int k = lane * 2; k < Kp; k += 64) {
+            float v[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = k + j;
+                float x = 0.0f;
+                if (c < Ca) x = fs[c];
+                else if (c < F) {
+                    x = ks[c - Ca];
+                    if (mu) x = (x - mu[c - Ca]) / sd[c - Ca];
+                }
+                v[j] = x;
+            }
+            const bool h0 = k >= hoff && k < hoff + H, h1 = k + 1 >= hoff && k + 1 < hoff + H;
+            if ((h0 || h1) && t != 0) {          // the h_{t-1} columns of the steps t > 0 belong to the recurrence kernel
+                if (!h0) dst[k] = __float2bfloat16_rn(v[0]);
+                if (!h1) dst[k + 1] = __float2bfloat16_rn(v[1]);
+            } else {
+                *reinterpret_cast<__nv_bfloat162 *>(dst + k) = __floats2bfloat162_rn(v[0], v[1]);
+            }
+        }
+    }
+}
+
 // dx [B, W, F] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F)
 __global__ void __launch_bounds__(256)
 lstm_unpack_bwf_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F, int W, int Kp) {
@@ -309,6 +355,21 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_inputs(c
     lstm_pack_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, (size_t)kPackWin * F * (W + 1) * 4, (cudaStream_t)stream>>>(
         x, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, F, W, H, Kp, hoff);
     return after_launch("lstm_pack_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_parts(
+    const float *feats, int32_t Ca, const float *kin_table, int64_t table_rows, int32_t Cb, const float *mean, const float *stdv,
+    int32_t stat_rows, const int32_t *starts, void *A0, int64_t B, int64_t Bpad, int32_t W, int32_t H, int32_t Kp, int32_t hoff,
+    void *stream) {
+    B200MED_REQUIRE(B >= 1 && Bpad >= B && Ca >= 1 && Cb >= 0 && W >= 1 && H >= 1, "bad shape");
+    B200MED_REQUIRE(Kp % 2 == 0 && hoff % 2 == 0 && hoff >= Ca + Cb && hoff + H <= Kp, "bad operand geometry");
+    B200MED_REQUIRE(feats && starts && A0 && (Cb == 0 || kin_table), "null pointer");
+    B200MED_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean and std must both be given or both NULL");
+    B200MED_REQUIRE(stat_rows == 1 || stat_rows == W, "statistics: one row, or one per window step");
+    const long long blocks = (B * (long long)W + 7) / 8, cap = (long long)num_sms() * 8;
+    lstm_pack_parts_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        feats, Ca, kin_table, table_rows, Cb, mean, stdv, stat_rows, starts, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, W, H, Kp, hoff);
+    return after_launch("lstm_pack_parts_kernel");
 }
 
 extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int64_t Bpad,

@@ -109,18 +109,27 @@ class WindowTrainStep:
         self._mark(0)
         from . import ops
         labels = ops.take_rows(self.label_col, self.idx2[cur], out=self.labels)
+        parts = None
         if self.fused:
-            # kinematics through K1 (26 columns), the image stream gathered INSIDE the first FeatureExtractor layer
+            # the image stream is gathered INSIDE the first FeatureExtractor layer; the kinematics (26 columns) either inside the
+            # kernel that builds the LSTM's first operand (heads that take WindowParts) or through K1 + one concat kernel
             from .heads import concat_features
             starts = ops.take_rows(self.ds._starts, self.idx2[cur])
             km = self.ds._kin_stats
-            ops.gather_norm([ops.GatherStream(self.ds._kin_table, km[0] if km else None, km[1] if km else None, self.kin2[cur], 0, True)],
-                            starts, self.W)
+            by_parts = getattr(self.model, "accepts_parts", lambda: False)()
+            if not by_parts:
+                ops.gather_norm([ops.GatherStream(self.ds._kin_table, km[0] if km else None, km[1] if km else None, self.kin2[cur], 0, True)],
+                                starts, self.W)
             self._mark(1)
             im = self.ds._img_stats
             feats = self.fe.forward_table(self.ds._image_table, im[0] if im else None, im[1] if im else None, starts, self.W,
                                           events=self.gather_events)
-            inputs = concat_features(feats, self.kin2[cur]).permute(0, 2, 1)
+            if by_parts:
+                from .lstm_stack import WindowParts
+                parts = WindowParts(self.ds._kin_table, km[0] if km else None, km[1] if km else None, starts)
+                inputs = feats
+            else:
+                inputs = concat_features(feats, self.kin2[cur]).permute(0, 2, 1)
         else:
             if not self.prefetch:
                 self._gather(cur)
@@ -135,7 +144,7 @@ class WindowTrainStep:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 self._gather(nxt, self.prefetch_sms)      # leaves the other SMs to the main stream's kernels
-        outputs = self.model(inputs)
+        outputs = self.model(inputs) if parts is None else self.model(inputs, parts=parts)
         self._mark(3)
         static = isinstance(self.crit, mu.FusedBCEWithLogitsLoss)
         if static:      # K3 writes the step's persistent result buffers itself (no copies at the end of the step)

@@ -4,7 +4,7 @@ b200med kernels, as two autograd nodes with explicit forward / backward launch s
 * :class:`MLPTailFunction` -- ``[ReLU ->] (Linear -> ReLU -> BatchNorm1d)* -> Linear``: fp32 SIMT GEMMs with the ReLUs folded into
   their operand loads / epilogues (``b200med_gemm_f32``), BatchNorm as deterministic two-kernel passes (``b200med_bn_fwd`` /
   ``_bwd``, the backward also applies the ReLU mask).  In the bf16 throughput mode the hidden layers' products run on the
-  tcgen05 GEMM (bf16 operands, fp32 accumulation and outputs).
+  tcgen05 GEMM as split-bf16 (hi + lo) products: fp32-like accuracy, fp32 outputs.
 * :class:`ConvStackFunction` -- ``(Conv1d(k=3) -> MaxPool1d(2) -> Dropout -> BatchNorm1d)* -> Flatten`` on TIME-MAJOR activations:
   the convolution is a GEMM over overlapping rows (no im2col copy, csrc/head.cu), pool + dropout one elementwise kernel.
 
@@ -35,24 +35,28 @@ class MLPTailFunction(torch.autograd.Function):
     def forward(ctx, x, relu_in, training, bn_cfg, precision, *t):
         """x [B, K]; t = (W, b, gamma, beta, running_mean, running_var, num_batches_tracked) per hidden layer, then (W, b) of
         the output layer; bn_cfg = [(eps, momentum)] per hidden layer.  precision "bf16": the hidden layers' products (forward,
-        data and weight gradients) run on the tcgen05 GEMM with bf16 operands and fp32 accumulation / outputs (the fp32 SIMT
-        GEMMs of these three small layers were 0.17 ms of the 2.1 ms bf16 step); BatchNorm and the output layer stay fp32."""
+        data and weight gradients) run on the tcgen05 GEMM as SPLIT-bf16 products (x = hi + lo; hi*hi' + lo*hi' + hi*lo' folded into
+        one GEMM over a 3x longer reduction, b200med_split_bf16x3): fp32-like accuracy (~1e-5) at tensor-core speed.  The fp32
+        SIMT GEMMs of these three small layers were 0.17 ms of the 2.1 ms step; plain bf16 operands were tried and dropped: BatchNorm
+        over a small batch amplified their rounding past the 2e-2 bar (3 % on the logits at B = 12).  BatchNorm and the output
+        layer stay fp32 kernels."""
         n_hidden = len(bn_cfg)
         x = x.contiguous().float()
         B = x.shape[0]
         tc = [precision == "bf16" and ops.has_tcgen05() and _tc_ok(t[7 * i]) for i in range(n_hidden)]
-        a_in, acts, ys, stats, ins_b, wbs = x, [], [], [], [], []
+        a_in, acts, ys, stats, extra = x, [], [], [], []
         for i in range(n_hidden):
             W, b, gamma, beta, rm, rv, nbt = t[7 * i:7 * i + 7]
             if tc[i]:
-                xb = ops.to_bf16(a_in, relu=(i == 0 and relu_in))
-                wb = ops.to_bf16(W.detach().contiguous())
-                a = ops.gemm_bf16(xb, wb, B, W.shape[0], W.shape[1], True, True, bias=b.detach(), relu=True, out_dtype=torch.float32)
-                ins_b.append(xb); wbs.append(wb)
+                N, K = W.shape
+                # left operand (hi, lo, hi) by rows for this product; stacked RIGHT copy (hi, hi, lo) for the weight gradient
+                x_row, x_stack = ops.split_bf16x3(a_in, 0, 1 if training else None, relu=(i == 0 and relu_in))
+                w_row, w_stack = ops.split_bf16x3(W.detach().contiguous(), 1, 1 if training else None)
+                a = ops.gemm_bf16(x_row, w_row, B, N, 3 * K, True, True, bias=b.detach(), relu=True, out_dtype=torch.float32)
+                extra += [x_stack, w_stack] if training else []
             else:
                 flags = ops.GEMM_RELU | (ops.GEMM_RELU_A if (i == 0 and relu_in) else 0)
                 a = ops.linear_f32(a_in, W.detach(), b.detach(), flags)
-                ins_b.append(None); wbs.append(None)
             eps, mom = bn_cfg[i]
             if mom is None:          # nn.BatchNorm1d(momentum=None): cumulative moving average
                 mom = 1.0 / float(nbt.item() + 1)
@@ -66,10 +70,6 @@ class MLPTailFunction(torch.autograd.Function):
         saved = [x] + acts + ys
         for sm, sr in stats:
             saved += [sm, sr] if training else []
-        ctx.n_extra = 0
-        extra = []
-        if training:
-            extra = [v for i in range(n_hidden) if tc[i] for v in (ins_b[i], wbs[i])]
         ctx.save_for_backward(*saved, *[t[7 * i] for i in range(n_hidden)], *[t[7 * i + 2] for i in range(n_hidden)], Wl, *extra)
         return out
 
@@ -84,10 +84,10 @@ class MLPTailFunction(torch.autograd.Function):
         stats = sv[1 + 2 * n:1 + 4 * n]
         Ws, gammas, Wl = sv[1 + 4 * n:1 + 5 * n], sv[1 + 5 * n:1 + 6 * n], sv[1 + 6 * n]
         extra = list(sv[2 + 6 * n:])
-        ins_b, wbs = [None] * n, [None] * n
+        x_stack, w_stack = [None] * n, [None] * n
         for i in range(n):
             if tc[i]:
-                ins_b[i], wbs[i] = extra.pop(0), extra.pop(0)
+                x_stack[i], w_stack[i] = extra.pop(0), extra.pop(0)
         grads = [None] * (7 * n + 2)
         g = dout.contiguous().float()
         B = g.shape[0]
@@ -104,13 +104,15 @@ class MLPTailFunction(torch.autograd.Function):
             grads[7 * i + 2], grads[7 * i + 3] = dgamma, dbeta
             if tc[i]:
                 N, K = Ws[i].shape
-                dzb = ops.to_bf16(dz)
-                # dW [N, K] = dz^T in: both operands reduce over their row (batch) index -> MN-major, deterministic split-K
-                grads[7 * i] = ops.gemm_bf16(dzb, ins_b[i], N, K, B, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
-                                             split_k=ops.gemm_split_k(N, K, B))
-                if i > 0 or need_dx:     # d_in [B, K] = dz [B, N] W [N, K]; the first layer's input went through the folded ReLU
-                    g = ops.gemm_bf16(dzb, wbs[i], B, K, N, a_kmajor=True, b_kmajor=False, out_dtype=torch.float32,
-                                      mask=ins_b[i] if (i == 0 and ctx.relu_in) else None)
+                want_dx = i > 0 or need_dx
+                dz_row, dz_stack = ops.split_bf16x3(dz, 0 if want_dx else None, 0)
+                # dW [N, K] = dz^T in over the (3x stacked) batch rows: both operands MN-major, deterministic split-K
+                grads[7 * i] = ops.gemm_bf16(dz_stack, x_stack[i], N, K, 3 * B, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
+                                             split_k=ops.gemm_split_k(N, K, 3 * B))
+                if want_dx:     # d_in [B, K] = dz [B, 3N] W'' [3N, K]; the first layer's input went through the folded ReLU:
+                    # its mask is the hi block of the stacked copy (bf16(max(x, 0)) > 0 exactly where x > 0)
+                    g = ops.gemm_bf16(dz_row, w_stack[i], B, K, 3 * N, a_kmajor=True, b_kmajor=False, out_dtype=torch.float32,
+                                      mask=x_stack[i][:B] if (i == 0 and ctx.relu_in) else None)
                 continue
             grads[7 * i] = ops.linear_wgrad_f32(dz, inp, relu_x=(i == 0 and ctx.relu_in))
             if i > 0:

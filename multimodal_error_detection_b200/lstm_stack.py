@@ -173,6 +173,15 @@ def _dg_perm2(device):
     return _PERM[key]
 
 
+class WindowParts:
+    """The kinematics half of the window path's head input, still in the frame table: (table [N, Cb] f32, mean, std
+    ([1 | W, Cb] or None), starts [B] int32).  With it the recurrence's first operand is built from the FeatureExtractor output
+    [B, W, Ca] and the table rows in ONE kernel (b200med_lstm_pack_parts) instead of gather + torch.cat + pack."""
+
+    def __init__(self, table, mean, std, starts):
+        self.table, self.mean, self.std, self.starts = table, mean, std, starts
+
+
 class LSTMRecFunction(torch.autograd.Function):
     """Persistent-recurrence path (hidden_size 128).  Layer buffers, time-major with the batch padded to Bp (multiple
     of 32) rows per step:
@@ -181,8 +190,13 @@ class LSTMRecFunction(torch.autograd.Function):
     dX_l [W*Bp, inp_l] f32."""
 
     @staticmethod
-    def forward(ctx, x, drop_p, seed_dev, *params):
-        B, F, W = x.shape
+    def forward(ctx, x, drop_p, seed_dev, parts, *params):
+        """x: the head input [B, F, W]; or, with ``parts`` (a WindowParts), the FeatureExtractor output [B, W, Ca]."""
+        if parts is None:
+            B, F, W = x.shape
+        else:
+            B, W, Ca = x.shape
+            F = Ca + parts.table.shape[1]
         L = len(params) // 4
         H = params[1].shape[1]
         dev = x.device
@@ -195,9 +209,17 @@ class LSTMRecFunction(torch.autograd.Function):
         alloc = torch.empty if Bp == B else torch.zeros          # pad rows must hold finite values
         A = [alloc(W, Bp, Kp[l], dtype=torch.bfloat16, device=dev) for l in range(L)]
         # the reference hands the head cat(...).permute(0, 2, 1): a view of a contiguous [B, W, F] tensor -- read it as such
-        bwf = x.transpose(1, 2).is_contiguous() and not x.is_contiguous()
-        xsrc = x.transpose(1, 2) if bwf else x.contiguous()
-        call("b200med_lstm_pack_inputs", _raw(xsrc.data_ptr()), _raw(A[0].data_ptr()), B, Bp, F, W, H, Kp[0], inp[0], int(bwf), st)
+        if parts is not None:
+            bwf = True
+            feats = x.contiguous().float()
+            kt, km, ks = parts.table, parts.mean, parts.std
+            call("b200med_lstm_pack_parts", _raw(feats.data_ptr()), Ca, _raw(kt.data_ptr()), kt.shape[0], kt.shape[1],
+                 _raw(km.data_ptr() if km is not None else 0), _raw(ks.data_ptr() if ks is not None else 0),
+                 km.shape[0] if km is not None else 1, _raw(parts.starts.data_ptr()), _raw(A[0].data_ptr()), B, Bp, W, H, Kp[0], inp[0], st)
+        else:
+            bwf = x.transpose(1, 2).is_contiguous() and not x.is_contiguous()
+            xsrc = x.transpose(1, 2) if bwf else x.contiguous()
+            call("b200med_lstm_pack_inputs", _raw(xsrc.data_ptr()), _raw(A[0].data_ptr()), B, Bp, F, W, H, Kp[0], inp[0], int(bwf), st)
         for l in range(1, L):
             call("b200med_zero_cols_bf16", _raw(A[l][0].data_ptr()), Bp, Kp[l], inp[l], H, st)
         out = torch.empty(B, H, dtype=torch.float32, device=dev)
@@ -254,6 +276,7 @@ class LSTMRecFunction(torch.autograd.Function):
             ctx.save_for_backward(*A, *Gact, *Cs, *Wih, *Whh)
         ctx.meta = (B, Bp, F, W, L, H, Kp, ins, inp, float(drop_p), seed_dev, bwf)
         ctx.gen2 = gen2
+        ctx.n_feat = None if parts is None else Ca      # with parts only the FeatureExtractor columns carry a gradient
         return out
 
     @staticmethod
@@ -326,12 +349,16 @@ class LSTMRecFunction(torch.autograd.Function):
         for g in grads:
             g.record_stream(main)
         dx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and ctx.n_feat is not None:
+            # columns [0, Ca) of dX_0, window-major: the gradient of the FeatureExtractor output (no cat to slice back out of)
+            dx = torch.empty(B, W, ctx.n_feat, dtype=torch.float32, device=dev)
+            call("b200med_lstm_unpack_dx", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, ctx.n_feat, W, inp[0], 1, st)
+        elif ctx.needs_input_grad[0]:
             dx = torch.empty((B, W, F) if bwf else (B, F, W), dtype=torch.float32, device=dev)
             call("b200med_lstm_unpack_dx", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, F, W, inp[0], int(bwf), st)
             if bwf:
                 dx = dx.transpose(1, 2)          # gradient of the permuted view, in the layout of its base tensor
-        return (dx, None, None, *grads)
+        return (dx, None, None, None, *grads)
 
 
 class LSTMF32Function(torch.autograd.Function):
@@ -424,7 +451,7 @@ class LSTMF32Function(torch.autograd.Function):
 
 
 def lstm_last_hidden(x: torch.Tensor, lstm: torch.nn.LSTM, training: bool, seed_dev=None, impl: str = "auto",
-                     precision: str = "bf16") -> torch.Tensor:
+                     precision: str = "bf16", parts: WindowParts = None) -> torch.Tensor:
     """h_{W-1} of the top layer for head input x [B, F, W].  precision "fp32": exact-math fp32 kernels (1e-5 mode);
     "bf16": persistent tcgen05 recurrence (hidden_size 128) or per-step tcgen05 gate GEMMs + cell kernels (other sizes;
     ``impl="per_step"`` forces that path -- used by the tests that hold the two implementations against each other)."""
@@ -438,8 +465,13 @@ def lstm_last_hidden(x: torch.Tensor, lstm: torch.nn.LSTM, training: bool, seed_
                    getattr(lstm, f"bias_ih_l{l}"), getattr(lstm, f"bias_hh_l{l}")]
     p = float(lstm.dropout) if training else 0.0
     if precision == "fp32":
+        if parts is not None:
+            raise ValueError("WindowParts input is served by the bf16 mode only")
         return LSTMF32Function.apply(x, p, seed_dev, *params)
     if precision != "bf16":
         raise ValueError(f"precision {precision!r} is not supported (fp32 | bf16)")
-    fn = LSTMRecFunction if (lstm.hidden_size == 128 and impl != "per_step") else LSTMStackFunction
-    return fn.apply(x, p, seed_dev, *params)
+    if lstm.hidden_size == 128 and impl != "per_step":
+        return LSTMRecFunction.apply(x, p, seed_dev, parts, *params)
+    if parts is not None:
+        raise ValueError("WindowParts input is served by the persistent recurrence path only (hidden_size 128)")
+    return LSTMStackFunction.apply(x, p, seed_dev, *params)

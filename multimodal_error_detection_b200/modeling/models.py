@@ -232,7 +232,14 @@ class LSTM(nn.Module):
             nn.Linear(256, 64), nn.ReLU(), nn.BatchNorm1d(64), nn.Linear(64, n_classes))
         self.initialize_weights()
 
-    def forward(self, l):
+    def accepts_parts(self) -> bool:
+        """True when forward(feats, parts=WindowParts) is served: bf16 mode on the persistent recurrence (hidden size 128)."""
+        return self.precision == "bf16" and self.hidden_size == 128
+
+    def forward(self, l, parts=None):
+        """l: the reference's head input [B, F, W]; or, with ``parts`` (lstm_stack.WindowParts: the window's kinematics still in
+        the frame table), the FeatureExtractor output [B, W, Ca] -- the concatenation of define_inputs then happens inside the
+        kernel that builds the recurrence's first operand."""
         if not l.is_cuda:
             raise RuntimeError("b200med LSTM head runs on CUDA tensors only (no CPU fallback)")
         from ..heads import mlp_tail
@@ -240,7 +247,7 @@ class LSTM(nn.Module):
         if self.training and self.lstm.dropout > 0:
             self._drop_seed.add_(1)
         # only h_{W-1} of the top layer is needed: the reference takes F.relu(out)[:, -1, :] (models.py:205-206)
-        h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed, precision=self.precision)
+        h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed, precision=self.precision, parts=parts)
         return mlp_tail(h, self.linear_layers, relu_in=True, training=self.training, precision=self.precision)
 
     def initialize_weights(self):

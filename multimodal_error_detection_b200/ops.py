@@ -411,6 +411,18 @@ def to_bf16(x: torch.Tensor, out=None, relu: bool = False) -> torch.Tensor:
     return y
 
 
+def split_bf16x3(x: torch.Tensor, row_order=None, stack_order=None, relu: bool = False):
+    """(row3 [R, 3C], stack3 [3R, C]) split-bf16 copies of x [R, C] f32 (b200med_split_bf16x3); order 0 = left operand
+    (hi, lo, hi), 1 = right operand (hi, hi, lo), None = that layout is not produced."""
+    x = _need(x, torch.float32, "x")
+    R, Cn = x.shape
+    row3 = torch.empty(R, 3 * Cn, dtype=torch.bfloat16, device=x.device) if row_order is not None else None
+    stack3 = torch.empty(3 * R, Cn, dtype=torch.bfloat16, device=x.device) if stack_order is not None else None
+    call("b200med_split_bf16x3", _ptr(x), _ptr(row3), _ptr(stack3), R, Cn, int(row_order or 0), int(stack_order or 0), int(bool(relu)),
+         _stream())
+    return row3, stack3
+
+
 def to_f32(x: torch.Tensor) -> torch.Tensor:
     x = _need(x, torch.bfloat16, "x")
     y = torch.empty(x.shape, dtype=torch.float32, device=x.device)

@@ -87,10 +87,12 @@ def test_mlp_tail_vs_torch(relu_in, dims, B):
 
 
 @pytest.mark.parametrize("relu_in,dims,B", [(True, [128, 256, 64, 1], 8192), (True, [128, 256, 64, 1], 700), (False, [128, 256, 32, 16, 6], 12)])
-def test_mlp_tail_bf16_vs_torch(relu_in, dims, B):
-    """The same head tail in the bf16 throughput mode (hidden-layer products on the tcgen05 GEMM, bf16 operands, fp32
-    accumulation; BatchNorm and the output layer fp32) against the fp64 nn.Sequential: the bf16-mode bar of north_star, 2e-2
-    norm-wise relative, on the logits, the input gradient and every parameter gradient."""
+def test_mlp_tail_bf16_mode_vs_torch(relu_in, dims, B):
+    """The same head tail in the bf16 throughput mode: hidden-layer products with K % 64 == 0 run on the tcgen05 GEMM as split-bf16
+    products (hi + lo operands, three terms folded into one GEMM; BatchNorm and the output layer fp32), against the exact
+    nn.Sequential in fp64 on the CPU.  The products carry ~1e-5 relative error, so the logits are held to 1e-4; gradients to
+    5e-3 NORM-wise: a pre-activation within ~1e-5 of zero may flip its ReLU, and each flipped unit (a handful in 2 M at
+    B = 8192) moves a whole row of the input gradient."""
     from multimodal_error_detection_b200 import ops
     from multimodal_error_detection_b200.heads import mlp_tail
     if not ops.has_tcgen05():
@@ -114,26 +116,43 @@ def test_mlp_tail_bf16_vs_torch(relu_in, dims, B):
     yr = ref(torch.relu(xr) if relu_in else xr)
     yr.backward(dy.double())
     xg = x.to(DEV).requires_grad_(True)
-    n0 = ops._lib.launch_count()
     yg = mlp_tail(xg, seq, relu_in=relu_in, training=True, precision="bf16")
     yg.backward(dy.to(DEV))
-    assert ops._lib.launch_count() > n0
-    assert nrel(yg, yr) < 2e-2
 
-    def frel(a, b):      # norm-wise: a unit whose pre-activation sits within bf16 rounding of zero flips its ReLU, and ONE flipped
-        a, b = a.detach().double().cpu(), b.detach().double().cpu()      # unit moves a whole row of the input gradient
+    def frel(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
         return float((a - b).norm() / b.norm().clamp_min(1e-30))
-    assert frel(xg.grad, xr.grad) < 2e-2
+    assert nrel(yg, yr) < 1e-4
+    assert frel(xg.grad, xr.grad) < 5e-3
     gmax = max(float(r.grad.norm()) for r in ref.parameters())
     for (k, p), (_, q) in zip(seq.named_parameters(), ref.named_parameters()):
         scale = max(float(q.grad.norm()), 1e-3 * gmax)
-        assert float((p.grad.double().cpu() - q.grad).norm()) <= 2e-2 * scale, k
+        assert float((p.grad.double().cpu() - q.grad).norm()) <= 5e-3 * scale, k
     for (k, b), (_, c) in zip(seq.named_buffers(), ref.named_buffers()):
-        assert nrel(b.double(), c.double()) < 2e-2, k
+        assert nrel(b.double(), c.double()) < 1e-4, k
     seq.eval(); ref.eval()
     with torch.no_grad():
         ye = mlp_tail(x.to(DEV), seq, relu_in=relu_in, training=False, precision="bf16")
-        assert nrel(ye, ref(torch.relu(x.double()) if relu_in else x.double())) < 2e-2
+        assert nrel(ye, ref(torch.relu(x.double()) if relu_in else x.double())) < 1e-4
+
+
+def test_split_bf16x3_kernel():
+    """b200med_split_bf16x3: hi = bf16(x), lo = bf16(x - hi) in both layouts and both operand orders, bit for bit."""
+    from multimodal_error_detection_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(37, 24, generator=g) * 3).to(DEV)
+    for relu in (False, True):
+        v = torch.relu(x) if relu else x
+        hi = v.to(torch.bfloat16)
+        lo = (v - hi.float()).to(torch.bfloat16)
+        for ro, so in ((0, 0), (1, 1), (0, 1), (1, 0)):
+            row3, stack3 = ops.split_bf16x3(x, ro, so, relu=relu)
+            want_row = torch.cat([hi, hi if ro else lo, lo if ro else hi], dim=1)
+            want_stack = torch.cat([hi, hi if so else lo, lo if so else hi], dim=0)
+            assert torch.equal(row3.view(torch.int16), want_row.view(torch.int16))
+            assert torch.equal(stack3.view(torch.int16), want_stack.view(torch.int16))
+    r, s = ops.split_bf16x3(x, None, 1)
+    assert r is None and s.shape == (111, 24)
 
 
 @pytest.mark.parametrize("W,B,view", [(10, 12, True), (10, 513, False), (30, 40, True), (30, 7, False)])

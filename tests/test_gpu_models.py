@@ -689,3 +689,46 @@ def test_feature_extractor_fused_gather_matches_unfused():
     nrel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
     assert nrel(y1, y2) < 5e-3
     assert max(nrel(a, b) for a, b in zip(g1, g2)) < 5e-3, [nrel(a, b) for a, b in zip(g1, g2)]
+
+
+@pytest.mark.parametrize("stat_rows", [1, 16])
+def test_lstm_head_window_parts_matches_concatenated_input(stat_rows):
+    """LSTM.forward(feats, parts=WindowParts(...)) -- the kinematics gathered / standardised and concatenated INSIDE the kernel
+    that builds the recurrence's first operand (b200med_lstm_pack_parts) -- against the reference-shaped call on
+    cat((feats, kinematics), dim=2).permute(0, 2, 1) (modeling_utils.py:40-47): the two operands hold the same bf16 values, so
+    logits and every gradient must be bit-identical (dropout off)."""
+    from multimodal_error_detection_b200 import ops
+    from multimodal_error_detection_b200.lstm_stack import WindowParts
+    from multimodal_error_detection_b200.modeling.models import LSTM
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    torch.manual_seed(3)
+    B, W, Ca, Cb, N = 333, 16, 32, 26, 5000
+    model = LSTM(Ca + Cb, W, 3, 128, 1).to(DEV)
+    model.precision = "bf16"
+    model.lstm.dropout = 0.0
+    model.train()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    table = torch.randn(N, Cb, device=DEV, generator=g)
+    mean = torch.randn(stat_rows, Cb, device=DEV, generator=g) * 0.3
+    std = torch.rand(stat_rows, Cb, device=DEV, generator=g) + 0.5
+    starts = torch.randint(0, N - W, (B,), device=DEV, generator=g, dtype=torch.int64).to(torch.int32)
+    feats = torch.randn(B, W, Ca, device=DEV, generator=g)
+    dy = torch.randn(B, 1, device=DEV, generator=g)
+
+    f1 = feats.clone().requires_grad_(True)
+    y1 = model(f1, parts=WindowParts(table, mean, std, starts))
+    y1.backward(dy)
+    g1 = [p.grad.clone() for p in model.parameters()]
+    model.zero_grad(set_to_none=True)
+
+    kin = torch.empty(B, W, Cb, device=DEV)
+    ops.gather_norm([ops.GatherStream(table, mean, std, kin, 0, True)], starts, W)
+    f2 = feats.clone().requires_grad_(True)
+    y2 = model(torch.cat((f2, kin), dim=2).permute(0, 2, 1))
+    y2.backward(dy)
+    g2 = [p.grad.clone() for p in model.parameters()]
+    assert torch.equal(y1, y2)
+    assert torch.equal(f1.grad, f2.grad)
+    for a, b in zip(g1, g2):
+        assert torch.equal(a, b)
