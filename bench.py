@@ -603,6 +603,10 @@ def run_gpu(args):
                            "frames_per_gpu": n_frames, "windows_per_gpu": n_windows, "params": n_params,
                            "parallelism": f"dp{world}", "launch": graph_note,
                            "gather_prefetch": bool(prefetch), "gather_fused_into_layer1": fused,
+                           "gradient_exchange": ("none (one rank)" if world == 1 else
+                                                 "one kernel over NVLink peer memory per step (b200med_peer_allreduce_f32: reduce-scatter + "
+                                                 "all-gather by direct peer loads / stores)" if getattr(opt, "_peer", None) is not None
+                                                 else "NCCL all-reduce (peer-memory mappings unavailable or switched off)"),
                            "l2": "every step gathers a fresh ~1.1 GB slice of a ~10 GB table (inputs larger than the 126 MB L2)",
                            "gather_variant": args.gather_variant},
                 "roofline": roofline, "roofline_gemm": gemm, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,

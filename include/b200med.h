@@ -540,6 +540,25 @@ int64_t b200med_roc_auc_ws_bytes(int64_t n);
 int b200med_roc_auc(const float *scores, const float *labels, int64_t n, double *auc, int64_t *stats,
                     void *workspace, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink peer memory (one gradient exchange per step; the reference
+ * itself is single-process, MED/modeling/modeling_utils.py:363-365 loss.backward(); optimizer.step()).
+ * One process per GPU; every rank allocates its flat gradient buffer and a flag block with b200med_peer_alloc, exports them
+ * (64-byte CUDA IPC handles, exchanged by the host code through torch.distributed), imports everybody else's, and then calls
+ * b200med_peer_allreduce_f32 once per step IN PLACE of the NCCL all-reduce: reduce-scatter + all-gather by direct peer loads
+ * and stores inside ONE kernel, sums in rank order (all ranks hold identical bits afterwards).
+ *   bufs_dev / flags_dev: DEVICE arrays of `world` pointers -- this rank's view of every rank's buffer / flag block (its own
+ *   at index `rank`); n floats per buffer; every rank must launch once per exchange (bounded waits trap otherwise).
+ * ---------------------------------------------------------------------------------------------- */
+int b200med_peer_alloc(int64_t bytes, void **ptr);             /* zero-filled cudaMalloc allocation (exportable) */
+int b200med_peer_free(void *ptr);
+int b200med_peer_export(const void *ptr, void *handle64);      /* cudaIpcGetMemHandle -> 64 bytes */
+int b200med_peer_import(const void *handle64, void **ptr);     /* cudaIpcOpenMemHandle (enables peer access) */
+int b200med_peer_close(void *ptr);
+int64_t b200med_peer_flag_bytes(void);                         /* size of a rank's flag block */
+int b200med_peer_allreduce_f32(void *const *bufs_dev, void *const *flags_dev, int32_t rank, int32_t world, int64_t n,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,13 @@ SIGNATURES = {
     "b200med_confusion": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _p]),
     "b200med_roc_auc_ws_bytes": (_i64, [_i64]),
     "b200med_roc_auc": (C.c_int, [_p, _p, _i64, _p, _p, _p, _p]),
+    "b200med_peer_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p)]),
+    "b200med_peer_free": (C.c_int, [_p]),
+    "b200med_peer_export": (C.c_int, [_p, _p]),
+    "b200med_peer_import": (C.c_int, [_p, C.POINTER(C.c_void_p)]),
+    "b200med_peer_close": (C.c_int, [_p]),
+    "b200med_peer_flag_bytes": (_i64, []),
+    "b200med_peer_allreduce_f32": (C.c_int, [_p, _p, _i32, _i32, _i64, _p]),
 }
 
 _lib = None

@@ -61,6 +61,7 @@ class WindowTrainStep:
         self.launches_per_step = None
         self._side = torch.cuda.Stream(device=dev)
         optimizer.prepare()
+        mu._setup_exchange(optimizer)      # several ranks: gradient exchange over NVLink peer memory (collective set-up)
 
     # the current batch buffers (what the last / next run() trains on)
     @property

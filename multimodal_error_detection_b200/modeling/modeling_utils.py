@@ -414,7 +414,9 @@ def _backward(loss, optimizer=None, weight: float = 1.0, exchange: bool = True):
     fused = isinstance(optimizer, FusedAdam)
     lstm_stack.DEFER_JOIN = fused      # only FusedAdam joins the side stream before using the gradients
     early = None
-    if exchange and fused and _dp_world() > 1 and os.environ.get("B200MED_EARLY_EXCHANGE", "1") != "0":
+    # the peer-memory exchange (one kernel over NVLink, ~20 us) needs no head start; the NCCL one is split in two
+    peer = fused and getattr(optimizer, "_peer", None) is not None
+    if exchange and fused and not peer and _dp_world() > 1 and os.environ.get("B200MED_EARLY_EXCHANGE", "1") != "0":
         early = _EARLY["state"] = _EarlyExchange(optimizer)
         _models.EARLY_EXCHANGE_HOOK = early.hook
     try:
@@ -422,6 +424,14 @@ def _backward(loss, optimizer=None, weight: float = 1.0, exchange: bool = True):
     finally:
         lstm_stack.DEFER_JOIN = False
         _models.EARLY_EXCHANGE_HOOK = None
+
+
+def _setup_exchange(optimizer):
+    """Entry of every train loop (all ranks pass here together, outside any graph capture): with several ranks, map the flat
+    gradient buffer into peer memory once so that the per-step exchange is the one-kernel NVLink path (parallel.PeerAllReduce)."""
+    if _dp_world() > 1 and isinstance(optimizer, FusedAdam) and torch.cuda.is_available() \
+            and not torch.cuda.is_current_stream_capturing():
+        optimizer.enable_peer_exchange()
 
 
 def _allreduce_grads(optimizer):
@@ -433,8 +443,9 @@ def _allreduce_grads(optimizer):
         early, _EARLY["state"] = _EARLY["state"], None
         if early is None or early.opt is not optimizer or not early.finish():
             optimizer._refresh_active()                      # gradients of first-time parameters move into the chunks
-            for buf in optimizer.grad_buffers():
-                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            if not (isinstance(optimizer, FusedAdam) and optimizer.peer_all_reduce()):
+                for buf in optimizer.grad_buffers():
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         optimizer.grad_scale = 1.0 / dist.get_world_size()
 
 
@@ -480,6 +491,7 @@ def train_single_epoch(model, feature_extractor, train_dataloader, criterion, op
     over batches of per-batch scores and the summed confusion matrix (:398-402) -- plus
     (probs, preds, labels, subjects) lists when ``return_train_preds``."""
     device = torch.device(device)
+    _setup_exchange(optimizer)
     _set_train(model, feature_extractor, exp_kwargs, True)
     if _graph_step_ok(train_dataloader, feature_extractor, criterion, exp_kwargs):
         return _train_epoch_graph(model, feature_extractor, train_dataloader, criterion, optimizer, scheduler, device, exp_kwargs)
@@ -771,6 +783,7 @@ def train_single_epoch_ES(model, feature_extractor, train_dataloader, criterion,
     float class index and raises on CPU/CUDA; the index is used as ``long`` here, which is
     what the call means.  Scores are pooled over the epoch (:519-528)."""
     device = torch.device(device)
+    _setup_exchange(optimizer)
     _set_train(model, feature_extractor, exp_kwargs, True)
     crit = criterion if isinstance(criterion, FusedCrossEntropyLoss) else FusedCrossEntropyLoss(
         getattr(criterion, "weight", None), getattr(criterion, "reduction", "mean"))
@@ -847,6 +860,7 @@ def train_single_epoch_Sequential(model, feature_extractor, train_dataloader, cr
     label-1 for the masked rows, sum / mask.sum().  The committed code feeds target -1 for unmasked
     rows (raises off-MPS); those rows carry zero weight, so the target is clamped to 0."""
     device = torch.device(device)
+    _setup_exchange(optimizer)
     _set_train(model, feature_extractor, exp_kwargs, True)
     crit = FusedCrossEntropyLoss()
     log = _EpochLog()

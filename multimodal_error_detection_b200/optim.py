@@ -112,6 +112,48 @@ class FusedAdam(torch.optim.Optimizer):
     def grad_buffers(self):
         return [c.grad for c in self.prepare().chunks]
 
+    def enable_peer_exchange(self) -> bool:
+        """Move the flat gradient buffer into peer-mapped memory and exchange it with parallel.PeerAllReduce (one kernel over
+        NVLink peer memory) instead of the NCCL all-reduce.  COLLECTIVE: every rank must call it at the same point.  Returns
+        False (and leaves everything as it was) when the mappings cannot be made on every rank."""
+        import os
+        from . import parallel
+        self.prepare()
+        if getattr(self, "_peer", None) is not None:
+            return True
+        if getattr(self, "_peer_failed", False) or os.environ.get("B200MED_PEER_EXCHANGE", "1") == "0":
+            return False
+        # ONE peer-mapped allocation holds the gradient twins of all chunks back to back (16-byte aligned): one kernel per step
+        offs, total = [], 0
+        for c in self.chunks:
+            offs.append(total)
+            total += (c.grad.numel() + 3) // 4 * 4
+        try:
+            peer = parallel.PeerAllReduce(total, self.chunks[0].grad.device)
+        except Exception as e:      # noqa: BLE001 -- collective failure: every rank lands here together
+            import warnings
+            warnings.warn(f"b200med: gradient exchange stays on NCCL ({e})", RuntimeWarning)
+            self._peer_failed = True
+            return False
+        for c, off in zip(self.chunks, offs):
+            new = peer.buffer[off:off + c.grad.numel()]
+            with torch.no_grad():
+                new.copy_(c.grad)
+            for p, o, n in c.members:       # gradient views that pointed into the old buffer
+                if p.grad is not None and p.grad.data_ptr() == c.grad[o:o + n].data_ptr():
+                    p.grad = new[o:o + n].view_as(p.data)
+            c.grad = new
+        self._peer = peer
+        return True
+
+    def peer_all_reduce(self) -> bool:
+        """Sum the flat gradient buffer over the ranks with the peer-memory kernel; False when it is not enabled."""
+        peer = getattr(self, "_peer", None)
+        if peer is None:
+            return False
+        peer.all_reduce()
+        return True
+
     # ------------------------------------------------------------------------------------ step protocol
     def zero_grad(self, set_to_none: bool = False):
         self.prepare()

@@ -29,8 +29,11 @@ def main():
     path = synthetic.write_fold(fold, os.path.join(tmp, "fold")) + "/"
     out = {}
     finals = {}
-    for precision, early in (("bf16", "1"), ("bf16", "0"), ("fp32", "1")):
-        os.environ["B200MED_EARLY_EXCHANGE"] = early      # "0": one all-reduce after the backward (the A/B of the overlap)
+    # exchange: "peer" = the one-kernel NVLink peer-memory all-reduce (default), "nccl1" = NCCL started inside the backward
+    # (two pieces), "nccl0" = one NCCL all-reduce after the backward
+    for precision, early in (("bf16", "peer"), ("bf16", "1"), ("bf16", "0"), ("fp32", "peer")):
+        os.environ["B200MED_PEER_EXCHANGE"] = "1" if early == "peer" else "0"
+        os.environ["B200MED_EARLY_EXCHANGE"] = "0" if early == "0" else "1"
         kw = dict(dataset_type="window", error_type="global", pos_weight=True, n_epochs=2, batch_size=64, lr=3e-4, lr_scheduler=True,
                   weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32, data_type="multimodal", delete_ND=True,
                   return_train_preds=False, siamese=False, model_name="SimpleLSTM", precision=precision, cuda_graph=True)
@@ -47,7 +50,8 @@ def main():
         dist.all_reduce(allsame, op=dist.ReduceOp.MIN)
         finals[(precision, early)] = flat.clone()
         out[f"{precision}_early{early}"] = {"graph_replayed": stepper.graph is not None, "stepper_batch": stepper.B, "global_batch": kw["batch_size"],
-                          "replicas_identical": bool(allsame.item()), "loss_rank0": losses}
+                          "replicas_identical": bool(allsame.item()), "loss_rank0": losses,
+                          "exchange": "peer-memory kernel" if getattr(opt, "_peer", None) is not None else "nccl"}
         assert stepper.B == kw["batch_size"] // world and stepper.graph is not None, out
         assert bool(allsame.item()), "replicas drifted apart"
         opt._b200_stepper = None
@@ -56,6 +60,12 @@ def main():
     diff = float((finals[("bf16", "1")] - finals[("bf16", "0")]).abs().max())
     out["early_vs_single_max_abs_param_diff"] = diff
     assert diff < 1e-4, diff
+    # the peer-memory kernel sums in rank order, NCCL in its own: same run up to the summation order (identical at 2 ranks)
+    diff = float((finals[("bf16", "peer")] - finals[("bf16", "0")]).abs().max())
+    out["peer_vs_nccl_max_abs_param_diff"] = diff
+    assert diff < 1e-4, diff
+    if os.environ.get("B200MED_REQUIRE_PEER"):
+        assert out["bf16_earlypeer"]["exchange"] == "peer-memory kernel", out
     if rank == 0:
         print(json.dumps({"world": world, **out}), flush=True)
     torch.cuda.synchronize()
