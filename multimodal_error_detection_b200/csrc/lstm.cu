@@ -167,6 +167,38 @@ lstm_pack_parts_kernel(const float *__restrict__ feats, int Ca, const float *__r
     }
 }
 
+// The common geometry (Ca, Cb even, Ca + Cb <= 64 = hoff, one statistics row): lane l owns columns 2l, 2l + 1 of the 64-column
+// x block -- one float2 load (feats or table row), mean / std in registers for the whole kernel, one 128-byte store per row and
+// warp; the h_{-1} block is zeroed by the rows of step 0 only.  (The generic kernel above walks Kp columns with a branch per
+// element: 52 us at B = 8192, W = 16 against ~80 MB of traffic.)
+__global__ void __launch_bounds__(256)
+lstm_pack_parts64_kernel(const float *__restrict__ feats, int Ca, const float *__restrict__ kin, long long table_rows, int Cb,
+                         const float *__restrict__ mean, const float *__restrict__ stdv, const int32_t *__restrict__ starts,
+                         __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int W, int H, int Kp) {
+    const int lane = threadIdx.x & 31;
+    const int c = lane * 2;
+    const bool is_f = c < Ca, is_k = !is_f && c < Ca + Cb;
+    float m0 = 0.0f, m1 = 0.0f, s0 = 1.0f, s1 = 1.0f;
+    if (is_k && mean) { m0 = mean[c - Ca]; m1 = mean[c - Ca + 1]; s0 = stdv[c - Ca]; s1 = stdv[c - Ca + 1]; }
+    const long long nrows = B * W, warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+        const long long b = r / W;
+        const int t = (int)(r - b * W);
+        const long long row = (long long)starts[b] + t;
+        if (row < 0 || row >= table_rows) __trap();          // a window outside the table: the reference raises IndexError
+        float2 v = make_float2(0.0f, 0.0f);
+        if (is_f) v = *reinterpret_cast<const float2 *>(feats + r * Ca + c);
+        else if (is_k) {
+            v = *reinterpret_cast<const float2 *>(kin + row * Cb + (c - Ca));
+            if (mean) { v.x = (v.x - m0) / s0; v.y = (v.y - m1) / s1; }
+        }
+        __nv_bfloat16 *dst = A0 + ((long long)t * Bpad + b) * Kp;
+        *reinterpret_cast<__nv_bfloat162 *>(dst + c) = __floats2bfloat162_rn(v.x, v.y);
+        if (t == 0)                                          // h_{-1} = 0 (and any padding behind it)
+            for (int k = 64 + c; k < Kp; k += 64) *reinterpret_cast<__nv_bfloat162 *>(dst + k) = __floats2bfloat162_rn(0.0f, 0.0f);
+    }
+}
+
 // dx [B, W, F] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F)
 __global__ void __launch_bounds__(256)
 lstm_unpack_bwf_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F, int W, int Kp) {
@@ -367,6 +399,12 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_parts(
     B200MED_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean and std must both be given or both NULL");
     B200MED_REQUIRE(stat_rows == 1 || stat_rows == W, "statistics: one row, or one per window step");
     const long long blocks = (B * (long long)W + 7) / 8, cap = (long long)num_sms() * 8;
+    if (Ca % 2 == 0 && Cb % 2 == 0 && Ca + Cb <= 64 && hoff == 64 && hoff + H == Kp && stat_rows == 1 &&
+        ((uintptr_t)feats % 8 == 0) && ((uintptr_t)kin_table % 8 == 0)) {
+        lstm_pack_parts64_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+            feats, Ca, kin_table, table_rows, Cb, mean, stdv, starts, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, W, H, Kp);
+        return after_launch("lstm_pack_parts64_kernel");
+    }
     lstm_pack_parts_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
         feats, Ca, kin_table, table_rows, Cb, mean, stdv, stat_rows, starts, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, W, H, Kp, hoff);
     return after_launch("lstm_pack_parts_kernel");

@@ -490,3 +490,52 @@ def test_ensemble_fusion(ops):
     assert np.array_equal(ops.cascade(dev(b), dev(m)).cpu().numpy(), O.cascade(b, m))
     cmk = ops.confusion(dev(m), dev(ops.cascade(dev(b), dev(m)).cpu().numpy()), 6).cpu().numpy()
     assert cmk.sum() == n and np.array_equal(np.diag(cmk) + 0, [int(((m == c) & (O.cascade(b, m) == c)).sum()) for c in range(6)])
+
+
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("world,n", [(2, 4096), (4, 10_001), (8, 1_599_265)])
+def test_peer_allreduce_kernel_ranks_emulated_on_one_gpu(world, n):
+    """b200med_peer_allreduce_f32 (the data-parallel gradient exchange, csrc/peer_exchange.cu) with the `world` ranks played by
+    `world` streams of ONE GPU: every "rank" owns a buffer and a flag block, sees the others through the same pointer arrays a
+    real rank gets from CUDA IPC, and launches the kernel once per exchange.  After each of three exchanges every buffer must
+    hold the sum in rank order, bit for bit the same in all of them (the real multi-GPU run is scripts/dp_window_check.py)."""
+    import ctypes as C
+    from multimodal_error_detection_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(world * 7 + 1)
+    bufs = [torch.empty(n, device=DEV) for _ in range(world)]
+    flags = [torch.zeros(int(lib.b200med_peer_flag_bytes()) // 4, dtype=torch.int32, device=DEV) for _ in range(world)]
+    bufs_dev = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    flags_dev = torch.tensor([f.data_ptr() for f in flags], dtype=torch.int64, device=DEV)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for rep in range(3):
+        src = [torch.randn(n, device=DEV, generator=g) * (q + 1) for q in range(world)]
+        want = src[0].clone()
+        for q in range(1, world):
+            want += src[q]                      # rank order, fp32: what the kernel computes
+        for q in range(world):
+            bufs[q].copy_(src[q])
+        torch.cuda.synchronize()
+        # at most ceil(n / world / 2048) CTAs per "rank": all of them fit the GPU together, as the flag barriers require
+        with _lib_sm_limit(lib, max(1, 148 // world)):
+            for q in range(world):
+                with torch.cuda.stream(streams[q]):
+                    _lib.call("b200med_peer_allreduce_f32", C.c_void_p(bufs_dev.data_ptr()), C.c_void_p(flags_dev.data_ptr()), q, world, n,
+                              C.c_void_p(streams[q].cuda_stream))
+        torch.cuda.synchronize()
+        for q in range(world):
+            assert torch.equal(bufs[q], want), (rep, q)
+        assert all(int(f[32]) == rep + 1 and int(f[33]) == 0 and int(f[34]) == 0 for f in flags)
+
+
+class _lib_sm_limit:
+    def __init__(self, lib, sms):
+        self.lib, self.sms = lib, sms
+
+    def __enter__(self):
+        self.prev = self.lib.b200med_set_sm_limit(self.sms)
+
+    def __exit__(self, *exc):
+        self.lib.b200med_set_sm_limit(self.prev)
