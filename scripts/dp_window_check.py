@@ -29,6 +29,28 @@ def main():
     path = synthetic.write_fold(fold, os.path.join(tmp, "fold")) + "/"
     out = {}
     finals = {}
+    # 0. the exchange kernel itself on the real ranks: every rank contributes a known vector; the result must be the fp32 sum in
+    #    rank order on EVERY rank (bit-identical across ranks) and agree with NCCL's all-reduce up to the summation order
+    n = 1_599_265
+    peer = parallel.PeerAllReduce(n, dev)
+    gen = [torch.Generator(device=dev).manual_seed(100 + q) for q in range(world)]
+    parts = [torch.randn(n, device=dev, generator=gen[q]) * (q + 1) for q in range(world)]      # every rank can rebuild all parts
+    want = parts[0].clone()
+    for q in range(1, world):
+        want += parts[q]
+    ref = parts[rank].clone()
+    dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+    for rep in range(3):
+        peer.buffer.copy_(parts[rank])
+        peer.all_reduce()
+        torch.cuda.synchronize()
+        exact = bool(torch.equal(peer.buffer, want))
+        flag = torch.tensor([int(exact)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert bool(flag.item()), f"peer all-reduce differs from the rank-ordered fp32 sum (repetition {rep})"
+    out["peer_kernel"] = {"n": n, "equals_rank_ordered_sum_on_every_rank": True,
+                          "max_abs_diff_vs_nccl": float((peer.buffer - ref).abs().max()), "max_abs_value": float(want.abs().max())}
+    del parts, gen
     # exchange: "peer" = the one-kernel NVLink peer-memory all-reduce (default), "nccl1" = NCCL started inside the backward
     # (two pieces), "nccl0" = one NCCL all-reduce after the backward
     for precision, early in (("bf16", "peer"), ("bf16", "1"), ("bf16", "0"), ("fp32", "peer")):
@@ -59,11 +81,13 @@ def main():
     # the early (two-piece) exchange and the single all-reduce give the same training run up to the summation order of NCCL
     diff = float((finals[("bf16", "1")] - finals[("bf16", "0")]).abs().max())
     out["early_vs_single_max_abs_param_diff"] = diff
-    assert diff < 1e-4, diff
+    assert diff < (1e-4 if world == 2 else 5e-3), diff
     # the peer-memory kernel sums in rank order, NCCL in its own: same run up to the summation order (identical at 2 ranks)
+    # (beyond 2 ranks the two sum in different orders and Adam turns round-off-level gradient differences into +-lr steps:
+    # 14 steps at lr 3e-4 bound the drift by 4.2e-3; what must hold exactly is checked in step 0 above and by the replicas)
     diff = float((finals[("bf16", "peer")] - finals[("bf16", "0")]).abs().max())
     out["peer_vs_nccl_max_abs_param_diff"] = diff
-    assert diff < 1e-4, diff
+    assert diff < (1e-4 if world == 2 else 5e-3), diff
     if os.environ.get("B200MED_REQUIRE_PEER"):
         assert out["bf16_earlypeer"]["exchange"] == "peer-memory kernel", out
     if rank == 0:
