@@ -131,7 +131,7 @@ def k1_traffic(precision, batch, window, variant, fused=False):
         rec = json.load(open(path))
         c = rec["config"]
         if (c["precision"], c["batch"], c["window"], c["gather_variant"]) == (precision, batch, window, variant):
-            return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), f"profiles/k1_traffic.json ({rec['source']})"
+            return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), f"profiles/{os.path.basename(path)} ({rec['source']})"
     except Exception:
         pass
     return None, None

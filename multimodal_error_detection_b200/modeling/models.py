@@ -102,19 +102,42 @@ class _MLPFunction(torch.autograd.Function):
                     g = ops.linear_bwd_data_f32(g, weights[i], relu_out=None)
             return (g if need_dx else None, None, *grads)
         g = ops.to_bf16(dy.contiguous().float())
+        # The bias gradients (column sums: a second pass over dY, HBM-bound) run on a side stream NEXT TO the tensor-bound
+        # weight-gradient GEMMs instead of between them; `keep` holds every dY they read until the join at the end.
+        main = torch.cuda.current_stream()
+        side = _bias_stream(dy.device)
+        keep = []
         for i in reversed(range(n)):
             if i == 0 and n > 1 and EARLY_EXCHANGE_HOOK is not None:
+                main.wait_stream(side)
                 grads = EARLY_EXCHANGE_HOOK(ctx.params, grads)
             N, K = weights[i].shape
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                grads[2 * i + 1] = ops.colsum(g)
+            keep.append(g)
             # dW[N,K] = g[M,N]^T acts_i[M,K]: both operands reduce over their ROW index -> MN-major
             grads[2 * i] = ops.gemm_bf16(g, acts[i], N, K, M, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
                                          split_k=ops.gemm_split_k(N, K, M))
-            grads[2 * i + 1] = ops.colsum(g)
             if i > 0:    # dh[M,K] = g[M,N] W[N,K], masked by relu'(acts_i)
                 g = ops.gemm_bf16(g, weights[i], M, K, N, a_kmajor=True, b_kmajor=False, mask=acts[i])
             elif need_dx:
                 g = ops.to_f32(ops.gemm_bf16(g, weights[i], M, K, N, a_kmajor=True, b_kmajor=False))
+        main.wait_stream(side)
+        keep.clear()
+        for i in range(n):
+            grads[2 * i + 1].record_stream(main)      # allocated on the side stream, consumed on the main one
         return (g if need_dx else None, None, *grads)
+
+
+_BIAS_STREAMS = {}
+
+
+def _bias_stream(device) -> torch.cuda.Stream:
+    key = str(device)
+    if key not in _BIAS_STREAMS:
+        _BIAS_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _BIAS_STREAMS[key]
 
 
 class FeatureExtractor(nn.Module):
