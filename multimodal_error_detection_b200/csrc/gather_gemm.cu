@@ -103,6 +103,42 @@ __device__ __forceinline__ void stg256(void *p, const uint32_t *v) {
                  :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
+// One warp's share of a tile's epilogue: 4 chunks of 32 accumulator columns [col0, col0 + 128) of the warp's TMEM lane quarter
+// (a lane owns one output row): + bias, ReLU, bf16, two 256-bit stores per chunk (whole 32-byte sectors; the 16-byte stores of
+// the first version left every sector half-written per instruction).  SIXTEEN warps per CTA share a tile -- the 8 epilogue warps
+// and the 8 converter warps, which have nothing to convert while the accumulator is being drained (the MMAs of the next tile
+// wait for it): the accumulator fills all 512 TMEM columns, so the MMAs idle for the length of the epilogue.
+__device__ __forceinline__ void gg_epilogue_part(uint32_t tmem_base, int quarter, int col0, long long m, const GatherGemmParams &p,
+                                                 uint32_t bias_s) {
+    const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+    uint32_t vbuf[2][32];
+    tmem_ld32_nowait(t_addr, vbuf[0]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+        uint32_t (&v)[32] = vbuf[ci & 1];
+        if (ci + 1 < 4) tmem_ld32_nowait(t_addr + (uint32_t)((ci + 1) * 32), vbuf[(ci + 1) & 1]);
+        const int c0 = col0 + ci * 32;
+        uint32_t o[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = lds128(bias_s + (uint32_t)((c0 + 4 * j4) * 4));          // same address in every lane: broadcast
+            float a0 = __uint_as_float(v[4 * j4]) + b4.x, a1 = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+            float a2 = __uint_as_float(v[4 * j4 + 2]) + b4.z, a3 = __uint_as_float(v[4 * j4 + 3]) + b4.w;
+            if (p.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); a2 = fmaxf(a2, 0.0f); a3 = fmaxf(a3, 0.0f); }
+            o[2 * j4] = pack_bf16x2(a0, a1);
+            o[2 * j4 + 1] = pack_bf16x2(a2, a3);
+        }
+        if (m < p.M && !(p.debug & 2)) {
+            __nv_bfloat16 *dst = p.y + m * kGgN + c0;
+            stg256(dst, o);
+            stg256(dst + 16, o + 8);
+        }
+        if (ci + 1 < 4) tmem_wait_ld();
+    }
+    tcgen05_fence_before();
+}
+
 template <int FS, int AS, int BS>
 __global__ void __launch_bounds__(kGgThreads, 1)
 gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_constant__ CUtensorMap tmap_w,
@@ -123,7 +159,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
     uint64_t *b_full = a_empty + AS;                 // [BS] leader: both halves of the W1 k-block have landed
     uint64_t *b_empty = b_full + BS;                 // [BS] tcgen05.commit multicast: the MMAs have read B[s]
     uint64_t *acc_full = b_empty + BS;               // tcgen05.commit multicast
-    uint64_t *acc_empty = acc_full + 1;              // leader: the 8 epilogue warps of both CTAs have drained the accumulator
+    uint64_t *acc_empty = acc_full + 1;              // leader: the 16 draining warps of both CTAs are done with the accumulator
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,7 +175,7 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
         for (int i = 0; i < AS; ++i) { bar_init(&a_full[i], 2 * kGgConvWarps); bar_init(&a_empty[i], 1); }
         for (int i = 0; i < BS; ++i) { bar_init(&b_full[i], 2); bar_init(&b_empty[i], 1); }
         bar_init(acc_full, 1);
-        bar_init(acc_empty, 16);
+        bar_init(acc_empty, 2 * (8 + kGgConvWarps));      // every epilogue and converter warp of both CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -265,10 +301,30 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
             m_nx = __ldg(reinterpret_cast<const float4 *>(p.mean + cg * 4));
             s_nx = __ldg(reinterpret_cast<const float4 *>(p.stdv + cg * 4));
         }
+        // The converter warps take column blocks 2 and 3 of their TMEM lane quarter in every tile's epilogue.  They join it when
+        // they have nothing else to do: the first AS k-steps of the NEXT tile are converted (the A ring is full and stays full
+        // until the MMAs of that tile may start, i.e. until the accumulator is drained), or after the last tile.
+        const int e_quarter = warp & 3, e_block = 2 + ((warp - 2) >> 2);
+        const uint32_t bias_s = s_addr(bias_sm);
+        uint32_t acc_par = 0;
+        auto drain = [&](long long tile_done) {
+            const long long m = tile_done * 256 + (long long)rank * 128 + e_quarter * 32 + lane;
+            bar_wait(acc_full, acc_par);
+            tcgen05_fence_after();
+            gg_epilogue_part(tmem_base, e_quarter, e_block * 128, m, p, bias_s);
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) bar_arrive(acc_empty);
+                else bar_arrive_cluster(mapa_rank(acc_empty, 0));
+            }
+            acc_par ^= 1;
+        };
+        const int drain_kb = AS < nkb ? AS : nkb - 1;      // short K: the ring holds a whole tile
         long long it = 0;
         for (long long tile = pair_id; tile < tiles; tile += pair_stride) {
             const long long m0 = tile * 256 + (long long)rank * 128;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
+                if (kb == drain_kb && tile != pair_id) drain(tile - pair_stride);
                 const int f = (int)(it % FS), s = (int)(it % AS);
                 const uint32_t fpar = (uint32_t)((it / FS) & 1), spar = (uint32_t)((it / AS) & 1);
                 const float mu0 = m_nx.x, mu1 = m_nx.y, mu2 = m_nx.z, mu3 = m_nx.w;
@@ -309,46 +365,19 @@ gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_
                 }
             }
         }
+        drain(tiles - 1 - ((tiles - 1 - pair_id) % pair_stride));      // this pair's last tile
         if (lane == 0) bulk_wait_all();
         __syncwarp();
     } else {
-        // ================================================================== epilogue (8 warps): bias, ReLU, bf16, stores
-        // A lane owns one output row; per 32-column chunk it writes 64 contiguous bytes as two 256-bit stores (whole 32-byte
-        // sectors: the 16-byte stores of the first version left every sector half-written per instruction).
-        const int quarter = warp & 3, half = (warp - 2 - kGgConvWarps) >> 2;
+        // ================================================================== epilogue warps (8): column blocks 0 and 1 of their quarter
+        const int quarter = warp & 3, block = (warp - 2 - kGgConvWarps) >> 2;
         const uint32_t bias_s = s_addr(bias_sm);
         uint32_t acc_par = 0;
         for (long long tile = pair_id; tile < tiles; tile += pair_stride) {
             const long long m = tile * 256 + (long long)rank * 128 + quarter * 32 + lane;
             bar_wait_sleep(acc_full, acc_par);       // a tile takes ~35 us: do not poll the issue slots away from the converters
             tcgen05_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 256);
-            uint32_t vbuf[2][32];
-            tmem_ld32_nowait(t_addr, vbuf[0]);
-            tmem_wait_ld();
-#pragma unroll
-            for (int ci = 0; ci < 8; ++ci) {
-                uint32_t (&v)[32] = vbuf[ci & 1];
-                if (ci + 1 < 8) tmem_ld32_nowait(t_addr + (uint32_t)((ci + 1) * 32), vbuf[(ci + 1) & 1]);
-                const int c0 = half * 256 + ci * 32;
-                uint32_t o[16];
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 b4 = lds128(bias_s + (uint32_t)((c0 + 4 * j4) * 4));          // same address in every lane: broadcast
-                    float a0 = __uint_as_float(v[4 * j4]) + b4.x, a1 = __uint_as_float(v[4 * j4 + 1]) + b4.y;
-                    float a2 = __uint_as_float(v[4 * j4 + 2]) + b4.z, a3 = __uint_as_float(v[4 * j4 + 3]) + b4.w;
-                    if (p.relu) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); a2 = fmaxf(a2, 0.0f); a3 = fmaxf(a3, 0.0f); }
-                    o[2 * j4] = pack_bf16x2(a0, a1);
-                    o[2 * j4 + 1] = pack_bf16x2(a2, a3);
-                }
-                if (m < p.M && !(p.debug & 2)) {
-                    __nv_bfloat16 *dst = p.y + m * kGgN + c0;
-                    stg256(dst, o);
-                    stg256(dst + 16, o + 8);
-                }
-                if (ci + 1 < 8) tmem_wait_ld();
-            }
-            tcgen05_fence_before();
+            gg_epilogue_part(tmem_base, quarter, block * 128, m, p, bias_s);
             __syncwarp();
             if (lane == 0) {
                 if (leader) bar_arrive(acc_empty);
