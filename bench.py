@@ -331,6 +331,8 @@ def other_configs(args, ds, device):
         r = bench_frame.measure(frames=600, videos=32, steps=20)
         out["train_frame"] = {"unit": "frames/s", "frames_per_video": 600,
                               "cuda_graph": r["b200_graph"]["train_frames_per_s"], "eager": r["b200"]["train_frames_per_s"],
+                              "cuda_graph_bf16_mode": r.get("b200_graph_bf16_fe", {}).get("train_frames_per_s"),
+                              "ms_per_video_cuda_graph_bf16_mode": r.get("b200_graph_bf16_fe", {}).get("train_ms_per_video"),
                               "stock_torch_layers": r["torch_layers"]["train_frames_per_s"],
                               "ms_per_video_cuda_graph": r["b200_graph"]["train_ms_per_video"],
                               "inference_ragged_frames_per_s": r["head_inference"]["ragged_frames_per_s"], "config": r["config"]}

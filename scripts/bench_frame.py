@@ -106,6 +106,18 @@ def measure(frames: int = 600, videos: int = 64, steps: int = 30) -> dict:
     step = FrameTrainStep(images, kin, e7, fe, model, crit, opt, kw).capture()
     ms = timed(step.run, args.steps)
     res["b200_graph"] = {"train_ms_per_video": ms, "train_frames_per_s": T / ms * 1e3, "own_launches_per_step": step.launches_per_step}
+    # the bf16 mode of the same step: FeatureExtractor on the tcgen05 GEMMs (2e-2 bar), TeCNo training on its fp32 kernels
+    try:
+        kw16 = dict(kw, precision="bf16")
+        fe16, model16, crit16, opt16, _ = mu.define_model_objects(kw16, {"multimodal": 58, "video": 32, "kinematics": 26}, dev, (0.4, 0.6))
+        model16.train(); fe16.train()
+        step16 = FrameTrainStep(images, kin, e7, fe16, model16, crit16, opt16, kw16).capture()
+        ms16 = timed(step16.run, args.steps)
+        res["b200_graph_bf16_fe"] = {"train_ms_per_video": ms16, "train_frames_per_s": T / ms16 * 1e3,
+                                     "own_launches_per_step": step16.launches_per_step, "loss": float(step16.loss.item())}
+        del step16
+    except Exception as e:      # noqa: BLE001 -- an auxiliary line must not take the others down
+        res["b200_graph_bf16_fe"] = {"error": f"{type(e).__name__}: {e}"}
     # ragged-batched inference of the head: V videos in one pass vs one pass per video
     model.eval()
     lengths = torch.randint(300, 901, (args.videos,), generator=g).tolist()

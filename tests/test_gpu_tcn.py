@@ -305,3 +305,47 @@ def test_bf16_tcgen05_inference_matches_fp32(ops, causal, lengths):
         alone = m.forward_ragged(frames[:lengths[0]], lengths[:1])
         m.precision = "fp32"
         ok, err = close(out[:, :, :lengths[0]], alone, 1e-6); assert ok, err
+
+
+def test_frame_train_step_bf16_mode_vs_fp32_mode():
+    """The frame path in the bf16 mode (exp_kwargs['precision'] = 'bf16'): the FeatureExtractor's products run on the tcgen05
+    GEMMs, TeCNo trains on its fp32 kernels (one video per step is a latency chain: bf16 MMAs would not shorten it).  One
+    train-mode forward / backward on the same seed-42 weights and the same video in both modes, dropout off: loss and logits
+    within the bf16-mode bar (2e-2), every gradient on the fp32 gradient's side (cosine > 0.99)."""
+    from multimodal_error_detection_b200 import ops
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    T = 437
+    g = torch.Generator().manual_seed(9)
+    images = torch.randn(1, T, 2048, generator=g).clamp_min(0).to(DEV)
+    kin = torch.randn(1, T, 26, generator=g).to(DEV)
+    y = (torch.rand(1, T, generator=g) > 0.5).float().to(DEV)
+    out = {}
+    for precision in ("fp32", "bf16"):
+        kw = dict(dataset_type="frame", error_type="global", pos_weight=False, n_epochs=2, batch_size=1, lr=3e-4, lr_scheduler=True,
+                  weight_decay=1e-4, num_layers=3, hidden_size=128, video_dims=32, data_type="multimodal", delete_ND=True,
+                  return_train_preds=False, siamese=False, model_name="TeCNo", mstcn_stages=2, mstcn_layers=8, mstcn_f_maps=64,
+                  mstcn_f_dim=58, out_features=2, mstcn_causal_conv=True, precision=precision)
+        fe, model, crit, opt, _ = mu.define_model_objects(kw, {"multimodal": 58, "video": 32, "kinematics": 26}, torch.device(DEV), (0.4, 0.6))
+        for mod in list(model.modules()) + list(fe.modules()):
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        model.train(); fe.train()
+        logits = model(mu.define_inputs(images, kin, fe, kw, torch.device(DEV)))
+        loss, _ = mu.compute_loss(logits, y, crit, "frame")
+        loss.backward()
+        grads = {f"fe.{k}": p.grad.detach().clone() for k, p in fe.named_parameters()}
+        grads.update({f"model.{k}": p.grad.detach().clone() for k, p in model.named_parameters()})
+        out[precision] = (float(loss), logits.detach().clone(), grads, getattr(fe, "precision", None))
+    assert out["bf16"][3] == "bf16" and out["fp32"][3] == "fp32"
+    l32, l16 = out["fp32"][0], out["bf16"][0]
+    assert abs(l16 - l32) <= 2e-2 * abs(l32), (l16, l32)
+    ok, err = close(out["bf16"][1], out["fp32"][1], 2e-2); assert ok, err
+    assert not torch.equal(out["bf16"][1], out["fp32"][1])          # really another arithmetic
+    for k, g32 in out["fp32"][2].items():
+        g16 = out["bf16"][2][k]
+        if float(g32.norm()) < 1e-12:
+            continue
+        cos = float((g16.double() * g32.double()).sum() / (g16.double().norm() * g32.double().norm()))
+        assert cos > 0.99, (k, cos)
