@@ -45,13 +45,29 @@ class MLPTailFunction(torch.autograd.Function):
         B = x.shape[0]
         tc = [precision == "bf16" and ops.has_tcgen05() and _tc_ok(t[7 * i]) for i in range(n_hidden)]
         a_in, acts, ys, stats, extra = x, [], [], [], []
+        # the split copies of the WEIGHTS do not depend on the activations: they are made on the side stream while the first
+        # layers run (a launch on the critical path costs ~5 us inside the replayed step, whatever its size)
+        main, side = torch.cuda.current_stream(), _side(x.device)
+        w_split = {}
+        if any(tc):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for i in range(n_hidden):
+                    if tc[i]:
+                        w_split[i] = ops.split_bf16x3(t[7 * i].detach().contiguous(), 1, 1 if training else None)
         for i in range(n_hidden):
             W, b, gamma, beta, rm, rv, nbt = t[7 * i:7 * i + 7]
             if tc[i]:
                 N, K = W.shape
                 # left operand (hi, lo, hi) by rows for this product; stacked RIGHT copy (hi, hi, lo) for the weight gradient
                 x_row, x_stack = ops.split_bf16x3(a_in, 0, 1 if training else None, relu=(i == 0 and relu_in))
-                w_row, w_stack = ops.split_bf16x3(W.detach().contiguous(), 1, 1 if training else None)
+                if i == min(w_split):
+                    main.wait_stream(side)
+                    for pair in w_split.values():
+                        for tns in pair:
+                            if tns is not None:
+                                tns.record_stream(main)
+                w_row, w_stack = w_split[i]
                 a = ops.gemm_bf16(x_row, w_row, B, N, 3 * K, True, True, bias=b.detach(), relu=True, out_dtype=torch.float32)
                 extra += [x_stack, w_stack] if training else []
             else:
@@ -92,34 +108,65 @@ class MLPTailFunction(torch.autograd.Function):
         g = dout.contiguous().float()
         B = g.shape[0]
         last_in = ys[-1] if n else x
-        grads[7 * n] = ops.linear_wgrad_f32(g, last_in, relu_x=(n == 0 and ctx.relu_in))
-        grads[7 * n + 1] = ops.colsum(g)
         need_dx = ctx.needs_input_grad[0]
+        # Only the data gradients feed the next layer: the weight / bias gradients run on the side stream, next to the rest
+        # of this backward and to the LSTM recurrence that follows (same stream and deferred join as lstm_stack's weight
+        # gradients).  `keep` holds what the side stream reads until the join.
+        from . import lstm_stack
+        main, side = torch.cuda.current_stream(), _side(g.device)
+        keep, side_grads = [], []
+
+        def on_side(fn, *reads):
+            keep.extend(reads)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.sm_limit(TAIL_SIDE_SMS):
+                out = fn()
+            side_grads.append(out)
+            return out
+
+        grads[7 * n] = on_side(lambda: ops.linear_wgrad_f32(g, last_in, relu_x=(n == 0 and ctx.relu_in)), g, last_in)
+        grads[7 * n + 1] = on_side(lambda: ops.colsum(g), g)
         if n or need_dx:
             g = ops.linear_dgrad_f32(g, Wl, mask=x if (n == 0 and ctx.relu_in) else None)
         for i in reversed(range(n)):
             dz, dgamma, dbeta = ops.bn_bwd(g, acts[i], gammas[i], stats[2 * i], stats[2 * i + 1], relu_mask=True)
             inp = ys[i - 1] if i > 0 else x
-            grads[7 * i + 1] = ops.colsum(dz)
+            grads[7 * i + 1] = on_side(lambda dz=dz: ops.colsum(dz), dz)
             grads[7 * i + 2], grads[7 * i + 3] = dgamma, dbeta
             if tc[i]:
                 N, K = Ws[i].shape
                 want_dx = i > 0 or need_dx
                 dz_row, dz_stack = ops.split_bf16x3(dz, 0 if want_dx else None, 0)
                 # dW [N, K] = dz^T in over the (3x stacked) batch rows: both operands MN-major, deterministic split-K
-                grads[7 * i] = ops.gemm_bf16(dz_stack, x_stack[i], N, K, 3 * B, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
-                                             split_k=ops.gemm_split_k(N, K, 3 * B))
+                grads[7 * i] = on_side(lambda dz_stack=dz_stack, i=i, N=N, K=K: ops.gemm_bf16(
+                    dz_stack, x_stack[i], N, K, 3 * B, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
+                    split_k=ops.gemm_split_k(N, K, 3 * B)), dz_stack, x_stack[i])
                 if want_dx:     # d_in [B, K] = dz [B, 3N] W'' [3N, K]; the first layer's input went through the folded ReLU:
                     # its mask is the hi block of the stacked copy (bf16(max(x, 0)) > 0 exactly where x > 0)
                     g = ops.gemm_bf16(dz_row, w_stack[i], B, K, 3 * N, a_kmajor=True, b_kmajor=False, out_dtype=torch.float32,
                                       mask=x_stack[i][:B] if (i == 0 and ctx.relu_in) else None)
                 continue
-            grads[7 * i] = ops.linear_wgrad_f32(dz, inp, relu_x=(i == 0 and ctx.relu_in))
+            grads[7 * i] = on_side(lambda dz=dz, inp=inp, i=i: ops.linear_wgrad_f32(dz, inp, relu_x=(i == 0 and ctx.relu_in)), dz, inp)
             if i > 0:
                 g = ops.linear_dgrad_f32(dz, Ws[i])
             elif need_dx:
                 g = ops.linear_dgrad_f32(dz, Ws[i], mask=x if ctx.relu_in else None)
+        if lstm_stack.DEFER_JOIN:
+            lstm_stack._PENDING.append((side, keep))      # joined by the gradient consumer (lstm_stack.join_pending)
+        else:
+            main.wait_stream(side)
+            keep = []
+        for sg in side_grads:
+            sg.record_stream(main)                        # allocated on the side stream, consumed on the main one
         return (g if need_dx else None, None, None, None, None, *grads)
+
+
+TAIL_SIDE_SMS = 32       # SMs the tail's side-stream gradient kernels may fill (they are a few tiles each)
+
+
+def _side(device):
+    from . import lstm_stack
+    return lstm_stack._side_stream(device)
 
 
 def mlp_tail(x: torch.Tensor, seq: nn.Sequential, relu_in: bool, training: bool, precision: str = "fp32") -> torch.Tensor:
