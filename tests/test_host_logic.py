@@ -231,3 +231,61 @@ def test_gloo_world2_gradient_exchange(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+_PEER_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from multimodal_error_detection_b200 import parallel
+rank, _, world = parallel.init_from_env("gloo")
+# no CUDA device here: the allocation of the peer buffer fails on every rank; the set-up must notice that COLLECTIVELY (every
+# rank raises, nobody is left waiting in a collective) so that the callers fall back to the NCCL / gloo all-reduce together
+try:
+    parallel.PeerAllReduce(1000, "cpu")
+    raise SystemExit("PeerAllReduce succeeded without a GPU")
+except RuntimeError as e:
+    assert "peer-memory exchange unavailable" in str(e), str(e)
+# the ranks are still in step: a collective after the failed set-up completes
+t = torch.tensor([float(rank + 1)])
+dist.all_reduce(t)
+assert float(t) == 3.0
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gloo_world2_peer_exchange_setup_fails_collectively(tmp_path, built_lib):
+    """parallel.PeerAllReduce (the NVLink peer-memory gradient exchange) negotiates its set-up: where the mappings cannot be
+    made -- here: no GPU at all -- EVERY rank gets the RuntimeError and the process group stays usable (FusedAdam then keeps
+    the all-reduce of torch.distributed, with a RuntimeWarning)."""
+    script = tmp_path / "peer_worker.py"
+    script.write_text(_PEER_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29733",
+                   CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_split_k_choice_fills_whole_waves(built_lib):
+    """b200med_gemm_bf16_pick_split (host logic, no GPU needed: 148 SMs assumed without a device): the weight-gradient shapes of
+    the headline step get a split whose tiles x splits work items fill the SMs (or SM pairs) in whole waves -- the first
+    heuristic gave the layer-1 gradient 160 items on 74 pairs = 3 waves at 72 %."""
+    import ctypes as C
+    lib = C.CDLL(built_lib)
+    lib.b200med_gemm_bf16_pick_split.restype = C.c_int32
+    lib.b200med_gemm_bf16_pick_split.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32]
+    rows = 8192 * 16
+    for M, N, pair in ((512, 2048, True), (512, 256, True), (256, 512, True), (512, 192, False), (32, 256, False)):
+        s = lib.b200med_gemm_bf16_pick_split(M, N, rows, 0)
+        assert 1 <= s <= 160 and (rows // 64) // s >= 8, (M, N, s)
+        bn = 256 if N >= 256 else 128 if N > 64 else 64
+        tiles = (-(-M // 256)) * (-(-N // 256)) if pair else (-(-M // 128)) * (-(-N // bn))
+        units = 74 if pair else 148
+        items = tiles * s
+        waves = -(-items // units)
+        assert items / (waves * units) >= 0.85 or items <= units, (M, N, s, items, waves)
+    assert lib.b200med_gemm_bf16_pick_split(512, 2048, rows, 0) == 9
+    assert lib.b200med_gemm_bf16_pick_split(512, 2048, 512, 0) == 1          # short K: no split
