@@ -289,3 +289,26 @@ def test_split_k_choice_fills_whole_waves(built_lib):
         assert items / (waves * units) >= 0.85 or items <= units, (M, N, s, items, waves)
     assert lib.b200med_gemm_bf16_pick_split(512, 2048, rows, 0) == 9
     assert lib.b200med_gemm_bf16_pick_split(512, 2048, 512, 0) == 1          # short K: no split
+
+
+def test_epoch_scores_equal_the_per_batch_scores():
+    """modeling_utils._epoch_scores (all batches of an epoch at once) == the per-batch `_batch_scores` accumulated batch after
+    batch, bit for bit: random counts plus the degenerate batches (one label present, empty predictions, empty batch)."""
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 400, size=(64, 4))
+    counts[3] = (50, 0, 0, 0)        # only label 0 present: sklearn's 1x1 confusion matrix is broadcast (reference quirk)
+    counts[7] = (0, 0, 0, 9)         # only label 1
+    counts[11] = (0, 12, 0, 0)       # y_true all 0, predictions all 1
+    counts[12] = (0, 0, 5, 0)
+    counts[20] = (0, 0, 0, 0)
+    tot, cm = np.zeros(4), np.zeros((2, 2), dtype=int)
+    for c in counts:
+        f1, f1w, acc, jac, contrib = mu._batch_scores(c)
+        tot += (f1, f1w, acc, jac)
+        cm += contrib
+    tot2, cm2 = mu._epoch_scores(counts)
+    assert np.array_equal(tot, tot2), (tot, tot2)
+    assert np.array_equal(cm, cm2), (cm, cm2)
+    t0, c0 = mu._epoch_scores(np.zeros((0, 4), dtype=np.int64))
+    assert not t0.any() and not c0.any()
