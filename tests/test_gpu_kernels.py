@@ -239,15 +239,17 @@ def test_gather_norm_benchmarked_instantiation_vs_oracle(B, W, want_variant, exa
     assert ops.gather_last_variant() == want_variant and torch.equal(img2, img_out)
 
 
-@pytest.mark.parametrize("B,W", [(8192, 16), (100, 16), (33, 32), (7, 128), (1, 64)])
-def test_gather_linear_fused_vs_k1_then_gemm(B, W, ops):
+@pytest.mark.parametrize("B,W,K", [(8192, 16, 2048), (100, 16, 2048), (33, 32, 2048), (7, 128, 2048), (1, 64, 2048),
+                                   (300, 16, 64), (300, 16, 128), (300, 16, 192), (1000, 16, 256)])
+def test_gather_linear_fused_vs_k1_then_gemm(B, W, K, ops):
     """b200med_gather_linear_bf16 (K1 fused into the FeatureExtractor's first layer): the bf16 batch it emits is BIT-IDENTICAL to
     the standalone K1 kernel's (which the tests above pin to the C oracle), and its output equals the tcgen05 GEMM on that batch
-    (same operands, same fp32 accumulation: at most an ulp of bf16 apart) -- at the headline size and on ragged tile tails."""
+    (same operands, same fp32 accumulation: at most an ulp of bf16 apart) -- at the headline size, on ragged tile tails and for
+    short reductions (K of one to four k-blocks: the operand rings then hold a whole tile and the tile hand-over changes)."""
     if not ops.has_tcgen05():
         pytest.skip("needs sm_100")
-    g = torch.Generator(device="cuda").manual_seed(B + W)
-    N, K = 30_000, 2048
+    g = torch.Generator(device="cuda").manual_seed(B + W + K)
+    N = 30_000
     table = torch.randn(N, K, device="cuda", generator=g).clamp_min_(0)
     mean, std = torch.randn(K, device="cuda", generator=g) * 0.3, torch.rand(K, device="cuda", generator=g) + 0.25
     starts = torch.randint(0, N - W, (B,), device="cuda", generator=g, dtype=torch.int64).to(torch.int32)
