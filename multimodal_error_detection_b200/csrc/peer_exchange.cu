@@ -9,8 +9,8 @@
 //      same bits, computed once by the slice's owner) and stores s into G_q[slice r] of EVERY rank (peer stores);
 //   C  fence, "my slice is everywhere" -> flags; wait for all peers; the kernel ends when this rank's buffer is complete.
 // 6.4 MB of gradients at 8 ranks: 2 x 7/8 x 6.4 MB per rank over NVLink (~16 us at 700 GB/s) + two flag round trips, against
-// ~0.1 ms for the NCCL call inside the captured step.  Every spin is bounded (trap): a rank that never launches its kernel is an
-// error on the others, not a hung box.  The kernel may be captured in a CUDA graph (all arguments are device-resident).
+// ~0.1 ms for the NCCL call inside the captured step.  Every spin is bounded (two minutes, then trap): a rank that never launches
+// its kernel is an error on the others, not a hung box.  The kernel may be captured in a CUDA graph (all arguments are device-resident).
 #include "common.cuh"
 
 namespace b200med {
@@ -36,11 +36,24 @@ __device__ __forceinline__ float4 ld_sys_f4(const float *p) {
 __device__ __forceinline__ void st_sys_f4(float *p, const float4 &v) {
     asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Ranks may arrive seconds apart (a rank that captures a graph, pages its table in, runs a host-side baseline): the wait is
+// bounded in TIME -- two minutes -- not in polls; past that a peer never launched its kernel and this is an error, not a wait.
+constexpr unsigned long long kPeerWaitNs = 120ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ void wait_flag(const uint32_t *p, uint32_t epoch) {
     // epochs only grow; the comparison is wrap-safe
-    for (unsigned long long spins = 0; (int32_t)(ld_acquire_sys(p) - epoch) < 0; ++spins) {
-        __nanosleep(64);
-        if (spins > (1ull << 25)) __trap();          // seconds: a peer never launched its kernel
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0; (int32_t)(ld_acquire_sys(p) - epoch) < 0; ++spins) {
+        __nanosleep(spins < 64 ? 32 : 256);
+        if ((spins & 1023u) == 1023u) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kPeerWaitNs) __trap();
+        }
     }
 }
 
