@@ -541,3 +541,39 @@ class _lib_sm_limit:
 
     def __exit__(self, *exc):
         self.lib.b200med_set_sm_limit(self.prev)
+
+
+@pytest.mark.parametrize("Ca,Cb,stat_rows,B,W", [(32, 26, 1, 77, 16), (32, 26, 16, 77, 16), (5, 3, 1, 40, 10), (31, 27, 1, 9, 7), (64, 0, 1, 33, 4)])
+def test_lstm_pack_parts_kernel(Ca, Cb, stat_rows, B, W):
+    """b200med_lstm_pack_parts (FeatureExtractor output + kinematics gathered / standardised from the frame table -> first operand
+    of the LSTM recurrence, bf16, time-major) against its definition built with torch: columns [0, Ca) = bf16(feats),
+    [Ca, Ca + Cb) = bf16((table[start + t] - mean) / std) (IEEE subtract / divide, as CustomWindowDataset.py:56-60), padding
+    and the h_{-1} columns of step 0 zero, the h columns of the later steps untouched.  Even / odd widths, one statistics row or
+    one per step: both the 64-column fast path and the generic kernel."""
+    import ctypes as C
+    from multimodal_error_detection_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(Ca * 100 + Cb)
+    H, hoff = 128, 64
+    Kp, Bp, N = hoff + H, (B + 31) // 32 * 32, 3000
+    feats = torch.randn(B, W, Ca, device=DEV, generator=g)
+    table = torch.randn(N, max(Cb, 1), device=DEV, generator=g)[:, :Cb].contiguous() if Cb else torch.zeros(N, 0, device=DEV)
+    mean = torch.randn(stat_rows, max(Cb, 1), device=DEV, generator=g)[:, :Cb].contiguous()
+    std = (torch.rand(stat_rows, max(Cb, 1), device=DEV, generator=g) + 0.5)[:, :Cb].contiguous()
+    starts = torch.randint(0, N - W, (B,), device=DEV, generator=g, dtype=torch.int64).to(torch.int32)
+    sentinel = 7.0
+    A0 = torch.full((W, Bp, Kp), sentinel, dtype=torch.bfloat16, device=DEV)
+    P = lambda t: C.c_void_p(t.data_ptr() if t is not None and t.numel() else 0)
+    _lib.call("b200med_lstm_pack_parts", P(feats), Ca, P(table), N, Cb, P(mean if Cb else None), P(std if Cb else None), stat_rows,
+              P(starts), P(A0), B, Bp, W, H, Kp, hoff, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    rows = starts.long()[:, None] + torch.arange(W, device=DEV)[None]                  # [B, W]
+    want = torch.full((W, Bp, Kp), sentinel, dtype=torch.float32, device=DEV)
+    want[:, :B, :Ca] = feats.permute(1, 0, 2)
+    if Cb:
+        kin = table[rows]                                                              # [B, W, Cb]
+        m = mean[0] if stat_rows == 1 else mean[None, :, :]
+        s = std[0] if stat_rows == 1 else std[None, :, :]
+        want[:, :B, Ca:Ca + Cb] = ((kin - m) / s).permute(1, 0, 2)
+    want[:, :B, Ca + Cb:hoff] = 0.0
+    want[0, :B, hoff:] = 0.0                                                           # h_{-1}; later steps keep the sentinel
+    assert torch.equal(A0.view(torch.int16), want.to(torch.bfloat16).view(torch.int16))
