@@ -121,7 +121,7 @@ int b200med_gather_last_variant(void);
  * Linear layer on the tensor cores -- what the reference does as CustomWindowDataset.__getitem__ + collate + .to(device)
  * (CustomWindowDataset.py:53-60, modeling_utils.py:40) followed by the FeatureExtractor's first Linear + ReLU (models.py:19-35).
  *   xb [B*W, K] bf16 OUT = bf16((table[starts[b] + t, :] - mean) * (1 / std))     (bit-identical to b200med_gather_norm's bf16
- *                          output with exact_div = 0; the backward's weight-gradient operand)
+ *                          output with exact_div = 0; the backward's weight-gradient operand; NULL = not kept: inference)
  *   y  [B*W, N] bf16 OUT = relu?(xb w^T + bias),  w [N, K] bf16 row-major (nn.Linear layout), N = 512, K % 64 == 0,
  *   W in {16, 32, 64, 128} (TMA boxes of W table rows tile the 128-row operand).  A window outside the table traps.   */
 int b200med_gather_linear_bf16(const float *table, int64_t table_rows, const float *mean, const float *stdv,

@@ -420,7 +420,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_linear_bf16
     const void *w_bf16, const float *bias, int32_t relu, void *xb, void *y, int32_t N, int32_t K, void *stream) {
     B200MED_REQUIRE(B >= 1 && table_rows >= W && N == kGgN && K >= 64 && K % 64 == 0, "N must be 512 and K a multiple of 64");
     B200MED_REQUIRE(W >= 16 && W <= 128 && 128 % W == 0, "window length must be 16, 32, 64 or 128 (TMA boxes of W rows tile the 128-row operand)");
-    B200MED_REQUIRE(table && starts && w_bf16 && xb && y, "null pointer");
+    B200MED_REQUIRE(table && starts && w_bf16 && y, "null pointer");      // xb may be NULL: inference keeps no bf16 batch
     B200MED_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean and std must both be given or both NULL");
     B200MED_REQUIRE(((uintptr_t)table % 16 == 0) && ((uintptr_t)w_bf16 % 16 == 0) && ((uintptr_t)xb % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
                     (!mean || (((uintptr_t)mean % 16 == 0) && ((uintptr_t)stdv % 16 == 0))), "operands must be 16-byte aligned");
@@ -435,10 +435,11 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_linear_bf16
     }
     if (int e = make_tmap_table_f32(&tt, table, K, table_rows, W, 64)) return e;
     if (int e = make_tmap(&tw, w_bf16, K, N, K, 64, 128)) return e;            // W1 [512, K] bf16: box {64 k, 128 rows}
-    if (int e = make_tmap(&tx, xb, K, M, K, 64, 128 / kGgConvWarps)) return e;  // Xb [M, K] bf16: box {64 k, 16 rows}: one per converter warp
+    if (xb) { if (int e = make_tmap(&tx, xb, K, M, K, 64, 128 / kGgConvWarps)) return e; }  // Xb [M, K] bf16: box {64 k, 16 rows}: one per converter warp
+    else tx = tw;                                                                              // never dereferenced: no Xb store
     GatherGemmParams p{};
     p.starts = starts; p.mean = mean; p.stdv = stdv; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16 *>(y);
-    p.B = B; p.M = M; p.W = W; p.K = K; p.relu = relu; p.table_rows = table_rows; p.debug = dbg_env;
+    p.B = B; p.M = M; p.W = W; p.K = K; p.relu = relu; p.table_rows = table_rows; p.debug = dbg_env | (xb ? 0 : 1);      // bit 1: the converter warps skip their TMA stores
     // ring depths: (fp32 staging, A, B); the alternatives are kept for scripts/bench_gather_gemm.py (B200MED_GG_RINGS)
     static int rings = -1;
     if (rings < 0) {

@@ -87,11 +87,25 @@ def window_model_probabilities(dataset, feature_extractor, model, exp_kwargs: di
     probs = torch.empty(n, dtype=torch.float32, device=dev)
     image_dtype = mu._image_dtype(feature_extractor)
     zeros = torch.zeros(batch_size, dtype=torch.float32, device=dev)
+    # bf16 mode, window lengths the fused kernel serves, a head that takes the kinematics from the table: the gather runs inside
+    # the first FeatureExtractor layer (no bf16 batch is written in inference) and inside the LSTM's first operand (no concat)
+    first = feature_extractor.linear[0] if feature_extractor is not None else None
+    stat_rows = dataset._img_stats[0].shape[0] if dataset._img_stats is not None else 1
+    fused = (feature_extractor is not None and image_dtype == torch.bfloat16 and exp_kwargs["data_type"] == "multimodal"
+             and getattr(model, "accepts_parts", lambda: False)()
+             and ops.gather_linear_supported(dataset._image_table, dataset.W, first.out_features, stat_rows))
     for lo in range(0, n, batch_size):
         hi = min(n, lo + batch_size)
-        idx = torch.arange(lo, hi, device=dev)
-        images, kin = dataset.gather_batch(idx, image_dtype=image_dtype, exact=image_dtype == torch.float32)
-        out = model(mu.define_inputs(images, kin, feature_extractor, exp_kwargs, dev))
+        if fused:
+            from .lstm_stack import WindowParts
+            starts = dataset._starts[lo:hi].contiguous()
+            im, km = dataset._img_stats, dataset._kin_stats
+            feats = feature_extractor.forward_table(dataset._image_table, im[0] if im else None, im[1] if im else None, starts, dataset.W)
+            out = model(feats, parts=WindowParts(dataset._kin_table, km[0] if km else None, km[1] if km else None, starts))
+        else:
+            idx = torch.arange(lo, hi, device=dev)
+            images, kin = dataset.gather_batch(idx, image_dtype=image_dtype, exact=image_dtype == torch.float32)
+            out = model(mu.define_inputs(images, kin, feature_extractor, exp_kwargs, dev))
         r = ops.bce_logits(out.reshape(-1).float().contiguous(), zeros[: hi - lo], want_grad=False, want_probs=True)
         probs[lo:hi] = r["probs"]
     return probs

@@ -158,8 +158,9 @@ def gather_linear_supported(table, W: int, n_out: int, stat_rows: int = 1) -> bo
             and W in (16, 32, 64, 128) and n_out == 512 and stat_rows == 1 and has_tcgen05())
 
 
-def gather_linear_bf16(table, mean, std, starts, W: int, w_bf16, bias, relu: bool = True, events=None):
-    """(xb [B*W, K] bf16, y [B*W, 512] bf16): standardised bf16 windows of `table` and relu(xb w^T + bias) in ONE kernel."""
+def gather_linear_bf16(table, mean, std, starts, W: int, w_bf16, bias, relu: bool = True, events=None, want_xb: bool = True):
+    """(xb [B*W, K] bf16, y [B*W, 512] bf16): standardised bf16 windows of `table` and relu(xb w^T + bias) in ONE kernel.
+    want_xb=False (inference: no backward will read the batch): xb is not written and None is returned in its place."""
     table = _need(table, torch.float32, "table")
     starts = _need(starts, torch.int32, "starts")
     w_bf16 = _need(w_bf16, torch.bfloat16, "w")
@@ -168,7 +169,7 @@ def gather_linear_bf16(table, mean, std, starts, W: int, w_bf16, bias, relu: boo
         mean = _need(mean.reshape(-1), torch.float32, "mean"); std = _need(std.reshape(-1), torch.float32, "std")
         if mean.numel() != K or std.numel() != K:
             raise ValueError("the fused gather takes one mean / std per column")
-    xb = torch.empty(B * W, K, dtype=torch.bfloat16, device=table.device)
+    xb = torch.empty(B * W, K, dtype=torch.bfloat16, device=table.device) if want_xb else None
     y = torch.empty(B * W, N, dtype=torch.bfloat16, device=table.device)
     if events is not None:
         events[0].record()

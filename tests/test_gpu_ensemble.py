@@ -94,3 +94,30 @@ def test_postprocessing_vs_executed_reference(golden_dir):
     assert abs(acc - g["acc"]) < 1e-12 and abs(f1 - g["f1"]) < 1e-12 and abs(jac - g["jaccard"]) < 1e-12
     z = np.load(os.path.join(golden_dir, "postproc_cascade.npz"))
     assert np.array_equal(mu.cascade_ensemble(z["b"], z["m"]).astype(np.int64), z["ens"])
+
+
+def test_window_model_probabilities_fused_route_bf16():
+    """ensemble.window_model_probabilities in the configuration of BASELINE configs[4] (W = 16, bf16 FE + LSTM): the gather runs
+    inside the first FeatureExtractor layer (no bf16 batch written) and inside the recurrence's first operand; the
+    probabilities must agree with the public validate loop (gather_batch + define_inputs on the same weights) to bf16 noise."""
+    from multimodal_error_detection_b200 import ensemble, ops, synthetic
+    from multimodal_error_detection_b200.dataset.CustomWindowDataset import DeviceWindowLoader
+    from multimodal_error_detection_b200.dataset.dataset_utils import dataset_from_index
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    from multimodal_error_detection_b200.table import FrameTable
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    fold = synthetic.make_fold(seed=6, n_train=6, n_test=0, t_lo=150, t_hi=400)
+    image, kin, g, e5, names, offsets = synthetic.flat_tables(fold.train)
+    table = FrameTable(torch.from_numpy(image), torch.from_numpy(kin), torch.from_numpy(g), torch.from_numpy(e5), names)
+    stats = {"image": {"mean": torch.from_numpy(fold.mean_image), "std": torch.from_numpy(fold.std_image)},
+             "kinematics": {"mean": torch.from_numpy(fold.mean_kin), "std": torch.from_numpy(fold.std_kin)}}
+    ds = dataset_from_index(table.window_index(16, 4), True, stats)
+    kw = cases.base_kwargs(model_name="SimpleLSTM", precision="bf16")
+    fe, model, _, _, _ = mu.define_model_objects(kw, cases.IN_FEATURES, torch.device(DEV), ds.binary_error_distribution, 16)
+    n0 = ops._lib.launch_count()
+    probs = ensemble.window_model_probabilities(ds, fe, model, kw, batch_size=150)
+    assert ops._lib.launch_count() > n0 and probs.shape == (len(ds),)
+    v = mu.validate_single_epoch(model, fe, DeviceWindowLoader(ds, 64, shuffle=False), mu.FusedBCEWithLogitsLoss(), DEV, kw)
+    ref = np.asarray(v[8]).reshape(-1)
+    assert np.abs(ref - probs.cpu().numpy()).max() < 5e-3, float(np.abs(ref - probs.cpu().numpy()).max())

