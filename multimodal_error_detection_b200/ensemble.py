@@ -37,6 +37,25 @@ def video_passes(lengths, frames_per_pass: int):
     return passes
 
 
+def frame_features(feature_extractor, image_table: torch.Tensor, r0: int, r1: int) -> torch.Tensor:
+    """FeatureExtractor output [r1 - r0, out] f32 for the rows [r0, r1) of the resident fp32 frame table (inference).  bf16 mode:
+    consecutive rows are "windows" of 128 frames for the fused gather + first-layer kernel (csrc/gather_gemm.cu), so the table
+    rows go fp32 -> bf16 operand tile -> tcgen05.mma inside ONE kernel -- no separate cast pass (8 KB read + 4 KB written per
+    frame) in front of the GEMM and no bf16 copy read back by it; a ragged tail is one more, overlapping, block."""
+    n = r1 - r0
+    first = feature_extractor.linear[0]
+    if (getattr(feature_extractor, "precision", "fp32") != "bf16" or n < 128 or torch.is_grad_enabled()
+            or not ops.gather_linear_supported(image_table, 128, first.out_features, 1)):
+        return feature_extractor(image_table[r0:r1]).float()
+    nb, rem = divmod(n, 128)
+    starts = torch.arange(r0, r0 + nb * 128, 128, dtype=torch.int32, device=image_table.device)
+    if rem:
+        starts = torch.cat([starts, torch.tensor([r1 - 128], dtype=torch.int32, device=image_table.device)])
+    feats = feature_extractor.forward_table(image_table, None, None, starts, 128).float()          # [blocks, 128, out]
+    out = feats[:nb].reshape(nb * 128, -1)
+    return out if not rem else torch.cat([out, feats[nb, 128 - rem:]], dim=0)
+
+
 @torch.no_grad()
 def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwargs: dict, kin_stats: Optional[dict] = None,
                             frames_per_pass: int = 1 << 17) -> torch.Tensor:
@@ -59,8 +78,8 @@ def frame_model_predictions(table: FrameTable, feature_extractor, model, exp_kwa
         r0, r1 = int(off[v]), int(off[w])
         cols = []
         if dt in ("multimodal", "video"):
-            img = table.image[r0:r1]
-            cols.append(img if (dt == "video" and exp_kwargs["video_dims"] == 2048) else feature_extractor(img).float())
+            cols.append(table.image[r0:r1] if (dt == "video" and exp_kwargs["video_dims"] == 2048)
+                        else frame_features(feature_extractor, table.image, r0, r1))
         if dt in ("multimodal", "kinematics"):
             kin = table.kin[r0:r1]
             if kin_stats is not None:

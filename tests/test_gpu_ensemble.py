@@ -121,3 +121,27 @@ def test_window_model_probabilities_fused_route_bf16():
     v = mu.validate_single_epoch(model, fe, DeviceWindowLoader(ds, 64, shuffle=False), mu.FusedBCEWithLogitsLoss(), DEV, kw)
     ref = np.asarray(v[8]).reshape(-1)
     assert np.abs(ref - probs.cpu().numpy()).max() < 5e-3, float(np.abs(ref - probs.cpu().numpy()).max())
+
+
+@pytest.mark.parametrize("n", [128, 1000, 4097])
+def test_frame_features_fused_rows_match_the_plain_forward(n):
+    """ensemble.frame_features (bf16 inference: table rows -> fused gather + first-layer kernel in blocks of 128 consecutive
+    frames, ragged tail as one overlapping block) against FeatureExtractor.forward on the same rows: same bf16 operands and
+    fp32 accumulation, so the features agree to bf16 rounding of the hidden activations."""
+    from multimodal_error_detection_b200 import ensemble, ops
+    from multimodal_error_detection_b200.modeling.models import FeatureExtractor
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    torch.manual_seed(1)
+    fe = FeatureExtractor(2048, 32, [512, 256], precision="bf16").to(DEV).eval()
+    g = torch.Generator(device=DEV).manual_seed(n)
+    table = torch.randn(n + 300, 2048, device=DEV, generator=g).clamp_min_(0)
+    r0 = 137
+    with torch.no_grad():
+        n0 = ops._lib.launch_count()
+        got = ensemble.frame_features(fe, table, r0, r0 + n)
+        assert ops._lib.launch_count() > n0
+        want = fe(table[r0:r0 + n]).float()
+    assert got.shape == want.shape == (n, 32)
+    err = float((got - want).norm() / want.norm())
+    assert err < 5e-3, err
