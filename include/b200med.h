@@ -49,6 +49,11 @@ int64_t b200med_launch_count(void);
 /* Limit the number of SMs the persistent kernels launched BY THE CALLING THREAD fill from now on (grids are sized from it);
  * 0 = all.  Returns the previous limit.  For work issued on a side stream next to a kernel that must keep its SMs.   */
 int b200med_set_sm_limit(int32_t sms);
+/* Programmatic dependent launch for every kernel of the library (process-wide; default on; returns the previous setting).
+ * on: a launch carries cudaLaunchAttributeProgrammaticStreamSerialization, every kernel begins with griddepcontrol.wait, so
+ * the launch latency of kernel k+1 is paid while kernel k drains -- also across the kernel nodes of a captured graph
+ * (the replayed train step of MED/modeling/modeling_utils.py:335-366 is ~100 dependent launches).  Results do not change.  */
+int b200med_set_pdl(int32_t on);
 
 /* ------------------------------------------------------------------------------------------------
  * K0  Window index + label transforms (integer work, bit-exact bar)

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b200med_last_error": (C.c_char_p, []),
     "b200med_launch_count": (_i64, []),
     "b200med_set_sm_limit": (C.c_int, [_i32]),
+    "b200med_set_pdl": (C.c_int, [_i32]),
     "b200med_window_count": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p, _p]),
     "b200med_window_fill": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "b200med_powerset": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
@@ -142,6 +143,8 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch
         fn.restype, fn.argtypes = res, args
+    if os.environ.get("B200MED_PDL", "1") == "0":      # A/B switch of the programmatic dependent launches (scripts, bench)
+        lib.b200med_set_pdl(0)
     _lib = lib
     return lib
 

@@ -10,6 +10,7 @@ namespace b200med {
 
 // state: {step, lr, bias_corr1, sqrt(bias_corr2)}
 __global__ void adam_advance_kernel(float *state, float beta1, float beta2) {
+    pdl_wait();
     const double step = (double)state[0] + 1.0;
     state[0] = (float)step;
     state[2] = (float)(1.0 - pow((double)beta1, step));
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(256)
 adam_step_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                  long long n, const float *__restrict__ state, float beta1, float beta2, float eps, float wd,
                  float gscale) {
+    pdl_wait();
     const float lr = state[1], bc1 = state[2], bc2s = state[3];
     const float step_size = lr / bc1;
     const long long n4 = n >> 2;
@@ -57,7 +59,7 @@ using namespace b200med;
 
 extern "C" __attribute__((visibility("default"))) int b200med_adam_advance(float *state, float beta1, float beta2, void *stream) {
     B200MED_REQUIRE(state, "null state");
-    adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, beta1, beta2);
+    launch_k(adam_advance_kernel, 1, 1, 0, (cudaStream_t)stream, state, beta1, beta2);
     return after_launch("adam_advance_kernel");
 }
 
@@ -69,7 +71,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_adam_step(float *p
     B200MED_REQUIRE(p && g && m && v && state, "null pointer");
     B200MED_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, "flat buffers must be 16-byte aligned");
     const long long want = ((n >> 2) + 255) / 256 + 1, cap = (long long)num_sms() * 8;
-    adam_step_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(adam_step_kernel, (unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream, 
         p, g, m, v, n, state, beta1, beta2, eps, weight_decay, grad_scale);
     return after_launch("adam_step_kernel");
 }

@@ -6,6 +6,7 @@ namespace b200med {
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 thread_local int g_sm_limit = 0;
+std::atomic<int> g_pdl{1};
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -22,4 +23,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_set_sm_limit(int32
     const int prev = b200med::g_sm_limit;
     b200med::g_sm_limit = sms > 0 ? sms : 0;
     return prev;
+}
+extern "C" __attribute__((visibility("default"))) int b200med_set_pdl(int32_t on) {
+    return b200med::g_pdl.exchange(on ? 1 : 0);
 }

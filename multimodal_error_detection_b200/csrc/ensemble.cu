@@ -10,6 +10,7 @@ namespace b200med {
 
 __global__ void window_vote_kernel(const float *__restrict__ fp, const int32_t *__restrict__ starts, long long n,
                                    int W, int binary, float *__restrict__ out) {
+    pdl_wait();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     // numpy mean: pairwise summation degenerates to a plain left-to-right fp64 sum below 8 elements per
@@ -24,6 +25,7 @@ __global__ void window_vote_kernel(const float *__restrict__ fp, const int32_t *
 __global__ void soft_vote_kernel(const float *__restrict__ pa, const float *__restrict__ pb,
                                  const float *__restrict__ labels, long long n, float *__restrict__ preds,
                                  unsigned long long *__restrict__ cnt) {
+    pdl_wait();
     __shared__ unsigned int c[4];
     if (threadIdx.x < 4) c[threadIdx.x] = 0;
     __syncthreads();
@@ -39,12 +41,14 @@ __global__ void soft_vote_kernel(const float *__restrict__ pa, const float *__re
 
 __global__ void cascade_kernel(const int32_t *__restrict__ bin, const int32_t *__restrict__ multi, long long n,
                                int32_t *__restrict__ out) {
+    pdl_wait();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) out[i] = bin[i] == 1 ? multi[i] : 0;
 }
 
 __global__ void confusion_kernel(const int32_t *__restrict__ t, const int32_t *__restrict__ p, long long n, int C,
                                  unsigned long long *__restrict__ cm) {
+    pdl_wait();
     __shared__ unsigned int c[64];
     for (int k = threadIdx.x; k < 64; k += blockDim.x) c[k] = 0;
     __syncthreads();
@@ -58,6 +62,7 @@ __global__ void confusion_kernel(const int32_t *__restrict__ t, const int32_t *_
 }
 
 __global__ void zero_u64_kernel(unsigned long long *p, int n) {
+    pdl_wait();
     if (threadIdx.x < n) p[threadIdx.x] = 0;
 }
 
@@ -70,7 +75,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_window_vote(const 
     B200MED_REQUIRE(n >= 0 && W >= 1, "bad shape");
     if (n == 0) return B200MED_OK;
     B200MED_REQUIRE(frame_preds && starts && out, "null pointer");
-    window_vote_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(frame_preds, starts, n, W, binary, out);
+    launch_k(window_vote_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, frame_preds, starts, n, W, binary, out);
     return after_launch("window_vote_kernel");
 }
 
@@ -80,11 +85,11 @@ extern "C" __attribute__((visibility("default"))) int b200med_soft_vote(const fl
     B200MED_REQUIRE(pa && pb && (!labels || counts), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (counts && !accumulate) {
-        zero_u64_kernel<<<1, 32, 0, st>>>((unsigned long long *)counts, 4);
+        launch_k(zero_u64_kernel, 1, 32, 0, st, (unsigned long long *)counts, 4);
         if (int e = after_launch("zero_u64_kernel")) return e;
     }
     const long long want = (n + 255) / 256, cap = (long long)num_sms() * 4;
-    soft_vote_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(pa, pb, labels, n, preds, (unsigned long long *)counts);
+    launch_k(soft_vote_kernel, (unsigned)(want < cap ? want : cap), 256, 0, st, pa, pb, labels, n, preds, (unsigned long long *)counts);
     return after_launch("soft_vote_kernel");
 }
 
@@ -92,7 +97,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_cascade(const int3
     B200MED_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return B200MED_OK;
     B200MED_REQUIRE(binary && multiclass && out, "null pointer");
-    cascade_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(binary, multiclass, n, out);
+    launch_k(cascade_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, binary, multiclass, n, out);
     return after_launch("cascade_kernel");
 }
 
@@ -102,11 +107,11 @@ extern "C" __attribute__((visibility("default"))) int b200med_confusion(const in
     B200MED_REQUIRE(cm && (n == 0 || (target && pred)), "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) {
-        zero_u64_kernel<<<1, 64, 0, st>>>((unsigned long long *)cm, C * C);
+        launch_k(zero_u64_kernel, 1, 64, 0, st, (unsigned long long *)cm, C * C);
         if (int e = after_launch("zero_u64_kernel")) return e;
     }
     if (n == 0) return B200MED_OK;
     const long long want = (n + 255) / 256, cap = (long long)num_sms() * 4;
-    confusion_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(target, pred, n, C, (unsigned long long *)cm);
+    launch_k(confusion_kernel, (unsigned)(want < cap ? want : cap), 256, 0, st, target, pred, n, C, (unsigned long long *)cm);
     return after_launch("confusion_kernel");
 }

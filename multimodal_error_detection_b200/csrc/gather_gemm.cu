@@ -143,6 +143,7 @@ template <int FS, int AS, int BS>
 __global__ void __launch_bounds__(kGgThreads, 1)
 gather_gemm_kernel(const __grid_constant__ CUtensorMap tmap_table, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_xb, const GatherGemmParams p) {
+    pdl_wait();
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     using S = GgSmem<FS, AS, BS>;
@@ -460,10 +461,10 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_linear_bf16
     cfg.blockDim = dim3(kGgThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1);
     if (int e = check_cuda(cudaLaunchKernelEx(&cfg, kern, tt, tw, tx, p), "cudaLaunchKernelEx(gather_gemm)")) return e;
     return after_launch("gather_gemm_kernel");
 }

@@ -165,6 +165,7 @@ __device__ __forceinline__ void generic_unit(const StreamParams &sp, const int32
 template <typename OutT, bool EXACT, bool HAS_WIDE>
 __global__ void __launch_bounds__(kThreads, (sizeof(OutT) == 2 ? 3 : 4))
 gather_norm_kernel(const __grid_constant__ GatherParams p) {
+    pdl_wait();
     const long long wide_units = HAS_WIDE ? p.s[1].unit_begin : 0;  // s[1].unit_begin == units of stream 0
     for (long long unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
         if (HAS_WIDE && unit < wide_units) {
@@ -219,6 +220,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 template <typename OutT, bool EXACT, int R, int S, int T>
 __global__ void __launch_bounds__(T)
 gather_norm_tma_kernel(const __grid_constant__ GatherParams p) {
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[S];
     const StreamParams &sp = p.s[0];
@@ -327,6 +329,7 @@ gather_norm_tma_kernel(const __grid_constant__ GatherParams p) {
 __global__ void standardise_rows_kernel(const float *__restrict__ x, const float *__restrict__ mean,
                                         const float *__restrict__ stdv, float *__restrict__ out, long long rows,
                                         int dim, int out_ld, int out_col) {
+    pdl_wait();
     const long long n = rows * dim;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / dim;
@@ -421,7 +424,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const 
         auto launch = [&](auto kern, int threads) -> int {
             if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                    "cudaFuncSetAttribute(gather_norm_tma)")) return e;
-            kern<<<grid, threads, smem, st>>>(pt);
+            launch_k(kern, grid, threads, smem, st, pt);
             return after_launch("gather_norm_tma_kernel");
         };
         const bool f32 = pt.s[0].out_dtype == B200MED_F32, ex = pt.s[0].exact_div != 0;
@@ -479,13 +482,13 @@ extern "C" __attribute__((visibility("default"))) int b200med_gather_norm(const 
     const long long max_grid = (long long)sms * 8;  // up to 8 CTAs of 256 threads per SM
     const int grid = (int)(q.total_units < max_grid ? q.total_units : max_grid);
     if (wide_idx < 0) {
-        gather_norm_kernel<float, true, false><<<grid, kThreads, 0, st>>>(q);
+        launch_k(gather_norm_kernel<float, true, false>, grid, kThreads, 0, st, q);
     } else if (q.s[0].out_dtype == B200MED_F32) {
-        if (q.s[0].exact_div) gather_norm_kernel<float, true, true><<<grid, kThreads, 0, st>>>(q);
-        else gather_norm_kernel<float, false, true><<<grid, kThreads, 0, st>>>(q);
+        if (q.s[0].exact_div) launch_k(gather_norm_kernel<float, true, true>, grid, kThreads, 0, st, q);
+        else launch_k(gather_norm_kernel<float, false, true>, grid, kThreads, 0, st, q);
     } else {
-        if (q.s[0].exact_div) gather_norm_kernel<__nv_bfloat16, true, true><<<grid, kThreads, 0, st>>>(q);
-        else gather_norm_kernel<__nv_bfloat16, false, true><<<grid, kThreads, 0, st>>>(q);
+        if (q.s[0].exact_div) launch_k(gather_norm_kernel<__nv_bfloat16, true, true>, grid, kThreads, 0, st, q);
+        else launch_k(gather_norm_kernel<__nv_bfloat16, false, true>, grid, kThreads, 0, st, q);
     }
     return after_launch("gather_norm_kernel");
 }
@@ -498,7 +501,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_standardise_rows(c
     const long long n = rows * dim;
     const long long want = (n + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
-    standardise_rows_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(standardise_rows_kernel, (unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream, 
         x, mean, stdv, out, rows, dim, out_ld, out_col);
     return after_launch("standardise_rows_kernel");
 }

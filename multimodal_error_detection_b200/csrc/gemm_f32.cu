@@ -30,6 +30,7 @@ gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float 
                 long long b_cs, long long ldc, const float *__restrict__ bias, int relu,
                 const float *__restrict__ mask, long long ld_mask, long long r_per_slab,
                 long long slab_stride) {
+    pdl_wait();
     constexpr int TB = 16 * TM;   // tile edge
     __shared__ __align__(16) float As[BK][TB + 4];
     __shared__ __align__(16) float Bs[BK][TB + 4];
@@ -120,6 +121,7 @@ gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ B, float 
 // out[e] (+)= sum_z part[z*stride + e], z ascending (fixed order).
 __global__ void slab_reduce_kernel(const float *__restrict__ part, float *__restrict__ out, long long n, int slabs,
                                    long long stride, int accumulate) {
+    pdl_wait();
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         float s = 0.0f;
         for (int z = 0; z < slabs; ++z) s += part[z * stride + e];
@@ -132,6 +134,7 @@ __global__ void slab_reduce_kernel(const float *__restrict__ part, float *__rest
 template <typename T>
 __global__ void colsum_partial_kernel(const T *__restrict__ x, float *__restrict__ part, long long M, int N,
                                       long long ld, long long rows_per_slab) {
+    pdl_wait();
     __shared__ float sh[8][33];
     const int col = blockIdx.x * 32 + (threadIdx.x & 31);
     const int lane_row = threadIdx.x >> 5;  // 8 row lanes
@@ -155,6 +158,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_vec_kernel(const T *__restrict__ x, float *__restrict__ part, long long M, int N, long long ld,
                           long long rows_per_slab) {
+    pdl_wait();
     constexpr int V = 16 / sizeof(T);
     __shared__ float sh[8][32 * V + 1];
     const int lane = threadIdx.x & 31, lane_row = threadIdx.x >> 5;
@@ -199,6 +203,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_flat_kernel(const T *__restrict__ x, float *__restrict__ part, long long M, int N, long long ld,
                            long long rows_per_slab) {
+    pdl_wait();
     constexpr int V = 16 / sizeof(T);
     __shared__ float sh[256][V + 1];
     const int lpr = N / V;                      // column groups (threads) per row
@@ -236,6 +241,7 @@ colsum_partial_flat_kernel(const T *__restrict__ x, float *__restrict__ part, lo
 // out[e] = sum_z part[z*n + e] in a fixed order: 8 strided partial sums per column (z = r, r+8, ...) added r = 0..7.
 __global__ void __launch_bounds__(256)
 slab_reduce8_kernel(const float *__restrict__ part, float *__restrict__ out, int n, int slabs) {
+    pdl_wait();
     __shared__ float sh[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
     float s = 0.0f;
@@ -252,10 +258,12 @@ slab_reduce8_kernel(const float *__restrict__ part, float *__restrict__ out, int
 }
 
 __global__ void cast_f32_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, long long n) {
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __float2bfloat16_rn(x[i]);
 }
 __global__ void relu_cast_f32_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ y, long long n) {
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __float2bfloat16_rn(fmaxf(x[i], 0.0f));
 }
@@ -265,6 +273,7 @@ __global__ void relu_cast_f32_bf16_kernel(const float *__restrict__ x, __nv_bflo
 // (reduction over columns); stack3 [3R, C]: the blocks one under the other (reduction over rows).  order 0 = left, 1 = right.
 __global__ void split_bf16x3_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ row3, __nv_bfloat16 *__restrict__ stack3,
                                     long long R, int C, int row_order, int stack_order, int relu) {
+    pdl_wait();
     const long long n = R * C;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float v = x[i];
@@ -283,6 +292,7 @@ __global__ void split_bf16x3_kernel(const float *__restrict__ x, __nv_bfloat16 *
     }
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, long long n) {
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = __bfloat162float(x[i]);
 }
@@ -325,11 +335,11 @@ static int launch_gemm(const float *A, const float *B, float *C, long long I, lo
     const long long ctas64 = ((J + BN - 1) / BN) * ((I + BM - 1) / BM) * slabs;
     if (ctas64 < num_sms()) {   // too few 64 x 64 tiles to fill the GPU: 32 x 32 tiles (4x the CTAs, identical results)
         dim3 grid((unsigned)((J + 31) / 32), (unsigned)((I + 31) / 32), (unsigned)slabs);
-        gemm_f32_kernel<2><<<grid, 256, 0, st>>>(A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, relu, mask, ld_mask,
+        launch_k(gemm_f32_kernel<2>, grid, 256, 0, st, A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, relu, mask, ld_mask,
                                                   per, slab_stride);
     } else {
         dim3 grid((unsigned)((J + BN - 1) / BN), (unsigned)((I + BM - 1) / BM), (unsigned)slabs);
-        gemm_f32_kernel<4><<<grid, 256, 0, st>>>(A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, relu, mask, ld_mask,
+        launch_k(gemm_f32_kernel<4>, grid, 256, 0, st, A, B, C, I, J, R, a_rs, a_cs, b_rs, b_cs, ldc, bias, relu, mask, ld_mask,
                                                   per, slab_stride);
     }
     return after_launch("gemm_f32_kernel");
@@ -366,7 +376,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_f32(const flo
     if (int e = launch_gemm(A, B, part, I, J, R, a_rs, a_cs, b_rs, b_cs, J, nullptr, flags & (kGemmReluA | kGemmReluB), nullptr, 0,
                             slabs, I * J, st)) return e;
     const long long n = I * J, blocks = (n + 255) / 256;
-    slab_reduce_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(part, C, n, slabs, n, (flags & kGemmAccum) ? 1 : 0);
+    launch_k(slab_reduce_kernel, (unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st, part, C, n, slabs, n, (flags & kGemmAccum) ? 1 : 0);
     return after_launch("slab_reduce_kernel");
 }
 
@@ -398,16 +408,16 @@ extern "C" __attribute__((visibility("default"))) int b200med_linear_bwd_weight_
         return e;
     const long long n = (long long)N * K;
     const long long blocks = (n + 255) / 256;
-    slab_reduce_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(part, dw, n, slabs, n, accumulate);
+    launch_k(slab_reduce_kernel, (unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st, part, dw, n, slabs, n, accumulate);
     if (int e = after_launch("slab_reduce_kernel")) return e;
     if (db) {
         float *cpart = part + (long long)slabs * n;
         const int cs = (int)colsum_slabs(M);
         const long long rows = (M + cs - 1) / cs;
         dim3 grid((unsigned)((N + 31) / 32), (unsigned)cs);
-        colsum_partial_kernel<float><<<grid, 256, 0, st>>>(dy, cpart, M, N, N, rows);
+        launch_k(colsum_partial_kernel<float>, grid, 256, 0, st, dy, cpart, M, N, N, rows);
         if (int e = after_launch("colsum_partial_kernel")) return e;
-        slab_reduce_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(cpart, db, N, cs, N, accumulate);
+        launch_k(slab_reduce_kernel, (unsigned)((N + 255) / 256), 256, 0, st, cpart, db, N, cs, N, accumulate);
         if (int e = after_launch("slab_reduce_kernel")) return e;
     }
     return B200MED_OK;
@@ -433,29 +443,29 @@ extern "C" __attribute__((visibility("default"))) int b200med_colsum(const void 
         const int slabs = (int)colsum_slabs_flat(M);
         const long long rps = (M + slabs - 1) / slabs;
         if (dtype == B200MED_F32)
-            colsum_partial_flat_kernel<float><<<slabs, 256, 0, st>>>(reinterpret_cast<const float *>(dy), cpart, M, N, ld, rps);
+            launch_k(colsum_partial_flat_kernel<float>, slabs, 256, 0, st, reinterpret_cast<const float *>(dy), cpart, M, N, ld, rps);
         else
-            colsum_partial_flat_kernel<__nv_bfloat16><<<slabs, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rps);
+            launch_k(colsum_partial_flat_kernel<__nv_bfloat16>, slabs, 256, 0, st, reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rps);
         if (int e = after_launch("colsum_partial_flat_kernel")) return e;
-        slab_reduce8_kernel<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(cpart, db, N, slabs);
+        launch_k(slab_reduce8_kernel, (unsigned)((N + 31) / 32), 256, 0, st, cpart, db, N, slabs);
         return after_launch("slab_reduce8_kernel");
     }
     if (N % V == 0 && ld % V == 0 && (uintptr_t)dy % 16 == 0) {
         dim3 grid((unsigned)((N + 32 * V - 1) / (32 * V)), (unsigned)cs);
         if (dtype == B200MED_F32)
-            colsum_partial_vec_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(dy), cpart, M, N, ld, rows);
+            launch_k(colsum_partial_vec_kernel<float>, grid, 256, 0, st, reinterpret_cast<const float *>(dy), cpart, M, N, ld, rows);
         else
-            colsum_partial_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rows);
+            launch_k(colsum_partial_vec_kernel<__nv_bfloat16>, grid, 256, 0, st, reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rows);
         if (int e = after_launch("colsum_partial_vec_kernel")) return e;
     } else {
         dim3 grid((unsigned)((N + 31) / 32), (unsigned)cs);
         if (dtype == B200MED_F32)
-            colsum_partial_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float *>(dy), cpart, M, N, ld, rows);
+            launch_k(colsum_partial_kernel<float>, grid, 256, 0, st, reinterpret_cast<const float *>(dy), cpart, M, N, ld, rows);
         else
-            colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rows);
+            launch_k(colsum_partial_kernel<__nv_bfloat16>, grid, 256, 0, st, reinterpret_cast<const __nv_bfloat16 *>(dy), cpart, M, N, ld, rows);
         if (int e = after_launch("colsum_partial_kernel")) return e;
     }
-    slab_reduce8_kernel<<<(unsigned)((N + 31) / 32), 256, 0, st>>>(cpart, db, N, cs);
+    launch_k(slab_reduce8_kernel, (unsigned)((N + 31) / 32), 256, 0, st, cpart, db, N, cs);
     return after_launch("slab_reduce8_kernel");
 }
 
@@ -463,7 +473,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_cast_f32_to_bf16(c
     if (n <= 0) return B200MED_OK;
     B200MED_REQUIRE(x && y, "null pointer");
     const long long blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
-    cast_f32_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(cast_f32_bf16_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
         x, reinterpret_cast<__nv_bfloat16 *>(y), n);
     return after_launch("cast_f32_bf16_kernel");
 }
@@ -471,7 +481,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_relu_cast_f32_to_b
     if (n <= 0) return B200MED_OK;
     B200MED_REQUIRE(x && y, "null pointer");
     const long long blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
-    relu_cast_f32_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(relu_cast_f32_bf16_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
         x, reinterpret_cast<__nv_bfloat16 *>(y), n);
     return after_launch("relu_cast_f32_bf16_kernel");
 }
@@ -482,7 +492,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_split_bf16x3(const
     B200MED_REQUIRE(x && (row3 || stack3), "null pointer");
     B200MED_REQUIRE((row_order == 0 || row_order == 1) && (stack_order == 0 || stack_order == 1), "order: 0 = left operand, 1 = right operand");
     const long long n = R * (long long)C, blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
-    split_bf16x3_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(split_bf16x3_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
         x, reinterpret_cast<__nv_bfloat16 *>(row3), reinterpret_cast<__nv_bfloat16 *>(stack3), R, C, row_order, stack_order, relu);
     return after_launch("split_bf16x3_kernel");
 }
@@ -490,7 +500,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_cast_bf16_to_f32(c
     if (n <= 0) return B200MED_OK;
     B200MED_REQUIRE(x && y, "null pointer");
     const long long blocks = (n + 255) / 256, cap = (long long)num_sms() * 16;
-    cast_bf16_f32_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(cast_bf16_f32_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
         reinterpret_cast<const __nv_bfloat16 *>(x), y, n);
     return after_launch("cast_bf16_f32_kernel");
 }

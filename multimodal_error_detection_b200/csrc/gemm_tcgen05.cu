@@ -47,14 +47,20 @@ struct GemmParams {
 };
 
 // kStage: the epilogue stages the bf16 output tile in shared memory (and fetches the ReLU-mask tile into the same buffer)
-template <int BLOCK_N, bool kPair = false, bool kStage = false>
+// kDouble (staged, single CTA, short K loops): TWO staging buffers and a 2-deep operand ring.  With one buffer a tile's mask
+// load could only start after the previous tile's TMA store had read the buffer, so load latency + store read sat between
+// the drains of consecutive tiles: the ReLU-masked data gradients (K = 32 / 256: one to four k-blocks per 128 x 256 tile) ran
+// at 6.8 us per tile against 4.4 us of HBM time.  Now the mask of tile i+1 lands while tile i drains.
+template <int BLOCK_N, bool kPair = false, bool kStage = false, bool kDouble = false>
 struct GemmCfg {
+    static_assert(!kDouble || (kStage && !kPair), "double staging: staged single-CTA kernel only");
     // CTA pair: each CTA stages its own 128 rows of A and HALF of the B tile's rows
     static constexpr int kBRows = kPair ? BLOCK_N / 2 : BLOCK_N;
     static constexpr uint32_t kBTileBytes = kBRows * BLOCK_K * 2;
     static constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
-    static constexpr uint32_t kStagingBytes = kStage ? BLOCK_M * BLOCK_N * 2 : 0;     // 64-column boxes of [128 rows][128 B]
-    static constexpr int kStages = kStage ? (kPair ? 5 : ((BLOCK_N >= 256) ? 3 : 5))
+    static constexpr uint32_t kStagingOne = kStage ? BLOCK_M * BLOCK_N * 2 : 0;       // 64-column boxes of [128 rows][128 B]
+    static constexpr uint32_t kStagingBytes = (kDouble ? 2 : 1) * kStagingOne;
+    static constexpr int kStages = kDouble ? 2 : kStage ? (kPair ? 5 : ((BLOCK_N >= 256) ? 3 : 5))
                                           : (kPair ? 6 : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8)));
     static constexpr int kAccStages = 2;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two: BLOCK_N in {32,64,128,256}
@@ -74,12 +80,13 @@ constexpr int kEpiRowMajor = 0, kEpiRbi = 1, kEpiPartial = 2, kEpiTmaBf16 = 3;
 // CTA r stages rows [128 r, 128 r + 128) of the A tile and rows [BLOCK_N/2 r, +BLOCK_N/2) of the B tile, so every byte of B
 // is fetched from L2 once per 256 output rows instead of once per 128 -- the 1-CTA kernel needs 96 B/cycle/SM of L2 -> SMEM
 // traffic at full MMA rate, the pair 64 B/cycle/SM.
-template <int BLOCK_N, int EPI, bool kPair>
+template <int BLOCK_N, int EPI, bool kPair, bool kDouble = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_mask,
                          const GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N, kPair, EPI == kEpiTmaBf16>;
+    pdl_wait();
+    using Cfg = GemmCfg<BLOCK_N, kPair, EPI == kEpiTmaBf16, kDouble>;
     constexpr int kTileM = kPair ? 2 * BLOCK_M : BLOCK_M;
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
@@ -93,8 +100,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint64_t *empty_bar = full_bar + Cfg::kStages;
     uint64_t *acc_full = empty_bar + Cfg::kStages;
     uint64_t *acc_empty = acc_full + Cfg::kAccStages;
-    uint64_t *mask_bar = acc_empty + Cfg::kAccStages;        // TMA-store epilogue: "the mask tile is in the staging buffer"
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mask_bar + 1);
+    uint64_t *mask_bar = acc_empty + Cfg::kAccStages;        // [2] TMA-store epilogue: "the mask tile is in staging buffer b"
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mask_bar + 2);
     float *bias_sm = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(full_bar) + 256);   // [256]: bias of the tile's columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,7 +116,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // collects the 8 epilogue warps of both CTAs
         for (int s = 0; s < Cfg::kStages; ++s) { bar_init(&full_bar[s], kPair ? 2 : 1); bar_init(&empty_bar[s], 1); }
         for (int s = 0; s < Cfg::kAccStages; ++s) { bar_init(&acc_full[s], 1); bar_init(&acc_empty[s], kPair ? 16 : 8); }
-        bar_init(mask_bar, 1);
+        bar_init(&mask_bar[0], 1); bar_init(&mask_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -240,15 +247,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         constexpr int kBoxes = BLOCK_N / 64;                      // TMA boxes of 64 columns x 128 rows per tile
         const bool elect = warp == 2 && lane == 0;                // issues the TMA stores / mask loads of this CTA
         const bool use_mask = staged && p.mask != nullptr;
-        uint32_t mask_phase = 0;
-        auto load_mask_tile = [&](long long t) {
+        uint32_t mask_phase = 0;                                  // kDouble: bit b = phase of buffer b's barrier
+        unsigned char *const staging0 = staging;
+        int sbuf = 0;                                             // kDouble: buffer of the current tile
+        auto load_mask_tile = [&](long long t, int b) {
             const long long mn_ = t % tiles_mn;
             const int m_ = (int)(mn_ / p.tiles_n) * kTileM + (int)rank * BLOCK_M, n_ = (int)(mn_ % p.tiles_n) * BLOCK_N;
-            bar_expect_tx(mask_bar, Cfg::kStagingBytes);
+            unsigned char *dst = staging0 + (size_t)b * Cfg::kStagingOne;
+            bar_expect_tx(&mask_bar[b], Cfg::kStagingOne);
 #pragma unroll
-            for (int bx = 0; bx < kBoxes; ++bx) tma_load_2d(staging + bx * 16384, &tmap_mask, mask_bar, n_ + 64 * bx, m_);
+            for (int bx = 0; bx < kBoxes; ++bx) tma_load_2d(dst + bx * 16384, &tmap_mask, &mask_bar[b], n_ + 64 * bx, m_);
         };
-        if (use_mask && elect && cta_id < total_tiles) load_mask_tile(cta_id);
+        if (use_mask && elect && cta_id < total_tiles) load_mask_tile(cta_id, 0);
         // N <= 512 (every GEMM of the train step that has a bias): the whole bias vector is loaded once per CTA
         const bool bias_all = !partial_k && p.bias && p.N <= Cfg::kBiasFloats;
         if (bias_all) {
@@ -270,9 +280,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const float *bias_tile = bias_all ? bias_sm + n0 : bias_sm;
             bar_wait(&acc_full[acc], acc_phase);
             tcgen05_fence_after();
-            if constexpr (staged) {
+            if constexpr (staged && kDouble) {
+                staging = staging0 + (size_t)sbuf * Cfg::kStagingOne;
                 if (use_mask) {
-                    bar_wait(mask_bar, mask_phase);               // the mask tile has landed (and the previous store has been read)
+                    if (elect && tile + cta_stride < total_tiles) {
+                        bulk_wait_read<0>();                      // the previous tile's store has read the OTHER buffer ...
+                        load_mask_tile(tile + cta_stride, sbuf ^ 1);      // ... so the next tile's mask lands there under this drain
+                    }
+                    bar_wait(&mask_bar[sbuf], (mask_phase >> sbuf) & 1u);
+                    mask_phase ^= 1u << sbuf;
+                } else {
+                    if (elect) bulk_wait_read<1>();               // the store of two tiles ago has read this buffer
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+            } else if constexpr (staged) {
+                if (use_mask) {
+                    bar_wait(&mask_bar[0], mask_phase);           // the mask tile has landed (and the previous store has been read)
                     mask_phase ^= 1;
                 } else {
                     if (elect) bulk_wait_read<0>();               // the previous tile's TMA store has finished reading the buffer
@@ -425,11 +448,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     for (int bx = 0; bx < kBoxes; ++bx)
                         if (n0 + 64 * bx < p.N) tma_store_2d(&tmap_d, staging + bx * 16384, (int)n0 + 64 * bx, (int)m0);
                     bulk_commit();
-                    if (use_mask && tile + cta_stride < total_tiles) {
+                    if (!kDouble && use_mask && tile + cta_stride < total_tiles) {
                         bulk_wait_read<0>();                      // the store has read the buffer: the next mask tile may land
-                        load_mask_tile(tile + cta_stride);
+                        load_mask_tile(tile + cta_stride, 0);
                     }
                 }
+                if constexpr (kDouble) sbuf ^= 1;
             }
         }
         if constexpr (staged) {
@@ -453,6 +477,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 __global__ void splitk_reduce_kernel(const float *__restrict__ part, int split, long long M, long long N, long long ldd,
                                      const float *__restrict__ bias, int relu, const __nv_bfloat16 *__restrict__ mask,
                                      void *__restrict__ D, int out_f32) {
+    pdl_wait();
     const long long total = M * N;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long m = e / N, n = e - m * N;
@@ -466,6 +491,11 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ part, int split, 
     }
 }
 
+// Widths the 256-column CTA-pair tile takes: whole tiles, or a last tile at least three quarters full (N = 192: the LSTM
+// layer-0 weight gradient dG^T [x | h] with 58 -> 64 + 128 columns; TMA zero-fills the missing rows of the B tile, the
+// epilogues mask columns >= N) -- the 128-column single-CTA kernel ran that product at 77 us against 50 us for N = 256.
+static bool pair_n_ok(long long N) { return N % 64 == 0 && (N % 256 == 0 || N % 256 >= 192); }
+
 static int pick_block_n(long long N, int b_kmajor) {
     if (N >= 256) return 256;
     if (N > 64) return 128;
@@ -473,11 +503,11 @@ static int pick_block_n(long long N, int b_kmajor) {
     return 32;
 }
 
-template <int BLOCK_N, int EPI, bool kPair = false>
+template <int BLOCK_N, int EPI, bool kPair = false, bool kDouble = false>
 static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &td, const CUtensorMap &tm,
                           const GemmParams &p, cudaStream_t st) {
-    using Cfg = GemmCfg<BLOCK_N, kPair, EPI == kEpiTmaBf16>;
-    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI, kPair>;
+    using Cfg = GemmCfg<BLOCK_N, kPair, EPI == kEpiTmaBf16, kDouble>;
+    auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, EPI, kPair, kDouble>;
     static bool attr_set = false;
     if (!attr_set) {
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes),
@@ -492,15 +522,15 @@ static int launch_gemm_tc(const CUtensorMap &ta, const CUtensorMap &tb, const CU
         cfg.blockDim = dim3(kGemmThreads);
         cfg.dynamicSmemBytes = Cfg::kSmemBytes;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;      // (the cluster scheduling policy makes no difference here, measured)
+        cfg.attrs = attr; cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1);      // (the cluster scheduling policy makes no difference here, measured)
         if (int e = check_cuda(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tm, p), "cudaLaunchKernelEx(gemm_bf16_tcgen05 pair)")) return e;
         return after_launch("gemm_bf16_tcgen05_kernel(pair)");
     } else {
         const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-        kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, td, tm, p);
+        launch_k(kern, grid, kGemmThreads, Cfg::kSmemBytes, st, ta, tb, td, tm, p);
         return after_launch("gemm_bf16_tcgen05_kernel");
     }
 }
@@ -529,16 +559,17 @@ static bool gemm_pair_allowed() {
 extern "C" __attribute__((visibility("default"))) int32_t b200med_gemm_bf16_pick_split(int64_t M, int64_t N, int64_t K,
                                                                                        int32_t b_kmajor) {
     if (M < 1 || N < 1 || K < 1) return 1;
-    const int block_n = pick_block_n(N, b_kmajor);
+    int block_n = pick_block_n(N, b_kmajor);
     const int nkb = (int)((K + BLOCK_K - 1) / BLOCK_K);
     if (nkb < 16) return 1;
+    if (N == 192 && M >= 256 && gemm_pair_allowed()) block_n = 256;      // three quarters of a pair tile (see pair_n_ok)
     const int sms = num_sms();
     double best = 1e300;
     int best_s = 1;
     for (int s = 1; s <= 160 && nkb / s >= 8; ++s) {
         const int kb_per = (nkb + s - 1) / s;
         if ((nkb + kb_per - 1) / kb_per != s) continue;
-        const bool pair = gemm_pair_allowed() && block_n == 256 && M >= 256 && N % 256 == 0 && nkb / s >= 8;
+        const bool pair = gemm_pair_allowed() && block_n == 256 && M >= 256 && pair_n_ok(N) && nkb / s >= 8;
         const long long tiles = pair ? ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((N + 255) / 256)
                                      : ((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
         const long long units = pair ? sms / 2 : sms;
@@ -572,18 +603,19 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
     if (!b200med_has_tcgen05()) { set_error("tcgen05 path needs a compute-capability 10.x device"); return B200MED_E_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
 
-    const int block_n = pick_block_n(N, b_kmajor);
+    int block_n = pick_block_n(N, b_kmajor);
     const int nkb = (int)((K + BLOCK_K - 1) / BLOCK_K);
     if (split_k < 1) split_k = 1;
     if (split_k > nkb) split_k = nkb;
     int kb_per = (nkb + split_k - 1) / split_k;
     split_k = (nkb + kb_per - 1) / kb_per;
+    if (N == 192 && M >= 256 && gemm_pair_allowed() && nkb / split_k >= 8) block_n = 256;    // three quarters of a pair tile
     B200MED_REQUIRE(split_k == 1 || workspace, "split_k > 1 needs a workspace");
 
     // CTA-pair mode (cta_group::2, 256 x 256 tiles): the wide GEMMs whose K loop is long enough to be bound by the
     // L2 -> shared-memory operand traffic of the 1-CTA kernel (FE layer 1 forward 231 -> 210 us, weight gradient 260 -> 238 us,
     // measured A/B on one box).  B200MED_GEMM_PAIR=0 switches it off.
-    const bool pair = gemm_pair_allowed() && block_n == 256 && M >= 256 && N % 256 == 0 && nkb / split_k >= 8;
+    const bool pair = gemm_pair_allowed() && block_n == 256 && M >= 256 && pair_n_ok(N) && nkb / split_k >= 8;
 
     CUtensorMap ta, tb;
     // K-major operand: rows x K, K contiguous -> box {64 k, rows}.  MN-major: K x rows -> box {64 rows, 64 k}.
@@ -622,7 +654,9 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
     if (pair) {
         e = epi == kEpiTmaBf16 ? launch_gemm_tc<256, kEpiTmaBf16, true>(ta, tb, td, tm, p, st) : B200MED_GEMM_EPI(256, true);
     } else if (block_n == 256) {
-        e = epi == kEpiTmaBf16 ? launch_gemm_tc<256, kEpiTmaBf16, false>(ta, tb, td, tm, p, st) : B200MED_GEMM_EPI(256, false);
+        static const bool dbl_allowed = []() { const char *v = getenv("B200MED_GEMM_DOUBLE_STAGING"); return !(v && v[0] == '0'); }();
+        if (epi == kEpiTmaBf16 && kb_per <= 4 && dbl_allowed) e = launch_gemm_tc<256, kEpiTmaBf16, false, true>(ta, tb, td, tm, p, st);
+        else e = epi == kEpiTmaBf16 ? launch_gemm_tc<256, kEpiTmaBf16, false>(ta, tb, td, tm, p, st) : B200MED_GEMM_EPI(256, false);
     } else if (block_n == 128) {
         e = epi == kEpiTmaBf16 ? launch_gemm_tc<128, kEpiTmaBf16, false>(ta, tb, td, tm, p, st) : B200MED_GEMM_EPI(128, false);
     } else if (block_n == 64) {
@@ -635,7 +669,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_gemm_bf16(const vo
     if (split_k > 1) {
         const long long total = M * N;
         const long long want = (total + 255) / 256, cap = (long long)num_sms() * 8;
-        splitk_reduce_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(
+        launch_k(splitk_reduce_kernel, (unsigned)(want < cap ? want : cap), 256, 0, st, 
             reinterpret_cast<const float *>(workspace), split_k, M, N, ldd, bias, relu,
             reinterpret_cast<const __nv_bfloat16 *>(mask), D, out_dtype == B200MED_F32);
         return after_launch("splitk_reduce_kernel");

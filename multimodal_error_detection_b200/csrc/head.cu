@@ -46,6 +46,7 @@ template <> struct BnVec<1> {
 template <int V>
 __global__ void __launch_bounds__(kBnCols * kBnWarps)
 bn_stats_partial_kernel(const float *__restrict__ x, long long M, int C, long long rows_per_slab, float *__restrict__ part) {
+    pdl_wait();
     __shared__ double sh[kBnWarps][kBnCols * V];
     __shared__ float sh_mean[kBnCols * V];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -122,6 +123,7 @@ bn_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, co
                    const float *__restrict__ beta, float eps, float momentum, float *__restrict__ scale_shift,
                    float *__restrict__ save_mean, float *__restrict__ save_rstd, float *__restrict__ running_mean,
                    float *__restrict__ running_var, long long *__restrict__ num_batches) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (col == 0 && lane == 0 && num_batches) *num_batches += 1;
@@ -162,6 +164,7 @@ bn_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, co
 template <int V>
 __global__ void bn_apply_kernel(const float *__restrict__ x, long long M, int C, const float *__restrict__ scale_shift,
                                 float *__restrict__ y) {
+    pdl_wait();
     const long long total = M * C / V;
     const int cv = C / V;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -178,6 +181,7 @@ __global__ void bn_apply_kernel(const float *__restrict__ x, long long M, int C,
 __global__ void bn_eval_kernel(const float *__restrict__ x, long long M, int C, const float *__restrict__ rm,
                                const float *__restrict__ rv, const float *__restrict__ gamma, const float *__restrict__ beta,
                                float eps, float *__restrict__ y) {
+    pdl_wait();
     const long long total = M * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(e % C);
@@ -192,6 +196,7 @@ template <int V>
 __global__ void __launch_bounds__(kBnCols * kBnWarps)
 bn_bwd_partial_kernel(const float *__restrict__ dy, const float *__restrict__ x, long long M, int C, long long rows_per_slab,
                       const float *__restrict__ save_mean, const float *__restrict__ save_rstd, float *__restrict__ part) {
+    pdl_wait();
     __shared__ float sh[2][kBnWarps][kBnCols * V];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int col = (blockIdx.x * kBnCols + lane) * V;
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const float *__restrict__ part, int S, long long M, int C, const float *__restrict__ gamma,
                        const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
                        float *__restrict__ coef, float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (col >= C) return;
@@ -254,6 +260,7 @@ bn_bwd_finalize_kernel(const float *__restrict__ part, int S, long long M, int C
 template <int V>
 __global__ void bn_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x, long long M, int C,
                                     const float *__restrict__ coef, int relu_mask, float *__restrict__ dx) {
+    pdl_wait();
     const long long total = M * C / V;
     const int cv = C / V;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -275,6 +282,7 @@ __global__ void bn_bwd_apply_kernel(const float *__restrict__ dy, const float *_
 // p [B*Lp, C], Lp = Lc / 2.
 __global__ void pool_drop_fwd_kernel(const float *__restrict__ z, float *__restrict__ p, long long B, int L, int Lp, int C,
                                      float drop_p, const uint32_t *__restrict__ seed_dev, unsigned long long drop_base) {
+    pdl_wait();
     const uint32_t seed = seed_dev ? *seed_dev : 0u;
     const long long total = B * (long long)Lp * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -295,6 +303,7 @@ __global__ void pool_drop_fwd_kernel(const float *__restrict__ z, float *__restr
 __global__ void pool_drop_bwd_kernel(const float *__restrict__ dp, const float *__restrict__ z, float *__restrict__ dz,
                                      long long B, int L, int Lp, int C, float drop_p, const uint32_t *__restrict__ seed_dev,
                                      unsigned long long drop_base) {
+    pdl_wait();
     const uint32_t seed = seed_dev ? *seed_dev : 0u;
     const long long total = (B * (long long)L + 2) * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -322,6 +331,7 @@ __global__ void pool_drop_bwd_kernel(const float *__restrict__ dp, const float *
 // w [Cout, Cin, 3] -> fwd [Cout, 3*Cin] (fwd[co, k*Cin + ci] = w[co, ci, k]) and bwd [Cin, 3*Cout]
 // (bwd[ci, k*Cout + co] = w[co, ci, 2-k]); either destination may be null.
 __global__ void conv_pack_kernel(const float *__restrict__ w, float *__restrict__ fwd, float *__restrict__ bwd, int Cout, int Cin) {
+    pdl_wait();
     const int total = Cout * Cin * 3;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int k = e % 3, ci = (e / 3) % Cin, co = e / (3 * Cin);
@@ -332,6 +342,7 @@ __global__ void conv_pack_kernel(const float *__restrict__ w, float *__restrict_
 }
 // gradient of the packed forward weight [Cout, 3*Cin] -> dw [Cout, Cin, 3]
 __global__ void conv_unpack_grad_kernel(const float *__restrict__ dfwd, float *__restrict__ dw, int Cout, int Cin) {
+    pdl_wait();
     const int total = Cout * Cin * 3;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int k = e % 3, ci = (e / 3) % Cin, co = e / (3 * Cin);
@@ -341,6 +352,7 @@ __global__ void conv_unpack_grad_kernel(const float *__restrict__ dfwd, float *_
 
 // y [B, C, R] <- x [B, R, C] (the reference's nn.Flatten runs over [B, C, L]; the native conv stack is time-major)
 __global__ void transpose_last2_kernel(const float *__restrict__ x, float *__restrict__ y, long long B, int R, int C) {
+    pdl_wait();
     const long long total = B * (long long)R * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(e % R);
@@ -354,6 +366,7 @@ __global__ void transpose_last2_kernel(const float *__restrict__ x, float *__res
 // out [M, Ca + Cb] = [a [M, Ca] | b [M, Cb]] -- torch.cat((features, kinematics), dim=2) of define_inputs (modeling_utils.py:41-47)
 __global__ void concat2_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out, long long M,
                                int Ca, int Cb) {
+    pdl_wait();
     const int C = Ca + Cb;
     const long long total = M * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -364,6 +377,7 @@ __global__ void concat2_kernel(const float *__restrict__ a, const float *__restr
 }
 // da [M, Ca] = dout [M, ld] columns [col0, col0 + Ca)
 __global__ void slice_cols_kernel(const float *__restrict__ dout, float *__restrict__ da, long long M, int ld, int col0, int Ca) {
+    pdl_wait();
     const long long total = M * Ca;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long m = e / Ca;
@@ -373,6 +387,7 @@ __global__ void slice_cols_kernel(const float *__restrict__ dout, float *__restr
 // out [n, C] = src [idx[i], :] for 4-byte elements (window-index -> start row / label lookups of a batch)
 __global__ void take_rows_kernel(const uint32_t *__restrict__ src, const long long *__restrict__ idx, uint32_t *__restrict__ out,
                                  long long n, int C) {
+    pdl_wait();
     const long long total = n * C;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long i = e / C;
@@ -404,7 +419,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_bn_fwd(const float
     cudaStream_t st = (cudaStream_t)stream;
     if (!training) {
         B200MED_REQUIRE(running_mean && running_var, "inference needs the running statistics");
-        bn_eval_kernel<<<ew_grid(M * C), 256, 0, st>>>(x, M, C, running_mean, running_var, gamma, beta, eps, y);
+        launch_k(bn_eval_kernel, ew_grid(M * C), 256, 0, st, x, M, C, running_mean, running_var, gamma, beta, eps, y);
         return after_launch("bn_eval_kernel");
     }
     B200MED_REQUIRE(save_mean && save_rstd && workspace, "training needs save_mean, save_rstd and a workspace");
@@ -415,14 +430,14 @@ extern "C" __attribute__((visibility("default"))) int b200med_bn_fwd(const float
     const bool vec = C % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
     const int V = vec ? 4 : 1;
     dim3 grid((unsigned)((C + kBnCols * V - 1) / (kBnCols * V)), (unsigned)S);
-    if (vec) bn_stats_partial_kernel<4><<<grid, kBnCols * kBnWarps, 0, st>>>(x, M, C, rows, part);
-    else bn_stats_partial_kernel<1><<<grid, kBnCols * kBnWarps, 0, st>>>(x, M, C, rows, part);
+    if (vec) launch_k(bn_stats_partial_kernel<4>, grid, kBnCols * kBnWarps, 0, st, x, M, C, rows, part);
+    else launch_k(bn_stats_partial_kernel<1>, grid, kBnCols * kBnWarps, 0, st, x, M, C, rows, part);
     if (int e = after_launch("bn_stats_partial_kernel")) return e;
-    bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, S, M, C, gamma, beta, eps, momentum, scale_shift, save_mean, save_rstd,
+    launch_k(bn_finalize_kernel, (C + 7) / 8, 256, 0, st, part, S, M, C, gamma, beta, eps, momentum, scale_shift, save_mean, save_rstd,
                                                       running_mean, running_var, (long long *)num_batches_tracked);
     if (int e = after_launch("bn_finalize_kernel")) return e;
-    if (vec) bn_apply_kernel<4><<<ew_grid(M * C / 4), 256, 0, st>>>(x, M, C, scale_shift, y);
-    else bn_apply_kernel<1><<<ew_grid(M * C), 256, 0, st>>>(x, M, C, scale_shift, y);
+    if (vec) launch_k(bn_apply_kernel<4>, ew_grid(M * C / 4), 256, 0, st, x, M, C, scale_shift, y);
+    else launch_k(bn_apply_kernel<1>, ew_grid(M * C), 256, 0, st, x, M, C, scale_shift, y);
     return after_launch("bn_apply_kernel");
 }
 
@@ -439,13 +454,13 @@ extern "C" __attribute__((visibility("default"))) int b200med_bn_bwd(const float
     const bool vec = C % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0);
     const int V = vec ? 4 : 1;
     dim3 grid((unsigned)((C + kBnCols * V - 1) / (kBnCols * V)), (unsigned)S);
-    if (vec) bn_bwd_partial_kernel<4><<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, save_mean, save_rstd, part);
-    else bn_bwd_partial_kernel<1><<<grid, kBnCols * kBnWarps, 0, st>>>(dy, x, M, C, rows, save_mean, save_rstd, part);
+    if (vec) launch_k(bn_bwd_partial_kernel<4>, grid, kBnCols * kBnWarps, 0, st, dy, x, M, C, rows, save_mean, save_rstd, part);
+    else launch_k(bn_bwd_partial_kernel<1>, grid, kBnCols * kBnWarps, 0, st, dy, x, M, C, rows, save_mean, save_rstd, part);
     if (int e = after_launch("bn_bwd_partial_kernel")) return e;
-    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, S, M, C, gamma, save_mean, save_rstd, coef, dgamma, dbeta);
+    launch_k(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, st, part, S, M, C, gamma, save_mean, save_rstd, coef, dgamma, dbeta);
     if (int e = after_launch("bn_bwd_finalize_kernel")) return e;
-    if (vec) bn_bwd_apply_kernel<4><<<ew_grid(M * C / 4), 256, 0, st>>>(dy, x, M, C, coef, relu_mask, dx);
-    else bn_bwd_apply_kernel<1><<<ew_grid(M * C), 256, 0, st>>>(dy, x, M, C, coef, relu_mask, dx);
+    if (vec) launch_k(bn_bwd_apply_kernel<4>, ew_grid(M * C / 4), 256, 0, st, dy, x, M, C, coef, relu_mask, dx);
+    else launch_k(bn_bwd_apply_kernel<1>, ew_grid(M * C), 256, 0, st, dy, x, M, C, coef, relu_mask, dx);
     return after_launch("bn_bwd_apply_kernel");
 }
 
@@ -454,7 +469,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_pool_drop_fwd(cons
     B200MED_REQUIRE(B >= 1 && L >= 2 && Lc >= 2 && Lc <= L && C >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
     B200MED_REQUIRE(z && p, "null pointer");
     const int Lp = Lc / 2;
-    pool_drop_fwd_kernel<<<ew_grid(B * (long long)Lp * C), 256, 0, (cudaStream_t)stream>>>(z, p, B, L, Lp, C, drop_p, seed, drop_base);
+    launch_k(pool_drop_fwd_kernel, ew_grid(B * (long long)Lp * C), 256, 0, (cudaStream_t)stream, z, p, B, L, Lp, C, drop_p, seed, drop_base);
     return after_launch("pool_drop_fwd_kernel");
 }
 
@@ -462,20 +477,20 @@ extern "C" __attribute__((visibility("default"))) int b200med_pool_drop_bwd(cons
                                       int32_t Lc, int32_t C, float drop_p, const uint32_t *seed, uint64_t drop_base, void *stream) {
     B200MED_REQUIRE(B >= 1 && L >= 2 && Lc >= 2 && Lc <= L && C >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
     B200MED_REQUIRE(dp && z && dz, "null pointer");
-    pool_drop_bwd_kernel<<<ew_grid((B * (long long)L + 2) * C), 256, 0, (cudaStream_t)stream>>>(dp, z, dz, B, L, Lc / 2, C, drop_p, seed,
+    launch_k(pool_drop_bwd_kernel, ew_grid((B * (long long)L + 2) * C), 256, 0, (cudaStream_t)stream, dp, z, dz, B, L, Lc / 2, C, drop_p, seed,
                                                                                           drop_base);
     return after_launch("pool_drop_bwd_kernel");
 }
 
 extern "C" __attribute__((visibility("default"))) int b200med_conv_pack(const float *w, float *fwd, float *bwd, int32_t Cout, int32_t Cin, void *stream) {
     B200MED_REQUIRE(Cout >= 1 && Cin >= 1 && w && (fwd || bwd), "bad argument");
-    conv_pack_kernel<<<ew_grid((long long)Cout * Cin * 3), 256, 0, (cudaStream_t)stream>>>(w, fwd, bwd, Cout, Cin);
+    launch_k(conv_pack_kernel, ew_grid((long long)Cout * Cin * 3), 256, 0, (cudaStream_t)stream, w, fwd, bwd, Cout, Cin);
     return after_launch("conv_pack_kernel");
 }
 
 extern "C" __attribute__((visibility("default"))) int b200med_conv_unpack_grad(const float *dfwd, float *dw, int32_t Cout, int32_t Cin, void *stream) {
     B200MED_REQUIRE(Cout >= 1 && Cin >= 1 && dfwd && dw, "bad argument");
-    conv_unpack_grad_kernel<<<ew_grid((long long)Cout * Cin * 3), 256, 0, (cudaStream_t)stream>>>(dfwd, dw, Cout, Cin);
+    launch_k(conv_unpack_grad_kernel, ew_grid((long long)Cout * Cin * 3), 256, 0, (cudaStream_t)stream, dfwd, dw, Cout, Cin);
     return after_launch("conv_unpack_grad_kernel");
 }
 
@@ -483,7 +498,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_transpose_last2(co
     B200MED_REQUIRE(B >= 0 && R >= 1 && C >= 1, "bad shape");
     if (B == 0) return B200MED_OK;
     B200MED_REQUIRE(x && y, "null pointer");
-    transpose_last2_kernel<<<ew_grid(B * (long long)R * C), 256, 0, (cudaStream_t)stream>>>(x, y, B, R, C);
+    launch_k(transpose_last2_kernel, ew_grid(B * (long long)R * C), 256, 0, (cudaStream_t)stream, x, y, B, R, C);
     return after_launch("transpose_last2_kernel");
 }
 
@@ -492,7 +507,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_concat2(const floa
     B200MED_REQUIRE(M >= 0 && Ca >= 1 && Cb >= 1, "bad shape");
     if (M == 0) return B200MED_OK;
     B200MED_REQUIRE(a && b && out, "null pointer");
-    concat2_kernel<<<ew_grid(M * (Ca + Cb)), 256, 0, (cudaStream_t)stream>>>(a, b, out, M, Ca, Cb);
+    launch_k(concat2_kernel, ew_grid(M * (Ca + Cb)), 256, 0, (cudaStream_t)stream, a, b, out, M, Ca, Cb);
     return after_launch("concat2_kernel");
 }
 
@@ -501,7 +516,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_slice_cols(const f
     B200MED_REQUIRE(M >= 0 && C >= 1 && col0 >= 0 && col0 + C <= ld, "bad shape");
     if (M == 0) return B200MED_OK;
     B200MED_REQUIRE(x && out, "null pointer");
-    slice_cols_kernel<<<ew_grid(M * C), 256, 0, (cudaStream_t)stream>>>(x, out, M, ld, col0, C);
+    launch_k(slice_cols_kernel, ew_grid(M * C), 256, 0, (cudaStream_t)stream, x, out, M, ld, col0, C);
     return after_launch("slice_cols_kernel");
 }
 
@@ -510,7 +525,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_take_rows(const vo
     B200MED_REQUIRE(n >= 0 && C >= 1, "bad shape");
     if (n == 0) return B200MED_OK;
     B200MED_REQUIRE(src && idx && out, "null pointer");
-    take_rows_kernel<<<ew_grid(n * C), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(src),
+    launch_k(take_rows_kernel, ew_grid(n * C), 256, 0, (cudaStream_t)stream, reinterpret_cast<const uint32_t *>(src),
                                                                         reinterpret_cast<const long long *>(idx),
                                                                         reinterpret_cast<uint32_t *>(out), n, C);
     return after_launch("take_rows_kernel");

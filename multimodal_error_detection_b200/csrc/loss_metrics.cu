@@ -52,6 +52,7 @@ bce_logits_kernel(const float *__restrict__ logits, const float *__restrict__ la
                   float grad_scale, float *__restrict__ loss, float *__restrict__ dlogits, float *__restrict__ probs,
                   float *__restrict__ preds, long long *__restrict__ counts, int accumulate,
                   unsigned int *ticket, double *partials) {
+    pdl_wait();
     __shared__ double sh[32];
     double l_sum = 0.0, c[4] = {0.0, 0.0, 0.0, 0.0};
     const float inv_b = grad_scale / (float)B;
@@ -92,6 +93,7 @@ ce_logits_kernel(const float *__restrict__ logits, const int32_t *__restrict__ t
                  float *__restrict__ dlogits, float *__restrict__ probs, int32_t *__restrict__ preds, int pred_shift,
                  int pred_mask_mode, long long *__restrict__ cm, int cm_classes, int accumulate,
                  unsigned int *ticket, double *partials) {
+    pdl_wait();
     __shared__ double sh[32];
     __shared__ double denom_sh;
     __shared__ unsigned int cm_sh[kCmSlots];
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(kLossThreads)
 ce_frame_kernel(const float *__restrict__ logits, const float *__restrict__ e, int stages, long long T,
                 float grad_scale, float *__restrict__ loss, float *__restrict__ dlogits, float *__restrict__ preds,
                 long long *__restrict__ counts, int accumulate, unsigned int *ticket, double *partials) {
+    pdl_wait();
     __shared__ double sh[32];
     double l_sum = 0.0, c[4] = {0.0, 0.0, 0.0, 0.0};
     const float gs = grad_scale / ((float)T * (float)stages);
@@ -249,7 +252,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_bce_logits(const f
     B200MED_REQUIRE(logits && labels && loss && workspace, "null pointer");
     unsigned int *ticket = reinterpret_cast<unsigned int *>(workspace);
     double *partials = reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + 64);
-    bce_logits_kernel<<<loss_grid(B), kLossThreads, 0, (cudaStream_t)stream>>>(
+    launch_k(bce_logits_kernel, loss_grid(B), kLossThreads, 0, (cudaStream_t)stream, 
         logits, labels, B, pos_weight, grad_scale, loss, dlogits, probs, preds, (long long *)counts, accumulate,
         ticket, partials);
     return after_launch("bce_logits_kernel");
@@ -267,7 +270,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_ce_logits(const fl
     B200MED_REQUIRE(logits && target && loss && workspace, "null pointer");
     unsigned int *ticket = reinterpret_cast<unsigned int *>(workspace);
     double *partials = reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + 64);
-    ce_logits_kernel<<<loss_grid(B), kLossThreads, 0, (cudaStream_t)stream>>>(
+    launch_k(ce_logits_kernel, loss_grid(B), kLossThreads, 0, (cudaStream_t)stream, 
         logits, target, class_weight, mask, B, C, target_shift, reduction, grad_scale, loss, dlogits, probs, preds,
         pred_shift, pred_mask_mode, (long long *)cm, cm_classes, accumulate, ticket, partials);
     return after_launch("ce_logits_kernel");
@@ -280,7 +283,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_ce_frame(const flo
     B200MED_REQUIRE(logits && e && loss && workspace, "null pointer");
     unsigned int *ticket = reinterpret_cast<unsigned int *>(workspace);
     double *partials = reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + 64);
-    ce_frame_kernel<<<loss_grid(T), kLossThreads, 0, (cudaStream_t)stream>>>(
+    launch_k(ce_frame_kernel, loss_grid(T), kLossThreads, 0, (cudaStream_t)stream, 
         logits, e, stages, T, grad_scale, loss, dlogits, preds, (long long *)counts, accumulate, ticket, partials);
     return after_launch("ce_frame_kernel");
 }

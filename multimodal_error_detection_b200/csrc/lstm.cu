@@ -43,6 +43,7 @@ constexpr int kPackWin = 4;
 __global__ void __launch_bounds__(256)
 lstm_pack_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int F, int W, int H,
                  int Kp, int hoff) {
+    pdl_wait();
     extern __shared__ float sh_pack[];            // [kPackWin][F][W + 1] (padded rows: column reads spread over the banks)
     const int FW = F * W, W1 = W + 1, FW1 = F * W1;
     for (long long b0 = (long long)blockIdx.x * kPackWin; b0 < B; b0 += (long long)gridDim.x * kPackWin) {
@@ -77,6 +78,7 @@ lstm_pack_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, lo
 // dx [B, F, W] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F): the mirror transpose through shared memory.
 __global__ void __launch_bounds__(256)
 lstm_unpack_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F, int W, int Kp) {
+    pdl_wait();
     extern __shared__ float sh_pack[];            // [kPackWin][F][W + 1]
     const int FW = F * W, W1 = W + 1, FW1 = F * W1;
     for (long long b0 = (long long)blockIdx.x * kPackWin; b0 < B; b0 += (long long)gridDim.x * kPackWin) {
@@ -101,6 +103,7 @@ lstm_unpack_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long l
 __global__ void __launch_bounds__(256)
 lstm_pack_bwf_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int F, int W, int H,
                      int Kp, int hoff) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long nrows = B * W, warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(256)
 lstm_pack_parts_kernel(const float *__restrict__ feats, int Ca, const float *__restrict__ kin, long long table_rows, int Cb,
                        const float *__restrict__ mean, const float *__restrict__ stdv, int stat_rows, const int32_t *__restrict__ starts,
                        __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int W, int H, int Kp, int hoff) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int F = Ca + Cb;
     const long long nrows = B * W, warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -175,6 +179,7 @@ __global__ void __launch_bounds__(256)
 lstm_pack_parts64_kernel(const float *__restrict__ feats, int Ca, const float *__restrict__ kin, long long table_rows, int Cb,
                          const float *__restrict__ mean, const float *__restrict__ stdv, const int32_t *__restrict__ starts,
                          __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int W, int H, int Kp) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int c = lane * 2;
     const bool is_f = c < Ca, is_k = !is_f && c < Ca + Cb;
@@ -202,6 +207,7 @@ lstm_pack_parts64_kernel(const float *__restrict__ feats, int Ca, const float *_
 // dx [B, W, F] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F)
 __global__ void __launch_bounds__(256)
 lstm_unpack_bwf_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F, int W, int Kp) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long nrows = B * W, warps = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
@@ -213,6 +219,7 @@ lstm_unpack_bwf_kernel(const float *__restrict__ dA0, float *__restrict__ dx, lo
 }
 
 __global__ void zero_cols_bf16_kernel(__nv_bfloat16 *__restrict__ A, long long rows, int ld, int col0, int ncols) {
+    pdl_wait();
     const long long total = rows * ncols;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
         A[(e / ncols) * ld + col0 + (int)(e % ncols)] = __float2bfloat16_rn(0.0f);
@@ -224,6 +231,7 @@ lstm_cell_fwd_kernel(float *__restrict__ G, const float *__restrict__ c_prev, fl
                      __nv_bfloat16 *__restrict__ h_next, int ld_next, __nv_bfloat16 *__restrict__ x_up, int ld_up,
                      float *__restrict__ h_out, long long B, int H, float drop_p, const uint32_t *__restrict__ seed_dev,
                      unsigned long long drop_base) {
+    pdl_wait();
     const uint32_t seed = seed_dev ? *seed_dev : 0u;
     const long long total = B * (long long)H;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -252,6 +260,7 @@ lstm_cell_bwd_kernel(const float *__restrict__ Gact, const float *__restrict__ c
                      const float *__restrict__ dh_up, int ld_up, const float *__restrict__ dh_rec, int ld_rec,
                      float *__restrict__ dc, int dc_init, __nv_bfloat16 *__restrict__ dG, long long B, int H,
                      float drop_p, const uint32_t *__restrict__ seed_dev, unsigned long long drop_base) {
+    pdl_wait();
     const uint32_t seed = seed_dev ? *seed_dev : 0u;
     const long long total = B * (long long)H;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -288,6 +297,7 @@ __device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + 
 
 // x ([B, F, W] when layout == 0, [B, W, F] when layout == 1) -> X0 [W, B, F]
 __global__ void lstm_pack_f32_kernel(const float *__restrict__ x, float *__restrict__ X0, long long B, int F, int W, int layout) {
+    pdl_wait();
     const long long total = B * (long long)F * W;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(e % F);
@@ -300,6 +310,7 @@ __global__ void lstm_pack_f32_kernel(const float *__restrict__ x, float *__restr
 // dX0 [W, B, ld] columns [0, F) -> dx in the layout of x
 __global__ void lstm_unpack_f32_kernel(const float *__restrict__ dX0, float *__restrict__ dx, long long B, int F, int W, int ld,
                                        int layout) {
+    pdl_wait();
     const long long total = B * (long long)F * W;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         long long b; int t, k;
@@ -313,6 +324,7 @@ __global__ void __launch_bounds__(256)
 lstm_cell_fwd_f32_kernel(float *__restrict__ G, const float *__restrict__ c_prev, float *__restrict__ c_out,
                          float *__restrict__ h_out, float *__restrict__ x_up, long long B, int H, float drop_p,
                          const uint32_t *__restrict__ seed_dev, unsigned long long drop_base) {
+    pdl_wait();
     const uint32_t seed = seed_dev ? *seed_dev : 0u;
     const long long total = B * (long long)H;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -334,6 +346,7 @@ lstm_cell_bwd_f32_kernel(const float *__restrict__ Gact, const float *__restrict
                          const float *__restrict__ dh_up, int ld_up, const float *__restrict__ dh_rec,
                          float *__restrict__ dc, int dc_init, float *__restrict__ dG, long long B, int H, float drop_p,
                          const uint32_t *__restrict__ seed_dev, unsigned long long drop_base) {
+    pdl_wait();
     const uint32_t seed = seed_dev ? *seed_dev : 0u;
     const long long total = B * (long long)H;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -377,14 +390,14 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_inputs(c
     if (x_layout == 1) {
         B200MED_REQUIRE(x && A0 && Kp % 8 == 0, "bad argument");
         const long long blocks = (B * (long long)W + 7) / 8, cap1 = (long long)num_sms() * 8;
-        lstm_pack_bwf_kernel<<<(unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream>>>(
+        launch_k(lstm_pack_bwf_kernel, (unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream, 
             x, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, F, W, H, Kp, hoff);
         return after_launch("lstm_pack_bwf_kernel");
     }
     B200MED_REQUIRE(x && A0, "null pointer");
     B200MED_REQUIRE(Kp % 8 == 0 && (size_t)kPackWin * F * (W + 1) * 4 <= 48 * 1024, "bad shape");
     const long long blocks = (B + kPackWin - 1) / kPackWin, cap = (long long)num_sms() * 8;
-    lstm_pack_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, (size_t)kPackWin * F * (W + 1) * 4, (cudaStream_t)stream>>>(
+    launch_k(lstm_pack_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, (size_t)kPackWin * F * (W + 1) * 4, (cudaStream_t)stream, 
         x, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, F, W, H, Kp, hoff);
     return after_launch("lstm_pack_kernel");
 }
@@ -401,11 +414,11 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_parts(
     const long long blocks = (B * (long long)W + 7) / 8, cap = (long long)num_sms() * 8;
     if (Ca % 2 == 0 && Cb % 2 == 0 && Ca + Cb <= 64 && hoff == 64 && hoff + H == Kp && stat_rows == 1 &&
         ((uintptr_t)feats % 8 == 0) && ((uintptr_t)kin_table % 8 == 0)) {
-        lstm_pack_parts64_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+        launch_k(lstm_pack_parts64_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
             feats, Ca, kin_table, table_rows, Cb, mean, stdv, starts, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, W, H, Kp);
         return after_launch("lstm_pack_parts64_kernel");
     }
-    lstm_pack_parts_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(lstm_pack_parts_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
         feats, Ca, kin_table, table_rows, Cb, mean, stdv, stat_rows, starts, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, W, H, Kp, hoff);
     return after_launch("lstm_pack_parts_kernel");
 }
@@ -418,13 +431,13 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(con
     if (x_layout == 1) {
         B200MED_REQUIRE(dA0 && dx, "null pointer");
         const long long blocks = (B * (long long)W + 7) / 8, cap1 = (long long)num_sms() * 8;
-        lstm_unpack_bwf_kernel<<<(unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream>>>(dA0, dx, B, Bpad, F, W, Kp);
+        launch_k(lstm_unpack_bwf_kernel, (unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream, dA0, dx, B, Bpad, F, W, Kp);
         return after_launch("lstm_unpack_bwf_kernel");
     }
     B200MED_REQUIRE(dA0 && dx, "null pointer");
     B200MED_REQUIRE((size_t)kPackWin * F * (W + 1) * 4 <= 48 * 1024, "bad shape");
     const long long blocks = (B + kPackWin - 1) / kPackWin, cap = (long long)num_sms() * 8;
-    lstm_unpack_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, (size_t)kPackWin * F * (W + 1) * 4, (cudaStream_t)stream>>>(
+    launch_k(lstm_unpack_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, (size_t)kPackWin * F * (W + 1) * 4, (cudaStream_t)stream, 
         dA0, dx, B, Bpad, F, W, Kp);
     return after_launch("lstm_unpack_kernel");
 }
@@ -434,7 +447,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_zero_cols_bf16(voi
     B200MED_REQUIRE(rows >= 0 && ncols >= 0 && col0 >= 0 && col0 + ncols <= ld, "bad shape");
     if (rows == 0 || ncols == 0) return B200MED_OK;
     B200MED_REQUIRE(A, "null pointer");
-    zero_cols_bf16_kernel<<<grid_for(rows * ncols), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<__nv_bfloat16 *>(A), rows, ld,
+    launch_k(zero_cols_bf16_kernel, grid_for(rows * ncols), 256, 0, (cudaStream_t)stream, reinterpret_cast<__nv_bfloat16 *>(A), rows, ld,
                                                                                     col0, ncols);
     return after_launch("zero_cols_bf16_kernel");
 }
@@ -446,7 +459,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_fwd(floa
                                                                             void *stream) {
     B200MED_REQUIRE(B >= 1 && H >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
     B200MED_REQUIRE(G && c_out, "null pointer");
-    lstm_cell_fwd_kernel<<<grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(lstm_cell_fwd_kernel, grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream, 
         G, c_prev, c_out, reinterpret_cast<__nv_bfloat16 *>(h_next), ld_next, reinterpret_cast<__nv_bfloat16 *>(x_up), ld_up,
         h_out, B, H, drop_p, seed, drop_base);
     return after_launch("lstm_cell_fwd_kernel");
@@ -459,7 +472,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_bwd(cons
                                                                             uint64_t drop_base, void *stream) {
     B200MED_REQUIRE(B >= 1 && H >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
     B200MED_REQUIRE(Gact && c && dc && dG, "null pointer");
-    lstm_cell_bwd_kernel<<<grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(lstm_cell_bwd_kernel, grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream, 
         Gact, c, c_prev, dh_up, ld_up, dh_rec, ld_rec, dc, dc_init, reinterpret_cast<__nv_bfloat16 *>(dG), B, H, drop_p, seed,
         drop_base);
     return after_launch("lstm_cell_bwd_kernel");
@@ -469,7 +482,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_f32(cons
                                                                            int32_t x_layout, void *stream) {
     B200MED_REQUIRE(B >= 1 && F >= 1 && W >= 1 && (x_layout == 0 || x_layout == 1), "bad shape");
     B200MED_REQUIRE(x && X0, "null pointer");
-    lstm_pack_f32_kernel<<<grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream>>>(x, X0, B, F, W, x_layout);
+    launch_k(lstm_pack_f32_kernel, grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream, x, X0, B, F, W, x_layout);
     return after_launch("lstm_pack_f32_kernel");
 }
 
@@ -477,7 +490,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_f32(co
                                                                              int32_t ld, int32_t x_layout, void *stream) {
     B200MED_REQUIRE(B >= 1 && F >= 1 && W >= 1 && ld >= F && (x_layout == 0 || x_layout == 1), "bad shape");
     B200MED_REQUIRE(dX0 && dx, "null pointer");
-    lstm_unpack_f32_kernel<<<grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream>>>(dX0, dx, B, F, W, ld, x_layout);
+    launch_k(lstm_unpack_f32_kernel, grid_for(B * (long long)F * W), 256, 0, (cudaStream_t)stream, dX0, dx, B, F, W, ld, x_layout);
     return after_launch("lstm_unpack_f32_kernel");
 }
 
@@ -486,7 +499,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_fwd_f32(
                                                                                const uint32_t *seed, uint64_t drop_base, void *stream) {
     B200MED_REQUIRE(B >= 1 && H >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
     B200MED_REQUIRE(G && c_out && h_out, "null pointer");
-    lstm_cell_fwd_f32_kernel<<<grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream>>>(G, c_prev, c_out, h_out, x_up, B, H, drop_p,
+    launch_k(lstm_cell_fwd_f32_kernel, grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream, G, c_prev, c_out, h_out, x_up, B, H, drop_p,
                                                                                            seed, drop_base);
     return after_launch("lstm_cell_fwd_f32_kernel");
 }
@@ -498,7 +511,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_cell_bwd_f32(
                                                                                void *stream) {
     B200MED_REQUIRE(B >= 1 && H >= 1 && drop_p >= 0.0f && drop_p < 1.0f, "bad shape");
     B200MED_REQUIRE(Gact && c && dc && dG, "null pointer");
-    lstm_cell_bwd_f32_kernel<<<grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream>>>(Gact, c, c_prev, dh_up, ld_up, dh_rec, dc,
+    launch_k(lstm_cell_bwd_f32_kernel, grid_for(B * (long long)H), 256, 0, (cudaStream_t)stream, Gact, c, c_prev, dh_up, ld_up, dh_rec, dc,
                                                                                            dc_init, dG, B, H, drop_p, seed, drop_base);
     return after_launch("lstm_cell_bwd_f32_kernel");
 }

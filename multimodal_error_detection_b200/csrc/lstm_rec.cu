@@ -144,6 +144,7 @@ template <bool kSave, bool kUp, bool kDrop>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 lstm_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_constant__ CUtensorMap tmap_next,
                     const __grid_constant__ CUtensorMap tmap_up, const RecFwdParams p) {
+    pdl_wait();
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = align_1024(smem_dyn);
     unsigned char *w_sm = smem;                     // [k-block 0..1][256-row half 0..1][256 rows][128 B]
@@ -364,6 +365,7 @@ template <bool kDrop>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 lstm_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_whh, const __grid_constant__ CUtensorMap tmap_dg,
                     const RecBwdParams p) {
+    pdl_wait();
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = align_1024(smem_dyn);
     unsigned char *b_sm = smem;                 // W_hh as MN-major B operand: [k-block 0..7][n-half 0..1][64 k][128 B]
@@ -605,7 +607,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_rec_fwd(
     auto launch = [&](auto kern) -> int {
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecFwdSmem),
                                "cudaFuncSetAttribute(lstm_rec_fwd)")) return e;
-        kern<<<grid, kFwdThreads, kRecFwdSmem, (cudaStream_t)stream>>>(tm, tn, tu, p);
+        launch_k(kern, grid, kFwdThreads, kRecFwdSmem, (cudaStream_t)stream, tm, tn, tu, p);
         return B200MED_OK;
     };
     int e;
@@ -636,7 +638,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_rec_bwd(
     auto launch = [&](auto kern) -> int {
         if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecBwdSmem),
                                "cudaFuncSetAttribute(lstm_rec_bwd)")) return e;
-        kern<<<grid, kBwdThreads, kRecBwdSmem, (cudaStream_t)stream>>>(tm, tg, p);
+        launch_k(kern, grid, kBwdThreads, kRecBwdSmem, (cudaStream_t)stream, tm, tg, p);
         return B200MED_OK;
     };
     if (int e = (dh_up && drop_p > 0.0f) ? launch(lstm_rec_bwd_kernel<true>) : launch(lstm_rec_bwd_kernel<false>)) return e;

@@ -91,6 +91,7 @@ template <int KXB, bool kSave, bool kUp, bool kDrop>
 __global__ void __launch_bounds__(kR2Threads, 1)
 lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
                      const __grid_constant__ CUtensorMap tmap_up, const Rec2FwdParams p) {
+    pdl_wait();
     using S = Rec2Smem<KXB>;
     extern __shared__ __align__(1024) unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
@@ -360,6 +361,7 @@ lstm_rec2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 __global__ void lstm_pack_weights2_kernel(const float *__restrict__ w_ih, const float *__restrict__ w_hh,
                                           const float *__restrict__ b_ih, const float *__restrict__ b_hh, int in, int kx,
                                           __nv_bfloat16 *__restrict__ wp, float *__restrict__ bias_p) {
+    pdl_wait();
     const int kc = kx + kR2H;
     const int total = 4 * kR2H * kc;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -420,6 +422,7 @@ struct Rec2BwdSmem {
 template <int KXB, bool kDrop>
 __global__ void __launch_bounds__(kR2BwdThreads, 1)
 lstm_rec2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_dg, const Rec2BwdParams p) {
+    pdl_wait();
     using S = Rec2BwdSmem<KXB>;
     constexpr int kNH = S::kNHalf;
     constexpr int kXH = KXB * 32;                 // dX columns per lane half
@@ -682,6 +685,7 @@ lstm_rec2_bwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 // the weight / bias gradients with it).
 __global__ void lstm_pack_weights2_bwd_kernel(const float *__restrict__ w_ih, const float *__restrict__ w_hh, int in, int kx,
                                               __nv_bfloat16 *__restrict__ wt, int32_t *__restrict__ perm) {
+    pdl_wait();
     const int n = kx + kR2H, nh = n / 2, xh = kx / 2;
     const int total = n * 512;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -703,6 +707,7 @@ __global__ void lstm_pack_weights2_bwd_kernel(const float *__restrict__ w_ih, co
 __global__ void lstm_unpack_grads2_kernel(const float *__restrict__ dwp, const float *__restrict__ dbp, int in, int kx,
                                           float *__restrict__ dw_ih, float *__restrict__ dw_hh, float *__restrict__ db_ih,
                                           float *__restrict__ db_hh) {
+    pdl_wait();
     const int kc = kx + kR2H;
     const int total = 512 * kc;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -734,7 +739,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_weights2
     B200MED_REQUIRE(in >= 1 && (kx == 64 || kx == 128) && in <= kx, "kx must be 64 or 128 and >= the input width");
     B200MED_REQUIRE(w_ih && w_hh && b_ih && b_hh && wp && bias_p, "null pointer");
     const int total = 4 * kR2H * (kx + kR2H);
-    lstm_pack_weights2_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_ih, w_hh, b_ih, b_hh, in, kx,
+    launch_k(lstm_pack_weights2_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, w_ih, w_hh, b_ih, b_hh, in, kx,
                                                                                     reinterpret_cast<__nv_bfloat16 *>(wp), bias_p);
     return after_launch("lstm_pack_weights2_kernel");
 }
@@ -767,10 +772,10 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_rec2_fwd(
         cfg.blockDim = dim3(kR2Threads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1);
         return check_cuda(cudaLaunchKernelEx(&cfg, kern, tw, ta, tu, p), "cudaLaunchKernelEx(lstm_rec2_fwd)");
     };
     int e;
@@ -793,7 +798,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_weights2
     B200MED_REQUIRE(in >= 1 && (kx == 64 || kx == 128) && in <= kx, "kx must be 64 or 128 and >= the input width");
     B200MED_REQUIRE(w_ih && w_hh && wt, "null pointer");
     const int total = (kx + kR2H) * 512;
-    lstm_pack_weights2_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_ih, w_hh, in, kx,
+    launch_k(lstm_pack_weights2_bwd_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, w_ih, w_hh, in, kx,
                                                                                         reinterpret_cast<__nv_bfloat16 *>(wt), perm);
     return after_launch("lstm_pack_weights2_bwd_kernel");
 }
@@ -821,10 +826,10 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_rec2_bwd(
         cfg.blockDim = dim3(kR2BwdThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1);
         return check_cuda(cudaLaunchKernelEx(&cfg, kern, tw, tg, p), "cudaLaunchKernelEx(lstm_rec2_bwd)");
     };
     const bool drp = dh_up && drop_p > 0.0f;
@@ -841,6 +846,6 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_grads2
     B200MED_REQUIRE(in >= 1 && (kx == 64 || kx == 128) && in <= kx, "kx must be 64 or 128 and >= the input width");
     B200MED_REQUIRE(dwp && dbp && dw_ih && dw_hh && db_ih && db_hh, "null pointer");
     const int total = 512 * (kx + kR2H);
-    lstm_unpack_grads2_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dwp, dbp, in, kx, dw_ih, dw_hh, db_ih, db_hh);
+    launch_k(lstm_unpack_grads2_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, dwp, dbp, in, kx, dw_ih, dw_hh, db_ih, db_hh);
     return after_launch("lstm_unpack_grads2_kernel");
 }

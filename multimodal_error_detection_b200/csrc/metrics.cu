@@ -25,6 +25,7 @@ __device__ __forceinline__ uint32_t order_key(float x) {
 // stats: [0] n_pos, [1] n_neg, [2] 2*less + equal, [3] unused
 __global__ void auc_keys_kernel(const float *__restrict__ score, const float *__restrict__ label, long long n,
                                 long long npad, uint32_t *__restrict__ keys, unsigned long long *__restrict__ stats) {
+    pdl_wait();
     unsigned int neg = 0, pos = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npad; i += (long long)gridDim.x * blockDim.x) {
         uint32_t k = 0xFFFFFFFFu;
@@ -49,6 +50,7 @@ __device__ __forceinline__ void cmp_swap(uint32_t &a, uint32_t &b, bool up) {
 // index so that the global stages can merge them.  FULL = false: finish stage k (k > kSortSpan) for j = kSortBlock .. 1.
 template <bool FULL>
 __global__ void __launch_bounds__(kSortBlock) bitonic_shared_kernel(uint32_t *__restrict__ keys, long long k_stage) {
+    pdl_wait();
     __shared__ uint32_t s[kSortSpan];
     const long long base = (long long)blockIdx.x * kSortSpan;
     s[threadIdx.x] = keys[base + threadIdx.x];
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(kSortBlock) bitonic_shared_kernel(uint32_t *__
 }
 
 __global__ void bitonic_global_kernel(uint32_t *__restrict__ keys, long long npad, long long k, long long j) {
+    pdl_wait();
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < npad / 2; t += (long long)gridDim.x * blockDim.x) {
         const long long lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         const bool up = ((lo & k) == 0);
@@ -88,6 +91,7 @@ __global__ void bitonic_global_kernel(uint32_t *__restrict__ keys, long long npa
 
 __global__ void auc_count_kernel(const float *__restrict__ score, const float *__restrict__ label, long long n,
                                  const uint32_t *__restrict__ sorted, unsigned long long *__restrict__ stats) {
+    pdl_wait();
     const long long n_neg = (long long)stats[1];
     long long acc = 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -105,6 +109,7 @@ __global__ void auc_count_kernel(const float *__restrict__ score, const float *_
 }
 
 __global__ void auc_final_kernel(const unsigned long long *__restrict__ stats, double *__restrict__ auc) {
+    pdl_wait();
     const double np = (double)stats[0], nn = (double)stats[1];
     // one class only: sklearn raises ValueError; the host wrapper does the same from stats, the device value is NaN
     *auc = (np > 0 && nn > 0) ? (double)stats[2] / (2.0 * np * nn) : __longlong_as_double(0x7FF8000000000000LL);
@@ -135,20 +140,20 @@ extern "C" __attribute__((visibility("default"))) int b200med_roc_auc(const floa
     if (int e = check_cuda(cudaMemsetAsync(stats, 0, 4 * sizeof(int64_t), st), "cudaMemsetAsync(stats)")) return e;
     const long long cap = (long long)num_sms() * 8;
     auto grid_for = [&](long long items, int threads) { const long long w = (items + threads - 1) / threads; return (unsigned)(w < cap ? (w < 1 ? 1 : w) : cap); };
-    auc_keys_kernel<<<grid_for(npad, 256), 256, 0, st>>>(scores, labels, n, npad, keys, s64);
+    launch_k(auc_keys_kernel, grid_for(npad, 256), 256, 0, st, scores, labels, n, npad, keys, s64);
     if (int e = after_launch("auc_keys_kernel")) return e;
-    bitonic_shared_kernel<true><<<(unsigned)(npad / kSortSpan), kSortBlock, 0, st>>>(keys, 0);
+    launch_k(bitonic_shared_kernel<true>, (unsigned)(npad / kSortSpan), kSortBlock, 0, st, keys, 0);
     if (int e = after_launch("bitonic_shared_kernel")) return e;
     for (long long k = 2LL * kSortSpan; k <= npad; k <<= 1) {
         for (long long j = k >> 1; j > kSortBlock; j >>= 1) {
-            bitonic_global_kernel<<<grid_for(npad / 2, 256), 256, 0, st>>>(keys, npad, k, j);
+            launch_k(bitonic_global_kernel, grid_for(npad / 2, 256), 256, 0, st, keys, npad, k, j);
             if (int e = after_launch("bitonic_global_kernel")) return e;
         }
-        bitonic_shared_kernel<false><<<(unsigned)(npad / kSortSpan), kSortBlock, 0, st>>>(keys, k);
+        launch_k(bitonic_shared_kernel<false>, (unsigned)(npad / kSortSpan), kSortBlock, 0, st, keys, k);
         if (int e = after_launch("bitonic_shared_kernel")) return e;
     }
-    auc_count_kernel<<<grid_for(n, 256), 256, 0, st>>>(scores, labels, n, keys, s64);
+    launch_k(auc_count_kernel, grid_for(n, 256), 256, 0, st, scores, labels, n, keys, s64);
     if (int e = after_launch("auc_count_kernel")) return e;
-    auc_final_kernel<<<1, 1, 0, st>>>(s64, auc);
+    launch_k(auc_final_kernel, 1, 1, 0, st, s64, auc);
     return after_launch("auc_final_kernel");
 }

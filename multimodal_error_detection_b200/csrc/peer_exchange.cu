@@ -59,6 +59,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t *p, uint32_t epoch) {
 
 __global__ void __launch_bounds__(512)
 peer_allreduce_kernel(float *const *__restrict__ bufs, uint32_t *const *__restrict__ flags, int rank, int world, long long n) {
+    pdl_wait();
     uint32_t *mine = flags[rank];
     __shared__ uint32_t epoch_sm;
     if (threadIdx.x == 0) epoch_sm = ld_acquire_sys(mine + 32) + 1;      // bumped only by the LAST CTA of a launch to leave
@@ -155,7 +156,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_peer_allreduce_f32
     const long long cap = num_sms();
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
-    peer_allreduce_kernel<<<(unsigned)ctas, 512, 0, (cudaStream_t)stream>>>(
+    peer_allreduce_kernel<<<(unsigned)ctas, 512, 0, (cudaStream_t)stream>>>(      // plain launch: its CTAs spin on each other and on the peers, they do not sit next to a draining predecessor
         reinterpret_cast<float *const *>(bufs_dev), reinterpret_cast<uint32_t *const *>(flags_dev), rank, world, n);
     return after_launch("peer_allreduce_kernel");
 }

@@ -129,6 +129,7 @@ __device__ __forceinline__ void half_sum(float (&acc)[RPW][4]) {
 // ptrs [L][4] = {conv_dilated.weight [64,64,3], conv_dilated.bias [64], conv_1x1.weight [64,64,1], conv_1x1.bias [64]}
 __global__ void __launch_bounds__(256)
 tcn_pack_kernel(const float *const *__restrict__ ptrs, float *__restrict__ packed) {
+    pdl_wait();
     const int layer = blockIdx.y;
     const float *wd = ptrs[layer * 4 + 0], *bd = ptrs[layer * 4 + 1], *w1 = ptrs[layer * 4 + 2], *b1 = ptrs[layer * 4 + 3];
     float *out = packed + (long long)layer * kPackFloats;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(kTcnThreads)
 tcn_layer_fwd_kernel(const float *__restrict__ x, const float *__restrict__ pack, float *__restrict__ out,
                      float *__restrict__ y_save, TcnGeom g, float drop_p, unsigned long long seed,
                      const unsigned long long *__restrict__ seed_dev, unsigned long long drop_base) {
+    pdl_wait();
     constexpr int TT = 4 * RPW;
     if (seed_dev) seed += *seed_dev;   // per-step counter in device memory: a replayed CUDA graph draws a fresh mask
     extern __shared__ __align__(128) float smem[];
@@ -223,6 +225,7 @@ tcn_layer_bwd_hidden_kernel(const float *__restrict__ dout, const float *__restr
                             const float *__restrict__ pack, float *__restrict__ dpre, float *__restrict__ partials,
                             TcnGeom g, float drop_p, unsigned long long seed,
                             const unsigned long long *__restrict__ seed_dev, unsigned long long drop_base) {
+    pdl_wait();
     constexpr int TT = 4 * RPW;
     if (seed_dev) seed += *seed_dev;
     extern __shared__ __align__(128) float smem[];
@@ -342,6 +345,7 @@ tcn_layer_bwd_hidden_kernel(const float *__restrict__ dout, const float *__restr
 // grads[layer][e] = sum over slots (ascending) of partials[layer][slot][e]
 __global__ void __launch_bounds__(256)
 tcn_reduce_grads_kernel(const float *__restrict__ partials, float *__restrict__ grads, int n_slots) {
+    pdl_wait();
     const int layer = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= kGradFloats) return;
@@ -357,6 +361,7 @@ template <int RPW>
 __global__ void __launch_bounds__(kTcnThreads)
 tcn_layer_bwd_input_kernel(const float *__restrict__ dpre, const float *__restrict__ dout, const float *__restrict__ pack,
                            float *__restrict__ dx, TcnGeom g) {
+    pdl_wait();
     constexpr int TT = 4 * RPW;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -388,6 +393,7 @@ tcn_layer_bwd_input_kernel(const float *__restrict__ dpre, const float *__restri
 __global__ void __launch_bounds__(128)
 tcn_out_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b,
                    float *__restrict__ logits, long long T, int C) {
+    pdl_wait();
     __shared__ float ws[kMaxClasses * kF];
     __shared__ float bs[kMaxClasses];
     for (int i = threadIdx.x; i < C * kF; i += blockDim.x) ws[i] = w[i];
@@ -419,6 +425,7 @@ tcn_out_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, con
 __global__ void __launch_bounds__(256)
 tcn_out_bwd_kernel(const float *__restrict__ dl, const float *__restrict__ w, float *__restrict__ dx,
                    float *__restrict__ dl_t, long long T, int C) {
+    pdl_wait();
     __shared__ float ws[kMaxClasses * kF];
     for (int i = threadIdx.x; i < C * kF; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
@@ -442,6 +449,7 @@ tcn_out_bwd_kernel(const float *__restrict__ dl, const float *__restrict__ w, fl
 // p[t][c] = softmax_c(logits[c][t])   (F.softmax(out, dim=1) between stages, models_TCN.py:48)
 __global__ void __launch_bounds__(128)
 tcn_softmax_fwd_kernel(const float *__restrict__ logits, float *__restrict__ p, long long T, int C) {
+    pdl_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     float v[kMaxClasses], m = -INFINITY;
@@ -461,6 +469,7 @@ tcn_softmax_fwd_kernel(const float *__restrict__ logits, float *__restrict__ p, 
 __global__ void __launch_bounds__(128)
 tcn_softmax_bwd_kernel(const float *__restrict__ p, const float *__restrict__ dp, float *__restrict__ dlogits, long long T,
                        int C) {
+    pdl_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     float pv[kMaxClasses], dv[kMaxClasses], dot = 0.f;
@@ -496,6 +505,7 @@ __global__ void __launch_bounds__(kTileF)
 tcn_layer_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                           const float *__restrict__ res_in, float *__restrict__ res_out, __nv_bfloat16 *__restrict__ opn_out,
                           const float *__restrict__ bias /* b_d | b_1 */, int layer, TcnGeom g) {
+    pdl_wait();
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char *a_sm = smem;                               // [3][128 rows][128 B]
@@ -642,6 +652,7 @@ tcn_layer_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 // wb16[layer][tap*64 + co][ci] (tap 3 = the 1x1 convolution) = bf16 of the fp32 pack's WdB | W1B block
 __global__ void __launch_bounds__(256)
 tcn_pack_bf16_kernel(const float *__restrict__ pack, __nv_bfloat16 *__restrict__ wb16) {
+    pdl_wait();
     const int layer = blockIdx.y;
     const float *src = pack + (long long)layer * kPackFloats + kOffWdB;
     __nv_bfloat16 *dst = wb16 + (long long)layer * 4 * kF * kF;
@@ -707,7 +718,7 @@ TCN_API int b200med_tcn_pack(const void *const *param_ptrs, int32_t n_layers, fl
     B200MED_REQUIRE(n_layers >= 1, "bad layer count");
     B200MED_REQUIRE(param_ptrs && packed, "null pointer");
     B200MED_REQUIRE((uintptr_t)packed % 16 == 0, "packed must be 16-byte aligned");
-    tcn_pack_kernel<<<dim3(8, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(tcn_pack_kernel, dim3(8, (unsigned)n_layers), 256, 0, (cudaStream_t)stream, 
         reinterpret_cast<const float *const *>(param_ptrs), packed);
     return after_launch("tcn_pack_kernel");
 }
@@ -725,7 +736,7 @@ TCN_API int b200med_tcn_layer_fwd(const float *x, const float *pack, float *out,
 #define TCN_LAUNCH_FWD(R)                                                                                          \
     {                                                                                                             \
         if (int e = opt_in_smem(tcn_layer_fwd_kernel<R>, smem_fwd(4 * R))) return e;                              \
-        tcn_layer_fwd_kernel<R><<<(unsigned)((T + 4 * R - 1) / (4 * R)), kTcnThreads, smem_fwd(4 * R), (cudaStream_t)stream>>>( \
+        launch_k(tcn_layer_fwd_kernel<R>, (unsigned)((T + 4 * R - 1) / (4 * R)), kTcnThreads, smem_fwd(4 * R), (cudaStream_t)stream,  \
             x, pack, out, y_save, g, drop_p, seed, reinterpret_cast<const unsigned long long *>(seed_dev), drop_base); \
     }
     switch (pick_rpw(T)) {
@@ -749,11 +760,11 @@ TCN_API int b200med_tcn_layer_bwd_hidden(const float *dout, const float *x, cons
     B200MED_REQUIRE(n_slots <= b200med_tcn_slots(T), "n_slots must not exceed b200med_tcn_slots(T)");
     if (pick_rpw_hidden(T) == 2) {
         if (int e = opt_in_smem(tcn_layer_bwd_hidden_kernel<2>, smem_bwd_h(8))) return e;
-        tcn_layer_bwd_hidden_kernel<2><<<(unsigned)n_slots, kTcnThreads, smem_bwd_h(8), (cudaStream_t)stream>>>(
+        launch_k(tcn_layer_bwd_hidden_kernel<2>, (unsigned)n_slots, kTcnThreads, smem_bwd_h(8), (cudaStream_t)stream, 
             dout, x, y, pack, dpre, partials, g, drop_p, seed, reinterpret_cast<const unsigned long long *>(seed_dev), drop_base);
     } else {
         if (int e = opt_in_smem(tcn_layer_bwd_hidden_kernel<4>, smem_bwd_h(16))) return e;
-        tcn_layer_bwd_hidden_kernel<4><<<(unsigned)n_slots, kTcnThreads, smem_bwd_h(16), (cudaStream_t)stream>>>(
+        launch_k(tcn_layer_bwd_hidden_kernel<4>, (unsigned)n_slots, kTcnThreads, smem_bwd_h(16), (cudaStream_t)stream, 
             dout, x, y, pack, dpre, partials, g, drop_p, seed, reinterpret_cast<const unsigned long long *>(seed_dev), drop_base);
     }
     return after_launch("tcn_layer_bwd_hidden_kernel");
@@ -770,7 +781,7 @@ TCN_API int b200med_tcn_layer_bwd_input(const float *dpre, const float *dout, co
 #define TCN_LAUNCH_BWD_I(R)                                                                                        \
     {                                                                                                             \
         if (int e = opt_in_smem(tcn_layer_bwd_input_kernel<R>, smem_bwd_i(4 * R))) return e;                      \
-        tcn_layer_bwd_input_kernel<R><<<(unsigned)((T + 4 * R - 1) / (4 * R)), kTcnThreads, smem_bwd_i(4 * R), (cudaStream_t)stream>>>( \
+        launch_k(tcn_layer_bwd_input_kernel<R>, (unsigned)((T + 4 * R - 1) / (4 * R)), kTcnThreads, smem_bwd_i(4 * R), (cudaStream_t)stream,  \
             dpre, dout, pack, dx, g);                                                                             \
     }
     switch (pick_rpw(T)) {
@@ -784,7 +795,7 @@ TCN_API int b200med_tcn_layer_bwd_input(const float *dpre, const float *dout, co
 TCN_API int b200med_tcn_reduce_grads(const float *partials, int32_t n_layers, int32_t n_slots, float *grads, void *stream) {
     B200MED_REQUIRE(n_layers >= 1 && n_slots >= 1, "bad shape");
     B200MED_REQUIRE(partials && grads, "null pointer");
-    tcn_reduce_grads_kernel<<<dim3((kGradFloats + 255) / 256, (unsigned)n_layers), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(tcn_reduce_grads_kernel, dim3((kGradFloats + 255) / 256, (unsigned)n_layers), 256, 0, (cudaStream_t)stream, 
         partials, grads, n_slots);
     return after_launch("tcn_reduce_grads_kernel");
 }
@@ -795,7 +806,7 @@ TCN_API int b200med_tcn_out_fwd(const float *x, const float *w, const float *b, 
     if (T == 0) return B200MED_OK;
     B200MED_REQUIRE(x && w && b && logits, "null pointer");
     B200MED_REQUIRE((uintptr_t)x % 16 == 0, "x must be 16-byte aligned");
-    tcn_out_fwd_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, w, b, logits, T, C);
+    launch_k(tcn_out_fwd_kernel, (unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream, x, w, b, logits, T, C);
     return after_launch("tcn_out_fwd_kernel");
 }
 
@@ -805,7 +816,7 @@ TCN_API int b200med_tcn_out_bwd(const float *dlogits, const float *w, float *dx,
     B200MED_REQUIRE(dlogits && w && dx && dlogits_t, "null pointer");
     B200MED_REQUIRE((uintptr_t)dx % 16 == 0, "dx must be 16-byte aligned");
     const long long n = T * (kF / 4);
-    tcn_out_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dlogits, w, dx, dlogits_t, T, C);
+    launch_k(tcn_out_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, dlogits, w, dx, dlogits_t, T, C);
     return after_launch("tcn_out_bwd_kernel");
 }
 
@@ -813,14 +824,14 @@ TCN_API int b200med_tcn_softmax_fwd(const float *logits, float *p, int64_t T, in
     B200MED_REQUIRE(T >= 0 && C >= 1 && C <= kMaxClasses, "1 <= C <= 8 classes");
     if (T == 0) return B200MED_OK;
     B200MED_REQUIRE(logits && p, "null pointer");
-    tcn_softmax_fwd_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(logits, p, T, C);
+    launch_k(tcn_softmax_fwd_kernel, (unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream, logits, p, T, C);
     return after_launch("tcn_softmax_fwd_kernel");
 }
 
 TCN_API int b200med_tcn_softmax_bwd(const float *p, const float *dp, float *dlogits, int64_t T, int32_t C, void *stream) {
     B200MED_REQUIRE(T >= 1 && C >= 1 && C <= kMaxClasses, "1 <= C <= 8 classes");
     B200MED_REQUIRE(p && dp && dlogits, "null pointer");
-    tcn_softmax_bwd_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p, dp, dlogits, T, C);
+    launch_k(tcn_softmax_bwd_kernel, (unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream, p, dp, dlogits, T, C);
     return after_launch("tcn_softmax_bwd_kernel");
 }
 
@@ -945,7 +956,7 @@ TCN_API int b200med_tcn_stage_fwd_bf16(const float *x, int32_t in_dim, int32_t s
     if (int e = b200med_linear_fwd_f32(xin, in_w, in_b, res, T, kF, in_dim, 0, stream)) return e;
     if (int e = b200med_cast_f32_to_bf16(res, opn16, (int64_t)plane, stream)) return e;
     if (int e = b200med_tcn_pack(layer_ptrs, n_layers, pack, stream)) return e;
-    tcn_pack_bf16_kernel<<<dim3(8, (unsigned)n_layers), 256, 0, st>>>(pack, reinterpret_cast<__nv_bfloat16 *>(wb16));
+    launch_k(tcn_pack_bf16_kernel, dim3(8, (unsigned)n_layers), 256, 0, st, pack, reinterpret_cast<__nv_bfloat16 *>(wb16));
     if (int e = after_launch("tcn_pack_bf16_kernel")) return e;
     CUtensorMap map_a[2], map_w;
     for (int i = 0; i < 2; ++i)
@@ -955,7 +966,7 @@ TCN_API int b200med_tcn_stage_fwd_bf16(const float *x, int32_t in_dim, int32_t s
     for (int l = 0; l < n_layers; ++l) {
         TcnGeom g; make_geom(g, T, 1 << l, causal, tloc, trem);
         const int src = l & 1, dst = (l + 1) & 1;
-        tcn_layer_fwd_bf16_kernel<<<(unsigned)((T + kTileF - 1) / kTileF), kTileF, kSmemBf16, st>>>(
+        launch_k(tcn_layer_fwd_bf16_kernel, (unsigned)((T + kTileF - 1) / kTileF), kTileF, kSmemBf16, st, 
             map_a[src], map_w, res + (size_t)src * plane, res + (size_t)dst * plane, opn16 + (size_t)dst * plane,
             pack + (size_t)l * kPackFloats + kOffBias, l, g);
         if (int e = after_launch("tcn_layer_fwd_bf16_kernel")) return e;

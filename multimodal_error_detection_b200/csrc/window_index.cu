@@ -33,6 +33,7 @@ __device__ __forceinline__ long long walk_subject(const float *__restrict__ g, l
 __global__ void window_count_kernel(const float *__restrict__ g, const int64_t *__restrict__ off,
                                      long long n_subj, int W, int S, int64_t *__restrict__ counts,
                                      int32_t *__restrict__ status) {
+    pdl_wait();
     const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (s >= n_subj) return;
     const long long c = walk_subject<false>(g, off[s], off[s + 1] - off[s], W, S, 0, nullptr);
@@ -42,6 +43,7 @@ __global__ void window_count_kernel(const float *__restrict__ g, const int64_t *
 
 // In-place exclusive scan of counts[0..n) into counts[0..n]; single block, fixed order.
 __global__ void exclusive_scan_kernel(int64_t *__restrict__ data, long long n, int32_t *__restrict__ status) {
+    pdl_wait();
     __shared__ long long warp_tot[32];
     __shared__ long long carry;
     if (threadIdx.x == 0) carry = 0;
@@ -85,6 +87,7 @@ __global__ void window_fill_kernel(const float *__restrict__ g, const int64_t *_
                                    const float *__restrict__ e5, int32_t *__restrict__ starts,
                                    float *__restrict__ g_win, float *__restrict__ e5_win,
                                    int32_t *__restrict__ subj_win) {
+    pdl_wait();
     const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (s >= n_subj) return;
     const long long o = win_off[s];
@@ -101,11 +104,13 @@ __global__ void window_fill_kernel(const float *__restrict__ g, const int64_t *_
     }
 }
 
-__global__ void set_i32_kernel(int32_t *p, int32_t v) { *p = v; }
+__global__ void set_i32_kernel(int32_t *p, int32_t v) {
+    pdl_wait(); *p = v; }
 
 // One thread per row; first matching rule wins, same order as dataset_utils.py:796-843.
 __global__ void powerset_kernel(const float *__restrict__ e5, long long n, int delete_nd,
                                 int32_t *__restrict__ e7, uint8_t *__restrict__ nd_mask) {
+    pdl_wait();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float oov = e5[i * 5 + 0], nd = e5[i * 5 + 1], ma = e5[i * 5 + 2], np_ = e5[i * 5 + 3],
@@ -138,15 +143,15 @@ extern "C" __attribute__((visibility("default"))) int b200med_window_count(const
     B200MED_REQUIRE(g && subj_offsets && win_offsets && status, "null pointer");
     B200MED_REQUIRE(n_subjects >= 0 && W >= 1 && S >= 1, "need n_subjects >= 0, W >= 1, S >= 1");
     cudaStream_t st = (cudaStream_t)stream;
-    set_i32_kernel<<<1, 1, 0, st>>>(status, INT32_MAX);
+    launch_k(set_i32_kernel, 1, 1, 0, st, status, INT32_MAX);
     if (int e = after_launch("set_i32_kernel")) return e;
     if (n_subjects > 0) {
         const int threads = 128;
         const long long blocks = (n_subjects + threads - 1) / threads;
-        window_count_kernel<<<(unsigned)blocks, threads, 0, st>>>(g, subj_offsets, n_subjects, W, S, win_offsets, status);
+        launch_k(window_count_kernel, (unsigned)blocks, threads, 0, st, g, subj_offsets, n_subjects, W, S, win_offsets, status);
         if (int e = after_launch("window_count_kernel")) return e;
     }
-    exclusive_scan_kernel<<<1, 1024, 0, st>>>(win_offsets, n_subjects, status);
+    launch_k(exclusive_scan_kernel, 1, 1024, 0, st, win_offsets, n_subjects, status);
     return after_launch("exclusive_scan_kernel");
 }
 
@@ -158,7 +163,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_window_fill(const 
     if (n_subjects == 0) return B200MED_OK;
     const int threads = 128;
     const long long blocks = (n_subjects + threads - 1) / threads;
-    window_fill_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+    launch_k(window_fill_kernel, (unsigned)blocks, threads, 0, (cudaStream_t)stream, 
         g, subj_offsets, win_offsets, n_subjects, W, S, e5, starts, g_win, e5_win, subj_win);
     return after_launch("window_fill_kernel");
 }
@@ -170,6 +175,6 @@ extern "C" __attribute__((visibility("default"))) int b200med_powerset(const flo
     B200MED_REQUIRE(e5 && e7 && nd_mask, "null pointer");
     const int threads = 256;
     const long long blocks = (n + threads - 1) / threads;
-    powerset_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(e5, n, delete_nd, e7, nd_mask);
+    launch_k(powerset_kernel, (unsigned)blocks, threads, 0, (cudaStream_t)stream, e5, n, delete_nd, e7, nd_mask);
     return after_launch("powerset_kernel");
 }

@@ -127,7 +127,9 @@ REC_GEN = 2
 # `.grad` right after backward() gets the join inside the backward.
 DEFER_JOIN = False
 _PENDING = []
-SIDE_SMS = 80        # SMs the side-stream GEMMs may fill: the recurrence kernel of the next layer needs 64 of the 148
+SIDE_SMS = 148       # SMs the side-stream weight-gradient GEMMs may fill.  All of them: the step is bound by its total work, not by
+# the recurrence chain (scripts/step_timeline.py) -- with 20 / 40 / 60 / 80 SMs the gradients pile up in front of the join at the
+# end of the backward (2.03 / 1.90 / 1.86 / 1.83 ms per step against 1.81 ms with 148, B = 8192)
 
 
 def join_pending():

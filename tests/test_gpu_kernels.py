@@ -309,6 +309,12 @@ GEMM_CASES = [
     (300, 200, 136, True, True, 1),        # ragged M / N / K tails
     (136, 72, 200, False, True, 1),        # MN-major A, K-major B
     (1000, 128, 1000, True, False, 3),     # K tail under split-K
+    (512, 192, 8192, False, False, 8),     # LSTM layer-0 weight gradient: N = 192 on the 256-column CTA-pair tile (B rows >= 192 zero-filled by TMA)
+    (512, 192, 1024, True, True, 1),       # the same width with K-major operands, one split (pair tile, row-major / staged epilogues)
+    (384, 448, 2048, False, True, 2),      # a last pair tile three quarters full behind a whole one, ragged M tile
+    (40000, 512, 256, True, False, 1),     # layer 2 data gradient, several tiles per CTA (double-buffered staging: 626 tiles on 148 CTAs)
+    (40000, 256, 32, True, False, 1),      # layer 3 data gradient, several tiles per CTA
+    (37000, 304, 200, True, True, 1),      # the same flow with ragged M / N / K (N = 304: a 48-column last tile, rows TMA can address)
 ]
 
 
@@ -334,6 +340,11 @@ def test_gemm_bf16_tcgen05(case, ops):
     want2 = torch.relu(want + bias.double()) * mask.double()
     err = (out - want2).abs().max() / want2.abs().max()
     assert err < 2e-2, f"bf16-out rel err {err:.3e}"
+    # bf16 output without a mask (the staged epilogue's other flow: buffers recycled on the TMA stores' read completion)
+    out = ops.gemm_bf16(Ad, Bd, Mr, N, K, ak, bk, bias=dev(bias), relu=True, split_k=split).cpu().double()
+    want3 = torch.relu(want + bias.double())
+    err = (out - want3).abs().max() / want3.abs().max()
+    assert err < 2e-2, f"bf16-out (no mask) rel err {err:.3e}"
 
 
 @pytest.mark.parametrize("M,N,K,f32", [(4096, 512, 64, False), (4096, 512, 128, False), (2048, 128, 512, True), (96, 64, 136, True)])
