@@ -309,8 +309,8 @@ def timed_steps(ds, kw, device, batch, steps, warmup=3, graph=True, prefetch=Fal
 
 def other_configs(args, ds, device):
     """Auxiliary, bounded measurements of the BASELINE configs the headline line does not cover (they are parity-test
-    cases, not bench lines), N = 1: the fp32 parity mode of the SAME train step (1e-5 arithmetic: SIMT fp32 GEMMs, exact-math
-    recurrence), config 0 (train_frame: FE + TeCNo, one video per step, eager / CUDA graph / stock torch layers) and config 5
+    cases, not bench lines), N = 1: the fp32 parity mode of the SAME train step (1e-5 arithmetic: six-product split-bf16 tcgen05 GEMMs for
+    the large products, fp32 FMA kernels and an exact-math recurrence for the rest), config 0 (train_frame: FE + TeCNo, one video per step, eager / CUDA graph / stock torch layers) and config 5
     (ensemble inference: frame model + window model + device-side fusion) on ONE rank's shard of the 100 k-video job
     (12 500 videos, ~62 GB table).  Failures are reported, never fatal."""
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
@@ -321,7 +321,9 @@ def other_configs(args, ds, device):
         flops = Bf * W * (5_029_888 + 3 * 2 * 714_752)        # FE train + LSTM fwd/bwd per (window, step), SURVEY section 8d
         out["train_window_fp32"] = {"value": Bf / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "batch": Bf, "launch": note,
                                     "gpu_launches_per_step": launches, "dtype": "f32",
-                                    "bound": "fp32 SIMT issue (no tensor cores: TF32 / bf16 products cannot hold the 1e-5 bar)",
+                                    "bound": "large products: tcgen05 on exactly split operands (x = h + m + l in bf16, six products, fp32 partial "
+                                             "sums every 12 k-blocks: closer to fp64 than the fp32 FMA chain); per-step recurrent products and "
+                                             "cells: fp32 FMA issue",
                                     "achieved_tflops": flops / (ms * 1e-3) / 1e12,
                                     "note": "same workload and step as the headline, exp_kwargs['precision'] = 'fp32'"}
     except Exception as e:

@@ -216,6 +216,13 @@ int b200med_relu_cast_f32_to_bf16(const float *x, void *y, int64_t n, void *stre
  * every row (reduction over columns); stack3 [3R,C]: blocks stacked (reduction over rows).  Either output may be NULL.  */
 int b200med_split_bf16x3(const float *x, void *row3, void *stack3, int64_t R, int32_t C, int32_t row_order,
                          int32_t stack_order, int32_t relu, void *stream);
+/* The fp32 mode's large products (FeatureExtractor layers MED/modeling/models.py:6-35 and the LSTM's x-part / gradient products,
+ * :135-210, held to 1e-5 against the reference) on the bf16 tensor cores: x = h + m + l EXACTLY (three bf16 terms), six
+ * products folded into one b200med_gemm_bf16 over a 6x longer reduction, small products first (the tensor core truncates when
+ * it adds into the fp32 accumulator; measured 1.4e-6 against fp64 at K = 2048, the fp32 FMA chain 6e-7).  role 0: blocks of
+ * a left operand (m, l, h, m, h, h); role 1: of a right operand (m, h, l, h, m, h).  row6 [R,6C] / stack6 [6R,C] as above.  */
+int b200med_split_bf16x6(const float *x, void *row6, void *stack6, int64_t R, int32_t C, int32_t role, int32_t relu,
+                         void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LSTM head (MED/modeling/models.py:135-210) in throughput mode: every time step is one b200med_gemm_bf16

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb200med.so")
+LIB_PATH = os.environ.get("B200MED_LIB") or os.path.join(_PKG, "libb200med.so")      # B200MED_LIB: another build of the same ABI (A/B timing)
 
 F32, BF16, F16 = 0, 1, 2
 
@@ -53,6 +53,7 @@ SIGNATURES = {
     "b200med_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_relu_cast_f32_to_bf16": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_split_bf16x3": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p]),
+    "b200med_split_bf16x6": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "b200med_cast_bf16_to_f32": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_lstm_pack_inputs": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "b200med_lstm_pack_parts": (C.c_int, [_p, _i32, _p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]),

@@ -291,6 +291,53 @@ __global__ void split_bf16x3_kernel(const float *__restrict__ x, __nv_bfloat16 *
         }
     }
 }
+// Three-way split x = h + m + l (h = bf16(x), m = bf16(x - h), l = bf16(x - h - m): exact, 8 + 8 + 8 mantissa bits) laid out for
+// ONE bf16 tensor-core GEMM over a 6x longer reduction that reproduces the fp32 product: blocks of a left operand
+// (m, l, h, m, h, h), of a right operand (m, h, l, h, m, h) -> products mm, lh, hl, mh, hm, hh (dropped: ml, lm, ll <= 2^-24).
+// Small products FIRST: the tensor core adds into its fp32 accumulator with truncation, so the order matters -- with the hh
+// block first every later (small) addition truncates against a full-size accumulator and the result is biased towards zero by
+// 2e-5 at K = 2048; with hh last the error is 1.4e-6 (fp32 FMA chain: 6e-7; scripts/split6_accuracy.py).
+template <int V>
+__global__ void split_bf16x6_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ row6, __nv_bfloat16 *__restrict__ stack6,
+                                    long long R, int C, int role, int relu) {
+    pdl_wait();
+    const long long n = R * C;
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < n; i += (long long)gridDim.x * blockDim.x * V) {
+        float v[V];
+        if (V == 4) {
+            const float4 q = *reinterpret_cast<const float4 *>(x + i);
+            v[0] = q.x; v[1 % V] = q.y; v[2 % V] = q.z; v[3 % V] = q.w;
+        } else {
+            v[0] = x[i];
+        }
+        __nv_bfloat16 h[V], m[V], l[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float a = relu ? fmaxf(v[k], 0.0f) : v[k];
+            h[k] = __float2bfloat16_rn(a);
+            const float r1 = a - __bfloat162float(h[k]);
+            m[k] = __float2bfloat16_rn(r1);
+            l[k] = __float2bfloat16_rn(r1 - __bfloat162float(m[k]));
+        }
+        const __nv_bfloat16 *blk[6];
+        if (role == 0) { blk[0] = m; blk[1] = l; blk[2] = h; blk[3] = m; blk[4] = h; blk[5] = h; }
+        else           { blk[0] = m; blk[1] = h; blk[2] = l; blk[3] = h; blk[4] = m; blk[5] = h; }
+        const long long r = i / C;
+        const int c = (int)(i - r * C);
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            if (V == 4) {
+                const uint2 u = make_uint2((uint32_t)__bfloat16_as_ushort(blk[b][0]) | ((uint32_t)__bfloat16_as_ushort(blk[b][1 % V]) << 16),
+                                           (uint32_t)__bfloat16_as_ushort(blk[b][2 % V]) | ((uint32_t)__bfloat16_as_ushort(blk[b][3 % V]) << 16));
+                if (row6) *reinterpret_cast<uint2 *>(row6 + r * 6 * C + (long long)b * C + c) = u;
+                if (stack6) *reinterpret_cast<uint2 *>(stack6 + b * n + i) = u;
+            } else {
+                if (row6) row6[r * 6 * C + (long long)b * C + c] = blk[b][0];
+                if (stack6) stack6[b * n + i] = blk[b][0];
+            }
+        }
+    }
+}
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, long long n) {
     pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -495,6 +542,20 @@ extern "C" __attribute__((visibility("default"))) int b200med_split_bf16x3(const
     launch_k(split_bf16x3_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
         x, reinterpret_cast<__nv_bfloat16 *>(row3), reinterpret_cast<__nv_bfloat16 *>(stack3), R, C, row_order, stack_order, relu);
     return after_launch("split_bf16x3_kernel");
+}
+extern "C" __attribute__((visibility("default"))) int b200med_split_bf16x6(const float *x, void *row6, void *stack6, int64_t R, int32_t C,
+                                                                           int32_t role, int32_t relu, void *stream) {
+    if (R <= 0 || C <= 0) return B200MED_OK;
+    B200MED_REQUIRE(x && (row6 || stack6), "null pointer");
+    B200MED_REQUIRE(role == 0 || role == 1, "role: 0 = left operand, 1 = right operand");
+    const long long n = R * (long long)C, cap = (long long)num_sms() * 16;
+    const bool vec = C % 4 == 0 && (uintptr_t)x % 16 == 0 && (!row6 || (uintptr_t)row6 % 8 == 0) && (!stack6 || (uintptr_t)stack6 % 8 == 0);
+    const long long blocks = ((vec ? n / 4 : n) + 255) / 256;
+    if (vec) launch_k(split_bf16x6_kernel<4>, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream,
+                      x, reinterpret_cast<__nv_bfloat16 *>(row6), reinterpret_cast<__nv_bfloat16 *>(stack6), R, C, role, relu);
+    else launch_k(split_bf16x6_kernel<1>, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream,
+                  x, reinterpret_cast<__nv_bfloat16 *>(row6), reinterpret_cast<__nv_bfloat16 *>(stack6), R, C, role, relu);
+    return after_launch("split_bf16x6_kernel");
 }
 extern "C" __attribute__((visibility("default"))) int b200med_cast_bf16_to_f32(const void *x, float *y, int64_t n, void *stream) {
     if (n <= 0) return B200MED_OK;

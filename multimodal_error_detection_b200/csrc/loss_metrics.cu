@@ -53,7 +53,6 @@ bce_logits_kernel(const float *__restrict__ logits, const float *__restrict__ la
                   float *__restrict__ preds, long long *__restrict__ counts, int accumulate,
                   unsigned int *ticket, double *partials) {
     pdl_wait();
-    __shared__ double sh[32];
     double l_sum = 0.0, c[4] = {0.0, 0.0, 0.0, 0.0};
     const float inv_b = grad_scale / (float)B;
     for (long long i = blockIdx.x * (long long)kLossThreads + threadIdx.x; i < B; i += (long long)gridDim.x * kLossThreads) {
@@ -69,20 +68,37 @@ bce_logits_kernel(const float *__restrict__ logits, const float *__restrict__ la
         const int yi = y > 0.5f ? 1 : 0, pi = (int)pred;
         c[yi * 2 + pi] += 1.0;
     }
+    // the five block sums in ONE pass (same shuffle trees as block_sum, so the same bits): one barrier instead of ten
     double vals[5] = {l_sum, c[0], c[1], c[2], c[3]};
+    __shared__ double shv[kLossThreads / 32][5];
+    __shared__ double part_sh[kMaxBlocks * 5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        const double t = block_sum(vals[k], sh);
-        if (threadIdx.x == 0) partials[blockIdx.x * kSlots + k] = t;
+        vals[k] = warp_sum(vals[k]);
+        if (lane == 0) shv[warp][k] = vals[k];
     }
-    if (publish_and_elect(ticket) && threadIdx.x == 0) {
-        double tot[5] = {0, 0, 0, 0, 0};
-        for (unsigned int b = 0; b < gridDim.x; ++b)
-            for (int k = 0; k < 5; ++k) tot[k] += partials[b * kSlots + k];
-        loss[0] = (float)(tot[0] / (double)B);
-        if (counts)
-            for (int k = 0; k < 4; ++k) counts[k] = (accumulate ? counts[k] : 0) + (long long)(tot[1 + k] + 0.5);
-        *ticket = 0;
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double t = warp_sum(lane < (kLossThreads >> 5) ? shv[lane][k] : 0.0);
+            if (lane == 0) partials[blockIdx.x * kSlots + k] = t;
+        }
+    }
+    if (publish_and_elect(ticket)) {
+        // the last block: all partials fetched in one round trip, then summed by one thread in ascending block order
+        for (int e = threadIdx.x; e < (int)gridDim.x * 5; e += kLossThreads) part_sh[e] = partials[(e / 5) * kSlots + e % 5];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot[5] = {0, 0, 0, 0, 0};
+            for (unsigned int b = 0; b < gridDim.x; ++b)
+                for (int k = 0; k < 5; ++k) tot[k] += part_sh[b * 5 + k];
+            loss[0] = (float)(tot[0] / (double)B);
+            if (counts)
+                for (int k = 0; k < 4; ++k) counts[k] = (accumulate ? counts[k] : 0) + (long long)(tot[1 + k] + 0.5);
+            *ticket = 0;
+        }
     }
 }
 

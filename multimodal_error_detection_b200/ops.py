@@ -6,6 +6,7 @@ handed CPU tensors -- the product path has no CPU implementation.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -62,7 +63,12 @@ class sm_limit:
 
 
 def workspace(nbytes: int, device, tag: str = "default", zero: bool = False) -> torch.Tensor:
-    """Grow-only scratch buffers keyed by (device, stream, tag); stream-ordered reuse is safe."""
+    """Grow-only scratch buffers keyed by (device, stream, tag); stream-ordered reuse is safe.  Under stream capture the
+    buffer is an ordinary temporary of the graph being recorded (allocated from ITS pool, never cached): a cached buffer
+    would tie later graphs to memory of a pool whose graph may be gone by the time they replay."""
+    if torch.cuda.is_current_stream_capturing():
+        n = max(int(nbytes), 256)
+        return torch.zeros(n, dtype=torch.uint8, device=device) if zero else torch.empty(n, dtype=torch.uint8, device=device)
     key = (str(device), torch.cuda.current_stream().cuda_stream, tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -209,6 +215,9 @@ def linear_fwd_f32(x, w, b, relu: bool, out=None):
     if w.shape[1] != K:
         raise ValueError(f"linear_fwd_f32: x has {K} columns, w has {w.shape[1]}")
     y = torch.empty(M, N, dtype=torch.float32, device=x.device) if out is None else _need(out, torch.float32, "out")
+    if _fp32_tc(M, N, K, 6 * K) and y.shape[-1] == N:
+        return gemm_bf16(split_bf16x6(x, 0)[0], split_bf16x6(w, 1)[0], M, N, 6 * K, True, True, bias=b, relu=relu, out=y,
+                         split_k=_fp32_tc_split(6 * K))
     call("b200med_linear_fwd_f32", _ptr(x), _ptr(w), _ptr(b), _ptr(y), M, N, K, int(relu), _stream())
     return y
 
@@ -218,8 +227,23 @@ def linear_bwd_data_f32(dy, w, relu_out=None):
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+    if _fp32_tc(M, K, N, 6 * N, K):
+        # dx [M, K] = dy [M, 6N] w6 [6N, K] (right operand stacked: reduction over its rows); ReLU mask = bf16(relu_out) > 0
+        mask = to_bf16(_need(relu_out, torch.float32, "relu_out")) if relu_out is not None else None
+        return gemm_bf16(split_bf16x6(dy, 0)[0], split_bf16x6(w, 1, False, True)[1], M, K, 6 * N, True, False, mask=mask, out=dx,
+                         split_k=_fp32_tc_split(6 * N))
     call("b200med_linear_bwd_data_f32", _ptr(dy), _ptr(w), _ptr(relu_out), _ptr(dx), M, N, K, _stream())
     return dx
+
+
+def _wgrad_fp32_tc(dy, x, relu_x: bool, dw):
+    """dW [N, K] = dy [M, N]^T x [M, K] as six stacked bf16 products (both operands MN-major, reduction over 6M rows,
+    deterministic split-K)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    a = split_bf16x6(dy, 0, False, True)[1]
+    b = split_bf16x6(x, 1, False, True, relu=relu_x)[1]
+    return gemm_bf16(a, b, N, K, 6 * M, a_kmajor=False, b_kmajor=False, split_k=max(gemm_split_k(N, K, 6 * M), _fp32_tc_split(6 * M)), out=dw)
 
 
 def linear_bwd_weight_f32(dy, x, want_bias=True):
@@ -228,6 +252,9 @@ def linear_bwd_weight_f32(dy, x, want_bias=True):
     K = x.shape[1]
     dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
     db = torch.empty(N, dtype=torch.float32, device=dy.device) if want_bias else None
+    if _fp32_tc(N, K, M, N, K):
+        dw = _wgrad_fp32_tc(dy, x, False, dw)
+        return dw, (colsum(dy) if want_bias else None)
     ws = workspace(_lib.load().b200med_linear_bwd_weight_ws_bytes(M, N, K), dy.device, "wgrad_f32")
     call("b200med_linear_bwd_weight_f32", _ptr(dy), _ptr(x), _ptr(dw), _ptr(db), M, N, K, 0, _ptr(ws), _stream())
     return dw, db
@@ -257,6 +284,10 @@ def linear_f32(x, w, b=None, flags=0, out=None):
     M, K = x.shape
     N = w.shape[0]
     y = torch.empty(M, N, dtype=torch.float32, device=x.device) if out is None else out
+    if not (flags & ~(GEMM_RELU | GEMM_RELU_A)) and _fp32_tc(M, N, K, 6 * K) and y.is_contiguous() and y.shape[-1] == N:
+        return gemm_bf16(split_bf16x6(_need(x, torch.float32, "x"), 0, relu=bool(flags & GEMM_RELU_A))[0],
+                         split_bf16x6(_need(w, torch.float32, "w"), 1)[0], M, N, 6 * K, True, True, bias=b,
+                         relu=bool(flags & GEMM_RELU), out=y.view(M, N), split_k=_fp32_tc_split(6 * K))
     return gemm_f32(x, w, y, M, N, K, K, 1, K, 1, N, bias=b, flags=flags)
 
 
@@ -265,6 +296,10 @@ def linear_dgrad_f32(dy, w, mask=None, out=None):
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty(M, K, dtype=torch.float32, device=dy.device) if out is None else out
+    if _fp32_tc(M, K, N, 6 * N, K) and dx.is_contiguous() and dx.shape[-1] == K:
+        mk = to_bf16(_need(mask, torch.float32, "mask")) if mask is not None else None
+        return gemm_bf16(split_bf16x6(_need(dy, torch.float32, "dy"), 0)[0], split_bf16x6(_need(w, torch.float32, "w"), 1, False, True)[1],
+                         M, K, 6 * N, True, False, mask=mk, out=dx.view(M, K), split_k=_fp32_tc_split(6 * N))
     return gemm_f32(dy, w, dx, M, K, N, N, 1, 1, K, K, mask=mask, ld_mask=K)
 
 
@@ -273,6 +308,8 @@ def linear_wgrad_f32(dy, x, relu_x=False):
     M, N = dy.shape
     K = x.shape[1]
     dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+    if _fp32_tc(N, K, M, N, K):
+        return _wgrad_fp32_tc(_need(dy, torch.float32, "dy"), _need(x, torch.float32, "x"), relu_x, dw)
     return gemm_f32(dy, x, dw, N, K, M, 1, N, 1, K, K, flags=GEMM_SPLIT | (GEMM_RELU_B if relu_x else 0))
 
 
@@ -422,6 +459,39 @@ def split_bf16x3(x: torch.Tensor, row_order=None, stack_order=None, relu: bool =
     call("b200med_split_bf16x3", _ptr(x), _ptr(row3), _ptr(stack3), R, Cn, int(row_order or 0), int(stack_order or 0), int(bool(relu)),
          _stream())
     return row3, stack3
+
+
+def split_bf16x6(x: torch.Tensor, role: int, want_row: bool = True, want_stack: bool = False, relu: bool = False):
+    """(row6 [R, 6C], stack6 [6R, C]) of the exact three-way bf16 split of x [R, C] f32 (b200med_split_bf16x6); role 0 = left
+    operand, 1 = right operand of the product."""
+    x = _need(x, torch.float32, "x")
+    R, Cn = x.shape
+    row6 = torch.empty(R, 6 * Cn, dtype=torch.bfloat16, device=x.device) if want_row else None
+    stack6 = torch.empty(6 * R, Cn, dtype=torch.bfloat16, device=x.device) if want_stack else None
+    call("b200med_split_bf16x6", _ptr(x), _ptr(row6), _ptr(stack6), R, Cn, int(role), int(bool(relu)), _stream())
+    return row6, stack6
+
+
+# The fp32 mode's LARGE products run on the bf16 tensor cores as six products of exactly split operands (fp32-like: 1.4e-6
+# against fp64 at K = 2048, scripts/split6_accuracy.py); below this many flop the fp32 FMA kernels of csrc/gemm_f32.cu are as
+# fast as split + GEMM.  0 switches the route off (B200MED_FP32_TC=0).
+FP32_TC_MIN_FLOP = 0.0 if os.environ.get("B200MED_FP32_TC", "1") == "0" else 1.0e9
+
+
+FP32_TC_KB_PER_SPLIT = 12      # k-blocks (of 64) one accumulator takes before it is rounded into the fp32 partial sum
+
+
+def _fp32_tc_split(k6: int) -> int:
+    """split_k of a six-product GEMM over a reduction of k6: the tensor core TRUNCATES when it adds into its fp32 accumulator,
+    so a long reduction drifts towards zero (1.4e-6 at 6 x 2048; the fp32 FMA chain 5.7e-7); partial sums of <= 12 k-blocks
+    added in fp32 by the fixed-order split-K reduction bring it to 4e-7 (scripts/split6_accuracy.py)."""
+    nkb = (k6 + 63) // 64
+    return max(1, min(256, (nkb + FP32_TC_KB_PER_SPLIT - 1) // FP32_TC_KB_PER_SPLIT))
+
+
+def _fp32_tc(M: int, N: int, K: int, *lds: int) -> bool:
+    return (FP32_TC_MIN_FLOP > 0 and 2.0 * M * N * K >= FP32_TC_MIN_FLOP and all(ld % 8 == 0 for ld in lds)
+            and torch.cuda.is_available() and has_tcgen05())
 
 
 def to_f32(x: torch.Tensor) -> torch.Tensor:

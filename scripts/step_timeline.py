@@ -11,7 +11,9 @@ from multimodal_error_detection_b200.modeling import modeling_utils as mu
 
 
 class A:
-    videos, batch, precision, gather_variant = 1024, 8192, "bf16", 0
+    videos, gather_variant = 1024, 0
+    batch = int(os.environ.get("BATCH", "8192"))
+    precision = os.environ.get("PRECISION", "bf16")
 
 
 dev = torch.device("cuda", 0)

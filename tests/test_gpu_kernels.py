@@ -588,3 +588,62 @@ def test_lstm_pack_parts_kernel(Ca, Cb, stat_rows, B, W):
     want[:, :B, Ca + Cb:hoff] = 0.0
     want[0, :B, hoff:] = 0.0                                                           # h_{-1}; later steps keep the sentinel
     assert torch.equal(A0.view(torch.int16), want.to(torch.bfloat16).view(torch.int16))
+
+
+# ------------------------------------------------------------------------------------------- fp32 products on the tensor cores
+def test_split_bf16x6_is_exact_and_laid_out_for_both_roles(ops):
+    """x = h + m + l exactly (three bf16 terms); blocks (m, l, h, m, h, h) for a left operand, (m, h, l, h, m, h) for a right
+    one, side by side in every row (row6) or stacked (stack6); relu folds max(., 0) in front of the split."""
+    g = torch.Generator().manual_seed(6)
+    for R, Cn in ((37, 24), (5, 7)):                    # vectorised and scalar instantiation
+        x = torch.randn(R, Cn, generator=g) * torch.logspace(-6, 6, Cn)[None, :]
+        for relu in (False, True):
+            xr = x.clamp_min(0) if relu else x
+            h = xr.to(torch.bfloat16); m = (xr - h.float()).to(torch.bfloat16); l = (xr - h.float() - m.float()).to(torch.bfloat16)
+            assert torch.equal(h.float() + m.float() + l.float(), xr)
+            for role, order in ((0, (m, l, h, m, h, h)), (1, (m, h, l, h, m, h))):
+                row6, stack6 = ops.split_bf16x6(dev(x), role, True, True, relu=relu)
+                assert torch.equal(row6.cpu().view(torch.int16), torch.cat(order, dim=1).view(torch.int16)), (R, Cn, relu, role)
+                assert torch.equal(stack6.cpu().view(torch.int16), torch.cat(order, dim=0).view(torch.int16)), (R, Cn, relu, role)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 2048), (8192, 256, 512), (16384, 512, 128)])
+def test_fp32_linear_ops_on_the_tensor_cores(M, N, K, ops):
+    """The fp32 mode's large products (forward, data gradient with ReLU mask, weight + bias gradient) take the six-product
+    bf16 route (ops._fp32_tc): held against fp64 at 5e-6 norm-wise -- the fp32 FMA kernels of the same ops (route switched off)
+    sit at ~6e-7 -- and bit-reproducible run to run."""
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    assert ops._fp32_tc(M, N, K, 6 * K) and ops._fp32_tc(M, K, N, 6 * N, K) and ops._fp32_tc(N, K, M, N, K)
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).clamp_min(0)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    rel = lambda a, r: float((a.double().cpu() - r).norm() / r.norm())
+    y64 = torch.relu(x.double() @ w.double().T + b.double())
+    dx64 = (dy.double() @ w.double()) * (x.double() > 0)
+    dw64, db64 = dy.double().T @ x.double(), dy.double().sum(0)
+    res = {}
+    for tc in (True, False):
+        old = ops.FP32_TC_MIN_FLOP
+        ops.FP32_TC_MIN_FLOP = old if tc else 0.0
+        try:
+            y = ops.linear_fwd_f32(dev(x), dev(w), dev(b), relu=True)
+            y2 = ops.linear_f32(dev(x), dev(w), dev(b), ops.GEMM_RELU)
+            dx = ops.linear_bwd_data_f32(dev(dy), dev(w), relu_out=dev(x))
+            dx2 = ops.linear_dgrad_f32(dev(dy), dev(w), mask=dev(x))
+            dw, db = ops.linear_bwd_weight_f32(dev(dy), dev(x))
+            dw2 = ops.linear_wgrad_f32(dev(dy), dev(x), relu_x=True)
+        finally:
+            ops.FP32_TC_MIN_FLOP = old
+        res[tc] = (y, dx, dw)
+        bar = 5e-6 if tc else 2e-6
+        assert rel(y, y64) < bar and rel(y2, y64) < bar, (tc, rel(y, y64))
+        assert rel(dx, dx64) < bar and rel(dx2, dx64) < bar, (tc, rel(dx, dx64))
+        assert rel(dw, dw64) < bar and rel(dw2, dw64) < bar, (tc, rel(dw, dw64))
+        assert rel(db, db64) < 2e-6
+        if tc:
+            assert torch.equal(y, y2) and torch.equal(dx, dx2) and torch.equal(dw, dw2)
+    dw_again, _ = ops.linear_bwd_weight_f32(dev(dy), dev(x))
+    assert torch.equal(dw_again, res[True][2])

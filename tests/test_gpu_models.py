@@ -616,6 +616,85 @@ def test_bench_step_bf16_B8192_vs_fp32_oracle():
         json.dump({"loss": lv, "oracle_loss": ov, "ours": errs, "torch_autocast_bf16": aerrs, "cosine_ours": cos}, f)
 
 
+def test_fp32_step_tensor_core_route_vs_oracle():
+    """The fp32 mode at a batch whose products are large enough for the tensor-core route (ops._fp32_tc: exactly split
+    operands, six bf16 products, fp32 partial sums) -- bench.py's objects at B = 512, W = 16 (8192 rows through the
+    FeatureExtractor) -- one train step (dropout off) against the ORACLE on the same batch.  Loss and train-mode logits are
+    held to the small-batch bars against the fp32 oracle (1e-5 / 2e-5).  The GRADIENTS of this network at this batch size are
+    ill-conditioned (BatchNorm backward over 512 random-label rows cancels to a fraction of its terms: the fp32 oracle itself
+    is ~5e-3 away from its own fp64 run), so they are held against the FP64 oracle, relative to what fp32 arithmetic leaves
+    there: no parameter's gradient may be further from fp64 than 2 x the worse of (torch fp32 on the CPU, this library's fp32
+    FMA kernels) + 5e-5."""
+    import argparse
+    import copy
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from multimodal_error_detection_b200 import lstm_stack, ops
+    from multimodal_error_detection_b200.modeling import modeling_utils as mu
+    from oracle import loops, nets
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    B, W = 512, bench.W
+    assert ops._fp32_tc(B * W, 512, 2048, 6 * 2048) and ops._fp32_tc(512, 2048, B * W, 512, 2048)
+    dev = torch.device(DEV)
+    ds, _ = bench.build_gpu_job(argparse.Namespace(videos=24), 0, dev)
+    assert len(ds) >= B
+    kw = bench.exp_kwargs(B, "fp32")
+    fe, model, crit, opt, sched = mu.define_model_objects(kw, cases.IN_FEATURES, dev, ds.binary_error_distribution, W)
+    ofe, omodel, ocrit, _, _ = nets.build_objects(kw, cases.IN_FEATURES, ds.binary_error_distribution, W)
+    _no_dropout(model, fe)
+    nets.disable_dropout(omodel, ofe)
+    for m in (fe, model, ofe, omodel):
+        m.train()
+    dfe, dmodel, dcrit = copy.deepcopy(ofe).double(), copy.deepcopy(omodel).double(), copy.deepcopy(ocrit).double()
+    idx = torch.randperm(len(ds), generator=torch.Generator().manual_seed(42))[:B].to(dev)
+    y = mu.define_error_labels(ds.e_labels_data.index_select(0, idx), kw).float()
+    img32, kin32 = ds.gather_batch(idx, image_dtype=torch.float32, exact=True)
+    oout = omodel(loops.fuse_inputs(img32.cpu(), kin32.cpu(), ofe, kw))
+    oloss, _ = loops.loss_fn(oout, y.cpu(), ocrit, "window")
+    oloss.backward()
+    dout = dmodel(loops.fuse_inputs(img32.cpu().double(), kin32.cpu().double(), dfe, kw))
+    dloss, _ = loops.loss_fn(dout, y.cpu().double(), dcrit, "window")
+    dloss.backward()
+    ov = float(oloss.detach())
+    names = [f"{pre}.{k}" for pre, mod in (("fe", dfe), ("model", dmodel)) for k, _ in mod.named_parameters()]
+    g64 = [q.grad.reshape(-1) for mod in (dfe, dmodel) for q in mod.parameters()]
+    gmax = max(float(g.norm()) for g in g64)
+
+    def errors(grads):
+        return {k: float((g.double().cpu().reshape(-1) - r).norm() / max(float(r.norm()), 1e-4 * gmax)) for k, g, r in zip(names, grads, g64)}
+
+    def step():
+        n0 = ops._lib.launch_count()
+        out = model(mu.define_inputs(img32, kin32, fe, kw, dev))
+        loss, _ = mu.compute_loss(out, y, crit, "window")
+        opt.zero_grad(); loss.backward()
+        lstm_stack.join_pending()
+        torch.cuda.synchronize()
+        assert ops._lib.launch_count() > n0
+        return (float(loss.detach()), rel(out.detach().cpu().numpy().reshape(-1), oout.detach().numpy().reshape(-1)),
+                errors([p.grad.detach() for mod in (fe, model) for p in mod.parameters()]))
+
+    lv, lerr, e_tc = step()
+    old = ops.FP32_TC_MIN_FLOP          # the same step on the fp32 FMA kernels (route switched off)
+    ops.FP32_TC_MIN_FLOP = 0.0
+    try:
+        lv0, lerr0, e_fma = step()
+    finally:
+        ops.FP32_TC_MIN_FLOP = old
+    e_ref = errors([q.grad for mod in (ofe, omodel) for q in mod.parameters()])
+    worst = max(e_tc, key=e_tc.get)
+    print("fp32 step, B = 512: loss (tensor-core route, FMA kernels, fp32 oracle, fp64 oracle)", lv, lv0, ov, float(dloss.detach()),
+          "logits vs fp32 oracle", lerr, lerr0, "| gradient error vs fp64, worst parameter", worst,
+          "tensor-core route %.3g, FMA kernels %.3g, torch fp32 %.3g" % (e_tc[worst], e_fma[worst], e_ref[worst]),
+          "| medians %.3g %.3g %.3g" % tuple(float(np.median(list(e.values()))) for e in (e_tc, e_fma, e_ref)))
+    assert abs(lv - ov) <= 1e-5 * abs(ov), (lv, ov)
+    assert lerr < 2e-5, lerr
+    for k in names:
+        assert e_tc[k] <= 2.0 * max(e_ref[k], e_fma[k]) + 5e-5, (k, e_tc[k], e_fma[k], e_ref[k])
+
+
 def test_lstm_rec_gen2_matches_gen1_with_dropout():
     """The two generations of the persistent recurrence share the dropout counter hash and the saved-tensor layouts: with the
     same seed they draw the SAME masks, so last hidden state, input gradient and every weight gradient agree to bf16 noise
