@@ -278,7 +278,7 @@ def test_split_k_choice_fills_whole_waves(built_lib):
     lib.b200med_gemm_bf16_pick_split.restype = C.c_int32
     lib.b200med_gemm_bf16_pick_split.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32]
     rows = 8192 * 16
-    for M, N, pair in ((512, 2048, True), (512, 256, True), (256, 512, True), (512, 192, False), (32, 256, False)):
+    for M, N, pair in ((512, 2048, True), (512, 256, True), (256, 512, True), (512, 192, True), (32, 256, False)):      # N = 192: three quarters of a pair tile
         s = lib.b200med_gemm_bf16_pick_split(M, N, rows, 0)
         assert 1 <= s <= 160 and (rows // 64) // s >= 8, (M, N, s)
         bn = 256 if N >= 256 else 128 if N > 64 else 64
@@ -289,6 +289,23 @@ def test_split_k_choice_fills_whole_waves(built_lib):
         assert items / (waves * units) >= 0.85 or items <= units, (M, N, s, items, waves)
     assert lib.b200med_gemm_bf16_pick_split(512, 2048, rows, 0) == 9
     assert lib.b200med_gemm_bf16_pick_split(512, 2048, 512, 0) == 1          # short K: no split
+
+
+def test_fp32_tensor_core_route_host_logic(built_lib):
+    """ops._fp32_tc_split: one accumulation of the six-product GEMM never runs over more than 12 k-blocks (the tensor core
+    truncates when it adds into the fp32 accumulator); ops._fp32_tc: without a GPU there is no such route (and no fallback:
+    the fp32 ops themselves raise on CPU tensors)."""
+    from multimodal_error_detection_b200 import ops
+    assert ops._fp32_tc_split(6 * 2048) == 16 and ops._fp32_tc_split(6 * 512) == 4 and ops._fp32_tc_split(6 * 32) == 1
+    for k6 in (64, 700, 6 * 58, 6 * 2048, 6 * 131072):
+        s = ops._fp32_tc_split(k6)
+        assert 1 <= s <= 256 and (s == 256 or -(-(-(-k6 // 64)) // s) <= ops.FP32_TC_KB_PER_SPLIT), (k6, s)
+    if not torch.cuda.is_available():
+        assert not ops._fp32_tc(32768, 512, 2048, 6 * 2048)
+        with pytest.raises(RuntimeError):
+            ops.linear_fwd_f32(torch.zeros(4, 8), torch.zeros(2, 8), None, relu=False)
+    assert not ops._fp32_tc(64, 64, 64, 384)                    # small products stay on the fp32 FMA kernels
+    assert not ops._fp32_tc(32768, 512, 58, 6 * 58)             # 6 x 58 elements per row: not a multiple of 16 bytes
 
 
 def test_epoch_scores_equal_the_per_batch_scores():
