@@ -300,6 +300,44 @@ int b200med_bn_fwd(const float *x, int64_t M, int32_t C, const float *gamma, con
 int b200med_bn_bwd(const float *dy, const float *x, int64_t M, int32_t C, const float *gamma, const float *save_mean,
                    const float *save_rstd, int32_t relu_mask, float *dx, float *dgamma, float *dbeta, void *workspace,
                    void *stream);
+/* The Linear / ReLU / BatchNorm1d tail of the window heads as THREE kernels per direction (csrc/mlp_tail.cu; replaces, for
+ * hidden widths of 64 / 128 / 256, the per-layer GEMM + BatchNorm launches above: models.py:166-186, 204-210, the
+ * ReLU -> Linear(128, 256) -> ReLU -> BatchNorm1d -> Linear(256, 64) -> ReLU -> BatchNorm1d -> Linear(64, C) of the LSTM head).
+ * One CTA owns 64 batch rows; BatchNorm statistics travel between consecutive kernels as per-CTA partials
+ * (b200med_tail_slabs(M) slabs) and are finalized redundantly, in a fixed order and in double, by every CTA of the consumer.
+ * fp32 FMA arithmetic in both precision modes.  All matrix pointers must be 16-byte aligned.
+ *   b200med_tail_supported(K, N, kind): kind 0 = forward hidden layer K -> N, 1 = its backward (K = the layer's outputs,
+ *   N = its inputs), 3 = kind 1 for the LAST hidden layer, 2 = output layer K -> N (N <= 8).                          */
+int32_t b200med_tail_supported(int32_t K, int32_t N, int32_t kind);
+int64_t b200med_tail_slabs(int64_t M);
+/* a [M, N] = relu(in' W^T + b) with in' = relu(in) (relu_in), or BatchNorm(in) (bn_mode 1: batch statistics from bn_part
+ * [slabs][3][K] = (n, mean, M2) written by the producing call, save_mean / save_rstd OUT, running statistics and
+ * *num_batches_tracked updated like nn.BatchNorm1d; bn_mode 2: running statistics), or in (bn_mode 0, relu_in 0).
+ * y [M, K] = in' OUT when bn_mode != 0 (may be NULL).  part [slabs][3][N] OUT (NULL: not wanted) for the next call.   */
+int b200med_tail_fwd_hidden(const float *in, int64_t M, int32_t K, int32_t relu_in, int32_t bn_mode, const float *bn_part,
+                            const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                            float *running_var, int64_t *num_batches_tracked, float *save_mean, float *save_rstd, float *y,
+                            const float *W, const float *b, int32_t N, float *a, float *part, void *stream);
+/* The output layer: out [M, C] = in' Wl^T + bl, C <= 8, in' as above.                                                  */
+int b200med_tail_fwd_out(const float *in, int64_t M, int32_t K, int32_t relu_in, int32_t bn_mode, const float *bn_part,
+                         const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                         float *running_var, int64_t *num_batches_tracked, float *save_mean, float *save_rstd, float *y,
+                         const float *W, const float *b, int32_t C, float *out, void *stream);
+/* Backward of the output layer into the last BatchNorm: part [slabs][2][N] = (sum g2, sum g2 xhat), g2 = g [M, C] Wl [C, N],
+ * xhat = (a - save_mean) save_rstd with a [M, N] that BatchNorm's input.                                                */
+int b200med_tail_bwd_out(const float *g, int32_t C, const float *Wl, const float *a, int64_t M, int32_t N,
+                         const float *save_mean, const float *save_rstd, float *part, void *stream);
+/* Backward of one hidden layer  in [M, N] -> Linear(W [K, N]) -> ReLU (= a [M, K]) -> BatchNorm:
+ *   dz [M, K] = (a > 0) BatchNorm'(dy) OUT (the Linear layer's pre-activation gradient: its weight / bias gradients are
+ *   dz^T in' and the column sums of dz), dgamma / dbeta [K] OUT (may be NULL), dx [M, N] = dz W OUT, zeroed where
+ *   relu_mask [M, N] <= 0 when given.  dy [M, K], or NULL for the LAST hidden layer (dy = g [M, C] Wl [C, K]); `part` from
+ *   b200med_tail_bwd_out / the previous call.  a_prev [M, N] != NULL (the BatchNorm in front of this layer, input a_prev,
+ *   mean_prev / rstd_prev): part_prev [slabs][2][N] OUT for the next call.                                             */
+int b200med_tail_bwd_hidden(const float *dy, const float *g, int32_t C, const float *Wl, const float *a, int64_t M, int32_t K,
+                            const float *part, const float *gamma, const float *save_mean, const float *save_rstd, float *dz,
+                            float *dgamma, float *dbeta, const float *W, int32_t N, float *dx, const float *a_prev,
+                            const float *mean_prev, const float *rstd_prev, float *part_prev, const float *relu_mask,
+                            void *stream);
 /* MaxPool1d(2, 2) + Dropout(p) over time-major rows: z [B*L, C] with Lc valid steps per window -> p [B*(Lc/2), C];
  * backward: dz [2 + B*L, C] -- two zero rows, then the gradient rows (to the first maximum of each pair, zero elsewhere);
  * the zero rows are what the convolution's data-gradient product reads for steps l < 2.  models.py:67-99.       */

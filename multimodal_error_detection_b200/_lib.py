@@ -76,6 +76,13 @@ SIGNATURES = {
     "b200med_bn_ws_bytes": (_i64, [_i64, _i32]),
     "b200med_bn_fwd": (C.c_int, [_p, _i64, _i32, _p, _p, _f, _f, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
     "b200med_bn_bwd": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _i32, _p, _p, _p, _p, _p]),
+    "b200med_tail_supported": (_i32, [_i32, _i32, _i32]),
+    "b200med_tail_slabs": (_i64, [_i64]),
+    "b200med_tail_fwd_hidden": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p]),
+    "b200med_tail_fwd_out": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p]),
+    "b200med_tail_bwd_out": (C.c_int, [_p, _i32, _p, _p, _i64, _i32, _p, _p, _p, _p]),
+    "b200med_tail_bwd_hidden": (C.c_int, [_p, _p, _i32, _p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p,
+                                          _p]),
     "b200med_pool_drop_fwd": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _f, _p, C.c_uint64, _p]),
     "b200med_pool_drop_bwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _f, _p, C.c_uint64, _p]),
     "b200med_conv_pack": (C.c_int, [_p, _p, _p, _i32, _i32, _p]),

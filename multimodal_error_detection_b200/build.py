@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libb200med.so")
 SOURCES = ["api_common.cu", "window_index.cu", "gather_norm.cu", "gather_gemm.cu", "gemm_f32.cu", "gemm_tcgen05.cu",
-           "loss_metrics.cu", "metrics.cu", "adam.cu", "ensemble.cu", "lstm.cu", "lstm_rec.cu", "lstm_rec2.cu", "tcn.cu", "head.cu", "peer_exchange.cu"]
+           "loss_metrics.cu", "metrics.cu", "adam.cu", "ensemble.cu", "lstm.cu", "lstm_rec.cu", "lstm_rec2.cu", "tcn.cu", "head.cu", "mlp_tail.cu", "peer_exchange.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

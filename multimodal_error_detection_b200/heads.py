@@ -14,6 +14,8 @@ parity bar of the fp32 mode holds for them by construction.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -44,6 +46,9 @@ class MLPTailFunction(torch.autograd.Function):
         x = x.contiguous().float()
         B = x.shape[0]
         tc = [precision == "bf16" and ops.has_tcgen05() and _tc_ok(t[7 * i]) for i in range(n_hidden)]
+        if _fused_ok(x, t, n_hidden):
+            return MLPTailFunction._forward_fused(ctx, x, relu_in, training, bn_cfg, tc, t)
+        ctx.fused = False
         a_in, acts, ys, stats, extra = x, [], [], [], []
         # the split copies of the WEIGHTS do not depend on the activations: they are made on the side stream while the first
         # layers run (a launch on the critical path costs ~5 us inside the replayed step, whatever its size)
@@ -90,10 +95,97 @@ class MLPTailFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    def _forward_fused(ctx, x, relu_in, training, bn_cfg, tc, t):
+        """Three kernels (csrc/mlp_tail.cu): every hidden layer's call applies the BatchNorm in front of it while it loads its
+        input tile (statistics finalized from the previous call's per-CTA partials) and leaves the partials of its own output;
+        the output layer's call does the same for the last BatchNorm.  fp32 FMA arithmetic in both precision modes."""
+        n_hidden = len(bn_cfg)
+        acts, ys, stats = [], [], []
+        cur, bn = x, None
+        for i in range(n_hidden):
+            W, b, gamma, beta, rm, rv, nbt = t[7 * i:7 * i + 7]
+            a, part, y, sm, sr = ops.tail_fwd_hidden(cur, W.detach(), b.detach(), relu_in=(i == 0 and relu_in), bn=bn,
+                                                     training=training, want_part=training)
+            if i > 0:
+                ys.append(y); stats.append((sm, sr))
+            acts.append(a)
+            eps, mom = bn_cfg[i]
+            if mom is None:          # nn.BatchNorm1d(momentum=None): cumulative moving average
+                mom = 1.0 / float(nbt.item() + 1)
+            bn = (part, gamma.detach(), beta.detach(), eps, mom, rm, rv, nbt)
+            cur = a
+        Wl, bl = t[7 * n_hidden], t[7 * n_hidden + 1]
+        out, y, sm, sr = ops.tail_fwd_out(cur, Wl.detach(), bl.detach(), relu_in=False, bn=bn, training=training)
+        ys.append(y); stats.append((sm, sr))
+        ctx.relu_in, ctx.training, ctx.n_hidden, ctx.tc, ctx.fused = relu_in, training, n_hidden, tc, True
+        if training:
+            saved = [x] + acts + ys + [s_ for st in stats for s_ in st]
+            ctx.save_for_backward(*saved, *[t[7 * i] for i in range(n_hidden)], *[t[7 * i + 2] for i in range(n_hidden)], Wl)
+        return out
+
+    @staticmethod
+    def _backward_fused(ctx, dout):
+        n, tc = ctx.n_hidden, ctx.tc
+        sv = ctx.saved_tensors
+        x, acts, ys = sv[0], sv[1:1 + n], sv[1 + n:1 + 2 * n]
+        stats = sv[1 + 2 * n:1 + 4 * n]
+        Ws, gammas, Wl = sv[1 + 4 * n:1 + 5 * n], sv[1 + 5 * n:1 + 6 * n], sv[1 + 6 * n]
+        grads = [None] * (7 * n + 2)
+        g = dout.contiguous().float()
+        B = g.shape[0]
+        from . import lstm_stack
+        main, side = torch.cuda.current_stream(), _side(g.device)
+        keep, side_grads = [], []
+
+        def on_side(fn, *reads):
+            keep.extend(reads)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.sm_limit(TAIL_SIDE_SMS):
+                out = fn()
+            side_grads.append(out)
+            return out
+
+        def wgrad(dz, inp, relu_x, use_tc):
+            if not use_tc:
+                return ops.linear_wgrad_f32(dz, inp, relu_x=relu_x)
+            # dW [N, K] = dz^T in over the (3x stacked) batch rows as one split-bf16 product on the tcgen05 GEMM
+            N, K = dz.shape[1], inp.shape[1]
+            dz_stack = ops.split_bf16x3(dz, None, 0)[1]
+            x_stack = ops.split_bf16x3(inp, None, 1, relu=relu_x)[1]
+            return ops.gemm_bf16(dz_stack, x_stack, N, K, 3 * B, a_kmajor=False, b_kmajor=False, out_dtype=torch.float32,
+                                 split_k=ops.gemm_split_k(N, K, 3 * B))
+
+        grads[7 * n] = on_side(lambda: ops.linear_wgrad_f32(g, ys[-1]), g, ys[-1])
+        grads[7 * n + 1] = on_side(lambda: ops.colsum(g), g)
+        part = ops.tail_bwd_out(g, Wl, acts[-1], stats[2 * (n - 1)], stats[2 * (n - 1) + 1])
+        dy = None
+        for i in reversed(range(n)):
+            inp = ys[i - 1] if i > 0 else x
+            prev = (acts[i - 1], stats[2 * (i - 1)], stats[2 * (i - 1) + 1]) if i > 0 else None
+            first = dy is None
+            dz, dx, dgamma, dbeta, part = ops.tail_bwd_hidden(
+                dy, g if first else None, Wl if first else None, acts[i], part, gammas[i], stats[2 * i], stats[2 * i + 1], Ws[i],
+                prev=prev, relu_mask=x if (i == 0 and ctx.relu_in) else None)
+            grads[7 * i + 2], grads[7 * i + 3] = dgamma, dbeta
+            grads[7 * i + 1] = on_side(lambda dz=dz: ops.colsum(dz), dz)
+            grads[7 * i] = on_side(lambda dz=dz, inp=inp, i=i: wgrad(dz, inp, i == 0 and ctx.relu_in, tc[i]), dz, inp)
+            dy = dx
+        if lstm_stack.DEFER_JOIN:
+            lstm_stack._PENDING.append((side, keep))      # joined by the gradient consumer (lstm_stack.join_pending)
+        else:
+            main.wait_stream(side)
+            keep = []
+        for sg in side_grads:
+            sg.record_stream(main)
+        return (dy if ctx.needs_input_grad[0] else None, None, None, None, None, *grads)
+
+    @staticmethod
     def backward(ctx, dout):
         if not ctx.training:
             raise NotImplementedError("b200med: backward through the head in eval mode (running BatchNorm statistics) is not "
                                       "part of the reference's train / validation loops")
+        if ctx.fused:
+            return MLPTailFunction._backward_fused(ctx, dout)
         n, tc = ctx.n_hidden, ctx.tc
         sv = ctx.saved_tensors
         x, acts, ys = sv[0], sv[1:1 + n], sv[1 + n:1 + 2 * n]
@@ -159,6 +251,28 @@ class MLPTailFunction(torch.autograd.Function):
         for sg in side_grads:
             sg.record_stream(main)                        # allocated on the side stream, consumed on the main one
         return (g if need_dx else None, None, None, None, None, *grads)
+
+
+FUSED_TAIL = os.environ.get("B200MED_FUSED_TAIL", "1") != "0"      # A/B switch (scripts): 0 = the layer-at-a-time kernels
+
+
+def _fused_ok(x, t, n_hidden: int) -> bool:
+    """The three-kernel tail of csrc/mlp_tail.cu serves hidden widths of 64 / 128 / 256 whose weights + one 64-row tile fit the
+    shared memory of an SM, and an output layer of <= 8 columns (the LSTM head: 128 -> 256 -> 64 -> C); other shapes (the CNN
+    head's 256 -> 32 -> 16 -> C) run layer by layer."""
+    if not FUSED_TAIL or n_hidden < 1:
+        return False
+    widths = [t[7 * i].shape[0] for i in range(n_hidden)]
+    ins = [x.shape[1]] + widths[:-1]
+    for i in range(n_hidden):
+        if t[7 * i].shape[1] != ins[i] or not ops.tail_supported(ins[i], widths[i], 0):
+            return False
+        if not ops.tail_supported(widths[i], ins[i], 3 if i == n_hidden - 1 else 1):
+            return False
+        if t[7 * i].data_ptr() % 16 or not t[7 * i].is_contiguous() or t[7 * i + 2] is None:
+            return False
+    Wl = t[7 * n_hidden]
+    return ops.tail_supported(widths[-1], Wl.shape[0], 2) and Wl.is_contiguous() and x.data_ptr() % 16 == 0
 
 
 TAIL_SIDE_SMS = 32       # SMs the tail's side-stream gradient kernels may fill (they are a few tiles each)

@@ -340,6 +340,88 @@ def bn_bwd(dy, x, gamma, save_mean, save_rstd, relu_mask=False, want_affine=True
     return dx, dg, db
 
 
+# ---- the heads' Linear / ReLU / BatchNorm tail as three kernels per direction (csrc/mlp_tail.cu)
+def tail_supported(K: int, N: int, kind: int) -> bool:
+    return bool(_lib.load().b200med_tail_supported(int(K), int(N), int(kind)))
+
+
+def _tail_part(M: int, rows: int, width: int, device) -> torch.Tensor:
+    return torch.empty(int(_lib.load().b200med_tail_slabs(M)) * rows * width, dtype=torch.float32, device=device)
+
+
+def _tail_bn_args(bn, training: bool):
+    """bn = None (no BatchNorm in front) or (part, gamma, beta, eps, momentum, running_mean, running_var, num_batches)."""
+    if bn is None:
+        return 0, None, None, None, 0.0, 0.0, None, None, None
+    part, gamma, beta, eps, mom, rm, rv, nbt = bn
+    return (1 if training else 2), part, gamma, beta, float(eps), float(mom or 0.0), rm, rv, nbt
+
+
+def tail_fwd_hidden(x, W, b, relu_in=False, bn=None, training=True, want_part=True):
+    """One hidden layer of the tail: a = relu(in' W^T + b); returns (a, part, y, save_mean, save_rstd) -- y = in' = BatchNorm(x)
+    and the saved statistics when ``bn`` is given (training), part = the statistics partials of a for the next call."""
+    x = _need(x, torch.float32, "x")
+    M, K = x.shape
+    N = W.shape[0]
+    dev = x.device
+    a = torch.empty(M, N, dtype=torch.float32, device=dev)
+    part = _tail_part(M, 3, N, dev) if want_part else None
+    mode, bpart, gamma, beta, eps, mom, rm, rv, nbt = _tail_bn_args(bn, training)
+    y = torch.empty_like(x) if (mode and training) else None
+    sm = torch.empty(K, dtype=torch.float32, device=dev) if mode == 1 else None
+    sr = torch.empty(K, dtype=torch.float32, device=dev) if mode == 1 else None
+    call("b200med_tail_fwd_hidden", _ptr(x), M, K, int(bool(relu_in)), mode, _ptr(bpart), _ptr(gamma), _ptr(beta), eps, mom,
+         _ptr(rm), _ptr(rv), _ptr(nbt), _ptr(sm), _ptr(sr), _ptr(y), _ptr(_need(W, torch.float32, "W")), _ptr(b), N, _ptr(a),
+         _ptr(part), _stream())
+    return a, part, y, sm, sr
+
+
+def tail_fwd_out(x, W, b, relu_in=False, bn=None, training=True):
+    """The output layer: out = in' W^T + b (C <= 8 columns); returns (out, y, save_mean, save_rstd)."""
+    x = _need(x, torch.float32, "x")
+    M, K = x.shape
+    Cn = W.shape[0]
+    dev = x.device
+    out = torch.empty(M, Cn, dtype=torch.float32, device=dev)
+    mode, bpart, gamma, beta, eps, mom, rm, rv, nbt = _tail_bn_args(bn, training)
+    y = torch.empty_like(x) if (mode and training) else None
+    sm = torch.empty(K, dtype=torch.float32, device=dev) if mode == 1 else None
+    sr = torch.empty(K, dtype=torch.float32, device=dev) if mode == 1 else None
+    call("b200med_tail_fwd_out", _ptr(x), M, K, int(bool(relu_in)), mode, _ptr(bpart), _ptr(gamma), _ptr(beta), eps, mom,
+         _ptr(rm), _ptr(rv), _ptr(nbt), _ptr(sm), _ptr(sr), _ptr(y), _ptr(_need(W, torch.float32, "W")), _ptr(b), Cn, _ptr(out),
+         _stream())
+    return out, y, sm, sr
+
+
+def tail_bwd_out(g, Wl, a, save_mean, save_rstd):
+    """Partials (sum g2, sum g2 xhat) of the last BatchNorm's backward, g2 = g Wl."""
+    g = _need(g, torch.float32, "g"); a = _need(a, torch.float32, "a")
+    M, N = a.shape
+    part = _tail_part(M, 2, N, a.device)
+    call("b200med_tail_bwd_out", _ptr(g), g.shape[1], _ptr(_need(Wl, torch.float32, "Wl")), _ptr(a), M, N, _ptr(save_mean),
+         _ptr(save_rstd), _ptr(part), _stream())
+    return part
+
+
+def tail_bwd_hidden(dy, g, Wl, a, part, gamma, save_mean, save_rstd, W, prev=None, relu_mask=None):
+    """Backward of one hidden layer (see b200med_tail_bwd_hidden): returns (dz, dx, dgamma, dbeta, part_prev).
+    dy = None for the last hidden layer (then g, Wl).  prev = (a_prev, mean_prev, rstd_prev) of the BatchNorm in front."""
+    a = _need(a, torch.float32, "a")
+    M, K = a.shape
+    N = W.shape[1]
+    dev = a.device
+    dz = torch.empty(M, K, dtype=torch.float32, device=dev)
+    dx = torch.empty(M, N, dtype=torch.float32, device=dev)
+    dgamma = torch.empty(K, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(K, dtype=torch.float32, device=dev)
+    part_prev = _tail_part(M, 2, N, dev) if prev is not None else None
+    a_prev, mean_prev, rstd_prev = prev if prev is not None else (None, None, None)
+    call("b200med_tail_bwd_hidden", _ptr(dy), _ptr(g), 0 if g is None else g.shape[1], _ptr(Wl), _ptr(a), M, K, _ptr(part),
+         _ptr(gamma), _ptr(save_mean), _ptr(save_rstd), _ptr(dz), _ptr(dgamma), _ptr(dbeta), _ptr(_need(W, torch.float32, "W")),
+         N, _ptr(dx), _ptr(a_prev), _ptr(mean_prev), _ptr(rstd_prev), _ptr(part_prev), _ptr(relu_mask), _stream())
+    return dz, dx, dgamma, dbeta, part_prev
+
+
 def pool_drop_fwd(z, B, L, Lc, Cn, drop_p=0.0, seed_dev=None, drop_base=0):
     p = torch.empty(B * (Lc // 2), Cn, dtype=torch.float32, device=z.device)
     call("b200med_pool_drop_fwd", _ptr(_need(z, torch.float32, "z")), _ptr(p), B, L, Lc, Cn, float(drop_p),

@@ -136,6 +136,86 @@ def test_mlp_tail_bf16_mode_vs_torch(relu_in, dims, B):
         assert nrel(ye, ref(torch.relu(x.double()) if relu_in else x.double())) < 1e-4
 
 
+def _tail_seq(dims, seed):
+    torch.manual_seed(seed)
+    mods = []
+    for i in range(len(dims) - 2):
+        mods += [nn.Linear(dims[i], dims[i + 1]), nn.ReLU(), nn.BatchNorm1d(dims[i + 1])]
+    mods += [nn.Linear(dims[-2], dims[-1])]
+    seq = nn.Sequential(*mods)
+    for m in seq:
+        if isinstance(m, nn.BatchNorm1d):
+            nn.init.uniform_(m.weight, 0.5, 1.5); nn.init.normal_(m.bias)
+            m.running_mean.normal_(); m.running_var.uniform_(0.5, 1.5)
+    return seq.to(DEV)
+
+
+@pytest.mark.parametrize("dims,B,relu_in", [([128, 256, 64, 1], 8192, True), ([128, 256, 64, 1], 70, True), ([128, 256, 64, 6], 64, True),
+                                             ([64, 128, 5], 3, False), ([256, 128, 256, 64, 8], 129, True), ([128, 64, 1], 1000, False)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_tail_vs_layerwise(dims, B, relu_in, precision, monkeypatch):
+    """The three-kernels-per-direction tail (csrc/mlp_tail.cu) against the layer-at-a-time kernels it replaces: logits, input
+    gradient, every parameter gradient, running statistics; ragged last row tile, 1-3 hidden layers, 1-8 output columns;
+    bit-identical when repeated; 2 n_hidden + 1 launches forward (a layer kernel and a statistics finalize per hidden layer, the output layer)."""
+    import copy
+    from multimodal_error_detection_b200 import _lib, heads
+    seq_f = _tail_seq(dims, B).train()
+    seq_l = copy.deepcopy(seq_f)
+    x = torch.randn(B, dims[0], device=DEV)
+    dy = torch.randn(B, dims[-1], device=DEV)
+    n_hidden = len(dims) - 2
+    assert heads._fused_ok(x, [p for m in seq_f if not isinstance(m, nn.ReLU) for p in
+                               ([m.weight, m.bias] + ([m.running_mean, m.running_var, m.num_batches_tracked] if isinstance(m, nn.BatchNorm1d) else []))],
+                           n_hidden)
+
+    def run(seq):
+        for p in seq.parameters():
+            p.grad = None
+        xg = x.clone().requires_grad_(True)
+        n0 = _lib.launch_count()
+        y = heads.mlp_tail(xg, seq, relu_in=relu_in, training=True, precision=precision)
+        n1 = _lib.launch_count()
+        y.backward(dy)
+        from multimodal_error_detection_b200 import lstm_stack
+        lstm_stack.join_pending()
+        torch.cuda.synchronize()
+        return y.detach(), xg.grad, [p.grad.clone() for p in seq.parameters()], [b.clone() for b in seq.buffers()], n1 - n0
+
+    yf, gxf, gpf, bf, launches = run(seq_f)
+    assert launches == 2 * n_hidden + 1
+    monkeypatch.setattr(heads, "FUSED_TAIL", False)
+    yl, gxl, gpl, bl, launches_l = run(seq_l)
+    assert launches_l > launches
+    monkeypatch.setattr(heads, "FUSED_TAIL", True)
+    tol = 2e-5 if precision == "fp32" else 2e-4
+    assert nrel(yf, yl) < tol
+    if precision == "fp32":
+        assert nrel(gxf, gxl) < 5 * tol
+        gmax = max(float(g.abs().max()) for g in gpl)
+        for (k, _), a, b in zip(seq_f.named_parameters(), gpf, gpl):
+            scale = max(float(b.abs().max()), 1e-4 * gmax)
+            assert float((a - b).abs().max()) <= 10 * tol * scale, k
+    else:       # the layer-at-a-time bf16 mode flips the ReLU of pre-activations within ~1e-5 of zero (a handful per batch, each
+        # moves a row of the input gradient): norm-wise, like test_mlp_tail_bf16_mode_vs_torch
+        def frel(a, b):
+            return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+        assert frel(gxf, gxl) < 1e-2
+        gmax = max(float(g.norm()) for g in gpl)
+        for (k, _), a, b in zip(seq_f.named_parameters(), gpf, gpl):
+            assert float((a.double() - b.double()).norm()) <= 1e-2 * max(float(b.norm()), 1e-3 * gmax), k
+    for (k, _), a, b in zip(seq_f.named_buffers(), bf, bl):
+        assert nrel(a.double(), b.double()) < 1e-5, k
+    seq_r = _tail_seq(dims, B).train()
+    yr, gxr, gpr, br, _ = run(seq_r)
+    assert torch.equal(yr, yf) and torch.equal(gxr, gxf) and all(torch.equal(a, b) for a, b in zip(gpr, gpf))
+    seq_f.eval(); seq_l.eval()
+    with torch.no_grad():
+        ye = heads.mlp_tail(x, seq_f, relu_in=relu_in, training=False, precision=precision)
+        monkeypatch.setattr(heads, "FUSED_TAIL", False)
+        yl = heads.mlp_tail(x, seq_l, relu_in=relu_in, training=False, precision=precision)
+    assert nrel(ye, yl) < tol
+
+
 def test_split_bf16x3_kernel():
     """b200med_split_bf16x3: hi = bf16(x), lo = bf16(x - hi) in both layouts and both operand orders, bit for bit."""
     from multimodal_error_detection_b200 import ops
