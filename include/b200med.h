@@ -552,6 +552,13 @@ int b200med_tcn_stage_fwd_bf16(const float *x, int32_t in_dim, int32_t softmax_i
 /* state [4] f32 device scalars, owned by the caller: {step, lr, bias_corr1, sqrt(bias_corr2)}.
  * b200med_adam_advance: step += 1 and recompute the corrections (1 thread, double precision).    */
 int b200med_adam_advance(float *state, float beta1, float beta2, void *stream);
+/* dst[i][0..n[i]) <- src[i][0..n[i]) for `count` tensor pairs in as few launches as possible (48 pairs each; pointers and
+ * sizes travel in the kernel parameters): the per-parameter gradients autograd hands over are gathered into the flat gradient
+ * buffer (replaces the optimiser's per-tensor traffic, modeling_utils.py:363-365), and the bf16 copies of the
+ * FeatureExtractor weights are made in one pass (dst_dtype B200MED_BF16; src is always f32).  src / dst / n are HOST arrays.
+ * adam_state != NULL: the launch also performs b200med_adam_advance(adam_state, beta1, beta2).                 */
+int b200med_multi_copy_f32(const void *const *src, void *const *dst, const int64_t *n, int32_t count, int32_t dst_dtype,
+                           float *adam_state, float beta1, float beta2, void *stream);
 /* p, g, m, v [n] f32 flat buffers.  g is multiplied by grad_scale first (1/world_size after the
  * gradient all-reduce).  lr and the bias corrections are read from `state` on the device so the
  * launch is CUDA-graph replayable.                                                               */

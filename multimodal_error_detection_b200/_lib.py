@@ -115,6 +115,7 @@ SIGNATURES = {
     "b200med_tcn_stage_fwd_bf16": (C.c_int, [_p, _i32, _i32, _p, _p, _p, _i32, _p, _p, _i32, _i64, _i32, _p, _p, _p, _p, _p, _p, _p,
                                              _p, _p]),
     "b200med_adam_advance": (C.c_int, [_p, _f, _f, _p]),
+    "b200med_multi_copy_f32": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _f, _f, _p]),
     "b200med_adam_step": (C.c_int, [_p, _p, _p, _p, _i64, _p, _f, _f, _f, _f, _f, _p]),
     "b200med_window_vote": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _p]),
     "b200med_soft_vote": (C.c_int, [_p, _p, _p, _i64, _p, _p, _i32, _p, _p]),

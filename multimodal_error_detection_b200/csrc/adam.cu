@@ -53,9 +53,92 @@ adam_step_kernel(float *__restrict__ p, const float *__restrict__ g, float *__re
         adam_one(p[i], g[i], m[i], v[i], step_size, bc2s, beta1, beta2, eps, wd, gscale);
 }
 
+// ---- many small copies in ONE launch: the gradients autograd hands over (one tensor per parameter) are gathered into the flat
+// gradient buffer; the bf16 copies of the FeatureExtractor weights are made in one pass.  Pointers, sizes and the first block
+// of every pair travel in the kernel's parameter space (no pointer table in device memory: nothing to upload per step, and a
+// captured graph keeps them by value).
+constexpr int kMultiMax = 48;           // pairs per launch
+constexpr int kMultiChunk = 8192;       // elements per block
+
+struct MultiCopyArgs {
+    const float *src[kMultiMax];
+    void *dst[kMultiMax];
+    long long n[kMultiMax];
+    int blk0[kMultiMax + 1];
+    int count;
+};
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+multi_copy_kernel(const __grid_constant__ MultiCopyArgs a, float *adam_state, float beta1, float beta2) {
+    pdl_wait();
+    if (adam_state && blockIdx.x == 0 && threadIdx.x == 0) {      // adam_advance_kernel's arithmetic
+        const double step = (double)adam_state[0] + 1.0;
+        adam_state[0] = (float)step;
+        adam_state[2] = (float)(1.0 - pow((double)beta1, step));
+        adam_state[3] = (float)sqrt(1.0 - pow((double)beta2, step));
+    }
+    int t = 0;
+    while (t + 1 < a.count && (int)blockIdx.x >= a.blk0[t + 1]) ++t;
+    const long long n = a.n[t], e0 = (long long)((int)blockIdx.x - a.blk0[t]) * kMultiChunk;
+    const long long e1 = e0 + kMultiChunk < n ? e0 + kMultiChunk : n;
+    const float *src = a.src[t];
+    TO *dst = reinterpret_cast<TO *>(a.dst[t]);
+    const bool vec = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    if (vec) {
+        const long long v1 = e0 + ((e1 - e0) & ~3LL);
+#pragma unroll 4
+        for (long long e = e0 + 4LL * threadIdx.x; e < v1; e += 4LL * blockDim.x) {
+            const float4 v = *reinterpret_cast<const float4 *>(src + e);
+            if constexpr (sizeof(TO) == 4) {
+                *reinterpret_cast<float4 *>(dst + e) = v;
+            } else {
+                uint2 o;
+                o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2 *>(dst + e) = o;
+            }
+        }
+        for (long long e = v1 + threadIdx.x; e < e1; e += blockDim.x) dst[e] = (TO)src[e];
+    } else {
+        for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[e] = (TO)src[e];
+    }
+}
+
 }  // namespace b200med
 
 using namespace b200med;
+
+extern "C" __attribute__((visibility("default"))) int b200med_multi_copy_f32(const void *const *src, void *const *dst, const int64_t *n,
+                                 int32_t count, int32_t dst_dtype, float *adam_state, float beta1, float beta2, void *stream) {
+    B200MED_REQUIRE(count >= 0 && (count == 0 || (src && dst && n)), "bad arguments");
+    B200MED_REQUIRE(dst_dtype == B200MED_F32 || dst_dtype == B200MED_BF16, "dst_dtype must be f32 or bf16");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool advanced = adam_state == nullptr;
+    for (int base = 0; base < count || !advanced; base += kMultiMax) {
+        MultiCopyArgs a;
+        a.count = 0;
+        int blocks = 0;
+        for (int i = base; i < count && i < base + kMultiMax; ++i) {
+            if (n[i] <= 0) continue;
+            B200MED_REQUIRE(src[i] && dst[i], "null pointer");
+            a.src[a.count] = (const float *)src[i]; a.dst[a.count] = dst[i]; a.n[a.count] = n[i]; a.blk0[a.count] = blocks;
+            blocks += (int)((n[i] + kMultiChunk - 1) / kMultiChunk);
+            ++a.count;
+        }
+        a.blk0[a.count] = blocks;
+        if (a.count == 0) {                    // nothing to copy in this batch: only the Adam scalars may be left to advance
+            if (advanced) continue;
+            a.src[0] = nullptr; a.dst[0] = nullptr; a.n[0] = 0; a.blk0[0] = 0; a.blk0[1] = 1; a.count = 1; blocks = 1;
+        }
+        float *state = advanced ? nullptr : adam_state;
+        advanced = true;
+        if (dst_dtype == B200MED_F32) launch_k(multi_copy_kernel<float>, (unsigned)blocks, 256, 0, st, a, state, beta1, beta2);
+        else launch_k(multi_copy_kernel<__nv_bfloat16>, (unsigned)blocks, 256, 0, st, a, state, beta1, beta2);
+        if (int e = after_launch("multi_copy_kernel")) return e;
+    }
+    return B200MED_OK;
+}
+
 
 extern "C" __attribute__((visibility("default"))) int b200med_adam_advance(float *state, float beta1, float beta2, void *stream) {
     B200MED_REQUIRE(state, "null state");

@@ -210,6 +210,29 @@ class LSTMRecFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         alloc = torch.empty if Bp == B else torch.zeros          # pad rows must hold finite values
         A = [alloc(W, Bp, Kp[l], dtype=torch.bfloat16, device=dev) for l in range(L)]
+        gen2 = REC_GEN == 2 and all(i in (64, 128) for i in inp)      # generation 2 stages [x | h] tiles of 64 / 128 + 128 columns
+        packed = None
+        if gen2:
+            # The weight operands of ALL layers (forward layout, and the transposed one of the backward) depend on the parameters
+            # only: they are packed on the side stream, under the kernel that builds the first layer's input operand, instead of
+            # one launch in front of every recurrence kernel (6 launches = ~16 us off the chain of the replayed step).
+            main, side = torch.cuda.current_stream(), _side_stream(dev)
+            side.wait_stream(main)
+            packed = []
+            with torch.cuda.stream(side):
+                sst = _stream()
+                for l in range(L):
+                    w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in params[4 * l:4 * l + 4])
+                    wp = torch.empty(4 * H, Kp[l], dtype=torch.bfloat16, device=dev)
+                    bias_p = torch.empty(4 * H, dtype=torch.float32, device=dev)
+                    call("b200med_lstm_pack_weights2", _raw(w_ih.data_ptr()), _raw(w_hh.data_ptr()), _raw(b_ih.data_ptr()),
+                         _raw(b_hh.data_ptr()), ins[l], inp[l], _raw(wp.data_ptr()), _raw(bias_p.data_ptr()), sst)
+                    wt = None
+                    if need_grad:
+                        wt = torch.empty(Kp[l], 4 * H, dtype=torch.bfloat16, device=dev)
+                        call("b200med_lstm_pack_weights2_bwd", _raw(w_ih.data_ptr()), _raw(w_hh.data_ptr()), ins[l], inp[l],
+                             _raw(wt.data_ptr()), _raw(0), sst)
+                    packed.append((wp, bias_p, wt))
         # the reference hands the head cat(...).permute(0, 2, 1): a view of a contiguous [B, W, F] tensor -- read it as such
         if parts is not None:
             bwf = True
@@ -227,7 +250,12 @@ class LSTMRecFunction(torch.autograd.Function):
         out = torch.empty(B, H, dtype=torch.float32, device=dev)
         seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
         Wih, Whh, Gact, Cs = [], [], [], []
-        gen2 = REC_GEN == 2 and all(i in (64, 128) for i in inp)      # generation 2 stages [x | h] tiles of 64 / 128 + 128 columns
+        if gen2:
+            torch.cuda.current_stream().wait_stream(side)
+            for tup in packed:
+                for t_ in tup:
+                    if t_ is not None:
+                        t_.record_stream(torch.cuda.current_stream())     # allocated on the side stream, read on this one
         xg = None if gen2 else torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev)
         # rows of the sigmoid gates (i, f, o) are halved for the forward kernels: sigmoid(z) = 0.5 * tanh(z / 2) + 0.5
         half = None
@@ -242,19 +270,15 @@ class LSTMRecFunction(torch.autograd.Function):
                 wpad[:, :ins[l]] = w_ih.detach()
                 Wih.append(ops.to_bf16(wpad))
                 Whh.append(ops.to_bf16(w_hh.detach().contiguous()))
-            elif need_grad:                                                            # generation 2 packs its own operand in the backward
-                Wih.append(w_ih.detach()); Whh.append(w_hh.detach())
+            elif need_grad:                                                            # generation 2: the packed backward operand
+                Wih.append(packed[l][2]); Whh.append(None)
             else:
                 Wih.append(None); Whh.append(None)
             gact = torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev) if need_grad else None
             cs = torch.empty(W * Bp, H, dtype=torch.float32, device=dev) if need_grad else None
             top = l == L - 1
             if gen2:
-                wp = torch.empty(4 * H, Kp[l], dtype=torch.bfloat16, device=dev)
-                bias_p = torch.empty(4 * H, dtype=torch.float32, device=dev)
-                call("b200med_lstm_pack_weights2", _raw(w_ih.detach().contiguous().data_ptr()), _raw(w_hh.detach().contiguous().data_ptr()),
-                     _raw(b_ih.detach().contiguous().data_ptr()), _raw(b_hh.detach().contiguous().data_ptr()), ins[l], inp[l],
-                     _raw(wp.data_ptr()), _raw(bias_p.data_ptr()), st)
+                wp, bias_p, _ = packed[l]
                 call("b200med_lstm_rec2_fwd", _raw(A[l].data_ptr()), Kp[l], inp[l], _raw(wp.data_ptr()), _raw(bias_p.data_ptr()),
                      _raw(gact.data_ptr() if need_grad else 0), _raw(cs.data_ptr() if need_grad else 0),
                      _raw(0 if top else A[l + 1].data_ptr()), 0 if top else Kp[l + 1], _raw(out.data_ptr() if top else 0),
@@ -304,9 +328,7 @@ class LSTMRecFunction(torch.autograd.Function):
             if gen2:
                 # one launch: dG_t, dh_{t-1} AND dX_t = dG_t W_ih (csrc/lstm_rec2.cu); dX leaves in the layout its consumer reads
                 # (row-block-interleaved for the recurrence of the layer below, row-major for the unpack into [B, F, W])
-                wt = torch.empty(Kp[l], 4 * H, dtype=torch.bfloat16, device=dev)
-                call("b200med_lstm_pack_weights2_bwd", _raw(Wih[l].contiguous().data_ptr()), _raw(Whh[l].contiguous().data_ptr()),
-                     ins[l], inp[l], _raw(wt.data_ptr()), _raw(0), st)
+                wt = Wih[l]           # [Kp, 4H] bf16, packed in the forward (lstm_pack_weights2_bwd)
                 dX = torch.empty(W * Bp, inp[l], dtype=torch.float32, device=dev)
                 call("b200med_lstm_rec2_bwd", _raw(Gact[l].data_ptr()), _raw(Cs[l].data_ptr()), _raw(wt.data_ptr()), inp[l],
                      _raw(dout.data_ptr() if top else 0), _raw(0 if top else dX_up.data_ptr()), _raw(dG.data_ptr()),

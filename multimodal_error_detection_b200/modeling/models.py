@@ -37,6 +37,15 @@ class TableWindows:
         self.table, self.mean, self.std, self.starts, self.W, self.events = table, mean, std, starts, W, events
 
 
+def _bf16_copies(weights):
+    """bf16 copies of all layers' weights in ONE launch (b200med_multi_copy_f32; was one cast kernel per layer in front of the
+    first GEMM of the step)."""
+    src = [w.detach().contiguous() for w in weights]
+    wb = [torch.empty(w.shape, dtype=torch.bfloat16, device=w.device) for w in src]
+    ops.multi_copy([b.view(-1) for b in wb], [w.view(-1) for w in src])
+    return wb
+
+
 class _MLPFunction(torch.autograd.Function):
     """y = L_n(...relu(L_1(x))) with every product on the b200med GEMM kernels (K2)."""
 
@@ -51,7 +60,7 @@ class _MLPFunction(torch.autograd.Function):
             # written once (the backward's weight-gradient operand) and never read back by this layer
             if precision != "bf16" or n < 2:
                 raise ValueError("the fused gather serves the bf16 mode of an MLP with at least two layers")
-            wb = [ops.to_bf16(w.detach().contiguous()) for w in weights]
+            wb = _bf16_copies(weights)
             # inference (no gradient will be asked for): the bf16 batch is not written at all -- 0.54 GB per 8192 windows
             keep = any(ctx.needs_input_grad)      # all False under torch.no_grad() / for frozen parameters
             xb, y1 = ops.gather_linear_bf16(x.table, x.mean, x.std, x.starts, x.W, wb[0], biases[0].detach(), relu=True, events=x.events,
@@ -77,7 +86,7 @@ class _MLPFunction(torch.autograd.Function):
             return acts[-1]
         # bf16: activations and weight copies in bf16, fp32 accumulation in TMEM, fp32 final output
         h = x if x.dtype == torch.bfloat16 else ops.to_bf16(x.contiguous())
-        wb = [ops.to_bf16(w.detach().contiguous()) for w in weights]
+        wb = _bf16_copies(weights)
         acts = [h.contiguous()]
         for i in range(n):
             N, K = weights[i].shape

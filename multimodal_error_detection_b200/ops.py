@@ -653,6 +653,26 @@ def adam_advance(state: torch.Tensor, beta1: float, beta2: float):
     call("b200med_adam_advance", _ptr(_need(state, torch.float32, "state")), beta1, beta2, _stream())
 
 
+def multi_copy(dst, src, adam=None):
+    """dst[i] <- src[i] for lists of equally sized contiguous tensors in one launch per 48 pairs (b200med_multi_copy_f32);
+    src f32, dst f32 or bf16 (all alike).  adam = (state, beta1, beta2): the launch also advances the Adam step scalars."""
+    k = len(dst)
+    if k == 0 and adam is None:
+        return
+    for d, s_ in zip(dst, src):
+        _need(s_, torch.float32, "src"); _need(d, None, "dst")
+        if d.numel() != s_.numel() or d.dtype != dst[0].dtype:
+            raise ValueError("b200med multi_copy: sizes / dtypes of the pairs do not match")
+    dt = _dt(dst[0]) if k else F32
+    if dt not in (F32, BF16):
+        raise TypeError("b200med multi_copy: dst must be float32 or bfloat16")
+    srcs = (C.c_void_p * max(k, 1))(*[s_.data_ptr() for s_ in src])
+    dsts = (C.c_void_p * max(k, 1))(*[d.data_ptr() for d in dst])
+    ns = (C.c_int64 * max(k, 1))(*[d.numel() for d in dst])
+    state, b1, b2 = adam if adam is not None else (None, 0.0, 0.0)
+    call("b200med_multi_copy_f32", srcs, dsts, ns, k, dt, _ptr(state), float(b1), float(b2), _stream())
+
+
 def adam_step(p, g, m, v, state, beta1, beta2, eps, weight_decay, grad_scale=1.0):
     call("b200med_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(state), beta1, beta2, eps, weight_decay,
          grad_scale, _stream())

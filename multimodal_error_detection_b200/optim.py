@@ -169,8 +169,9 @@ class FusedAdam(torch.optim.Optimizer):
             for p, _, _ in c.members:
                 p.grad = None
 
-    def _refresh_active(self):
-        """Adopt the gradients of parameters seen for the first time and rebuild the active ranges."""
+    def _refresh_active(self, advance=None):
+        """Adopt the gradients of parameters seen for the first time and rebuild the active ranges.  advance = (beta1, beta2):
+        the launch that gathers the gradients also advances the Adam step scalars (returns True when it did)."""
         from . import lstm_stack
         lstm_stack.join_pending()      # gradient GEMMs still running on the side stream (lstm_stack.DEFER_JOIN)
         changed = self._active is None
@@ -199,8 +200,11 @@ class FusedAdam(torch.optim.Optimizer):
                     dst.append(view)
                     src.append(p.grad.detach())
                     p.grad = view
-        if dst:
-            torch._foreach_copy_(dst, src)
+        advanced = False
+        if dst:      # one kernel for all tensors (was torch._foreach_copy_: 18 us for 28 tensors on 44 CTAs)
+            ops.multi_copy([d.reshape(-1) for d in dst], [s_.contiguous().reshape(-1) for s_ in src],
+                           adam=None if advance is None else (self.state_dev, *advance))
+            advanced = advance is not None
         if zero:
             torch._foreach_zero_(zero)
         if changed:
@@ -215,6 +219,7 @@ class FusedAdam(torch.optim.Optimizer):
                     else:
                         runs.append([b, e])
                 c.runs = [(b, min(e, c.param.numel())) for b, e in runs]
+        return advanced
 
     def sync_lr(self):
         lr = float(self.param_groups[0]["lr"])
@@ -225,11 +230,12 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         self.prepare()
-        self._refresh_active()
         g = self.param_groups[0]
-        self.sync_lr()
         b1, b2 = g["betas"]
-        ops.adam_advance(self.state_dev, b1, b2)
+        advanced = self._refresh_active(advance=(b1, b2))
+        self.sync_lr()
+        if not advanced:
+            ops.adam_advance(self.state_dev, b1, b2)
         for c in self.chunks:
             for b, e in c.runs:
                 ops.adam_step(c.param[b:e], c.grad[b:e], c.exp_avg[b:e], c.exp_avg_sq[b:e], self.state_dev, b1, b2,
