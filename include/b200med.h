@@ -243,6 +243,15 @@ int b200med_lstm_pack_inputs(const float *x, void *A0, int64_t B, int64_t Bpad, 
 int b200med_lstm_pack_parts(const float *feats, int32_t Ca, const float *kin_table, int64_t table_rows, int32_t Cb,
                             const float *mean, const float *stdv, int32_t stat_rows, const int32_t *starts, void *A0,
                             int64_t B, int64_t Bpad, int32_t W, int32_t H, int32_t Kp, int32_t hoff, void *stream);
+/* The same with feats [B,W,Ca] in bf16 (the FeatureExtractor's last GEMM then writes the rounding this kernel applies anyway:
+ * identical operand bits, half the bytes) for the common geometry: Ca, Cb even, Ca + Cb <= 64, Kp = 64 + H, one statistics row. */
+int b200med_lstm_pack_parts_bf16(const void *feats, int32_t Ca, const float *kin_table, int64_t table_rows, int32_t Cb,
+                                 const float *mean, const float *stdv, const int32_t *starts, void *A0, int64_t B, int64_t Bpad,
+                                 int32_t W, int32_t H, int32_t Kp, void *stream);
+/* dx [B,W,F] bf16 <- dA0 [W,Bpad,Kp] f32 columns [0,F): the gradient of bf16 feats (the FeatureExtractor's backward rounds its
+ * incoming gradient to bf16 first; this removes that pass from the critical path of the step).                      */
+int b200med_lstm_unpack_dx_bf16(const float *dA0, void *dx, int64_t B, int64_t Bpad, int32_t F, int32_t W, int32_t Kp,
+                                void *stream);
 /* dx [B,F,W] f32 <- dA0 [W,Bpad,Kp] f32 (row-major) columns [0,F).                                   */
 int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int64_t Bpad, int32_t F, int32_t W, int32_t Kp,
                            int32_t x_layout, void *stream);

@@ -57,6 +57,8 @@ SIGNATURES = {
     "b200med_cast_bf16_to_f32": (C.c_int, [_p, _p, _i64, _p]),
     "b200med_lstm_pack_inputs": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "b200med_lstm_pack_parts": (C.c_int, [_p, _i32, _p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _i64, _i32, _i32, _i32, _i32, _p]),
+    "b200med_lstm_pack_parts_bf16": (C.c_int, [_p, _i32, _p, _i64, _i32, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
+    "b200med_lstm_unpack_dx_bf16": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _i32, _p]),
     "b200med_lstm_rec_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p,
                                        C.c_uint64, _p]),
     "b200med_lstm_rec_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i32, _p, _i64, _i64, _i32, _i32, _f, _p, C.c_uint64, _p]),

@@ -175,8 +175,12 @@ lstm_pack_parts_kernel(const float *__restrict__ feats, int Ca, const float *__r
 // x block -- one float2 load (feats or table row), mean / std in registers for the whole kernel, one 128-byte store per row and
 // warp; the h_{-1} block is zeroed by the rows of step 0 only.  (The generic kernel above walks Kp columns with a branch per
 // element: 52 us at B = 8192, W = 16 against ~80 MB of traffic.)
+__device__ __forceinline__ float2 load_pair(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+__device__ __forceinline__ float2 load_pair(const __nv_bfloat16 *p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p)); }
+
+template <typename TF>      // feats f32, or bf16 (the FeatureExtractor's last GEMM writes the rounding this kernel would apply)
 __global__ void __launch_bounds__(256)
-lstm_pack_parts64_kernel(const float *__restrict__ feats, int Ca, const float *__restrict__ kin, long long table_rows, int Cb,
+lstm_pack_parts64_kernel(const TF *__restrict__ feats, int Ca, const float *__restrict__ kin, long long table_rows, int Cb,
                          const float *__restrict__ mean, const float *__restrict__ stdv, const int32_t *__restrict__ starts,
                          __nv_bfloat16 *__restrict__ A0, long long B, long long Bpad, int W, int H, int Kp) {
     pdl_wait();
@@ -205,7 +209,7 @@ lstm_pack_parts64_kernel(const float *__restrict__ feats, int Ca, const float *_
             v[u] = make_float2(0.0f, 0.0f);
             if (bs[u] < 0) continue;
             if (rows[u] < 0 || rows[u] >= table_rows) __trap();  // a window outside the table: the reference raises IndexError
-            if (is_f) v[u] = *reinterpret_cast<const float2 *>(feats + (r0 + u * warps) * Ca + c);
+            if (is_f) v[u] = load_pair(feats + (r0 + u * warps) * Ca + c);
             else if (is_k) v[u] = *reinterpret_cast<const float2 *>(kin + rows[u] * Cb + (c - Ca));
         }
 #pragma unroll
@@ -221,8 +225,9 @@ lstm_pack_parts64_kernel(const float *__restrict__ feats, int Ca, const float *_
 }
 
 // dx [B, W, F] f32 <- dA0 [W, Bpad, Kp] f32 columns [0, F)
+template <typename TO>      // dx f32, or bf16 (the rounding the FeatureExtractor's backward applies to its incoming gradient)
 __global__ void __launch_bounds__(256)
-lstm_unpack_bwf_kernel(const float *__restrict__ dA0, float *__restrict__ dx, long long B, long long Bpad, int F, int W, int Kp) {
+lstm_unpack_bwf_kernel(const float *__restrict__ dA0, TO *__restrict__ dx, long long B, long long Bpad, int F, int W, int Kp) {
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long nrows = B * W, warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -240,7 +245,7 @@ lstm_unpack_bwf_kernel(const float *__restrict__ dA0, float *__restrict__ dx, lo
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const long long r = r0 + u * warps;
-                if (r < nrows && lane < F) dx[r * F + lane] = v[u];
+                if (r < nrows && lane < F) dx[r * F + lane] = (TO)v[u];
             }
         }
         return;
@@ -249,7 +254,7 @@ lstm_unpack_bwf_kernel(const float *__restrict__ dA0, float *__restrict__ dx, lo
         const long long b = r / W;
         const int t = (int)(r - b * W);
         const float *src = dA0 + ((long long)t * Bpad + b) * Kp;
-        for (int k = lane; k < F; k += 32) dx[r * F + k] = src[k];
+        for (int k = lane; k < F; k += 32) dx[r * F + k] = (TO)src[k];
     }
 }
 
@@ -449,13 +454,38 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_parts(
     const long long blocks = (B * (long long)W + 7) / 8, cap = (long long)num_sms() * 8;
     if (Ca % 2 == 0 && Cb % 2 == 0 && Ca + Cb <= 64 && hoff == 64 && hoff + H == Kp && stat_rows == 1 &&
         ((uintptr_t)feats % 8 == 0) && ((uintptr_t)kin_table % 8 == 0)) {
-        launch_k(lstm_pack_parts64_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
+        launch_k(lstm_pack_parts64_kernel<float>, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
             feats, Ca, kin_table, table_rows, Cb, mean, stdv, starts, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, W, H, Kp);
         return after_launch("lstm_pack_parts64_kernel");
     }
     launch_k(lstm_pack_parts_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, 
         feats, Ca, kin_table, table_rows, Cb, mean, stdv, stat_rows, starts, reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, W, H, Kp, hoff);
     return after_launch("lstm_pack_parts_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_pack_parts_bf16(
+    const void *feats, int32_t Ca, const float *kin_table, int64_t table_rows, int32_t Cb, const float *mean, const float *stdv,
+    const int32_t *starts, void *A0, int64_t B, int64_t Bpad, int32_t W, int32_t H, int32_t Kp, void *stream) {
+    B200MED_REQUIRE(B >= 1 && Bpad >= B && Ca >= 2 && Cb >= 0 && W >= 1 && H >= 1, "bad shape");
+    B200MED_REQUIRE(Ca % 2 == 0 && Cb % 2 == 0 && Ca + Cb <= 64 && Kp == 64 + H, "geometry: even widths, Ca + Cb <= 64, Kp = 64 + H");
+    B200MED_REQUIRE(feats && starts && A0 && (Cb == 0 || kin_table), "null pointer");
+    B200MED_REQUIRE((mean == nullptr) == (stdv == nullptr), "mean and std must both be given or both NULL");
+    B200MED_REQUIRE(((uintptr_t)feats % 4 == 0) && ((uintptr_t)kin_table % 8 == 0), "misaligned feats / table");
+    const long long blocks = (B * (long long)W + 7) / 8, cap = (long long)num_sms() * 8;
+    launch_k(lstm_pack_parts64_kernel<__nv_bfloat16>, (unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream,
+             reinterpret_cast<const __nv_bfloat16 *>(feats), Ca, kin_table, table_rows, Cb, mean, stdv, starts,
+             reinterpret_cast<__nv_bfloat16 *>(A0), B, Bpad, W, H, Kp);
+    return after_launch("lstm_pack_parts64_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx_bf16(const float *dA0, void *dx, int64_t B, int64_t Bpad,
+                                                                                  int32_t F, int32_t W, int32_t Kp, void *stream) {
+    B200MED_REQUIRE(B >= 1 && Bpad >= B && F >= 1 && W >= 1 && Kp >= F, "bad shape");
+    B200MED_REQUIRE(dA0 && dx, "null pointer");
+    const long long blocks = (B * (long long)W + 7) / 8, cap1 = (long long)num_sms() * 8;
+    launch_k(lstm_unpack_bwf_kernel<__nv_bfloat16>, (unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream, dA0,
+             reinterpret_cast<__nv_bfloat16 *>(dx), B, Bpad, F, W, Kp);
+    return after_launch("lstm_unpack_bwf_kernel");
 }
 
 extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(const float *dA0, float *dx, int64_t B, int64_t Bpad,
@@ -466,7 +496,7 @@ extern "C" __attribute__((visibility("default"))) int b200med_lstm_unpack_dx(con
     if (x_layout == 1) {
         B200MED_REQUIRE(dA0 && dx, "null pointer");
         const long long blocks = (B * (long long)W + 7) / 8, cap1 = (long long)num_sms() * 8;
-        launch_k(lstm_unpack_bwf_kernel, (unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream, dA0, dx, B, Bpad, F, W, Kp);
+        launch_k(lstm_unpack_bwf_kernel<float>, (unsigned)(blocks < cap1 ? blocks : cap1), 256, 0, (cudaStream_t)stream, dA0, dx, B, Bpad, F, W, Kp);
         return after_launch("lstm_unpack_bwf_kernel");
     }
     B200MED_REQUIRE(dA0 && dx, "null pointer");

@@ -109,6 +109,9 @@ class WindowTrainStep:
         nxt = 1 - cur
         self._mark(0)
         from . import ops
+        prepack = getattr(self.model, "prepack", None)
+        if prepack is not None:        # parameter-only operand packing of the head: on the side stream, under the first kernels
+            prepack(self.B, self.W)
         labels = ops.take_rows(self.label_col, self.idx2[cur], out=self.labels)
         parts = None
         if self.fused:
@@ -123,8 +126,9 @@ class WindowTrainStep:
                                 starts, self.W)
             self._mark(1)
             im = self.ds._img_stats
+            # heads that build their own first operand round the features to bf16 there: they take them in bf16 right away
             feats = self.fe.forward_table(self.ds._image_table, im[0] if im else None, im[1] if im else None, starts, self.W,
-                                          events=self.gather_events)
+                                          events=self.gather_events, out_bf16=by_parts)
             if by_parts:
                 from .lstm_stack import WindowParts
                 parts = WindowParts(self.ds._kin_table, km[0] if km else None, km[1] if km else None, starts)

@@ -184,6 +184,58 @@ class WindowParts:
         self.table, self.mean, self.std, self.starts = table, mean, std, starts
 
 
+_PREPACKED = {}      # id(weight_ih_l0) -> what prepack() left for the next forward of that LSTM
+
+
+def _prepack(params, B, W, F, need_grad, dev):
+    """Generation-2 recurrence: packed weight operands (wp, bias_p, wt) per layer and the upper layers' operand buffers with
+    their h_{-1} columns zeroed, all on the side stream (forked from the current one here)."""
+    L = len(params) // 4
+    H = params[1].shape[1]
+    Bp = (B + 31) // 32 * 32
+    ins = [F if l == 0 else H for l in range(L)]
+    inp = [(i + 63) // 64 * 64 for i in ins]
+    Kp = [ip + H for ip in inp]
+    alloc = torch.empty if Bp == B else torch.zeros
+    main, side = torch.cuda.current_stream(), _side_stream(dev)
+    side.wait_stream(main)
+    packed, upper = [], []
+    with torch.cuda.stream(side):
+        sst = _stream()
+        for l in range(L):
+            w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in params[4 * l:4 * l + 4])
+            wp = torch.empty(4 * H, Kp[l], dtype=torch.bfloat16, device=dev)
+            bias_p = torch.empty(4 * H, dtype=torch.float32, device=dev)
+            call("b200med_lstm_pack_weights2", _raw(w_ih.data_ptr()), _raw(w_hh.data_ptr()), _raw(b_ih.data_ptr()),
+                 _raw(b_hh.data_ptr()), ins[l], inp[l], _raw(wp.data_ptr()), _raw(bias_p.data_ptr()), sst)
+            wt = None
+            if need_grad:
+                wt = torch.empty(Kp[l], 4 * H, dtype=torch.bfloat16, device=dev)
+                call("b200med_lstm_pack_weights2_bwd", _raw(w_ih.data_ptr()), _raw(w_hh.data_ptr()), ins[l], inp[l],
+                     _raw(wt.data_ptr()), _raw(0), sst)
+            packed.append((wp, bias_p, wt))
+        for l in range(1, L):
+            a = alloc(W, Bp, Kp[l], dtype=torch.bfloat16, device=dev)
+            call("b200med_zero_cols_bf16", _raw(a[0].data_ptr()), Bp, Kp[l], inp[l], H, sst)
+            upper.append(a)
+    return {"key": (B, W, F, L, H, bool(need_grad)), "side": side, "packed": packed, "upper": upper}
+
+
+def prepack(lstm: torch.nn.LSTM, B: int, W: int, F: int, need_grad: bool = True):
+    """Start the parameter-only preparation of the next ``lstm_last_hidden(..)`` call of this LSTM (bf16 mode, hidden size 128)
+    NOW, on the side stream: a train step calls it first thing, so that these ~8 small kernels run under the FeatureExtractor
+    instead of between it and the recurrence.  Harmless when the forward then runs with other shapes (it redoes the work)."""
+    if REC_GEN != 2 or lstm.hidden_size != 128 or lstm.bidirectional or lstm.proj_size or not lstm.bias:
+        return
+    params = []
+    for l in range(lstm.num_layers):
+        params += [getattr(lstm, f"weight_ih_l{l}"), getattr(lstm, f"weight_hh_l{l}"),
+                   getattr(lstm, f"bias_ih_l{l}"), getattr(lstm, f"bias_hh_l{l}")]
+    if (F + 63) // 64 * 64 not in (64, 128) or not params[0].is_cuda:
+        return
+    _PREPACKED[id(params[0])] = _prepack(params, B, W, F, need_grad, params[0].device)
+
+
 class LSTMRecFunction(torch.autograd.Function):
     """Persistent-recurrence path (hidden_size 128).  Layer buffers, time-major with the batch padded to Bp (multiple
     of 32) rows per step:
@@ -208,54 +260,52 @@ class LSTMRecFunction(torch.autograd.Function):
         inp = [(i + 63) // 64 * 64 for i in ins]
         Kp = [ip + H for ip in inp]
         need_grad = any(ctx.needs_input_grad)
-        alloc = torch.empty if Bp == B else torch.zeros          # pad rows must hold finite values
-        A = [alloc(W, Bp, Kp[l], dtype=torch.bfloat16, device=dev) for l in range(L)]
         gen2 = REC_GEN == 2 and all(i in (64, 128) for i in inp)      # generation 2 stages [x | h] tiles of 64 / 128 + 128 columns
-        packed = None
+        alloc = torch.empty if Bp == B else torch.zeros          # pad rows must hold finite values
+        packed, side = None, None
+        pre = _PREPACKED.pop(id(params[0]), None)
         if gen2:
-            # The weight operands of ALL layers (forward layout, and the transposed one of the backward) depend on the parameters
-            # only: they are packed on the side stream, under the kernel that builds the first layer's input operand, instead of
-            # one launch in front of every recurrence kernel (6 launches = ~16 us off the chain of the replayed step).
-            main, side = torch.cuda.current_stream(), _side_stream(dev)
-            side.wait_stream(main)
-            packed = []
-            with torch.cuda.stream(side):
-                sst = _stream()
-                for l in range(L):
-                    w_ih, w_hh, b_ih, b_hh = (t.detach().contiguous() for t in params[4 * l:4 * l + 4])
-                    wp = torch.empty(4 * H, Kp[l], dtype=torch.bfloat16, device=dev)
-                    bias_p = torch.empty(4 * H, dtype=torch.float32, device=dev)
-                    call("b200med_lstm_pack_weights2", _raw(w_ih.data_ptr()), _raw(w_hh.data_ptr()), _raw(b_ih.data_ptr()),
-                         _raw(b_hh.data_ptr()), ins[l], inp[l], _raw(wp.data_ptr()), _raw(bias_p.data_ptr()), sst)
-                    wt = None
-                    if need_grad:
-                        wt = torch.empty(Kp[l], 4 * H, dtype=torch.bfloat16, device=dev)
-                        call("b200med_lstm_pack_weights2_bwd", _raw(w_ih.data_ptr()), _raw(w_hh.data_ptr()), ins[l], inp[l],
-                             _raw(wt.data_ptr()), _raw(0), sst)
-                    packed.append((wp, bias_p, wt))
+            # The weight operands of ALL layers (forward layout, and the transposed one of the backward) and the zeroed h_{-1}
+            # columns of the upper layers' operands depend on the parameters only: they are made on the side stream -- at the
+            # start of the step when the caller asked for it (prepack(): under the FeatureExtractor's kernels), else here.
+            if pre is None or pre["key"] != (B, W, F, L, H, bool(need_grad)):
+                pre = _prepack(params, B, W, F, need_grad, dev)
+            side, packed, upper = pre["side"], pre["packed"], pre["upper"]
+            A = [alloc(W, Bp, Kp[0], dtype=torch.bfloat16, device=dev)] + upper
+        else:
+            A = [alloc(W, Bp, Kp[l], dtype=torch.bfloat16, device=dev) for l in range(L)]
         # the reference hands the head cat(...).permute(0, 2, 1): a view of a contiguous [B, W, F] tensor -- read it as such
+        feat_bf16 = False
         if parts is not None:
             bwf = True
-            feats = x.contiguous().float()
             kt, km, ks = parts.table, parts.mean, parts.std
-            call("b200med_lstm_pack_parts", _raw(feats.data_ptr()), Ca, _raw(kt.data_ptr()), kt.shape[0], kt.shape[1],
-                 _raw(km.data_ptr() if km is not None else 0), _raw(ks.data_ptr() if ks is not None else 0),
-                 km.shape[0] if km is not None else 1, _raw(parts.starts.data_ptr()), _raw(A[0].data_ptr()), B, Bp, W, H, Kp[0], inp[0], st)
+            Cb = kt.shape[1]
+            feat_bf16 = (x.dtype == torch.bfloat16 and Ca % 2 == 0 and Cb % 2 == 0 and Ca + Cb <= 64 and inp[0] == 64
+                         and (km is None or km.shape[0] == 1))
+            if feat_bf16:      # bf16 features (TableWindows.out_bf16): copied as they are; their gradient leaves in bf16 too
+                feats = x.contiguous()
+                call("b200med_lstm_pack_parts_bf16", _raw(feats.data_ptr()), Ca, _raw(kt.data_ptr()), kt.shape[0], Cb,
+                     _raw(km.data_ptr() if km is not None else 0), _raw(ks.data_ptr() if ks is not None else 0),
+                     _raw(parts.starts.data_ptr()), _raw(A[0].data_ptr()), B, Bp, W, H, Kp[0], st)
+            else:
+                feats = x.contiguous().float()
+                call("b200med_lstm_pack_parts", _raw(feats.data_ptr()), Ca, _raw(kt.data_ptr()), kt.shape[0], kt.shape[1],
+                     _raw(km.data_ptr() if km is not None else 0), _raw(ks.data_ptr() if ks is not None else 0),
+                     km.shape[0] if km is not None else 1, _raw(parts.starts.data_ptr()), _raw(A[0].data_ptr()), B, Bp, W, H, Kp[0], inp[0], st)
         else:
             bwf = x.transpose(1, 2).is_contiguous() and not x.is_contiguous()
             xsrc = x.transpose(1, 2) if bwf else x.contiguous()
             call("b200med_lstm_pack_inputs", _raw(xsrc.data_ptr()), _raw(A[0].data_ptr()), B, Bp, F, W, H, Kp[0], inp[0], int(bwf), st)
-        for l in range(1, L):
+        for l in range(1, L if not gen2 else 0):
             call("b200med_zero_cols_bf16", _raw(A[l][0].data_ptr()), Bp, Kp[l], inp[l], H, st)
         out = torch.empty(B, H, dtype=torch.float32, device=dev)
         seed_ptr = 0 if seed_dev is None else seed_dev.data_ptr()
         Wih, Whh, Gact, Cs = [], [], [], []
         if gen2:
             torch.cuda.current_stream().wait_stream(side)
-            for tup in packed:
-                for t_ in tup:
-                    if t_ is not None:
-                        t_.record_stream(torch.cuda.current_stream())     # allocated on the side stream, read on this one
+            for t_ in [t_ for tup in packed for t_ in tup] + A[1:]:
+                if t_ is not None:
+                    t_.record_stream(torch.cuda.current_stream())     # allocated on the side stream, read on this one
         xg = None if gen2 else torch.empty(W * Bp, 4 * H, dtype=torch.float16, device=dev)
         # rows of the sigmoid gates (i, f, o) are halved for the forward kernels: sigmoid(z) = 0.5 * tanh(z / 2) + 0.5
         half = None
@@ -303,6 +353,7 @@ class LSTMRecFunction(torch.autograd.Function):
         ctx.meta = (B, Bp, F, W, L, H, Kp, ins, inp, float(drop_p), seed_dev, bwf)
         ctx.gen2 = gen2
         ctx.n_feat = None if parts is None else Ca      # with parts only the FeatureExtractor columns carry a gradient
+        ctx.feat_bf16 = feat_bf16
         return out
 
     @staticmethod
@@ -375,8 +426,12 @@ class LSTMRecFunction(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0] and ctx.n_feat is not None:
             # columns [0, Ca) of dX_0, window-major: the gradient of the FeatureExtractor output (no cat to slice back out of)
-            dx = torch.empty(B, W, ctx.n_feat, dtype=torch.float32, device=dev)
-            call("b200med_lstm_unpack_dx", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, ctx.n_feat, W, inp[0], 1, st)
+            if ctx.feat_bf16:
+                dx = torch.empty(B, W, ctx.n_feat, dtype=torch.bfloat16, device=dev)
+                call("b200med_lstm_unpack_dx_bf16", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, ctx.n_feat, W, inp[0], st)
+            else:
+                dx = torch.empty(B, W, ctx.n_feat, dtype=torch.float32, device=dev)
+                call("b200med_lstm_unpack_dx", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, ctx.n_feat, W, inp[0], 1, st)
         elif ctx.needs_input_grad[0]:
             dx = torch.empty((B, W, F) if bwf else (B, F, W), dtype=torch.float32, device=dev)
             call("b200med_lstm_unpack_dx", _raw(dX_up.data_ptr()), _raw(dx.data_ptr()), B, Bp, F, W, inp[0], int(bwf), st)

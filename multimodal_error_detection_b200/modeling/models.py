@@ -33,8 +33,11 @@ class TableWindows:
     """The FeatureExtractor's input as (device-resident fp32 table, per-column mean / std, window start rows, window length)
     instead of a gathered batch: the first layer's kernel gathers and standardises the windows itself (csrc/gather_gemm.cu)."""
 
-    def __init__(self, table, mean, std, starts, W, events=None):
+    def __init__(self, table, mean, std, starts, W, events=None, out_bf16=False):
         self.table, self.mean, self.std, self.starts, self.W, self.events = table, mean, std, starts, W, events
+        # features leave in bf16 (for a consumer that rounds them to bf16 anyway: the LSTM's first operand): same operand bits,
+        # and the gradient comes back in bf16 -- the rounding this layer's backward applies first -- without a cast pass
+        self.out_bf16 = out_bf16
 
 
 def _bf16_copies(weights):
@@ -71,7 +74,7 @@ class _MLPFunction(torch.autograd.Function):
                 N, K = weights[i].shape
                 last = i == n - 1
                 acts.append(ops.gemm_bf16(acts[-1], wb[i], M, N, K, True, True, bias=biases[i], relu=not last,
-                                          out_dtype=torch.float32 if last else torch.bfloat16))
+                                          out_dtype=torch.float32 if (last and not x.out_bf16) else torch.bfloat16))
             if not keep:
                 return acts[-1]
             ctx.save_for_backward(*acts[:-1], *wb)
@@ -115,7 +118,7 @@ class _MLPFunction(torch.autograd.Function):
                 elif need_dx:
                     g = ops.linear_bwd_data_f32(g, weights[i], relu_out=None)
             return (g if need_dx else None, None, *grads)
-        g = ops.to_bf16(dy.contiguous().float())
+        g = dy.contiguous() if dy.dtype == torch.bfloat16 else ops.to_bf16(dy.contiguous().float())
         # The bias gradients (column sums: a second pass over dY, HBM-bound) run on a side stream NEXT TO the tensor-bound
         # weight-gradient GEMMs instead of between them; `keep` holds every dY they read until the join at the end.
         main = torch.cuda.current_stream()
@@ -182,10 +185,11 @@ class FeatureExtractor(nn.Module):
                 out += [m.weight, m.bias]
         return out
 
-    def forward_table(self, table, mean, std, starts, W: int, events=None):
+    def forward_table(self, table, mean, std, starts, W: int, events=None, out_bf16: bool = False):
         """Features [B, W, output_dim] of the windows starting at rows ``starts`` of the fp32 ``table``, standardised with
-        (mean, std): the gather runs inside the first layer's kernel (bf16 mode; see ops.gather_linear_supported)."""
-        y = _MLPFunction.apply(TableWindows(table, mean, std, starts, W, events), self.precision, *self._params())
+        (mean, std): the gather runs inside the first layer's kernel (bf16 mode; see ops.gather_linear_supported).
+        out_bf16: the features leave in bf16 (see TableWindows)."""
+        y = _MLPFunction.apply(TableWindows(table, mean, std, starts, W, events, out_bf16), self.precision, *self._params())
         return y.reshape(starts.numel(), W, y.shape[-1])
 
     def forward(self, x):
@@ -268,6 +272,12 @@ class LSTM(nn.Module):
             nn.Flatten(), nn.Linear(hidden_size, 256), nn.ReLU(), nn.BatchNorm1d(256),
             nn.Linear(256, 64), nn.ReLU(), nn.BatchNorm1d(64), nn.Linear(64, n_classes))
         self.initialize_weights()
+
+    def prepack(self, B: int, W: int):
+        """Train step hook (engine.WindowTrainStep): start the weight-only preparation of the next forward on the side stream."""
+        if self.precision == "bf16" and self.training:
+            from ..lstm_stack import prepack
+            prepack(self.lstm, B, W, self.in_features, need_grad=True)
 
     def accepts_parts(self) -> bool:
         """True when forward(feats, parts=WindowParts) is served: bf16 mode on the persistent recurrence (hidden size 128)."""

@@ -813,6 +813,45 @@ def test_lstm_head_window_parts_matches_concatenated_input(stat_rows):
         assert torch.equal(a, b)
 
 
+def test_bf16_feature_handover_is_bit_identical():
+    """FeatureExtractor.forward_table(out_bf16=True) -> LSTM(parts): the features leave the last GEMM in bf16 (the rounding the
+    LSTM's operand pack applies anyway) and their gradient comes back in bf16 (the rounding the FeatureExtractor's backward
+    applies first): logits and every gradient of both modules are bit-identical with the fp32 hand-over; the bf16 route
+    launches one kernel less in the backward (no cast pass)."""
+    from multimodal_error_detection_b200 import ops
+    from multimodal_error_detection_b200.lstm_stack import WindowParts
+    from multimodal_error_detection_b200.modeling.models import LSTM, FeatureExtractor
+    if not ops.has_tcgen05():
+        pytest.skip("needs sm_100")
+    torch.manual_seed(11)
+    B, W, Cb, N = 257, 16, 26, 6000
+    fe = FeatureExtractor(2048, 32, [512, 256], precision="bf16").to(DEV)
+    model = LSTM(32 + Cb, W, 3, 128, 1).to(DEV)
+    model.precision = "bf16"
+    model.lstm.dropout = 0.0
+    model.train()
+    g = torch.Generator(device=DEV).manual_seed(7)
+    img = torch.randn(N, 2048, device=DEV, generator=g).clamp_min_(0)
+    im, isd = torch.randn(2048, device=DEV, generator=g) * 0.2, torch.rand(2048, device=DEV, generator=g) + 0.5
+    kin = torch.randn(N, Cb, device=DEV, generator=g)
+    km, ks = torch.randn(1, Cb, device=DEV, generator=g) * 0.3, torch.rand(1, Cb, device=DEV, generator=g) + 0.5
+    starts = torch.randint(0, N - W, (B,), device=DEV, generator=g, dtype=torch.int64).to(torch.int32)
+    dy = torch.randn(B, 1, device=DEV, generator=g)
+    res = []
+    for out_bf16 in (False, True):
+        for m in (fe, model):
+            m.zero_grad(set_to_none=True)
+        feats = fe.forward_table(img, im, isd, starts, W, out_bf16=out_bf16)
+        assert feats.dtype == (torch.bfloat16 if out_bf16 else torch.float32)
+        y = model(feats, parts=WindowParts(kin, km, ks, starts))
+        y.backward(dy)
+        torch.cuda.synchronize()
+        res.append((y.detach().clone(), [p.grad.clone() for m in (fe, model) for p in m.parameters()]))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b)
+
+
 def test_fused_gather_inference_keeps_no_batch_and_matches_training_forward():
     """FeatureExtractor.forward_table under torch.no_grad(): the fused kernel writes no bf16 batch (xb = NULL in the C call) and
     returns the same features, bit for bit, as the training-mode call that keeps it; ensemble.window_model_probabilities takes
