@@ -226,14 +226,15 @@ def prepack(lstm: torch.nn.LSTM, B: int, W: int, F: int, need_grad: bool = True)
     NOW, on the side stream: a train step calls it first thing, so that these ~8 small kernels run under the FeatureExtractor
     instead of between it and the recurrence.  Harmless when the forward then runs with other shapes (it redoes the work)."""
     if REC_GEN != 2 or lstm.hidden_size != 128 or lstm.bidirectional or lstm.proj_size or not lstm.bias:
-        return
+        return False
     params = []
     for l in range(lstm.num_layers):
         params += [getattr(lstm, f"weight_ih_l{l}"), getattr(lstm, f"weight_hh_l{l}"),
                    getattr(lstm, f"bias_ih_l{l}"), getattr(lstm, f"bias_hh_l{l}")]
     if (F + 63) // 64 * 64 not in (64, 128) or not params[0].is_cuda:
-        return
+        return False
     _PREPACKED[id(params[0])] = _prepack(params, B, W, F, need_grad, params[0].device)
+    return True
 
 
 class LSTMRecFunction(torch.autograd.Function):

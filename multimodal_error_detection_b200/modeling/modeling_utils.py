@@ -45,6 +45,7 @@ class _BCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels, pos_weight, out=None):
         r = ops.bce_logits(logits.detach().contiguous().float(), labels.contiguous().float(), pos_weight, want_probs=True, out=out)
+        ctx.set_materialize_grads(False)      # no zero-filled gradients for the probs / preds / counts outputs (three fills per step)
         ctx.save_for_backward(r["dlogits"])
         ctx.shape = logits.shape
         ctx.mark_non_differentiable(r["probs"], r["preds"], r["counts"])
@@ -62,6 +63,7 @@ class _CEFn(torch.autograd.Function):
         r = ops.ce_logits(logits.detach().contiguous().float(), target.to(torch.int32).contiguous(), weight, mask,
                           target_shift=target_shift, reduction=reduction, want_probs=True, pred_shift=pred_shift,
                           pred_mask_mode=pred_mask_mode, cm_classes=cm_classes)
+        ctx.set_materialize_grads(False)      # no zero-filled gradients for the probs / preds / counts outputs (three fills per step)
         ctx.save_for_backward(r["dlogits"])
         ctx.mark_non_differentiable(r["probs"], r["preds"], r["cm"])
         return r["loss"].reshape(()), r["probs"], r["preds"], r["cm"]
@@ -76,6 +78,7 @@ class _FrameCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, e):
         r = ops.ce_frame(logits.detach().contiguous().float(), e.contiguous().float())
+        ctx.set_materialize_grads(False)      # no zero-filled gradients for the probs / preds / counts outputs (three fills per step)
         ctx.save_for_backward(r["dlogits"])
         ctx.mark_non_differentiable(r["preds"], r["counts"])
         return r["loss"].reshape(()), r["preds"], r["counts"]

@@ -276,8 +276,12 @@ class LSTM(nn.Module):
     def prepack(self, B: int, W: int):
         """Train step hook (engine.WindowTrainStep): start the weight-only preparation of the next forward on the side stream."""
         if self.precision == "bf16" and self.training:
-            from ..lstm_stack import prepack
-            prepack(self.lstm, B, W, self.in_features, need_grad=True)
+            from .. import lstm_stack
+            if lstm_stack.prepack(self.lstm, B, W, self.in_features, need_grad=True) and self.lstm.dropout > 0:
+                # the dropout seed of this forward advances on the side stream too (joined before the first recurrence kernel)
+                with torch.cuda.stream(lstm_stack._side_stream(self._drop_seed.device)):
+                    self._drop_seed.add_(1)
+                self._seed_advanced = True
 
     def accepts_parts(self) -> bool:
         """True when forward(feats, parts=WindowParts) is served: bf16 mode on the persistent recurrence (hidden size 128)."""
@@ -292,7 +296,10 @@ class LSTM(nn.Module):
         from ..heads import mlp_tail
         from ..lstm_stack import lstm_last_hidden
         if self.training and self.lstm.dropout > 0:
-            self._drop_seed.add_(1)
+            if getattr(self, "_seed_advanced", False):
+                self._seed_advanced = False          # prepack() has advanced it already
+            else:
+                self._drop_seed.add_(1)
         # only h_{W-1} of the top layer is needed: the reference takes F.relu(out)[:, -1, :] (models.py:205-206)
         h = lstm_last_hidden(l, self.lstm, self.training, self._drop_seed, precision=self.precision, parts=parts)
         return mlp_tail(h, self.linear_layers, relu_in=True, training=self.training, precision=self.precision)
