@@ -117,9 +117,17 @@ __device__ __forceinline__ void tail_bn_coefs(const TailBn &bn, int K, float *c_
     }
 }
 
-__device__ __forceinline__ float tail_bn_apply(int mode, const float *c_s, int K, int c, float x) {
-    if (mode == 1) return fmaf(x, c_s[c], c_s[K + c]);
-    return (x - c_s[K + c]) * c_s[c] * c_s[2 * K + c] + c_s[3 * K + c];
+// y = BatchNorm(x) for four consecutive columns k .. k + 3 (k % 4 == 0): the coefficients by 16-byte shared loads (scalar loads at a stride of four
+// floats across the lanes were 4-way bank conflicts: 14 % of the wavefronts of the second layer's kernel)
+__device__ __forceinline__ void tail_bn_apply4(int mode, const float *c_s, int K, int k, float4 &v) {
+    const float4 a = *reinterpret_cast<const float4 *>(c_s + k), b = *reinterpret_cast<const float4 *>(c_s + K + k);
+    if (mode == 1) {
+        v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+    } else {
+        const float4 g = *reinterpret_cast<const float4 *>(c_s + 2 * K + k), h = *reinterpret_cast<const float4 *>(c_s + 3 * K + k);
+        v.x = (v.x - b.x) * a.x * g.x + h.x; v.y = (v.y - b.y) * a.y * g.y + h.y;
+        v.z = (v.z - b.z) * a.z * g.z + h.z; v.w = (v.w - b.w) * a.w * g.w + h.w;
+    }
 }
 
 // acc[i][4j + q] = sum_k in_s[row_i][k] * w_s[k][col_j + q] over one 64-row tile.  8 warps as WARPS_M x WARPS_N; a warp's
@@ -244,10 +252,7 @@ tail_fwd_hidden_kernel(const float *__restrict__ in, long long M, int K, int rel
             const int r = idx / k4n, k = (idx - r * k4n) * 4;
             float4 v = *reinterpret_cast<const float4 *>(in_s + r * ldi + k);
             if (bn.mode) {
-                v.x = tail_bn_apply(bn.mode, c_s, K, k + 0, v.x);
-                v.y = tail_bn_apply(bn.mode, c_s, K, k + 1, v.y);
-                v.z = tail_bn_apply(bn.mode, c_s, K, k + 2, v.z);
-                v.w = tail_bn_apply(bn.mode, c_s, K, k + 3, v.w);
+                tail_bn_apply4(bn.mode, c_s, K, k, v);
                 if (y) *reinterpret_cast<float4 *>(y + (r0 + r) * K + k) = v;
             } else {
                 v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
@@ -313,10 +318,7 @@ tail_fwd_out_kernel(const float *__restrict__ in, long long M, int K, int relu_i
         if (r < nvalid) {
             v = *reinterpret_cast<const float4 *>(in + (r0 + r) * K + k);
             if (bn.mode) {
-                v.x = tail_bn_apply(bn.mode, c_s, K, k + 0, v.x);
-                v.y = tail_bn_apply(bn.mode, c_s, K, k + 1, v.y);
-                v.z = tail_bn_apply(bn.mode, c_s, K, k + 2, v.z);
-                v.w = tail_bn_apply(bn.mode, c_s, K, k + 3, v.w);
+                tail_bn_apply4(bn.mode, c_s, K, k, v);
                 if (y) *reinterpret_cast<float4 *>(y + (r0 + r) * K + k) = v;
             } else if (relu_in) {
                 v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
@@ -439,9 +441,12 @@ tail_bwd_hidden_kernel(const float *__restrict__ dy, const float *__restrict__ g
                 const float4 d4 = *reinterpret_cast<const float4 *>(dy + (r0 + r) * K + k);
                 gv[0] = d4.x; gv[1] = d4.y; gv[2] = d4.z; gv[3] = d4.w;
             }
+            const float4 q0 = *reinterpret_cast<const float4 *>(c_s + k), q1 = *reinterpret_cast<const float4 *>(c_s + K + k),
+                         q2 = *reinterpret_cast<const float4 *>(c_s + 2 * K + k);
+            const float k0[4] = {q0.x, q0.y, q0.z, q0.w}, k1[4] = {q1.x, q1.y, q1.z, q1.w}, k2[4] = {q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                float v = fmaf(c_s[k + e], gv[e], -c_s[K + k + e]) - c_s[2 * K + k + e] * av[e];
+                float v = fmaf(k0[e], gv[e], -k1[e]) - k2[e] * av[e];
                 if (!(av[e] > 0.0f)) v = 0.0f;
                 o[e] = v;
             }

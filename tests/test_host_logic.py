@@ -44,6 +44,44 @@ def test_no_cpu_fallback(built_lib):
         fe(torch.zeros(2, 64))
 
 
+def test_tail_shape_rule_and_argument_errors(built_lib):
+    """Host logic of csrc/mlp_tail.cu and the multi-copy entry point, no kernel launched: which layer shapes the fused head tail
+    serves (weights + one 64-row tile within the shared memory of an SM, hidden widths 64 / 128 / 256, <= 8 output columns), the
+    slab count of the statistics partials, and the C-ABI error convention (B200MED_E_ARG = -1 with a message before any CUDA
+    call) for unsupported shapes, misaligned pointers and malformed pointer tables."""
+    import ctypes as C
+    from multimodal_error_detection_b200 import _lib
+    lib = _lib.load()
+    sup = lib.b200med_tail_supported
+    # the LSTM head: 128 -> 256 -> 64 -> C, forward and backward kinds
+    assert sup(128, 256, 0) and sup(256, 64, 0) and sup(64, 1, 2) and sup(64, 8, 2)
+    assert sup(64, 256, 3) and sup(256, 128, 1)
+    assert not sup(64, 9, 2)                      # more than 8 output columns
+    assert not sup(256, 32, 0) and not sup(32, 16, 0)      # the CNN head's narrow layers run layer by layer
+    assert not sup(96, 256, 3)                    # the last hidden width must be 64 / 128 / 256
+    assert not sup(130, 256, 0)                   # K must be a multiple of 4
+    assert not sup(512, 256, 0) and not sup(512, 256, 1)   # over the shared memory of an SM
+    assert [lib.b200med_tail_slabs(m) for m in (1, 64, 65, 8192)] == [1, 1, 2, 128]
+    null = C.c_void_p(0)
+    one = C.c_void_p(16)
+    rc = lib.b200med_tail_fwd_hidden(one, 8, 256, 0, 0, null, null, null, 1e-5, 0.1, null, null, null, null, null, null, one, null, 32,
+                                     one, null, null)
+    assert rc == -1 and b"unsupported layer shape" in lib.b200med_last_error()
+    rc = lib.b200med_tail_fwd_hidden(C.c_void_p(4), 8, 128, 0, 0, null, null, null, 1e-5, 0.1, null, null, null, null, null, null, one,
+                                     null, 256, one, null, null)
+    assert rc == -1 and b"16-byte aligned" in lib.b200med_last_error()
+    rc = lib.b200med_tail_fwd_out(one, 8, 64, 0, 1, null, null, null, 1e-5, 0.1, null, null, null, null, null, null, one, null, 1, one,
+                                  null)
+    assert rc == -1 and b"batch statistics need" in lib.b200med_last_error()
+    rc = lib.b200med_tail_bwd_out(one, 9, one, one, 8, 64, one, one, one, null)
+    assert rc == -1
+    rc = lib.b200med_multi_copy_f32(null, null, null, 3, 0, null, 0.9, 0.999, null)
+    assert rc == -1 and b"bad arguments" in lib.b200med_last_error()
+    rc = lib.b200med_multi_copy_f32(null, null, null, 0, 7, null, 0.9, 0.999, null)
+    assert rc == -1 and b"dst_dtype" in lib.b200med_last_error()
+    assert lib.b200med_multi_copy_f32(null, null, null, 0, 0, null, 0.9, 0.999, null) == 0      # nothing to do
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "multimodal_error_detection_b200")
     for dirpath, _, files in os.walk(pkg):
