@@ -112,13 +112,7 @@ class WindowTrainStep:
         prepack = getattr(self.model, "prepack", None)
         if prepack is not None:        # parameter-only operand packing of the head: on the side stream, under the first kernels
             prepack(self.B, self.W)
-        # Off the chain in front of the first big kernel: the batch's labels (read by the loss only) and the bf16 copies of the
-        # FeatureExtractor weights run on the side stream next to the lookup of the window start rows.
-        main = torch.cuda.current_stream()
-        self._side.wait_stream(main)
-        with torch.cuda.stream(self._side):
-            labels = ops.take_rows(self.label_col, self.idx2[cur], out=self.labels)
-            wb = self.fe.bf16_weights() if self.fused else None
+        labels = ops.take_rows(self.label_col, self.idx2[cur], out=self.labels)
         parts = None
         if self.fused:
             # the image stream is gathered INSIDE the first FeatureExtractor layer; the kinematics (26 columns) either inside the
@@ -132,12 +126,9 @@ class WindowTrainStep:
                                 starts, self.W)
             self._mark(1)
             im = self.ds._img_stats
-            main.wait_stream(self._side)
-            for t_ in wb:
-                t_.record_stream(main)
             # heads that build their own first operand round the features to bf16 there: they take them in bf16 right away
             feats = self.fe.forward_table(self.ds._image_table, im[0] if im else None, im[1] if im else None, starts, self.W,
-                                          events=self.gather_events, out_bf16=by_parts, wb=wb)
+                                          events=self.gather_events, out_bf16=by_parts)
             if by_parts:
                 from .lstm_stack import WindowParts
                 parts = WindowParts(self.ds._kin_table, km[0] if km else None, km[1] if km else None, starts)
@@ -148,7 +139,6 @@ class WindowTrainStep:
             if not self.prefetch:
                 self._gather(cur)
             self._mark(1)
-            main.wait_stream(self._side)
             inputs = mu.define_inputs(self.images2[cur], self.kin2[cur], self.fe, self.kw, self.device)
         self._mark(2)
         if self.phase_events is not None and inputs.requires_grad:

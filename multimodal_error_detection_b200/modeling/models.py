@@ -33,9 +33,8 @@ class TableWindows:
     """The FeatureExtractor's input as (device-resident fp32 table, per-column mean / std, window start rows, window length)
     instead of a gathered batch: the first layer's kernel gathers and standardises the windows itself (csrc/gather_gemm.cu)."""
 
-    def __init__(self, table, mean, std, starts, W, events=None, out_bf16=False, wb=None):
+    def __init__(self, table, mean, std, starts, W, events=None, out_bf16=False):
         self.table, self.mean, self.std, self.starts, self.W, self.events = table, mean, std, starts, W, events
-        self.wb = wb      # bf16 copies of the layers' weights made ahead by the caller (FeatureExtractor.bf16_weights), or None
         # features leave in bf16 (for a consumer that rounds them to bf16 anyway: the LSTM's first operand): same operand bits,
         # and the gradient comes back in bf16 -- the rounding this layer's backward applies first -- without a cast pass
         self.out_bf16 = out_bf16
@@ -64,7 +63,7 @@ class _MLPFunction(torch.autograd.Function):
             # written once (the backward's weight-gradient operand) and never read back by this layer
             if precision != "bf16" or n < 2:
                 raise ValueError("the fused gather serves the bf16 mode of an MLP with at least two layers")
-            wb = x.wb if x.wb is not None else _bf16_copies(weights)
+            wb = _bf16_copies(weights)
             # inference (no gradient will be asked for): the bf16 batch is not written at all -- 0.54 GB per 8192 windows
             keep = any(ctx.needs_input_grad)      # all False under torch.no_grad() / for frozen parameters
             xb, y1 = ops.gather_linear_bf16(x.table, x.mean, x.std, x.starts, x.W, wb[0], biases[0].detach(), relu=True, events=x.events,
@@ -186,16 +185,11 @@ class FeatureExtractor(nn.Module):
                 out += [m.weight, m.bias]
         return out
 
-    def bf16_weights(self):
-        """bf16 copies of all layers' weights in one launch: a train step makes them ahead, on a side stream, and hands them to
-        :meth:`forward_table` (``wb``)."""
-        return _bf16_copies(self._params()[0::2])
-
-    def forward_table(self, table, mean, std, starts, W: int, events=None, out_bf16: bool = False, wb=None):
+    def forward_table(self, table, mean, std, starts, W: int, events=None, out_bf16: bool = False):
         """Features [B, W, output_dim] of the windows starting at rows ``starts`` of the fp32 ``table``, standardised with
         (mean, std): the gather runs inside the first layer's kernel (bf16 mode; see ops.gather_linear_supported).
         out_bf16: the features leave in bf16 (see TableWindows)."""
-        y = _MLPFunction.apply(TableWindows(table, mean, std, starts, W, events, out_bf16, wb), self.precision, *self._params())
+        y = _MLPFunction.apply(TableWindows(table, mean, std, starts, W, events, out_bf16), self.precision, *self._params())
         return y.reshape(starts.numel(), W, y.shape[-1])
 
     def forward(self, x):
