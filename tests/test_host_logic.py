@@ -82,6 +82,37 @@ def test_tail_shape_rule_and_argument_errors(built_lib):
     assert lib.b200med_multi_copy_f32(null, null, null, 0, 0, null, 0.9, 0.999, null) == 0      # nothing to do
 
 
+def test_fused_tail_is_chosen_for_the_lstm_head_only(built_lib):
+    """heads._fused_ok (host logic): the three-kernel tail takes the LSTM head's 128 -> 256 -> 64 -> C layers (MED/modeling/
+    models.py:166-186) and leaves the CNN head's 256 -> 32 -> 16 -> C tail (models.py:100-110) to the layer-at-a-time kernels;
+    the switch B200MED_FUSED_TAIL / heads.FUSED_TAIL turns it off for A/B timing."""
+    import torch.nn as nn
+    from multimodal_error_detection_b200 import heads
+    from multimodal_error_detection_b200.modeling.models import CNN, LSTM
+
+    def tensors(seq):
+        t = []
+        for m in seq:
+            if isinstance(m, nn.Linear):
+                t += [m.weight, m.bias]
+            elif isinstance(m, nn.BatchNorm1d):
+                t += [m.weight, m.bias, m.running_mean, m.running_var, m.num_batches_tracked]
+        return t
+
+    for C_ in (1, 6):
+        lstm = LSTM(58, 16, 3, 128, C_)
+        assert heads._fused_ok(torch.zeros(8, 128), tensors(lstm.linear_layers), 2)
+    cnn = CNN(58, 10, 1)
+    assert not heads._fused_ok(torch.zeros(8, 128), tensors(cnn.linear_layers), 3)
+    lstm = LSTM(58, 16, 3, 128, 1)
+    assert not heads._fused_ok(torch.zeros(8, 96), tensors(lstm.linear_layers), 2)        # input width != the first layer's
+    prev, heads.FUSED_TAIL = heads.FUSED_TAIL, False
+    try:
+        assert not heads._fused_ok(torch.zeros(8, 128), tensors(lstm.linear_layers), 2)
+    finally:
+        heads.FUSED_TAIL = prev
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "multimodal_error_detection_b200")
     for dirpath, _, files in os.walk(pkg):
