@@ -67,8 +67,9 @@ class ClockSampler(threading.Thread):
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
-            t0 = time.perf_counter()
-            self._sample_nvml()                      # priming query: only its COST is kept (the GPU is idle right now)
+            self._sample_nvml()                      # priming queries: only the COST of the second one is kept (the first pays
+            t0 = time.perf_counter()                 # NVML's lazy set-up: ~1.4 ms on a one-GPU box, which pushed the first
+            self._sample_nvml()                      # in-region sample past the end of a 34 ms region; the GPU is idle right now)
             self.rows.clear()
             self.first_cost = time.perf_counter() - t0
         except Exception:
